@@ -1,0 +1,155 @@
+/*
+ * vct_c.h -- the C ABI of libvct_cuda.so: the drop-in boundary of the B200-native voxel cone
+ * tracing hot path (voxelize -> anisotropic mip build -> G-buffer -> cone trace).
+ *
+ * The reference (latencyhiding/voxel_cone_tracing) has no FFI/plugin system: its hot path sits
+ * behind `struct Renderer` (src/renderer.h:122-196) and is executed by OpenGL.  Every entry point
+ * below names the reference interface it replaces.  The C++ host layer (include/vct/renderer.h,
+ * texture_3d.h, device.h) and the Python/ctypes harness both sit on top of this file.
+ *
+ * Conventions: plain pointers and sizes only; every function returns 0 (VCT_OK) or a negative
+ * error code and never throws; vct_last_error() returns a thread-local message; host pointers are
+ * borrowed for the duration of the call; all work is enqueued on the device's stream and is
+ * asynchronous unless the function copies results to the host.  There is NO CPU fallback: every
+ * call fails with VCT_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef VCT_C_H
+#define VCT_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VCT_OK 0
+#define VCT_ERR_INVALID (-1) /* bad argument                                   */
+#define VCT_ERR_CUDA (-2)    /* CUDA runtime / driver error, or no usable GPU   */
+#define VCT_ERR_OOM (-3)     /* device or pinned-host allocation failed         */
+#define VCT_ERR_OVERFLOW (-4) /* fragment arena too small; see vct_voxelize     */
+
+#define VCT_MAX_POINT_LIGHTS 10 /* shader/voxelize.frag:40 */
+#define VCT_NO_TRIANGLE 0xFFFFFFFFu
+
+typedef struct vct_device vct_device_t; /* replaces the (empty) class Device, src/device.h:32-38 */
+typedef struct vct_scene vct_scene_t;   /* replaces m_models/m_draw_objs/m_materials/m_draw_queue/m_point_lights, src/renderer.h:168-191 */
+typedef struct vct_grid vct_grid_t;     /* replaces m_voxel_maps[6], src/renderer.h:180 (six GL 3-D textures) */
+typedef struct vct_target_t_ vct_target_t; /* replaces the default framebuffer + depth buffer, src/renderer.cpp:355-361 */
+typedef struct vct_tex3d vct_tex3d_t;   /* replaces one GLuint 3-D texture of src/texture_3d.h:6-10 */
+
+/* vert_data_t, src/renderer.cpp:24-35 */
+typedef struct { float pos[3]; float norm[3]; float uv[2]; } vct_vertex_t;
+/* draw_obj_t + model_t::model_matrix, src/renderer.h:57-79; model is column-major (glm::mat4) */
+typedef struct {
+  uint32_t first_index, index_count, vertex_base, material;
+  float model[16];
+} vct_draw_t;
+/* point_light_t, src/renderer.h:87-92 */
+typedef struct { float position[3]; float color[3]; float intensity; } vct_point_light_t;
+/* material_data_t, src/renderer.h:94-120 (128 bytes, std140-compatible) */
+typedef struct {
+  float ambient[4], diffuse[4], specular[4], transmittance[4];
+  float emission[3];
+  float shininess, ior, dissolve;
+  int32_t illum;
+  float roughness, metallic, sheen, clearcoat_thickness, clearcoat_roughness, anisotropy, anisotropy_rotation;
+  float pad[2];
+} vct_material_t;
+
+/* uniforms of Renderer::visualize, src/renderer.cpp:365-374, + the multi-GPU tile split */
+typedef struct {
+  int32_t enable_direct, enable_diffuse, enable_specular, enable_shadow; /* set_rendering_phases, renderer.cpp:195-201 */
+  int32_t view_voxel_dir; /* set_voxel_view_dir, renderer.cpp:203-207; >= 7 = shade normally */
+  float view_voxel_lod;
+  int32_t n_diffuse_cones; /* 9 = reference (voxel_cone_tracing.frag:153-165); 5 = normal + 4 side cones */
+  int32_t tile_rank, tile_nranks; /* this call shades 32x32 screen tiles t with t % tile_nranks == tile_rank */
+} vct_trace_params_t;
+
+typedef struct {
+  uint64_t fragments;      /* fragments folded into the grid                    */
+  uint64_t occupied;       /* voxels written                                    */
+  uint64_t items;          /* 8x8 raster work items                             */
+  uint64_t capacity;       /* fragment arena capacity                           */
+  uint64_t max_per_voxel;  /* longest per-voxel fragment list                   */
+} vct_voxel_stats_t;
+
+typedef struct {
+  uint64_t shaded_pixels;
+  uint64_t samples_diffuse, samples_shadow, samples_specular, samples_refraction;
+} vct_trace_stats_t;
+
+/* ---- device (class Device, src/device.h:32-38; GL context creation src/main.cpp:55-76) ---- */
+int vct_device_create(int cuda_ordinal, vct_device_t** out);
+int vct_device_destroy(vct_device_t* dev);
+int vct_device_sync(vct_device_t* dev);
+void* vct_device_stream(vct_device_t* dev); /* cudaStream_t, for interop (torch / NCCL) */
+const char* vct_last_error(void);
+const char* vct_version(void);
+
+/* ---- scene state (Renderer::load_model upload renderer.cpp:559-600, add_material/upload_material_data
+ *      :643-665, queue_model :209-218, queue_point_light :220-223, set_grid_size :190-193) ---- */
+int vct_scene_create(vct_device_t* dev, vct_scene_t** out);
+int vct_scene_destroy(vct_scene_t* sc);
+int vct_scene_set_geometry(vct_scene_t* sc, const vct_vertex_t* verts, uint32_t n_verts, const uint32_t* indices, uint32_t n_indices);
+int vct_scene_set_materials(vct_scene_t* sc, const vct_material_t* mats, uint32_t n_mats);
+int vct_scene_set_draws(vct_scene_t* sc, const vct_draw_t* draws, uint32_t n_draws);
+int vct_scene_set_lights(vct_scene_t* sc, const vct_point_light_t* lights, uint32_t n_lights);
+int vct_scene_set_cube_size(vct_scene_t* sc, float cube_size);
+
+/* ---- voxel grid = the six directional textures (set_grid_resolution renderer.cpp:178-188,
+ *      create_tex_3d texture_3d.cpp:3-25).  Level 0 is stored once (the reference writes the
+ *      same value to all six, voxelize.frag:159-160); levels 1.. hold 6 directions per texel. ---- */
+int vct_grid_create(vct_device_t* dev, int resolution, int levels, vct_grid_t** out);
+int vct_grid_destroy(vct_grid_t* g);
+int vct_grid_clear(vct_grid_t* g);                                        /* clear_tex_3d x6, renderer.cpp:320-321 */
+int vct_grid_upload_base(vct_grid_t* g, const uint32_t* host_rgba8);      /* R^3 texels, [z][y][x] */
+int vct_grid_download(vct_grid_t* g, int level, int dir, uint32_t* host); /* glGetTexImage equivalent; level 0 ignores dir */
+void* vct_grid_base_device_ptr(vct_grid_t* g);                            /* device pointer of level 0 (in-place NCCL allgather of z-slabs) */
+size_t vct_grid_bytes(const vct_grid_t* g);
+
+/* ---- render target: visibility + G-buffer + RGBA8 colour ---- */
+int vct_target_create(vct_device_t* dev, int width, int height, vct_target_t** out);
+int vct_target_destroy(vct_target_t* t);
+int vct_target_download_frame(vct_target_t* t, uint32_t* host_rgba8);     /* row 0 = bottom (GL window coords) */
+int vct_target_download_gbuffer(vct_target_t* t, uint32_t* tri_id, float* depth, float* world_pos3, float* normal3, uint32_t* material);
+void* vct_target_frame_device_ptr(vct_target_t* t);
+
+/* ---- the hot path ---- */
+/* Renderer::voxelize() draw part (renderer.cpp:323-347 + voxelize.vert/geom/frag): folds every
+ * fragment whose voxel z lies in [z0,z1) into level 0 with the reference's RGBA8 running average,
+ * in the canonical order (draw, triangle, pixel row, pixel column).  The grid must have been
+ * cleared.  VCT_ERR_OVERFLOW is reported by vct_voxelize_stats if the fragment arena was too small
+ * (the arena is then grown; re-run the frame). */
+int vct_voxelize(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, int z0, int z1);
+int vct_voxelize_reserve(vct_device_t* dev, uint64_t max_fragments);
+int vct_voxelize_stats(vct_device_t* dev, vct_voxel_stats_t* out);        /* synchronises */
+/* Renderer::filter() (renderer.cpp:283-314 + mipmap.comp) */
+int vct_mipmap(vct_device_t* dev, vct_grid_t* g);
+/* vertex + raster + depth part of Renderer::visualize() (renderer.cpp:355-390, voxel_cone_tracing.vert) */
+int vct_gbuffer(vct_device_t* dev, vct_scene_t* sc, const float view[16], const float proj[16], vct_target_t* t);
+/* fragment part of Renderer::visualize() (voxel_cone_tracing.frag) */
+int vct_cone_trace(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, const float view[16], const vct_trace_params_t* p, vct_target_t* t);
+/* same, instrumented: counts trace_cone loop iterations (untimed build of the kernel) */
+int vct_cone_trace_count(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, const float view[16], const vct_trace_params_t* p, vct_target_t* t,
+                         vct_trace_stats_t* out);
+/* Renderer::render() (renderer.cpp:392-405): clear + voxelize + mip + G-buffer + trace, one stream-ordered sequence */
+int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_target_t* t, const float view[16], const float proj[16],
+                     const vct_trace_params_t* p);
+
+/* per-stage device timings (CUDA events on the device stream) of the last vct_render_frame, in ms:
+ * [0] clear [1] voxelize [2] mipmap [3] gbuffer [4] trace [5] total; synchronises */
+int vct_last_frame_timings(vct_device_t* dev, float out_ms[6]);
+
+/* ---- texture_3d.h:6-10, one generic RGBA8 3-D texture with a mip chain ---- */
+int vct_tex3d_create(vct_device_t* dev, int width, int height, int depth, int levels, vct_tex3d_t** out); /* create_tex_3d */
+int vct_tex3d_destroy(vct_tex3d_t* t);                                                                     /* destroy_tex_3d */
+int vct_tex3d_clear(vct_tex3d_t* t, const float clear_color[4]);                                           /* clear_tex_3d (level 0) */
+int vct_tex3d_mip(vct_tex3d_t* t);                                                                          /* mip_tex_3d (glGenerateMipmap, 2x2x2 box) */
+int vct_tex3d_upload(vct_tex3d_t* t, int level, const uint32_t* host);
+int vct_tex3d_download(vct_tex3d_t* t, int level, uint32_t* host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCT_C_H */

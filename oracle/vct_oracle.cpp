@@ -21,7 +21,7 @@
  *      an edge is covered iff the edge is a left edge (dy < 0 for the counter-clockwise
  *      orientation in y-up window space) or a top edge (dy == 0 && dx < 0); zero-area
  *      triangles produce nothing; x/y clipping = scissor to the viewport; triangles with a
- *      vertex beyond a +-2^22 pixel guard band, or (camera pass) with any w <= 0, are dropped.
+ *      vertex beyond a +-2^21 pixel guard band, or (camera pass) with any w <= 0, are dropped.
  *   R3 interpolation: b_k = float(E_k) / float(2A) from the SNAPPED positions; affine
  *      attributes ((b0*a0 + b1*a1) + b2*a2); perspective attributes
  *      ((q0*a0 + q1*a1) + q2*a2) / ((q0 + q1) + q2) with q_k = b_k * (1 / w_k);
@@ -180,7 +180,7 @@ inline RasterTri raster_setup(const float xw[3], const float yw[3], int W, int H
   RasterTri t;
   t.valid = false;
   for (int k = 0; k < 3; k++) {
-    if (!(fabsf(xw[k]) <= 4194304.0f) || !(fabsf(yw[k]) <= 4194304.0f)) return t; /* guard band, also NaN */
+    if (!(fabsf(xw[k]) <= 2097152.0f) || !(fabsf(yw[k]) <= 2097152.0f)) return t; /* guard band, also NaN */
     t.X[k] = (int64_t)rintf(xw[k] * 256.0f);
     t.Y[k] = (int64_t)rintf(yw[k] * 256.0f);
   }

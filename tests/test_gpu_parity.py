@@ -1,0 +1,270 @@
+"""GPU parity tests: every stage of the CUDA path (through the C ABI) against the CPU oracle on
+the same inputs.  Bars (BASELINE.json north_star): voxel occupancy bit-exact, voxel colour <= 1 LSB
+(we require bit-exact: the kernels share the oracle's arithmetic rules), frame max-abs <= 2/255 and
+PSNR >= 45 dB.  Oracle = CPU restatement; llvmpipe is unavailable in this image (parity unpinned)."""
+import numpy as np
+import pytest
+
+from oracle import orc
+from voxel_cone_tracing_b200 import capi
+from voxel_cone_tracing_b200 import scene as S
+
+pytestmark = pytest.mark.gpu
+
+FRAME_MAX_ABS = 2        # of 255
+FRAME_MIN_PSNR = 45.0    # dB
+
+
+def psnr(a: np.ndarray, b: np.ndarray) -> float:
+    a = a.view(np.uint8).astype(np.float64); b = b.view(np.uint8).astype(np.float64)
+    mse = np.mean((a - b) ** 2)
+    return 99.0 if mse == 0 else 10.0 * np.log10(255.0 ** 2 / mse)
+
+
+def max_abs(a, b) -> int:
+    return int(np.max(np.abs(a.view(np.uint8).astype(np.int32) - b.view(np.uint8).astype(np.int32))))
+
+
+def assert_pyramid_equal(grid: capi.Grid, pyr: orc.Pyramid):
+    for l in range(pyr.n_levels):
+        for d in range(6):
+            got = grid.download(l, d)
+            exp = pyr.levels[d][l]
+            assert np.array_equal(got, exp), f"level {l} dir {d}: {(got != exp).sum()} texels differ"
+
+
+@pytest.fixture(scope="module")
+def dev():
+    d = capi.Device(0)
+    yield d
+    d.close()
+
+
+# --------------------------------------------------------------------------- mip
+@pytest.mark.parametrize("R,levels,density", [(128, 7, 1.0), (64, 7, 1.0), (64, 7, 0.02), (32, 6, 1.0), (16, 5, 0.5), (8, 4, 1.0), (64, 3, 1.0)])
+def test_mip_random_grid_bit_exact(dev, R, levels, density):
+    rng = np.random.default_rng(1)
+    base = rng.integers(0, 2 ** 32, (R, R, R), dtype=np.uint64).astype(np.uint32)
+    if density < 1.0:
+        base[rng.random((R, R, R)) > density] = 0
+    g = capi.Grid(dev, R, levels)
+    g.upload_base(base)
+    capi.check(dev.L.vct_mipmap(dev.h, g.h))
+    assert_pyramid_equal(g, orc.mipmap(base, levels))
+    g.close()
+
+
+def test_mip_empty_grid(dev):
+    g = capi.Grid(dev, 64, 7)
+    g.upload_base(np.full((64, 64, 64), 0xFFFFFFFF, np.uint32))
+    capi.check(dev.L.vct_mipmap(dev.h, g.h))
+    g.clear()
+    capi.check(dev.L.vct_mipmap(dev.h, g.h))
+    for l in range(7):
+        assert not g.download(l, 3).any()
+    g.close()
+
+
+# --------------------------------------------------------------------------- voxelize
+@pytest.mark.parametrize("R,suzanne", [(128, False), (128, True), (256, True), (64, False)])
+def test_voxelize_bit_exact(R, suzanne):
+    sc = S.cornell_scene(with_suzanne=suzanne)
+    exp, st = orc.voxelize(sc, R)
+    p = capi.Pipeline(sc, R, 64, 64)
+    for _ in range(2):  # twice: determinism + arena reuse
+        p.clear(); p.voxelize()
+        got = p.grid.download(0)
+        gst = p.voxel_stats()
+        assert gst.fragments == st.fragments and gst.occupied == st.occupied and gst.max_per_voxel == st.max_per_voxel
+        assert np.array_equal(got != 0, exp != 0), "occupancy differs"
+        assert np.array_equal(got, exp), f"{(got != exp).sum()} voxel colours differ"
+    p.mipmap()
+    assert_pyramid_equal(p.grid, orc.mipmap(exp, 7))
+    p.close()
+
+
+def test_voxelize_slabs_equal_full():
+    sc = S.cornell_scene(with_suzanne=True)
+    R = 128
+    p = capi.Pipeline(sc, R, 64, 64)
+    p.clear(); p.voxelize()
+    full = p.grid.download(0)
+    acc = np.zeros_like(full)
+    for k in range(4):
+        p.clear(); p.voxelize(k * R // 4, (k + 1) * R // 4)
+        part = p.grid.download(0)
+        exp, _ = orc.voxelize(sc, R, k * R // 4, (k + 1) * R // 4)
+        assert np.array_equal(part, exp)
+        acc += part
+    assert np.array_equal(acc, full)
+    p.close()
+
+
+def test_voxelize_many_fragments_per_voxel_and_wrap():
+    """Stack 40 coplanar quads in one voxel column: exercises the 16-sample count wrap (voxelize.frag:95-120)
+    and the long-list path of the resolve kernel."""
+    b = S.SceneBuilder(1.0)
+    m = S.default_material(); m["diffuse"][:3] = (0.3, 0.6, 0.9); m["emission"] = (0.1, 0.0, 0.2)
+    mid = b.add_material(m)
+    v = np.zeros(4, S.VERTEX)
+    v["pos"] = [(-0.2, -0.2, 0.1), (0.2, -0.2, 0.1), (0.2, 0.2, 0.1), (-0.2, 0.2, 0.1)]
+    v["norm"] = (0, 0, 1)
+    mesh = S.Mesh(v, np.array([0, 1, 2, 0, 2, 3] * 40, "<u4"), [(0, 240, -1)], np.zeros(0, S.MATERIAL))
+    b.add_mesh(mesh, material_override=mid)
+    b.add_light((0.0, 0.0, 0.8))
+    sc = b.build()
+    exp, st = orc.voxelize(sc, 32)
+    assert st.wrapped_voxels > 0 and st.max_per_voxel >= 80
+    p = capi.Pipeline(sc, 32, 64, 64, levels=6)
+    p.clear(); p.voxelize()
+    assert np.array_equal(p.grid.download(0), exp)
+    assert p.voxel_stats().max_per_voxel == st.max_per_voxel
+    p.close()
+
+
+def test_voxelize_arena_overflow_is_reported():
+    sc = S.cornell_scene()
+    p = capi.Pipeline(sc, 128, 64, 64)
+    capi.check(p.dev.L.vct_voxelize_reserve(p.dev.h, 1024))
+    # a fresh device starts with the default arena; force a tiny one through a new device
+    p.close()
+    dev = capi.Device(0)
+    capi.check(dev.L.vct_voxelize_reserve(dev.h, 1000))
+    scn = capi.DeviceScene(dev, sc); g = capi.Grid(dev, 128, 7)
+    capi.check(dev.L.vct_voxelize(dev.h, scn.h, g.h, 0, 128))
+    st = capi.VoxelStats()
+    import ctypes
+    assert dev.L.vct_voxelize_stats(dev.h, ctypes.byref(st)) == -4        # VCT_ERR_OVERFLOW, arena grown
+    g.clear()
+    capi.check(dev.L.vct_voxelize(dev.h, scn.h, g.h, 0, 128))
+    capi.check(dev.L.vct_voxelize_stats(dev.h, ctypes.byref(st)))
+    exp, _ = orc.voxelize(sc, 128)
+    assert np.array_equal(g.download(0), exp)
+    g.close(); scn.close(); dev.close()
+
+
+# --------------------------------------------------------------------------- G-buffer
+@pytest.mark.parametrize("W,H,suzanne", [(512, 512, False), (400, 300, True), (333, 217, True)])
+def test_gbuffer_matches_oracle(W, H, suzanne):
+    sc = S.cornell_scene(with_suzanne=suzanne)
+    view, proj = S.reference_camera(W / H)
+    exp = orc.gbuffer(sc, view, proj, W, H)
+    p = capi.Pipeline(sc, 32, W, H, levels=6)
+    p.gbuffer(view, proj)
+    got = p.target.gbuffer()
+    assert np.array_equal(got["tri_id"], exp.tri_id)
+    hit = exp.tri_id != 0xFFFFFFFF
+    assert hit.mean() > 0.3
+    assert np.array_equal(got["depth"][hit], exp.depth[hit])
+    assert np.array_equal(got["material"][hit], exp.material[hit])
+    assert np.array_equal(got["world_pos"][hit], exp.world_pos[hit])
+    assert np.array_equal(got["normal"][hit], exp.normal[hit])
+    p.close()
+
+
+# --------------------------------------------------------------------------- full frame
+def _frame_pair(sc, R, W, H, params_kw=None, levels=7):
+    params_kw = params_kw or {}
+    view, proj = S.reference_camera(W / H)
+    ref = orc.render_frame(sc, view, proj, R, W, H, orc.default_params(**params_kw), levels)
+    p = capi.Pipeline(sc, R, W, H, levels)
+    p.render_frame(view, proj, capi.default_params(**params_kw))
+    got = p.target.frame()
+    cnt = p.trace_count(view, capi.default_params(**params_kw))
+    p.close()
+    return got, ref, cnt
+
+
+def _check_frame(got, ref):
+    exp = ref["frame"]
+    assert max_abs(got, exp) <= FRAME_MAX_ABS, f"max abs {max_abs(got, exp)}/255"
+    assert psnr(got, exp) >= FRAME_MIN_PSNR, f"PSNR {psnr(got, exp):.2f} dB"
+
+
+def test_frame_config1_cornell_128_512():
+    """BASELINE config 1: CornellBox-Glossy, 128^3, 512x512, 9 diffuse + 1 specular + 1 shadow cone."""
+    got, ref, cnt = _frame_pair(S.cornell_scene(), 128, 512, 512)
+    _check_frame(got, ref)
+    ts = ref["trace_stats"]
+    assert cnt.shaded_pixels == ts.shaded_pixels
+    for k in ("samples_diffuse", "samples_shadow", "samples_specular", "samples_refraction"):
+        a, b = getattr(cnt, k), getattr(ts, k)
+        assert abs(a - b) <= 1e-2 * max(b, 1), (k, a, b)   # alpha ~ 1 rounding may flip a loop exit by one (negligible) sample
+
+
+def test_frame_with_suzanne_refraction():
+    got, ref, cnt = _frame_pair(S.cornell_scene(with_suzanne=True), 128, 400, 300)
+    _check_frame(got, ref)
+    assert cnt.samples_refraction > 0
+
+
+@pytest.mark.parametrize("kw", [dict(n_diffuse_cones=5), dict(enable_shadow=0), dict(enable_diffuse=0, enable_specular=0),
+                                dict(enable_direct=0), dict(view_voxel_dir=1, view_voxel_lod=1.5), dict(view_voxel_dir=4, view_voxel_lod=0.0)])
+def test_frame_variants(kw):
+    got, ref, _ = _frame_pair(S.cornell_scene(with_suzanne=True), 64, 256, 192, kw)
+    _check_frame(got, ref)
+
+
+def test_frame_config2_cornell_256_1080p():
+    """BASELINE config 2 (the benchmark workload) at full size."""
+    got, ref, cnt = _frame_pair(S.cornell_scene(), 256, 1920, 1080)
+    _check_frame(got, ref)
+    assert abs(cnt.samples - ref["trace_stats"].samples) <= 1e-2 * ref["trace_stats"].samples
+
+
+def test_tile_split_equals_full_frame():
+    sc = S.cornell_scene(with_suzanne=True)
+    R, W, H = 64, 320, 200
+    view, proj = S.reference_camera(W / H)
+    p = capi.Pipeline(sc, R, W, H)
+    p.render_frame(view, proj)
+    full = p.target.frame().copy()
+    parts = []
+    for r in range(3):
+        p.trace(view, capi.default_params(tile_rank=r, tile_nranks=3))
+        parts.append(p.target.frame().copy())
+    ty, tx = np.meshgrid(np.arange(H) // 32, np.arange(W) // 32, indexing="ij")
+    owner = (ty * ((W + 31) // 32) + tx) % 3
+    merged = np.zeros_like(full)
+    for r in range(3):
+        # a rank only writes its own tiles; the rest of its buffer still holds the previous content
+        merged[owner == r] = parts[r][owner == r]
+    assert np.array_equal(merged, full)
+    p.close()
+
+
+def test_render_is_deterministic():
+    sc = S.cornell_scene(with_suzanne=True)
+    view, proj = S.reference_camera(4 / 3)
+    p = capi.Pipeline(sc, 128, 400, 300)
+    frames = []
+    for _ in range(3):
+        p.render_frame(view, proj)
+        frames.append((p.target.frame().copy(), p.grid.download(0), p.grid.download(3, 2)))
+    for f in frames[1:]:
+        assert all(np.array_equal(a, b) for a, b in zip(f, frames[0]))
+    p.close()
+
+
+# --------------------------------------------------------------------------- texture_3d.h surface
+def test_tex3d_clear_and_box_mip(dev):
+    import ctypes
+    h = ctypes.c_void_p()
+    capi.check(dev.L.vct_tex3d_create(dev.h, 16, 8, 4, 3, ctypes.byref(h)))
+    col = (ctypes.c_float * 4)(1.0, 0.5, 0.0, 1.0)
+    capi.check(dev.L.vct_tex3d_clear(h, col))
+    capi.check(dev.L.vct_tex3d_mip(h))
+    out = np.zeros((1, 2, 4), np.uint32)
+    capi.check(dev.L.vct_tex3d_download(h, 2, out.ctypes.data))
+    assert np.all(out == 0xFF0080FF)
+    rng = np.random.default_rng(3)
+    src = rng.integers(0, 2 ** 32, (4, 8, 16), dtype=np.uint64).astype(np.uint32)
+    capi.check(dev.L.vct_tex3d_upload(h, 0, src.ctypes.data))
+    capi.check(dev.L.vct_tex3d_mip(h))
+    l1 = np.zeros((2, 4, 8), np.uint32)
+    capi.check(dev.L.vct_tex3d_download(h, 1, l1.ctypes.data))
+    b = src.view(np.uint8).reshape(4, 8, 16, 4).astype(np.uint32)
+    exp = (b.reshape(2, 2, 4, 2, 8, 2, 4).sum(axis=(1, 3, 5)) + 4) // 8
+    assert np.array_equal(l1.view(np.uint8).reshape(2, 4, 8, 4), exp.astype(np.uint8))
+    assert dev.L.vct_tex3d_create(dev.h, 16, 8, 4, 9, ctypes.byref(ctypes.c_void_p())) == -1   # too many levels (glTexStorage3D rule)
+    capi.check(dev.L.vct_tex3d_destroy(h))

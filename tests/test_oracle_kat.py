@@ -1,0 +1,157 @@
+"""Known-answer tests pinning the CPU oracle.  The vectors were derived by hand
+from the shader text (shader/voxelize.frag:66-120, voxelize.geom:25-55, mipmap.comp:40-98,
+voxel_cone_tracing.frag:88-119, src/camera.h, glm::perspective); the reference itself ships no
+tests or golden data, so these are the oracle's only pins ("parity unpinned")."""
+import math
+
+import numpy as np
+import pytest
+
+from oracle import orc
+from voxel_cone_tracing_b200 import scene as S
+
+
+def _fold_seq(vals):
+    cur, out = 0, []
+    for v in vals:
+        cur = orc.fold(cur, v)
+        out.append("%08X" % cur)
+    return out
+
+
+def test_rgba8_avg_white_18():
+    exp = ["FEFEFEFF", "FEFEFFFE", "FEFEFFFF", "FEFFFEFE", "FEFFFEFF", "FEFFFFFE", "FEFFFFFF", "FFFEFEFE", "FFFEFEFF",
+           "FFFEFFFE", "FFFEFFFF", "FFFFFEFE", "FFFFFEFF", "FFFFFFFE", "FFFFFFFF", "FEFEFEFE", "00000001", "80808180"]
+    assert _fold_seq([[1, 1, 1, 1]] * 18) == exp
+
+
+def test_rgba8_avg_colour_18():
+    got = _fold_seq([[0.2, 0.4, 0.6, 1.0]] * 18)
+    assert got[:4] == ["FE986633", "FE986732", "FE986733", "FE996632"]
+    assert got[14:] == ["FF996733", "FE986632", "00986635", "80986734"]
+
+
+def test_rgba8_avg_rgb_sequence():
+    assert _fold_seq([[1, 0, 0, 1], [0, 1, 0, 1], [0, 0, 1, 1]]) == ["FE0000FF", "FE008180", "FE545757"]
+
+
+def test_rgba8_count_wraps_at_16():
+    cur = 0
+    for i in range(1, 40):
+        cur = orc.fold(cur, [0.5, 0.5, 0.5, 1.0])
+        n = (cur & 1) | ((cur >> 7) & 2) | ((cur >> 14) & 4) | ((cur >> 21) & 8)
+        # a stored word that wrapped to count 0 with colour 0 would restart; colour 0.5 never does
+        assert n == i % 16 or cur == 0
+
+
+@pytest.mark.parametrize("normal,axis", [((0, 0, 1), 0), ((1, 0, 0), 1), ((0, 1, 0), 2), ((1, 1, 0), 2), ((1, 0, 1), 2), ((0, 1, 1), 2)])
+def test_axis_selection(normal, axis):
+    n = np.array(normal, np.float64)
+    # two edges spanning the plane orthogonal to n, |cross| proportional to n exactly (integers)
+    a = np.array([1.0, 0, 0]) if abs(n[0]) < 1 or n[1] or n[2] else np.array([0, 1.0, 0])
+    e1 = np.cross(n, [0.0, 0.0, 1.0]) if np.any(np.cross(n, [0.0, 0.0, 1.0])) else np.cross(n, [0.0, 1.0, 0.0])
+    e2 = np.cross(n, e1)
+    p0 = np.zeros(3)
+    assert orc.select_axis(p0, p0 + e1, p0 + e2) == axis
+
+
+def test_camera_matrices():
+    proj = orc.perspective(45.0, 4.0 / 3.0, 0.1, 100.0)
+    assert abs(proj[0] - 1.34444) < 1e-4 and abs(proj[5] - 1.79259) < 1e-4      # tan(22.5 rad) = 0.557852
+    assert proj[11] == -1.0
+    front = orc.camera_front(0.0, -90.0)
+    eye = np.array([0, 0.9, 3], np.float32)
+    view = orc.look_at(eye, eye + front, [0, 1, 0])
+    assert np.allclose(view[12:15], [0, -0.9, -3], atol=1e-5)                   # glm::column(view, 3), renderer.cpp:279
+    v2, p2 = S.reference_camera(4.0 / 3.0)
+    assert np.allclose(v2, view, atol=1e-6) and np.allclose(p2, proj, atol=1e-6)
+
+
+def test_specular_aperture():
+    for ns in (10.0, 32.0, 80.0, 1000.0):
+        a = math.tan(1.57079 * math.sqrt(2.0 / (ns + 2.0)))
+        assert abs(orc.specular_aperture(ns) - min(max(a, 0.0174533), 3.14159265)) < 1e-4 * max(1, a)
+
+
+def _single_child_pyramid(R=8, levels=4, pos=(0, 0, 0), word=0xFEFEFEFF):
+    base = np.zeros((R, R, R), np.uint32)
+    base[pos[2], pos[1], pos[0]] = word
+    return orc.mipmap(base, levels)
+
+
+def test_mip_single_child_quarter():
+    p = _single_child_pyramid()
+    for d in range(6):
+        w = int(p.levels[d][1][0, 0, 0])
+        r, g, b, a = w & 255, (w >> 8) & 255, (w >> 16) & 255, w >> 24
+        assert r == 64                     # 255/4 = 63.75 -> 64
+        assert g in (63, 64) and b in (63, 64) and a in (63, 64)   # 254/4 = 63.5: tie
+        assert int((p.levels[d][1] != 0).sum()) == 1
+
+
+def test_mip_two_opaque_children_along_x():
+    R = 8
+    base = np.zeros((R, R, R), np.uint32)
+    base[0, 0, 0] = 0xFF0000FF  # x = 0: red, alpha 1
+    base[0, 0, 1] = 0xFF00FF00  # x = 1: green, alpha 1
+    p = orc.mipmap(base, 3)
+    neg_x = int(p.levels[0][1][0, 0, 0])  # cone travelling -x meets x=1 first: green in front hides red
+    pos_x = int(p.levels[1][1][0, 0, 0])  # cone travelling +x meets x=0 first
+    assert (neg_x & 0xFF, (neg_x >> 8) & 0xFF) == (0, 64)
+    assert (pos_x & 0xFF, (pos_x >> 8) & 0xFF) == (64, 0)
+    assert neg_x >> 24 == 64 and pos_x >> 24 == 64
+    # orthogonal directions see both side by side
+    for d in (2, 3, 4, 5):
+        w = int(p.levels[d][1][0, 0, 0])
+        assert (w & 0xFF, (w >> 8) & 0xFF, w >> 24) == (64, 64, 128)
+
+
+def test_cone_step_sequence_r128():
+    """voxel_cone_tracing.frag:95-116: dist*R = 3, 4, 5.116, 6.543, ... 18 iterations to sqrt(3) at R=128."""
+    R = 128
+    base = np.zeros((R, R, R), np.uint32)
+    p = orc.mipmap(base, 7)
+    _, n = orc.trace_cone(p, [0.5, 0.5, 0.5], [1, 0, 0], 0.55785173935, 1.73205080757)
+    # reproduce the recurrence in float32
+    dist, it = np.float32(3.0) * (np.float32(1.0) / np.float32(R)), 0
+    seq = []
+    while dist < np.float32(1.73205080757):
+        seq.append(float(dist) * R)
+        diam = dist * np.float32(0.55785173935)
+        dist = dist + max(diam / np.float32(2), np.float32(1.0) / np.float32(R))
+        it += 1
+    assert n == it == 18
+    assert abs(seq[1] - 4.0) < 1e-4 and abs(seq[2] - 5.1157) < 1e-3 and abs(seq[3] - 6.5426) < 1e-3
+
+
+def test_texture_lod_border_and_levels():
+    R = 8
+    base = np.full((R, R, R), 0xFFFFFFFF, np.uint32)
+    p = orc.mipmap(base, 4)
+    c = orc.texture_lod(p, 0, [0.5, 0.5, 0.5], 0.0)
+    assert np.allclose(c, 1.0)
+    edge = orc.texture_lod(p, 0, [0.0, 0.5, 0.5], 0.0)       # half of the footprint is border (0)
+    assert np.allclose(edge, 0.5, atol=1e-6)
+    out = orc.texture_lod(p, 0, [-0.2, 0.5, 0.5], 0.0)
+    assert np.allclose(out, 0.0)
+    top = orc.texture_lod(p, 3, [0.5, 0.5, 0.5], 99.0)       # lod clamped to levels-1
+    assert np.allclose(top, orc.texture_lod(p, 3, [0.5, 0.5, 0.5], 3.0))
+
+
+def test_reference_scene_statistics():
+    """Sanity targets of SURVEY.md App. C (float64 emulation of V1-V4): box + Suzanne at 128^3."""
+    sc = S.cornell_scene(with_suzanne=True)
+    assert sc.n_triangles == 2080
+    base, st = orc.voxelize(sc, 128)
+    assert (st.fragments, st.occupied, st.tris_no_frag, st.max_per_voxel) == (41167, 10517, 425, 11)
+    assert st.wrapped_voxels == 0 and st.fragments_oob == 0
+    assert int((base != 0).sum()) == 10517
+
+
+def test_slab_union_equals_full():
+    sc = S.cornell_scene()
+    full, _ = orc.voxelize(sc, 64)
+    lo, _ = orc.voxelize(sc, 64, 0, 32)
+    hi, _ = orc.voxelize(sc, 64, 32, 64)
+    assert not np.any(lo[32:]) and not np.any(hi[:32])
+    assert np.array_equal(lo + hi, full)

@@ -1,0 +1,419 @@
+// capi.cu -- the extern "C" layer of include/vct/vct_c.h: object lifetime, uploads/downloads and
+// the stream-ordered frame sequence.  No compute lives here; there is no CPU fallback anywhere.
+#include <stdarg.h>
+
+#include <new>
+
+#include "vct_internal.cuh"
+
+namespace vct {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+
+// R9: mat3(transpose(inverse(model))) for an affine model matrix = cofactor / det, in double
+static void normal_matrix(const float* m, float* nm) {
+  double a00 = m[0], a10 = m[1], a20 = m[2];
+  double a01 = m[4], a11 = m[5], a21 = m[6];
+  double a02 = m[8], a12 = m[9], a22 = m[10];
+  volatile double c00 = a11 * a22 - a12 * a21, c01 = a12 * a20 - a10 * a22, c02 = a10 * a21 - a11 * a20;
+  volatile double c10 = a02 * a21 - a01 * a22, c11 = a00 * a22 - a02 * a20, c12 = a01 * a20 - a00 * a21;
+  volatile double c20 = a01 * a12 - a02 * a11, c21 = a02 * a10 - a00 * a12, c22 = a00 * a11 - a01 * a10;
+  volatile double d0 = a00 * c00, d1 = a01 * c01, d2 = a02 * c02;
+  double det = (d0 + d1) + d2;
+  nm[0] = (float)(c00 / det); nm[1] = (float)(c10 / det); nm[2] = (float)(c20 / det);
+  nm[3] = (float)(c01 / det); nm[4] = (float)(c11 / det); nm[5] = (float)(c21 / det);
+  nm[6] = (float)(c02 / det); nm[7] = (float)(c12 / det); nm[8] = (float)(c22 / det);
+}
+
+template <class T>
+static int ensure_capacity(T** p, size_t* cap, size_t n) {
+  if (n <= *cap) return VCT_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr; *cap = 0;
+  size_t want = n + n / 4 + 64;
+  VCT_CUDA(cudaMalloc((void**)p, want * sizeof(T)));
+  *cap = want;
+  return VCT_OK;
+}
+
+static int stage_upload(vct_scene* sc, void* dst, const void* src, size_t bytes) {
+  if (bytes == 0) return VCT_OK;
+  if (bytes > sc->stage_bytes) {
+    // the previous staging buffer may still be in flight
+    VCT_CUDA(cudaStreamSynchronize(sc->dev->stream));
+    if (sc->stage) cudaFreeHost(sc->stage);
+    sc->stage = nullptr; sc->stage_bytes = 0;
+    size_t want = bytes + bytes / 2 + 4096;
+    VCT_CUDA(cudaMallocHost(&sc->stage, want));
+    sc->stage_bytes = want;
+  } else {
+    VCT_CUDA(cudaStreamSynchronize(sc->dev->stream));  // staging buffer reuse; uploads are rare and small
+  }
+  memcpy(sc->stage, src, bytes);
+  VCT_CUDA(cudaMemcpyAsync(dst, sc->stage, bytes, cudaMemcpyHostToDevice, sc->dev->stream));
+  return VCT_OK;
+}
+
+}  // namespace vct
+
+using namespace vct;
+
+extern "C" {
+
+const char* vct_last_error(void) { return g_err; }
+const char* vct_version(void) { return "vct-b200 0.1 (sm_100a)"; }
+
+// ------------------------------------------------------------------ device
+int vct_device_create(int ordinal, vct_device_t** out) {
+  VCT_REQUIRE(out != nullptr, "out is null");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    set_error("no CUDA device available (%s); this library has no CPU fallback", e != cudaSuccess ? cudaGetErrorString(e) : "count = 0");
+    return VCT_ERR_CUDA;
+  }
+  VCT_REQUIRE(ordinal >= 0 && ordinal < n, "bad device ordinal");
+  VCT_CUDA(cudaSetDevice(ordinal));
+  vct_device* d = new (std::nothrow) vct_device();
+  if (!d) { set_error("out of host memory"); return VCT_ERR_OOM; }
+  d->ordinal = ordinal;
+  VCT_CUDA(cudaGetDeviceProperties(&d->prop, ordinal));
+  if (d->prop.major < 10) {
+    set_error("device %d is sm_%d%d; this library is built for sm_100a only", ordinal, d->prop.major, d->prop.minor);
+    delete d;
+    return VCT_ERR_CUDA;
+  }
+  VCT_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  VCT_CUDA(cudaMalloc(&d->counters, CNT_TOTAL * sizeof(uint32_t)));
+  VCT_CUDA(cudaMemset(d->counters, 0, CNT_TOTAL * sizeof(uint32_t)));
+  VCT_CUDA(cudaMallocHost(&d->counters_host, CNT_TOTAL * sizeof(uint32_t)));
+  for (int i = 0; i < 8; i++) VCT_CUDA(cudaEventCreate(&d->ev[i]));
+  *out = d;
+  return VCT_OK;
+}
+
+int vct_device_destroy(vct_device_t* d) {
+  if (!d) return VCT_OK;
+  cudaSetDevice(d->ordinal);
+  cudaStreamSynchronize(d->stream);
+  cudaFree(d->frags); cudaFree(d->occupied); cudaFree(d->tri_recs); cudaFree(d->item_local); cudaFree(d->item_block);
+  cudaFree(d->counters); cudaFreeHost(d->counters_host);
+  for (int i = 0; i < 8; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
+  cudaStreamDestroy(d->stream);
+  delete d;
+  return VCT_OK;
+}
+
+int vct_device_sync(vct_device_t* d) {
+  VCT_REQUIRE(d, "device is null");
+  VCT_CUDA(cudaStreamSynchronize(d->stream));
+  return VCT_OK;
+}
+
+void* vct_device_stream(vct_device_t* d) { return d ? (void*)d->stream : nullptr; }
+
+// ------------------------------------------------------------------ scene
+int vct_scene_create(vct_device_t* dev, vct_scene_t** out) {
+  VCT_REQUIRE(dev && out, "null argument");
+  vct_scene* s = new (std::nothrow) vct_scene();
+  if (!s) { set_error("out of host memory"); return VCT_ERR_OOM; }
+  s->dev = dev;
+  *out = s;
+  return VCT_OK;
+}
+
+int vct_scene_destroy(vct_scene_t* s) {
+  if (!s) return VCT_OK;
+  cudaStreamSynchronize(s->dev->stream);
+  cudaFree(s->verts); cudaFree(s->indices); cudaFree(s->mats); cudaFree(s->draws);
+  if (s->stage) cudaFreeHost(s->stage);
+  delete s;
+  return VCT_OK;
+}
+
+int vct_scene_set_geometry(vct_scene_t* s, const vct_vertex_t* verts, uint32_t n_verts, const uint32_t* indices, uint32_t n_indices) {
+  VCT_REQUIRE(s, "scene is null");
+  VCT_REQUIRE((verts || !n_verts) && (indices || !n_indices), "null geometry");
+  int rc;
+  if ((rc = ensure_capacity(&s->verts, &s->verts_cap, n_verts))) return rc;
+  if ((rc = ensure_capacity(&s->indices, &s->indices_cap, n_indices))) return rc;
+  if ((rc = stage_upload(s, s->verts, verts, (size_t)n_verts * sizeof(vct_vertex_t)))) return rc;
+  if ((rc = stage_upload(s, s->indices, indices, (size_t)n_indices * sizeof(uint32_t)))) return rc;
+  s->n_verts = n_verts; s->n_indices = n_indices;
+  return VCT_OK;
+}
+
+int vct_scene_set_materials(vct_scene_t* s, const vct_material_t* mats, uint32_t n) {
+  VCT_REQUIRE(s && (mats || !n), "null argument");
+  int rc;
+  if ((rc = ensure_capacity(&s->mats, &s->mats_cap, n))) return rc;
+  if ((rc = stage_upload(s, s->mats, mats, (size_t)n * sizeof(vct_material_t)))) return rc;
+  s->n_mats = n;
+  return VCT_OK;
+}
+
+int vct_scene_set_draws(vct_scene_t* s, const vct_draw_t* draws, uint32_t n) {
+  VCT_REQUIRE(s && (draws || !n), "null argument");
+  std::vector<DrawRec> recs(n);
+  uint32_t tri = 0;
+  for (uint32_t i = 0; i < n; i++) {
+    const vct_draw_t& d = draws[i];
+    VCT_REQUIRE((uint64_t)d.first_index + d.index_count <= s->n_indices, "draw range outside the index buffer");
+    VCT_REQUIRE(d.material < s->n_mats, "draw references an unknown material");
+    DrawRec& r = recs[i];
+    memset(&r, 0, sizeof r);
+    r.first_index = d.first_index; r.index_count = d.index_count; r.vertex_base = d.vertex_base; r.material = d.material;
+    memcpy(r.model, d.model, sizeof r.model);
+    normal_matrix(d.model, r.nmat);
+    r.tri_base = tri;
+    tri += d.index_count / 3;
+  }
+  int rc;
+  if ((rc = ensure_capacity(&s->draws, &s->draws_cap, n))) return rc;
+  if ((rc = stage_upload(s, s->draws, recs.data(), (size_t)n * sizeof(DrawRec)))) return rc;
+  s->n_draws = n;
+  s->n_tris = tri;
+  return VCT_OK;
+}
+
+int vct_scene_set_lights(vct_scene_t* s, const vct_point_light_t* lights, uint32_t n) {
+  VCT_REQUIRE(s && (lights || !n), "null argument");
+  uint32_t m = n < VCT_MAX_POINT_LIGHTS ? n : VCT_MAX_POINT_LIGHTS;  // min(point_light_count, MAX_POINT_LIGHTS), voxelize.frag:128
+  memset(&s->lights, 0, sizeof s->lights);
+  for (uint32_t i = 0; i < m; i++) s->lights.l[i] = lights[i];
+  s->lights.n = (int32_t)m;
+  return VCT_OK;
+}
+
+int vct_scene_set_cube_size(vct_scene_t* s, float cube_size) {
+  VCT_REQUIRE(s, "scene is null");
+  s->cube_size = cube_size;
+  return VCT_OK;
+}
+
+// ------------------------------------------------------------------ grid
+int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) {
+  VCT_REQUIRE(dev && out, "null argument");
+  VCT_REQUIRE(R >= 2 && R <= 2048 && (R & (R - 1)) == 0, "resolution must be a power of two in [2, 2048]");
+  VCT_REQUIRE(levels >= 1 && levels <= VCT_MAX_LEVELS && (R >> (levels - 1)) >= 1, "levels must satisfy 1 <= levels <= log2(R)+1");
+  vct_grid* g = new (std::nothrow) vct_grid();
+  if (!g) { set_error("out of host memory"); return VCT_ERR_OOM; }
+  g->dev = dev; g->R = R; g->levels = levels;
+  size_t n0 = (size_t)R * R * R;
+  cudaError_t e = cudaMalloc(&g->base, n0 * 4);
+  g->bytes = n0 * 4;
+  for (int l = 1; l < levels && e == cudaSuccess; l++) {
+    size_t n = (size_t)(R >> l) * (R >> l) * (R >> l);
+    e = cudaMalloc(&g->lvl[l], n * 24);
+    g->bytes += n * 24;
+  }
+  if (e != cudaSuccess) {
+    set_error("grid allocation failed: %s", cudaGetErrorString(e));
+    vct_grid_destroy(g);
+    return VCT_ERR_OOM;
+  }
+  *out = g;
+  return vct_grid_clear(g);
+}
+
+int vct_grid_destroy(vct_grid_t* g) {
+  if (!g) return VCT_OK;
+  cudaStreamSynchronize(g->dev->stream);
+  cudaFree(g->base);
+  for (int l = 0; l < VCT_MAX_LEVELS; l++) cudaFree(g->lvl[l]);
+  delete g;
+  return VCT_OK;
+}
+
+int vct_grid_clear(vct_grid_t* g) {
+  VCT_REQUIRE(g, "grid is null");
+  VCT_CUDA(cudaMemsetAsync(g->base, 0, (size_t)g->R * g->R * g->R * 4, g->dev->stream));
+  return VCT_OK;
+}
+
+int vct_grid_upload_base(vct_grid_t* g, const uint32_t* host) {
+  VCT_REQUIRE(g && host, "null argument");
+  VCT_CUDA(cudaMemcpyAsync(g->base, host, (size_t)g->R * g->R * g->R * 4, cudaMemcpyHostToDevice, g->dev->stream));
+  VCT_CUDA(cudaStreamSynchronize(g->dev->stream));
+  return VCT_OK;
+}
+
+int vct_grid_download(vct_grid_t* g, int level, int dir, uint32_t* host) {
+  VCT_REQUIRE(g && host, "null argument");
+  VCT_REQUIRE(level >= 0 && level < g->levels, "bad level");
+  VCT_REQUIRE(dir >= 0 && dir < 6, "bad direction");
+  cudaStream_t s = g->dev->stream;
+  size_t N = (size_t)(g->R >> level), n = N * N * N;
+  if (level == 0) {
+    VCT_CUDA(cudaMemcpyAsync(host, g->base, n * 4, cudaMemcpyDeviceToHost, s));
+  } else {
+    // strided gather of one direction out of the 6-word records
+    VCT_CUDA(cudaMemcpy2DAsync(host, 4, g->lvl[level] + dir, 24, 4, n, cudaMemcpyDeviceToHost, s));
+  }
+  VCT_CUDA(cudaStreamSynchronize(s));
+  return VCT_OK;
+}
+
+void* vct_grid_base_device_ptr(vct_grid_t* g) { return g ? (void*)g->base : nullptr; }
+size_t vct_grid_bytes(const vct_grid_t* g) { return g ? g->bytes : 0; }
+
+// ------------------------------------------------------------------ target
+int vct_target_create(vct_device_t* dev, int W, int H, vct_target_t** out) {
+  VCT_REQUIRE(dev && out, "null argument");
+  VCT_REQUIRE(W > 0 && H > 0 && W <= 16384 && H <= 16384, "bad frame size");
+  vct_target_t_* t = new (std::nothrow) vct_target_t_();
+  if (!t) { set_error("out of host memory"); return VCT_ERR_OOM; }
+  t->dev = dev; t->W = W; t->H = H;
+  size_t n = (size_t)W * H;
+  cudaError_t e = cudaMalloc(&t->vis, n * 8);
+  if (e == cudaSuccess) e = cudaMalloc(&t->world_pos, n * 12);
+  if (e == cudaSuccess) e = cudaMalloc(&t->normal, n * 12);
+  if (e == cudaSuccess) e = cudaMalloc(&t->material, n * 4);
+  if (e == cudaSuccess) e = cudaMalloc(&t->frame, n * 4);
+  if (e != cudaSuccess) {
+    set_error("target allocation failed: %s", cudaGetErrorString(e));
+    vct_target_destroy(t);
+    return VCT_ERR_OOM;
+  }
+  int rc = launch_fill_u32(dev->stream, t->material, n, VCT_NO_TRIANGLE);
+  if (rc) return rc;
+  *out = t;
+  return VCT_OK;
+}
+
+int vct_target_destroy(vct_target_t* t) {
+  if (!t) return VCT_OK;
+  cudaStreamSynchronize(t->dev->stream);
+  cudaFree(t->vis); cudaFree(t->world_pos); cudaFree(t->normal); cudaFree(t->material); cudaFree(t->frame);
+  delete t;
+  return VCT_OK;
+}
+
+int vct_target_download_frame(vct_target_t* t, uint32_t* host) {
+  VCT_REQUIRE(t && host, "null argument");
+  VCT_CUDA(cudaMemcpyAsync(host, t->frame, (size_t)t->W * t->H * 4, cudaMemcpyDeviceToHost, t->dev->stream));
+  VCT_CUDA(cudaStreamSynchronize(t->dev->stream));
+  return VCT_OK;
+}
+
+int vct_target_download_gbuffer(vct_target_t* t, uint32_t* tri_id, float* depth, float* world_pos, float* normal, uint32_t* material) {
+  VCT_REQUIRE(t, "target is null");
+  cudaStream_t s = t->dev->stream;
+  size_t n = (size_t)t->W * t->H;
+  if (tri_id) VCT_CUDA(cudaMemcpy2DAsync(tri_id, 4, t->vis, 8, 4, n, cudaMemcpyDeviceToHost, s));                      // low word
+  if (depth) VCT_CUDA(cudaMemcpy2DAsync(depth, 4, (const uint32_t*)t->vis + 1, 8, 4, n, cudaMemcpyDeviceToHost, s));  // high word
+  if (world_pos) VCT_CUDA(cudaMemcpyAsync(world_pos, t->world_pos, n * 12, cudaMemcpyDeviceToHost, s));
+  if (normal) VCT_CUDA(cudaMemcpyAsync(normal, t->normal, n * 12, cudaMemcpyDeviceToHost, s));
+  if (material) VCT_CUDA(cudaMemcpyAsync(material, t->material, n * 4, cudaMemcpyDeviceToHost, s));
+  VCT_CUDA(cudaStreamSynchronize(s));
+  return VCT_OK;
+}
+
+void* vct_target_frame_device_ptr(vct_target_t* t) { return t ? (void*)t->frame : nullptr; }
+
+// ------------------------------------------------------------------ hot path
+int vct_voxelize_reserve(vct_device_t* dev, uint64_t max_fragments) {
+  VCT_REQUIRE(dev, "device is null");
+  VCT_REQUIRE(max_fragments > 0 && max_fragments < 0xFFFFFFF0ull, "fragment capacity out of range");
+  if (max_fragments <= dev->frag_capacity) return VCT_OK;
+  VCT_CUDA(cudaStreamSynchronize(dev->stream));
+  cudaFree(dev->frags); cudaFree(dev->occupied);
+  dev->frags = nullptr; dev->occupied = nullptr; dev->frag_capacity = 0;
+  VCT_CUDA(cudaMalloc(&dev->frags, max_fragments * sizeof(FragRec)));
+  VCT_CUDA(cudaMalloc(&dev->occupied, max_fragments * sizeof(uint32_t)));
+  dev->frag_capacity = max_fragments;
+  return VCT_OK;
+}
+
+int vct_voxelize(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, int z0, int z1) {
+  VCT_REQUIRE(dev && sc && g, "null argument");
+  VCT_REQUIRE(z0 >= 0 && z1 <= g->R && z0 <= z1, "bad z slab");
+  return launch_voxelize(dev, sc, g, z0, z1);
+}
+
+int vct_voxelize_stats(vct_device_t* dev, vct_voxel_stats_t* out) {
+  VCT_REQUIRE(dev && out, "null argument");
+  VCT_CUDA(cudaMemcpyAsync(dev->counters_host, dev->counters, CNT_TOTAL * sizeof(uint32_t), cudaMemcpyDeviceToHost, dev->stream));
+  VCT_CUDA(cudaStreamSynchronize(dev->stream));
+  out->items = dev->counters_host[CNT_ITEMS];
+  out->fragments = dev->counters_host[CNT_FRAGS];
+  out->occupied = dev->counters_host[CNT_OCCUPIED];
+  out->max_per_voxel = dev->counters_host[CNT_MAXLIST];
+  out->capacity = dev->frag_capacity;
+  if (out->fragments > dev->frag_capacity) {
+    uint64_t want = out->fragments + out->fragments / 4;
+    set_error("fragment arena overflow: %llu fragments > capacity %llu; arena grown, re-run the frame", (unsigned long long)out->fragments,
+              (unsigned long long)dev->frag_capacity);
+    int rc = vct_voxelize_reserve(dev, want);
+    if (rc) return rc;
+    return VCT_ERR_OVERFLOW;
+  }
+  return VCT_OK;
+}
+
+int vct_mipmap(vct_device_t* dev, vct_grid_t* g) {
+  VCT_REQUIRE(dev && g, "null argument");
+  return launch_mipmap(dev, g);
+}
+
+int vct_gbuffer(vct_device_t* dev, vct_scene_t* sc, const float view[16], const float proj[16], vct_target_t* t) {
+  VCT_REQUIRE(dev && sc && view && proj && t, "null argument");
+  return launch_gbuffer(dev, sc, view, proj, t);
+}
+
+int vct_cone_trace(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, const float view[16], const vct_trace_params_t* p, vct_target_t* t) {
+  VCT_REQUIRE(dev && sc && g && view && p && t, "null argument");
+  return launch_cone_trace(dev, sc, g, view, p, t, false);
+}
+
+int vct_cone_trace_count(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, const float view[16], const vct_trace_params_t* p, vct_target_t* t,
+                         vct_trace_stats_t* out) {
+  VCT_REQUIRE(dev && sc && g && view && p && t && out, "null argument");
+  int rc = launch_cone_trace(dev, sc, g, view, p, t, true);
+  if (rc) return rc;
+  unsigned long long h[8];
+  VCT_CUDA(cudaMemcpyAsync(h, dev->counters + 16, sizeof h, cudaMemcpyDeviceToHost, dev->stream));
+  VCT_CUDA(cudaStreamSynchronize(dev->stream));
+  out->samples_diffuse = h[0]; out->samples_shadow = h[1]; out->samples_specular = h[2]; out->samples_refraction = h[3];
+  out->shaded_pixels = h[4];
+  return VCT_OK;
+}
+
+int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_target_t* t, const float view[16], const float proj[16],
+                     const vct_trace_params_t* p) {
+  VCT_REQUIRE(dev && sc && g && t && view && proj && p, "null argument");
+  cudaStream_t s = dev->stream;
+  int rc;
+  VCT_CUDA(cudaEventRecord(dev->ev[0], s));
+  if ((rc = vct_grid_clear(g))) return rc;
+  VCT_CUDA(cudaEventRecord(dev->ev[1], s));
+  if ((rc = launch_voxelize(dev, sc, g, 0, g->R))) return rc;
+  VCT_CUDA(cudaEventRecord(dev->ev[2], s));
+  if ((rc = launch_mipmap(dev, g))) return rc;
+  VCT_CUDA(cudaEventRecord(dev->ev[3], s));
+  if ((rc = launch_gbuffer(dev, sc, view, proj, t))) return rc;
+  VCT_CUDA(cudaEventRecord(dev->ev[4], s));
+  if ((rc = launch_cone_trace(dev, sc, g, view, p, t, false))) return rc;
+  VCT_CUDA(cudaEventRecord(dev->ev[5], s));
+  dev->have_timings = true;
+  return VCT_OK;
+}
+
+int vct_last_frame_timings(vct_device_t* dev, float out_ms[6]) {
+  VCT_REQUIRE(dev && out_ms, "null argument");
+  VCT_REQUIRE(dev->have_timings, "no frame has been rendered");
+  VCT_CUDA(cudaEventSynchronize(dev->ev[5]));
+  for (int i = 0; i < 5; i++) VCT_CUDA(cudaEventElapsedTime(&out_ms[i], dev->ev[i], dev->ev[i + 1]));
+  VCT_CUDA(cudaEventElapsedTime(&out_ms[5], dev->ev[0], dev->ev[5]));
+  return VCT_OK;
+}
+
+}  // extern "C"

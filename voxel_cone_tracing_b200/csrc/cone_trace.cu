@@ -1,0 +1,414 @@
+// cone_trace.cu -- per-pixel diffuse / specular / shadow / refraction cone tracing over the G-buffer.
+//
+// Replaces shader/voxel_cone_tracing.frag (src/renderer.cpp:355-390 binds it).  Not a port of the
+// fragment shader's one-thread-per-fragment loop: a CTA owns an 8x4 screen tile and runs ONE WARP
+// PER CONE SLOT (9 diffuse, 1 specular, 1 refraction, 1 shadow per light), so all 32 lanes of a warp
+// march the same cone of neighbouring pixels (same aperture, near-identical direction and LOD
+// sequence -> coherent texel gathers, no divergence between cone types).  Cone results meet in
+// shared memory and warp 0 evaluates the Blinn-Phong / mix of main() (voxel_cone_tracing.frag:246-275).
+//
+// Texture sampling is done in software with fp32 weights (rule R7 of the oracle): textureLod =
+// trilinear in floor(lod) and floor(lod)+1, CLAMP_TO_BORDER with a zero border.  Result-preserving
+// savings over the literal shader: level 0 is fetched once for the three directions (all six level-0
+// textures are identical), the second level is skipped when the LOD fraction is exactly 0, footprints
+// wholly outside the grid are skipped, and a cone stops as soon as it has left the (border-padded)
+// cube for good -- every skipped term is exactly zero in the reference.
+// FMA contraction is allowed here: the frame is compared against the oracle with a tolerance
+// (max abs 2/255, PSNR >= 45 dB), not bit for bit.
+#include "vct_internal.cuh"
+
+namespace vct {
+
+struct F3 { float x, y, z; };
+__device__ __forceinline__ F3 f3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ F3 operator+(F3 a, F3 b) { return f3(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ F3 operator-(F3 a, F3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ F3 operator*(F3 a, float s) { return f3(a.x * s, a.y * s, a.z * s); }
+__device__ __forceinline__ F3 operator*(F3 a, F3 b) { return f3(a.x * b.x, a.y * b.y, a.z * b.z); }
+__device__ __forceinline__ F3 operator-(F3 a) { return f3(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ float dot(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ F3 cross(F3 a, F3 b) { return f3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
+__device__ __forceinline__ float length(F3 a) { return sqrtf(dot(a, a)); }
+__device__ __forceinline__ F3 normalize(F3 a) { float l = length(a); return f3(a.x / l, a.y / l, a.z / l); }
+__device__ __forceinline__ F3 mix(F3 a, F3 b, float t) { return a * (1.0f - t) + b * t; }
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+__device__ __forceinline__ F3 reflect(F3 I, F3 N) { return I - N * (2.0f * dot(N, I)); }
+__device__ __forceinline__ F3 refract(F3 I, F3 N, float eta) {
+  float d = dot(N, I);
+  float k = 1.0f - eta * eta * (1.0f - d * d);
+  if (k < 0.0f) return f3(0.f, 0.f, 0.f);
+  return I * eta - N * (eta * d + sqrtf(k));
+}
+
+struct TraceArgs {
+  GridView grid;
+  const float* world_pos;
+  const float* normal;
+  const uint32_t* material;
+  uint32_t* frame;
+  int W, H;
+  const vct_material_t* mats;
+  Lights lights;
+  float cube_size;
+  float cam_pos[3];
+  vct_trace_params_t prm;
+  unsigned long long* counts;  // [4] diffuse, shadow, specular, refraction (+[4] shaded pixels)
+  int n_diffuse, n_slots;
+};
+
+// byte k of a packed RGBA8 word as float (exact), without an I2F conversion
+__device__ __forceinline__ float byte_f(uint32_t w, int k) {
+  return __uint_as_float(__byte_perm(w, 0x4B000000u, 0x7650 + k)) - 8388608.0f;
+}
+__device__ __forceinline__ void madd4(float acc[4], float w, uint32_t word) {
+  acc[0] = fmaf(w, byte_f(word, 0), acc[0]);
+  acc[1] = fmaf(w, byte_f(word, 1), acc[1]);
+  acc[2] = fmaf(w, byte_f(word, 2), acc[2]);
+  acc[3] = fmaf(w, byte_f(word, 3), acc[3]);
+}
+
+// one mip level of sample_voxel (voxel_cone_tracing.frag:80-86): adds
+//   weight * (|d.x| * tex[ix] + |d.y| * tex[iy] + |d.z| * tex[iz]) (pos)   in BYTE units (0..255)
+__device__ __forceinline__ void fetch_level(const GridView& g, int level, F3 pos, F3 adir, int ix, int iy, int iz, float weight, float acc[4]) {
+  const int N = g.R >> level;
+  const float fN = (float)N;
+  const float ux = fmaf(pos.x, fN, -0.5f), uy = fmaf(pos.y, fN, -0.5f), uz = fmaf(pos.z, fN, -0.5f);
+  // footprint wholly outside (also catches NaN): border colour = 0
+  if (!(ux > -1.0f && ux < fN && uy > -1.0f && uy < fN && uz > -1.0f && uz < fN)) return;
+  const float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
+  const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+  const float ax = ux - fx, ay = uy - fy, az = uz - fz;
+  const float wxs[2] = {1.0f - ax, ax}, wys[2] = {1.0f - ay, ay}, wzs[2] = {1.0f - az, az};
+  if (level == 0) {
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int dz = 0; dz < 2; dz++) {
+      const int z = z0 + dz;
+      if ((unsigned)z >= (unsigned)N) continue;
+#pragma unroll
+      for (int dy = 0; dy < 2; dy++) {
+        const int y = y0 + dy;
+        if ((unsigned)y >= (unsigned)N) continue;
+        const float wyz = wys[dy] * wzs[dz];
+        const uint32_t* row = g.base + ((size_t)z * N + y) * N;
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++) {
+          const int x = x0 + dx;
+          if ((unsigned)x >= (unsigned)N) continue;
+          const uint32_t w = __ldg(row + x);
+          if (w) madd4(t, wxs[dx] * wyz, w);
+        }
+      }
+    }
+    const float s = weight * ((adir.x + adir.y) + adir.z);
+#pragma unroll
+    for (int k = 0; k < 4; k++) acc[k] = fmaf(s, t[k], acc[k]);
+  } else {
+    float tx[4] = {0.f, 0.f, 0.f, 0.f}, ty[4] = {0.f, 0.f, 0.f, 0.f}, tz[4] = {0.f, 0.f, 0.f, 0.f};
+    const uint32_t* lv = g.lvl[level];
+#pragma unroll
+    for (int dz = 0; dz < 2; dz++) {
+      const int z = z0 + dz;
+      if ((unsigned)z >= (unsigned)N) continue;
+#pragma unroll
+      for (int dy = 0; dy < 2; dy++) {
+        const int y = y0 + dy;
+        if ((unsigned)y >= (unsigned)N) continue;
+        const float wyz = wys[dy] * wzs[dz];
+        const uint32_t* row = lv + ((size_t)z * N + y) * N * 6;
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++) {
+          const int x = x0 + dx;
+          if ((unsigned)x >= (unsigned)N) continue;
+          const float w = wxs[dx] * wyz;
+          const uint32_t* rec = row + x * 6;
+          const uint32_t a = __ldg(rec + ix), b = __ldg(rec + iy), c = __ldg(rec + iz);
+          if (a) madd4(tx, w, a);
+          if (b) madd4(ty, w, b);
+          if (c) madd4(tz, w, c);
+        }
+      }
+    }
+    const float sx = weight * adir.x, sy = weight * adir.y, sz = weight * adir.z;
+#pragma unroll
+    for (int k = 0; k < 4; k++) acc[k] = fmaf(sx, tx[k], fmaf(sy, ty[k], fmaf(sz, tz[k], acc[k])));
+  }
+}
+
+// trace_cone (voxel_cone_tracing.frag:88-119).  Returns the number of loop iterations the reference
+// would execute when COUNT is set (no early exit in that build).
+template <bool COUNT>
+__device__ __forceinline__ uint32_t trace_cone(const GridView& g, F3 origin, F3 dir, float aperture, float max_dist, float out[4]) {
+  dir = normalize(dir);
+  const int ix = dir.x < 0.0f ? 0 : 1, iy = dir.y < 0.0f ? 2 : 3, iz = dir.z < 0.0f ? 4 : 5;
+  const F3 adir = f3(fabsf(dir.x), fabsf(dir.y), fabsf(dir.z));
+  const float cube_res = (float)g.R;
+  const float voxel_size = 1.0f / cube_res;
+  const float max_level = (float)(g.levels - 1);
+  const float margin = 0.5f / (float)(g.R >> (g.levels - 1));  // half a texel of the coarsest level
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};  // byte units
+  float dist = 3.0f * voxel_size;
+  float diam = dist * aperture;
+  F3 sp = f3(fmaf(dir.x, dist, origin.x), fmaf(dir.y, dist, origin.y), fmaf(dir.z, dist, origin.z));
+  uint32_t iters = 0;
+  while (acc[3] < 255.0f && dist < max_dist) {
+    if (!COUNT) {
+      // the cone has left the border-padded cube for good: every later sample is exactly zero
+      if ((sp.x <= -margin && dir.x <= 0.f) || (sp.x >= 1.0f + margin && dir.x >= 0.f) || (sp.y <= -margin && dir.y <= 0.f) ||
+          (sp.y >= 1.0f + margin && dir.y >= 0.f) || (sp.z <= -margin && dir.z <= 0.f) || (sp.z >= 1.0f + margin && dir.z >= 0.f))
+        break;
+    }
+    float lod = fmaxf(log2f(diam * cube_res), 0.0f);
+    lod = fminf(lod, max_level);
+    const float fl = floorf(lod);
+    const int l0 = (int)fl;
+    const float f = lod - fl;
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    fetch_level(g, l0, sp, adir, ix, iy, iz, 1.0f - f, s);
+    if (f > 0.0f) fetch_level(g, l0 + 1, sp, adir, ix, iy, iz, f, s);
+    const float k = 1.0f - acc[3] * (1.0f / 255.0f);
+#pragma unroll
+    for (int c = 0; c < 4; c++) acc[c] = fmaf(k, s[c], acc[c]);
+    const float step = fmaxf(diam * 0.5f, voxel_size);
+    dist = dist + step;
+    diam = dist * aperture;
+    sp = f3(fmaf(dir.x, dist, origin.x), fmaf(dir.y, dist, origin.y), fmaf(dir.z, dist, origin.z));
+    iters++;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) out[c] = acc[c] * (1.0f / 255.0f);
+  return iters;
+}
+
+__device__ __forceinline__ F3 tangent(F3 n) {
+  F3 t1 = cross(n, f3(0.f, 0.f, 1.f)), t2 = cross(n, f3(0.f, 1.f, 0.f));
+  return length(t1) > length(t2) ? normalize(t1) : normalize(t2);
+}
+
+__device__ __forceinline__ float specular_aperture(float shininess) {
+  float rough = sqrtf(2.0f / (shininess + 2.0f));
+  float a = tanf(1.57079f * rough);
+  return fminf(fmaxf(a, 0.0174533f), 3.14159265f);
+}
+
+__device__ __forceinline__ uint32_t pack_rgba8(const float v[4]) {
+  uint32_t r = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) r |= ((uint32_t)rintf(clamp01(v[k]) * 255.0f)) << (8 * k);
+  return r;
+}
+
+constexpr float kTan22_5 = 0.55785173935f;
+constexpr float kMaxDistance = 1.73205080757f;
+constexpr uint32_t kBackground = 0xFF404026u;  // (0.15,0.25,0.25,1) -> (38,64,64,255), renderer.cpp:398
+constexpr int kMaxSlots = 9 + 2 + VCT_MAX_POINT_LIGHTS;
+
+template <bool COUNT>
+__global__ void __launch_bounds__(32 * kMaxSlots)
+cone_trace_kernel(const TraceArgs a) {
+  __shared__ float res[kMaxSlots][32][4];
+  const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
+  const int tiles_x = (a.W + 7) / 8;
+  const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+  // multi-GPU split: 32x32 screen tiles are dealt round-robin to ranks
+  if (a.prm.tile_nranks > 1) {
+    const int t32 = (tile_y / 8) * ((a.W + 31) / 32) + (tile_x / 4);
+    if (t32 % a.prm.tile_nranks != a.prm.tile_rank) return;
+  }
+  const int px = tile_x * 8 + (lane & 7), py = tile_y * 4 + (lane >> 3);
+  const bool in_frame = px < a.W && py < a.H;
+  const size_t pix = (size_t)py * a.W + px;
+  const uint32_t mat_id = in_frame ? a.material[pix] : VCT_NO_TRIANGLE;
+  bool live = mat_id != VCT_NO_TRIANGLE;
+  F3 world = f3(0.f, 0.f, 0.f), normal = f3(0.f, 0.f, 1.f), pos = f3(0.f, 0.f, 0.f);
+  if (live) {
+    world = f3(a.world_pos[pix * 3], a.world_pos[pix * 3 + 1], a.world_pos[pix * 3 + 2]);
+    normal = f3(a.normal[pix * 3], a.normal[pix * 3 + 1], a.normal[pix * 3 + 2]);
+    pos = f3(0.5f * (world.x / a.cube_size) + 0.5f, 0.5f * (world.y / a.cube_size) + 0.5f, 0.5f * (world.z / a.cube_size) + 0.5f);
+    // main(): fragments outside the cube return before writing (voxel_cone_tracing.frag:250-251)
+    live = fabsf(pos.x) < 1.0f && fabsf(pos.y) < 1.0f && fabsf(pos.z) < 1.0f;
+  }
+  if (!__syncthreads_or((int)live)) {
+    if (slot == 0 && in_frame) a.frame[pix] = kBackground;
+    return;
+  }
+  const vct_material_t* m = live ? a.mats + mat_id : a.mats;
+  const F3 cam = f3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]);
+  const int nd = a.n_diffuse;
+  const bool debug_view = a.prm.view_voxel_dir < 7;
+
+  // ---------------- one cone per warp ----------------
+  float r[4] = {0.f, 0.f, 0.f, 0.f};
+  uint32_t iters = 0;
+  int kind = -1;  // 0 diffuse, 1 shadow, 2 specular, 3 refraction
+  if (live && !debug_view) {
+    if (slot < nd) {
+      if (a.prm.enable_diffuse) {
+        const F3 o1 = normalize(tangent(normal));
+        const F3 o2 = normalize(cross(o1, normal));
+        F3 d;
+        switch (slot) {
+          case 0: d = normal; break;
+          case 1: d = mix(normal, o1, 0.5f); break;
+          case 2: d = mix(normal, -o1, 0.5f); break;
+          case 3: d = mix(normal, o2, 0.5f); break;
+          case 4: d = mix(normal, -o2, 0.5f); break;
+          case 5: d = mix(normal, (o1 + o2) * 0.5f, 0.5f); break;
+          case 6: d = mix(normal, -((o1 + o2) * 0.5f), 0.5f); break;
+          case 7: d = mix(normal, (o1 - o2) * 0.5f, 0.5f); break;
+          default: d = mix(normal, -((o1 - o2) * 0.5f), 0.5f); break;
+        }
+        iters = trace_cone<COUNT>(a.grid, pos, d, kTan22_5, kMaxDistance, r);
+        kind = 0;
+      }
+    } else if (slot == nd) {
+      if (a.prm.enable_specular) {
+        const F3 view_dir = normalize(world - cam);
+        const F3 sd = normalize(reflect(-view_dir, normal));
+        iters = trace_cone<COUNT>(a.grid, pos, sd, specular_aperture(m->shininess), kMaxDistance, r);
+        kind = 2;
+      }
+    } else if (slot == nd + 1) {
+      const bool transmissive = m->illum == 4 || m->illum == 6 || m->illum == 7 || m->illum == 9;
+      if (transmissive && a.prm.enable_specular) {
+        const F3 view_dir = normalize(world - cam);
+        const F3 rd = refract(view_dir, normal, 1.0f / m->ior);
+        iters = trace_cone<COUNT>(a.grid, pos, rd, specular_aperture(m->shininess), kMaxDistance, r);
+        kind = 3;
+      }
+    } else {
+      const int li = slot - (nd + 2);
+      if (li < a.lights.n && a.prm.enable_direct && a.prm.enable_shadow) {
+        const vct_point_light_t& L = a.lights.l[li];
+        const F3 lp = f3(0.5f * (L.position[0] / a.cube_size) + 0.5f, 0.5f * (L.position[1] / a.cube_size) + 0.5f,
+                         0.5f * (L.position[2] / a.cube_size) + 0.5f);
+        F3 ld = lp - pos;
+        const float d = length(ld);
+        ld = f3(ld.x / d, ld.y / d, ld.z / d);
+        iters = trace_cone<COUNT>(a.grid, pos, ld, 0.1f, d, r);
+        kind = 1;
+      }
+    }
+  }
+  res[slot][lane][0] = r[0]; res[slot][lane][1] = r[1]; res[slot][lane][2] = r[2]; res[slot][lane][3] = r[3];
+  if (COUNT) {
+    // per-warp totals; kind is warp-uniform except for dead lanes
+    uint32_t it = iters;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
+    int kk = kind;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) kk = max(kk, __shfl_xor_sync(0xffffffffu, kk, o));
+    if (lane == 0 && kk >= 0) atomicAdd(&a.counts[kk], (unsigned long long)it);
+    if (slot == 0) {
+      uint32_t ball = __ballot_sync(0xffffffffu, live);
+      if (lane == 0) atomicAdd(&a.counts[4], (unsigned long long)__popc(ball));
+    }
+  }
+  __syncthreads();
+  if (slot != 0 || !in_frame) return;
+
+  // ---------------- main() (voxel_cone_tracing.frag:246-275) ----------------
+  if (!live) { a.frame[pix] = kBackground; return; }
+  float out[4];
+  if (debug_view) {
+    // textureLod(tex3D[view_voxel_dir], pos, view_voxel_lod), blended over the clear colour
+    const int d = a.prm.view_voxel_dir;
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    if (d >= 0 && d <= 5) {
+      float lod = fminf(fmaxf(a.prm.view_voxel_lod, 0.0f), (float)(a.grid.levels - 1));
+      const float fl = floorf(lod), f = lod - fl;
+      const int l0 = (int)fl;
+      // a unit weight on direction d only
+      F3 ad = f3(d < 2 ? 1.f : 0.f, (d == 2 || d == 3) ? 1.f : 0.f, d >= 4 ? 1.f : 0.f);
+      const int ix = d < 2 ? d : 0, iy = (d == 2 || d == 3) ? d : 2, iz = d >= 4 ? d : 4;
+      fetch_level(a.grid, l0, pos, ad, ix, iy, iz, 1.0f - f, t);
+      if (f > 0.0f) fetch_level(a.grid, l0 + 1, pos, ad, ix, iy, iz, f, t);
+    }
+    const float bg[4] = {0.15f, 0.25f, 0.25f, 1.0f};
+    const float al = t[3] * (1.0f / 255.0f);
+#pragma unroll
+    for (int k = 0; k < 4; k++) out[k] = (t[k] * (1.0f / 255.0f)) * al + bg[k] * (1.0f - al);
+    a.frame[pix] = pack_rgba8(out);
+    return;
+  }
+  const F3 view_dir = normalize(world - cam);
+  const F3 kd = f3(m->diffuse[0], m->diffuse[1], m->diffuse[2]);
+  const F3 ks = f3(m->specular[0], m->specular[1], m->specular[2]);
+  F3 fdiff = f3(0.f, 0.f, 0.f), fdir = f3(0.f, 0.f, 0.f), fspec = f3(0.f, 0.f, 0.f);
+  if (a.prm.enable_diffuse) {
+    F3 s = f3(0.f, 0.f, 0.f);
+    for (int i = 0; i < nd; i++) s = s + f3(res[i][lane][0], res[i][lane][1], res[i][lane][2]);
+    const float inv = 1.0f / (float)nd;
+    fdiff = kd * (s * inv);
+  }
+  if (a.prm.enable_direct) {  // direct_light(), voxel_cone_tracing.frag:175-218
+    F3 result = f3(0.f, 0.f, 0.f);
+    for (int i = 0; i < a.lights.n; i++) {
+      const vct_point_light_t& L = a.lights.l[i];
+      const F3 lp = f3(0.5f * (L.position[0] / a.cube_size) + 0.5f, 0.5f * (L.position[1] / a.cube_size) + 0.5f,
+                       0.5f * (L.position[2] / a.cube_size) + 0.5f);
+      F3 ld = lp - pos;
+      const float d = length(ld);
+      ld = f3(ld.x / d, ld.y / d, ld.z / d);
+      const float cos_surf = fmaxf(dot(normal, ld), 0.0f);
+      const float att = 1.0f / (1.0f + d * d);
+      const F3 light_color = f3(L.color[0], L.color[1], L.color[2]) * (att * cos_surf) * L.intensity;
+      float shadow_level = 1.0f;
+      if (a.prm.enable_shadow) shadow_level = fmaxf(0.0f, 1.0f - res[nd + 2 + i][lane][3]);
+      const float lambertian = fmaxf(dot(ld, normal), 0.0f);
+      float refract_angle = 0.0f;
+      if (m->dissolve <= 0.1f) {
+        const F3 rf = refract(view_dir, normal, 1.0f / m->ior);
+        refract_angle = fmaxf((1.0f - m->dissolve) * dot(rf, ld), 0.0f);
+      }
+      const F3 half_vec = normalize(ld + view_dir);
+      float specular_angle = fmaxf(dot(half_vec, normal), 0.0f);
+      specular_angle = fmaxf(specular_angle, refract_angle);
+      const float specular_coeff = powf(specular_angle, m->shininess);
+      const F3 brdf = kd * lambertian + ks * specular_coeff;
+      result = result + (brdf * (shadow_level + 0.04f)) * light_color;
+    }
+    fdir = result + f3(clamp01(m->emission[0]), clamp01(m->emission[1]), clamp01(m->emission[2]));
+  }
+  if (a.prm.enable_specular) fspec = ks * f3(res[nd][lane][0], res[nd][lane][1], res[nd][lane][2]);
+  F3 rgb = (fspec + fdiff) + fdir;
+  const bool transmissive = m->illum == 4 || m->illum == 6 || m->illum == 7 || m->illum == 9;
+  if (transmissive && a.prm.enable_specular) {
+    const F3 rr = f3(m->transmittance[0], m->transmittance[1], m->transmittance[2]) *
+                  f3(res[nd + 1][lane][0], res[nd + 1][lane][1], res[nd + 1][lane][2]);
+    rgb = mix(rr, rgb, m->dissolve);
+  }
+  out[0] = rgb.x; out[1] = rgb.y; out[2] = rgb.z; out[3] = 1.0f;
+  a.frame[pix] = pack_rgba8(out);
+}
+
+int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* view, const vct_trace_params_t* p, vct_target_t_* t,
+                      bool count_samples) {
+  TraceArgs a;
+  a.grid = g->view();
+  a.world_pos = t->world_pos; a.normal = t->normal; a.material = t->material; a.frame = t->frame;
+  a.W = t->W; a.H = t->H;
+  a.mats = sc->mats;
+  a.lights = sc->lights;
+  a.cube_size = sc->cube_size;
+  // "camera_position" = column 3 of the VIEW matrix (src/renderer.cpp:279-280) -- reproduced, not fixed
+  a.cam_pos[0] = view[12]; a.cam_pos[1] = view[13]; a.cam_pos[2] = view[14];
+  a.prm = *p;
+  if (a.prm.tile_nranks < 1) { a.prm.tile_nranks = 1; a.prm.tile_rank = 0; }
+  a.counts = (unsigned long long*)(dev->counters + 16);
+  a.n_diffuse = p->n_diffuse_cones == 5 ? 5 : 9;
+  a.n_slots = a.n_diffuse + 2 + sc->lights.n;
+  const int tiles = ((t->W + 7) / 8) * ((t->H + 3) / 4);
+  cudaStream_t s = dev->stream;
+  if (count_samples) {
+    VCT_CUDA(cudaMemsetAsync(dev->counters + 16, 0, 8 * sizeof(unsigned long long), s));
+    cone_trace_kernel<true><<<tiles, 32 * a.n_slots, 0, s>>>(a);
+  } else {
+    cone_trace_kernel<false><<<tiles, 32 * a.n_slots, 0, s>>>(a);
+  }
+  VCT_CUDA(cudaGetLastError());
+  return VCT_OK;
+}
+
+}  // namespace vct

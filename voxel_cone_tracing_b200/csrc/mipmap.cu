@@ -1,0 +1,319 @@
+// mipmap.cu -- six-direction anisotropic mip chain of the voxel grid.
+//
+// Replaces Renderer::filter() (src/renderer.cpp:283-314) + shader/mipmap.comp.  The reference
+// dispatches one compute pass per level, each re-reading six full textures (and launching 8x more
+// threads than texels).  Here the chain is built in TWO launches for the reference's 7 levels:
+//   mip_fused_low_kernel   one CTA per 32x8x8 tile of level 0 staged in shared memory
+//                          -> levels 1, 2, 3 for all six directions (level 0 is read ONCE, not 6x)
+//   mip_fused_high_kernel  one CTA per 8x8x8 tile of level 3 -> levels 4, 5, 6
+// so the DRAM traffic is the algorithmic minimum 4*R^3 (read) + 24*R^3*(1/8+1/64+...) (write).
+// Levels >= 1 are stored as records of six RGBA8 words per texel (direction-minor), the layout the
+// cone tracer gathers from.  All-zero child groups are skipped (exact: the filter of zeros is zero).
+//
+// Arithmetic = oracle rules R5/R6 (built with -fmad=false): c/255.0f correctly rounded (multiply
+// by 1/255 plus one exact Newton step, verified for all 256 inputs), blend f + (1-f.a)*b per
+// mipmap.comp:40-43, sum of the four pairs in order, /4, rint(clamp*255) -> bit-exact vs the oracle.
+#include "vct_internal.cuh"
+
+namespace vct {
+
+// children numbering of mipmap.comp:10-20: bit 2 = (x == 0), bit 1 = (y == 0), bit 0 = (z == 0)
+// => child i sits at offset (x,y,z) = (!(i>>2&1), !(i>>1&1), !(i&1)).
+// pairs[d][p] = {front, back} (mipmap.comp:59-98)
+__device__ constexpr int kPairs[6][4][2] = {
+    {{0, 4}, {1, 5}, {2, 6}, {3, 7}},  // -x
+    {{4, 0}, {5, 1}, {6, 2}, {7, 3}},  // +x
+    {{0, 2}, {1, 3}, {5, 7}, {4, 6}},  // -y
+    {{2, 0}, {3, 1}, {7, 5}, {6, 4}},  // +y
+    {{0, 1}, {2, 3}, {4, 5}, {6, 7}},  // -z
+    {{1, 0}, {3, 2}, {5, 4}, {7, 6}},  // +z
+};
+
+// exact unorm8 -> float: fl(b / 255)
+__device__ __forceinline__ float unorm(uint32_t word, int byte) {
+  // byte -> float without I2F: insert it into the mantissa of 2^23 and subtract 2^23
+  float b = __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7650 + byte)) - 8388608.0f;
+  const float k = 0.003921568859368563f;  // fl(1/255)
+  float q = b * k;
+  float r = fmaf(-q, 255.0f, b);  // exact residual
+  return fmaf(r, k, q);           // correctly rounded quotient
+}
+__device__ __forceinline__ void unpack4(uint32_t w, float c[4]) {
+  c[0] = unorm(w, 0); c[1] = unorm(w, 1); c[2] = unorm(w, 2); c[3] = unorm(w, 3);
+}
+// rintf(clamp(v,0,1) * 255) via the 1.5*2^23 trick (ties-to-even, same as rintf)
+__device__ __forceinline__ uint32_t to_unorm(float v) {
+  float t = fminf(fmaxf(v, 0.0f), 1.0f) * 255.0f;
+  return __float_as_uint(t + 12582912.0f) & 0xFFu;
+}
+
+// one direction of one parent texel from its 8 unpacked children
+template <int D>
+__device__ __forceinline__ uint32_t filter_dir(const float (&c)[8][4]) {
+  uint32_t out = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    float s = 0.f;
+#pragma unroll
+    for (int p = 0; p < 4; p++) {
+      const int f = kPairs[D][p][0], b = kPairs[D][p][1];
+      float v = c[f][k] + ((1.0f - c[f][3]) * c[b][k]);
+      s = p == 0 ? v : s + v;
+    }
+    out |= to_unorm(s * 0.25f) << (8 * k);
+  }
+  return out;
+}
+
+__device__ __forceinline__ uint32_t filter_dir_dyn(const float (&c)[8][4], int d) {
+  switch (d) {
+    case 0: return filter_dir<0>(c);
+    case 1: return filter_dir<1>(c);
+    case 2: return filter_dir<2>(c);
+    case 3: return filter_dir<3>(c);
+    case 4: return filter_dir<4>(c);
+    default: return filter_dir<5>(c);
+  }
+}
+
+// child index i of mipmap.comp for local offsets (dx,dy,dz)
+__device__ __forceinline__ constexpr int child_id(int dx, int dy, int dz) { return ((dx ^ 1) << 2) | ((dy ^ 1) << 1) | (dz ^ 1); }
+
+// ---------------------------------------------------------------------------------------------
+// generic fallback: one thread per (destination texel, direction)
+__global__ void mip_generic_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int Ns, int Nd, int src_is_base) {
+  const size_t n = (size_t)Nd * Nd * Nd * 6;
+  for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < n; u += (size_t)gridDim.x * blockDim.x) {
+    const int d = (int)(u % 6);
+    size_t tex = u / 6;
+    const int x = (int)(tex % Nd), y = (int)((tex / Nd) % Nd), z = (int)(tex / ((size_t)Nd * Nd));
+    float c[8][4];
+    uint32_t any = 0;
+#pragma unroll
+    for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+      for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++) {
+          size_t si = ((size_t)(2 * z + dz) * Ns + (2 * y + dy)) * Ns + (2 * x + dx);
+          uint32_t w = src_is_base ? src[si] : src[si * 6 + d];
+          any |= w;
+          unpack4(w, c[child_id(dx, dy, dz)]);
+        }
+    dst[u] = any ? filter_dir_dyn(c, d) : 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused levels 0 -> 1,2,3.  Tile = 32 x 8 x 8 level-0 texels, 256 threads.
+constexpr int TX = 32, TY = 8, TZ = 8;
+
+__global__ void __launch_bounds__(256)
+mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l1, uint32_t* __restrict__ l2, uint32_t* __restrict__ l3, int R) {
+  __shared__ __align__(16) uint32_t s0[TZ][TY][TX];           // 8 KB
+  __shared__ uint32_t s1[TZ / 2][TY / 2][TX / 2][6];          // 6 KB
+  __shared__ uint32_t s2[TZ / 4][TY / 4][TX / 4][6];          // 768 B
+  const int tiles_x = R / TX, tiles_y = R / TY;
+  const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
+  const int x0 = bx * TX, y0 = by * TY, z0 = bz * TZ;
+  const int t = threadIdx.x;
+
+  // ---- stage the level-0 tile: 64 rows of 128 B, two 16-byte loads per thread ----
+  uint32_t any0 = 0;
+#pragma unroll
+  for (int k = 0; k < 2; k++) {
+    const int row = (t >> 3) + 32 * k, quad = t & 7;
+    const int y = row & 7, z = row >> 3;
+    const uint4 v = *reinterpret_cast<const uint4*>(base + ((size_t)(z0 + z) * R + (y0 + y)) * R + x0 + 4 * quad);
+    *reinterpret_cast<uint4*>(&s0[z][y][4 * quad]) = v;
+    any0 |= v.x | v.y | v.z | v.w;
+  }
+  const int tile_nonzero = __syncthreads_or((int)(any0 != 0u));
+  const int N1 = R >> 1, N2 = R >> 2, N3 = R >> 3;
+
+  if (!tile_nonzero) {
+    // empty tile: every output of this tile is zero
+    {
+      const int x = t & 15, y = (t >> 4) & 3, z = t >> 6;
+      uint2* o = reinterpret_cast<uint2*>(l1 + (((size_t)(z0 / 2 + z) * N1 + (y0 / 2 + y)) * N1 + (x0 / 2 + x)) * 6);
+      o[0] = make_uint2(0u, 0u); o[1] = make_uint2(0u, 0u); o[2] = make_uint2(0u, 0u);
+    }
+    if (t < 192) {
+      const int d = t % 6, tex = t / 6, x = tex & 7, y = (tex >> 3) & 1, z = tex >> 4;
+      l2[(((size_t)(z0 / 4 + z) * N2 + (y0 / 4 + y)) * N2 + (x0 / 4 + x)) * 6 + d] = 0u;
+    }
+    if (t < 24) {
+      const int d = t % 6, x = t / 6;
+      l3[(((size_t)(z0 / 8) * N3 + (y0 / 8)) * N3 + (x0 / 8 + x)) * 6 + d] = 0u;
+    }
+    return;
+  }
+
+  // ---- level 1: one texel per thread, six directions ----
+  {
+    const int x = t & 15, y = (t >> 4) & 3, z = t >> 6;
+    uint32_t w[8];
+    uint32_t any = 0;
+#pragma unroll
+    for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+      for (int dy = 0; dy < 2; dy++) {
+        const uint2 p = *reinterpret_cast<const uint2*>(&s0[2 * z + dz][2 * y + dy][2 * x]);
+        w[child_id(0, dy, dz)] = p.x;
+        w[child_id(1, dy, dz)] = p.y;
+        any |= p.x | p.y;
+      }
+    uint32_t o[6] = {0u, 0u, 0u, 0u, 0u, 0u};
+    if (any) {
+      float c[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; i++) unpack4(w[i], c[i]);
+      o[0] = filter_dir<0>(c); o[1] = filter_dir<1>(c); o[2] = filter_dir<2>(c);
+      o[3] = filter_dir<3>(c); o[4] = filter_dir<4>(c); o[5] = filter_dir<5>(c);
+    }
+    uint2* g = reinterpret_cast<uint2*>(l1 + (((size_t)(z0 / 2 + z) * N1 + (y0 / 2 + y)) * N1 + (x0 / 2 + x)) * 6);
+    g[0] = make_uint2(o[0], o[1]); g[1] = make_uint2(o[2], o[3]); g[2] = make_uint2(o[4], o[5]);
+#pragma unroll
+    for (int d = 0; d < 6; d++) s1[z][y][x][d] = o[d];
+  }
+  __syncthreads();
+
+  // ---- level 2: 32 texels x 6 directions = 192 threads ----
+  if (t < 192) {
+    const int d = t % 6, tex = t / 6, x = tex & 7, y = (tex >> 3) & 1, z = tex >> 4;
+    float c[8][4];
+    uint32_t any = 0;
+#pragma unroll
+    for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+      for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++) {
+          uint32_t w = s1[2 * z + dz][2 * y + dy][2 * x + dx][d];
+          any |= w;
+          unpack4(w, c[child_id(dx, dy, dz)]);
+        }
+    const uint32_t o = any ? filter_dir_dyn(c, d) : 0u;
+    l2[(((size_t)(z0 / 4 + z) * N2 + (y0 / 4 + y)) * N2 + (x0 / 4 + x)) * 6 + d] = o;
+    s2[z][y][x][d] = o;
+  }
+  __syncthreads();
+
+  // ---- level 3: 4 texels x 6 directions ----
+  if (t < 24) {
+    const int d = t % 6, x = t / 6;
+    float c[8][4];
+    uint32_t any = 0;
+#pragma unroll
+    for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+      for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++) {
+          uint32_t w = s2[dz][dy][2 * x + dx][d];
+          any |= w;
+          unpack4(w, c[child_id(dx, dy, dz)]);
+        }
+    l3[(((size_t)(z0 / 8) * N3 + (y0 / 8)) * N3 + (x0 / 8 + x)) * 6 + d] = any ? filter_dir_dyn(c, d) : 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused levels 3 -> 4,5,6.  Tile = 8^3 level-3 records, 256 threads.
+__global__ void __launch_bounds__(256)
+mip_fused_high_kernel(const uint32_t* __restrict__ l3, uint32_t* __restrict__ l4, uint32_t* __restrict__ l5, uint32_t* __restrict__ l6, int N3) {
+  __shared__ uint32_t s3[8][8][8][6];  // 12 KB
+  __shared__ uint32_t s4[4][4][4][6];
+  __shared__ uint32_t s5[2][2][2][6];
+  const int tiles = N3 / 8;
+  const int bx = blockIdx.x % tiles, by = (blockIdx.x / tiles) % tiles, bz = blockIdx.x / (tiles * tiles);
+  const int t = threadIdx.x;
+  // 64 rows (z,y) of 48 words
+  for (int u = t; u < 64 * 48; u += 256) {
+    const int row = u / 48, wdx = u % 48, y = row & 7, z = row >> 3;
+    (&s3[z][y][0][0])[wdx] = l3[(((size_t)(bz * 8 + z) * N3 + (by * 8 + y)) * N3 + bx * 8) * 6 + wdx];
+  }
+  __syncthreads();
+  const int N4 = N3 / 2, N5 = N3 / 4, N6 = N3 / 8;
+  for (int u = t; u < 64 * 6; u += 256) {
+    const int d = u % 6, tex = u / 6, x = tex & 3, y = (tex >> 2) & 3, z = tex >> 4;
+    float c[8][4];
+    uint32_t any = 0;
+#pragma unroll
+    for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+      for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++) {
+          uint32_t w = s3[2 * z + dz][2 * y + dy][2 * x + dx][d];
+          any |= w;
+          unpack4(w, c[child_id(dx, dy, dz)]);
+        }
+    const uint32_t o = any ? filter_dir_dyn(c, d) : 0u;
+    l4[(((size_t)(bz * 4 + z) * N4 + (by * 4 + y)) * N4 + (bx * 4 + x)) * 6 + d] = o;
+    s4[z][y][x][d] = o;
+  }
+  __syncthreads();
+  if (t < 48) {
+    const int d = t % 6, tex = t / 6, x = tex & 1, y = (tex >> 1) & 1, z = tex >> 2;
+    float c[8][4];
+    uint32_t any = 0;
+#pragma unroll
+    for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+      for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++) {
+          uint32_t w = s4[2 * z + dz][2 * y + dy][2 * x + dx][d];
+          any |= w;
+          unpack4(w, c[child_id(dx, dy, dz)]);
+        }
+    const uint32_t o = any ? filter_dir_dyn(c, d) : 0u;
+    l5[(((size_t)(bz * 2 + z) * N5 + (by * 2 + y)) * N5 + (bx * 2 + x)) * 6 + d] = o;
+    s5[z][y][x][d] = o;
+  }
+  __syncthreads();
+  if (t < 6) {
+    const int d = t;
+    float c[8][4];
+    uint32_t any = 0;
+#pragma unroll
+    for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+      for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++) {
+          uint32_t w = s5[dz][dy][dx][d];
+          any |= w;
+          unpack4(w, c[child_id(dx, dy, dz)]);
+        }
+    l6[(((size_t)bz * N6 + by) * N6 + bx) * 6 + d] = any ? filter_dir_dyn(c, d) : 0u;
+  }
+}
+
+int launch_mipmap(vct_device* dev, vct_grid* g) {
+  cudaStream_t s = dev->stream;
+  const int R = g->R;
+  int level = 0;  // highest level already built
+  if (g->levels >= 4 && R % 32 == 0 && R >= 32) {
+    const int n_tiles = (R / TX) * (R / TY) * (R / TZ);
+    mip_fused_low_kernel<<<n_tiles, 256, 0, s>>>(g->base, g->lvl[1], g->lvl[2], g->lvl[3], R);
+    level = 3;
+    if (g->levels >= 7 && (R >> 3) % 8 == 0) {
+      const int tiles = (R >> 3) / 8;
+      mip_fused_high_kernel<<<tiles * tiles * tiles, 256, 0, s>>>(g->lvl[3], g->lvl[4], g->lvl[5], g->lvl[6], R >> 3);
+      level = 6;
+    }
+  }
+  for (int l = level; l + 1 < g->levels; l++) {
+    const int Ns = max(R >> l, 1), Nd = R >> (l + 1);
+    if (Nd < 1) break;
+    const size_t n = (size_t)Nd * Nd * Nd * 6;
+    const int blocks = (int)grid_for(n);
+    mip_generic_kernel<<<blocks, 256, 0, s>>>(l == 0 ? g->base : g->lvl[l], g->lvl[l + 1], Ns, Nd, l == 0);
+  }
+  VCT_CUDA(cudaGetLastError());
+  return VCT_OK;
+}
+
+}  // namespace vct

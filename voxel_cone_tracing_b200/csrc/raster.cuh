@@ -1,0 +1,179 @@
+// raster.cuh -- triangle setup, coverage and work-item machinery shared by the voxelizer and
+// the camera (G-buffer) pass.  Implements raster rules R1-R3 of DESIGN.md: vertices snapped to
+// 1/256 pixel, 64-bit integer edge functions at pixel centres, top-left rule, barycentrics
+// b_k = float(E_k) / float(2A).  Replaces the fixed-function rasteriser the reference drives at
+// src/renderer.cpp:339-347 (voxelization viewport 2R x 2R) and :358-389 (camera viewport).
+//
+// Work distribution: every triangle's bounding box is cut into 8x8-pixel tiles ("items");
+// a block-local scan in the setup kernel plus a one-block scan of the block totals give every
+// item a global index without a host round trip; the raster kernel walks items with one warp
+// per item (2 pixels per lane), so a wall-sized triangle and a sub-pixel sliver cost the same
+// per covered tile.
+#pragma once
+
+#include "vct_internal.cuh"
+
+namespace vct {
+
+constexpr int kSetupThreads = 256;
+constexpr int kTile = 8;  // 8x8 pixels per item
+
+__device__ __forceinline__ int imin3(int a, int b, int c) { return min(a, min(b, c)); }
+__device__ __forceinline__ int imax3(int a, int b, int c) { return max(a, max(b, c)); }
+
+// R1/R2. Returns false (t.sign = 0) when the triangle produces no fragment.
+__device__ __forceinline__ bool raster_setup(const float xw[3], const float yw[3], int W, int H, RasterTri& t) {
+  t.sign = 0;
+  t.imin = 0; t.imax = -1; t.jmin = 0; t.jmax = -1;
+  t.area = 0;
+  t.inv_unused = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    if (!(fabsf(xw[k]) <= 2097152.0f) || !(fabsf(yw[k]) <= 2097152.0f)) return false;  // guard band / NaN
+    t.X[k] = (int)rintf(xw[k] * 256.0f);
+    t.Y[k] = (int)rintf(yw[k] * 256.0f);
+  }
+  long long a = ((long long)t.X[1] - t.X[0]) * ((long long)t.Y[2] - t.Y[0]) -
+                ((long long)t.Y[1] - t.Y[0]) * ((long long)t.X[2] - t.X[0]);
+  if (a == 0) return false;
+  int minx = imin3(t.X[0], t.X[1], t.X[2]), maxx = imax3(t.X[0], t.X[1], t.X[2]);
+  int miny = imin3(t.Y[0], t.Y[1], t.Y[2]), maxy = imax3(t.Y[0], t.Y[1], t.Y[2]);
+  // pixel centres (i*256+128) inside [min,max]:  i >= ceil((min-128)/256), i <= floor((max-128)/256)
+  int i0 = (minx - 128 + 255) >> 8, i1 = (maxx - 128) >> 8;
+  int j0 = (miny - 128 + 255) >> 8, j1 = (maxy - 128) >> 8;
+  i0 = max(i0, 0); j0 = max(j0, 0);
+  i1 = min(i1, W - 1); j1 = min(j1, H - 1);
+  if (i0 > i1 || j0 > j1) return false;
+  t.imin = i0; t.imax = i1; t.jmin = j0; t.jmax = j1;
+  t.area = a > 0 ? a : -a;
+  t.sign = a > 0 ? 1 : -1;
+  return true;
+}
+
+__device__ __forceinline__ uint32_t raster_item_count(const RasterTri& t) {
+  if (t.sign == 0) return 0u;
+  int tx = (t.imax >> 3) - (t.imin >> 3) + 1, ty = (t.jmax >> 3) - (t.jmin >> 3) + 1;
+  return (uint32_t)tx * (uint32_t)ty;
+}
+
+// R2/R3: coverage + barycentrics of pixel (i,j)
+__device__ __forceinline__ bool raster_sample(const RasterTri& t, int i, int j, float b[3]) {
+  long long px = (long long)i * 256 + 128, py = (long long)j * 256 + 128;
+  long long E[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int a = (k + 1) % 3, c = (k + 2) % 3;
+    long long dx = (long long)t.X[c] - t.X[a], dy = (long long)t.Y[c] - t.Y[a];
+    long long e = dx * (py - t.Y[a]) - dy * (px - t.X[a]);
+    if (t.sign < 0) { e = -e; dx = -dx; dy = -dy; }
+    if (e < 0) return false;
+    if (e == 0 && !((dy < 0) || (dy == 0 && dx < 0))) return false;  // top-left rule
+    E[k] = e;
+  }
+  float fa = (float)t.area;
+  b[0] = (float)E[0] / fa;
+  b[1] = (float)E[1] / fa;
+  b[2] = (float)E[2] / fa;
+  return true;
+}
+
+__device__ __forceinline__ float interp3(const float b[3], float a0, float a1, float a2) {
+  return (b[0] * a0 + b[1] * a1) + b[2] * a2;  // compiled with -fmad=false: two roundings per term, like the oracle
+}
+
+// ---- block-local exclusive scan of per-triangle item counts (used inside the setup kernels) ----
+// Writes local[t] (exclusive prefix inside the 256-thread block) and block_total[blockIdx.x].
+__device__ __forceinline__ void block_scan_items(uint32_t count, uint32_t t, uint32_t n_tris, uint32_t* local, uint32_t* block_total) {
+  __shared__ uint32_t warp_sums[kSetupThreads / 32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  uint32_t v = count;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += n;
+  }
+  if (lane == 31) warp_sums[wid] = v;
+  __syncthreads();
+  if (wid == 0) {
+    uint32_t w = lane < kSetupThreads / 32 ? warp_sums[lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t n = __shfl_up_sync(0xffffffffu, w, o);
+      if (lane >= o) w += n;
+    }
+    if (lane < kSetupThreads / 32) warp_sums[lane] = w;  // inclusive
+  }
+  __syncthreads();
+  uint32_t warp_off = wid ? warp_sums[wid - 1] : 0u;
+  if (t < n_tris) local[t] = warp_off + v - count;
+  if (threadIdx.x == kSetupThreads - 1) block_total[blockIdx.x] = warp_off + v;
+}
+
+// one block: exclusive scan of block totals in place, grand total -> *total
+static __global__ void scan_block_totals_kernel(uint32_t* __restrict__ block_total, uint32_t n_blocks, uint32_t* __restrict__ total) {
+  __shared__ uint32_t warp_sums[32];
+  __shared__ uint32_t carry_s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (uint32_t base = 0; base < n_blocks; base += blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t c = i < n_blocks ? block_total[i] : 0u, v = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
+      if (lane >= o) v += n;
+    }
+    if (lane == 31) warp_sums[wid] = v;
+    __syncthreads();
+    if (wid == 0) {
+      uint32_t w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        uint32_t n = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o) w += n;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    uint32_t carry = carry_s;
+    uint32_t off = carry + (wid ? warp_sums[wid - 1] : 0u);
+    if (i < n_blocks) block_total[i] = off + v - c;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) carry_s = off + v;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) *total = carry_s;
+}
+
+// item index -> (triangle, tile).  item_block: exclusive prefix per setup block; item_local: exclusive
+// prefix inside the block.  Picks the LAST entry whose prefix <= the target so that empty triangles /
+// empty blocks (equal prefixes) are skipped.
+__device__ __forceinline__ uint32_t find_item_triangle(uint32_t g, const uint32_t* __restrict__ item_block, uint32_t n_blocks,
+                                                       const uint32_t* __restrict__ item_local, uint32_t n_tris, uint32_t& rank) {
+  uint32_t lo = 0, hi = n_blocks;  // invariant: item_block[lo] <= g
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (__ldg(item_block + mid) <= g) lo = mid; else hi = mid;
+  }
+  uint32_t x = g - __ldg(item_block + lo);
+  uint32_t tlo = lo * kSetupThreads, thi = min(tlo + kSetupThreads, n_tris);
+  while (thi - tlo > 1) {
+    uint32_t mid = (tlo + thi) >> 1;
+    if (__ldg(item_local + mid) <= x) tlo = mid; else thi = mid;
+  }
+  rank = x - __ldg(item_local + tlo);
+  return tlo;
+}
+
+// draw lookup for a global triangle sequence number
+__device__ __forceinline__ uint32_t find_draw(uint32_t tri, const DrawRec* __restrict__ draws, uint32_t n_draws) {
+  uint32_t lo = 0, hi = n_draws;
+  while (hi - lo > 1) {
+    uint32_t mid = (lo + hi) >> 1;
+    if (draws[mid].tri_base <= tri) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+}  // namespace vct

@@ -1,0 +1,176 @@
+// vct_internal.cuh -- objects behind the opaque handles of include/vct/vct_c.h and small
+// host/device helpers shared by the kernels.  Not part of the public interface.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "vct/vct_c.h"
+
+namespace vct {
+
+void set_error(const char* fmt, ...);
+
+#define VCT_CUDA(expr)                                                                              \
+  do {                                                                                              \
+    cudaError_t e_ = (expr);                                                                        \
+    if (e_ != cudaSuccess) {                                                                        \
+      ::vct::set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #expr, cudaGetErrorString(e_));  \
+      return e_ == cudaErrorMemoryAllocation ? VCT_ERR_OOM : VCT_ERR_CUDA;                          \
+    }                                                                                               \
+  } while (0)
+
+#define VCT_REQUIRE(cond, msg)                                    \
+  do {                                                            \
+    if (!(cond)) {                                                \
+      ::vct::set_error("%s: %s", __func__, msg);                  \
+      return VCT_ERR_INVALID;                                     \
+    }                                                             \
+  } while (0)
+
+// ---- device-side records -------------------------------------------------------------
+
+// per-draw record built on the host when the draw list is set
+struct DrawRec {
+  uint32_t first_index, index_count, vertex_base, material;
+  float model[16];
+  float nmat[9];      // mat3(transpose(inverse(model))), column-major (rule R9)
+  uint32_t tri_base;  // global sequence number of the draw's first triangle
+  uint32_t pad[2];
+};
+
+// a rasterisable triangle after setup (rules R1-R3), shared by the voxelizer and the camera pass
+struct RasterTri {
+  int32_t X[3], Y[3];   // 24.8 fixed-point window coordinates
+  int32_t sign;         // orientation (+1 / -1), 0 = rejected
+  int32_t imin, imax, jmin, jmax;
+  float inv_unused;
+  long long area;       // > 0
+};
+
+struct VoxTri {        // voxelizer per-triangle record
+  RasterTri rt;
+  float wp[3][3];      // world position / cube_size per vertex (voxelize.vert:26)
+  float nn[3][3];      // normalised normals per vertex (voxelize.vert:28)
+  uint32_t material;
+  uint32_t axis;
+};
+
+struct CamTri {        // camera-pass per-triangle record
+  RasterTri rt;
+  float world[3][3];
+  float nn[3][3];
+  float iw[3];
+  float zw[3];
+  uint32_t material;
+  uint32_t pad;
+};
+
+struct FragRec {       // one voxelization fragment (32 bytes)
+  uint32_t next;       // 1-based index of the next fragment in the voxel's list, 0 = end
+  uint32_t voxel;
+  unsigned long long key;  // canonical order key: (triangle sequence << 24) | (row << 12) | column
+  float val[4];        // colour * 255 (voxelize.frag:99)
+};
+
+struct Lights {
+  vct_point_light_t l[VCT_MAX_POINT_LIGHTS];
+  int32_t n;
+};
+
+// level pointers of the directional pyramid
+#define VCT_MAX_LEVELS 12
+struct GridView {
+  uint32_t* base;                 // level 0: R^3 u32, [z][y][x]
+  uint32_t* lvl[VCT_MAX_LEVELS];  // level l >= 1: (R>>l)^3 records of 6 u32 (direction-minor)
+  int R, levels;
+};
+
+}  // namespace vct
+
+// ---- the objects behind the opaque handles -----------------------------------------------
+
+struct vct_device {
+  int ordinal = 0;
+  cudaStream_t stream = nullptr;
+  cudaDeviceProp prop{};
+  // voxelizer arenas
+  vct::FragRec* frags = nullptr;
+  uint32_t* occupied = nullptr;      // voxel indices that received >= 1 fragment
+  uint64_t frag_capacity = 0;
+  // raster scratch (grown on demand)
+  void* tri_recs = nullptr;  size_t tri_recs_bytes = 0;
+  uint32_t* item_local = nullptr;    // per-triangle exclusive prefix inside its 256-block
+  uint32_t* item_block = nullptr;    // per-block exclusive prefix
+  size_t item_capacity_tris = 0;
+  uint32_t* counters = nullptr;      // device counters, see enum below
+  uint32_t* counters_host = nullptr; // pinned mirror
+  cudaEvent_t ev[8] = {};
+  bool have_timings = false;
+};
+enum { CNT_ITEMS = 0, CNT_FRAGS = 1, CNT_OCCUPIED = 2, CNT_MAXLIST = 3, CNT_CAM_ITEMS = 4, CNT_SAMPLES = 8 /* ..15 */, CNT_TOTAL = 32 };
+
+struct vct_scene {
+  vct_device* dev = nullptr;
+  vct_vertex_t* verts = nullptr;  uint32_t n_verts = 0;   size_t verts_cap = 0;
+  uint32_t* indices = nullptr;    uint32_t n_indices = 0; size_t indices_cap = 0;
+  vct_material_t* mats = nullptr; uint32_t n_mats = 0;    size_t mats_cap = 0;
+  vct::DrawRec* draws = nullptr;  uint32_t n_draws = 0;   size_t draws_cap = 0;
+  uint32_t n_tris = 0;
+  vct::Lights lights{};
+  float cube_size = 1.0f;
+  // pinned staging so that per-frame updates are true async copies
+  void* stage = nullptr; size_t stage_bytes = 0;
+};
+
+struct vct_grid {
+  vct_device* dev = nullptr;
+  int R = 0, levels = 0;
+  uint32_t* base = nullptr;
+  uint32_t* lvl[VCT_MAX_LEVELS] = {};
+  size_t bytes = 0;
+  vct::GridView view() const {
+    vct::GridView v;
+    v.base = base; v.R = R; v.levels = levels;
+    for (int i = 0; i < VCT_MAX_LEVELS; i++) v.lvl[i] = lvl[i];
+    return v;
+  }
+};
+
+struct vct_target_t_ {
+  vct_device* dev = nullptr;
+  int W = 0, H = 0;
+  unsigned long long* vis = nullptr;  // (depth bits << 32) | triangle sequence, atomicMin
+  float* world_pos = nullptr;         // 3 floats / pixel
+  float* normal = nullptr;            // 3 floats / pixel (interpolated, NOT renormalised)
+  uint32_t* material = nullptr;
+  uint32_t* frame = nullptr;          // RGBA8
+};
+
+struct vct_tex3d {
+  vct_device* dev = nullptr;
+  int w = 0, h = 0, d = 0, levels = 0;
+  uint32_t* lvl[VCT_MAX_LEVELS] = {};
+};
+
+static inline unsigned grid_for(size_t n, unsigned threads = 256, unsigned cap = 148 * 16) {
+  size_t b = (n + threads - 1) / threads;
+  return (unsigned)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ---- stage entry points implemented in the .cu files ------------------------------------
+namespace vct {
+int ensure_tri_scratch(vct_device* dev, size_t n_tris, size_t rec_bytes);
+int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1);
+int launch_mipmap(vct_device* dev, vct_grid* g);
+int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const float* proj, vct_target_t_* t);
+int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* view, const vct_trace_params_t* p, vct_target_t_* t,
+                      bool count_samples);
+int launch_fill_u32(cudaStream_t s, uint32_t* p, size_t n, uint32_t v);
+int launch_tex3d_mip(vct_tex3d* t);
+}  // namespace vct

@@ -1,0 +1,293 @@
+// voxelize.cu -- triangle voxelization into the RGBA8 radiance/opacity grid (level 0).
+//
+// Replaces the reference's voxelize.vert / voxelize.geom / fixed-function raster / voxelize.frag
+// pass (src/renderer.cpp:316-347).  Not a port: the geometry-shader + ROP pipeline becomes
+//   1. vox_setup_kernel   triangle-parallel: vertex transform (voxelize.vert:24-30), dominant-axis
+//                         selection (voxelize.geom:25-55), 1/256-pixel snapping, 8x8-pixel item count,
+//                         block-local scan
+//   2. scan_block_totals  one block: global item offsets (no host round trip)
+//   3. vox_raster_kernel  one warp per 8x8 item: coverage, fragment shading (voxelize.frag:122-157),
+//                         append of a 32-byte fragment record to a per-voxel linked list whose head
+//                         lives in the grid word itself (atomicExch), occupied-voxel list
+//   4. vox_resolve_kernel one thread per occupied voxel: sorts the voxel's fragments by the canonical
+//                         order key (draw, triangle, row, column) and folds them with the reference's
+//                         RGBA8 running average (voxelize.frag:95-120) -> deterministic and bit-exact
+//                         against the sequential oracle, which the CAS loop of the reference is not.
+// Built with -fmad=false: the arithmetic (IEEE add/mul/div/sqrt only, fixed evaluation order) is the
+// same as the oracle's so that voxel occupancy AND colour match bit for bit.
+#include "raster.cuh"
+
+namespace vct {
+
+struct F3 { float x, y, z; };
+__device__ __forceinline__ F3 f3(float x, float y, float z) { F3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ F3 sub(F3 a, F3 b) { return f3(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ float dot(F3 a, F3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
+__device__ __forceinline__ F3 cross(F3 a, F3 b) { return f3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y); }
+__device__ __forceinline__ F3 normalize(F3 a) { float l = sqrtf(dot(a, a)); return f3(a.x / l, a.y / l, a.z / l); }
+__device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
+
+__global__ void __launch_bounds__(kSetupThreads)
+vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ draws,
+                 uint32_t n_draws, uint32_t n_tris, float cube_size, int R, VoxTri* __restrict__ out, uint32_t* __restrict__ item_local,
+                 uint32_t* __restrict__ item_block) {
+  uint32_t t = blockIdx.x * kSetupThreads + threadIdx.x;
+  uint32_t count = 0;
+  if (t < n_tris) {
+    const DrawRec& d = draws[find_draw(t, draws, n_draws)];
+    uint32_t first = d.first_index + 3u * (t - d.tri_base);
+    VoxTri v;
+    const float* m = d.model;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const vct_vertex_t vx = verts[d.vertex_base + indices[first + k]];
+      float px = vx.pos[0], py = vx.pos[1], pz = vx.pos[2];
+      float wx = ((m[0] * px + m[4] * py) + m[8] * pz) + m[12];   // model * vec4(position, 1)
+      float wy = ((m[1] * px + m[5] * py) + m[9] * pz) + m[13];
+      float wz = ((m[2] * px + m[6] * py) + m[10] * pz) + m[14];
+      v.wp[k][0] = wx / cube_size; v.wp[k][1] = wy / cube_size; v.wp[k][2] = wz / cube_size;
+      const float* nm = d.nmat;
+      F3 n = f3((nm[0] * vx.norm[0] + nm[3] * vx.norm[1]) + nm[6] * vx.norm[2],
+                (nm[1] * vx.norm[0] + nm[4] * vx.norm[1]) + nm[7] * vx.norm[2],
+                (nm[2] * vx.norm[0] + nm[5] * vx.norm[1]) + nm[8] * vx.norm[2]);
+      n = normalize(n);
+      v.nn[k][0] = n.x; v.nn[k][1] = n.y; v.nn[k][2] = n.z;
+    }
+    // dominant axis of the face normal; strict comparisons, ties fall through to the (x,z) branch
+    F3 w0 = f3(v.wp[0][0], v.wp[0][1], v.wp[0][2]);
+    F3 c = cross(sub(f3(v.wp[1][0], v.wp[1][1], v.wp[1][2]), w0), sub(f3(v.wp[2][0], v.wp[2][1], v.wp[2][2]), w0));
+    float ax = fabsf(c.x), ay = fabsf(c.y), az = fabsf(c.z);
+    uint32_t axis = (az > ax && az > ay) ? 0u : ((ax > ay && ax > az) ? 1u : 2u);
+    float xw[3], yw[3];
+    const float half = (float)(2 * R) * 0.5f;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      float a = axis == 1u ? v.wp[k][1] : v.wp[k][0];
+      float b = axis == 0u ? v.wp[k][1] : v.wp[k][2];
+      xw[k] = (a + 1.0f) * half;
+      yw[k] = (b + 1.0f) * half;
+    }
+    raster_setup(xw, yw, 2 * R, 2 * R, v.rt);
+    v.material = d.material;
+    v.axis = axis;
+    out[t] = v;
+    count = raster_item_count(v.rt);
+  }
+  block_scan_items(count, t, n_tris, item_local, item_block);
+}
+
+// fragment colour (voxelize.frag:122-153), returns colour * 255
+__device__ __forceinline__ void shade_fragment(const VoxTri& v, const float b[3], const vct_material_t* __restrict__ mats, const Lights& L,
+                                               float cube_size, F3& pos, float val[4]) {
+  pos = f3(interp3(b, v.wp[0][0], v.wp[1][0], v.wp[2][0]), interp3(b, v.wp[0][1], v.wp[1][1], v.wp[2][1]),
+           interp3(b, v.wp[0][2], v.wp[1][2], v.wp[2][2]));
+  F3 nrm = f3(interp3(b, v.nn[0][0], v.nn[1][0], v.nn[2][0]), interp3(b, v.nn[0][1], v.nn[1][1], v.nn[2][1]),
+              interp3(b, v.nn[0][2], v.nn[1][2], v.nn[2][2]));
+  F3 color = f3(0.f, 0.f, 0.f);
+  for (int i = 0; i < L.n; i++) {
+    F3 lp = f3(L.l[i].position[0] / cube_size, L.l[i].position[1] / cube_size, L.l[i].position[2] / cube_size);
+    F3 dv = sub(lp, pos);
+    float dist = sqrtf(dot(dv, dv));
+    F3 dir = f3(dv.x / dist, dv.y / dist, dv.z / dist);
+    float att = 1.0f / ((1.0f + 0.0f * dist) + (1.0f * dist) * dist);
+    float cos_surf = fmaxf(dot(normalize(nrm), dir), 0.0f);
+    float s = cos_surf * att;
+    color.x = color.x + (L.l[i].color[0] * s) * L.l[i].intensity;
+    color.y = color.y + (L.l[i].color[1] * s) * L.l[i].intensity;
+    color.z = color.z + (L.l[i].color[2] * s) * L.l[i].intensity;
+  }
+  const vct_material_t& m = mats[v.material];
+  color = f3(m.diffuse[0] * color.x + m.emission[0], m.diffuse[1] * color.y + m.emission[1], m.diffuse[2] * color.z + m.emission[2]);
+  float tr0 = 1.f, tr1 = 1.f, tr2 = 1.f, alpha = 1.f;
+  if (m.illum == 4 || m.illum == 6 || m.illum == 7 || m.illum == 9) {
+    tr0 = m.transmittance[0]; tr1 = m.transmittance[1]; tr2 = m.transmittance[2];
+    alpha = m.dissolve;
+  }
+  val[0] = clamp01(tr0 * color.x) * 255.0f;
+  val[1] = clamp01(tr1 * color.y) * 255.0f;
+  val[2] = clamp01(tr2 * color.z) * 255.0f;
+  val[3] = clamp01(alpha) * 255.0f;
+}
+
+__global__ void __launch_bounds__(256)
+vox_raster_kernel(const VoxTri* __restrict__ tris, uint32_t n_tris, const uint32_t* __restrict__ item_local,
+                  const uint32_t* __restrict__ item_block, uint32_t n_blocks, const vct_material_t* __restrict__ mats, Lights L,
+                  float cube_size, int R, int z0, int z1, uint32_t* __restrict__ base, FragRec* __restrict__ frags,
+                  uint32_t frag_capacity, uint32_t* __restrict__ occupied, uint32_t* __restrict__ counters) {
+  const uint32_t total = counters[CNT_ITEMS];
+  const int lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  const float fR = (float)R;
+  for (uint32_t chunk = warp; (unsigned long long)chunk * 32ull < total; chunk += n_warps) {
+    uint32_t g = chunk * 32u + lane;
+    uint32_t my_tri = 0, my_rank = 0;
+    if (g < total) my_tri = find_item_triangle(g, item_block, n_blocks, item_local, n_tris, my_rank);
+    const int n_here = min(32u, total - chunk * 32u);
+    for (int s = 0; s < n_here; s++) {
+      const uint32_t ti = __shfl_sync(0xffffffffu, my_tri, s);
+      const uint32_t rank = __shfl_sync(0xffffffffu, my_rank, s);
+      const VoxTri& v = tris[ti];
+      const RasterTri rt = v.rt;
+      const int tiles_x = (rt.imax >> 3) - (rt.imin >> 3) + 1;
+      const int tx = (rt.imin >> 3) + (int)(rank % (uint32_t)tiles_x), ty = (rt.jmin >> 3) + (int)(rank / (uint32_t)tiles_x);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int p = lane + 32 * h;
+        const int i = tx * kTile + (p & 7), j = ty * kTile + (p >> 3);
+        float b[3];
+        bool covered = i >= rt.imin && i <= rt.imax && j >= rt.jmin && j <= rt.jmax && raster_sample(rt, i, j, b);
+        uint32_t voxel = 0;
+        float val[4];
+        if (covered) {
+          F3 pos;
+          shade_fragment(v, b, mats, L, cube_size, pos, val);
+          // ivec3(dim * scale_and_bias(pos)): truncation toward zero, then the image bounds check (voxelize.frag:156-157)
+          int vx = (int)(fR * (0.5f * pos.x + 0.5f)), vy = (int)(fR * (0.5f * pos.y + 0.5f)), vz = (int)(fR * (0.5f * pos.z + 0.5f));
+          covered = vx >= 0 && vy >= 0 && vz >= 0 && vx < R && vy < R && vz < R && vz >= z0 && vz < z1;
+          voxel = ((uint32_t)vz * (uint32_t)R + (uint32_t)vy) * (uint32_t)R + (uint32_t)vx;
+        }
+        // warp-aggregated arena allocation
+        const uint32_t mask = __ballot_sync(0xffffffffu, covered);
+        if (mask) {
+          uint32_t basei = 0;
+          const int leader = __ffs(mask) - 1;
+          if (lane == leader) basei = atomicAdd(&counters[CNT_FRAGS], (uint32_t)__popc(mask));
+          basei = __shfl_sync(0xffffffffu, basei, leader);
+          if (covered) {
+            const uint32_t idx = basei + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+            if (idx < frag_capacity) {
+              const uint32_t prev = atomicExch(&base[voxel], idx + 1u);
+              FragRec r;
+              r.next = prev;
+              r.voxel = voxel;
+              r.key = ((unsigned long long)ti << 24) | ((unsigned long long)j << 12) | (unsigned long long)i;
+              r.val[0] = val[0]; r.val[1] = val[1]; r.val[2] = val[2]; r.val[3] = val[3];
+              frags[idx] = r;
+              if (prev == 0u) occupied[atomicAdd(&counters[CNT_OCCUPIED], 1u)] = voxel;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// ---- imageAtomicRGBA8Avg (voxelize.frag:66-120) applied sequentially ----
+__device__ __forceinline__ uint32_t conv_rgba8(const float v[4]) {
+  return (((uint32_t)v[3]) & 0xFFu) << 24 | (((uint32_t)v[2]) & 0xFFu) << 16 | (((uint32_t)v[1]) & 0xFFu) << 8 | (((uint32_t)v[0]) & 0xFFu);
+}
+__device__ __forceinline__ uint32_t enc_nibble(uint32_t m, uint32_t n) {
+  return (m & 0xFEFEFEFEu) | (n & 1u) | (n & 2u) << 7 | (n & 4u) << 14 | (n & 8u) << 21;
+}
+__device__ __forceinline__ uint32_t dec_nibble(uint32_t m) {
+  return (m & 1u) | (m & 0x100u) >> 7 | (m & 0x10000u) >> 14 | (m & 0x1000000u) >> 21;
+}
+__device__ __forceinline__ uint32_t avg_fold(uint32_t stored, const float val[4]) {
+  if (stored == 0u) return enc_nibble(conv_rgba8(val), 1u);  // first CAS (expected 0) succeeds
+  const uint32_t c = stored & 0xFEFEFEFEu;
+  float r[4] = {(float)(c & 0xFFu), (float)((c >> 8) & 0xFFu), (float)((c >> 16) & 0xFFu), (float)((c >> 24) & 0xFFu)};
+  uint32_t n = dec_nibble(stored);
+  const float fn = (float)n;
+  n = n + 1u;
+  const float fn1 = (float)n;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    float t = r[k] * fn + val[k];
+    t = t / fn1;
+    r[k] = rintf(t / 2.0f) * 2.0f;
+  }
+  return enc_nibble(conv_rgba8(r), n);
+}
+
+constexpr int kSortMax = 24;
+
+__global__ void __launch_bounds__(128)
+vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frags, const uint32_t* __restrict__ occupied,
+                   uint32_t* __restrict__ counters, uint32_t frag_capacity) {
+  const uint32_t n_occ = counters[CNT_OCCUPIED];
+  for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < n_occ; o += gridDim.x * blockDim.x) {
+    const uint32_t voxel = occupied[o];
+    const uint32_t head = base[voxel];
+    unsigned long long keys[kSortMax];
+    uint32_t ids[kSortMax];
+    uint32_t n = 0;
+    for (uint32_t node = head; node != 0u; node = frags[node - 1u].next) {
+      if (n < kSortMax) {
+        // insertion sort, ascending key
+        unsigned long long k = frags[node - 1u].key;
+        int pos = (int)n;
+        while (pos > 0 && keys[pos - 1] > k) { keys[pos] = keys[pos - 1]; ids[pos] = ids[pos - 1]; pos--; }
+        keys[pos] = k; ids[pos] = node - 1u;
+      }
+      n++;
+    }
+    uint32_t stored = 0u;
+    if (n <= (uint32_t)kSortMax) {
+      for (uint32_t i = 0; i < n; i++) stored = avg_fold(stored, frags[ids[i]].val);
+    } else {
+      // long list: repeated selection of the next key (O(n^2) list walks, no extra storage)
+      unsigned long long last = 0ull;
+      bool first = true;
+      for (uint32_t i = 0; i < n; i++) {
+        unsigned long long best = ~0ull;
+        uint32_t best_id = 0u;
+        for (uint32_t node = head; node != 0u; node = frags[node - 1u].next) {
+          unsigned long long k = frags[node - 1u].key;
+          if ((first || k > last) && k <= best) { best = k; best_id = node - 1u; }
+        }
+        stored = avg_fold(stored, frags[best_id].val);
+        last = best;
+        first = false;
+      }
+    }
+    base[voxel] = stored;
+    atomicMax(&counters[CNT_MAXLIST], n);
+  }
+}
+
+int ensure_tri_scratch(vct_device* dev, size_t n_tris, size_t rec_bytes) {
+  size_t need = n_tris * rec_bytes;
+  if (need > dev->tri_recs_bytes) {
+    if (dev->tri_recs) cudaFree(dev->tri_recs);
+    dev->tri_recs = nullptr; dev->tri_recs_bytes = 0;
+    size_t want = need + need / 4 + 4096;
+    VCT_CUDA(cudaMalloc(&dev->tri_recs, want));
+    dev->tri_recs_bytes = want;
+  }
+  if (n_tris > dev->item_capacity_tris) {
+    if (dev->item_local) cudaFree(dev->item_local);
+    if (dev->item_block) cudaFree(dev->item_block);
+    dev->item_local = dev->item_block = nullptr; dev->item_capacity_tris = 0;
+    size_t cap = n_tris + n_tris / 4 + 1024;
+    VCT_CUDA(cudaMalloc(&dev->item_local, cap * sizeof(uint32_t)));
+    VCT_CUDA(cudaMalloc(&dev->item_block, (cap / kSetupThreads + 2) * sizeof(uint32_t)));
+    dev->item_capacity_tris = cap;
+  }
+  return VCT_OK;
+}
+
+int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1) {
+  if (sc->n_tris == 0) return VCT_OK;
+  int rc = ensure_tri_scratch(dev, sc->n_tris, sizeof(VoxTri));
+  if (rc) return rc;
+  if (dev->frag_capacity == 0) {
+    rc = vct_voxelize_reserve(dev, 1u << 20);
+    if (rc) return rc;
+  }
+  cudaStream_t s = dev->stream;
+  VCT_CUDA(cudaMemsetAsync(dev->counters, 0, 8 * sizeof(uint32_t), s));
+  const uint32_t n_blocks = (sc->n_tris + kSetupThreads - 1) / kSetupThreads;
+  VoxTri* tris = (VoxTri*)dev->tri_recs;
+  vox_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, sc->cube_size, g->R, tris,
+                                                        dev->item_local, dev->item_block);
+  scan_block_totals_kernel<<<1, 1024, 0, s>>>(dev->item_block, n_blocks, dev->counters + CNT_ITEMS);
+  const int sms = dev->prop.multiProcessorCount;
+  vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->item_local, dev->item_block, n_blocks, sc->mats, sc->lights, sc->cube_size,
+                                            g->R, z0, z1, g->base, dev->frags, (uint32_t)dev->frag_capacity, dev->occupied, dev->counters);
+  vox_resolve_kernel<<<sms * 4, 128, 0, s>>>(g->base, dev->frags, dev->occupied, dev->counters, (uint32_t)dev->frag_capacity);
+  VCT_CUDA(cudaGetLastError());
+  return VCT_OK;
+}
+
+}  // namespace vct
