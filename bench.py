@@ -41,7 +41,7 @@ CONFIGS = {
     5: dict(name="synthetic 4M triangles 1024^3 7680x4320 (RGBA8, 7 levels, 9 cones: reference mode)", R=1024, W=7680, H=4320,
             scene="synthetic", tris=4_000_000, seed=0x5EED0002),
 }
-KERNELS_PER_FRAME = 12  # voxelize 4 (setup, scan, raster, resolve) + mip 2 + gbuffer 5 (clear, setup, scan, raster, resolve) + trace 1
+KERNELS_PER_FRAME = 14  # voxelize 4 (setup, scan, raster, resolve) + mip 2 + gbuffer 5 (clear, setup, scan, raster, resolve) + trace 3 (tile list, cones, shade)
 
 
 def build_scene(cfg, frame: int = 0):
@@ -279,16 +279,16 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
         e2e = {"value": args.steps / dt, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                "ms_per_step": 1e3 * dt / args.steps}
 
-    # ---- roofline of the dominant kernel (cone_trace_kernel) ----
+    # ---- roofline of the dominant kernel (cone_kernel, timed alone with CUDA events on its stream) ----
     peak, peak_src = measured_peaks()
     roof = None
     stages = None
     if world == 1:
         cnt = pipe.trace_count(view, prm)
-        t_trace = stage_acc["trace"] * 1e-3
+        t_trace = stage_acc["cone_kernel"] * 1e-3
         gather_bytes = 192.0 * cnt.samples     # 3 directions x 2 levels x 8 texels x 4 B per sample_voxel
         ach = gather_bytes / t_trace / 1e9
-        roof = {"kernel": "cone_trace_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+        roof = {"kernel": "cone_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": gather_bytes, "samples_per_launch": int(cnt.samples),
                 "gsamples_per_s": cnt.samples / t_trace / 1e9,
                 "note": "algorithmic gather bytes (192 B per sample_voxel) / CUDA-event kernel time; the gathers are served by L1/L2 (pyramid fits L2), "

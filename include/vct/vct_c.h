@@ -64,7 +64,11 @@ typedef struct {
   float view_voxel_lod;
   int32_t n_diffuse_cones; /* 9 = reference (voxel_cone_tracing.frag:153-165); 5 = normal + 4 side cones */
   int32_t tile_rank, tile_nranks; /* this call shades 32x32 screen tiles t with t % tile_nranks == tile_rank */
+  int32_t sampler; /* VCT_SAMPLER_*: how textureLod is evaluated */
 } vct_trace_params_t;
+
+#define VCT_SAMPLER_FP32 0 /* software trilinear + mip-linear with fp32 weights (oracle rule R7) */
+#define VCT_SAMPLER_TEX 1  /* levels >= 1 filtered by the texture units (8-bit weights), level 0 in software */
 
 typedef struct {
   uint64_t fragments;      /* fragments folded into the grid                    */
@@ -138,8 +142,9 @@ int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_targ
                      const vct_trace_params_t* p);
 
 /* per-stage device timings (CUDA events on the device stream) of the last vct_render_frame, in ms:
- * [0] clear [1] voxelize [2] mipmap [3] gbuffer [4] trace [5] total; synchronises */
-int vct_last_frame_timings(vct_device_t* dev, float out_ms[6]);
+ * [0] clear [1] voxelize [2] mipmap [3] gbuffer [4] trace (tile list + cones + shade) [5] total
+ * [6] cone kernel alone [7] reserved; synchronises */
+int vct_last_frame_timings(vct_device_t* dev, float out_ms[8]);
 
 /* ---- texture_3d.h:6-10, one generic RGBA8 3-D texture with a mip chain ---- */
 int vct_tex3d_create(vct_device_t* dev, int width, int height, int depth, int levels, vct_tex3d_t** out); /* create_tex_3d */

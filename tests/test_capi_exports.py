@@ -31,7 +31,7 @@ def test_struct_layouts_match_reference_sizes():
     assert S.LIGHT.itemsize == 28       # point_light_t, renderer.h:87-92
     assert S.MATERIAL.fields["emission"][1] == 64 and S.MATERIAL.fields["shininess"][1] == 76
     assert S.MATERIAL.fields["illum"][1] == 88 and S.MATERIAL.fields["anisotropy_rotation"][1] == 116
-    assert ctypes.sizeof(capi.TraceParams) == 36
+    assert ctypes.sizeof(capi.TraceParams) == 40
 
 
 def test_no_cpu_fallback(gpu_available):

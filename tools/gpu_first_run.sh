@@ -1,7 +1,7 @@
 #!/bin/bash
-# first GPU contact: parity suite + a quick timing of the benchmark frame
+# parity suite + quick timings (development helper)
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -40 > gpurun_out/pytest_gpu.txt
+timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -25 > gpurun_out/pytest_gpu.txt
 cat gpurun_out/pytest_gpu.txt
-timeout 300 python tools/quick_time.py 2>&1 | tee gpurun_out/quick_time.txt
+VCT_SAMPLER=1 timeout 1500 python -m pytest tests -x -q -m gpu -k "frame or tile or determin" 2>&1 | tail -15
+timeout 300 python tools/sampler_experiment.py 2>&1 | tee gpurun_out/sampler.txt

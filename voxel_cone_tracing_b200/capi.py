@@ -33,7 +33,7 @@ class VctError(RuntimeError):
 class TraceParams(C.Structure):
     _fields_ = [("enable_direct", C.c_int32), ("enable_diffuse", C.c_int32), ("enable_specular", C.c_int32), ("enable_shadow", C.c_int32),
                 ("view_voxel_dir", C.c_int32), ("view_voxel_lod", C.c_float), ("n_diffuse_cones", C.c_int32),
-                ("tile_rank", C.c_int32), ("tile_nranks", C.c_int32)]
+                ("tile_rank", C.c_int32), ("tile_nranks", C.c_int32), ("sampler", C.c_int32)]
 
 
 class VoxelStats(C.Structure):
@@ -49,13 +49,15 @@ class TraceStats(C.Structure):
 
 
 def default_params(**kw) -> TraceParams:
-    p = TraceParams(1, 1, 1, 1, 7, 0.0, 9, 0, 1)
+    p = TraceParams(1, 1, 1, 1, 7, 0.0, 9, 0, 1, DEFAULT_SAMPLER)
     for k, v in kw.items():
         setattr(p, k, v)
     return p
 
 
 _lib = None
+SAMPLER_FP32, SAMPLER_TEX = 0, 1
+DEFAULT_SAMPLER = int(os.environ.get("VCT_SAMPLER", "0"))
 
 
 def load():
@@ -263,9 +265,9 @@ class Pipeline:
         check(self.dev.L.vct_render_frame(self.dev.h, self.scene.h, self.grid.h, self.target.h, _f32p(v), _f32p(p), C.byref(params)))
 
     def timings(self) -> dict:
-        t = np.zeros(6, np.float32)
+        t = np.zeros(8, np.float32)
         check(self.dev.L.vct_last_frame_timings(self.dev.h, _f32p(t)))
-        return dict(zip(("clear", "voxelize", "mipmap", "gbuffer", "trace", "total"), [float(x) for x in t]))
+        return dict(zip(("clear", "voxelize", "mipmap", "gbuffer", "trace", "total", "cone_kernel"), [float(x) for x in t[:7]]))
 
     def sync(self): self.dev.sync()
 

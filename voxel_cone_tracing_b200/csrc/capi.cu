@@ -215,6 +215,42 @@ int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) {
     e = cudaMalloc(&g->lvl[l], n * 24);
     g->bytes += n * 24;
   }
+  // levels 1.. additionally live in six mipmapped CUDA arrays so that the cone tracer can use the texture units
+  if (levels >= 2 && e == cudaSuccess) {
+    cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
+    cudaExtent ext = make_cudaExtent((size_t)R / 2, (size_t)R / 2, (size_t)R / 2);
+    for (int d = 0; d < 6 && e == cudaSuccess; d++) {
+      e = cudaMallocMipmappedArray(&g->marr[d], &fmt, ext, (unsigned)(levels - 1), cudaArraySurfaceLoadStore);
+      if (e != cudaSuccess) break;
+      for (int l = 1; l < levels && e == cudaSuccess; l++) {
+        cudaArray_t arr;
+        e = cudaGetMipmappedArrayLevel(&arr, g->marr[d], (unsigned)(l - 1));
+        if (e != cudaSuccess) break;
+        cudaResourceDesc rd;
+        memset(&rd, 0, sizeof rd);
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = arr;
+        e = cudaCreateSurfaceObject(&g->surf.s[d][l], &rd);
+        size_t n = (size_t)(R >> l);
+        g->bytes += n * n * n * 4;
+      }
+      if (e != cudaSuccess) break;
+      cudaResourceDesc rd;
+      memset(&rd, 0, sizeof rd);
+      rd.resType = cudaResourceTypeMipmappedArray;
+      rd.res.mipmap.mipmap = g->marr[d];
+      cudaTextureDesc td;
+      memset(&td, 0, sizeof td);
+      td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;  // CLAMP_TO_BORDER, border (0,0,0,0): texture_3d.cpp:10-12
+      td.filterMode = cudaFilterModeLinear;                                               // GL_LINEAR_MIPMAP_LINEAR: texture_3d.cpp:14
+      td.mipmapFilterMode = cudaFilterModeLinear;
+      td.readMode = cudaReadModeNormalizedFloat;
+      td.normalizedCoords = 1;
+      td.minMipmapLevelClamp = 0.0f;
+      td.maxMipmapLevelClamp = (float)(levels - 2);
+      e = cudaCreateTextureObject(&g->tex[d], &rd, &td, nullptr);
+    }
+  }
   if (e != cudaSuccess) {
     set_error("grid allocation failed: %s", cudaGetErrorString(e));
     vct_grid_destroy(g);
@@ -229,6 +265,11 @@ int vct_grid_destroy(vct_grid_t* g) {
   cudaStreamSynchronize(g->dev->stream);
   cudaFree(g->base);
   for (int l = 0; l < VCT_MAX_LEVELS; l++) cudaFree(g->lvl[l]);
+  for (int d = 0; d < 6; d++) {
+    if (g->tex[d]) cudaDestroyTextureObject(g->tex[d]);
+    for (int l = 0; l < VCT_MAX_LEVELS; l++) if (g->surf.s[d][l]) cudaDestroySurfaceObject(g->surf.s[d][l]);
+    if (g->marr[d]) cudaFreeMipmappedArray(g->marr[d]);
+  }
   delete g;
   return VCT_OK;
 }
@@ -293,6 +334,7 @@ int vct_target_destroy(vct_target_t* t) {
   if (!t) return VCT_OK;
   cudaStreamSynchronize(t->dev->stream);
   cudaFree(t->vis); cudaFree(t->world_pos); cudaFree(t->normal); cudaFree(t->material); cudaFree(t->frame);
+  cudaFree(t->cone_out); cudaFree(t->tile_list);
   delete t;
   return VCT_OK;
 }
@@ -407,12 +449,17 @@ int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_targ
   return VCT_OK;
 }
 
-int vct_last_frame_timings(vct_device_t* dev, float out_ms[6]) {
+int vct_last_frame_timings(vct_device_t* dev, float out_ms[8]) {
   VCT_REQUIRE(dev && out_ms, "null argument");
   VCT_REQUIRE(dev->have_timings, "no frame has been rendered");
   VCT_CUDA(cudaEventSynchronize(dev->ev[5]));
   for (int i = 0; i < 5; i++) VCT_CUDA(cudaEventElapsedTime(&out_ms[i], dev->ev[i], dev->ev[i + 1]));
   VCT_CUDA(cudaEventElapsedTime(&out_ms[5], dev->ev[0], dev->ev[5]));
+  out_ms[6] = out_ms[7] = 0.0f;
+  if (cudaEventQuery(dev->ev[7]) == cudaSuccess && cudaEventElapsedTime(&out_ms[6], dev->ev[6], dev->ev[7]) != cudaSuccess) {
+    out_ms[6] = 0.0f;
+    cudaGetLastError();
+  }
   return VCT_OK;
 }
 

@@ -1,11 +1,14 @@
 // cone_trace.cu -- per-pixel diffuse / specular / shadow / refraction cone tracing over the G-buffer.
 //
 // Replaces shader/voxel_cone_tracing.frag (src/renderer.cpp:355-390 binds it).  Not a port of the
-// fragment shader's one-thread-per-fragment loop: a CTA owns an 8x4 screen tile and runs ONE WARP
-// PER CONE SLOT (9 diffuse, 1 specular, 1 refraction, 1 shadow per light), so all 32 lanes of a warp
-// march the same cone of neighbouring pixels (same aperture, near-identical direction and LOD
-// sequence -> coherent texel gathers, no divergence between cone types).  Cone results meet in
-// shared memory and warp 0 evaluates the Blinn-Phong / mix of main() (voxel_cone_tracing.frag:246-275).
+// fragment shader's one-thread-per-fragment loop.  Three launches:
+//   tile_list_kernel   compacts the 8x4 screen tiles that contain at least one shaded pixel
+//   cone_kernel        ONE WARP = one live tile x one cone slot (9 diffuse, 1 specular, 1 refraction,
+//                      1 shadow per light): all 32 lanes march the same cone of neighbouring pixels
+//                      (same aperture, near-identical direction and LOD sequence -> coherent texel
+//                      gathers, no divergence between cone types).  Warps are independent (no barrier),
+//                      long cones (shadow) are scheduled first, results go to a [slot][pixel] buffer.
+//   shade_kernel       per pixel: Blinn-Phong / mix of main() (voxel_cone_tracing.frag:246-275).
 //
 // Texture sampling is done in software with fp32 weights (rule R7 of the oracle): textureLod =
 // trilinear in floor(lod) and floor(lod)+1, CLAMP_TO_BORDER with a zero border.  Result-preserving
@@ -54,6 +57,10 @@ struct TraceArgs {
   vct_trace_params_t prm;
   unsigned long long* counts;  // [4] diffuse, shadow, specular, refraction (+[4] shaded pixels)
   int n_diffuse, n_slots;
+  const uint32_t* tile_list;   // live 8x4 tiles (tile_y * tiles_x + tile_x), built by tile_list_kernel
+  uint32_t* tile_count;
+  float4* cone_out;            // [slot][pixel] cone results (rgba)
+  size_t npix;
 };
 
 // byte k of a packed RGBA8 word as float (exact), without an I2F conversion
@@ -137,7 +144,21 @@ __device__ __forceinline__ void fetch_level(const GridView& g, int level, F3 pos
 
 // trace_cone (voxel_cone_tracing.frag:88-119).  Returns the number of loop iterations the reference
 // would execute when COUNT is set (no early exit in that build).
-template <bool COUNT>
+// the three directional textureLod fetches of sample_voxel through the texture units:
+//   acc += weight255 * (|d.x| * tex[ix] + |d.y| * tex[iy] + |d.z| * tex[iz])(pos, tex_lod)      (byte units)
+__device__ __forceinline__ void fetch_tex(cudaTextureObject_t tx, cudaTextureObject_t ty, cudaTextureObject_t tz, F3 pos, F3 adir, float tex_lod,
+                                          float weight255, float acc[4]) {
+  const float4 a = tex3DLod<float4>(tx, pos.x, pos.y, pos.z, tex_lod);
+  const float4 b = tex3DLod<float4>(ty, pos.x, pos.y, pos.z, tex_lod);
+  const float4 c = tex3DLod<float4>(tz, pos.x, pos.y, pos.z, tex_lod);
+  const float sx = weight255 * adir.x, sy = weight255 * adir.y, sz = weight255 * adir.z;
+  acc[0] = fmaf(sx, a.x, fmaf(sy, b.x, fmaf(sz, c.x, acc[0])));
+  acc[1] = fmaf(sx, a.y, fmaf(sy, b.y, fmaf(sz, c.y, acc[1])));
+  acc[2] = fmaf(sx, a.z, fmaf(sy, b.z, fmaf(sz, c.z, acc[2])));
+  acc[3] = fmaf(sx, a.w, fmaf(sy, b.w, fmaf(sz, c.w, acc[3])));
+}
+
+template <bool COUNT, bool TEX>
 __device__ __forceinline__ uint32_t trace_cone(const GridView& g, F3 origin, F3 dir, float aperture, float max_dist, float out[4]) {
   dir = normalize(dir);
   const int ix = dir.x < 0.0f ? 0 : 1, iy = dir.y < 0.0f ? 2 : 3, iz = dir.z < 0.0f ? 4 : 5;
@@ -147,6 +168,7 @@ __device__ __forceinline__ uint32_t trace_cone(const GridView& g, F3 origin, F3 
   const float max_level = (float)(g.levels - 1);
   const float margin = 0.5f / (float)(g.R >> (g.levels - 1));  // half a texel of the coarsest level
   float acc[4] = {0.f, 0.f, 0.f, 0.f};  // byte units
+  const cudaTextureObject_t tx = g.tex[ix], ty = g.tex[iy], tz = g.tex[iz];
   float dist = 3.0f * voxel_size;
   float diam = dist * aperture;
   F3 sp = f3(fmaf(dir.x, dist, origin.x), fmaf(dir.y, dist, origin.y), fmaf(dir.z, dist, origin.z));
@@ -164,8 +186,17 @@ __device__ __forceinline__ uint32_t trace_cone(const GridView& g, F3 origin, F3 
     const int l0 = (int)fl;
     const float f = lod - fl;
     float s[4] = {0.f, 0.f, 0.f, 0.f};
-    fetch_level(g, l0, sp, adir, ix, iy, iz, 1.0f - f, s);
-    if (f > 0.0f) fetch_level(g, l0 + 1, sp, adir, ix, iy, iz, f, s);
+    if (TEX) {
+      if (lod < 1.0f) {
+        fetch_level(g, 0, sp, adir, ix, iy, iz, 1.0f - lod, s);                 // level 0 in software (shared by the three directions)
+        if (lod > 0.0f) fetch_tex(tx, ty, tz, sp, adir, 0.0f, 255.0f * lod, s);  // level 1 = array level 0
+      } else {
+        fetch_tex(tx, ty, tz, sp, adir, lod - 1.0f, 255.0f, s);                 // trilinear + mip-linear in the texture unit
+      }
+    } else {
+      fetch_level(g, l0, sp, adir, ix, iy, iz, 1.0f - f, s);
+      if (f > 0.0f) fetch_level(g, l0 + 1, sp, adir, ix, iy, iz, f, s);
+    }
     const float k = 1.0f - acc[3] * (1.0f / 255.0f);
 #pragma unroll
     for (int c = 0; c < 4; c++) acc[c] = fmaf(k, s[c], acc[c]);
@@ -201,47 +232,74 @@ __device__ __forceinline__ uint32_t pack_rgba8(const float v[4]) {
 constexpr float kTan22_5 = 0.55785173935f;
 constexpr float kMaxDistance = 1.73205080757f;
 constexpr uint32_t kBackground = 0xFF404026u;  // (0.15,0.25,0.25,1) -> (38,64,64,255), renderer.cpp:398
-constexpr int kMaxSlots = 9 + 2 + VCT_MAX_POINT_LIGHTS;
+constexpr int kConeWarps = 4;                  // warps (= tiles) per cone_kernel CTA
 
-template <bool COUNT>
-__global__ void __launch_bounds__(32 * kMaxSlots)
-cone_trace_kernel(const TraceArgs a) {
-  __shared__ float res[kMaxSlots][32][4];
-  const int lane = threadIdx.x & 31, slot = threadIdx.x >> 5;
-  const int tiles_x = (a.W + 7) / 8;
-  const int tile_x = blockIdx.x % tiles_x, tile_y = blockIdx.x / tiles_x;
+struct Pixel {
+  size_t pix;
+  uint32_t mat_id;
+  bool in_frame, live;
+  F3 world, normal, pos;
+};
+
+// G-buffer fetch + the within_cube test of main() (voxel_cone_tracing.frag:248-251)
+__device__ __forceinline__ Pixel load_pixel(const TraceArgs& a, int px, int py) {
+  Pixel p;
+  p.in_frame = px < a.W && py < a.H;
+  p.pix = (size_t)py * a.W + px;
+  p.mat_id = p.in_frame ? a.material[p.pix] : VCT_NO_TRIANGLE;
+  p.live = p.mat_id != VCT_NO_TRIANGLE;
+  p.world = f3(0.f, 0.f, 0.f); p.normal = f3(0.f, 0.f, 1.f); p.pos = f3(0.f, 0.f, 0.f);
+  if (p.live) {
+    p.world = f3(a.world_pos[p.pix * 3], a.world_pos[p.pix * 3 + 1], a.world_pos[p.pix * 3 + 2]);
+    p.normal = f3(a.normal[p.pix * 3], a.normal[p.pix * 3 + 1], a.normal[p.pix * 3 + 2]);
+    p.pos = f3(0.5f * (p.world.x / a.cube_size) + 0.5f, 0.5f * (p.world.y / a.cube_size) + 0.5f, 0.5f * (p.world.z / a.cube_size) + 0.5f);
+    p.live = fabsf(p.pos.x) < 1.0f && fabsf(p.pos.y) < 1.0f && fabsf(p.pos.z) < 1.0f;
+  }
+  return p;
+}
+
+__device__ __forceinline__ bool tile_is_mine(const TraceArgs& a, int tile_x, int tile_y) {
   // multi-GPU split: 32x32 screen tiles are dealt round-robin to ranks
-  if (a.prm.tile_nranks > 1) {
-    const int t32 = (tile_y / 8) * ((a.W + 31) / 32) + (tile_x / 4);
-    if (t32 % a.prm.tile_nranks != a.prm.tile_rank) return;
-  }
-  const int px = tile_x * 8 + (lane & 7), py = tile_y * 4 + (lane >> 3);
-  const bool in_frame = px < a.W && py < a.H;
-  const size_t pix = (size_t)py * a.W + px;
-  const uint32_t mat_id = in_frame ? a.material[pix] : VCT_NO_TRIANGLE;
-  bool live = mat_id != VCT_NO_TRIANGLE;
-  F3 world = f3(0.f, 0.f, 0.f), normal = f3(0.f, 0.f, 1.f), pos = f3(0.f, 0.f, 0.f);
-  if (live) {
-    world = f3(a.world_pos[pix * 3], a.world_pos[pix * 3 + 1], a.world_pos[pix * 3 + 2]);
-    normal = f3(a.normal[pix * 3], a.normal[pix * 3 + 1], a.normal[pix * 3 + 2]);
-    pos = f3(0.5f * (world.x / a.cube_size) + 0.5f, 0.5f * (world.y / a.cube_size) + 0.5f, 0.5f * (world.z / a.cube_size) + 0.5f);
-    // main(): fragments outside the cube return before writing (voxel_cone_tracing.frag:250-251)
-    live = fabsf(pos.x) < 1.0f && fabsf(pos.y) < 1.0f && fabsf(pos.z) < 1.0f;
-  }
-  if (!__syncthreads_or((int)live)) {
-    if (slot == 0 && in_frame) a.frame[pix] = kBackground;
-    return;
-  }
-  const vct_material_t* m = live ? a.mats + mat_id : a.mats;
-  const F3 cam = f3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]);
-  const int nd = a.n_diffuse;
-  const bool debug_view = a.prm.view_voxel_dir < 7;
+  if (a.prm.tile_nranks <= 1) return true;
+  const int t32 = (tile_y / 8) * ((a.W + 31) / 32) + (tile_x / 4);
+  return t32 % a.prm.tile_nranks == a.prm.tile_rank;
+}
 
-  // ---------------- one cone per warp ----------------
+// one warp per 8x4 tile: append the tile if any of its pixels is shaded
+__global__ void __launch_bounds__(256)
+tile_list_kernel(const TraceArgs a, uint32_t* __restrict__ tile_list, uint32_t* __restrict__ tile_count) {
+  const int lane = threadIdx.x & 31;
+  const int tiles_x = (a.W + 7) / 8, tiles_y = (a.H + 3) / 4;
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tile >= tiles_x * tiles_y) return;
+  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+  if (!tile_is_mine(a, tile_x, tile_y)) return;
+  const Pixel p = load_pixel(a, tile_x * 8 + (lane & 7), tile_y * 4 + (lane >> 3));
+  const uint32_t any = __ballot_sync(0xffffffffu, p.live);
+  if (any && lane == 0) tile_list[atomicAdd(tile_count, 1u)] = (uint32_t)tile;
+}
+
+template <bool COUNT, bool TEX>
+__global__ void __launch_bounds__(32 * kConeWarps)
+cone_kernel(const TraceArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t t = blockIdx.x * kConeWarps + (threadIdx.x >> 5);
+  if (t >= *a.tile_count) return;
+  // long cones first: blockIdx.y = 0 is the last slot (shadow cones, up to ~5x more steps than diffuse)
+  const int slot = a.n_slots - 1 - (int)blockIdx.y;
+  const int nd = a.n_diffuse;
+  const uint32_t tile = a.tile_list[t];
+  const int tiles_x = (a.W + 7) / 8;
+  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+  const Pixel p = load_pixel(a, tile_x * 8 + (lane & 7), tile_y * 4 + (lane >> 3));
+  const vct_material_t* m = p.live ? a.mats + p.mat_id : a.mats;
+  const F3 cam = f3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]);
+  const F3 normal = p.normal, pos = p.pos;
+
   float r[4] = {0.f, 0.f, 0.f, 0.f};
   uint32_t iters = 0;
   int kind = -1;  // 0 diffuse, 1 shadow, 2 specular, 3 refraction
-  if (live && !debug_view) {
+  if (p.live) {
     if (slot < nd) {
       if (a.prm.enable_diffuse) {
         const F3 o1 = normalize(tangent(normal));
@@ -258,22 +316,22 @@ cone_trace_kernel(const TraceArgs a) {
           case 7: d = mix(normal, (o1 - o2) * 0.5f, 0.5f); break;
           default: d = mix(normal, -((o1 - o2) * 0.5f), 0.5f); break;
         }
-        iters = trace_cone<COUNT>(a.grid, pos, d, kTan22_5, kMaxDistance, r);
+        iters = trace_cone<COUNT, TEX>(a.grid, pos, d, kTan22_5, kMaxDistance, r);
         kind = 0;
       }
     } else if (slot == nd) {
       if (a.prm.enable_specular) {
-        const F3 view_dir = normalize(world - cam);
+        const F3 view_dir = normalize(p.world - cam);
         const F3 sd = normalize(reflect(-view_dir, normal));
-        iters = trace_cone<COUNT>(a.grid, pos, sd, specular_aperture(m->shininess), kMaxDistance, r);
+        iters = trace_cone<COUNT, TEX>(a.grid, pos, sd, specular_aperture(m->shininess), kMaxDistance, r);
         kind = 2;
       }
     } else if (slot == nd + 1) {
       const bool transmissive = m->illum == 4 || m->illum == 6 || m->illum == 7 || m->illum == 9;
       if (transmissive && a.prm.enable_specular) {
-        const F3 view_dir = normalize(world - cam);
+        const F3 view_dir = normalize(p.world - cam);
         const F3 rd = refract(view_dir, normal, 1.0f / m->ior);
-        iters = trace_cone<COUNT>(a.grid, pos, rd, specular_aperture(m->shininess), kMaxDistance, r);
+        iters = trace_cone<COUNT, TEX>(a.grid, pos, rd, specular_aperture(m->shininess), kMaxDistance, r);
         kind = 3;
       }
     } else {
@@ -285,14 +343,13 @@ cone_trace_kernel(const TraceArgs a) {
         F3 ld = lp - pos;
         const float d = length(ld);
         ld = f3(ld.x / d, ld.y / d, ld.z / d);
-        iters = trace_cone<COUNT>(a.grid, pos, ld, 0.1f, d, r);
+        iters = trace_cone<COUNT, TEX>(a.grid, pos, ld, 0.1f, d, r);
         kind = 1;
       }
     }
+    a.cone_out[(size_t)slot * a.npix + p.pix] = make_float4(r[0], r[1], r[2], r[3]);
   }
-  res[slot][lane][0] = r[0]; res[slot][lane][1] = r[1]; res[slot][lane][2] = r[2]; res[slot][lane][3] = r[3];
   if (COUNT) {
-    // per-warp totals; kind is warp-uniform except for dead lanes
     uint32_t it = iters;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) it += __shfl_xor_sync(0xffffffffu, it, o);
@@ -301,17 +358,29 @@ cone_trace_kernel(const TraceArgs a) {
     for (int o = 16; o > 0; o >>= 1) kk = max(kk, __shfl_xor_sync(0xffffffffu, kk, o));
     if (lane == 0 && kk >= 0) atomicAdd(&a.counts[kk], (unsigned long long)it);
     if (slot == 0) {
-      uint32_t ball = __ballot_sync(0xffffffffu, live);
+      const uint32_t ball = __ballot_sync(0xffffffffu, p.live);
       if (lane == 0) atomicAdd(&a.counts[4], (unsigned long long)__popc(ball));
     }
   }
-  __syncthreads();
-  if (slot != 0 || !in_frame) return;
+}
 
-  // ---------------- main() (voxel_cone_tracing.frag:246-275) ----------------
-  if (!live) { a.frame[pix] = kBackground; return; }
+// main() (voxel_cone_tracing.frag:246-275): one thread per pixel
+__global__ void __launch_bounds__(256)
+shade_kernel(const TraceArgs a) {
+  const int tiles_x = (a.W + 7) / 8;
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+  if (tile_y * 4 >= a.H) return;
+  if (!tile_is_mine(a, tile_x, tile_y)) return;
+  const Pixel p = load_pixel(a, tile_x * 8 + (lane & 7), tile_y * 4 + (lane >> 3));
+  if (!p.in_frame) return;
+  if (!p.live) { a.frame[p.pix] = kBackground; return; }
+  const vct_material_t* m = a.mats + p.mat_id;
+  const F3 normal = p.normal, pos = p.pos;
+  const int nd = a.n_diffuse;
   float out[4];
-  if (debug_view) {
+  if (a.prm.view_voxel_dir < 7) {
     // textureLod(tex3D[view_voxel_dir], pos, view_voxel_lod), blended over the clear colour
     const int d = a.prm.view_voxel_dir;
     float t[4] = {0.f, 0.f, 0.f, 0.f};
@@ -319,8 +388,7 @@ cone_trace_kernel(const TraceArgs a) {
       float lod = fminf(fmaxf(a.prm.view_voxel_lod, 0.0f), (float)(a.grid.levels - 1));
       const float fl = floorf(lod), f = lod - fl;
       const int l0 = (int)fl;
-      // a unit weight on direction d only
-      F3 ad = f3(d < 2 ? 1.f : 0.f, (d == 2 || d == 3) ? 1.f : 0.f, d >= 4 ? 1.f : 0.f);
+      const F3 ad = f3(d < 2 ? 1.f : 0.f, (d == 2 || d == 3) ? 1.f : 0.f, d >= 4 ? 1.f : 0.f);  // unit weight on direction d only
       const int ix = d < 2 ? d : 0, iy = (d == 2 || d == 3) ? d : 2, iz = d >= 4 ? d : 4;
       fetch_level(a.grid, l0, pos, ad, ix, iy, iz, 1.0f - f, t);
       if (f > 0.0f) fetch_level(a.grid, l0 + 1, pos, ad, ix, iy, iz, f, t);
@@ -329,18 +397,21 @@ cone_trace_kernel(const TraceArgs a) {
     const float al = t[3] * (1.0f / 255.0f);
 #pragma unroll
     for (int k = 0; k < 4; k++) out[k] = (t[k] * (1.0f / 255.0f)) * al + bg[k] * (1.0f - al);
-    a.frame[pix] = pack_rgba8(out);
+    a.frame[p.pix] = pack_rgba8(out);
     return;
   }
-  const F3 view_dir = normalize(world - cam);
+  const F3 cam = f3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]);
+  const F3 view_dir = normalize(p.world - cam);
   const F3 kd = f3(m->diffuse[0], m->diffuse[1], m->diffuse[2]);
   const F3 ks = f3(m->specular[0], m->specular[1], m->specular[2]);
   F3 fdiff = f3(0.f, 0.f, 0.f), fdir = f3(0.f, 0.f, 0.f), fspec = f3(0.f, 0.f, 0.f);
   if (a.prm.enable_diffuse) {
     F3 s = f3(0.f, 0.f, 0.f);
-    for (int i = 0; i < nd; i++) s = s + f3(res[i][lane][0], res[i][lane][1], res[i][lane][2]);
-    const float inv = 1.0f / (float)nd;
-    fdiff = kd * (s * inv);
+    for (int i = 0; i < nd; i++) {
+      const float4 c = a.cone_out[(size_t)i * a.npix + p.pix];
+      s = s + f3(c.x, c.y, c.z);
+    }
+    fdiff = kd * (s * (1.0f / (float)nd));
   }
   if (a.prm.enable_direct) {  // direct_light(), voxel_cone_tracing.frag:175-218
     F3 result = f3(0.f, 0.f, 0.f);
@@ -355,7 +426,7 @@ cone_trace_kernel(const TraceArgs a) {
       const float att = 1.0f / (1.0f + d * d);
       const F3 light_color = f3(L.color[0], L.color[1], L.color[2]) * (att * cos_surf) * L.intensity;
       float shadow_level = 1.0f;
-      if (a.prm.enable_shadow) shadow_level = fmaxf(0.0f, 1.0f - res[nd + 2 + i][lane][3]);
+      if (a.prm.enable_shadow) shadow_level = fmaxf(0.0f, 1.0f - a.cone_out[(size_t)(nd + 2 + i) * a.npix + p.pix].w);
       const float lambertian = fmaxf(dot(ld, normal), 0.0f);
       float refract_angle = 0.0f;
       if (m->dissolve <= 0.1f) {
@@ -371,16 +442,19 @@ cone_trace_kernel(const TraceArgs a) {
     }
     fdir = result + f3(clamp01(m->emission[0]), clamp01(m->emission[1]), clamp01(m->emission[2]));
   }
-  if (a.prm.enable_specular) fspec = ks * f3(res[nd][lane][0], res[nd][lane][1], res[nd][lane][2]);
+  if (a.prm.enable_specular) {
+    const float4 c = a.cone_out[(size_t)nd * a.npix + p.pix];
+    fspec = ks * f3(c.x, c.y, c.z);
+  }
   F3 rgb = (fspec + fdiff) + fdir;
   const bool transmissive = m->illum == 4 || m->illum == 6 || m->illum == 7 || m->illum == 9;
   if (transmissive && a.prm.enable_specular) {
-    const F3 rr = f3(m->transmittance[0], m->transmittance[1], m->transmittance[2]) *
-                  f3(res[nd + 1][lane][0], res[nd + 1][lane][1], res[nd + 1][lane][2]);
+    const float4 c = a.cone_out[(size_t)(nd + 1) * a.npix + p.pix];
+    const F3 rr = f3(m->transmittance[0], m->transmittance[1], m->transmittance[2]) * f3(c.x, c.y, c.z);
     rgb = mix(rr, rgb, m->dissolve);
   }
   out[0] = rgb.x; out[1] = rgb.y; out[2] = rgb.z; out[3] = 1.0f;
-  a.frame[pix] = pack_rgba8(out);
+  a.frame[p.pix] = pack_rgba8(out);
 }
 
 int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* view, const vct_trace_params_t* p, vct_target_t_* t,
@@ -399,14 +473,42 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
   a.counts = (unsigned long long*)(dev->counters + 16);
   a.n_diffuse = p->n_diffuse_cones == 5 ? 5 : 9;
   a.n_slots = a.n_diffuse + 2 + sc->lights.n;
-  const int tiles = ((t->W + 7) / 8) * ((t->H + 3) / 4);
-  cudaStream_t s = dev->stream;
-  if (count_samples) {
-    VCT_CUDA(cudaMemsetAsync(dev->counters + 16, 0, 8 * sizeof(unsigned long long), s));
-    cone_trace_kernel<true><<<tiles, 32 * a.n_slots, 0, s>>>(a);
-  } else {
-    cone_trace_kernel<false><<<tiles, 32 * a.n_slots, 0, s>>>(a);
+  a.npix = (size_t)t->W * t->H;
+  const int n_tiles = ((t->W + 7) / 8) * ((t->H + 3) / 4);
+  // cone result buffer [slot][pixel] and the live-tile list, grown on demand
+  const size_t need = (size_t)a.n_slots * a.npix;
+  if (need > t->cone_out_elems) {
+    VCT_CUDA(cudaStreamSynchronize(dev->stream));
+    cudaFree(t->cone_out);
+    t->cone_out = nullptr; t->cone_out_elems = 0;
+    VCT_CUDA(cudaMalloc(&t->cone_out, need * sizeof(float4)));
+    t->cone_out_elems = need;
   }
+  if (!t->tile_list) {
+    VCT_CUDA(cudaMalloc(&t->tile_list, ((size_t)n_tiles + 1) * sizeof(uint32_t)));
+  }
+  a.tile_list = t->tile_list + 1;
+  a.tile_count = t->tile_list;
+  a.cone_out = (float4*)t->cone_out;
+  cudaStream_t s = dev->stream;
+  const bool debug_view = p->view_voxel_dir < 7;
+  if (!debug_view) {
+    VCT_CUDA(cudaMemsetAsync(t->tile_list, 0, sizeof(uint32_t), s));
+    tile_list_kernel<<<(n_tiles + 7) / 8, 256, 0, s>>>(a, t->tile_list + 1, t->tile_list);
+    const dim3 grid((n_tiles + kConeWarps - 1) / kConeWarps, a.n_slots);
+    const bool tex = p->sampler == VCT_SAMPLER_TEX && g->levels >= 2;
+    VCT_CUDA(cudaEventRecord(dev->ev[6], s));
+    if (count_samples) {
+      VCT_CUDA(cudaMemsetAsync(dev->counters + 16, 0, 8 * sizeof(unsigned long long), s));
+      cone_kernel<true, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
+    } else if (tex) {
+      cone_kernel<false, true><<<grid, 32 * kConeWarps, 0, s>>>(a);
+    } else {
+      cone_kernel<false, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
+    }
+    VCT_CUDA(cudaEventRecord(dev->ev[7], s));
+  }
+  shade_kernel<<<(n_tiles + 7) / 8, 256, 0, s>>>(a);
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;
 }

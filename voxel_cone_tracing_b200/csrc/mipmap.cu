@@ -81,7 +81,7 @@ __device__ __forceinline__ constexpr int child_id(int dx, int dy, int dz) { retu
 
 // ---------------------------------------------------------------------------------------------
 // generic fallback: one thread per (destination texel, direction)
-__global__ void mip_generic_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int Ns, int Nd, int src_is_base) {
+__global__ void mip_generic_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int Ns, int Nd, int src_is_base, SurfSet surf, int dst_level) {
   const size_t n = (size_t)Nd * Nd * Nd * 6;
   for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < n; u += (size_t)gridDim.x * blockDim.x) {
     const int d = (int)(u % 6);
@@ -100,7 +100,9 @@ __global__ void mip_generic_kernel(const uint32_t* __restrict__ src, uint32_t* _
           any |= w;
           unpack4(w, c[child_id(dx, dy, dz)]);
         }
-    dst[u] = any ? filter_dir_dyn(c, d) : 0u;
+    const uint32_t o = any ? filter_dir_dyn(c, d) : 0u;
+    dst[u] = o;
+    surf3Dwrite(o, surf.s[d][dst_level], x * 4, y, z);
   }
 }
 
@@ -109,7 +111,7 @@ __global__ void mip_generic_kernel(const uint32_t* __restrict__ src, uint32_t* _
 constexpr int TX = 32, TY = 8, TZ = 8;
 
 __global__ void __launch_bounds__(256)
-mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l1, uint32_t* __restrict__ l2, uint32_t* __restrict__ l3, int R) {
+mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l1, uint32_t* __restrict__ l2, uint32_t* __restrict__ l3, int R, const SurfSet surf) {
   __shared__ __align__(16) uint32_t s0[TZ][TY][TX];           // 8 KB
   __shared__ uint32_t s1[TZ / 2][TY / 2][TX / 2][6];          // 6 KB
   __shared__ uint32_t s2[TZ / 4][TY / 4][TX / 4][6];          // 768 B
@@ -137,14 +139,18 @@ mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l
       const int x = t & 15, y = (t >> 4) & 3, z = t >> 6;
       uint2* o = reinterpret_cast<uint2*>(l1 + (((size_t)(z0 / 2 + z) * N1 + (y0 / 2 + y)) * N1 + (x0 / 2 + x)) * 6);
       o[0] = make_uint2(0u, 0u); o[1] = make_uint2(0u, 0u); o[2] = make_uint2(0u, 0u);
+#pragma unroll
+      for (int d = 0; d < 6; d++) surf3Dwrite(0u, surf.s[d][1], (x0 / 2 + x) * 4, y0 / 2 + y, z0 / 2 + z);
     }
     if (t < 192) {
       const int d = t % 6, tex = t / 6, x = tex & 7, y = (tex >> 3) & 1, z = tex >> 4;
       l2[(((size_t)(z0 / 4 + z) * N2 + (y0 / 4 + y)) * N2 + (x0 / 4 + x)) * 6 + d] = 0u;
+      surf3Dwrite(0u, surf.s[d][2], (x0 / 4 + x) * 4, y0 / 4 + y, z0 / 4 + z);
     }
     if (t < 24) {
       const int d = t % 6, x = t / 6;
       l3[(((size_t)(z0 / 8) * N3 + (y0 / 8)) * N3 + (x0 / 8 + x)) * 6 + d] = 0u;
+      surf3Dwrite(0u, surf.s[d][3], (x0 / 8 + x) * 4, y0 / 8, z0 / 8);
     }
     return;
   }
@@ -174,7 +180,10 @@ mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l
     uint2* g = reinterpret_cast<uint2*>(l1 + (((size_t)(z0 / 2 + z) * N1 + (y0 / 2 + y)) * N1 + (x0 / 2 + x)) * 6);
     g[0] = make_uint2(o[0], o[1]); g[1] = make_uint2(o[2], o[3]); g[2] = make_uint2(o[4], o[5]);
 #pragma unroll
-    for (int d = 0; d < 6; d++) s1[z][y][x][d] = o[d];
+    for (int d = 0; d < 6; d++) {
+      s1[z][y][x][d] = o[d];
+      surf3Dwrite(o[d], surf.s[d][1], (x0 / 2 + x) * 4, y0 / 2 + y, z0 / 2 + z);
+    }
   }
   __syncthreads();
 
@@ -195,6 +204,7 @@ mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l
         }
     const uint32_t o = any ? filter_dir_dyn(c, d) : 0u;
     l2[(((size_t)(z0 / 4 + z) * N2 + (y0 / 4 + y)) * N2 + (x0 / 4 + x)) * 6 + d] = o;
+    surf3Dwrite(o, surf.s[d][2], (x0 / 4 + x) * 4, y0 / 4 + y, z0 / 4 + z);
     s2[z][y][x][d] = o;
   }
   __syncthreads();
@@ -214,14 +224,16 @@ mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l
           any |= w;
           unpack4(w, c[child_id(dx, dy, dz)]);
         }
-    l3[(((size_t)(z0 / 8) * N3 + (y0 / 8)) * N3 + (x0 / 8 + x)) * 6 + d] = any ? filter_dir_dyn(c, d) : 0u;
+    const uint32_t o = any ? filter_dir_dyn(c, d) : 0u;
+    l3[(((size_t)(z0 / 8) * N3 + (y0 / 8)) * N3 + (x0 / 8 + x)) * 6 + d] = o;
+    surf3Dwrite(o, surf.s[d][3], (x0 / 8 + x) * 4, y0 / 8, z0 / 8);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
 // fused levels 3 -> 4,5,6.  Tile = 8^3 level-3 records, 256 threads.
 __global__ void __launch_bounds__(256)
-mip_fused_high_kernel(const uint32_t* __restrict__ l3, uint32_t* __restrict__ l4, uint32_t* __restrict__ l5, uint32_t* __restrict__ l6, int N3) {
+mip_fused_high_kernel(const uint32_t* __restrict__ l3, uint32_t* __restrict__ l4, uint32_t* __restrict__ l5, uint32_t* __restrict__ l6, int N3, const SurfSet surf) {
   __shared__ uint32_t s3[8][8][8][6];  // 12 KB
   __shared__ uint32_t s4[4][4][4][6];
   __shared__ uint32_t s5[2][2][2][6];
@@ -251,6 +263,7 @@ mip_fused_high_kernel(const uint32_t* __restrict__ l3, uint32_t* __restrict__ l4
         }
     const uint32_t o = any ? filter_dir_dyn(c, d) : 0u;
     l4[(((size_t)(bz * 4 + z) * N4 + (by * 4 + y)) * N4 + (bx * 4 + x)) * 6 + d] = o;
+    surf3Dwrite(o, surf.s[d][4], (bx * 4 + x) * 4, by * 4 + y, bz * 4 + z);
     s4[z][y][x][d] = o;
   }
   __syncthreads();
@@ -270,6 +283,7 @@ mip_fused_high_kernel(const uint32_t* __restrict__ l3, uint32_t* __restrict__ l4
         }
     const uint32_t o = any ? filter_dir_dyn(c, d) : 0u;
     l5[(((size_t)(bz * 2 + z) * N5 + (by * 2 + y)) * N5 + (bx * 2 + x)) * 6 + d] = o;
+    surf3Dwrite(o, surf.s[d][5], (bx * 2 + x) * 4, by * 2 + y, bz * 2 + z);
     s5[z][y][x][d] = o;
   }
   __syncthreads();
@@ -287,7 +301,9 @@ mip_fused_high_kernel(const uint32_t* __restrict__ l3, uint32_t* __restrict__ l4
           any |= w;
           unpack4(w, c[child_id(dx, dy, dz)]);
         }
-    l6[(((size_t)bz * N6 + by) * N6 + bx) * 6 + d] = any ? filter_dir_dyn(c, d) : 0u;
+    const uint32_t o = any ? filter_dir_dyn(c, d) : 0u;
+    l6[(((size_t)bz * N6 + by) * N6 + bx) * 6 + d] = o;
+    surf3Dwrite(o, surf.s[d][6], bx * 4, by, bz);
   }
 }
 
@@ -297,11 +313,11 @@ int launch_mipmap(vct_device* dev, vct_grid* g) {
   int level = 0;  // highest level already built
   if (g->levels >= 4 && R % 32 == 0 && R >= 32) {
     const int n_tiles = (R / TX) * (R / TY) * (R / TZ);
-    mip_fused_low_kernel<<<n_tiles, 256, 0, s>>>(g->base, g->lvl[1], g->lvl[2], g->lvl[3], R);
+    mip_fused_low_kernel<<<n_tiles, 256, 0, s>>>(g->base, g->lvl[1], g->lvl[2], g->lvl[3], R, g->surf);
     level = 3;
     if (g->levels >= 7 && (R >> 3) % 8 == 0) {
       const int tiles = (R >> 3) / 8;
-      mip_fused_high_kernel<<<tiles * tiles * tiles, 256, 0, s>>>(g->lvl[3], g->lvl[4], g->lvl[5], g->lvl[6], R >> 3);
+      mip_fused_high_kernel<<<tiles * tiles * tiles, 256, 0, s>>>(g->lvl[3], g->lvl[4], g->lvl[5], g->lvl[6], R >> 3, g->surf);
       level = 6;
     }
   }
@@ -310,7 +326,7 @@ int launch_mipmap(vct_device* dev, vct_grid* g) {
     if (Nd < 1) break;
     const size_t n = (size_t)Nd * Nd * Nd * 6;
     const int blocks = (int)grid_for(n);
-    mip_generic_kernel<<<blocks, 256, 0, s>>>(l == 0 ? g->base : g->lvl[l], g->lvl[l + 1], Ns, Nd, l == 0);
+    mip_generic_kernel<<<blocks, 256, 0, s>>>(l == 0 ? g->base : g->lvl[l], g->lvl[l + 1], Ns, Nd, l == 0, g->surf, l + 1);
   }
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;

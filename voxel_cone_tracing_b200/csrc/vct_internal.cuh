@@ -88,7 +88,13 @@ struct Lights {
 struct GridView {
   uint32_t* base;                 // level 0: R^3 u32, [z][y][x]
   uint32_t* lvl[VCT_MAX_LEVELS];  // level l >= 1: (R>>l)^3 records of 6 u32 (direction-minor)
+  cudaTextureObject_t tex[6];     // per direction: mipmapped 3-D RGBA8 texture of levels 1.. (array level k = grid level k+1)
   int R, levels;
+};
+
+// surface handles of the per-direction mipmapped arrays: s[dir][grid level], level >= 1
+struct SurfSet {
+  cudaSurfaceObject_t s[6][VCT_MAX_LEVELS];
 };
 
 }  // namespace vct
@@ -134,10 +140,15 @@ struct vct_grid {
   uint32_t* base = nullptr;
   uint32_t* lvl[VCT_MAX_LEVELS] = {};
   size_t bytes = 0;
+  // hardware-filtered copy of levels 1.. (written by the mip kernels through surfaces)
+  cudaMipmappedArray_t marr[6] = {};
+  cudaTextureObject_t tex[6] = {};
+  vct::SurfSet surf{};
   vct::GridView view() const {
     vct::GridView v;
     v.base = base; v.R = R; v.levels = levels;
     for (int i = 0; i < VCT_MAX_LEVELS; i++) v.lvl[i] = lvl[i];
+    for (int d = 0; d < 6; d++) v.tex[d] = tex[d];
     return v;
   }
 };
@@ -150,6 +161,9 @@ struct vct_target_t_ {
   float* normal = nullptr;            // 3 floats / pixel (interpolated, NOT renormalised)
   uint32_t* material = nullptr;
   uint32_t* frame = nullptr;          // RGBA8
+  void* cone_out = nullptr;           // float4 [slot][pixel], grown on demand by the cone tracer
+  size_t cone_out_elems = 0;
+  uint32_t* tile_list = nullptr;      // [0] = count, [1..] = live 8x4 tiles
 };
 
 struct vct_tex3d {
