@@ -54,6 +54,40 @@ def test_mip_random_grid_bit_exact(dev, R, levels, density):
     g.close()
 
 
+def _expected_occupancy(pyr: orc.Pyramid, level: int):
+    occ = np.zeros_like(pyr.levels[0][level], dtype=bool)
+    for d in range(6):
+        occ |= pyr.levels[d][level] != 0
+    n = occ.shape[0]
+    pad = np.zeros((n + 2,) * 3, bool)
+    pad[1:-1, 1:-1, 1:-1] = occ
+    dil = np.zeros((n + 1,) * 3, bool)
+    for dz in (0, 1):
+        for dy in (0, 1):
+            for dx in (0, 1):
+                dil |= pad[dz:dz + n + 1, dy:dy + n + 1, dx:dx + n + 1]
+    return occ, dil
+
+
+@pytest.mark.parametrize("R,levels,density", [(128, 7, 0.001), (64, 7, 0.01), (32, 6, 0.05), (16, 5, 0.02), (64, 3, 0.3)])
+def test_occupancy_masks_match_pyramid(dev, R, levels, density):
+    """the zero-footprint skip of the cone tracer is only exact if the masks are: bit set <=> some texel of the footprint is non-zero"""
+    rng = np.random.default_rng(7)
+    base = rng.integers(0, 2 ** 32, (R, R, R), dtype=np.uint64).astype(np.uint32)
+    base[rng.random((R, R, R)) > density] = 0
+    base[R - 1, R - 1, R - 1] = 0x01010101   # corner texel: value that filters to zero at coarser levels
+    base[0, 0, 0] = 0xFFFFFFFF
+    g = capi.Grid(dev, R, levels)
+    g.upload_base(base)
+    capi.check(dev.L.vct_mipmap(dev.h, g.h))
+    pyr = orc.mipmap(base, levels)
+    for l in range(levels):
+        occ, dil = _expected_occupancy(pyr, l)
+        assert np.array_equal(g.occupancy(l, False), occ), f"level {l} occupancy"
+        assert np.array_equal(g.occupancy(l, True), dil), f"level {l} dilated occupancy"
+    g.close()
+
+
 def test_mip_empty_grid(dev):
     g = capi.Grid(dev, 64, 7)
     g.upload_base(np.full((64, 64, 64), 0xFFFFFFFF, np.uint32))
@@ -163,14 +197,18 @@ def test_gbuffer_matches_oracle(W, H, suzanne):
 
 
 # --------------------------------------------------------------------------- full frame
-def _frame_pair(sc, R, W, H, params_kw=None, levels=7):
+SAMPLERS = [capi.SAMPLER_FP32, capi.SAMPLER_TEX]   # software fp32 filtering / texture units: both must pass the frame gate
+
+
+def _frame_pair(sc, R, W, H, params_kw=None, levels=7, sampler=capi.SAMPLER_FP32, camera=None):
     params_kw = params_kw or {}
-    view, proj = S.reference_camera(W / H)
+    view, proj = S.reference_camera(W / H, **(camera or {}))
     ref = orc.render_frame(sc, view, proj, R, W, H, orc.default_params(**params_kw), levels)
     p = capi.Pipeline(sc, R, W, H, levels)
-    p.render_frame(view, proj, capi.default_params(**params_kw))
+    prm = capi.default_params(sampler=sampler, **params_kw)
+    p.render_frame(view, proj, prm)
     got = p.target.frame()
-    cnt = p.trace_count(view, capi.default_params(**params_kw))
+    cnt = p.trace_count(view, prm)
     p.close()
     return got, ref, cnt
 
@@ -181,9 +219,10 @@ def _check_frame(got, ref):
     assert psnr(got, exp) >= FRAME_MIN_PSNR, f"PSNR {psnr(got, exp):.2f} dB"
 
 
-def test_frame_config1_cornell_128_512():
+@pytest.mark.parametrize("sampler", SAMPLERS)
+def test_frame_config1_cornell_128_512(sampler):
     """BASELINE config 1: CornellBox-Glossy, 128^3, 512x512, 9 diffuse + 1 specular + 1 shadow cone."""
-    got, ref, cnt = _frame_pair(S.cornell_scene(), 128, 512, 512)
+    got, ref, cnt = _frame_pair(S.cornell_scene(), 128, 512, 512, sampler=sampler)
     _check_frame(got, ref)
     ts = ref["trace_stats"]
     assert cnt.shaded_pixels == ts.shaded_pixels
@@ -192,22 +231,33 @@ def test_frame_config1_cornell_128_512():
         assert abs(a - b) <= 5e-2 * max(b, 1), (k, a, b)   # alpha == 1.0 rounding may flip a loop exit by one (invisible) sample
 
 
-def test_frame_with_suzanne_refraction():
-    got, ref, cnt = _frame_pair(S.cornell_scene(with_suzanne=True), 128, 400, 300)
+@pytest.mark.parametrize("sampler", SAMPLERS)
+def test_frame_with_suzanne_refraction(sampler):
+    got, ref, cnt = _frame_pair(S.cornell_scene(with_suzanne=True), 128, 400, 300, sampler=sampler)
     _check_frame(got, ref)
     assert cnt.samples_refraction > 0
 
 
-@pytest.mark.parametrize("kw", [dict(n_diffuse_cones=5), dict(enable_shadow=0), dict(enable_diffuse=0, enable_specular=0),
-                                dict(enable_direct=0), dict(view_voxel_dir=1, view_voxel_lod=1.5), dict(view_voxel_dir=4, view_voxel_lod=0.0)])
-def test_frame_variants(kw):
-    got, ref, _ = _frame_pair(S.cornell_scene(with_suzanne=True), 64, 256, 192, kw)
+@pytest.mark.parametrize("sampler", SAMPLERS)
+@pytest.mark.parametrize("camera", [dict(eye=(0.6, 1.3, 2.2), pitch=-12.0, yaw=-105.0), dict(eye=(-0.5, 0.4, 1.5), pitch=15.0, yaw=-70.0)])
+def test_frame_other_cameras(sampler, camera):
+    """camera poses other than main.cpp's default (close to walls / the glossy sphere, grazing angles)"""
+    got, ref, _ = _frame_pair(S.cornell_scene(with_suzanne=True, theta=0.7), 128, 480, 270, sampler=sampler, camera=camera)
     _check_frame(got, ref)
 
 
-def test_frame_config2_cornell_256_1080p():
+@pytest.mark.parametrize("kw", [dict(n_diffuse_cones=5), dict(enable_shadow=0), dict(enable_diffuse=0, enable_specular=0),
+                                dict(enable_direct=0), dict(view_voxel_dir=1, view_voxel_lod=1.5), dict(view_voxel_dir=4, view_voxel_lod=0.0)])
+@pytest.mark.parametrize("sampler", SAMPLERS)
+def test_frame_variants(kw, sampler):
+    got, ref, _ = _frame_pair(S.cornell_scene(with_suzanne=True), 64, 256, 192, kw, sampler=sampler)
+    _check_frame(got, ref)
+
+
+@pytest.mark.parametrize("sampler", SAMPLERS)
+def test_frame_config2_cornell_256_1080p(sampler):
     """BASELINE config 2 (the benchmark workload) at full size."""
-    got, ref, cnt = _frame_pair(S.cornell_scene(), 256, 1920, 1080)
+    got, ref, cnt = _frame_pair(S.cornell_scene(), 256, 1920, 1080, sampler=sampler)
     _check_frame(got, ref)
     assert abs(cnt.samples - ref["trace_stats"].samples) <= 5e-2 * ref["trace_stats"].samples
 

@@ -1,12 +1,8 @@
 #!/bin/bash
-# bench + ncu launch list + full capture of the cone tracer (development helper)
+# ncu full captures of the cone tracer (both samplers) and the mip kernels + sampler accuracy experiment
 mkdir -p gpurun_out
-export VCT_SAMPLER=${VCT_SAMPLER:-1}
-python bench.py --steps 50 --warmup 3 --no-cpu > gpurun_out/bench.json 2> gpurun_out/bench.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench.json'))
-print({k:d[k] for k in ('value','ms_per_step')}, d['e2e'], d['stages'], d['roofline']['gsamples_per_s'], d['clocks'])
-PY
-tail -5 gpurun_out/bench.err
-ncu --set full --clock-control none --import-source on -k regex:cone_trace -s 3 -c 1 -o gpurun_out/prof_trace -f python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_trace.log 2>&1
+timeout 600 python tools/sampler_experiment.py > gpurun_out/sampler.txt 2>&1; cat gpurun_out/sampler.txt
+VCT_SAMPLER=0 timeout 900 ncu --set full --clock-control none --import-source on -k regex:cone_kernel -s 3 -c 1 -o gpurun_out/prof_cone_fp32 -f python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_cone_fp32.log 2>&1
+VCT_SAMPLER=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:cone_kernel -s 3 -c 1 -o gpurun_out/prof_cone_tex -f python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_cone_tex.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"mip_fused|vox_|cam_" -s 27 -c 9 -o gpurun_out/prof_small -f python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_small.log 2>&1
+ls -la gpurun_out

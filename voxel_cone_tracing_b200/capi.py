@@ -18,7 +18,7 @@ EXPORTS = [
     "vct_scene_create", "vct_scene_destroy", "vct_scene_set_geometry", "vct_scene_set_materials", "vct_scene_set_draws",
     "vct_scene_set_lights", "vct_scene_set_cube_size",
     "vct_grid_create", "vct_grid_destroy", "vct_grid_clear", "vct_grid_upload_base", "vct_grid_download",
-    "vct_grid_base_device_ptr", "vct_grid_bytes",
+    "vct_grid_base_device_ptr", "vct_grid_bytes", "vct_grid_occupancy_words", "vct_grid_download_occupancy",
     "vct_target_create", "vct_target_destroy", "vct_target_download_frame", "vct_target_download_gbuffer", "vct_target_frame_device_ptr",
     "vct_voxelize", "vct_voxelize_reserve", "vct_voxelize_stats", "vct_mipmap", "vct_gbuffer", "vct_cone_trace", "vct_cone_trace_count",
     "vct_render_frame", "vct_last_frame_timings",
@@ -89,6 +89,8 @@ def load():
     L.vct_grid_download.argtypes = [vp, i32, i32, vp]
     L.vct_grid_base_device_ptr.argtypes = [vp]; L.vct_grid_base_device_ptr.restype = vp
     L.vct_grid_bytes.argtypes = [vp]; L.vct_grid_bytes.restype = C.c_size_t
+    L.vct_grid_occupancy_words.argtypes = [vp, i32, i32]; L.vct_grid_occupancy_words.restype = C.c_size_t
+    L.vct_grid_download_occupancy.argtypes = [vp, i32, i32, vp]
     L.vct_target_create.argtypes = [vp, i32, i32, C.POINTER(vp)]
     L.vct_target_destroy.argtypes = [vp]
     L.vct_target_download_frame.argtypes = [vp, vp]
@@ -156,6 +158,17 @@ class Grid:
         out = np.empty((n, n, n), np.uint32)
         check(self.dev.L.vct_grid_download(self.h, level, d, out.ctypes.data))
         return out
+
+    def occupancy(self, level: int, dilated: bool) -> np.ndarray:
+        """occupancy bits of one level as a bool volume: [N,N,N] (plain) or [N+1,N+1,N+1] (dilated, index = coordinate + 1)"""
+        n = self.R >> level
+        words = np.empty(int(self.dev.L.vct_grid_occupancy_words(self.h, level, int(dilated))), np.uint32)
+        check(self.dev.L.vct_grid_download_occupancy(self.h, level, int(dilated), words.ctypes.data))
+        bits = np.unpackbits(words.view(np.uint8), bitorder="little")
+        if not dilated:
+            return bits[:n ** 3].reshape(n, n, n).astype(bool)
+        wpr = (n + 32) // 32
+        return bits.reshape(n + 1, n + 1, wpr * 32)[:, :, :n + 1].astype(bool)
 
     @property
     def base_ptr(self) -> int: return int(self.dev.L.vct_grid_base_device_ptr(self.h))

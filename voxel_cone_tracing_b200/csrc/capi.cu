@@ -215,6 +215,15 @@ int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) {
     e = cudaMalloc(&g->lvl[l], n * 24);
     g->bytes += n * 24;
   }
+  // occupancy bit masks (plain + 2x2x2-dilated) per level, written by the mip stage
+  for (int l = 0; l < levels && e == cudaSuccess; l++) {
+    const int N = R >> l;
+    e = cudaMalloc(&g->occ[l], occ_words(N) * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&g->docc[l], docc_words(N) * 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->occ[l], 0, occ_words(N) * 4, dev->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->docc[l], 0, docc_words(N) * 4, dev->stream);
+    g->bytes += (occ_words(N) + docc_words(N)) * 4;
+  }
   // levels 1.. additionally live in six mipmapped CUDA arrays so that the cone tracer can use the texture units
   if (levels >= 2 && e == cudaSuccess) {
     cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
@@ -264,7 +273,7 @@ int vct_grid_destroy(vct_grid_t* g) {
   if (!g) return VCT_OK;
   cudaStreamSynchronize(g->dev->stream);
   cudaFree(g->base);
-  for (int l = 0; l < VCT_MAX_LEVELS; l++) cudaFree(g->lvl[l]);
+  for (int l = 0; l < VCT_MAX_LEVELS; l++) { cudaFree(g->lvl[l]); cudaFree(g->occ[l]); cudaFree(g->docc[l]); }
   for (int d = 0; d < 6; d++) {
     if (g->tex[d]) cudaDestroyTextureObject(g->tex[d]);
     for (int l = 0; l < VCT_MAX_LEVELS; l++) if (g->surf.s[d][l]) cudaDestroySurfaceObject(g->surf.s[d][l]);
@@ -300,6 +309,20 @@ int vct_grid_download(vct_grid_t* g, int level, int dir, uint32_t* host) {
     VCT_CUDA(cudaMemcpy2DAsync(host, 4, g->lvl[level] + dir, 24, 4, n, cudaMemcpyDeviceToHost, s));
   }
   VCT_CUDA(cudaStreamSynchronize(s));
+  return VCT_OK;
+}
+
+size_t vct_grid_occupancy_words(const vct_grid_t* g, int level, int dilated) {
+  if (!g || level < 0 || level >= g->levels) return 0;
+  return dilated ? docc_words(g->R >> level) : occ_words(g->R >> level);
+}
+
+int vct_grid_download_occupancy(vct_grid_t* g, int level, int dilated, uint32_t* host) {
+  VCT_REQUIRE(g && host, "null argument");
+  VCT_REQUIRE(level >= 0 && level < g->levels, "bad level");
+  VCT_CUDA(cudaMemcpyAsync(host, dilated ? g->docc[level] : g->occ[level], vct_grid_occupancy_words(g, level, dilated) * 4, cudaMemcpyDeviceToHost,
+                           g->dev->stream));
+  VCT_CUDA(cudaStreamSynchronize(g->dev->stream));
   return VCT_OK;
 }
 

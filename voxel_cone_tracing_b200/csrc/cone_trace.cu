@@ -74,6 +74,19 @@ __device__ __forceinline__ void madd4(float acc[4], float w, uint32_t word) {
   acc[3] = fmaf(w, byte_f(word, 3), acc[3]);
 }
 
+// true when the 2x2x2 filter footprint of `pos` at `level` holds no non-zero texel in any direction
+// (dilated occupancy bits written by the mip stage) or lies wholly outside the grid: the level's
+// contribution to the sample is then exactly zero in the reference as well.
+__device__ __forceinline__ bool footprint_empty(const GridView& g, int level, F3 pos) {
+  const int N = g.R >> level;
+  const float fN = (float)N;
+  const float ux = fmaf(pos.x, fN, -0.5f), uy = fmaf(pos.y, fN, -0.5f), uz = fmaf(pos.z, fN, -0.5f);
+  if (!(ux > -1.0f && ux < fN && uy > -1.0f && uy < fN && uz > -1.0f && uz < fN)) return true;  // also NaN
+  const int x = (int)floorf(ux) + 1, y = (int)floorf(uy) + 1, z = (int)floorf(uz) + 1;           // in [0, N]
+  const uint32_t w = __ldg(g.docc[level] + ((size_t)z * (N + 1) + y) * occ_wpr(N) + (x >> 5));
+  return ((w >> (x & 31)) & 1u) == 0u;
+}
+
 // one mip level of sample_voxel (voxel_cone_tracing.frag:80-86): adds
 //   weight * (|d.x| * tex[ix] + |d.y| * tex[iy] + |d.z| * tex[iz]) (pos)   in BYTE units (0..255)
 __device__ __forceinline__ void fetch_level(const GridView& g, int level, F3 pos, F3 adir, int ix, int iy, int iz, float weight, float acc[4]) {
@@ -186,16 +199,19 @@ __device__ __forceinline__ uint32_t trace_cone(const GridView& g, F3 origin, F3 
     const int l0 = (int)fl;
     const float f = lod - fl;
     float s[4] = {0.f, 0.f, 0.f, 0.f};
+    // levels whose filter footprint is all zero are skipped (exactly zero in the reference too)
+    const bool e0 = footprint_empty(g, l0, sp);
+    const bool e1 = (f > 0.0f) ? footprint_empty(g, l0 + 1, sp) : true;
     if (TEX) {
       if (lod < 1.0f) {
-        fetch_level(g, 0, sp, adir, ix, iy, iz, 1.0f - lod, s);                 // level 0 in software (shared by the three directions)
-        if (lod > 0.0f) fetch_tex(tx, ty, tz, sp, adir, 0.0f, 255.0f * lod, s);  // level 1 = array level 0
-      } else {
-        fetch_tex(tx, ty, tz, sp, adir, lod - 1.0f, 255.0f, s);                 // trilinear + mip-linear in the texture unit
+        if (!e0) fetch_level(g, 0, sp, adir, ix, iy, iz, 1.0f - lod, s);          // level 0 in software (shared by the three directions)
+        if (!e1) fetch_tex(tx, ty, tz, sp, adir, 0.0f, 255.0f * lod, s);           // level 1 = array level 0
+      } else if (!(e0 && e1)) {
+        fetch_tex(tx, ty, tz, sp, adir, lod - 1.0f, 255.0f, s);                   // trilinear + mip-linear in the texture unit
       }
     } else {
-      fetch_level(g, l0, sp, adir, ix, iy, iz, 1.0f - f, s);
-      if (f > 0.0f) fetch_level(g, l0 + 1, sp, adir, ix, iy, iz, f, s);
+      if (!e0) fetch_level(g, l0, sp, adir, ix, iy, iz, 1.0f - f, s);
+      if (!e1) fetch_level(g, l0 + 1, sp, adir, ix, iy, iz, f, s);
     }
     const float k = 1.0f - acc[3] * (1.0f / 255.0f);
 #pragma unroll

@@ -74,30 +74,24 @@ cam_raster_kernel(const CamTri* __restrict__ tris, uint32_t n_tris, const uint32
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t chunk = warp; (unsigned long long)chunk * 32ull < total; chunk += n_warps) {
-    uint32_t g = chunk * 32u + lane;
-    uint32_t my_tri = 0, my_rank = 0;
-    if (g < total) my_tri = find_item_triangle(g, item_block, n_blocks, item_local, n_tris, my_rank);
-    const int n_here = min(32u, total - chunk * 32u);
-    for (int s = 0; s < n_here; s++) {
-      const uint32_t ti = __shfl_sync(0xffffffffu, my_tri, s);
-      const uint32_t rank = __shfl_sync(0xffffffffu, my_rank, s);
-      const CamTri& v = tris[ti];
-      const RasterTri rt = v.rt;
-      const float z0 = v.zw[0], z1 = v.zw[1], z2 = v.zw[2];
-      const int tiles_x = (rt.imax >> 3) - (rt.imin >> 3) + 1;
-      const int tx = (rt.imin >> 3) + (int)(rank % (uint32_t)tiles_x), ty = (rt.jmin >> 3) + (int)(rank / (uint32_t)tiles_x);
+  for (uint32_t g = warp; g < total; g += n_warps) {  // one warp per 8x8 item
+    uint32_t rank;
+    const uint32_t ti = find_item_triangle(g, item_block, n_blocks, item_local, n_tris, rank);
+    const CamTri& v = tris[ti];
+    const RasterTri rt = v.rt;
+    const float z0 = v.zw[0], z1 = v.zw[1], z2 = v.zw[2];
+    const int tiles_x = (rt.imax >> 3) - (rt.imin >> 3) + 1;
+    const int tx = (rt.imin >> 3) + (int)(rank % (uint32_t)tiles_x), ty = (rt.jmin >> 3) + (int)(rank / (uint32_t)tiles_x);
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int p = lane + 32 * h;
-        const int i = tx * kTile + (p & 7), j = ty * kTile + (p >> 3);
-        float b[3];
-        if (i >= rt.imin && i <= rt.imax && j >= rt.jmin && j <= rt.jmax && raster_sample(rt, i, j, b)) {
-          const float zw = interp3(b, z0, z1, z2);
-          if (zw >= 0.0f && zw <= 1.0f) {  // near / far (R3); also rejects NaN
-            const unsigned long long key = ((unsigned long long)__float_as_uint(zw) << 32) | (unsigned long long)ti;
-            atomicMin(&vis[(size_t)j * W + i], key);
-          }
+    for (int h = 0; h < 2; h++) {
+      const int p = lane + 32 * h;
+      const int i = tx * kTile + (p & 7), j = ty * kTile + (p >> 3);
+      float b[3];
+      if (i >= rt.imin && i <= rt.imax && j >= rt.jmin && j <= rt.jmax && raster_sample(rt, i, j, b)) {
+        const float zw = interp3(b, z0, z1, z2);
+        if (zw >= 0.0f && zw <= 1.0f) {  // near / far (R3); also rejects NaN
+          const unsigned long long key = ((unsigned long long)__float_as_uint(zw) << 32) | (unsigned long long)ti;
+          atomicMin(&vis[(size_t)j * W + i], key);
         }
       }
     }

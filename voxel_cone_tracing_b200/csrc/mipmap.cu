@@ -111,7 +111,8 @@ __global__ void mip_generic_kernel(const uint32_t* __restrict__ src, uint32_t* _
 constexpr int TX = 32, TY = 8, TZ = 8;
 
 __global__ void __launch_bounds__(256)
-mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l1, uint32_t* __restrict__ l2, uint32_t* __restrict__ l3, int R, const SurfSet surf) {
+mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l1, uint32_t* __restrict__ l2, uint32_t* __restrict__ l3, int R, const SurfSet surf,
+                     uint32_t* __restrict__ occ0, uint16_t* __restrict__ occ1, uint8_t* __restrict__ occ2) {
   __shared__ __align__(16) uint32_t s0[TZ][TY][TX];           // 8 KB
   __shared__ uint32_t s1[TZ / 2][TY / 2][TX / 2][6];          // 6 KB
   __shared__ uint32_t s2[TZ / 4][TY / 4][TX / 4][6];          // 768 B
@@ -129,6 +130,12 @@ mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l
     const uint4 v = *reinterpret_cast<const uint4*>(base + ((size_t)(z0 + z) * R + (y0 + y)) * R + x0 + 4 * quad);
     *reinterpret_cast<uint4*>(&s0[z][y][4 * quad]) = v;
     any0 |= v.x | v.y | v.z | v.w;
+    // occupancy bits of the row: 8 consecutive lanes hold its 32 voxels
+    uint32_t bits = ((v.x != 0u) | (v.y != 0u) << 1 | (v.z != 0u) << 2 | (v.w != 0u) << 3) << (4 * quad);
+    bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
+    bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
+    bits |= __shfl_xor_sync(0xffffffffu, bits, 4);
+    if (quad == 0) occ0[((size_t)(z0 + z) * R + (y0 + y)) * (R / 32) + bx] = bits;
   }
   const int tile_nonzero = __syncthreads_or((int)(any0 != 0u));
   const int N1 = R >> 1, N2 = R >> 2, N3 = R >> 3;
@@ -141,6 +148,11 @@ mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l
       o[0] = make_uint2(0u, 0u); o[1] = make_uint2(0u, 0u); o[2] = make_uint2(0u, 0u);
 #pragma unroll
       for (int d = 0; d < 6; d++) surf3Dwrite(0u, surf.s[d][1], (x0 / 2 + x) * 4, y0 / 2 + y, z0 / 2 + z);
+      if (x == 0) occ1[((size_t)(z0 / 2 + z) * N1 + (y0 / 2 + y)) * (N1 / 16) + bx] = 0;
+    }
+    if (t >= 192 && t < 196) {
+      const int y = t & 1, z = (t >> 1) & 1;
+      occ2[((size_t)(z0 / 4 + z) * N2 + (y0 / 4 + y)) * (N2 / 8) + bx] = 0;
     }
     if (t < 192) {
       const int d = t % 6, tex = t / 6, x = tex & 7, y = (tex >> 3) & 1, z = tex >> 4;
@@ -184,6 +196,9 @@ mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l
       s1[z][y][x][d] = o[d];
       surf3Dwrite(o[d], surf.s[d][1], (x0 / 2 + x) * 4, y0 / 2 + y, z0 / 2 + z);
     }
+    // a warp holds two rows of 16 texels
+    const uint32_t bal = __ballot_sync(0xffffffffu, (o[0] | o[1] | o[2] | o[3] | o[4] | o[5]) != 0u);
+    if (x == 0) occ1[((size_t)(z0 / 2 + z) * N1 + (y0 / 2 + y)) * (N1 / 16) + bx] = (uint16_t)(bal >> (16 * (y & 1)));
   }
   __syncthreads();
 
@@ -209,6 +224,18 @@ mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l
   }
   __syncthreads();
 
+  if (t >= 192 && t < 196) {  // level-2 occupancy: one byte per row of 8 texels
+    const int y = t & 1, z = (t >> 1) & 1;
+    uint32_t bits = 0;
+#pragma unroll
+    for (int x = 0; x < 8; x++) {
+      uint32_t a = 0;
+#pragma unroll
+      for (int d = 0; d < 6; d++) a |= s2[z][y][x][d];
+      bits |= (uint32_t)(a != 0u) << x;
+    }
+    occ2[((size_t)(z0 / 4 + z) * N2 + (y0 / 4 + y)) * (N2 / 8) + bx] = (uint8_t)bits;
+  }
   // ---- level 3: 4 texels x 6 directions ----
   if (t < 24) {
     const int d = t % 6, x = t / 6;
@@ -307,14 +334,78 @@ mip_fused_high_kernel(const uint32_t* __restrict__ l3, uint32_t* __restrict__ l4
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// occupancy bits from the texel data of one level (blockIdx.y selects the level): one warp per 32 texels
+struct OccArgs {
+  const uint32_t* src[VCT_MAX_LEVELS];  // level 0: base words, level >= 1: 6-word records
+  uint32_t* occ[VCT_MAX_LEVELS];
+  uint32_t* docc[VCT_MAX_LEVELS];
+  int R, first_level;
+};
+
+__global__ void __launch_bounds__(256)
+occ_bits_kernel(const OccArgs a) {
+  const int level = a.first_level + (int)blockIdx.y;
+  const size_t N = (size_t)(a.R >> level), n = N * N * N;
+  const uint32_t* src = a.src[level];
+  const int lane = threadIdx.x & 31;
+  const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w * 32 < n; w += n_warps) {
+    const size_t i = w * 32 + lane;
+    uint32_t any = 0;
+    if (i < n) {
+      if (level == 0) any = src[i];
+      else {
+        const uint2* r = reinterpret_cast<const uint2*>(src + i * 6);
+        const uint2 p = r[0], q = r[1], s = r[2];
+        any = p.x | p.y | q.x | q.y | s.x | s.y;
+      }
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, any != 0u);
+    if (lane == 0) a.occ[level][w] = bal;
+  }
+}
+
+// 32 occupancy bits of row (y,z) starting at x = 32*k; rows outside the level read as zero
+__device__ __forceinline__ uint32_t occ_row_bits(const uint32_t* __restrict__ occ, int N, int y, int z, int k) {
+  if ((unsigned)y >= (unsigned)N || (unsigned)z >= (unsigned)N || k < 0 || k * 32 >= N) return 0u;
+  const size_t flat = ((size_t)z * N + y) * N + (size_t)k * 32;
+  if (N >= 32) return occ[flat >> 5];
+  return (occ[flat >> 5] >> (flat & 31)) & ((1u << N) - 1u);
+}
+
+// dilation: docc bit (x+1,y+1,z+1) = OR of occ over [x,x+1]x[y,y+1]x[z,z+1]; one thread per output word
+__global__ void __launch_bounds__(256)
+occ_dilate_kernel(const OccArgs a) {
+  const int level = (int)blockIdx.y;
+  const int N = a.R >> level, D = N + 1, wpr = occ_wpr(N);
+  const size_t n = (size_t)D * D * wpr;
+  const uint32_t* occ = a.occ[level];
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % wpr), y = (int)((i / wpr) % D) - 1, z = (int)(i / ((size_t)wpr * D)) - 1;
+    uint32_t r = 0, rp = 0;
+#pragma unroll
+    for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+      for (int dy = 0; dy < 2; dy++) {
+        r |= occ_row_bits(occ, N, y + dy, z + dz, k);
+        rp |= occ_row_bits(occ, N, y + dy, z + dz, k - 1);
+      }
+    a.docc[level][i] = (r << 1) | (rp >> 31) | r;
+  }
+}
+
 int launch_mipmap(vct_device* dev, vct_grid* g) {
   cudaStream_t s = dev->stream;
   const int R = g->R;
   int level = 0;  // highest level already built
+  int occ_from_data = 0;
   if (g->levels >= 4 && R % 32 == 0 && R >= 32) {
     const int n_tiles = (R / TX) * (R / TY) * (R / TZ);
-    mip_fused_low_kernel<<<n_tiles, 256, 0, s>>>(g->base, g->lvl[1], g->lvl[2], g->lvl[3], R, g->surf);
+    mip_fused_low_kernel<<<n_tiles, 256, 0, s>>>(g->base, g->lvl[1], g->lvl[2], g->lvl[3], R, g->surf, g->occ[0], (uint16_t*)g->occ[1],
+                                                 (uint8_t*)g->occ[2]);
     level = 3;
+    occ_from_data = 3;  // levels 0..2 got their occupancy bits from the fused kernel
     if (g->levels >= 7 && (R >> 3) % 8 == 0) {
       const int tiles = (R >> 3) / 8;
       mip_fused_high_kernel<<<tiles * tiles * tiles, 256, 0, s>>>(g->lvl[3], g->lvl[4], g->lvl[5], g->lvl[6], R >> 3, g->surf);
@@ -328,6 +419,15 @@ int launch_mipmap(vct_device* dev, vct_grid* g) {
     const int blocks = (int)grid_for(n);
     mip_generic_kernel<<<blocks, 256, 0, s>>>(l == 0 ? g->base : g->lvl[l], g->lvl[l + 1], Ns, Nd, l == 0, g->surf, l + 1);
   }
+  // occupancy masks for the cone tracer's zero-footprint skip
+  OccArgs oa;
+  oa.R = R; oa.first_level = occ_from_data;
+  for (int l = 0; l < VCT_MAX_LEVELS; l++) { oa.src[l] = l == 0 ? g->base : g->lvl[l]; oa.occ[l] = g->occ[l]; oa.docc[l] = g->docc[l]; }
+  if (occ_from_data < g->levels) {
+    const size_t n = (size_t)(R >> occ_from_data) * (R >> occ_from_data) * (R >> occ_from_data);
+    occ_bits_kernel<<<dim3(grid_for(n, 256, 148 * 8), g->levels - occ_from_data), 256, 0, s>>>(oa);
+  }
+  occ_dilate_kernel<<<dim3(grid_for(docc_words(R), 256, 148 * 8), g->levels), 256, 0, s>>>(oa);
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;
 }

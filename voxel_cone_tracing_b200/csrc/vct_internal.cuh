@@ -89,8 +89,17 @@ struct GridView {
   uint32_t* base;                 // level 0: R^3 u32, [z][y][x]
   uint32_t* lvl[VCT_MAX_LEVELS];  // level l >= 1: (R>>l)^3 records of 6 u32 (direction-minor)
   cudaTextureObject_t tex[6];     // per direction: mipmapped 3-D RGBA8 texture of levels 1.. (array level k = grid level k+1)
+  const uint32_t* docc[VCT_MAX_LEVELS];  // per level: dilated occupancy bits, see occ_word_index()
   int R, levels;
 };
+
+// Occupancy bits (built by the mip stage, read by the cone tracer to skip all-zero filter footprints):
+//   occ[l]  bit (x,y,z) at flat index (z*N + y)*N + x               = texel (x,y,z) of level l is non-zero in any direction
+//   docc[l] bit (x+1,y+1,z+1) of a (N+1)^3 volume, rows of occ_wpr(N) words, for x,y,z in [-1, N-1]
+//                                                                   = any texel of the 2x2x2 footprint whose low corner is (x,y,z) is non-zero
+__host__ __device__ __forceinline__ int occ_wpr(int N) { return (N + 32) / 32; }
+__host__ __device__ __forceinline__ size_t occ_words(int N) { size_t n = (size_t)N * N * N; return (n + 31) / 32; }
+__host__ __device__ __forceinline__ size_t docc_words(int N) { return (size_t)(N + 1) * (N + 1) * occ_wpr(N); }
 
 // surface handles of the per-direction mipmapped arrays: s[dir][grid level], level >= 1
 struct SurfSet {
@@ -144,10 +153,12 @@ struct vct_grid {
   cudaMipmappedArray_t marr[6] = {};
   cudaTextureObject_t tex[6] = {};
   vct::SurfSet surf{};
+  uint32_t* occ[VCT_MAX_LEVELS] = {};   // non-dilated occupancy bits per level
+  uint32_t* docc[VCT_MAX_LEVELS] = {};  // dilated occupancy bits per level
   vct::GridView view() const {
     vct::GridView v;
     v.base = base; v.R = R; v.levels = levels;
-    for (int i = 0; i < VCT_MAX_LEVELS; i++) v.lvl[i] = lvl[i];
+    for (int i = 0; i < VCT_MAX_LEVELS; i++) { v.lvl[i] = lvl[i]; v.docc[i] = docc[i]; }
     for (int d = 0; d < 6; d++) v.tex[d] = tex[d];
     return v;
   }

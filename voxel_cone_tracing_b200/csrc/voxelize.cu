@@ -119,14 +119,11 @@ vox_raster_kernel(const VoxTri* __restrict__ tris, uint32_t n_tris, const uint32
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
   const float fR = (float)R;
-  for (uint32_t chunk = warp; (unsigned long long)chunk * 32ull < total; chunk += n_warps) {
-    uint32_t g = chunk * 32u + lane;
-    uint32_t my_tri = 0, my_rank = 0;
-    if (g < total) my_tri = find_item_triangle(g, item_block, n_blocks, item_local, n_tris, my_rank);
-    const int n_here = min(32u, total - chunk * 32u);
-    for (int s = 0; s < n_here; s++) {
-      const uint32_t ti = __shfl_sync(0xffffffffu, my_tri, s);
-      const uint32_t rank = __shfl_sync(0xffffffffu, my_rank, s);
+  // one warp per 8x8 item (grid-stride): every lane runs the same two binary searches (broadcast loads)
+  for (uint32_t g = warp; g < total; g += n_warps) {
+    uint32_t rank;
+    const uint32_t ti = find_item_triangle(g, item_block, n_blocks, item_local, n_tris, rank);
+    {
       const VoxTri& v = tris[ti];
       const RasterTri rt = v.rt;
       const int tiles_x = (rt.imax >> 3) - (rt.imin >> 3) + 1;
