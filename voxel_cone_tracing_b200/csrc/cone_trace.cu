@@ -161,9 +161,11 @@ __device__ __forceinline__ void fetch_level(const GridView& g, int level, F3 pos
 //   acc += weight255 * (|d.x| * tex[ix] + |d.y| * tex[iy] + |d.z| * tex[iz])(pos, tex_lod)      (byte units)
 __device__ __forceinline__ void fetch_tex(cudaTextureObject_t tx, cudaTextureObject_t ty, cudaTextureObject_t tz, F3 pos, F3 adir, float tex_lod,
                                           float weight255, float acc[4]) {
-  const float4 a = tex3DLod<float4>(tx, pos.x, pos.y, pos.z, tex_lod);
-  const float4 b = tex3DLod<float4>(ty, pos.x, pos.y, pos.z, tex_lod);
-  const float4 c = tex3DLod<float4>(tz, pos.x, pos.y, pos.z, tex_lod);
+  // a direction whose weight |d.a| is exactly 0 contributes exactly 0 (axis-aligned cones of the box walls): no fetch
+  const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 a = adir.x != 0.0f ? tex3DLod<float4>(tx, pos.x, pos.y, pos.z, tex_lod) : zero;
+  const float4 b = adir.y != 0.0f ? tex3DLod<float4>(ty, pos.x, pos.y, pos.z, tex_lod) : zero;
+  const float4 c = adir.z != 0.0f ? tex3DLod<float4>(tz, pos.x, pos.y, pos.z, tex_lod) : zero;
   const float sx = weight255 * adir.x, sy = weight255 * adir.y, sz = weight255 * adir.z;
   acc[0] = fmaf(sx, a.x, fmaf(sy, b.x, fmaf(sz, c.x, acc[0])));
   acc[1] = fmaf(sx, a.y, fmaf(sy, b.y, fmaf(sz, c.y, acc[1])));
