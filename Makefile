@@ -9,7 +9,7 @@ OUT      := voxel_cone_tracing_b200
 NVFLAGS  := -O3 -std=c++17 $(ARCH) -lineinfo -Iinclude -I$(CSRC) -Xcompiler -fPIC,-Wall,-ffp-contract=off -ccbin $(CXX)
 # bit-exact units (same arithmetic as the oracle: no FMA contraction)
 EXACT    := -fmad=false
-OBJS     := $(CSRC)/capi.o $(CSRC)/tex3d.o $(CSRC)/voxelize.o $(CSRC)/mipmap.o $(CSRC)/gbuffer.o $(CSRC)/cone_trace.o
+OBJS     := $(CSRC)/capi.o $(CSRC)/tex3d.o $(CSRC)/voxelize.o $(CSRC)/mipmap.o $(CSRC)/gbuffer.o $(CSRC)/cone_trace.o $(CSRC)/peer.o
 HDRS     := include/vct/vct_c.h $(CSRC)/vct_internal.cuh $(CSRC)/raster.cuh
 
 all: $(OUT)/libvct_cuda.so oracle host
@@ -25,6 +25,8 @@ $(CSRC)/cone_trace.o: $(CSRC)/cone_trace.cu $(HDRS)
 $(CSRC)/capi.o: $(CSRC)/capi.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
 $(CSRC)/tex3d.o: $(CSRC)/tex3d.cu $(HDRS)
+	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
+$(CSRC)/peer.o: $(CSRC)/peer.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
 
 $(OUT)/libvct_cuda.so: $(OBJS)

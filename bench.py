@@ -203,9 +203,16 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
         base_t = torch.as_tensor(CudaArray(pipe.grid.base_ptr, (R * R * R,), "<i4"), device=torch.device("cuda", local_rank))
         frame_t = torch.as_tensor(CudaArray(pipe.target.frame_ptr, (W * H,), "<i4"), device=torch.device("cuda", local_rank))
     per_rank = R * R * R // world
+    p2p = world > 1 and args.exchange == "p2p"
+    if p2p:
+        # NVLink peer-memory exchange fused into the resolve / shade kernels (csrc/peer.cu): handles travel once, here
+        handles = [None] * world
+        dist.all_gather_object(handles, pipe.peer_export())
+        pipe.peer_connect(rank, world, handles, frame_root=0)
+        dist.barrier()
 
     def frame_device():
-        if world == 1:
+        if world == 1 or p2p:
             pipe.render_frame(view, proj, prm)
             return
         with torch.cuda.stream(stream):
@@ -254,10 +261,19 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
                 stage_acc[k] = stage_acc.get(k, 0.0) + v
             n_stage += 1
         stage_acc = {k: v / n_stage for k, v in stage_acc.items()}
+    rank_stages = None
     if world > 1:
         t = torch.tensor([ms_total], device=f"cuda:{local_rank}")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
+        if p2p:   # per-rank stage times of the last frames (CUDA events inside vct_render_frame), for the scaling analysis
+            acc = {}
+            for _ in range(10):
+                pipe.render_frame(view, proj, prm)
+                for k, v in pipe.timings().items():
+                    acc[k] = acc.get(k, 0.0) + v * 100.0     # -> us, averaged over 10
+            rank_stages = [None] * world
+            dist.all_gather_object(rank_stages, {k: round(v, 1) for k, v in acc.items()})
     ms_step = ms_total / args.steps
     value = 1e3 / ms_step
 
@@ -321,13 +337,20 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
                "data": "synthetic",
                "config": {"workload": cfg["name"] + ", revoxelize+mip+gbuffer+trace per frame, 9 diffuse + 1 specular + 1 shadow cone",
                           "sampler": "texture units (levels >= 1), software level 0" if args.sampler == 1 else "software fp32 trilinear",
-                          "grid": R, "frame": [W, H], "triangles": sc.n_triangles, "parallelism": f"z-slab voxelize + screen-tile trace x{world}",
+                          "grid": R, "frame": [W, H], "triangles": sc.n_triangles, "parallelism": f"z-slab voxelize + screen-tile trace x{world}" + ("" if world == 1 else (", sparse NVLink peer-store exchange fused into the resolve/shade kernels (CUDA IPC, no collective)" if p2p else ", NCCL all-gather of the base level + all-reduce of the frame")),
                           "l2": "no explicit flush: grid + G-buffer + frame working set (%.0f MB) exceeds the 126 MB L2 and is rewritten every frame"
                                 % ((pipe.grid.nbytes + W * H * 40) / 1e6)},
                "clocks": clocks, "e2e": e2e, "gpu_launches": KERNELS_PER_FRAME * args.steps, "roofline": roof, "cpu_baseline": cpu}
         if stages:
             out["stages"] = stages
+        if rank_stages:
+            out["stages_us_per_rank"] = rank_stages
         print(json.dumps(out), flush=True)
+    if p2p:
+        pipe.peer_check()        # raises if a flag wait ever timed out
+        barrier()                # nobody unmaps while a peer may still be storing into it
+        pipe.peer_disconnect()
+        barrier()
     pipe.close()
     if world > 1:
         dist.destroy_process_group()
@@ -341,6 +364,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="multi-GPU exchange: p2p = sparse voxel push + tile push over NVLink peer memory, fused into the kernels (default); "
+                         "nccl = dense in-place all-gather of the base level + all-reduce of the frame (the library baseline)")
     ap.add_argument("--sampler", type=int, default=1, choices=[0, 1],
                     help="textureLod evaluator of the cone tracer: 1 = texture units (default; frame within 2/255, PSNR > 60 dB of the oracle), 0 = software fp32")
     args = ap.parse_args()

@@ -151,6 +151,21 @@ int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_targ
  * [6] cone kernel alone [7] reserved; synchronises */
 int vct_last_frame_timings(vct_device_t* dev, float out_ms[8]);
 
+/* ---- multi-GPU (no reference counterpart: the reference is single-GPU).  One process per GPU on one node; the exchange
+ *      runs over NVLink peer memory (CUDA IPC), fused into the producing kernels -- see csrc/peer.cu.  Protocol:
+ *        every rank:  vct_peer_export(...)  ->  exchange the handles (any transport: torch.distributed, MPI, a file)
+ *                     vct_peer_connect(..., all_handles, frame_root)  ->  process barrier  ->  vct_render_frame per frame
+ *      After the connect, vct_render_frame on that grid/target renders this rank's share: voxelizes its z-slab
+ *      [rank*R/n, (rank+1)*R/n) (integer division) and stores the resolved voxels into every peer's grid, builds the mip chain locally once
+ *      all slabs have arrived, traces the 32x32 screen tiles with tile % n == rank and stores the finished pixels into the
+ *      frame of rank `frame_root` (-1: of every rank).  All ranks must call vct_render_frame the same number of times.
+ *      The grid and the frame are bit-identical to the single-GPU result. ---- */
+typedef struct { unsigned char bytes[320]; } vct_peer_handle_t;
+int vct_peer_export(vct_device_t* dev, vct_grid_t* g, vct_target_t* t, vct_peer_handle_t* out);
+int vct_peer_connect(vct_device_t* dev, vct_grid_t* g, vct_target_t* t, int rank, int nranks, const vct_peer_handle_t* all_ranks, int frame_root);
+int vct_peer_disconnect(vct_device_t* dev);
+int vct_peer_error(vct_device_t* dev); /* VCT_ERR_CUDA if a flag wait timed out (~5 s) since the connect; synchronises */
+
 /* ---- texture_3d.h:6-10, one generic RGBA8 3-D texture with a mip chain ---- */
 int vct_tex3d_create(vct_device_t* dev, int width, int height, int depth, int levels, vct_tex3d_t** out); /* create_tex_3d */
 int vct_tex3d_destroy(vct_tex3d_t* t);                                                                     /* destroy_tex_3d */

@@ -22,6 +22,7 @@ EXPORTS = [
     "vct_target_create", "vct_target_destroy", "vct_target_download_frame", "vct_target_download_gbuffer", "vct_target_frame_device_ptr",
     "vct_voxelize", "vct_voxelize_reserve", "vct_voxelize_stats", "vct_mipmap", "vct_gbuffer", "vct_cone_trace", "vct_cone_trace_count",
     "vct_render_frame", "vct_last_frame_timings",
+    "vct_peer_export", "vct_peer_connect", "vct_peer_disconnect", "vct_peer_error",
     "vct_tex3d_create", "vct_tex3d_destroy", "vct_tex3d_clear", "vct_tex3d_mip", "vct_tex3d_upload", "vct_tex3d_download",
 ]
 
@@ -56,6 +57,7 @@ def default_params(**kw) -> TraceParams:
 
 
 _lib = None
+PEER_HANDLE_BYTES = 320   # sizeof(vct_peer_handle_t)
 SAMPLER_FP32, SAMPLER_TEX = 0, 1
 DEFAULT_SAMPLER = int(os.environ.get("VCT_SAMPLER", "0"))
 
@@ -105,6 +107,10 @@ def load():
     L.vct_cone_trace_count.argtypes = [vp, vp, vp, f32p, C.POINTER(TraceParams), vp, C.POINTER(TraceStats)]
     L.vct_render_frame.argtypes = [vp, vp, vp, vp, f32p, f32p, C.POINTER(TraceParams)]
     L.vct_last_frame_timings.argtypes = [vp, f32p]
+    L.vct_peer_export.argtypes = [vp, vp, vp, vp]
+    L.vct_peer_connect.argtypes = [vp, vp, vp, i32, i32, vp, i32]
+    L.vct_peer_disconnect.argtypes = [vp]
+    L.vct_peer_error.argtypes = [vp]
     L.vct_tex3d_create.argtypes = [vp, i32, i32, i32, i32, C.POINTER(vp)]
     L.vct_tex3d_destroy.argtypes = [vp]
     L.vct_tex3d_clear.argtypes = [vp, f32p]
@@ -283,6 +289,23 @@ class Pipeline:
         return dict(zip(("clear", "voxelize", "mipmap", "gbuffer", "trace", "total", "cone_kernel"), [float(x) for x in t[:7]]))
 
     def sync(self): self.dev.sync()
+
+    # ---- multi-GPU: exchange over NVLink peer memory (include/vct/vct_c.h "multi-GPU") ----
+    def peer_export(self) -> bytes:
+        """this rank's handle (send it to every other rank by any transport)"""
+        buf = C.create_string_buffer(PEER_HANDLE_BYTES)
+        check(self.dev.L.vct_peer_export(self.dev.h, self.grid.h, self.target.h, buf))
+        return buf.raw
+
+    def peer_connect(self, rank: int, nranks: int, handles: list, frame_root: int = 0):
+        """handles[r] = peer_export() of rank r.  Follow with a process barrier before the first render_frame()."""
+        assert len(handles) == nranks and all(len(h) == PEER_HANDLE_BYTES for h in handles)
+        blob = C.create_string_buffer(b"".join(handles), PEER_HANDLE_BYTES * nranks)
+        check(self.dev.L.vct_peer_connect(self.dev.h, self.grid.h, self.target.h, rank, nranks, blob, frame_root))
+
+    def peer_check(self): check(self.dev.L.vct_peer_error(self.dev.h))
+
+    def peer_disconnect(self): check(self.dev.L.vct_peer_disconnect(self.dev.h))
 
     def close(self):
         self.target.close(); self.grid.close(); self.scene.close(); self.dev.close()

@@ -103,7 +103,9 @@ int vct_device_create(int ordinal, vct_device_t** out) {
 int vct_device_destroy(vct_device_t* d) {
   if (!d) return VCT_OK;
   cudaSetDevice(d->ordinal);
+  vct_peer_disconnect(d);
   cudaStreamSynchronize(d->stream);
+  cudaFree(d->peer_flags);
   cudaFree(d->frags); cudaFree(d->occupied); cudaFree(d->tri_recs); cudaFree(d->item_local); cudaFree(d->item_block);
   cudaFree(d->counters); cudaFreeHost(d->counters_host);
   for (int i = 0; i < 8; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
@@ -209,6 +211,7 @@ int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) {
   g->dev = dev; g->R = R; g->levels = levels;
   size_t n0 = (size_t)R * R * R;
   cudaError_t e = cudaMalloc(&g->base, n0 * 4);
+  g->base_buf[0] = g->base;
   g->bytes = n0 * 4;
   for (int l = 1; l < levels && e == cudaSuccess; l++) {
     size_t n = (size_t)(R >> l) * (R >> l) * (R >> l);
@@ -271,8 +274,9 @@ int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) {
 
 int vct_grid_destroy(vct_grid_t* g) {
   if (!g) return VCT_OK;
+  if (g->dev->peer_grid == g) vct_peer_disconnect(g->dev);
   cudaStreamSynchronize(g->dev->stream);
-  cudaFree(g->base);
+  cudaFree(g->base_buf[0]); cudaFree(g->base_buf[1]);
   for (int l = 0; l < VCT_MAX_LEVELS; l++) { cudaFree(g->lvl[l]); cudaFree(g->occ[l]); cudaFree(g->docc[l]); }
   for (int d = 0; d < 6; d++) {
     if (g->tex[d]) cudaDestroyTextureObject(g->tex[d]);
@@ -355,6 +359,7 @@ int vct_target_create(vct_device_t* dev, int W, int H, vct_target_t** out) {
 
 int vct_target_destroy(vct_target_t* t) {
   if (!t) return VCT_OK;
+  if (t->dev->peer_target == t) vct_peer_disconnect(t->dev);
   cudaStreamSynchronize(t->dev->stream);
   cudaFree(t->vis); cudaFree(t->world_pos); cudaFree(t->normal); cudaFree(t->material); cudaFree(t->frame);
   cudaFree(t->cone_out); cudaFree(t->tile_list);
@@ -452,9 +457,49 @@ int vct_cone_trace_count(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, cons
   return VCT_OK;
 }
 
+// One rank's share of a frame after vct_peer_connect.  Buffer-reuse argument (e = frame number, b = e & 1):
+//  * this rank pushes frame e into base_buf[b] of every peer.  A peer cleared that buffer during ITS frame e-1 (below:
+//    "clear the next buffer") before it published PUSHED(e-1), and this rank waited for PUSHED(e-1) of every peer in
+//    its frame e-1 -> the clear happened before the push.
+//  * the buffer cleared here, base_buf[b^1], was last written by pushes of frame e-1, all complete once every PUSHED(e-1)
+//    flag was seen (frame e-1 of this rank), and last read by this rank's own trace of frame e-1 (stream order).
+//  * a peer's frame buffer receives tiles of frame e only after that peer published PUSHED(e), i.e. after everything it
+//    had enqueued for frame e-1 (including a frame download) in stream order.
+static int render_frame_sharded(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_target_t* t, const float view[16], const float proj[16],
+                                const vct_trace_params_t* p) {
+  cudaStream_t s = dev->stream;
+  const uint32_t epoch = ++dev->peer_epoch;
+  const int b = (int)(epoch & 1u);
+  PeerView pv = dev->peers;
+  pv.epoch = epoch;
+  for (int r = 0; r < pv.nranks; r++) pv.base[r] = dev->peer_base_all[b][r];
+  g->base = g->base_buf[b];
+  const int z0 = (int)((long long)pv.rank * g->R / pv.nranks), z1 = (int)((long long)(pv.rank + 1) * g->R / pv.nranks);
+  vct_trace_params_t prm = *p;
+  prm.tile_rank = pv.rank; prm.tile_nranks = pv.nranks;
+  int rc;
+  VCT_CUDA(cudaEventRecord(dev->ev[0], s));
+  VCT_CUDA(cudaMemsetAsync(g->base_buf[b ^ 1], 0, (size_t)g->R * g->R * g->R * 4, s));   // clear the NEXT frame's buffer
+  VCT_CUDA(cudaEventRecord(dev->ev[1], s));
+  if ((rc = launch_voxelize(dev, sc, g, z0, z1, &pv))) return rc;   // + push of the slab to the peers
+  VCT_CUDA(cudaEventRecord(dev->ev[2], s));
+  if ((rc = launch_peer_wait(dev, PEER_FLAG_PUSHED, epoch))) return rc;                     // every slab has arrived
+  if ((rc = launch_mipmap(dev, g))) return rc;
+  VCT_CUDA(cudaEventRecord(dev->ev[3], s));
+  if ((rc = launch_gbuffer(dev, sc, view, proj, t, pv.rank, pv.nranks))) return rc;                // visibility of this rank's tiles only
+  VCT_CUDA(cudaEventRecord(dev->ev[4], s));
+  if ((rc = launch_cone_trace(dev, sc, g, view, &prm, t, false, &pv))) return rc;            // + push of the tiles to the root
+  if (pv.frame_root < 0 || pv.frame_root == pv.rank)
+    if ((rc = launch_peer_wait(dev, PEER_FLAG_FRAME, epoch))) return rc;                    // every tile has arrived
+  VCT_CUDA(cudaEventRecord(dev->ev[5], s));
+  dev->have_timings = true;
+  return VCT_OK;
+}
+
 int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_target_t* t, const float view[16], const float proj[16],
                      const vct_trace_params_t* p) {
   VCT_REQUIRE(dev && sc && g && t && view && proj && p, "null argument");
+  if (dev->peers.nranks > 1 && dev->peer_grid == g && dev->peer_target == t) return render_frame_sharded(dev, sc, g, t, view, proj, p);
   cudaStream_t s = dev->stream;
   int rc;
   VCT_CUDA(cudaEventRecord(dev->ev[0], s));

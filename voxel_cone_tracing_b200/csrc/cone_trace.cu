@@ -61,6 +61,7 @@ struct TraceArgs {
   uint32_t* tile_count;
   float4* cone_out;            // [slot][pixel] cone results (rgba)
   size_t npix;
+  PeerView pv;                 // multi-GPU: where the finished pixels of this rank's tiles go (nranks <= 1: nowhere)
 };
 
 // byte k of a packed RGBA8 word as float (exact), without an I2F conversion
@@ -382,18 +383,13 @@ cone_kernel(const TraceArgs a) {
   }
 }
 
-// main() (voxel_cone_tracing.frag:246-275): one thread per pixel
-__global__ void __launch_bounds__(256)
-shade_kernel(const TraceArgs a) {
-  const int tiles_x = (a.W + 7) / 8;
-  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
-  if (tile_y * 4 >= a.H) return;
-  if (!tile_is_mine(a, tile_x, tile_y)) return;
+// main() (voxel_cone_tracing.frag:246-275) for one pixel
+__device__ __forceinline__ void store_pixel(const TraceArgs& a, size_t pix, uint32_t rgba) { a.frame[pix] = rgba; }
+
+__device__ void shade_pixel(const TraceArgs& a, int tile_x, int tile_y, int lane) {
   const Pixel p = load_pixel(a, tile_x * 8 + (lane & 7), tile_y * 4 + (lane >> 3));
   if (!p.in_frame) return;
-  if (!p.live) { a.frame[p.pix] = kBackground; return; }
+  if (!p.live) { store_pixel(a, p.pix, kBackground); return; }
   const vct_material_t* m = a.mats + p.mat_id;
   const F3 normal = p.normal, pos = p.pos;
   const int nd = a.n_diffuse;
@@ -415,7 +411,7 @@ shade_kernel(const TraceArgs a) {
     const float al = t[3] * (1.0f / 255.0f);
 #pragma unroll
     for (int k = 0; k < 4; k++) out[k] = (t[k] * (1.0f / 255.0f)) * al + bg[k] * (1.0f - al);
-    a.frame[p.pix] = pack_rgba8(out);
+    store_pixel(a, p.pix, pack_rgba8(out));
     return;
   }
   const F3 cam = f3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]);
@@ -472,12 +468,53 @@ shade_kernel(const TraceArgs a) {
     rgb = mix(rr, rgb, m->dissolve);
   }
   out[0] = rgb.x; out[1] = rgb.y; out[2] = rgb.z; out[3] = 1.0f;
-  a.frame[p.pix] = pack_rgba8(out);
+  store_pixel(a, p.pix, pack_rgba8(out));
+}
+
+
+__global__ void __launch_bounds__(256)
+shade_kernel(const TraceArgs a) {
+  const int tiles_x = (a.W + 7) / 8;
+  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+  const bool mine = tile_y * 4 < a.H && tile_is_mine(a, tile_x, tile_y);
+  if (mine) shade_pixel(a, tile_x, tile_y, lane);
+}
+
+// multi-GPU: one CTA per 32x32 screen tile of this rank copies the finished pixels into the frame of the root rank
+// (or of every rank) over NVLink with 16-byte stores (a tile row = 128 contiguous bytes); the last CTA then publishes
+// this rank's "tiles done" flag to the destination(s).
+__global__ void __launch_bounds__(256)
+frame_push_kernel(const TraceArgs a) {
+  const int tiles_x = (a.W + 31) >> 5, tiles_y = (a.H + 31) >> 5;
+  const int n_mine = (tiles_x * tiles_y - a.pv.rank + a.pv.nranks - 1) / a.pv.nranks;
+  for (int k = blockIdx.x; k < n_mine; k += gridDim.x) {
+    const int tile = a.pv.rank + k * a.pv.nranks;
+    const int x0 = (tile % tiles_x) * 32, y0 = (tile / tiles_x) * 32;
+    for (int u = threadIdx.x; u < 32 * 8; u += blockDim.x) {   // 32 rows x 8 uint4
+      const int x = x0 + 4 * (u & 7), y = y0 + (u >> 3);
+      if (y >= a.H || x >= a.W) continue;
+      const size_t pix = (size_t)y * a.W + x;
+      if (x + 3 < a.W && (pix & 3) == 0) {
+        const uint4 v = *reinterpret_cast<const uint4*>(a.frame + pix);
+        for (int p = 0; p < a.pv.nranks; p++)
+          if (p != a.pv.rank && (a.pv.frame_root < 0 || p == a.pv.frame_root)) *reinterpret_cast<uint4*>(a.pv.frame[p] + pix) = v;
+      } else {
+        for (int c = 0; c < 4 && x + c < a.W; c++)
+          for (int p = 0; p < a.pv.nranks; p++)
+            if (p != a.pv.rank && (a.pv.frame_root < 0 || p == a.pv.frame_root)) a.pv.frame[p][pix + c] = a.frame[pix + c];
+      }
+    }
+  }
+  peer_signal_last_block(a.pv, PEER_FLAG_FRAME, a.pv.frame_root);
 }
 
 int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* view, const vct_trace_params_t* p, vct_target_t_* t,
-                      bool count_samples) {
+                      bool count_samples, const PeerView* push) {
   TraceArgs a;
+  memset(&a.pv, 0, sizeof a.pv);
+  if (push) a.pv = *push;
   a.grid = g->view();
   a.world_pos = t->world_pos; a.normal = t->normal; a.material = t->material; a.frame = t->frame;
   a.W = t->W; a.H = t->H;
@@ -527,6 +564,10 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
     VCT_CUDA(cudaEventRecord(dev->ev[7], s));
   }
   shade_kernel<<<(n_tiles + 7) / 8, 256, 0, s>>>(a);
+  if (a.pv.nranks > 1) {
+    const int n32 = ((t->W + 31) / 32) * ((t->H + 31) / 32);
+    frame_push_kernel<<<min(n32 / a.pv.nranks + 1, dev->prop.multiProcessorCount * 4), 256, 0, s>>>(a);
+  }
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;
 }

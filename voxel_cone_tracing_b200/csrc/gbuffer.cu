@@ -69,7 +69,7 @@ cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
 __global__ void __launch_bounds__(256)
 cam_raster_kernel(const CamTri* __restrict__ tris, uint32_t n_tris, const uint32_t* __restrict__ item_local,
                   const uint32_t* __restrict__ item_block, uint32_t n_blocks, int W, unsigned long long* __restrict__ vis,
-                  const uint32_t* __restrict__ counters) {
+                  const uint32_t* __restrict__ counters, int tile_rank, int tile_nranks) {
   const uint32_t total = counters[CNT_CAM_ITEMS];
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -82,6 +82,8 @@ cam_raster_kernel(const CamTri* __restrict__ tris, uint32_t n_tris, const uint32
     const float z0 = v.zw[0], z1 = v.zw[1], z2 = v.zw[2];
     const int tiles_x = (rt.imax >> 3) - (rt.imin >> 3) + 1;
     const int tx = (rt.imin >> 3) + (int)(rank % (uint32_t)tiles_x), ty = (rt.jmin >> 3) + (int)(rank / (uint32_t)tiles_x);
+    // multi-GPU: only the 32x32 screen tiles this rank shades need visibility
+    if (tile_nranks > 1 && ((ty >> 2) * ((W + 31) >> 5) + (tx >> 2)) % tile_nranks != tile_rank) continue;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const int p = lane + 32 * h;
@@ -104,9 +106,13 @@ constexpr unsigned long long kVisClear = ((unsigned long long)0x3F800000u << 32)
 
 __global__ void __launch_bounds__(256)
 cam_resolve_kernel(const CamTri* __restrict__ tris, const unsigned long long* vis, int W, int H, float* __restrict__ world_pos,
-                   float* __restrict__ normal, uint32_t* __restrict__ material, unsigned long long* vis_out) {
+                   float* __restrict__ normal, uint32_t* __restrict__ material, unsigned long long* vis_out, int tile_rank, int tile_nranks) {
   const size_t n = (size_t)W * H;
   for (size_t px = (size_t)blockIdx.x * blockDim.x + threadIdx.x; px < n; px += (size_t)gridDim.x * blockDim.x) {
+    if (tile_nranks > 1) {  // pixels of other ranks' tiles are never read by this rank's tracer
+      const int i = (int)(px % W), j = (int)(px / W);
+      if (((j >> 5) * ((W + 31) >> 5) + (i >> 5)) % tile_nranks != tile_rank) continue;
+    }
     unsigned long long key = vis[px];
     uint32_t ti = (uint32_t)(key & 0xFFFFFFFFull);
     // GL_LESS against the cleared depth 1.0: a fragment exactly at zw == 1.0 fails
@@ -157,7 +163,7 @@ static void mat4_mul_host(const float* a, const float* b, float* out) {  // colu
     }
 }
 
-int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const float* proj, vct_target_t_* t) {
+int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const float* proj, vct_target_t_* t, int tile_rank, int tile_nranks) {
   cudaStream_t s = dev->stream;
   const size_t npx = (size_t)t->W * t->H;
   fill_u64_kernel<<<dev->prop.multiProcessorCount * 8, 256, 0, s>>>(t->vis, npx, kVisClear);
@@ -172,8 +178,8 @@ int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const floa
     cam_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, pv, t->W, t->H, tris,
                                                         dev->item_local, dev->item_block);
     scan_block_totals_kernel<<<1, 1024, 0, s>>>(dev->item_block, n_blocks, dev->counters + CNT_CAM_ITEMS);
-    cam_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->item_local, dev->item_block, n_blocks, t->W, t->vis, dev->counters);
-    cam_resolve_kernel<<<sms * 8, 256, 0, s>>>(tris, t->vis, t->W, t->H, t->world_pos, t->normal, t->material, t->vis);
+    cam_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->item_local, dev->item_block, n_blocks, t->W, t->vis, dev->counters, tile_rank, tile_nranks);
+    cam_resolve_kernel<<<sms * 8, 256, 0, s>>>(tris, t->vis, t->W, t->H, t->world_pos, t->normal, t->material, t->vis, tile_rank, tile_nranks);
   } else {
     launch_fill_u32(s, t->material, npx, VCT_NO_TRIANGLE);
   }

@@ -101,6 +101,43 @@ __host__ __device__ __forceinline__ int occ_wpr(int N) { return (N + 32) / 32; }
 __host__ __device__ __forceinline__ size_t occ_words(int N) { size_t n = (size_t)N * N * N; return (n + 31) / 32; }
 __host__ __device__ __forceinline__ size_t docc_words(int N) { return (size_t)(N + 1) * (N + 1) * occ_wpr(N); }
 
+// ---- multi-GPU exchange over NVLink peer memory (csrc/peer.cu) ------------------------------------
+#define VCT_MAX_RANKS 16
+enum { PEER_FLAG_PUSHED = 0, PEER_FLAG_FRAME = 1, PEER_FLAG_KINDS = 2 };
+// what a kernel needs to push results into the peers and to signal them
+struct PeerView {
+  int rank, nranks;              // nranks <= 1: not connected (single GPU)
+  uint32_t epoch;                // frame number (> 0), the value written into the flags
+  uint32_t* base[VCT_MAX_RANKS];   // level-0 buffer of THIS frame on every rank (own entry = local pointer)
+  uint32_t* frame[VCT_MAX_RANKS];  // RGBA8 frame on every rank
+  uint32_t* flags[VCT_MAX_RANKS];  // flag block of every rank: [PEER_FLAG_KINDS][VCT_MAX_RANKS] epochs, written by the source rank
+  uint32_t* done_counter;        // local: blocks of the signalling kernel that have finished
+  int frame_root;                // rank that receives the finished tiles (-1: every rank)
+};
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Called by every thread at the end of a kernel that pushed data to the peers: the LAST block to arrive
+// publishes `epoch` in slot [kind][rank] of every destination's flag block.  All peer stores of the kernel are
+// ordered before the flag by the system-scope fence + release store.
+__device__ __forceinline__ void peer_signal_last_block(const PeerView& pv, int kind, int only_rank) {
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+    if (atomicAdd(pv.done_counter + kind, 1u) == total - 1u) {
+      pv.done_counter[kind] = 0u;
+      __threadfence_system();
+      for (int p = 0; p < pv.nranks; p++)
+        if (only_rank < 0 || p == only_rank) st_release_sys(pv.flags[p] + kind * VCT_MAX_RANKS + pv.rank, pv.epoch);
+    }
+  }
+}
+
 // surface handles of the per-direction mipmapped arrays: s[dir][grid level], level >= 1
 struct SurfSet {
   cudaSurfaceObject_t s[6][VCT_MAX_LEVELS];
@@ -127,6 +164,15 @@ struct vct_device {
   uint32_t* counters_host = nullptr; // pinned mirror
   cudaEvent_t ev[8] = {};
   bool have_timings = false;
+  // multi-GPU connection (vct_peer_connect)
+  vct::PeerView peers{};               // peers.nranks <= 1 when not connected
+  uint32_t* peer_flags = nullptr;      // local flag block [PEER_FLAG_KINDS][VCT_MAX_RANKS] + done counters + error word
+  void* peer_mapped[3 * VCT_MAX_RANKS + VCT_MAX_RANKS] = {};  // pointers opened with cudaIpcOpenMemHandle (to close)
+  int n_peer_mapped = 0;
+  uint32_t* peer_base_all[2][VCT_MAX_RANKS] = {};   // both level-0 buffers of every rank
+  vct_grid* peer_grid = nullptr;
+  vct_target_t_* peer_target = nullptr;
+  uint32_t peer_epoch = 0;             // frames rendered since vct_peer_connect
 };
 enum { CNT_ITEMS = 0, CNT_FRAGS = 1, CNT_OCCUPIED = 2, CNT_MAXLIST = 3, CNT_CAM_ITEMS = 4, CNT_SAMPLES = 8 /* ..15 */, CNT_TOTAL = 32 };
 
@@ -146,7 +192,8 @@ struct vct_scene {
 struct vct_grid {
   vct_device* dev = nullptr;
   int R = 0, levels = 0;
-  uint32_t* base = nullptr;
+  uint32_t* base = nullptr;             // level 0 of the current frame
+  uint32_t* base_buf[2] = {};           // base_buf[0] == the allocation; base_buf[1] only in multi-GPU mode (double buffering)
   uint32_t* lvl[VCT_MAX_LEVELS] = {};
   size_t bytes = 0;
   // hardware-filtered copy of levels 1.. (written by the mip kernels through surfaces)
@@ -191,11 +238,12 @@ static inline unsigned grid_for(size_t n, unsigned threads = 256, unsigned cap =
 // ---- stage entry points implemented in the .cu files ------------------------------------
 namespace vct {
 int ensure_tri_scratch(vct_device* dev, size_t n_tris, size_t rec_bytes);
-int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1);
+int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1, const PeerView* push = nullptr);
+int launch_peer_wait(vct_device* dev, int kind, uint32_t epoch);
 int launch_mipmap(vct_device* dev, vct_grid* g);
-int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const float* proj, vct_target_t_* t);
+int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const float* proj, vct_target_t_* t, int tile_rank = 0, int tile_nranks = 1);
 int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* view, const vct_trace_params_t* p, vct_target_t_* t,
-                      bool count_samples);
+                      bool count_samples, const PeerView* push = nullptr);
 int launch_fill_u32(cudaStream_t s, uint32_t* p, size_t n, uint32_t v);
 int launch_tex3d_mip(vct_tex3d* t);
 }  // namespace vct

@@ -201,7 +201,7 @@ constexpr int kSortMax = 24;
 
 __global__ void __launch_bounds__(128)
 vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frags, const uint32_t* __restrict__ occupied,
-                   uint32_t* __restrict__ counters, uint32_t frag_capacity) {
+                   uint32_t* __restrict__ counters, uint32_t frag_capacity, const PeerView pv) {
   const uint32_t n_occ = counters[CNT_OCCUPIED];
   for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < n_occ; o += gridDim.x * blockDim.x) {
     const uint32_t voxel = occupied[o];
@@ -239,8 +239,13 @@ vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frag
       }
     }
     base[voxel] = stored;
+    // multi-GPU: the slab owner writes the resolved voxel straight into every peer's grid over NVLink (sparse
+    // exchange: only occupied voxels travel; replaces the dense all-gather of the base level)
+    for (int p = 0; p < pv.nranks; p++)
+      if (p != pv.rank) pv.base[p][voxel] = stored;
     atomicMax(&counters[CNT_MAXLIST], n);
   }
+  if (pv.nranks > 1) peer_signal_last_block(pv, PEER_FLAG_PUSHED, -1);
 }
 
 int ensure_tri_scratch(vct_device* dev, size_t n_tris, size_t rec_bytes) {
@@ -264,8 +269,11 @@ int ensure_tri_scratch(vct_device* dev, size_t n_tris, size_t rec_bytes) {
   return VCT_OK;
 }
 
-int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1) {
-  if (sc->n_tris == 0) return VCT_OK;
+int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1, const PeerView* push) {
+  PeerView pv;
+  memset(&pv, 0, sizeof pv);
+  if (push) pv = *push;
+  if (sc->n_tris == 0 && !push) return VCT_OK;
   int rc = ensure_tri_scratch(dev, sc->n_tris, sizeof(VoxTri));
   if (rc) return rc;
   if (dev->frag_capacity == 0) {
@@ -276,13 +284,15 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1)
   VCT_CUDA(cudaMemsetAsync(dev->counters, 0, 8 * sizeof(uint32_t), s));
   const uint32_t n_blocks = (sc->n_tris + kSetupThreads - 1) / kSetupThreads;
   VoxTri* tris = (VoxTri*)dev->tri_recs;
-  vox_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, sc->cube_size, g->R, tris,
-                                                        dev->item_local, dev->item_block);
-  scan_block_totals_kernel<<<1, 1024, 0, s>>>(dev->item_block, n_blocks, dev->counters + CNT_ITEMS);
   const int sms = dev->prop.multiProcessorCount;
-  vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->item_local, dev->item_block, n_blocks, sc->mats, sc->lights, sc->cube_size,
-                                            g->R, z0, z1, g->base, dev->frags, (uint32_t)dev->frag_capacity, dev->occupied, dev->counters);
-  vox_resolve_kernel<<<sms * 4, 128, 0, s>>>(g->base, dev->frags, dev->occupied, dev->counters, (uint32_t)dev->frag_capacity);
+  if (sc->n_tris) {   // an empty scene still runs the resolve kernel in multi-GPU mode: the peers wait for its signal
+    vox_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, sc->cube_size, g->R, tris,
+                                                          dev->item_local, dev->item_block);
+    scan_block_totals_kernel<<<1, 1024, 0, s>>>(dev->item_block, n_blocks, dev->counters + CNT_ITEMS);
+    vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->item_local, dev->item_block, n_blocks, sc->mats, sc->lights, sc->cube_size,
+                                              g->R, z0, z1, g->base, dev->frags, (uint32_t)dev->frag_capacity, dev->occupied, dev->counters);
+  }
+  vox_resolve_kernel<<<sms * 4, 128, 0, s>>>(g->base, dev->frags, dev->occupied, dev->counters, (uint32_t)dev->frag_capacity, pv);
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;
 }
