@@ -203,6 +203,16 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
         base_t = torch.as_tensor(CudaArray(pipe.grid.base_ptr, (R * R * R,), "<i4"), device=torch.device("cuda", local_rank))
         frame_t = torch.as_tensor(CudaArray(pipe.target.frame_ptr, (W * H,), "<i4"), device=torch.device("cuda", local_rank))
     per_rank = R * R * R // world
+    # size the fragment arena for this rank's slab before anything is timed (the library grows it on overflow and asks for a re-run)
+    for _ in range(4):
+        pipe.clear(); pipe.voxelize(z0, z1)
+        try:
+            pipe.voxel_stats()
+            break
+        except capi.VctError as e:
+            if "overflow" not in str(e):
+                raise
+    pipe.clear()
     p2p = world > 1 and args.exchange == "p2p"
     if p2p:
         # NVLink peer-memory exchange fused into the resolve / shade kernels (csrc/peer.cu): handles travel once, here

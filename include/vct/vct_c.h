@@ -109,6 +109,7 @@ int vct_grid_destroy(vct_grid_t* g);
 int vct_grid_clear(vct_grid_t* g);                                        /* clear_tex_3d x6, renderer.cpp:320-321 */
 int vct_grid_upload_base(vct_grid_t* g, const uint32_t* host_rgba8);      /* R^3 texels, [z][y][x] */
 int vct_grid_download(vct_grid_t* g, int level, int dir, uint32_t* host); /* glGetTexImage equivalent; level 0 ignores dir */
+int vct_grid_download_array(vct_grid_t* g, int level, int dir, uint32_t* host); /* level >= 1 read back from the mipmapped CUDA array the texture units sample (must equal vct_grid_download) */
 /* occupancy bit masks written by vct_mipmap and read by the cone tracer to skip all-zero filter footprints (no reference
  * counterpart; inspection only).  dilated = 0: bit (z*N + y)*N + x = texel non-zero in any direction; dilated = 1: volume of
  * (N+1)^3 bits in rows of (N+32)/32 words, bit (x+1,y+1,z+1) = any texel of [x,x+1]x[y,y+1]x[z,z+1] non-zero. */

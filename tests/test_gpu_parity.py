@@ -26,11 +26,15 @@ def max_abs(a, b) -> int:
 
 
 def assert_pyramid_equal(grid: capi.Grid, pyr: orc.Pyramid):
+    """both copies of the pyramid: the 24-byte records (software sampler) and the mipmapped arrays (texture units)"""
     for l in range(pyr.n_levels):
         for d in range(6):
             got = grid.download(l, d)
             exp = pyr.levels[d][l]
             assert np.array_equal(got, exp), f"level {l} dir {d}: {(got != exp).sum()} texels differ"
+            if l >= 1:
+                arr = grid.download_array(l, d)
+                assert np.array_equal(arr, exp), f"array level {l} dir {d}: {(arr != exp).sum()} texels differ"
 
 
 @pytest.fixture(scope="module")
@@ -85,6 +89,25 @@ def test_occupancy_masks_match_pyramid(dev, R, levels, density):
         occ, dil = _expected_occupancy(pyr, l)
         assert np.array_equal(g.occupancy(l, False), occ), f"level {l} occupancy"
         assert np.array_equal(g.occupancy(l, True), dil), f"level {l} dilated occupancy"
+    g.close()
+
+
+def test_mip_sequence_on_one_grid(dev):
+    """the mip stage skips rewriting tiles it knows to be zero: a sequence of different grids on ONE grid object
+    (dense -> sparse -> empty -> other sparse -> dense) must give the same pyramids as fresh builds"""
+    R, levels = 64, 7
+    rng = np.random.default_rng(11)
+    g = capi.Grid(dev, R, levels)
+    for density in (1.0, 0.002, 0.0, 0.004, 0.002, 1.0):
+        base = rng.integers(0, 2 ** 32, (R, R, R), dtype=np.uint64).astype(np.uint32)
+        base[rng.random((R, R, R)) >= density] = 0
+        g.upload_base(base)
+        capi.check(dev.L.vct_mipmap(dev.h, g.h))
+        pyr = orc.mipmap(base, levels)
+        assert_pyramid_equal(g, pyr)
+        for l in range(levels):
+            occ, dil = _expected_occupancy(pyr, l)
+            assert np.array_equal(g.occupancy(l, False), occ) and np.array_equal(g.occupancy(l, True), dil)
     g.close()
 
 

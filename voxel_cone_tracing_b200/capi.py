@@ -18,7 +18,7 @@ EXPORTS = [
     "vct_scene_create", "vct_scene_destroy", "vct_scene_set_geometry", "vct_scene_set_materials", "vct_scene_set_draws",
     "vct_scene_set_lights", "vct_scene_set_cube_size",
     "vct_grid_create", "vct_grid_destroy", "vct_grid_clear", "vct_grid_upload_base", "vct_grid_download",
-    "vct_grid_base_device_ptr", "vct_grid_bytes", "vct_grid_occupancy_words", "vct_grid_download_occupancy",
+    "vct_grid_base_device_ptr", "vct_grid_bytes", "vct_grid_occupancy_words", "vct_grid_download_occupancy", "vct_grid_download_array",
     "vct_target_create", "vct_target_destroy", "vct_target_download_frame", "vct_target_download_gbuffer", "vct_target_frame_device_ptr",
     "vct_voxelize", "vct_voxelize_reserve", "vct_voxelize_stats", "vct_mipmap", "vct_gbuffer", "vct_cone_trace", "vct_cone_trace_count",
     "vct_render_frame", "vct_last_frame_timings",
@@ -93,6 +93,7 @@ def load():
     L.vct_grid_bytes.argtypes = [vp]; L.vct_grid_bytes.restype = C.c_size_t
     L.vct_grid_occupancy_words.argtypes = [vp, i32, i32]; L.vct_grid_occupancy_words.restype = C.c_size_t
     L.vct_grid_download_occupancy.argtypes = [vp, i32, i32, vp]
+    L.vct_grid_download_array.argtypes = [vp, i32, i32, vp]
     L.vct_target_create.argtypes = [vp, i32, i32, C.POINTER(vp)]
     L.vct_target_destroy.argtypes = [vp]
     L.vct_target_download_frame.argtypes = [vp, vp]
@@ -163,6 +164,13 @@ class Grid:
         n = self.R >> level
         out = np.empty((n, n, n), np.uint32)
         check(self.dev.L.vct_grid_download(self.h, level, d, out.ctypes.data))
+        return out
+
+    def download_array(self, level: int, d: int) -> np.ndarray:
+        """level >= 1 as stored in the mipmapped CUDA array the texture units read"""
+        n = self.R >> level
+        out = np.empty((n, n, n), np.uint32)
+        check(self.dev.L.vct_grid_download_array(self.h, level, d, out.ctypes.data))
         return out
 
     def occupancy(self, level: int, dilated: bool) -> np.ndarray:

@@ -276,7 +276,7 @@ int vct_grid_destroy(vct_grid_t* g) {
   if (!g) return VCT_OK;
   if (g->dev->peer_grid == g) vct_peer_disconnect(g->dev);
   cudaStreamSynchronize(g->dev->stream);
-  cudaFree(g->base_buf[0]); cudaFree(g->base_buf[1]);
+  cudaFree(g->base_buf[0]); cudaFree(g->base_buf[1]); cudaFree(g->tile_zero);
   for (int l = 0; l < VCT_MAX_LEVELS; l++) { cudaFree(g->lvl[l]); cudaFree(g->occ[l]); cudaFree(g->docc[l]); }
   for (int d = 0; d < 6; d++) {
     if (g->tex[d]) cudaDestroyTextureObject(g->tex[d]);
@@ -313,6 +313,24 @@ int vct_grid_download(vct_grid_t* g, int level, int dir, uint32_t* host) {
     VCT_CUDA(cudaMemcpy2DAsync(host, 4, g->lvl[level] + dir, 24, 4, n, cudaMemcpyDeviceToHost, s));
   }
   VCT_CUDA(cudaStreamSynchronize(s));
+  return VCT_OK;
+}
+
+int vct_grid_download_array(vct_grid_t* g, int level, int dir, uint32_t* host) {
+  VCT_REQUIRE(g && host, "null argument");
+  VCT_REQUIRE(level >= 1 && level < g->levels, "bad level (the arrays hold levels >= 1)");
+  VCT_REQUIRE(dir >= 0 && dir < 6, "bad direction");
+  cudaArray_t arr;
+  VCT_CUDA(cudaGetMipmappedArrayLevel(&arr, g->marr[dir], (unsigned)(level - 1)));
+  const size_t N = (size_t)(g->R >> level);
+  cudaMemcpy3DParms p;
+  memset(&p, 0, sizeof p);
+  p.srcArray = arr;
+  p.dstPtr = make_cudaPitchedPtr(host, N * 4, N, N);
+  p.extent = make_cudaExtent(N, N, N);
+  p.kind = cudaMemcpyDeviceToHost;
+  VCT_CUDA(cudaMemcpy3DAsync(&p, g->dev->stream));
+  VCT_CUDA(cudaStreamSynchronize(g->dev->stream));
   return VCT_OK;
 }
 

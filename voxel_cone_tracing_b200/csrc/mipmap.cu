@@ -13,6 +13,8 @@
 // Arithmetic = oracle rules R5/R6 (built with -fmad=false): c/255.0f correctly rounded (multiply
 // by 1/255 plus one exact Newton step, verified for all 256 inputs), blend f + (1-f.a)*b per
 // mipmap.comp:40-43, sum of the four pairs in order, /4, rint(clamp*255) -> bit-exact vs the oracle.
+#include <cuda.h>
+
 #include "vct_internal.cuh"
 
 namespace vct {
@@ -107,66 +109,130 @@ __global__ void mip_generic_kernel(const uint32_t* __restrict__ src, uint32_t* _
 }
 
 // ---------------------------------------------------------------------------------------------
-// fused levels 0 -> 1,2,3.  Tile = 32 x 8 x 8 level-0 texels, 256 threads.
+// fused levels 0 -> 1,2,3.  Tile = 32 x 8 x 8 level-0 texels (8 KB).  PERSISTENT kernel: each CTA walks tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ...; the tiles are fetched by TMA (cp.async.bulk.tensor.3d, one instruction per
+// tile, issued by one thread) into a ring of kLowStages shared-memory buffers and signalled through mbarriers, so that
+// kLowStages-1 tiles per CTA are in flight while one is being reduced -- the HBM stream never waits for the arithmetic.
 constexpr int TX = 32, TY = 8, TZ = 8;
+constexpr int kLowStages = 4;
+constexpr uint32_t kLowTileBytes = TX * TY * TZ * 4;
 
-__global__ void __launch_bounds__(256)
-mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l1, uint32_t* __restrict__ l2, uint32_t* __restrict__ l3, int R, const SurfSet surf,
-                     uint32_t* __restrict__ occ0, uint16_t* __restrict__ occ1, uint8_t* __restrict__ occ2) {
-  __shared__ __align__(16) uint32_t s0[TZ][TY][TX];           // 8 KB
-  __shared__ uint32_t s1[TZ / 2][TY / 2][TX / 2][6];          // 6 KB
-  __shared__ uint32_t s2[TZ / 4][TY / 4][TX / 4][6];          // 768 B
-  const int tiles_x = R / TX, tiles_y = R / TY;
-  const int bx = blockIdx.x % tiles_x, by = (blockIdx.x / tiles_x) % tiles_y, bz = blockIdx.x / (tiles_x * tiles_y);
+struct LowArgs {
+  uint32_t *l1, *l2, *l3;
+  uint32_t* occ0; uint16_t* occ1; uint8_t* occ2;
+  int R, n_tiles, log_tiles_x, log_tiles_y;
+  uint8_t* tile_zero;   // per tile: 1 = every output of this tile (levels 1-3, both copies, occupancy bits) is known to be zero
+  SurfSet surf;
+};
+
+struct LowSmem {
+  uint32_t s0[kLowStages][TZ][TY][TX];         // 4 x 8 KB, TMA destinations (128-byte aligned)
+  uint32_t s1[TZ / 2][TY / 2][TX / 2][6];      // 6 KB
+  uint32_t s2[TZ / 4][TY / 4][TX / 4][6];      // 768 B
+  uint32_t s3[TX / 8][6];                      // 96 B
+  uint32_t zero_flag[kLowStages];              // tile_zero[] of the tile in each stage, prefetched with the tile
+  unsigned long long full[kLowStages];         // mbarriers: "tile landed"
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// one thread: arm the barrier with the tile size and start the 3-D tensor copy global -> shared
+__device__ __forceinline__ void tma_load_tile(const CUtensorMap* tmap, void* dst, unsigned long long* bar, int x, int y, int z) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(kLowTileBytes) : "memory");
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(dst)),
+               "l"(tmap), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// R is a power of two (vct_grid_create), so are the tile counts: shifts instead of integer divisions
+__device__ __forceinline__ void low_tile_coords(int tile, int log_tiles_x, int log_tiles_y, int& bx, int& by, int& bz) {
+  bx = tile & ((1 << log_tiles_x) - 1);
+  by = (tile >> log_tiles_x) & ((1 << log_tiles_y) - 1);
+  bz = tile >> (log_tiles_x + log_tiles_y);
+}
+
+// Writes one level's share of a tile from shared memory (or zeros when src == nullptr) with 16-byte stores:
+// ROWS rows of NX texels; records: a row is NX*24 contiguous bytes; arrays: per direction NX*4 contiguous bytes.
+template <int NX, int ROWS_Y, int ROWS_Z>
+__device__ __forceinline__ void low_store_level(const uint32_t* __restrict__ src /* [ROWS_Z][ROWS_Y][NX][6] */, uint32_t* __restrict__ rec, const SurfSet& surf, int level,
+                                                int N, int x1, int y1, int z1, int t) {
+  constexpr int kRowQuads = NX * 6 / 4;            // uint4 per record row
+  constexpr int kRecQuads = ROWS_Y * ROWS_Z * kRowQuads;
+  for (int u = t; u < kRecQuads; u += 256) {
+    const int row = u / kRowQuads, q = u % kRowQuads, y = row % ROWS_Y, z = row / ROWS_Y;
+    const uint4 v = src ? *reinterpret_cast<const uint4*>(src + (size_t)row * NX * 6 + 4 * q) : make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(rec + (((size_t)(z1 + z) * N + (y1 + y)) * N + x1) * 6 + 4 * q) = v;
+  }
+  constexpr int kXQ = NX / 4;                       // 4 texels (16 bytes) per surface store
+  constexpr int kSurfQuads = ROWS_Y * ROWS_Z * 6 * kXQ;
+  for (int u = t; u < kSurfQuads; u += 256) {
+    const int xq = u % kXQ, d = (u / kXQ) % 6, row = u / (kXQ * 6), y = row % ROWS_Y, z = row / ROWS_Y;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (src) {
+      const uint32_t* p = src + ((size_t)row * NX + 4 * xq) * 6 + d;
+      v = make_uint4(p[0], p[6], p[12], p[18]);
+    }
+    surf3Dwrite(v, surf.s[d][level], (x1 + 4 * xq) * 4, y1 + y, z1 + z);
+  }
+}
+
+// reduces one staged tile; every thread of the CTA calls it (contains barriers)
+__device__ __forceinline__ void low_process_tile(const uint32_t (&s0)[TZ][TY][TX], uint32_t (&s1)[TZ / 2][TY / 2][TX / 2][6],
+                                                 uint32_t (&s2)[TZ / 4][TY / 4][TX / 4][6], uint32_t (&s3)[TX / 8][6], const LowArgs& a, int tile,
+                                                 uint32_t known_zero, int bx, int by, int bz) {
+  const int R = a.R;
+  uint32_t* __restrict__ occ0 = a.occ0; uint16_t* __restrict__ occ1 = a.occ1; uint8_t* __restrict__ occ2 = a.occ2;
   const int x0 = bx * TX, y0 = by * TY, z0 = bz * TZ;
   const int t = threadIdx.x;
+  const int N1 = R >> 1, N2 = R >> 2, N3 = R >> 3;
 
-  // ---- stage the level-0 tile: 64 rows of 128 B, two 16-byte loads per thread ----
-  uint32_t any0 = 0;
+  // ---- "is the tile empty": 64 rows of 128 B, two 16-byte shared loads per thread ----
+  uint4 v0[2];
+#pragma unroll
+  for (int k = 0; k < 2; k++) v0[k] = *reinterpret_cast<const uint4*>(&s0[((t >> 3) + 32 * k) >> 3][((t >> 3) + 32 * k) & 7][4 * (t & 7)]);
+  const uint32_t any0 = (v0[0].x | v0[0].y | v0[0].z | v0[0].w) | (v0[1].x | v0[1].y | v0[1].z | v0[1].w);
+  const int tile_nonzero = __syncthreads_or((int)(any0 != 0u));
+  // empty now and every output (incl. the occupancy words) known to be zero from the previous build: nothing to write.
+  // The usual case: < 1 % of the grid is occupied and the occupied set moves little between frames.
+  if (!tile_nonzero && known_zero) return;
+  // ---- occupancy bits of level 0: 8 consecutive lanes hold the 32 voxels of a row ----
 #pragma unroll
   for (int k = 0; k < 2; k++) {
     const int row = (t >> 3) + 32 * k, quad = t & 7;
     const int y = row & 7, z = row >> 3;
-    const uint4 v = *reinterpret_cast<const uint4*>(base + ((size_t)(z0 + z) * R + (y0 + y)) * R + x0 + 4 * quad);
-    *reinterpret_cast<uint4*>(&s0[z][y][4 * quad]) = v;
-    any0 |= v.x | v.y | v.z | v.w;
-    // occupancy bits of the row: 8 consecutive lanes hold its 32 voxels
+    const uint4 v = v0[k];
     uint32_t bits = ((v.x != 0u) | (v.y != 0u) << 1 | (v.z != 0u) << 2 | (v.w != 0u) << 3) << (4 * quad);
     bits |= __shfl_xor_sync(0xffffffffu, bits, 1);
     bits |= __shfl_xor_sync(0xffffffffu, bits, 2);
     bits |= __shfl_xor_sync(0xffffffffu, bits, 4);
     if (quad == 0) occ0[((size_t)(z0 + z) * R + (y0 + y)) * (R / 32) + bx] = bits;
   }
-  const int tile_nonzero = __syncthreads_or((int)(any0 != 0u));
-  const int N1 = R >> 1, N2 = R >> 2, N3 = R >> 3;
 
   if (!tile_nonzero) {
-    // empty tile: every output of this tile is zero
-    {
-      const int x = t & 15, y = (t >> 4) & 3, z = t >> 6;
-      uint2* o = reinterpret_cast<uint2*>(l1 + (((size_t)(z0 / 2 + z) * N1 + (y0 / 2 + y)) * N1 + (x0 / 2 + x)) * 6);
-      o[0] = make_uint2(0u, 0u); o[1] = make_uint2(0u, 0u); o[2] = make_uint2(0u, 0u);
-#pragma unroll
-      for (int d = 0; d < 6; d++) surf3Dwrite(0u, surf.s[d][1], (x0 / 2 + x) * 4, y0 / 2 + y, z0 / 2 + z);
-      if (x == 0) occ1[((size_t)(z0 / 2 + z) * N1 + (y0 / 2 + y)) * (N1 / 16) + bx] = 0;
-    }
-    if (t >= 192 && t < 196) {
-      const int y = t & 1, z = (t >> 1) & 1;
-      occ2[((size_t)(z0 / 4 + z) * N2 + (y0 / 4 + y)) * (N2 / 8) + bx] = 0;
-    }
-    if (t < 192) {
-      const int d = t % 6, tex = t / 6, x = tex & 7, y = (tex >> 3) & 1, z = tex >> 4;
-      l2[(((size_t)(z0 / 4 + z) * N2 + (y0 / 4 + y)) * N2 + (x0 / 4 + x)) * 6 + d] = 0u;
-      surf3Dwrite(0u, surf.s[d][2], (x0 / 4 + x) * 4, y0 / 4 + y, z0 / 4 + z);
-    }
-    if (t < 24) {
-      const int d = t % 6, x = t / 6;
-      l3[(((size_t)(z0 / 8) * N3 + (y0 / 8)) * N3 + (x0 / 8 + x)) * 6 + d] = 0u;
-      surf3Dwrite(0u, surf.s[d][3], (x0 / 8 + x) * 4, y0 / 8, z0 / 8);
-    }
+    // empty tile: every output of this tile is zero (exact: the filter of zeros is zero)
+    if (t == 0) a.tile_zero[tile] = 1;
+    if (t < 16) occ1[((size_t)(z0 / 2 + (t >> 2)) * N1 + (y0 / 2 + (t & 3))) * (N1 / 16) + bx] = 0;
+    if (t >= 32 && t < 36) occ2[((size_t)(z0 / 4 + ((t >> 1) & 1)) * N2 + (y0 / 4 + (t & 1))) * (N2 / 8) + bx] = 0;
+    low_store_level<TX / 2, TY / 2, TZ / 2>(nullptr, a.l1, a.surf, 1, N1, x0 / 2, y0 / 2, z0 / 2, t);
+    low_store_level<TX / 4, TY / 4, TZ / 4>(nullptr, a.l2, a.surf, 2, N2, x0 / 4, y0 / 4, z0 / 4, t);
+    low_store_level<TX / 8, 1, 1>(nullptr, a.l3, a.surf, 3, N3, x0 / 8, y0 / 8, z0 / 8, t);
     return;
   }
 
+  if (t == 0) a.tile_zero[tile] = 0;
   // ---- level 1: one texel per thread, six directions ----
   {
     const int x = t & 15, y = (t >> 4) & 3, z = t >> 6;
@@ -189,13 +255,8 @@ mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l
       o[0] = filter_dir<0>(c); o[1] = filter_dir<1>(c); o[2] = filter_dir<2>(c);
       o[3] = filter_dir<3>(c); o[4] = filter_dir<4>(c); o[5] = filter_dir<5>(c);
     }
-    uint2* g = reinterpret_cast<uint2*>(l1 + (((size_t)(z0 / 2 + z) * N1 + (y0 / 2 + y)) * N1 + (x0 / 2 + x)) * 6);
-    g[0] = make_uint2(o[0], o[1]); g[1] = make_uint2(o[2], o[3]); g[2] = make_uint2(o[4], o[5]);
-#pragma unroll
-    for (int d = 0; d < 6; d++) {
-      s1[z][y][x][d] = o[d];
-      surf3Dwrite(o[d], surf.s[d][1], (x0 / 2 + x) * 4, y0 / 2 + y, z0 / 2 + z);
-    }
+    uint2* sp = reinterpret_cast<uint2*>(&s1[z][y][x][0]);
+    sp[0] = make_uint2(o[0], o[1]); sp[1] = make_uint2(o[2], o[3]); sp[2] = make_uint2(o[4], o[5]);
     // a warp holds two rows of 16 texels
     const uint32_t bal = __ballot_sync(0xffffffffu, (o[0] | o[1] | o[2] | o[3] | o[4] | o[5]) != 0u);
     if (x == 0) occ1[((size_t)(z0 / 2 + z) * N1 + (y0 / 2 + y)) * (N1 / 16) + bx] = (uint16_t)(bal >> (16 * (y & 1)));
@@ -217,11 +278,9 @@ mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l
           any |= w;
           unpack4(w, c[child_id(dx, dy, dz)]);
         }
-    const uint32_t o = any ? filter_dir_dyn(c, d) : 0u;
-    l2[(((size_t)(z0 / 4 + z) * N2 + (y0 / 4 + y)) * N2 + (x0 / 4 + x)) * 6 + d] = o;
-    surf3Dwrite(o, surf.s[d][2], (x0 / 4 + x) * 4, y0 / 4 + y, z0 / 4 + z);
-    s2[z][y][x][d] = o;
+    s2[z][y][x][d] = any ? filter_dir_dyn(c, d) : 0u;
   }
+  low_store_level<TX / 2, TY / 2, TZ / 2>(&s1[0][0][0][0], a.l1, a.surf, 1, N1, x0 / 2, y0 / 2, z0 / 2, t);   // overlaps the level-2 arithmetic of other warps
   __syncthreads();
 
   if (t >= 192 && t < 196) {  // level-2 occupancy: one byte per row of 8 texels
@@ -229,10 +288,10 @@ mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l
     uint32_t bits = 0;
 #pragma unroll
     for (int x = 0; x < 8; x++) {
-      uint32_t a = 0;
+      uint32_t acc = 0;
 #pragma unroll
-      for (int d = 0; d < 6; d++) a |= s2[z][y][x][d];
-      bits |= (uint32_t)(a != 0u) << x;
+      for (int d = 0; d < 6; d++) acc |= s2[z][y][x][d];
+      bits |= (uint32_t)(acc != 0u) << x;
     }
     occ2[((size_t)(z0 / 4 + z) * N2 + (y0 / 4 + y)) * (N2 / 8) + bx] = (uint8_t)bits;
   }
@@ -251,9 +310,60 @@ mip_fused_low_kernel(const uint32_t* __restrict__ base, uint32_t* __restrict__ l
           any |= w;
           unpack4(w, c[child_id(dx, dy, dz)]);
         }
-    const uint32_t o = any ? filter_dir_dyn(c, d) : 0u;
-    l3[(((size_t)(z0 / 8) * N3 + (y0 / 8)) * N3 + (x0 / 8 + x)) * 6 + d] = o;
-    surf3Dwrite(o, surf.s[d][3], (x0 / 8 + x) * 4, y0 / 8, z0 / 8);
+    s3[x][d] = any ? filter_dir_dyn(c, d) : 0u;
+  }
+  low_store_level<TX / 4, TY / 4, TZ / 4>(&s2[0][0][0][0], a.l2, a.surf, 2, N2, x0 / 4, y0 / 4, z0 / 4, t);
+  __syncthreads();
+  low_store_level<TX / 8, 1, 1>(&s3[0][0], a.l3, a.surf, 3, N3, x0 / 8, y0 / 8, z0 / 8, t);
+}
+
+__global__ void __launch_bounds__(256, 4)
+mip_fused_low_kernel(const __grid_constant__ CUtensorMap tmap, const LowArgs a) {
+  extern __shared__ __align__(128) unsigned char low_smem_raw[];
+  LowSmem& sm = *reinterpret_cast<LowSmem*>(low_smem_raw);
+  const int t = threadIdx.x;
+  if (t == 0) {
+#pragma unroll
+    for (int s = 0; s < kLowStages; s++) mbar_init(&sm.full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // make the initialised barriers visible to the async (TMA) proxy
+  }
+  __syncthreads();
+  if (t == 0) {   // prologue: fill the ring
+#pragma unroll
+    for (int s = 0; s < kLowStages; s++) {
+      const int tile = blockIdx.x + s * gridDim.x;
+      if (tile < a.n_tiles) {
+        int bx, by, bz;
+        low_tile_coords(tile, a.log_tiles_x, a.log_tiles_y, bx, by, bz);
+        tma_load_tile(&tmap, &sm.s0[s][0][0][0], &sm.full[s], bx * TX, by * TY, bz * TZ);
+        sm.zero_flag[s] = a.tile_zero[tile];
+      }
+    }
+  }
+  __syncthreads();
+  // thread 32 prefetches the tile_zero flag of the tile that thread 0 requests, one iteration ahead of storing it to
+  // shared memory, so that the flag's global-load latency never sits on the per-tile critical path
+  uint32_t pending_value = 0;
+  int pending_slot = -1;
+  int i = 0;
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, i++) {
+    const int stage = i % kLowStages;
+    mbar_wait(&sm.full[stage], (uint32_t)((i / kLowStages) & 1));
+    int bx, by, bz;
+    low_tile_coords(tile, a.log_tiles_x, a.log_tiles_y, bx, by, bz);
+    low_process_tile(sm.s0[stage], sm.s1, sm.s2, sm.s3, a, tile, sm.zero_flag[stage], bx, by, bz);
+    __syncthreads();   // every read of this stage (and of s1/s2) is done: the buffer can be refilled
+    const int next = tile + kLowStages * gridDim.x;
+    if (t == 0) {
+      if (next < a.n_tiles) {
+        low_tile_coords(next, a.log_tiles_x, a.log_tiles_y, bx, by, bz);
+        tma_load_tile(&tmap, &sm.s0[stage][0][0][0], &sm.full[stage], bx * TX, by * TY, bz * TZ);
+      }
+    } else if (t == 32) {
+      if (pending_slot >= 0) sm.zero_flag[pending_slot] = pending_value;   // loaded one iteration ago; its stage is read >= 2 barriers from now
+      pending_slot = -1;
+      if (next < a.n_tiles) { pending_value = a.tile_zero[next]; pending_slot = stage; }
+    }
   }
 }
 
@@ -374,25 +484,67 @@ __device__ __forceinline__ uint32_t occ_row_bits(const uint32_t* __restrict__ oc
   return (occ[flat >> 5] >> (flat & 31)) & ((1u << N) - 1u);
 }
 
-// dilation: docc bit (x+1,y+1,z+1) = OR of occ over [x,x+1]x[y,y+1]x[z,z+1]; one thread per output word
-__global__ void __launch_bounds__(256)
+// dilation: docc bit (x+1,y+1,z+1) = OR of occ over [x,x+1]x[y,y+1]x[z,z+1].  One thread per output ROW (y,z): walks the
+// row's words carrying the top bit of the previous word.  grid: x = rows of one z-slice, y = z-slice, z = level
+__global__ void __launch_bounds__(128)
 occ_dilate_kernel(const OccArgs a) {
-  const int level = (int)blockIdx.y;
+  const int level = (int)blockIdx.z;
   const int N = a.R >> level, D = N + 1, wpr = occ_wpr(N);
-  const size_t n = (size_t)D * D * wpr;
-  const uint32_t* occ = a.occ[level];
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-    const int k = (int)(i % wpr), y = (int)((i / wpr) % D) - 1, z = (int)(i / ((size_t)wpr * D)) - 1;
-    uint32_t r = 0, rp = 0;
+  const int zz = (int)blockIdx.y, yy = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (zz >= D || yy >= D) return;
+  const uint32_t* __restrict__ occ = a.occ[level];
+  uint32_t* __restrict__ out = a.docc[level] + ((size_t)zz * D + yy) * wpr;
+  const int y = yy - 1, z = zz - 1;
+  if (N >= 32) {
+    const int nw = N >> 5;
+    const uint32_t* rows[4];
+    bool ok[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const int ry = y + (q & 1), rz = z + (q >> 1);
+      ok[q] = (unsigned)ry < (unsigned)N && (unsigned)rz < (unsigned)N;
+      rows[q] = occ + ((size_t)(ok[q] ? rz : 0) * N + (ok[q] ? ry : 0)) * nw;
+    }
+    uint32_t carry = 0;
+    for (int k = 0; k < wpr; k++) {
+      uint32_t r = 0;
+      if (k < nw) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) r |= ok[q] ? __ldg(rows[q] + k) : 0u;
+      }
+      out[k] = (r << 1) | carry | r;
+      carry = r >> 31;
+    }
+  } else {
+    uint32_t r = 0;
 #pragma unroll
     for (int dz = 0; dz < 2; dz++)
 #pragma unroll
-      for (int dy = 0; dy < 2; dy++) {
-        r |= occ_row_bits(occ, N, y + dy, z + dz, k);
-        rp |= occ_row_bits(occ, N, y + dy, z + dz, k - 1);
-      }
-    a.docc[level][i] = (r << 1) | (rp >> 31) | r;
+      for (int dy = 0; dy < 2; dy++) r |= occ_row_bits(occ, N, y + dy, z + dz, 0);
+    out[0] = (r << 1) | r;
   }
+}
+
+// TMA descriptor of one level-0 buffer: 3-D u32 tensor R x R x R (x fastest), box = one 32 x 8 x 8 tile
+static int make_base_tensor_map(uint32_t* base, int R, CUtensorMap* out) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    VCT_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available from the driver"); return VCT_ERR_CUDA; }
+    encode = (encode_fn)fn;
+  }
+  const cuuint64_t dims[3] = {(cuuint64_t)R, (cuuint64_t)R, (cuuint64_t)R};
+  const cuuint64_t strides[2] = {(cuuint64_t)R * 4, (cuuint64_t)R * R * 4};   // bytes, dims 1 and 2
+  const cuuint32_t box[3] = {TX, TY, TZ};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = encode(out, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return VCT_ERR_CUDA; }
+  return VCT_OK;
 }
 
 int launch_mipmap(vct_device* dev, vct_grid* g) {
@@ -402,8 +554,26 @@ int launch_mipmap(vct_device* dev, vct_grid* g) {
   int occ_from_data = 0;
   if (g->levels >= 4 && R % 32 == 0 && R >= 32) {
     const int n_tiles = (R / TX) * (R / TY) * (R / TZ);
-    mip_fused_low_kernel<<<n_tiles, 256, 0, s>>>(g->base, g->lvl[1], g->lvl[2], g->lvl[3], R, g->surf, g->occ[0], (uint16_t*)g->occ[1],
-                                                 (uint8_t*)g->occ[2]);
+    const int buf = g->base == g->base_buf[1] ? 1 : 0;
+    if (g->tmap_base_ptr[buf] != g->base) {   // descriptor of this level-0 buffer (built once)
+      int rc = make_base_tensor_map(g->base, R, reinterpret_cast<CUtensorMap*>(g->tmap_storage[buf]));
+      if (rc) return rc;
+      g->tmap_base_ptr[buf] = g->base;
+    }
+    LowArgs la;
+    la.l1 = g->lvl[1]; la.l2 = g->lvl[2]; la.l3 = g->lvl[3];
+    la.occ0 = g->occ[0]; la.occ1 = (uint16_t*)g->occ[1]; la.occ2 = (uint8_t*)g->occ[2];
+    la.R = R; la.n_tiles = n_tiles; la.surf = g->surf;
+    la.log_tiles_x = 0; la.log_tiles_y = 0;
+    while ((TX << la.log_tiles_x) < R) la.log_tiles_x++;
+    while ((TY << la.log_tiles_y) < R) la.log_tiles_y++;
+    if (!g->tile_zero) {
+      VCT_CUDA(cudaMalloc(&g->tile_zero, (size_t)n_tiles));
+      VCT_CUDA(cudaMemsetAsync(g->tile_zero, 0, (size_t)n_tiles, s));   // unknown: the first build writes everything
+    }
+    la.tile_zero = g->tile_zero;
+    const int ctas = min(n_tiles, dev->prop.multiProcessorCount * 4);   // persistent: 4 CTAs of 40 KB shared memory per SM
+    mip_fused_low_kernel<<<ctas, 256, sizeof(LowSmem), s>>>(*reinterpret_cast<const CUtensorMap*>(g->tmap_storage[buf]), la);
     level = 3;
     occ_from_data = 3;  // levels 0..2 got their occupancy bits from the fused kernel
     if (g->levels >= 7 && (R >> 3) % 8 == 0) {
@@ -427,7 +597,7 @@ int launch_mipmap(vct_device* dev, vct_grid* g) {
     const size_t n = (size_t)(R >> occ_from_data) * (R >> occ_from_data) * (R >> occ_from_data);
     occ_bits_kernel<<<dim3(grid_for(n, 256, 148 * 8), g->levels - occ_from_data), 256, 0, s>>>(oa);
   }
-  occ_dilate_kernel<<<dim3(grid_for(docc_words(R), 256, 148 * 8), g->levels), 256, 0, s>>>(oa);
+  occ_dilate_kernel<<<dim3((R + 1 + 127) / 128, R + 1, g->levels), 128, 0, s>>>(oa);
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;
 }

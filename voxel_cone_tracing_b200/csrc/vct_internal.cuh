@@ -200,6 +200,9 @@ struct vct_grid {
   cudaMipmappedArray_t marr[6] = {};
   cudaTextureObject_t tex[6] = {};
   vct::SurfSet surf{};
+  alignas(64) unsigned char tmap_storage[2][128] = {};   // CUtensorMap (TMA descriptor) of base_buf[0] / base_buf[1], built on first use
+  uint32_t* tmap_base_ptr[2] = {};
+  uint8_t* tile_zero = nullptr;         // mip stage: per 32x8x8 tile "levels 1-3 of this tile are known to be zero" (skip rewriting zeros)
   uint32_t* occ[VCT_MAX_LEVELS] = {};   // non-dilated occupancy bits per level
   uint32_t* docc[VCT_MAX_LEVELS] = {};  // dilated occupancy bits per level
   vct::GridView view() const {

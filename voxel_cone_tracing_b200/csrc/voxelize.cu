@@ -29,7 +29,7 @@ __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f),
 
 __global__ void __launch_bounds__(kSetupThreads)
 vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ draws,
-                 uint32_t n_draws, uint32_t n_tris, float cube_size, int R, VoxTri* __restrict__ out, uint32_t* __restrict__ item_local,
+                 uint32_t n_draws, uint32_t n_tris, float cube_size, int R, int z0, int z1, VoxTri* __restrict__ out, uint32_t* __restrict__ item_local,
                  uint32_t* __restrict__ item_block) {
   uint32_t t = blockIdx.x * kSetupThreads + threadIdx.x;
   uint32_t count = 0;
@@ -68,6 +68,13 @@ vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
       yw[k] = (b + 1.0f) * half;
     }
     raster_setup(xw, yw, 2 * R, 2 * R, v.rt);
+    if (z0 > 0 || z1 < R) {
+      // z-slab voxelization (multi-GPU): a fragment's z is a convex combination of the vertex z's, so a triangle whose
+      // voxel-z range (widened by one voxel for interpolation rounding) misses [z0,z1) cannot contribute: no items
+      const float zmin = fminf(v.wp[0][2], fminf(v.wp[1][2], v.wp[2][2])), zmax = fmaxf(v.wp[0][2], fmaxf(v.wp[1][2], v.wp[2][2]));
+      const float vz_lo = (float)R * (0.5f * zmin + 0.5f) - 1.0f, vz_hi = (float)R * (0.5f * zmax + 0.5f) + 1.0f;
+      if (vz_hi < (float)z0 || vz_lo >= (float)z1) { v.rt.sign = 0; v.rt.imin = 0; v.rt.imax = -1; v.rt.jmin = 0; v.rt.jmax = -1; }
+    }
     v.material = d.material;
     v.axis = axis;
     out[t] = v;
@@ -286,7 +293,7 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
   VoxTri* tris = (VoxTri*)dev->tri_recs;
   const int sms = dev->prop.multiProcessorCount;
   if (sc->n_tris) {   // an empty scene still runs the resolve kernel in multi-GPU mode: the peers wait for its signal
-    vox_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, sc->cube_size, g->R, tris,
+    vox_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, sc->cube_size, g->R, z0, z1, tris,
                                                           dev->item_local, dev->item_block);
     scan_block_totals_kernel<<<1, 1024, 0, s>>>(dev->item_block, n_blocks, dev->counters + CNT_ITEMS);
     vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->item_local, dev->item_block, n_blocks, sc->mats, sc->lights, sc->cube_size,
