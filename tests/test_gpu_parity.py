@@ -140,6 +140,32 @@ def test_voxelize_bit_exact(R, suzanne):
     p.close()
 
 
+def test_synthetic_many_small_triangles():
+    """BASELINE configs 4/5 in miniature: thousands of sub-voxel / sub-pixel triangles (icospheres) take the in-thread
+    small-triangle path of both rasterisers; big wall triangles take the 8x8 item path.  Grid, G-buffer and frame vs the oracle."""
+    sc = S.synthetic_scene(60_000, 0x5EED0001)
+    R, W, H = 64, 320, 240
+    exp, st = orc.voxelize(sc, R)
+    assert st.fragments > 50_000 and st.tris_no_frag > 10_000       # mostly sub-pixel triangles; many emit nothing (non-conservative raster)
+    view, proj = S.reference_camera(W / H, eye=(0.0, 0.3, 2.6))
+    p = capi.Pipeline(sc, R, W, H, reserve=1 << 21)
+    p.clear(); p.voxelize()
+    gst = p.voxel_stats()
+    assert gst.fragments == st.fragments and gst.occupied == st.occupied and gst.max_per_voxel == st.max_per_voxel
+    assert np.array_equal(p.grid.download(0), exp)
+    eg = orc.gbuffer(sc, view, proj, W, H)
+    p.gbuffer(view, proj)
+    got = p.target.gbuffer()
+    assert np.array_equal(got["tri_id"], eg.tri_id)
+    hit = eg.tri_id != 0xFFFFFFFF
+    assert np.array_equal(got["world_pos"][hit], eg.world_pos[hit]) and np.array_equal(got["normal"][hit], eg.normal[hit])
+    for sampler in SAMPLERS:
+        p.render_frame(view, proj, capi.default_params(sampler=sampler))
+        ref = orc.render_frame(sc, view, proj, R, W, H)
+        _check_frame(p.target.frame(), ref)
+    p.close()
+
+
 def test_voxelize_slabs_equal_full():
     sc = S.cornell_scene(with_suzanne=True)
     R = 128

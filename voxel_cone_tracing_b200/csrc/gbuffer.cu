@@ -15,13 +15,17 @@
 namespace vct {
 
 struct Mat4 { float m[16]; };
+constexpr int kSmallCamPixels = 36;
 
 __global__ void __launch_bounds__(kSetupThreads)
 cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ draws,
                  uint32_t n_draws, uint32_t n_tris, Mat4 pv, int W, int H, CamTri* __restrict__ out, uint32_t* __restrict__ item_local,
-                 uint32_t* __restrict__ item_block) {
+                 uint32_t* __restrict__ item_block, unsigned long long* __restrict__ vis, int tile_rank, int tile_nranks, int small_limit) {
   uint32_t t = blockIdx.x * kSetupThreads + threadIdx.x;
   uint32_t count = 0;
+  RasterTri srt;   // copy for the small-triangle path below
+  srt.sign = 0; srt.imin = 0; srt.imax = -1; srt.jmin = 0; srt.jmax = -1;
+  float sz0 = 0.f, sz1 = 0.f, sz2 = 0.f;
   if (t < n_tris) {
     const DrawRec& d = draws[find_draw(t, draws, n_draws)];
     uint32_t first = d.first_index + 3u * (t - d.tri_base);
@@ -60,9 +64,25 @@ cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
     else { v.rt.sign = 0; v.rt.imin = 0; v.rt.imax = -1; v.rt.jmin = 0; v.rt.jmax = -1; v.rt.area = 0; }
     v.material = d.material;
     v.pad = 0;
-    out[t] = v;
+    out[t] = v;   // always: the resolve kernel reads the record of whichever triangle wins a pixel
     count = raster_item_count(v.rt);
+    srt = v.rt; sz0 = v.zw[0]; sz1 = v.zw[1]; sz2 = v.zw[2];
   }
+  // ---- small triangles (bounding box of at most kSmallCamPixels pixel centres): depth-tested right here, one lane per
+  //      triangle, instead of one warp per 8x8 item ----
+  const int bw = srt.imax - srt.imin + 1, bh = srt.jmax - srt.jmin + 1;
+  const bool small = count > 0 && bw * bh <= small_limit;
+  const int npx = small ? bw * bh : 0;
+  for (int p = 0; p < npx; p++) {
+    const int i = srt.imin + p % bw, j = srt.jmin + p / bw;
+    if (tile_nranks > 1 && ((j >> 5) * ((W + 31) >> 5) + (i >> 5)) % tile_nranks != tile_rank) continue;   // multi-GPU: not this rank's screen tile
+    float b[3];
+    if (raster_sample(srt, i, j, b)) {
+      const float zw = interp3(b, sz0, sz1, sz2);
+      if (zw >= 0.0f && zw <= 1.0f) atomicMin(&vis[(size_t)j * W + i], ((unsigned long long)__float_as_uint(zw) << 32) | (unsigned long long)t);
+    }
+  }
+  if (small) count = 0;
   block_scan_items(count, t, n_tris, item_local, item_block);
 }
 
@@ -84,12 +104,14 @@ cam_raster_kernel(const CamTri* __restrict__ tris, uint32_t n_tris, const uint32
     const int tx = (rt.imin >> 3) + (int)(rank % (uint32_t)tiles_x), ty = (rt.jmin >> 3) + (int)(rank / (uint32_t)tiles_x);
     // multi-GPU: only the 32x32 screen tiles this rank shades need visibility
     if (tile_nranks > 1 && ((ty >> 2) * ((W + 31) >> 5) + (tx >> 2)) % tile_nranks != tile_rank) continue;
+    EdgeBlock eb;
+    edge_block_setup(rt, tx * kTile, ty * kTile, eb);
 #pragma unroll
     for (int h = 0; h < 2; h++) {
       const int p = lane + 32 * h;
       const int i = tx * kTile + (p & 7), j = ty * kTile + (p >> 3);
       float b[3];
-      if (i >= rt.imin && i <= rt.imax && j >= rt.jmin && j <= rt.jmax && raster_sample(rt, i, j, b)) {
+      if (i >= rt.imin && i <= rt.imax && j >= rt.jmin && j <= rt.jmax && edge_block_sample(eb, p & 7, p >> 3, b)) {
         const float zw = interp3(b, z0, z1, z2);
         if (zw >= 0.0f && zw <= 1.0f) {  // near / far (R3); also rejects NaN
           const unsigned long long key = ((unsigned long long)__float_as_uint(zw) << 32) | (unsigned long long)ti;
@@ -176,7 +198,8 @@ int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const floa
     const uint32_t n_blocks = (sc->n_tris + kSetupThreads - 1) / kSetupThreads;
     CamTri* tris = (CamTri*)dev->tri_recs;
     cam_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, pv, t->W, t->H, tris,
-                                                        dev->item_local, dev->item_block);
+                                                        dev->item_local, dev->item_block, t->vis, tile_rank, tile_nranks,
+                                                        sc->n_tris >= kSmallPathMinTris ? kSmallCamPixels : 0);
     scan_block_totals_kernel<<<1, 1024, 0, s>>>(dev->item_block, n_blocks, dev->counters + CNT_CAM_ITEMS);
     cam_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->item_local, dev->item_block, n_blocks, t->W, t->vis, dev->counters, tile_rank, tile_nranks);
     cam_resolve_kernel<<<sms * 8, 256, 0, s>>>(tris, t->vis, t->W, t->H, t->world_pos, t->normal, t->material, t->vis, tile_rank, tile_nranks);

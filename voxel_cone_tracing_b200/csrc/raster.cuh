@@ -17,7 +17,9 @@ namespace vct {
 
 constexpr int kSetupThreads = 256;
 constexpr int kTile = 8;  // 8x8 pixels per item
-
+// The in-thread small-triangle path of the setup kernels pays off when there are many triangles; a scene of a few thousand
+// triangles has too few setup threads to hide the fragment work there, its 8x8 items parallelise better.
+constexpr uint32_t kSmallPathMinTris = 32768;
 __device__ __forceinline__ int imin3(int a, int b, int c) { return min(a, min(b, c)); }
 __device__ __forceinline__ int imax3(int a, int b, int c) { return max(a, max(b, c)); }
 
@@ -74,6 +76,41 @@ __device__ __forceinline__ bool raster_sample(const RasterTri& t, int i, int j, 
   b[0] = (float)E[0] / fa;
   b[1] = (float)E[1] / fa;
   b[2] = (float)E[2] / fa;
+  return true;
+}
+
+// The same coverage test and barycentrics as raster_sample, factored for a block of pixels: the three edge functions are
+// evaluated once (64-bit) at pixel (i0,j0); a pixel at offset (ox,oy) then costs two 32x32->64 multiply-adds per edge.
+// E_k(px + 256*ox, py + 256*oy) = E_k(px,py) + dx_k*256*oy - dy_k*256*ox -- exact integers, identical to raster_sample.
+struct EdgeBlock {
+  long long e0[3];
+  int dx[3], dy[3];   // after the orientation flip
+  float fa;
+};
+__device__ __forceinline__ void edge_block_setup(const RasterTri& t, int i0, int j0, EdgeBlock& q) {
+  const long long px = (long long)i0 * 256 + 128, py = (long long)j0 * 256 + 128;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const int a = (k + 1) % 3, c = (k + 2) % 3;
+    int dx = t.X[c] - t.X[a], dy = t.Y[c] - t.Y[a];   // |X|,|Y| <= 2^29: no overflow
+    long long e = (long long)dx * (py - t.Y[a]) - (long long)dy * (px - t.X[a]);
+    if (t.sign < 0) { e = -e; dx = -dx; dy = -dy; }
+    q.e0[k] = e; q.dx[k] = dx; q.dy[k] = dy;
+  }
+  q.fa = (float)t.area;
+}
+__device__ __forceinline__ bool edge_block_sample(const EdgeBlock& q, int ox, int oy, float b[3]) {
+  long long E[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const long long e = q.e0[k] + (long long)q.dx[k] * (256 * oy) - (long long)q.dy[k] * (256 * ox);
+    if (e < 0) return false;
+    if (e == 0 && !((q.dy[k] < 0) || (q.dy[k] == 0 && q.dx[k] < 0))) return false;  // top-left rule
+    E[k] = e;
+  }
+  b[0] = (float)E[0] / q.fa;
+  b[1] = (float)E[1] / q.fa;
+  b[2] = (float)E[2] / q.fa;
   return true;
 }
 

@@ -27,16 +27,103 @@ __device__ __forceinline__ F3 cross(F3 a, F3 b) { return f3(a.y * b.z - b.y * a.
 __device__ __forceinline__ F3 normalize(F3 a) { float l = sqrtf(dot(a, a)); return f3(a.x / l, a.y / l, a.z / l); }
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 
+// fragment colour (voxelize.frag:122-153), returns colour * 255
+__device__ __forceinline__ void shade_fragment(const VoxTri& v, const float b[3], const vct_material_t* __restrict__ mats, const Lights& L,
+                                               float cube_size, F3& pos, float val[4]) {
+  pos = f3(interp3(b, v.wp[0][0], v.wp[1][0], v.wp[2][0]), interp3(b, v.wp[0][1], v.wp[1][1], v.wp[2][1]),
+           interp3(b, v.wp[0][2], v.wp[1][2], v.wp[2][2]));
+  F3 nrm = f3(interp3(b, v.nn[0][0], v.nn[1][0], v.nn[2][0]), interp3(b, v.nn[0][1], v.nn[1][1], v.nn[2][1]),
+              interp3(b, v.nn[0][2], v.nn[1][2], v.nn[2][2]));
+  F3 color = f3(0.f, 0.f, 0.f);
+  for (int i = 0; i < L.n; i++) {
+    F3 lp = f3(L.l[i].position[0] / cube_size, L.l[i].position[1] / cube_size, L.l[i].position[2] / cube_size);
+    F3 dv = sub(lp, pos);
+    float dist = sqrtf(dot(dv, dv));
+    F3 dir = f3(dv.x / dist, dv.y / dist, dv.z / dist);
+    float att = 1.0f / ((1.0f + 0.0f * dist) + (1.0f * dist) * dist);
+    float cos_surf = fmaxf(dot(normalize(nrm), dir), 0.0f);
+    float s = cos_surf * att;
+    color.x = color.x + (L.l[i].color[0] * s) * L.l[i].intensity;
+    color.y = color.y + (L.l[i].color[1] * s) * L.l[i].intensity;
+    color.z = color.z + (L.l[i].color[2] * s) * L.l[i].intensity;
+  }
+  const vct_material_t& m = mats[v.material];
+  color = f3(m.diffuse[0] * color.x + m.emission[0], m.diffuse[1] * color.y + m.emission[1], m.diffuse[2] * color.z + m.emission[2]);
+  float tr0 = 1.f, tr1 = 1.f, tr2 = 1.f, alpha = 1.f;
+  if (m.illum == 4 || m.illum == 6 || m.illum == 7 || m.illum == 9) {
+    tr0 = m.transmittance[0]; tr1 = m.transmittance[1]; tr2 = m.transmittance[2];
+    alpha = m.dissolve;
+  }
+  val[0] = clamp01(tr0 * color.x) * 255.0f;
+  val[1] = clamp01(tr1 * color.y) * 255.0f;
+  val[2] = clamp01(tr2 * color.z) * 255.0f;
+  val[3] = clamp01(alpha) * 255.0f;
+}
+
+// what the fragment stage needs besides the triangle
+struct FragCtx {
+  const vct_material_t* mats;
+  Lights L;
+  float cube_size;
+  int R, z0, z1;
+  uint32_t* base;
+  FragRec* frags;
+  uint32_t frag_capacity;
+  uint32_t* occupied;
+  uint32_t* counters;
+};
+
+// One fragment candidate per lane (covered = the pixel centre is inside the triangle): shade it, find its voxel
+// (voxelize.frag:156-157: truncation, then the image bounds check; multi-GPU: the z-slab test) and append it to the voxel's list.
+// Must be called by all 32 lanes of the warp (warp-aggregated arena allocation).
+__device__ __forceinline__ void emit_fragment(const FragCtx& c, const VoxTri& v, uint32_t ti, int i, int j, const float b[3], bool covered, int lane) {
+  uint32_t voxel = 0;
+  float val[4];
+  if (covered) {
+    F3 pos;
+    shade_fragment(v, b, c.mats, c.L, c.cube_size, pos, val);
+    const float fR = (float)c.R;
+    int vx = (int)(fR * (0.5f * pos.x + 0.5f)), vy = (int)(fR * (0.5f * pos.y + 0.5f)), vz = (int)(fR * (0.5f * pos.z + 0.5f));
+    covered = vx >= 0 && vy >= 0 && vz >= 0 && vx < c.R && vy < c.R && vz < c.R && vz >= c.z0 && vz < c.z1;
+    voxel = ((uint32_t)vz * (uint32_t)c.R + (uint32_t)vy) * (uint32_t)c.R + (uint32_t)vx;
+  }
+  const uint32_t mask = __ballot_sync(0xffffffffu, covered);
+  if (!mask) return;
+  uint32_t basei = 0;
+  const int leader = __ffs(mask) - 1;
+  if (lane == leader) basei = atomicAdd(&c.counters[CNT_FRAGS], (uint32_t)__popc(mask));
+  basei = __shfl_sync(0xffffffffu, basei, leader);
+  if (covered) {
+    const uint32_t idx = basei + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+    if (idx < c.frag_capacity) {
+      const uint32_t prev = atomicExch(&c.base[voxel], idx + 1u);
+      FragRec r;
+      r.next = prev;
+      r.voxel = voxel;
+      r.key = ((unsigned long long)ti << 24) | ((unsigned long long)j << 12) | (unsigned long long)i;
+      r.val[0] = val[0]; r.val[1] = val[1]; r.val[2] = val[2]; r.val[3] = val[3];
+      c.frags[idx] = r;
+      if (prev == 0u) c.occupied[atomicAdd(&c.counters[CNT_OCCUPIED], 1u)] = voxel;
+    }
+  }
+}
+
+// triangles whose bounding box holds at most this many pixel centres are rasterised inside the setup kernel (one lane
+// per triangle, the warp walks the boxes in lock-step) instead of becoming 8x8 work items: a scene of millions of
+// sub-voxel triangles would otherwise spend a whole warp on one or two fragments
+constexpr int kSmallPixels = 36;
+
 __global__ void __launch_bounds__(kSetupThreads)
 vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ draws,
                  uint32_t n_draws, uint32_t n_tris, float cube_size, int R, int z0, int z1, VoxTri* __restrict__ out, uint32_t* __restrict__ item_local,
-                 uint32_t* __restrict__ item_block) {
+                 uint32_t* __restrict__ item_block, const FragCtx ctx, int small_limit) {
   uint32_t t = blockIdx.x * kSetupThreads + threadIdx.x;
   uint32_t count = 0;
+  VoxTri v;
+  v.rt.sign = 0; v.rt.imin = 0; v.rt.imax = -1; v.rt.jmin = 0; v.rt.jmax = -1;
   if (t < n_tris) {
     const DrawRec& d = draws[find_draw(t, draws, n_draws)];
     uint32_t first = d.first_index + 3u * (t - d.tri_base);
-    VoxTri v;
     const float* m = d.model;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -77,102 +164,53 @@ vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
     }
     v.material = d.material;
     v.axis = axis;
-    out[t] = v;
     count = raster_item_count(v.rt);
   }
+  // ---- small triangles: rasterised here ----
+  const int bw = v.rt.imax - v.rt.imin + 1, bh = v.rt.jmax - v.rt.jmin + 1;
+  const bool small = count > 0 && bw * bh <= small_limit;
+  const int npx = small ? bw * bh : 0;
+  const int maxpx = __reduce_max_sync(0xffffffffu, npx);
+  const int lane = threadIdx.x & 31;
+  for (int p = 0; p < maxpx; p++) {
+    float b[3];
+    int i = 0, j = 0;
+    bool covered = false;
+    if (p < npx) {
+      i = v.rt.imin + p % bw; j = v.rt.jmin + p / bw;
+      covered = raster_sample(v.rt, i, j, b);
+    }
+    emit_fragment(ctx, v, t, i, j, b, covered, lane);
+  }
+  if (small) count = 0;
+  else if (t < n_tris) out[t] = v;   // only triangles that become work items are read again
   block_scan_items(count, t, n_tris, item_local, item_block);
-}
-
-// fragment colour (voxelize.frag:122-153), returns colour * 255
-__device__ __forceinline__ void shade_fragment(const VoxTri& v, const float b[3], const vct_material_t* __restrict__ mats, const Lights& L,
-                                               float cube_size, F3& pos, float val[4]) {
-  pos = f3(interp3(b, v.wp[0][0], v.wp[1][0], v.wp[2][0]), interp3(b, v.wp[0][1], v.wp[1][1], v.wp[2][1]),
-           interp3(b, v.wp[0][2], v.wp[1][2], v.wp[2][2]));
-  F3 nrm = f3(interp3(b, v.nn[0][0], v.nn[1][0], v.nn[2][0]), interp3(b, v.nn[0][1], v.nn[1][1], v.nn[2][1]),
-              interp3(b, v.nn[0][2], v.nn[1][2], v.nn[2][2]));
-  F3 color = f3(0.f, 0.f, 0.f);
-  for (int i = 0; i < L.n; i++) {
-    F3 lp = f3(L.l[i].position[0] / cube_size, L.l[i].position[1] / cube_size, L.l[i].position[2] / cube_size);
-    F3 dv = sub(lp, pos);
-    float dist = sqrtf(dot(dv, dv));
-    F3 dir = f3(dv.x / dist, dv.y / dist, dv.z / dist);
-    float att = 1.0f / ((1.0f + 0.0f * dist) + (1.0f * dist) * dist);
-    float cos_surf = fmaxf(dot(normalize(nrm), dir), 0.0f);
-    float s = cos_surf * att;
-    color.x = color.x + (L.l[i].color[0] * s) * L.l[i].intensity;
-    color.y = color.y + (L.l[i].color[1] * s) * L.l[i].intensity;
-    color.z = color.z + (L.l[i].color[2] * s) * L.l[i].intensity;
-  }
-  const vct_material_t& m = mats[v.material];
-  color = f3(m.diffuse[0] * color.x + m.emission[0], m.diffuse[1] * color.y + m.emission[1], m.diffuse[2] * color.z + m.emission[2]);
-  float tr0 = 1.f, tr1 = 1.f, tr2 = 1.f, alpha = 1.f;
-  if (m.illum == 4 || m.illum == 6 || m.illum == 7 || m.illum == 9) {
-    tr0 = m.transmittance[0]; tr1 = m.transmittance[1]; tr2 = m.transmittance[2];
-    alpha = m.dissolve;
-  }
-  val[0] = clamp01(tr0 * color.x) * 255.0f;
-  val[1] = clamp01(tr1 * color.y) * 255.0f;
-  val[2] = clamp01(tr2 * color.z) * 255.0f;
-  val[3] = clamp01(alpha) * 255.0f;
 }
 
 __global__ void __launch_bounds__(256)
 vox_raster_kernel(const VoxTri* __restrict__ tris, uint32_t n_tris, const uint32_t* __restrict__ item_local,
-                  const uint32_t* __restrict__ item_block, uint32_t n_blocks, const vct_material_t* __restrict__ mats, Lights L,
-                  float cube_size, int R, int z0, int z1, uint32_t* __restrict__ base, FragRec* __restrict__ frags,
-                  uint32_t frag_capacity, uint32_t* __restrict__ occupied, uint32_t* __restrict__ counters) {
-  const uint32_t total = counters[CNT_ITEMS];
+                  const uint32_t* __restrict__ item_block, uint32_t n_blocks, const FragCtx ctx) {
+  const uint32_t total = ctx.counters[CNT_ITEMS];
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-  const float fR = (float)R;
   // one warp per 8x8 item (grid-stride): every lane runs the same two binary searches (broadcast loads)
   for (uint32_t g = warp; g < total; g += n_warps) {
     uint32_t rank;
     const uint32_t ti = find_item_triangle(g, item_block, n_blocks, item_local, n_tris, rank);
-    {
-      const VoxTri& v = tris[ti];
-      const RasterTri rt = v.rt;
-      const int tiles_x = (rt.imax >> 3) - (rt.imin >> 3) + 1;
-      const int tx = (rt.imin >> 3) + (int)(rank % (uint32_t)tiles_x), ty = (rt.jmin >> 3) + (int)(rank / (uint32_t)tiles_x);
+    const VoxTri& v = tris[ti];
+    const RasterTri rt = v.rt;
+    const int tiles_x = (rt.imax >> 3) - (rt.imin >> 3) + 1;
+    const int tx = (rt.imin >> 3) + (int)(rank % (uint32_t)tiles_x), ty = (rt.jmin >> 3) + (int)(rank / (uint32_t)tiles_x);
+    EdgeBlock eb;
+    edge_block_setup(rt, tx * kTile, ty * kTile, eb);
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int p = lane + 32 * h;
-        const int i = tx * kTile + (p & 7), j = ty * kTile + (p >> 3);
-        float b[3];
-        bool covered = i >= rt.imin && i <= rt.imax && j >= rt.jmin && j <= rt.jmax && raster_sample(rt, i, j, b);
-        uint32_t voxel = 0;
-        float val[4];
-        if (covered) {
-          F3 pos;
-          shade_fragment(v, b, mats, L, cube_size, pos, val);
-          // ivec3(dim * scale_and_bias(pos)): truncation toward zero, then the image bounds check (voxelize.frag:156-157)
-          int vx = (int)(fR * (0.5f * pos.x + 0.5f)), vy = (int)(fR * (0.5f * pos.y + 0.5f)), vz = (int)(fR * (0.5f * pos.z + 0.5f));
-          covered = vx >= 0 && vy >= 0 && vz >= 0 && vx < R && vy < R && vz < R && vz >= z0 && vz < z1;
-          voxel = ((uint32_t)vz * (uint32_t)R + (uint32_t)vy) * (uint32_t)R + (uint32_t)vx;
-        }
-        // warp-aggregated arena allocation
-        const uint32_t mask = __ballot_sync(0xffffffffu, covered);
-        if (mask) {
-          uint32_t basei = 0;
-          const int leader = __ffs(mask) - 1;
-          if (lane == leader) basei = atomicAdd(&counters[CNT_FRAGS], (uint32_t)__popc(mask));
-          basei = __shfl_sync(0xffffffffu, basei, leader);
-          if (covered) {
-            const uint32_t idx = basei + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-            if (idx < frag_capacity) {
-              const uint32_t prev = atomicExch(&base[voxel], idx + 1u);
-              FragRec r;
-              r.next = prev;
-              r.voxel = voxel;
-              r.key = ((unsigned long long)ti << 24) | ((unsigned long long)j << 12) | (unsigned long long)i;
-              r.val[0] = val[0]; r.val[1] = val[1]; r.val[2] = val[2]; r.val[3] = val[3];
-              frags[idx] = r;
-              if (prev == 0u) occupied[atomicAdd(&counters[CNT_OCCUPIED], 1u)] = voxel;
-            }
-          }
-        }
-      }
+    for (int h = 0; h < 2; h++) {
+      const int p = lane + 32 * h;
+      const int i = tx * kTile + (p & 7), j = ty * kTile + (p >> 3);
+      float b[3];
+      const bool covered = i >= rt.imin && i <= rt.imax && j >= rt.jmin && j <= rt.jmax && edge_block_sample(eb, p & 7, p >> 3, b);
+      emit_fragment(ctx, v, ti, i, j, b, covered, lane);
     }
   }
 }
@@ -293,11 +331,13 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
   VoxTri* tris = (VoxTri*)dev->tri_recs;
   const int sms = dev->prop.multiProcessorCount;
   if (sc->n_tris) {   // an empty scene still runs the resolve kernel in multi-GPU mode: the peers wait for its signal
+    FragCtx ctx;
+    ctx.mats = sc->mats; ctx.L = sc->lights; ctx.cube_size = sc->cube_size; ctx.R = g->R; ctx.z0 = z0; ctx.z1 = z1;
+    ctx.base = g->base; ctx.frags = dev->frags; ctx.frag_capacity = (uint32_t)dev->frag_capacity; ctx.occupied = dev->occupied; ctx.counters = dev->counters;
     vox_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, sc->cube_size, g->R, z0, z1, tris,
-                                                          dev->item_local, dev->item_block);
+                                                          dev->item_local, dev->item_block, ctx, sc->n_tris >= kSmallPathMinTris ? kSmallPixels : 0);
     scan_block_totals_kernel<<<1, 1024, 0, s>>>(dev->item_block, n_blocks, dev->counters + CNT_ITEMS);
-    vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->item_local, dev->item_block, n_blocks, sc->mats, sc->lights, sc->cube_size,
-                                              g->R, z0, z1, g->base, dev->frags, (uint32_t)dev->frag_capacity, dev->occupied, dev->counters);
+    vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->item_local, dev->item_block, n_blocks, ctx);
   }
   vox_resolve_kernel<<<sms * 4, 128, 0, s>>>(g->base, dev->frags, dev->occupied, dev->counters, (uint32_t)dev->frag_capacity, pv);
   VCT_CUDA(cudaGetLastError());
