@@ -59,10 +59,17 @@ def test_mip_random_grid_bit_exact(dev, R, levels, density):
 
 
 def _expected_occupancy(pyr: orc.Pyramid, level: int):
-    occ = np.zeros_like(pyr.levels[0][level], dtype=bool)
+    """occupancy bit of a texel = a voxel of its level-0 support is non-zero (for level >= 1 the OR of the 8 child bits; a
+    superset of "the texel is non-zero in some direction", which is what makes skipping a footprint exact); dilated bit
+    (x+1,y+1,z+1) = OR over the 2x2x2 footprint whose low corner is (x,y,z)"""
+    base = pyr.levels[0][0] != 0
+    n = base.shape[0] >> level
+    b = 1 << level
+    occ = base.reshape(n, b, n, b, n, b).any(axis=(1, 3, 5))
+    nonzero = np.zeros_like(occ)
     for d in range(6):
-        occ |= pyr.levels[d][level] != 0
-    n = occ.shape[0]
+        nonzero |= pyr.levels[d][level] != 0
+    assert not (nonzero & ~occ).any(), "a non-zero texel without an occupancy bit would make the skip inexact"
     pad = np.zeros((n + 2,) * 3, bool)
     pad[1:-1, 1:-1, 1:-1] = occ
     dil = np.zeros((n + 1,) * 3, bool)
@@ -75,7 +82,7 @@ def _expected_occupancy(pyr: orc.Pyramid, level: int):
 
 @pytest.mark.parametrize("R,levels,density", [(128, 7, 0.001), (64, 7, 0.01), (32, 6, 0.05), (16, 5, 0.02), (64, 3, 0.3)])
 def test_occupancy_masks_match_pyramid(dev, R, levels, density):
-    """the zero-footprint skip of the cone tracer is only exact if the masks are: bit set <=> some texel of the footprint is non-zero"""
+    """the zero-footprint skip of the cone tracer is only exact if the masks are: bit clear => every texel of the footprint is zero"""
     rng = np.random.default_rng(7)
     base = rng.integers(0, 2 ** 32, (R, R, R), dtype=np.uint64).astype(np.uint32)
     base[rng.random((R, R, R)) > density] = 0

@@ -230,6 +230,89 @@ __device__ __forceinline__ uint32_t trace_cone(const GridView& g, F3 origin, F3 
   return iters;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// The production march.  Same samples, same order and same arithmetic per sample as trace_cone above; what changes is the
+// bookkeeping around the fetch (measured with ncu: the literal loop spent 45 % of its issue slots on log2f, two occupancy
+// tests and the cube-exit test per step):
+//  * ONE occupancy test per step.  The occupancy bit of a texel of level >= 1 is the OR of its 8 children (mip stage), and the
+//    2x2x2 footprint of level l around a point lies inside the children of the footprint of level l+1 around the same point
+//    (x0 = floor(u - 1/2) is in {2X0, 2X0+1, 2X0+2} for X0 = floor(u/2 - 1/2)), so "footprint of l+1 empty" implies
+//    "footprint of l empty": when both levels are blended only the coarser one is tested.
+//  * the distance at which the cone has left the border-padded cube for good is computed once and folded into the loop bound.
+//  * lod through the hardware lg2 (2 ulp-class error on a value that only weights two neighbouring levels).
+__device__ __forceinline__ bool footprint_empty_fast(const GridView& g, int level, F3 pos) {
+  const int N = g.R >> level;
+  const float fN = (float)N;
+  const int x = __float2int_rd(fmaf(pos.x, fN, -0.5f)) + 1, y = __float2int_rd(fmaf(pos.y, fN, -0.5f)) + 1, z = __float2int_rd(fmaf(pos.z, fN, -0.5f)) + 1;
+  if ((unsigned)x > (unsigned)N || (unsigned)y > (unsigned)N || (unsigned)z > (unsigned)N) return true;   // footprint wholly outside
+  const uint32_t wpr = (uint32_t)(N + 32) >> 5;
+  const uint32_t w = __ldg(g.docc[level] + ((uint32_t)z * (uint32_t)(N + 1) + (uint32_t)y) * wpr + ((uint32_t)x >> 5));
+  return ((w >> (x & 31)) & 1u) == 0u;
+}
+
+template <bool TEX>
+__device__ __forceinline__ void trace_cone_fast(const GridView& g, bool alive, F3 origin, F3 dir, float aperture, float max_dist, float out[4]) {
+  dir = normalize(dir);
+  const int ix = dir.x < 0.0f ? 0 : 1, iy = dir.y < 0.0f ? 2 : 3, iz = dir.z < 0.0f ? 4 : 5;
+  const F3 adir = f3(fabsf(dir.x), fabsf(dir.y), fabsf(dir.z));
+  const float cube_res = (float)g.R;
+  const float voxel_size = 1.0f / cube_res;
+  const float max_level = (float)(g.levels - 1);
+  // past one texel of the coarsest level outside [0,1] every footprint of every level is wholly outside the grid
+  const float margin = 1.0f / (float)(g.R >> (g.levels - 1));
+  float end = max_dist;
+  {
+    const float o[3] = {origin.x, origin.y, origin.z}, d[3] = {dir.x, dir.y, dir.z};
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      float t_exit;
+      if (d[k] < 0.0f) t_exit = (o[k] + margin) / -d[k];
+      else if (d[k] > 0.0f) t_exit = ((1.0f + margin) - o[k]) / d[k];
+      else t_exit = (o[k] <= -margin || o[k] >= 1.0f + margin) ? 0.0f : max_dist;
+      end = fminf(end, t_exit + voxel_size);   // + one voxel: rounding slack, the extra samples are exactly zero
+    }
+    if (!(d[0] == d[0] && d[1] == d[1] && d[2] == d[2]) || !alive) end = 0.0f;   // NaN direction (refract() of total reflection): every sample is zero
+  }
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};  // byte units
+  const cudaTextureObject_t tx = g.tex[ix], ty = g.tex[iy], tz = g.tex[iz];
+  float dist = 3.0f * voxel_size;
+  float diam = dist * aperture;
+  while (acc[3] < 255.0f && dist < end) {
+    const F3 sp = f3(fmaf(dir.x, dist, origin.x), fmaf(dir.y, dist, origin.y), fmaf(dir.z, dist, origin.z));
+    const float lod = fminf(fmaxf(__log2f(diam * cube_res), 0.0f), max_level);
+    float s[4] = {0.f, 0.f, 0.f, 0.f};
+    if (TEX) {
+      if (lod < 1.0f) {
+        // level 0 in software (shared by the three directions) + level 1 = array level 0 through the texture unit
+        const bool e1 = lod > 0.0f ? footprint_empty_fast(g, 1, sp) : true;
+        const bool e0 = (lod > 0.0f && e1) ? true : footprint_empty_fast(g, 0, sp);
+        if (!e0) fetch_level(g, 0, sp, adir, ix, iy, iz, 1.0f - lod, s);
+        if (!e1) fetch_tex(tx, ty, tz, sp, adir, 0.0f, 255.0f * lod, s);
+      } else {
+        const float fl = floorf(lod);
+        const int l0 = (int)fl;
+        if (!footprint_empty_fast(g, lod > fl ? l0 + 1 : l0, sp)) fetch_tex(tx, ty, tz, sp, adir, lod - 1.0f, 255.0f, s);
+      }
+    } else {
+      const float fl = floorf(lod);
+      const int l0 = (int)fl;
+      const float f = lod - fl;
+      const bool e1 = f > 0.0f ? footprint_empty_fast(g, l0 + 1, sp) : true;
+      const bool e0 = (f > 0.0f && e1) ? true : footprint_empty_fast(g, l0, sp);
+      if (!e0) fetch_level(g, l0, sp, adir, ix, iy, iz, 1.0f - f, s);
+      if (!e1) fetch_level(g, l0 + 1, sp, adir, ix, iy, iz, f, s);
+    }
+    const float k = 1.0f - acc[3] * (1.0f / 255.0f);
+#pragma unroll
+    for (int c = 0; c < 4; c++) acc[c] = fmaf(k, s[c], acc[c]);
+    dist = dist + fmaxf(diam * 0.5f, voxel_size);
+    diam = dist * aperture;
+  }
+#pragma unroll
+  for (int c = 0; c < 4; c++) out[c] = acc[c] * (1.0f / 255.0f);
+}
+
 __device__ __forceinline__ F3 tangent(F3 n) {
   F3 t1 = cross(n, f3(0.f, 0.f, 1.f)), t2 = cross(n, f3(0.f, 1.f, 0.f));
   return length(t1) > length(t2) ? normalize(t1) : normalize(t2);
@@ -381,6 +464,82 @@ cone_kernel(const TraceArgs a) {
       if (lane == 0) atomicAdd(&a.counts[4], (unsigned long long)__popc(ball));
     }
   }
+}
+
+
+// cone parameters of one (pixel, slot): direction, aperture, max distance; false = this slot traces nothing for the pixel
+__device__ __forceinline__ bool cone_setup(const TraceArgs& a, const Pixel& p, int slot, F3& d, float& aperture, float& max_dist) {
+  const int nd = a.n_diffuse;
+  const vct_material_t* m = a.mats + p.mat_id;
+  const F3 normal = p.normal;
+  aperture = kTan22_5;
+  max_dist = kMaxDistance;
+  d = normal;
+  if (slot < nd) {
+    if (!a.prm.enable_diffuse) return false;
+    const F3 o1 = normalize(tangent(normal));
+    const F3 o2 = normalize(cross(o1, normal));
+    switch (slot) {
+      case 0: d = normal; break;
+      case 1: d = mix(normal, o1, 0.5f); break;
+      case 2: d = mix(normal, -o1, 0.5f); break;
+      case 3: d = mix(normal, o2, 0.5f); break;
+      case 4: d = mix(normal, -o2, 0.5f); break;
+      case 5: d = mix(normal, (o1 + o2) * 0.5f, 0.5f); break;
+      case 6: d = mix(normal, -((o1 + o2) * 0.5f), 0.5f); break;
+      case 7: d = mix(normal, (o1 - o2) * 0.5f, 0.5f); break;
+      default: d = mix(normal, -((o1 - o2) * 0.5f), 0.5f); break;
+    }
+    return true;
+  }
+  const F3 cam = f3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]);
+  if (slot == nd) {
+    if (!a.prm.enable_specular) return false;
+    const F3 view_dir = normalize(p.world - cam);
+    d = normalize(reflect(-view_dir, normal));
+    aperture = specular_aperture(m->shininess);
+    return true;
+  }
+  if (slot == nd + 1) {
+    const bool transmissive = m->illum == 4 || m->illum == 6 || m->illum == 7 || m->illum == 9;
+    if (!(transmissive && a.prm.enable_specular)) return false;
+    const F3 view_dir = normalize(p.world - cam);
+    d = refract(view_dir, normal, 1.0f / m->ior);
+    aperture = specular_aperture(m->shininess);
+    return true;
+  }
+  const int li = slot - (nd + 2);
+  if (!(li < a.lights.n && a.prm.enable_direct && a.prm.enable_shadow)) return false;
+  const vct_point_light_t& L = a.lights.l[li];
+  const F3 lp = f3(0.5f * (L.position[0] / a.cube_size) + 0.5f, 0.5f * (L.position[1] / a.cube_size) + 0.5f,
+                   0.5f * (L.position[2] / a.cube_size) + 0.5f);
+  const F3 ld = lp - p.pos;
+  const float dl = length(ld);
+  d = f3(ld.x / dl, ld.y / dl, ld.z / dl);
+  aperture = 0.1f;
+  max_dist = dl;
+  return true;
+}
+
+template <bool TEX>
+__global__ void __launch_bounds__(32 * kConeWarps)
+cone_kernel_fast(const TraceArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t t = blockIdx.x * kConeWarps + (threadIdx.x >> 5);
+  if (t >= *a.tile_count) return;
+  // long cones first: blockIdx.y = 0 is the last slot (shadow cones, up to ~5x more steps than diffuse)
+  const int slot = a.n_slots - 1 - (int)blockIdx.y;
+  const uint32_t tile = a.tile_list[t];
+  const int tiles_x = (a.W + 7) / 8;
+  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+  const Pixel p = load_pixel(a, tile_x * 8 + (lane & 7), tile_y * 4 + (lane >> 3));
+  if (!p.live) return;
+  F3 d = f3(0.f, 0.f, 1.f);
+  float aperture = kTan22_5, max_dist = 0.f;
+  const bool on = cone_setup(a, p, slot, d, aperture, max_dist);
+  float r[4];
+  trace_cone_fast<TEX>(a.grid, on, p.pos, d, aperture, max_dist, r);
+  a.cone_out[(size_t)slot * a.npix + p.pix] = make_float4(r[0], r[1], r[2], r[3]);
 }
 
 // main() (voxel_cone_tracing.frag:246-275) for one pixel
@@ -556,10 +715,15 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
     if (count_samples) {
       VCT_CUDA(cudaMemsetAsync(dev->counters + 16, 0, 8 * sizeof(unsigned long long), s));
       cone_kernel<true, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
-    } else if (tex) {
-      cone_kernel<false, true><<<grid, 32 * kConeWarps, 0, s>>>(a);
     } else {
-      cone_kernel<false, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
+      static const int variant = getenv("VCT_CONE_VARIANT") ? atoi(getenv("VCT_CONE_VARIANT")) : 1;
+      if (variant == 0) {
+        if (tex) cone_kernel<false, true><<<grid, 32 * kConeWarps, 0, s>>>(a);
+        else cone_kernel<false, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
+      } else {
+        if (tex) cone_kernel_fast<true><<<grid, 32 * kConeWarps, 0, s>>>(a);
+        else cone_kernel_fast<false><<<grid, 32 * kConeWarps, 0, s>>>(a);
+      }
     }
     VCT_CUDA(cudaEventRecord(dev->ev[7], s));
   }

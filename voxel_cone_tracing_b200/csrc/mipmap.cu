@@ -78,6 +78,16 @@ __device__ __forceinline__ uint32_t filter_dir_dyn(const float (&c)[8][4], int d
   }
 }
 
+// OR of adjacent bit pairs: bit k of the result = bit 2k | bit 2k+1 of the 32-bit input (16 result bits)
+__host__ __device__ __forceinline__ uint32_t occ_pair_or(uint32_t v) {
+  v = (v | (v >> 1)) & 0x55555555u;
+  v = (v | (v >> 1)) & 0x33333333u;
+  v = (v | (v >> 2)) & 0x0F0F0F0Fu;
+  v = (v | (v >> 4)) & 0x00FF00FFu;
+  v = (v | (v >> 8)) & 0x0000FFFFu;
+  return v;
+}
+
 // child index i of mipmap.comp for local offsets (dx,dy,dz)
 __device__ __forceinline__ constexpr int child_id(int dx, int dy, int dz) { return ((dx ^ 1) << 2) | ((dy ^ 1) << 1) | (dz ^ 1); }
 
@@ -130,6 +140,7 @@ struct LowSmem {
   uint32_t s1[TZ / 2][TY / 2][TX / 2][6];      // 6 KB
   uint32_t s2[TZ / 4][TY / 4][TX / 4][6];      // 768 B
   uint32_t s3[TX / 8][6];                      // 96 B
+  uint32_t occ_l1[8];                          // per warp of the level-1 step: 8 bits = (x pairs) of its two rows with a non-zero voxel below
   uint32_t zero_flag[kLowStages];              // tile_zero[] of the tile in each stage, prefetched with the tile
   unsigned long long full[kLowStages];         // mbarriers: "tile landed"
 };
@@ -191,7 +202,7 @@ __device__ __forceinline__ void low_store_level(const uint32_t* __restrict__ src
 
 // reduces one staged tile; every thread of the CTA calls it (contains barriers)
 __device__ __forceinline__ void low_process_tile(const uint32_t (&s0)[TZ][TY][TX], uint32_t (&s1)[TZ / 2][TY / 2][TX / 2][6],
-                                                 uint32_t (&s2)[TZ / 4][TY / 4][TX / 4][6], uint32_t (&s3)[TX / 8][6], const LowArgs& a, int tile,
+                                                 uint32_t (&s2)[TZ / 4][TY / 4][TX / 4][6], uint32_t (&s3)[TX / 8][6], uint32_t (&occ_l1)[8], const LowArgs& a, int tile,
                                                  uint32_t known_zero, int bx, int by, int bz) {
   const int R = a.R;
   uint32_t* __restrict__ occ0 = a.occ0; uint16_t* __restrict__ occ1 = a.occ1; uint8_t* __restrict__ occ2 = a.occ2;
@@ -257,9 +268,12 @@ __device__ __forceinline__ void low_process_tile(const uint32_t (&s0)[TZ][TY][TX
     }
     uint2* sp = reinterpret_cast<uint2*>(&s1[z][y][x][0]);
     sp[0] = make_uint2(o[0], o[1]); sp[1] = make_uint2(o[2], o[3]); sp[2] = make_uint2(o[4], o[5]);
-    // a warp holds two rows of 16 texels
-    const uint32_t bal = __ballot_sync(0xffffffffu, (o[0] | o[1] | o[2] | o[3] | o[4] | o[5]) != 0u);
+    // occupancy of a texel of level >= 1 = "a voxel of its level-0 support is non-zero" (a superset of "the texel is non-zero": a
+    // filtered value can round to zero), so that the bits of a level are the OR of the 8 child bits -- the tracer relies on that.
+    // A warp holds two rows of 16 texels.
+    const uint32_t bal = __ballot_sync(0xffffffffu, any != 0u);
     if (x == 0) occ1[((size_t)(z0 / 2 + z) * N1 + (y0 / 2 + y)) * (N1 / 16) + bx] = (uint16_t)(bal >> (16 * (y & 1)));
+    if ((t & 31) == 0) occ_l1[t >> 5] = occ_pair_or((bal | (bal >> 16)) & 0xFFFFu);   // warp w: z = w >> 1, level-2 row y = w & 1
   }
   __syncthreads();
 
@@ -285,14 +299,7 @@ __device__ __forceinline__ void low_process_tile(const uint32_t (&s0)[TZ][TY][TX
 
   if (t >= 192 && t < 196) {  // level-2 occupancy: one byte per row of 8 texels
     const int y = t & 1, z = (t >> 1) & 1;
-    uint32_t bits = 0;
-#pragma unroll
-    for (int x = 0; x < 8; x++) {
-      uint32_t acc = 0;
-#pragma unroll
-      for (int d = 0; d < 6; d++) acc |= s2[z][y][x][d];
-      bits |= (uint32_t)(acc != 0u) << x;
-    }
+    const uint32_t bits = occ_l1[4 * z + y] | occ_l1[4 * z + 2 + y];
     occ2[((size_t)(z0 / 4 + z) * N2 + (y0 / 4 + y)) * (N2 / 8) + bx] = (uint8_t)bits;
   }
   // ---- level 3: 4 texels x 6 directions ----
@@ -351,7 +358,7 @@ mip_fused_low_kernel(const __grid_constant__ CUtensorMap tmap, const LowArgs a) 
     mbar_wait(&sm.full[stage], (uint32_t)((i / kLowStages) & 1));
     int bx, by, bz;
     low_tile_coords(tile, a.log_tiles_x, a.log_tiles_y, bx, by, bz);
-    low_process_tile(sm.s0[stage], sm.s1, sm.s2, sm.s3, a, tile, sm.zero_flag[stage], bx, by, bz);
+    low_process_tile(sm.s0[stage], sm.s1, sm.s2, sm.s3, sm.occ_l1, a, tile, sm.zero_flag[stage], bx, by, bz);
     __syncthreads();   // every read of this stage (and of s1/s2) is done: the buffer can be refilled
     const int next = tile + kLowStages * gridDim.x;
     if (t == 0) {
@@ -445,7 +452,7 @@ mip_fused_high_kernel(const uint32_t* __restrict__ l3, uint32_t* __restrict__ l4
 }
 
 // ---------------------------------------------------------------------------------------------
-// occupancy bits from the texel data of one level (blockIdx.y selects the level): one warp per 32 texels
+// occupancy bits
 struct OccArgs {
   const uint32_t* src[VCT_MAX_LEVELS];  // level 0: base words, level >= 1: 6-word records
   uint32_t* occ[VCT_MAX_LEVELS];
@@ -454,25 +461,60 @@ struct OccArgs {
 };
 
 __global__ void __launch_bounds__(256)
-occ_bits_kernel(const OccArgs a) {
-  const int level = a.first_level + (int)blockIdx.y;
-  const size_t N = (size_t)(a.R >> level), n = N * N * N;
-  const uint32_t* src = a.src[level];
+occ_bits_kernel(const OccArgs a) {   // level 0 from the voxel words (only when the fused kernel did not run)
+  const size_t N = (size_t)a.R, n = N * N * N;
+  const uint32_t* src = a.src[0];
   const int lane = threadIdx.x & 31;
   const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
   for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w * 32 < n; w += n_warps) {
     const size_t i = w * 32 + lane;
-    uint32_t any = 0;
-    if (i < n) {
-      if (level == 0) any = src[i];
-      else {
-        const uint2* r = reinterpret_cast<const uint2*>(src + i * 6);
-        const uint2 p = r[0], q = r[1], s = r[2];
-        any = p.x | p.y | q.x | q.y | s.x | s.y;
-      }
-    }
+    const uint32_t any = i < n ? src[i] : 0u;
     const uint32_t bal = __ballot_sync(0xffffffffu, any != 0u);
-    if (lane == 0) a.occ[level][w] = bal;
+    if (lane == 0) a.occ[0][w] = bal;
+  }
+}
+
+// occupancy bit (x,y,z) of a level (flat index (z*N + y)*N + x)
+__device__ __forceinline__ uint32_t occ_bit(const uint32_t* __restrict__ occ, int N, int x, int y, int z) {
+  const size_t flat = ((size_t)z * N + y) * N + x;
+  return (occ[flat >> 5] >> (flat & 31)) & 1u;
+}
+
+// levels first_level.. from the level below: bit = OR of the 8 child bits (= "a voxel of the texel's level-0 support is non-zero").
+// The levels are tiny and depend on each other, so ONE CTA walks them in order.
+__global__ void __launch_bounds__(1024)
+occ_reduce_kernel(const OccArgs a, int levels) {
+  for (int level = a.first_level; level < levels; level++) {
+    const int N = a.R >> level, Ns = N * 2;
+    const uint32_t* __restrict__ src = a.occ[level - 1];
+    uint32_t* __restrict__ dst = a.occ[level];
+    const size_t n_words = occ_words(N);
+    for (size_t w = threadIdx.x; w < n_words; w += blockDim.x) {
+      uint32_t out = 0;
+      if (N >= 32) {   // the word is 32 texels of one row: two source words in each of four source rows
+        const size_t row = w / (N >> 5);
+        const int k = (int)(w % (N >> 5)), y = (int)(row % N), z = (int)(row / N);
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const uint32_t* r = src + (((size_t)(2 * z + (q >> 1)) * Ns + (2 * y + (q & 1))) * Ns >> 5) + 2 * k;
+          lo |= r[0]; hi |= r[1];
+        }
+        out = occ_pair_or(lo) | (occ_pair_or(hi) << 16);
+      } else {
+        for (int b = 0; b < 32; b++) {
+          const size_t flat = w * 32 + b;
+          if (flat >= (size_t)N * N * N) break;
+          const int x = (int)(flat % N), y = (int)((flat / N) % N), z = (int)(flat / ((size_t)N * N));
+          uint32_t any = 0;
+#pragma unroll
+          for (int q = 0; q < 8; q++) any |= occ_bit(src, Ns, 2 * x + (q & 1), 2 * y + ((q >> 1) & 1), 2 * z + (q >> 2));
+          out |= any << b;
+        }
+      }
+      dst[w] = out;
+    }
+    __syncthreads();   // the next level reads what this CTA just wrote
   }
 }
 
@@ -593,10 +635,11 @@ int launch_mipmap(vct_device* dev, vct_grid* g) {
   OccArgs oa;
   oa.R = R; oa.first_level = occ_from_data;
   for (int l = 0; l < VCT_MAX_LEVELS; l++) { oa.src[l] = l == 0 ? g->base : g->lvl[l]; oa.occ[l] = g->occ[l]; oa.docc[l] = g->docc[l]; }
-  if (occ_from_data < g->levels) {
-    const size_t n = (size_t)(R >> occ_from_data) * (R >> occ_from_data) * (R >> occ_from_data);
-    occ_bits_kernel<<<dim3(grid_for(n, 256, 148 * 8), g->levels - occ_from_data), 256, 0, s>>>(oa);
+  if (occ_from_data == 0) {
+    occ_bits_kernel<<<grid_for((size_t)R * R * R, 256, 148 * 8), 256, 0, s>>>(oa);
+    oa.first_level = 1;
   }
+  if (oa.first_level < g->levels) occ_reduce_kernel<<<1, 1024, 0, s>>>(oa, g->levels);
   occ_dilate_kernel<<<dim3((R + 1 + 127) / 128, R + 1, g->levels), 128, 0, s>>>(oa);
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;
