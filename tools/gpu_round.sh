@@ -1,11 +1,11 @@
 #!/bin/bash
-# GPU session helper: parity suite, per-stage timings, bench (both arms), ncu launch list.
+# one GPU box visit: parity tests, bench, ncu launch list, ncu --set full of the cone and mip kernels
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/smi.txt 2>&1
-timeout 1500 python -m pytest tests -x -q -m gpu 2>&1 | tail -25 > gpurun_out/pytest_gpu.txt
-cat gpurun_out/pytest_gpu.txt
-timeout 300 python tools/quick_time.py > gpurun_out/quick_time.txt 2>&1; cat gpurun_out/quick_time.txt
-timeout 600 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; cat gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-timeout 600 python __graft_entry__.py smoke 2>&1 | tail -3
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu > gpurun_out/ncu_launch.log 2>&1
-tail -3 gpurun_out/ncu_launch.log
+O=gpurun_out
+( time timeout 1200 python -m pytest tests -m gpu -x -q ) > $O/pytest_gpu.log 2>&1; tail -5 $O/pytest_gpu.log
+timeout 600 python bench.py --steps 200 --warmup 10 > $O/bench.json 2> $O/bench.err; cut -c1-400 $O/bench.json; tail -3 $O/bench.err
+timeout 300 python tools/quick_time.py > $O/quick_time.txt 2>&1; cat $O/quick_time.txt
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 5 --warmup 3 --no-cpu > $O/launch_bench.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:cone_kernel -s 3 -c 1 -f -o $O/cone_full python bench.py --steps 1 --warmup 3 --no-cpu > $O/ncu_cone.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"mip_|occ_" -s 12 -c 6 -f -o $O/mip_full python bench.py --steps 1 --warmup 3 --no-cpu > $O/ncu_mip.log 2>&1
+ls -la $O
