@@ -291,21 +291,37 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
     # memory (geometry, materials, draw list, lights) and read the finished frame back into pinned host memory ----
     e2e = None
     if world == 1:
-        host_frame = torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        # two pinned host frames: the read-back of frame i (copy stream) overlaps the rendering of frame i+1 (device stream);
+        # every frame's pixels have landed in host memory before the clock stops
+        host_frames = [torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(2)]
         h2d = sc.verts.nbytes + sc.indices.nbytes + sc.materials.nbytes + sc.draws.nbytes + sc.lights.nbytes + 128 + 36
-        d2h = host_frame.nbytes
-        for _ in range(2):
-            pipe.scene.upload(sc); pipe.render_frame(view, proj, prm); pipe.target.frame(host_frame)
+        d2h = host_frames[0].nbytes
+        for i in range(2):
+            pipe.scene.upload(sc); pipe.render_frame(view, proj, prm); pipe.target.wait(pipe.target.frame_async(host_frames[i]))
         pipe.sync()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            pipe.scene.upload(sc)
+        prev = None
+        for i in range(args.steps):
+            pipe.scene.upload(sc)                                # H2D: geometry, materials, draw list (pinned staging ring, async)
             pipe.render_frame(view, proj, prm)
-            pipe.target.frame(host_frame)      # D2H + stream sync
+            tk = pipe.target.frame_async(host_frames[i & 1])     # D2H of this frame, asynchronous
+            if prev is not None:
+                pipe.target.wait(prev)                           # frame i-1 is in host memory
+            prev = tk
+        pipe.target.wait(prev)
         pipe.sync()
         dt = time.perf_counter() - t0
         e2e = {"value": args.steps / dt, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": 1e3 * dt / args.steps}
+               "ms_per_step": 1e3 * dt / args.steps,
+               "note": "scene uploaded from host memory and the finished frame read back to pinned host memory EVERY step through the C ABI; "
+                       "the read-back of frame i overlaps the rendering of frame i+1 (vct_target_download_frame_async)"}
+        # the same loop fully serialised (blocking read-back each step), for reference
+        pipe.sync()
+        t0 = time.perf_counter()
+        for i in range(min(args.steps, 50)):
+            pipe.scene.upload(sc); pipe.render_frame(view, proj, prm); pipe.target.frame(host_frames[0])
+        pipe.sync()
+        e2e["blocking_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / min(args.steps, 50)
 
     # ---- roofline of the dominant kernel (cone_kernel, timed alone with CUDA events on its stream) ----
     peak, peak_src = measured_peaks()
@@ -327,6 +343,8 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
         stages = {k + "_us": v * 1e3 for k, v in stage_acc.items()}
         stages["mip_roofline"] = {"bound": "hbm", "achieved": mip_bytes / (stage_acc["mipmap"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                                   "frac": mip_bytes / (stage_acc["mipmap"] * 1e-3) / 1e9 / peak, "algorithmic_bytes": mip_bytes}
+        stages["note"] = ("gbuffer_us = the part of the G-buffer pass on the critical path: the pass (gbuffer_pass_us) runs on a second stream "
+                          "beside clear + voxelize + mip and joins before the trace, so the stage times overlap and need not add up to total_us")
         stages["clear_gbs"] = 4.0 * R ** 3 / (stage_acc["clear"] * 1e-3) / 1e9
         stages["voxelize_mfrag_per_s"] = st.fragments / (stage_acc["voxelize"] * 1e-3) / 1e6
         stages["fragments"] = int(st.fragments)

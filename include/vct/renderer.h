@@ -106,6 +106,8 @@ struct Renderer {
   int width() const { return m_viewport_width; }
   int height() const { return m_viewport_height; }
   bool read_frame(uint32_t* rgba8);                     // W*H RGBA8, row 0 = bottom (GL window coordinates); synchronises
+  uint64_t read_frame_async(uint32_t* pinned_rgba8);    // same, on a copy stream that overlaps the next render(); 0 on failure, else a ticket
+  bool wait_frame(uint64_t ticket);                     // blocks until that read-back has landed
   void* frame_device_ptr();                             // device pointer of the RGBA8 frame
   bool read_voxels(int level, int dir, uint32_t* rgba8); // one level of one directional texture (glGetTexImage)
   void set_sampler(int vct_sampler) { m_sampler = vct_sampler; }  // VCT_SAMPLER_FP32 / VCT_SAMPLER_TEX

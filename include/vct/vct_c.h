@@ -122,6 +122,11 @@ size_t vct_grid_bytes(const vct_grid_t* g);
 int vct_target_create(vct_device_t* dev, int width, int height, vct_target_t** out);
 int vct_target_destroy(vct_target_t* t);
 int vct_target_download_frame(vct_target_t* t, uint32_t* host_rgba8);     /* row 0 = bottom (GL window coords) */
+/* Asynchronous read-back (the SwapBuffers of this build, src/main.cpp:387): snapshots the finished frame in stream order and
+ * copies it to `host_rgba8` (pinned memory for a truly asynchronous copy) on a second stream; returns at once with a ticket so
+ * that the next vct_render_frame overlaps the transfer.  vct_target_download_wait blocks until that ticket's copy has landed. */
+int vct_target_download_frame_async(vct_target_t* t, uint32_t* host_rgba8, uint64_t* ticket);
+int vct_target_download_wait(vct_target_t* t, uint64_t ticket);
 int vct_target_download_gbuffer(vct_target_t* t, uint32_t* tri_id, float* depth, float* world_pos3, float* normal3, uint32_t* material);
 void* vct_target_frame_device_ptr(vct_target_t* t);
 
@@ -148,8 +153,9 @@ int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_targ
                      const vct_trace_params_t* p);
 
 /* per-stage device timings (CUDA events on the device stream) of the last vct_render_frame, in ms:
- * [0] clear [1] voxelize [2] mipmap [3] gbuffer [4] trace (tile list + cones + shade) [5] total
- * [6] cone kernel alone [7] reserved; synchronises */
+ * [0] clear [1] voxelize [2] mipmap [3] gbuffer, the part on the critical path (single GPU: the pass runs on a second stream
+ * beside [0]-[2], this is what is left of it after the mip build) [4] trace (tile list + cones + shade) [5] total
+ * [6] cone kernel alone [7] the G-buffer pass itself on its own stream (0 when it ran in line); synchronises */
 int vct_last_frame_timings(vct_device_t* dev, float out_ms[8]);
 
 /* ---- multi-GPU (no reference counterpart: the reference is single-GPU).  One process per GPU on one node; the exchange

@@ -318,6 +318,51 @@ def test_frame_config2_cornell_256_1080p(sampler):
     assert abs(cnt.samples - ref["trace_stats"].samples) <= 5e-2 * ref["trace_stats"].samples
 
 
+def test_cone_kernel_variants_agree(monkeypatch):
+    """the production march (one-level fetches through the nearest-mip texture objects, VCT_CONE_VARIANT=2) against the march
+    that blends two levels in every fetch (1) and the literal loop (0): same frame within 1/255, and each inside the oracle gate"""
+    sc = S.cornell_scene(with_suzanne=True)
+    R, W, H = 128, 480, 270
+    view, proj = S.reference_camera(W / H)
+    ref = orc.render_frame(sc, view, proj, R, W, H, orc.default_params(), 7)
+    p = capi.Pipeline(sc, R, W, H)
+    prm = capi.default_params(sampler=capi.SAMPLER_TEX)
+    frames = {}
+    for v in ("2", "1", "0"):
+        monkeypatch.setenv("VCT_CONE_VARIANT", v)
+        p.render_frame(view, proj, prm)
+        frames[v] = p.target.frame().copy()
+        _check_frame(frames[v], ref)
+    p.close()
+    assert max_abs(frames["2"], frames["1"]) <= 1
+    assert max_abs(frames["1"], frames["0"]) <= 1
+
+
+def test_async_readback_equals_blocking_readback():
+    """vct_target_download_frame_async: a moving object, every frame read back through the copy stream while the next frame renders"""
+    import torch
+    R, W, H = 64, 320, 200
+    view, proj = S.reference_camera(W / H)
+    p = capi.Pipeline(S.cornell_scene(with_suzanne=True), R, W, H)
+    n = 6
+    host = [torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(n)]
+    tickets = []
+    for i in range(n):
+        p.scene.upload(S.cornell_scene(with_suzanne=True, theta=0.3 * i))
+        p.render_frame(view, proj)
+        tickets.append(p.target.frame_async(host[i]))
+    for tk in tickets:
+        p.target.wait(tk)
+    with pytest.raises(capi.VctError):
+        p.target.wait(n + 1)
+    for i in range(n):
+        p.scene.upload(S.cornell_scene(with_suzanne=True, theta=0.3 * i))
+        p.render_frame(view, proj)
+        assert np.array_equal(p.target.frame(), host[i]), f"frame {i}"
+    assert not np.array_equal(host[0], host[1])
+    p.close()
+
+
 def test_tile_split_equals_full_frame():
     sc = S.cornell_scene(with_suzanne=True)
     R, W, H = 64, 320, 200

@@ -19,7 +19,8 @@ EXPORTS = [
     "vct_scene_set_lights", "vct_scene_set_cube_size",
     "vct_grid_create", "vct_grid_destroy", "vct_grid_clear", "vct_grid_upload_base", "vct_grid_download",
     "vct_grid_base_device_ptr", "vct_grid_bytes", "vct_grid_occupancy_words", "vct_grid_download_occupancy", "vct_grid_download_array",
-    "vct_target_create", "vct_target_destroy", "vct_target_download_frame", "vct_target_download_gbuffer", "vct_target_frame_device_ptr",
+    "vct_target_create", "vct_target_destroy", "vct_target_download_frame", "vct_target_download_frame_async", "vct_target_download_wait",
+    "vct_target_download_gbuffer", "vct_target_frame_device_ptr",
     "vct_voxelize", "vct_voxelize_reserve", "vct_voxelize_stats", "vct_mipmap", "vct_gbuffer", "vct_cone_trace", "vct_cone_trace_count",
     "vct_render_frame", "vct_last_frame_timings",
     "vct_peer_export", "vct_peer_connect", "vct_peer_disconnect", "vct_peer_error",
@@ -97,6 +98,8 @@ def load():
     L.vct_target_create.argtypes = [vp, i32, i32, C.POINTER(vp)]
     L.vct_target_destroy.argtypes = [vp]
     L.vct_target_download_frame.argtypes = [vp, vp]
+    L.vct_target_download_frame_async.argtypes = [vp, vp, C.POINTER(C.c_uint64)]
+    L.vct_target_download_wait.argtypes = [vp, C.c_uint64]
     L.vct_target_download_gbuffer.argtypes = [vp, vp, vp, vp, vp, vp]
     L.vct_target_frame_device_ptr.argtypes = [vp]; L.vct_target_frame_device_ptr.restype = vp
     L.vct_voxelize.argtypes = [vp, vp, vp, i32, i32]
@@ -207,6 +210,16 @@ class Target:
         check(self.dev.L.vct_target_download_frame(self.h, out.ctypes.data))
         return out
 
+    def frame_async(self, out: np.ndarray) -> int:
+        """start the read-back of the finished frame into `out` (pinned host memory) on the copy stream; returns a ticket for wait()"""
+        assert out.nbytes == self.W * self.H * 4 and out.flags.c_contiguous
+        tk = C.c_uint64(0)
+        check(self.dev.L.vct_target_download_frame_async(self.h, out.ctypes.data, C.byref(tk)))
+        return int(tk.value)
+
+    def wait(self, ticket: int):
+        check(self.dev.L.vct_target_download_wait(self.h, ticket))
+
     def gbuffer(self):
         H, W = self.H, self.W
         tri = np.empty((H, W), np.uint32); depth = np.empty((H, W), np.float32)
@@ -294,7 +307,7 @@ class Pipeline:
     def timings(self) -> dict:
         t = np.zeros(8, np.float32)
         check(self.dev.L.vct_last_frame_timings(self.dev.h, _f32p(t)))
-        return dict(zip(("clear", "voxelize", "mipmap", "gbuffer", "trace", "total", "cone_kernel"), [float(x) for x in t[:7]]))
+        return dict(zip(("clear", "voxelize", "mipmap", "gbuffer", "trace", "total", "cone_kernel", "gbuffer_pass"), [float(x) for x in t[:8]]))
 
     def sync(self): self.dev.sync()
 

@@ -43,21 +43,33 @@ static int ensure_capacity(T** p, size_t* cap, size_t n) {
   return VCT_OK;
 }
 
+// Host -> device copy of `bytes` through pinned staging, asynchronous on the device stream.  The staging memory is a ring of
+// slots filled front to back; a slot is reused only after the event recorded behind its last copy has completed (normally
+// long ago), so per-frame scene updates do not serialise the host with the frames queued on the stream.
 static int stage_upload(vct_scene* sc, void* dst, const void* src, size_t bytes) {
   if (bytes == 0) return VCT_OK;
-  if (bytes > sc->stage_bytes) {
-    // the previous staging buffer may still be in flight
-    VCT_CUDA(cudaStreamSynchronize(sc->dev->stream));
-    if (sc->stage) cudaFreeHost(sc->stage);
-    sc->stage = nullptr; sc->stage_bytes = 0;
-    size_t want = bytes + bytes / 2 + 4096;
-    VCT_CUDA(cudaMallocHost(&sc->stage, want));
-    sc->stage_bytes = want;
-  } else {
-    VCT_CUDA(cudaStreamSynchronize(sc->dev->stream));  // staging buffer reuse; uploads are rare and small
+  cudaStream_t s = sc->dev->stream;
+  vct_scene::StageSlot* slot = &sc->stage[sc->stage_cur];
+  const size_t need = (bytes + 255) & ~(size_t)255;
+  if (slot->used + need > slot->cap) {
+    sc->stage_cur = (sc->stage_cur + 1) % vct_scene::kStageSlots;
+    slot = &sc->stage[sc->stage_cur];
+    if (slot->pending) { VCT_CUDA(cudaEventSynchronize(slot->done)); slot->pending = false; }
+    slot->used = 0;
+    if (slot->cap < need) {
+      if (slot->buf) cudaFreeHost(slot->buf);
+      slot->buf = nullptr; slot->cap = 0;
+      const size_t want = need * 2 > ((size_t)1 << 20) ? need * 2 : ((size_t)1 << 20);
+      VCT_CUDA(cudaMallocHost((void**)&slot->buf, want));
+      slot->cap = want;
+    }
+    if (!slot->done) VCT_CUDA(cudaEventCreateWithFlags(&slot->done, cudaEventDisableTiming));
   }
-  memcpy(sc->stage, src, bytes);
-  VCT_CUDA(cudaMemcpyAsync(dst, sc->stage, bytes, cudaMemcpyHostToDevice, sc->dev->stream));
+  memcpy(slot->buf + slot->used, src, bytes);
+  VCT_CUDA(cudaMemcpyAsync(dst, slot->buf + slot->used, bytes, cudaMemcpyHostToDevice, s));
+  VCT_CUDA(cudaEventRecord(slot->done, s));
+  slot->pending = true;
+  slot->used += need;
   return VCT_OK;
 }
 
@@ -96,6 +108,11 @@ int vct_device_create(int ordinal, vct_device_t** out) {
   VCT_CUDA(cudaMemset(d->counters, 0, CNT_TOTAL * sizeof(uint32_t)));
   VCT_CUDA(cudaMallocHost(&d->counters_host, CNT_TOTAL * sizeof(uint32_t)));
   for (int i = 0; i < 8; i++) VCT_CUDA(cudaEventCreate(&d->ev[i]));
+  VCT_CUDA(cudaStreamCreateWithFlags(&d->stream2, cudaStreamNonBlocking));
+  VCT_CUDA(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+  VCT_CUDA(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
+  VCT_CUDA(cudaEventCreate(&d->ev_g0));
+  VCT_CUDA(cudaEventCreate(&d->ev_g1));
   *out = d;
   return VCT_OK;
 }
@@ -106,7 +123,10 @@ int vct_device_destroy(vct_device_t* d) {
   vct_peer_disconnect(d);
   cudaStreamSynchronize(d->stream);
   cudaFree(d->peer_flags);
-  cudaFree(d->frags); cudaFree(d->occupied); cudaFree(d->tri_recs); cudaFree(d->item_local); cudaFree(d->item_block);
+  cudaFree(d->frags); cudaFree(d->occupied);
+  for (auto& r : d->rs) { cudaFree(r.tri_recs); cudaFree(r.item_local); cudaFree(r.item_block); }
+  if (d->stream2) { cudaStreamSynchronize(d->stream2); cudaStreamDestroy(d->stream2); }
+  for (cudaEvent_t e : {d->ev_fork, d->ev_join, d->ev_g0, d->ev_g1}) if (e) cudaEventDestroy(e);
   cudaFree(d->counters); cudaFreeHost(d->counters_host);
   for (int i = 0; i < 8; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
   cudaStreamDestroy(d->stream);
@@ -136,7 +156,10 @@ int vct_scene_destroy(vct_scene_t* s) {
   if (!s) return VCT_OK;
   cudaStreamSynchronize(s->dev->stream);
   cudaFree(s->verts); cudaFree(s->indices); cudaFree(s->mats); cudaFree(s->draws);
-  if (s->stage) cudaFreeHost(s->stage);
+  for (auto& slot : s->stage) {
+    if (slot.buf) cudaFreeHost(slot.buf);
+    if (slot.done) cudaEventDestroy(slot.done);
+  }
   delete s;
   return VCT_OK;
 }
@@ -219,38 +242,69 @@ int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) {
     g->bytes += n * 24;
   }
   // occupancy bit masks (plain + 2x2x2-dilated) per level, written by the mip stage
+  size_t docc_total = 0;   // the dilated bits of all levels share one allocation (256-byte aligned parts)
+  for (int l = 0; l < levels; l++) {
+    g->docc_off[l] = (uint32_t)docc_total;
+    docc_total += (docc_words(R >> l) + 63) & ~(size_t)63;
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&g->docc_all, docc_total * 4);
+  if (e == cudaSuccess) e = cudaMemsetAsync(g->docc_all, 0, docc_total * 4, dev->stream);
+  g->bytes += docc_total * 4;
   for (int l = 0; l < levels && e == cudaSuccess; l++) {
     const int N = R >> l;
+    g->docc[l] = g->docc_all + g->docc_off[l];
     e = cudaMalloc(&g->occ[l], occ_words(N) * 4);
-    if (e == cudaSuccess) e = cudaMalloc(&g->docc[l], docc_words(N) * 4);
     if (e == cudaSuccess) e = cudaMemsetAsync(g->occ[l], 0, occ_words(N) * 4, dev->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(g->docc[l], 0, docc_words(N) * 4, dev->stream);
-    g->bytes += (occ_words(N) + docc_words(N)) * 4;
+    g->bytes += occ_words(N) * 4;
   }
-  // levels 1.. additionally live in six mipmapped CUDA arrays so that the cone tracer can use the texture units
+  // levels 1.. additionally live in ONE mipmapped CUDA array (six directions stacked along z, zero pads between them) so that
+  // the cone tracer can use the texture units with a single, warp-uniform texture object (GridView)
   if (levels >= 2 && e == cudaSuccess) {
+    const int L = levels - 1;                                   // array levels
+    const int n_coarse = R >> (levels - 1);                     // size of the coarsest level
+    const int pitch_coarse = n_coarse + 1;                      // volume + one zero texel
+    const size_t depth0 = (size_t)6 * pitch_coarse << (L - 1);  // divisible by 2^(L-1): every level's depth is exactly 6 * pitch
     cudaChannelFormatDesc fmt = cudaCreateChannelDesc<uchar4>();
-    cudaExtent ext = make_cudaExtent((size_t)R / 2, (size_t)R / 2, (size_t)R / 2);
-    for (int d = 0; d < 6 && e == cudaSuccess; d++) {
-      e = cudaMallocMipmappedArray(&g->marr[d], &fmt, ext, (unsigned)(levels - 1), cudaArraySurfaceLoadStore);
-      if (e != cudaSuccess) break;
-      for (int l = 1; l < levels && e == cudaSuccess; l++) {
-        cudaArray_t arr;
-        e = cudaGetMipmappedArrayLevel(&arr, g->marr[d], (unsigned)(l - 1));
-        if (e != cudaSuccess) break;
-        cudaResourceDesc rd;
-        memset(&rd, 0, sizeof rd);
-        rd.resType = cudaResourceTypeArray;
-        rd.res.array.array = arr;
-        e = cudaCreateSurfaceObject(&g->surf.s[d][l], &rd);
-        size_t n = (size_t)(R >> l);
-        g->bytes += n * n * n * 4;
-      }
+    cudaExtent ext = make_cudaExtent((size_t)R / 2, (size_t)R / 2, depth0);
+    e = cudaMallocMipmappedArray(&g->marr, &fmt, ext, (unsigned)L, cudaArraySurfaceLoadStore);
+    for (int l = 1; l < levels && e == cudaSuccess; l++) {
+      cudaArray_t arr;
+      e = cudaGetMipmappedArrayLevel(&arr, g->marr, (unsigned)(l - 1));
       if (e != cudaSuccess) break;
       cudaResourceDesc rd;
       memset(&rd, 0, sizeof rd);
+      rd.resType = cudaResourceTypeArray;
+      rd.res.array.array = arr;
+      e = cudaCreateSurfaceObject(&g->surf.s[l], &rd);
+      g->surf.pitch[l] = pitch_coarse << (levels - 1 - l);
+      const size_t n = (size_t)(R >> l);
+      g->bytes += n * n * (size_t)6 * g->surf.pitch[l] * 4;
+      // the pads must read as zero for ever (the volumes are rewritten by every mip build): zero the level in z-chunks
+      if (e == cudaSuccess) {
+        const size_t depth = (size_t)6 * g->surf.pitch[l], chunk = depth < 32 ? depth : 32;
+        void* zeros = nullptr;
+        e = cudaMalloc(&zeros, n * n * 4 * chunk);
+        if (e != cudaSuccess) break;
+        cudaMemsetAsync(zeros, 0, n * n * 4 * chunk, dev->stream);
+        for (size_t z0 = 0; z0 < depth && e == cudaSuccess; z0 += chunk) {
+          cudaMemcpy3DParms z;
+          memset(&z, 0, sizeof z);
+          z.srcPtr = make_cudaPitchedPtr(zeros, n * 4, n, n);
+          z.dstArray = arr;
+          z.dstPos = make_cudaPos(0, 0, z0);
+          z.extent = make_cudaExtent(n, n, depth - z0 < chunk ? depth - z0 : chunk);
+          z.kind = cudaMemcpyDeviceToDevice;
+          e = cudaMemcpy3DAsync(&z, dev->stream);
+        }
+        cudaStreamSynchronize(dev->stream);
+        cudaFree(zeros);
+      }
+    }
+    if (e == cudaSuccess) {
+      cudaResourceDesc rd;
+      memset(&rd, 0, sizeof rd);
       rd.resType = cudaResourceTypeMipmappedArray;
-      rd.res.mipmap.mipmap = g->marr[d];
+      rd.res.mipmap.mipmap = g->marr;
       cudaTextureDesc td;
       memset(&td, 0, sizeof td);
       td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeBorder;  // CLAMP_TO_BORDER, border (0,0,0,0): texture_3d.cpp:10-12
@@ -260,7 +314,10 @@ int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) {
       td.normalizedCoords = 1;
       td.minMipmapLevelClamp = 0.0f;
       td.maxMipmapLevelClamp = (float)(levels - 2);
-      e = cudaCreateTextureObject(&g->tex[d], &rd, &td, nullptr);
+      e = cudaCreateTextureObject(&g->tex_lin, &rd, &td, nullptr);
+      td.mipmapFilterMode = cudaFilterModePoint;   // same texels, one (the nearest) level per fetch
+      if (e == cudaSuccess) e = cudaCreateTextureObject(&g->tex_one, &rd, &td, nullptr);
+      g->tex_zs = (float)n_coarse / (float)(6 * pitch_coarse);
     }
   }
   if (e != cudaSuccess) {
@@ -277,12 +334,12 @@ int vct_grid_destroy(vct_grid_t* g) {
   if (g->dev->peer_grid == g) vct_peer_disconnect(g->dev);
   cudaStreamSynchronize(g->dev->stream);
   cudaFree(g->base_buf[0]); cudaFree(g->base_buf[1]); cudaFree(g->tile_zero);
-  for (int l = 0; l < VCT_MAX_LEVELS; l++) { cudaFree(g->lvl[l]); cudaFree(g->occ[l]); cudaFree(g->docc[l]); }
-  for (int d = 0; d < 6; d++) {
-    if (g->tex[d]) cudaDestroyTextureObject(g->tex[d]);
-    for (int l = 0; l < VCT_MAX_LEVELS; l++) if (g->surf.s[d][l]) cudaDestroySurfaceObject(g->surf.s[d][l]);
-    if (g->marr[d]) cudaFreeMipmappedArray(g->marr[d]);
-  }
+  for (int l = 0; l < VCT_MAX_LEVELS; l++) { cudaFree(g->lvl[l]); cudaFree(g->occ[l]); }
+  cudaFree(g->docc_all);
+  if (g->tex_lin) cudaDestroyTextureObject(g->tex_lin);
+  if (g->tex_one) cudaDestroyTextureObject(g->tex_one);
+  for (int l = 0; l < VCT_MAX_LEVELS; l++) if (g->surf.s[l]) cudaDestroySurfaceObject(g->surf.s[l]);
+  if (g->marr) cudaFreeMipmappedArray(g->marr);
   delete g;
   return VCT_OK;
 }
@@ -321,11 +378,12 @@ int vct_grid_download_array(vct_grid_t* g, int level, int dir, uint32_t* host) {
   VCT_REQUIRE(level >= 1 && level < g->levels, "bad level (the arrays hold levels >= 1)");
   VCT_REQUIRE(dir >= 0 && dir < 6, "bad direction");
   cudaArray_t arr;
-  VCT_CUDA(cudaGetMipmappedArrayLevel(&arr, g->marr[dir], (unsigned)(level - 1)));
+  VCT_CUDA(cudaGetMipmappedArrayLevel(&arr, g->marr, (unsigned)(level - 1)));
   const size_t N = (size_t)(g->R >> level);
   cudaMemcpy3DParms p;
   memset(&p, 0, sizeof p);
   p.srcArray = arr;
+  p.srcPos = make_cudaPos(0, 0, (size_t)dir * g->surf.pitch[level]);   // direction `dir` of the stacked array
   p.dstPtr = make_cudaPitchedPtr(host, N * 4, N, N);
   p.extent = make_cudaExtent(N, N, N);
   p.kind = cudaMemcpyDeviceToHost;
@@ -381,6 +439,12 @@ int vct_target_destroy(vct_target_t* t) {
   cudaStreamSynchronize(t->dev->stream);
   cudaFree(t->vis); cudaFree(t->world_pos); cudaFree(t->normal); cudaFree(t->material); cudaFree(t->frame);
   cudaFree(t->cone_out); cudaFree(t->tile_list);
+  if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
+  for (int i = 0; i < 2; i++) {
+    cudaFree(t->snap[i]);
+    if (t->snap_ready[i]) cudaEventDestroy(t->snap_ready[i]);
+    if (t->copy_done[i]) cudaEventDestroy(t->copy_done[i]);
+  }
   delete t;
   return VCT_OK;
 }
@@ -389,6 +453,40 @@ int vct_target_download_frame(vct_target_t* t, uint32_t* host) {
   VCT_REQUIRE(t && host, "null argument");
   VCT_CUDA(cudaMemcpyAsync(host, t->frame, (size_t)t->W * t->H * 4, cudaMemcpyDeviceToHost, t->dev->stream));
   VCT_CUDA(cudaStreamSynchronize(t->dev->stream));
+  return VCT_OK;
+}
+
+// Asynchronous read-back.  The finished frame is snapshotted on the device stream (8 MB device-to-device at 1080p, a few us),
+// the snapshot is copied to the host on a second stream, and the call returns at once: the next vct_render_frame overlaps the
+// PCIe transfer.  Two snapshots alternate; the device stream waits for the copy that last read the one it is about to overwrite.
+int vct_target_download_frame_async(vct_target_t* t, uint32_t* host, uint64_t* ticket) {
+  VCT_REQUIRE(t && host && ticket, "null argument");
+  cudaStream_t s = t->dev->stream;
+  const size_t bytes = (size_t)t->W * t->H * 4;
+  if (!t->copy_stream) {
+    VCT_CUDA(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+      VCT_CUDA(cudaMalloc(&t->snap[i], bytes));
+      VCT_CUDA(cudaEventCreateWithFlags(&t->snap_ready[i], cudaEventDisableTiming));
+      VCT_CUDA(cudaEventCreateWithFlags(&t->copy_done[i], cudaEventDisableTiming));
+    }
+  }
+  const int b = (int)(t->n_async & 1);
+  if (t->n_async >= 2) VCT_CUDA(cudaStreamWaitEvent(s, t->copy_done[b], 0));
+  VCT_CUDA(cudaMemcpyAsync(t->snap[b], t->frame, bytes, cudaMemcpyDeviceToDevice, s));
+  VCT_CUDA(cudaEventRecord(t->snap_ready[b], s));
+  VCT_CUDA(cudaStreamWaitEvent(t->copy_stream, t->snap_ready[b], 0));
+  VCT_CUDA(cudaMemcpyAsync(host, t->snap[b], bytes, cudaMemcpyDeviceToHost, t->copy_stream));
+  VCT_CUDA(cudaEventRecord(t->copy_done[b], t->copy_stream));
+  *ticket = ++t->n_async;
+  return VCT_OK;
+}
+
+int vct_target_download_wait(vct_target_t* t, uint64_t ticket) {
+  VCT_REQUIRE(t, "target is null");
+  VCT_REQUIRE(ticket >= 1 && ticket <= t->n_async, "unknown ticket");
+  // copy_done[b] always carries the newest copy out of snapshot b, issued at or after `ticket` on the same (ordered) copy stream
+  VCT_CUDA(cudaEventSynchronize(t->copy_done[(ticket - 1) & 1]));
   return VCT_OK;
 }
 
@@ -511,6 +609,7 @@ static int render_frame_sharded(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* 
     if ((rc = launch_peer_wait(dev, PEER_FLAG_FRAME, epoch))) return rc;                    // every tile has arrived
   VCT_CUDA(cudaEventRecord(dev->ev[5], s));
   dev->have_timings = true;
+  dev->gbuffer_overlapped = false;
   return VCT_OK;
 }
 
@@ -521,17 +620,29 @@ int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_targ
   cudaStream_t s = dev->stream;
   int rc;
   VCT_CUDA(cudaEventRecord(dev->ev[0], s));
+  // The G-buffer pass needs the scene and the camera, not the voxel grid: it runs on a second stream beside
+  // clear + voxelize + mip (chains of small, latency-bound kernels that leave most SMs idle) and joins before the trace.
+  VCT_CUDA(cudaEventRecord(dev->ev_fork, s));               // everything queued so far (scene uploads, the previous frame's read-back)
+  VCT_CUDA(cudaStreamWaitEvent(dev->stream2, dev->ev_fork, 0));
+  dev->stream = dev->stream2;
+  VCT_CUDA(cudaEventRecord(dev->ev_g0, dev->stream2));
+  rc = launch_gbuffer(dev, sc, view, proj, t);
+  dev->stream = s;
+  if (rc) return rc;
+  VCT_CUDA(cudaEventRecord(dev->ev_g1, dev->stream2));
+  VCT_CUDA(cudaEventRecord(dev->ev_join, dev->stream2));
   if ((rc = vct_grid_clear(g))) return rc;
   VCT_CUDA(cudaEventRecord(dev->ev[1], s));
   if ((rc = launch_voxelize(dev, sc, g, 0, g->R))) return rc;
   VCT_CUDA(cudaEventRecord(dev->ev[2], s));
   if ((rc = launch_mipmap(dev, g))) return rc;
   VCT_CUDA(cudaEventRecord(dev->ev[3], s));
-  if ((rc = launch_gbuffer(dev, sc, view, proj, t))) return rc;
-  VCT_CUDA(cudaEventRecord(dev->ev[4], s));
+  VCT_CUDA(cudaStreamWaitEvent(s, dev->ev_join, 0));
+  VCT_CUDA(cudaEventRecord(dev->ev[4], s));                 // ev[3]..ev[4] = what is left of the G-buffer pass after the mip build
   if ((rc = launch_cone_trace(dev, sc, g, view, p, t, false))) return rc;
   VCT_CUDA(cudaEventRecord(dev->ev[5], s));
   dev->have_timings = true;
+  dev->gbuffer_overlapped = true;
   return VCT_OK;
 }
 
@@ -542,6 +653,7 @@ int vct_last_frame_timings(vct_device_t* dev, float out_ms[8]) {
   for (int i = 0; i < 5; i++) VCT_CUDA(cudaEventElapsedTime(&out_ms[i], dev->ev[i], dev->ev[i + 1]));
   VCT_CUDA(cudaEventElapsedTime(&out_ms[5], dev->ev[0], dev->ev[5]));
   out_ms[6] = out_ms[7] = 0.0f;
+  if (dev->gbuffer_overlapped) VCT_CUDA(cudaEventElapsedTime(&out_ms[7], dev->ev_g0, dev->ev_g1));
   if (cudaEventQuery(dev->ev[7]) == cudaSuccess && cudaEventElapsedTime(&out_ms[6], dev->ev[6], dev->ev[7]) != cudaSuccess) {
     out_ms[6] = 0.0f;
     cudaGetLastError();

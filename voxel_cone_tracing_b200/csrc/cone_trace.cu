@@ -34,6 +34,10 @@ __device__ __forceinline__ F3 cross(F3 a, F3 b) { return f3(a.y * b.z - b.y * a.
 __device__ __forceinline__ float length(F3 a) { return sqrtf(dot(a, a)); }
 __device__ __forceinline__ F3 normalize(F3 a) { float l = length(a); return f3(a.x / l, a.y / l, a.z / l); }
 __device__ __forceinline__ F3 mix(F3 a, F3 b, float t) { return a * (1.0f - t) + b * t; }
+// production march only: a / |a| through the hardware rsqrt (2 ulp) instead of sqrt + three IEEE divisions (~40 instructions).  A zero
+// component stays exactly zero and a zero vector still gives NaN, so direction signs and the zero-weight tests are unchanged.
+__device__ __forceinline__ F3 normalize_fast(F3 a) { return a * rsqrtf(dot(a, a)); }
+__device__ __forceinline__ float lg2_fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 __device__ __forceinline__ F3 reflect(F3 I, F3 N) { return I - N * (2.0f * dot(N, I)); }
 __device__ __forceinline__ F3 refract(F3 I, F3 N, float eta) {
@@ -160,13 +164,14 @@ __device__ __forceinline__ void fetch_level(const GridView& g, int level, F3 pos
 // would execute when COUNT is set (no early exit in that build).
 // the three directional textureLod fetches of sample_voxel through the texture units:
 //   acc += weight255 * (|d.x| * tex[ix] + |d.y| * tex[iy] + |d.z| * tex[iz])(pos, tex_lod)      (byte units)
-__device__ __forceinline__ void fetch_tex(cudaTextureObject_t tx, cudaTextureObject_t ty, cudaTextureObject_t tz, F3 pos, F3 adir, float tex_lod,
-                                          float weight255, float acc[4]) {
-  // a direction whose weight |d.a| is exactly 0 contributes exactly 0 (axis-aligned cones of the box walls): no fetch
+__device__ __forceinline__ void fetch_tex(const GridView& g, int ix, int iy, int iz, F3 pos, F3 adir, float tex_lod, float weight255, float acc[4]) {
+  // a direction whose weight |d.a| is exactly 0 contributes exactly 0 (axis-aligned cones of the box walls): no fetch.
+  // Direction d of the stacked array starts at normalised depth d/6 (GridView).
   const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 a = adir.x != 0.0f ? tex3DLod<float4>(tx, pos.x, pos.y, pos.z, tex_lod) : zero;
-  const float4 b = adir.y != 0.0f ? tex3DLod<float4>(ty, pos.x, pos.y, pos.z, tex_lod) : zero;
-  const float4 c = adir.z != 0.0f ? tex3DLod<float4>(tz, pos.x, pos.y, pos.z, tex_lod) : zero;
+  const float zz = pos.z * g.tex_zs;
+  const float4 a = adir.x != 0.0f ? tex3DLod<float4>(g.tex_lin, pos.x, pos.y, zz + (float)ix * (1.0f / 6.0f), tex_lod) : zero;
+  const float4 b = adir.y != 0.0f ? tex3DLod<float4>(g.tex_lin, pos.x, pos.y, zz + (float)iy * (1.0f / 6.0f), tex_lod) : zero;
+  const float4 c = adir.z != 0.0f ? tex3DLod<float4>(g.tex_lin, pos.x, pos.y, zz + (float)iz * (1.0f / 6.0f), tex_lod) : zero;
   const float sx = weight255 * adir.x, sy = weight255 * adir.y, sz = weight255 * adir.z;
   acc[0] = fmaf(sx, a.x, fmaf(sy, b.x, fmaf(sz, c.x, acc[0])));
   acc[1] = fmaf(sx, a.y, fmaf(sy, b.y, fmaf(sz, c.y, acc[1])));
@@ -184,7 +189,6 @@ __device__ __forceinline__ uint32_t trace_cone(const GridView& g, F3 origin, F3 
   const float max_level = (float)(g.levels - 1);
   const float margin = 0.5f / (float)(g.R >> (g.levels - 1));  // half a texel of the coarsest level
   float acc[4] = {0.f, 0.f, 0.f, 0.f};  // byte units
-  const cudaTextureObject_t tx = g.tex[ix], ty = g.tex[iy], tz = g.tex[iz];
   float dist = 3.0f * voxel_size;
   float diam = dist * aperture;
   F3 sp = f3(fmaf(dir.x, dist, origin.x), fmaf(dir.y, dist, origin.y), fmaf(dir.z, dist, origin.z));
@@ -208,9 +212,9 @@ __device__ __forceinline__ uint32_t trace_cone(const GridView& g, F3 origin, F3 
     if (TEX) {
       if (lod < 1.0f) {
         if (!e0) fetch_level(g, 0, sp, adir, ix, iy, iz, 1.0f - lod, s);          // level 0 in software (shared by the three directions)
-        if (!e1) fetch_tex(tx, ty, tz, sp, adir, 0.0f, 255.0f * lod, s);           // level 1 = array level 0
+        if (!e1) fetch_tex(g, ix, iy, iz, sp, adir, 0.0f, 255.0f * lod, s);         // level 1 = array level 0
       } else if (!(e0 && e1)) {
-        fetch_tex(tx, ty, tz, sp, adir, lod - 1.0f, 255.0f, s);                   // trilinear + mip-linear in the texture unit
+        fetch_tex(g, ix, iy, iz, sp, adir, lod - 1.0f, 255.0f, s);                 // trilinear + mip-linear in the texture unit
       }
     } else {
       if (!e0) fetch_level(g, l0, sp, adir, ix, iy, iz, 1.0f - f, s);
@@ -242,18 +246,49 @@ __device__ __forceinline__ uint32_t trace_cone(const GridView& g, F3 origin, F3 
 //  * the distance at which the cone has left the border-padded cube for good is computed once and folded into the loop bound.
 //  * lod through the hardware lg2 (2 ulp-class error on a value that only weights two neighbouring levels).
 __device__ __forceinline__ bool footprint_empty_fast(const GridView& g, int level, F3 pos) {
-  const int N = g.R >> level;
-  const float fN = (float)N;
-  const int x = __float2int_rd(fmaf(pos.x, fN, -0.5f)) + 1, y = __float2int_rd(fmaf(pos.y, fN, -0.5f)) + 1, z = __float2int_rd(fmaf(pos.z, fN, -0.5f)) + 1;
-  if ((unsigned)x > (unsigned)N || (unsigned)y > (unsigned)N || (unsigned)z > (unsigned)N) return true;   // footprint wholly outside
-  const uint32_t wpr = (uint32_t)(N + 32) >> 5;
-  const uint32_t w = __ldg(g.docc[level] + ((uint32_t)z * (uint32_t)(N + 1) + (uint32_t)y) * wpr + ((uint32_t)x >> 5));
+  const uint4 t = g.occ_tab[level];   // {word offset, N + 1, words per row, float bits of N}
+  const float fN = __uint_as_float(t.w);
+  // bit index = low corner of the two-texel footprint + 1 = floor(pos*N - 1/2) + 1 = the texel BOUNDARY nearest to pos*N, taken with
+  // the 1.5*2^23 trick (one FFMA, no float->int conversion).  At an exact tie either neighbour may come out: the texel that drops
+  // out of the tested footprint is the one whose filter weight is 0.  Negative and NaN positions give huge unsigned values.
+  const uint32_t x = __float_as_uint(fmaf(pos.x, fN, 12582912.0f)) - 0x4B400000u;
+  const uint32_t y = __float_as_uint(fmaf(pos.y, fN, 12582912.0f)) - 0x4B400000u;
+  const uint32_t z = __float_as_uint(fmaf(pos.z, fN, 12582912.0f)) - 0x4B400000u;
+  if (max(max(x, y), z) >= t.y) return true;   // footprint wholly outside the grid
+  const uint32_t w = __ldg(g.docc_all + (t.x + (z * t.y + y) * t.z + (x >> 5)));
   return ((w >> (x & 31)) & 1u) == 0u;
 }
 
-template <bool TEX>
+// The three directional fetches of the production march.  All six volumes live in one array (GridView), so the texture object
+// is the same for every lane and every direction -- a uniform register, one predicated TEX per direction -- and the direction
+// is picked by the z offset zo.* = d/6.  (With one object per direction the handle differs between lanes and the compiler wraps
+// every TEX in a "waterfall" loop: R2UR + vote + branch, 13 instructions per fetch instead of 2; 13 % of the kernel's issue slots.)
+// ONE = the nearest-mip object.
+template <bool ONE>
+__device__ __forceinline__ void fetch_tex_u(const GridView& g, F3 zo, F3 pos, F3 adir, float tex_lod, float weight255, float acc[4]) {
+  const cudaTextureObject_t t = ONE ? g.tex_one : g.tex_lin;
+  const float zz = pos.z * g.tex_zs;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
+  // a direction whose weight |d.a| is exactly 0 contributes exactly 0: no fetch
+  if (adir.x != 0.0f) a = tex3DLod<float4>(t, pos.x, pos.y, zz + zo.x, tex_lod);
+  if (adir.y != 0.0f) b = tex3DLod<float4>(t, pos.x, pos.y, zz + zo.y, tex_lod);
+  if (adir.z != 0.0f) c = tex3DLod<float4>(t, pos.x, pos.y, zz + zo.z, tex_lod);
+  const float sx = weight255 * adir.x, sy = weight255 * adir.y, sz = weight255 * adir.z;
+  acc[0] = fmaf(sx, a.x, fmaf(sy, b.x, fmaf(sz, c.x, acc[0])));
+  acc[1] = fmaf(sx, a.y, fmaf(sy, b.y, fmaf(sz, c.y, acc[1])));
+  acc[2] = fmaf(sx, a.z, fmaf(sy, b.z, fmaf(sz, c.z, acc[2])));
+  acc[3] = fmaf(sx, a.w, fmaf(sy, b.w, fmaf(sz, c.w, acc[3])));
+}
+
+// SPLIT (texture-unit sampler only): a fetch that needs ONE level goes through the nearest-mip texture object (g.tex_one),
+// which filter one level instead of two -- half the work of the binding unit (the TEX pipe does not shortcut a zero LOD fraction:
+// measured ~4 quad-cycles per trilinear + mip-linear request whatever the fraction).  One level suffices when
+//  * the LOD is integral (lod < 1: level 1 is the only array level involved; lod clamped at the last level), or
+//  * the finer of the two blended levels has an empty footprint: its term is exactly zero, what remains is f * coarser level.
+//    (costs a second occupancy lookup on the LSU pipe, which has slack, only when the coarser footprint is not empty).
+template <bool TEX, bool SPLIT>
 __device__ __forceinline__ void trace_cone_fast(const GridView& g, bool alive, F3 origin, F3 dir, float aperture, float max_dist, float out[4]) {
-  dir = normalize(dir);
+  dir = normalize_fast(dir);
   const int ix = dir.x < 0.0f ? 0 : 1, iy = dir.y < 0.0f ? 2 : 3, iz = dir.z < 0.0f ? 4 : 5;
   const F3 adir = f3(fabsf(dir.x), fabsf(dir.y), fabsf(dir.z));
   const float cube_res = (float)g.R;
@@ -267,20 +302,20 @@ __device__ __forceinline__ void trace_cone_fast(const GridView& g, bool alive, F
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       float t_exit;
-      if (d[k] < 0.0f) t_exit = (o[k] + margin) / -d[k];
-      else if (d[k] > 0.0f) t_exit = ((1.0f + margin) - o[k]) / d[k];
+      if (d[k] < 0.0f) t_exit = __fdividef(o[k] + margin, -d[k]);            // approximate division: the bound carries a voxel of slack
+      else if (d[k] > 0.0f) t_exit = __fdividef((1.0f + margin) - o[k], d[k]);
       else t_exit = (o[k] <= -margin || o[k] >= 1.0f + margin) ? 0.0f : max_dist;
       end = fminf(end, t_exit + voxel_size);   // + one voxel: rounding slack, the extra samples are exactly zero
     }
     if (!(d[0] == d[0] && d[1] == d[1] && d[2] == d[2]) || !alive) end = 0.0f;   // NaN direction (refract() of total reflection): every sample is zero
   }
   float acc[4] = {0.f, 0.f, 0.f, 0.f};  // byte units
-  const cudaTextureObject_t tx = g.tex[ix], ty = g.tex[iy], tz = g.tex[iz];
+  const F3 zo = f3((float)ix * (1.0f / 6.0f), (float)iy * (1.0f / 6.0f), (float)iz * (1.0f / 6.0f));   // where the cone's three directions start in the stacked array
   float dist = 3.0f * voxel_size;
   float diam = dist * aperture;
   while (acc[3] < 255.0f && dist < end) {
     const F3 sp = f3(fmaf(dir.x, dist, origin.x), fmaf(dir.y, dist, origin.y), fmaf(dir.z, dist, origin.z));
-    const float lod = fminf(fmaxf(__log2f(diam * cube_res), 0.0f), max_level);
+    const float lod = fminf(fmaxf(lg2_fast(diam * cube_res), 0.0f), max_level);
     float s[4] = {0.f, 0.f, 0.f, 0.f};
     if (TEX) {
       if (lod < 1.0f) {
@@ -288,11 +323,23 @@ __device__ __forceinline__ void trace_cone_fast(const GridView& g, bool alive, F
         const bool e1 = lod > 0.0f ? footprint_empty_fast(g, 1, sp) : true;
         const bool e0 = (lod > 0.0f && e1) ? true : footprint_empty_fast(g, 0, sp);
         if (!e0) fetch_level(g, 0, sp, adir, ix, iy, iz, 1.0f - lod, s);
-        if (!e1) fetch_tex(tx, ty, tz, sp, adir, 0.0f, 255.0f * lod, s);
+        if (!e1) fetch_tex_u<SPLIT>(g, zo, sp, adir, 0.0f, 255.0f * lod, s);
       } else {
         const float fl = floorf(lod);
         const int l0 = (int)fl;
-        if (!footprint_empty_fast(g, lod > fl ? l0 + 1 : l0, sp)) fetch_tex(tx, ty, tz, sp, adir, lod - 1.0f, 255.0f, s);
+        const bool two = lod > fl;
+        if (!footprint_empty_fast(g, two ? l0 + 1 : l0, sp)) {
+          if (!SPLIT) {
+            fetch_tex_u<false>(g, zo, sp, adir, lod - 1.0f, 255.0f, s);
+          } else {
+            // one level (nearest-mip objects, integral array level) unless both levels contribute
+            bool one = !two;
+            float tl = fl - 1.0f, w = 255.0f;
+            if (two && footprint_empty_fast(g, l0, sp)) { one = true; tl = fl; w = 255.0f * (lod - fl); }
+            if (one) fetch_tex_u<SPLIT>(g, zo, sp, adir, tl, w, s);
+            else fetch_tex_u<false>(g, zo, sp, adir, lod - 1.0f, 255.0f, s);
+          }
+        }
       }
     } else {
       const float fl = floorf(lod);
@@ -316,6 +363,11 @@ __device__ __forceinline__ void trace_cone_fast(const GridView& g, bool alive, F
 __device__ __forceinline__ F3 tangent(F3 n) {
   F3 t1 = cross(n, f3(0.f, 0.f, 1.f)), t2 = cross(n, f3(0.f, 1.f, 0.f));
   return length(t1) > length(t2) ? normalize(t1) : normalize(t2);
+}
+
+__device__ __forceinline__ F3 tangent_fast(F3 n) {
+  const F3 t1 = cross(n, f3(0.f, 0.f, 1.f)), t2 = cross(n, f3(0.f, 1.f, 0.f));
+  return length(t1) > length(t2) ? normalize_fast(t1) : normalize_fast(t2);
 }
 
 __device__ __forceinline__ float specular_aperture(float shininess) {
@@ -367,18 +419,35 @@ __device__ __forceinline__ bool tile_is_mine(const TraceArgs& a, int tile_x, int
   return t32 % a.prm.tile_nranks == a.prm.tile_rank;
 }
 
-// one warp per 8x4 tile: append the tile if any of its pixels is shaded
+// Compacts the 8x4 tiles that contain at least one shaded pixel.  One warp takes kTilesPerWarp consecutive tiles: the G-buffer
+// loads of all of them are in flight together (the kernel is a chain of dependent latencies: material -> position -> atomic ->
+// store; with one tile per warp and an atomic per tile it took 21 us at 1080p), and the warp reserves its list entries with ONE
+// atomicAdd.
+constexpr int kTilesPerWarp = 4;
 __global__ void __launch_bounds__(256)
 tile_list_kernel(const TraceArgs a, uint32_t* __restrict__ tile_list, uint32_t* __restrict__ tile_count) {
   const int lane = threadIdx.x & 31;
-  const int tiles_x = (a.W + 7) / 8, tiles_y = (a.H + 3) / 4;
-  const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (tile >= tiles_x * tiles_y) return;
-  const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
-  if (!tile_is_mine(a, tile_x, tile_y)) return;
-  const Pixel p = load_pixel(a, tile_x * 8 + (lane & 7), tile_y * 4 + (lane >> 3));
-  const uint32_t any = __ballot_sync(0xffffffffu, p.live);
-  if (any && lane == 0) tile_list[atomicAdd(tile_count, 1u)] = (uint32_t)tile;
+  const int tiles_x = (a.W + 7) / 8, tiles_y = (a.H + 3) / 4, n_tiles = tiles_x * tiles_y;
+  const int first = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kTilesPerWarp;
+  if (first >= n_tiles) return;
+  bool live[kTilesPerWarp];
+#pragma unroll
+  for (int k = 0; k < kTilesPerWarp; k++) {
+    const int tile = first + k;
+    live[k] = false;
+    if (tile < n_tiles) {
+      const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+      if (tile_is_mine(a, tile_x, tile_y)) live[k] = load_pixel(a, tile_x * 8 + (lane & 7), tile_y * 4 + (lane >> 3)).live;
+    }
+  }
+  uint32_t mask = 0;
+#pragma unroll
+  for (int k = 0; k < kTilesPerWarp; k++) mask |= (__any_sync(0xffffffffu, live[k]) ? 1u : 0u) << k;
+  if (mask == 0u) return;
+  uint32_t base = 0;
+  if (lane == 0) base = atomicAdd(tile_count, (uint32_t)__popc(mask));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (lane < kTilesPerWarp && ((mask >> lane) & 1u)) tile_list[base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)(first + lane);
 }
 
 template <bool COUNT, bool TEX>
@@ -477,8 +546,8 @@ __device__ __forceinline__ bool cone_setup(const TraceArgs& a, const Pixel& p, i
   d = normal;
   if (slot < nd) {
     if (!a.prm.enable_diffuse) return false;
-    const F3 o1 = normalize(tangent(normal));
-    const F3 o2 = normalize(cross(o1, normal));
+    const F3 o1 = tangent_fast(normal);   // (the reference normalises it twice: a no-op up to an ulp)
+    const F3 o2 = normalize_fast(cross(o1, normal));
     switch (slot) {
       case 0: d = normal; break;
       case 1: d = mix(normal, o1, 0.5f); break;
@@ -495,15 +564,15 @@ __device__ __forceinline__ bool cone_setup(const TraceArgs& a, const Pixel& p, i
   const F3 cam = f3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]);
   if (slot == nd) {
     if (!a.prm.enable_specular) return false;
-    const F3 view_dir = normalize(p.world - cam);
-    d = normalize(reflect(-view_dir, normal));
+    const F3 view_dir = normalize_fast(p.world - cam);
+    d = reflect(-view_dir, normal);   // trace_cone_fast normalises
     aperture = specular_aperture(m->shininess);
     return true;
   }
   if (slot == nd + 1) {
     const bool transmissive = m->illum == 4 || m->illum == 6 || m->illum == 7 || m->illum == 9;
     if (!(transmissive && a.prm.enable_specular)) return false;
-    const F3 view_dir = normalize(p.world - cam);
+    const F3 view_dir = normalize_fast(p.world - cam);
     d = refract(view_dir, normal, 1.0f / m->ior);
     aperture = specular_aperture(m->shininess);
     return true;
@@ -515,14 +584,14 @@ __device__ __forceinline__ bool cone_setup(const TraceArgs& a, const Pixel& p, i
                    0.5f * (L.position[2] / a.cube_size) + 0.5f);
   const F3 ld = lp - p.pos;
   const float dl = length(ld);
-  d = f3(ld.x / dl, ld.y / dl, ld.z / dl);
+  d = ld;   // trace_cone_fast normalises
   aperture = 0.1f;
   max_dist = dl;
   return true;
 }
 
-template <bool TEX>
-__global__ void __launch_bounds__(32 * kConeWarps)
+template <bool TEX, bool SPLIT, int MIN_CTAS>
+__global__ void __launch_bounds__(32 * kConeWarps, MIN_CTAS)
 cone_kernel_fast(const TraceArgs a) {
   const int lane = threadIdx.x & 31;
   const uint32_t t = blockIdx.x * kConeWarps + (threadIdx.x >> 5);
@@ -538,7 +607,7 @@ cone_kernel_fast(const TraceArgs a) {
   float aperture = kTan22_5, max_dist = 0.f;
   const bool on = cone_setup(a, p, slot, d, aperture, max_dist);
   float r[4];
-  trace_cone_fast<TEX>(a.grid, on, p.pos, d, aperture, max_dist, r);
+  trace_cone_fast<TEX, SPLIT>(a.grid, on, p.pos, d, aperture, max_dist, r);
   a.cone_out[(size_t)slot * a.npix + p.pix] = make_float4(r[0], r[1], r[2], r[3]);
 }
 
@@ -708,7 +777,7 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
   const bool debug_view = p->view_voxel_dir < 7;
   if (!debug_view) {
     VCT_CUDA(cudaMemsetAsync(t->tile_list, 0, sizeof(uint32_t), s));
-    tile_list_kernel<<<(n_tiles + 7) / 8, 256, 0, s>>>(a, t->tile_list + 1, t->tile_list);
+    tile_list_kernel<<<(n_tiles + 8 * kTilesPerWarp - 1) / (8 * kTilesPerWarp), 256, 0, s>>>(a, t->tile_list + 1, t->tile_list);
     const dim3 grid((n_tiles + kConeWarps - 1) / kConeWarps, a.n_slots);
     const bool tex = p->sampler == VCT_SAMPLER_TEX && g->levels >= 2;
     VCT_CUDA(cudaEventRecord(dev->ev[6], s));
@@ -716,13 +785,19 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
       VCT_CUDA(cudaMemsetAsync(dev->counters + 16, 0, 8 * sizeof(unsigned long long), s));
       cone_kernel<true, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
     } else {
-      static const int variant = getenv("VCT_CONE_VARIANT") ? atoi(getenv("VCT_CONE_VARIANT")) : 1;
+      // 2 = production (one-level fetches through the nearest-mip texture objects), 1 = every fetch blends two levels, 0 = literal loop; read per call so that tests can compare them
+      const char* ev = getenv("VCT_CONE_VARIANT");
+      const int variant = ev ? atoi(ev) : 2;
       if (variant == 0) {
         if (tex) cone_kernel<false, true><<<grid, 32 * kConeWarps, 0, s>>>(a);
         else cone_kernel<false, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
       } else {
-        if (tex) cone_kernel_fast<true><<<grid, 32 * kConeWarps, 0, s>>>(a);
-        else cone_kernel_fast<false><<<grid, 32 * kConeWarps, 0, s>>>(a);
+        if (tex && variant == 1) cone_kernel_fast<true, false, 9><<<grid, 32 * kConeWarps, 0, s>>>(a);
+        else if (tex && variant == 3) cone_kernel_fast<true, true, 10><<<grid, 32 * kConeWarps, 0, s>>>(a);
+        else if (tex && variant == 4) cone_kernel_fast<true, true, 12><<<grid, 32 * kConeWarps, 0, s>>>(a);
+        else if (tex && variant == 5) cone_kernel_fast<true, true, 9><<<grid, 32 * kConeWarps, 0, s>>>(a);
+        else if (tex) cone_kernel_fast<true, true, 10><<<grid, 32 * kConeWarps, 0, s>>>(a);
+        else cone_kernel_fast<false, false, 7><<<grid, 32 * kConeWarps, 0, s>>>(a);
       }
     }
     VCT_CUDA(cudaEventRecord(dev->ev[7], s));

@@ -191,17 +191,17 @@ int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const floa
   fill_u64_kernel<<<dev->prop.multiProcessorCount * 8, 256, 0, s>>>(t->vis, npx, kVisClear);
   const int sms = dev->prop.multiProcessorCount;
   if (sc->n_tris) {
-    int rc = ensure_tri_scratch(dev, sc->n_tris, sizeof(CamTri));
+    int rc = ensure_tri_scratch(dev, 1, sc->n_tris, sizeof(CamTri));
     if (rc) return rc;
     Mat4 pv;
     mat4_mul_host(proj, view, pv.m);  // projection * view (voxel_cone_tracing.vert:25)
     const uint32_t n_blocks = (sc->n_tris + kSetupThreads - 1) / kSetupThreads;
-    CamTri* tris = (CamTri*)dev->tri_recs;
+    CamTri* tris = (CamTri*)dev->rs[1].tri_recs;
     cam_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, pv, t->W, t->H, tris,
-                                                        dev->item_local, dev->item_block, t->vis, tile_rank, tile_nranks,
+                                                        dev->rs[1].item_local, dev->rs[1].item_block, t->vis, tile_rank, tile_nranks,
                                                         sc->n_tris >= kSmallPathMinTris ? kSmallCamPixels : 0);
-    scan_block_totals_kernel<<<1, 1024, 0, s>>>(dev->item_block, n_blocks, dev->counters + CNT_CAM_ITEMS);
-    cam_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->item_local, dev->item_block, n_blocks, t->W, t->vis, dev->counters, tile_rank, tile_nranks);
+    scan_block_totals_kernel<<<1, 1024, 0, s>>>(dev->rs[1].item_block, n_blocks, dev->counters + CNT_CAM_ITEMS);
+    cam_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->rs[1].item_local, dev->rs[1].item_block, n_blocks, t->W, t->vis, dev->counters, tile_rank, tile_nranks);
     cam_resolve_kernel<<<sms * 8, 256, 0, s>>>(tris, t->vis, t->W, t->H, t->world_pos, t->normal, t->material, t->vis, tile_rank, tile_nranks);
   } else {
     launch_fill_u32(s, t->material, npx, VCT_NO_TRIANGLE);

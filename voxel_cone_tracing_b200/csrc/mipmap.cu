@@ -114,7 +114,7 @@ __global__ void mip_generic_kernel(const uint32_t* __restrict__ src, uint32_t* _
         }
     const uint32_t o = any ? filter_dir_dyn(c, d) : 0u;
     dst[u] = o;
-    surf3Dwrite(o, surf.s[d][dst_level], x * 4, y, z);
+    surf_write(surf, d, dst_level, o, x * 4, y, z);
   }
 }
 
@@ -196,7 +196,7 @@ __device__ __forceinline__ void low_store_level(const uint32_t* __restrict__ src
       const uint32_t* p = src + ((size_t)row * NX + 4 * xq) * 6 + d;
       v = make_uint4(p[0], p[6], p[12], p[18]);
     }
-    surf3Dwrite(v, surf.s[d][level], (x1 + 4 * xq) * 4, y1 + y, z1 + z);
+    surf_write(surf, d, level, v, (x1 + 4 * xq) * 4, y1 + y, z1 + z);
   }
 }
 
@@ -407,7 +407,7 @@ mip_fused_high_kernel(const uint32_t* __restrict__ l3, uint32_t* __restrict__ l4
         }
     const uint32_t o = any ? filter_dir_dyn(c, d) : 0u;
     l4[(((size_t)(bz * 4 + z) * N4 + (by * 4 + y)) * N4 + (bx * 4 + x)) * 6 + d] = o;
-    surf3Dwrite(o, surf.s[d][4], (bx * 4 + x) * 4, by * 4 + y, bz * 4 + z);
+    surf_write(surf, d, 4, o, (bx * 4 + x) * 4, by * 4 + y, bz * 4 + z);
     s4[z][y][x][d] = o;
   }
   __syncthreads();
@@ -427,7 +427,7 @@ mip_fused_high_kernel(const uint32_t* __restrict__ l3, uint32_t* __restrict__ l4
         }
     const uint32_t o = any ? filter_dir_dyn(c, d) : 0u;
     l5[(((size_t)(bz * 2 + z) * N5 + (by * 2 + y)) * N5 + (bx * 2 + x)) * 6 + d] = o;
-    surf3Dwrite(o, surf.s[d][5], (bx * 2 + x) * 4, by * 2 + y, bz * 2 + z);
+    surf_write(surf, d, 5, o, (bx * 2 + x) * 4, by * 2 + y, bz * 2 + z);
     s5[z][y][x][d] = o;
   }
   __syncthreads();
@@ -447,7 +447,7 @@ mip_fused_high_kernel(const uint32_t* __restrict__ l3, uint32_t* __restrict__ l4
         }
     const uint32_t o = any ? filter_dir_dyn(c, d) : 0u;
     l6[(((size_t)bz * N6 + by) * N6 + bx) * 6 + d] = o;
-    surf3Dwrite(o, surf.s[d][6], bx * 4, by, bz);
+    surf_write(surf, d, 6, o, bx * 4, by, bz);
   }
 }
 
@@ -480,39 +480,60 @@ __device__ __forceinline__ uint32_t occ_bit(const uint32_t* __restrict__ occ, in
   return (occ[flat >> 5] >> (flat & 31)) & 1u;
 }
 
-// levels first_level.. from the level below: bit = OR of the 8 child bits (= "a voxel of the texel's level-0 support is non-zero").
-// The levels are tiny and depend on each other, so ONE CTA walks them in order.
+// Occupancy of a level from the level below: bit = OR of the 8 child bits (= "a voxel of the texel's level-0 support is non-zero").
+// R is a power of two (vct_grid_create), so every index below is shifts and masks.
+// N >= 32: an output word is 32 texels of one row = two source words in each of four source rows.
+__device__ __forceinline__ uint32_t occ_reduce_word(const uint32_t* __restrict__ src, int logN, uint32_t w) {
+  const int lw = logN - 5;                                   // log2(words per destination row)
+  const uint32_t k = w & ((1u << lw) - 1u), row = w >> lw, y = row & ((1u << logN) - 1u), z = row >> logN;
+  uint32_t lo = 0, hi = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint32_t* r = src + ((((size_t)(2 * z + (q >> 1)) << (logN + 1)) + (2 * y + (q & 1))) << (lw + 1)) + 2 * k;
+    lo |= r[0]; hi |= r[1];
+  }
+  return occ_pair_or(lo) | (occ_pair_or(hi) << 16);
+}
+// N < 32: one thread per texel (flat bit order), the warp's ballot is the output word
+__device__ __forceinline__ uint32_t occ_reduce_texel(const uint32_t* __restrict__ src, int logN, uint32_t i) {
+  const uint32_t m = (1u << logN) - 1u, x = i & m, y = (i >> logN) & m, z = i >> (2 * logN);
+  const int ls = logN + 1;                                   // source level: Ns = 2N <= 32 texels per row
+  uint32_t any = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint32_t flat = ((((2 * z + (q >> 1)) << ls) + (2 * y + (q & 1))) << ls) + 2 * x;   // children (2x, .) and (2x+1, .): same word
+    any |= (src[flat >> 5] >> (flat & 31)) & 3u;
+  }
+  return any;
+}
+
+// one level with N >= 64: a word per thread over the whole grid
+__global__ void __launch_bounds__(256)
+occ_reduce_level_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int logN) {
+  const uint32_t n_words = 1u << (3 * logN - 5);
+  for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_words; w += gridDim.x * blockDim.x) dst[w] = occ_reduce_word(src, logN, w);
+}
+
+// the small levels (N <= 32) depend on each other and are tiny: ONE CTA walks them in order
 __global__ void __launch_bounds__(1024)
-occ_reduce_kernel(const OccArgs a, int levels) {
-  for (int level = a.first_level; level < levels; level++) {
-    const int N = a.R >> level, Ns = N * 2;
+occ_reduce_kernel(const OccArgs a, int first_level, int levels) {
+  for (int level = first_level; level < levels; level++) {
+    const int N = a.R >> level;
+    int logN = 0;
+    while ((1 << logN) < N) logN++;
     const uint32_t* __restrict__ src = a.occ[level - 1];
     uint32_t* __restrict__ dst = a.occ[level];
-    const size_t n_words = occ_words(N);
-    for (size_t w = threadIdx.x; w < n_words; w += blockDim.x) {
-      uint32_t out = 0;
-      if (N >= 32) {   // the word is 32 texels of one row: two source words in each of four source rows
-        const size_t row = w / (N >> 5);
-        const int k = (int)(w % (N >> 5)), y = (int)(row % N), z = (int)(row / N);
-        uint32_t lo = 0, hi = 0;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          const uint32_t* r = src + (((size_t)(2 * z + (q >> 1)) * Ns + (2 * y + (q & 1))) * Ns >> 5) + 2 * k;
-          lo |= r[0]; hi |= r[1];
-        }
-        out = occ_pair_or(lo) | (occ_pair_or(hi) << 16);
-      } else {
-        for (int b = 0; b < 32; b++) {
-          const size_t flat = w * 32 + b;
-          if (flat >= (size_t)N * N * N) break;
-          const int x = (int)(flat % N), y = (int)((flat / N) % N), z = (int)(flat / ((size_t)N * N));
-          uint32_t any = 0;
-#pragma unroll
-          for (int q = 0; q < 8; q++) any |= occ_bit(src, Ns, 2 * x + (q & 1), 2 * y + ((q >> 1) & 1), 2 * z + (q >> 2));
-          out |= any << b;
-        }
+    if (N >= 32) {
+      const uint32_t n_words = 1u << (3 * logN - 5);
+      for (uint32_t w = threadIdx.x; w < n_words; w += blockDim.x) dst[w] = occ_reduce_word(src, logN, w);
+    } else {
+      const uint32_t n = 1u << (3 * logN);
+      for (uint32_t base = 0; base < n; base += blockDim.x) {   // uniform per warp: every lane takes part in the ballot
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t any = i < n ? occ_reduce_texel(src, logN, i) : 0u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, any != 0u);
+        if ((threadIdx.x & 31) == 0 && i < n) dst[i >> 5] = bal;
       }
-      dst[w] = out;
     }
     __syncthreads();   // the next level reads what this CTA just wrote
   }
@@ -639,7 +660,16 @@ int launch_mipmap(vct_device* dev, vct_grid* g) {
     occ_bits_kernel<<<grid_for((size_t)R * R * R, 256, 148 * 8), 256, 0, s>>>(oa);
     oa.first_level = 1;
   }
-  if (oa.first_level < g->levels) occ_reduce_kernel<<<1, 1024, 0, s>>>(oa, g->levels);
+  {
+    int l = oa.first_level;
+    for (; l < g->levels && (R >> l) >= 64; l++) {   // large levels: one grid-wide launch each
+      int logN = 0;
+      while ((1 << logN) < (R >> l)) logN++;
+      const size_t n_words = (size_t)1 << (3 * logN - 5);
+      occ_reduce_level_kernel<<<grid_for(n_words), 256, 0, s>>>(g->occ[l - 1], g->occ[l], logN);
+    }
+    if (l < g->levels) occ_reduce_kernel<<<1, 1024, 0, s>>>(oa, l, g->levels);
+  }
   occ_dilate_kernel<<<dim3((R + 1 + 127) / 128, R + 1, g->levels), 128, 0, s>>>(oa);
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;

@@ -88,8 +88,19 @@ struct Lights {
 struct GridView {
   uint32_t* base;                 // level 0: R^3 u32, [z][y][x]
   uint32_t* lvl[VCT_MAX_LEVELS];  // level l >= 1: (R>>l)^3 records of 6 u32 (direction-minor)
-  cudaTextureObject_t tex[6];     // per direction: mipmapped 3-D RGBA8 texture of levels 1.. (array level k = grid level k+1)
+  // Hardware-filtered copy of levels 1..: ONE mipmapped 3-D RGBA8 array (array level k = grid level k+1) that holds the six
+  // directional volumes stacked along z, each followed by a pad of zero texels (>= 1 texel at every level = the zero border of
+  // CLAMP_TO_BORDER, texture_3d.cpp:10-12): direction d occupies z' in [d/6, d/6 + tex_zs) of the normalised depth.  One array
+  // means ONE texture object for every fetch -- a warp-uniform handle, so a fetch is a plain TEX instead of a per-lane handle
+  // "waterfall" loop -- and the direction is chosen by the z coordinate.
+  cudaTextureObject_t tex_lin;    // trilinear + mip-linear (GL_LINEAR_MIPMAP_LINEAR, texture_3d.cpp:14)
+  cudaTextureObject_t tex_one;    // same texels, NEAREST mip level: one level per fetch, half the filter work when the LOD is integral
+  float tex_zs;                   // z' = z * tex_zs + d / 6
   const uint32_t* docc[VCT_MAX_LEVELS];  // per level: dilated occupancy bits, see occ_word_index()
+  // the same bits for the production march: all levels live in ONE allocation, docc[l] == docc_all + occ_tab[l].x, and the
+  // per-level constants of the lookup come with one 16-byte load: {word offset, N + 1, words per row, float bits of N}
+  const uint32_t* docc_all;
+  uint4 occ_tab[VCT_MAX_LEVELS];
   int R, levels;
 };
 
@@ -138,10 +149,16 @@ __device__ __forceinline__ void peer_signal_last_block(const PeerView& pv, int k
   }
 }
 
-// surface handles of the per-direction mipmapped arrays: s[dir][grid level], level >= 1
+// surface handles of the stacked mipmapped array: s[grid level], level >= 1; direction d starts at z = d * pitch[level]
 struct SurfSet {
-  cudaSurfaceObject_t s[6][VCT_MAX_LEVELS];
+  cudaSurfaceObject_t s[VCT_MAX_LEVELS];
+  int pitch[VCT_MAX_LEVELS];
 };
+// one texel / four texels of direction d
+template <class T>
+__device__ __forceinline__ void surf_write(const SurfSet& surf, int d, int level, T v, int x_bytes, int y, int z) {
+  surf3Dwrite(v, surf.s[level], x_bytes, y, z + d * surf.pitch[level]);
+}
 
 }  // namespace vct
 
@@ -156,14 +173,21 @@ struct vct_device {
   uint32_t* occupied = nullptr;      // voxel indices that received >= 1 fragment
   uint64_t frag_capacity = 0;
   // raster scratch (grown on demand)
-  void* tri_recs = nullptr;  size_t tri_recs_bytes = 0;
-  uint32_t* item_local = nullptr;    // per-triangle exclusive prefix inside its 256-block
-  uint32_t* item_block = nullptr;    // per-block exclusive prefix
-  size_t item_capacity_tris = 0;
+  // one set per rasteriser (0 = voxelizer, 1 = G-buffer): the two run concurrently on different streams
+  struct RasterScratch {
+    void* tri_recs = nullptr;  size_t tri_recs_bytes = 0;
+    uint32_t* item_local = nullptr;    // per-triangle exclusive prefix inside its 256-block
+    uint32_t* item_block = nullptr;    // per-block exclusive prefix
+    size_t item_capacity_tris = 0;
+  } rs[2];
+  // second stream: the G-buffer pass of a frame does not depend on the voxel grid and runs beside clear + voxelize + mip
+  cudaStream_t stream2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_g0 = nullptr, ev_g1 = nullptr;
   uint32_t* counters = nullptr;      // device counters, see enum below
   uint32_t* counters_host = nullptr; // pinned mirror
   cudaEvent_t ev[8] = {};
   bool have_timings = false;
+  bool gbuffer_overlapped = false;   // the last frame ran its G-buffer pass on stream2 (ev_g0..ev_g1)
   // multi-GPU connection (vct_peer_connect)
   vct::PeerView peers{};               // peers.nranks <= 1 when not connected
   uint32_t* peer_flags = nullptr;      // local flag block [PEER_FLAG_KINDS][VCT_MAX_RANKS] + done counters + error word
@@ -174,7 +198,7 @@ struct vct_device {
   vct_target_t_* peer_target = nullptr;
   uint32_t peer_epoch = 0;             // frames rendered since vct_peer_connect
 };
-enum { CNT_ITEMS = 0, CNT_FRAGS = 1, CNT_OCCUPIED = 2, CNT_MAXLIST = 3, CNT_CAM_ITEMS = 4, CNT_SAMPLES = 8 /* ..15 */, CNT_TOTAL = 32 };
+enum { CNT_ITEMS = 0, CNT_FRAGS = 1, CNT_OCCUPIED = 2, CNT_MAXLIST = 3, CNT_CAM_ITEMS = 12 /* outside the words the voxelizer clears every frame */, CNT_SAMPLES = 16 /* ..31, as 8 x u64 */, CNT_TOTAL = 32 };
 
 struct vct_scene {
   vct_device* dev = nullptr;
@@ -185,8 +209,12 @@ struct vct_scene {
   uint32_t n_tris = 0;
   vct::Lights lights{};
   float cube_size = 1.0f;
-  // pinned staging so that per-frame updates are true async copies
-  void* stage = nullptr; size_t stage_bytes = 0;
+  // pinned staging so that per-frame updates are true async copies: a ring of bump-allocated slots, each guarded by the
+  // event of its last copy, so that an upload never waits for the frames still in flight on the stream
+  struct StageSlot { unsigned char* buf = nullptr; size_t cap = 0, used = 0; cudaEvent_t done = nullptr; bool pending = false; };
+  static constexpr int kStageSlots = 3;
+  StageSlot stage[kStageSlots];
+  int stage_cur = 0;
 };
 
 struct vct_grid {
@@ -197,19 +225,30 @@ struct vct_grid {
   uint32_t* lvl[VCT_MAX_LEVELS] = {};
   size_t bytes = 0;
   // hardware-filtered copy of levels 1.. (written by the mip kernels through surfaces)
-  cudaMipmappedArray_t marr[6] = {};
-  cudaTextureObject_t tex[6] = {};
+  cudaMipmappedArray_t marr = nullptr;   // the six directions stacked along z (see GridView)
+  cudaTextureObject_t tex_lin = 0, tex_one = 0;
+  float tex_zs = 0.0f;
   vct::SurfSet surf{};
   alignas(64) unsigned char tmap_storage[2][128] = {};   // CUtensorMap (TMA descriptor) of base_buf[0] / base_buf[1], built on first use
   uint32_t* tmap_base_ptr[2] = {};
   uint8_t* tile_zero = nullptr;         // mip stage: per 32x8x8 tile "levels 1-3 of this tile are known to be zero" (skip rewriting zeros)
   uint32_t* occ[VCT_MAX_LEVELS] = {};   // non-dilated occupancy bits per level
-  uint32_t* docc[VCT_MAX_LEVELS] = {};  // dilated occupancy bits per level
+  uint32_t* docc[VCT_MAX_LEVELS] = {};  // dilated occupancy bits per level: pointers into docc_all
+  uint32_t* docc_all = nullptr;
+  uint32_t docc_off[VCT_MAX_LEVELS] = {};   // word offset of each level in docc_all
   vct::GridView view() const {
     vct::GridView v;
     v.base = base; v.R = R; v.levels = levels;
     for (int i = 0; i < VCT_MAX_LEVELS; i++) { v.lvl[i] = lvl[i]; v.docc[i] = docc[i]; }
-    for (int d = 0; d < 6; d++) v.tex[d] = tex[d];
+    v.tex_lin = tex_lin; v.tex_one = tex_one; v.tex_zs = tex_zs;
+    v.docc_all = docc_all;
+    for (int l = 0; l < VCT_MAX_LEVELS; l++) {
+      const int N = l < levels ? (R >> l) : 0;
+      const float fN = (float)N;
+      uint32_t bits;
+      memcpy(&bits, &fN, 4);
+      v.occ_tab[l] = make_uint4(docc_off[l], (uint32_t)(N + 1), (uint32_t)vct::occ_wpr(N), bits);
+    }
     return v;
   }
 };
@@ -225,6 +264,11 @@ struct vct_target_t_ {
   void* cone_out = nullptr;           // float4 [slot][pixel], grown on demand by the cone tracer
   size_t cone_out_elems = 0;
   uint32_t* tile_list = nullptr;      // [0] = count, [1..] = live 8x4 tiles
+  // asynchronous read-back (vct_target_download_frame_async): device-side snapshots + a copy stream
+  uint32_t* snap[2] = {};
+  cudaStream_t copy_stream = nullptr;
+  cudaEvent_t snap_ready[2] = {}, copy_done[2] = {};
+  uint64_t n_async = 0;               // tickets issued
 };
 
 struct vct_tex3d {
@@ -240,7 +284,7 @@ static inline unsigned grid_for(size_t n, unsigned threads = 256, unsigned cap =
 
 // ---- stage entry points implemented in the .cu files ------------------------------------
 namespace vct {
-int ensure_tri_scratch(vct_device* dev, size_t n_tris, size_t rec_bytes);
+int ensure_tri_scratch(vct_device* dev, int which /* 0 voxelizer, 1 G-buffer */, size_t n_tris, size_t rec_bytes);
 int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1, const PeerView* push = nullptr);
 int launch_peer_wait(vct_device* dev, int kind, uint32_t epoch);
 int launch_mipmap(vct_device* dev, vct_grid* g);

@@ -293,23 +293,24 @@ vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frag
   if (pv.nranks > 1) peer_signal_last_block(pv, PEER_FLAG_PUSHED, -1);
 }
 
-int ensure_tri_scratch(vct_device* dev, size_t n_tris, size_t rec_bytes) {
+int ensure_tri_scratch(vct_device* dev, int which, size_t n_tris, size_t rec_bytes) {
+  vct_device::RasterScratch& r = dev->rs[which];
   size_t need = n_tris * rec_bytes;
-  if (need > dev->tri_recs_bytes) {
-    if (dev->tri_recs) cudaFree(dev->tri_recs);
-    dev->tri_recs = nullptr; dev->tri_recs_bytes = 0;
+  if (need > r.tri_recs_bytes) {
+    if (r.tri_recs) cudaFree(r.tri_recs);
+    r.tri_recs = nullptr; r.tri_recs_bytes = 0;
     size_t want = need + need / 4 + 4096;
-    VCT_CUDA(cudaMalloc(&dev->tri_recs, want));
-    dev->tri_recs_bytes = want;
+    VCT_CUDA(cudaMalloc(&r.tri_recs, want));
+    r.tri_recs_bytes = want;
   }
-  if (n_tris > dev->item_capacity_tris) {
-    if (dev->item_local) cudaFree(dev->item_local);
-    if (dev->item_block) cudaFree(dev->item_block);
-    dev->item_local = dev->item_block = nullptr; dev->item_capacity_tris = 0;
+  if (n_tris > r.item_capacity_tris) {
+    if (r.item_local) cudaFree(r.item_local);
+    if (r.item_block) cudaFree(r.item_block);
+    r.item_local = r.item_block = nullptr; r.item_capacity_tris = 0;
     size_t cap = n_tris + n_tris / 4 + 1024;
-    VCT_CUDA(cudaMalloc(&dev->item_local, cap * sizeof(uint32_t)));
-    VCT_CUDA(cudaMalloc(&dev->item_block, (cap / kSetupThreads + 2) * sizeof(uint32_t)));
-    dev->item_capacity_tris = cap;
+    VCT_CUDA(cudaMalloc(&r.item_local, cap * sizeof(uint32_t)));
+    VCT_CUDA(cudaMalloc(&r.item_block, (cap / kSetupThreads + 2) * sizeof(uint32_t)));
+    r.item_capacity_tris = cap;
   }
   return VCT_OK;
 }
@@ -319,7 +320,7 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
   memset(&pv, 0, sizeof pv);
   if (push) pv = *push;
   if (sc->n_tris == 0 && !push) return VCT_OK;
-  int rc = ensure_tri_scratch(dev, sc->n_tris, sizeof(VoxTri));
+  int rc = ensure_tri_scratch(dev, 0, sc->n_tris, sizeof(VoxTri));
   if (rc) return rc;
   if (dev->frag_capacity == 0) {
     rc = vct_voxelize_reserve(dev, 1u << 20);
@@ -328,16 +329,16 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
   cudaStream_t s = dev->stream;
   VCT_CUDA(cudaMemsetAsync(dev->counters, 0, 8 * sizeof(uint32_t), s));
   const uint32_t n_blocks = (sc->n_tris + kSetupThreads - 1) / kSetupThreads;
-  VoxTri* tris = (VoxTri*)dev->tri_recs;
+  VoxTri* tris = (VoxTri*)dev->rs[0].tri_recs;
   const int sms = dev->prop.multiProcessorCount;
   if (sc->n_tris) {   // an empty scene still runs the resolve kernel in multi-GPU mode: the peers wait for its signal
     FragCtx ctx;
     ctx.mats = sc->mats; ctx.L = sc->lights; ctx.cube_size = sc->cube_size; ctx.R = g->R; ctx.z0 = z0; ctx.z1 = z1;
     ctx.base = g->base; ctx.frags = dev->frags; ctx.frag_capacity = (uint32_t)dev->frag_capacity; ctx.occupied = dev->occupied; ctx.counters = dev->counters;
     vox_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, sc->cube_size, g->R, z0, z1, tris,
-                                                          dev->item_local, dev->item_block, ctx, sc->n_tris >= kSmallPathMinTris ? kSmallPixels : 0);
-    scan_block_totals_kernel<<<1, 1024, 0, s>>>(dev->item_block, n_blocks, dev->counters + CNT_ITEMS);
-    vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->item_local, dev->item_block, n_blocks, ctx);
+                                                          dev->rs[0].item_local, dev->rs[0].item_block, ctx, sc->n_tris >= kSmallPathMinTris ? kSmallPixels : 0);
+    scan_block_totals_kernel<<<1, 1024, 0, s>>>(dev->rs[0].item_block, n_blocks, dev->counters + CNT_ITEMS);
+    vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->rs[0].item_local, dev->rs[0].item_block, n_blocks, ctx);
   }
   vox_resolve_kernel<<<sms * 4, 128, 0, s>>>(g->base, dev->frags, dev->occupied, dev->counters, (uint32_t)dev->frag_capacity, pv);
   VCT_CUDA(cudaGetLastError());

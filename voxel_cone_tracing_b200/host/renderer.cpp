@@ -211,6 +211,12 @@ void Renderer::render() {
 }
 
 bool Renderer::read_frame(uint32_t* rgba8) { return ok() && check(vct_target_download_frame(m_target, rgba8), "vct_target_download_frame"); }
+uint64_t Renderer::read_frame_async(uint32_t* pinned_rgba8) {
+  uint64_t ticket = 0;
+  if (!ok() || !check(vct_target_download_frame_async(m_target, pinned_rgba8, &ticket), "vct_target_download_frame_async")) return 0;
+  return ticket;
+}
+bool Renderer::wait_frame(uint64_t ticket) { return ok() && check(vct_target_download_wait(m_target, ticket), "vct_target_download_wait"); }
 void* Renderer::frame_device_ptr() { return m_target ? vct_target_frame_device_ptr(m_target) : nullptr; }
 bool Renderer::read_voxels(int level, int dir, uint32_t* rgba8) { return ok() && check(vct_grid_download(m_grid, level, dir, rgba8), "vct_grid_download"); }
 
