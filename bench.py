@@ -41,7 +41,7 @@ CONFIGS = {
     5: dict(name="synthetic 4M triangles 1024^3 7680x4320 (RGBA8, 7 levels, 9 cones: reference mode)", R=1024, W=7680, H=4320,
             scene="synthetic", tris=4_000_000, seed=0x5EED0002),
 }
-KERNELS_PER_FRAME = 16  # voxelize 4 (setup, scan, raster, resolve) + mip 4 (fused low, fused high, occupancy bits, dilate) + gbuffer 5 (clear, setup, scan, raster, resolve) + trace 3 (tile list, cones, shade)
+KERNELS_PER_FRAME = 12  # voxelize 3 (setup+scan, raster, resolve) + mip 2 (fused low; tail = levels 4-6 + occupancy + dilation) + gbuffer 4 (clear, setup+scan, raster, resolve) + trace 3 (tile list, cones, shade)
 # ncu --set full capture of cone_kernel on this workload (profiles/r01_cone_kernel_ncu.md): dram__bytes_read.sum + dram__bytes_write.sum per launch
 CONE_KERNEL_DRAM_TRAFFIC = {1: 31.4e6 + 97.0e6, 0: 31.1e6 + 99.5e6}
 

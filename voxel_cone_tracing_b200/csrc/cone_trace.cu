@@ -793,9 +793,6 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
         else cone_kernel<false, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
       } else {
         if (tex && variant == 1) cone_kernel_fast<true, false, 9><<<grid, 32 * kConeWarps, 0, s>>>(a);
-        else if (tex && variant == 3) cone_kernel_fast<true, true, 10><<<grid, 32 * kConeWarps, 0, s>>>(a);
-        else if (tex && variant == 4) cone_kernel_fast<true, true, 12><<<grid, 32 * kConeWarps, 0, s>>>(a);
-        else if (tex && variant == 5) cone_kernel_fast<true, true, 9><<<grid, 32 * kConeWarps, 0, s>>>(a);
         else if (tex) cone_kernel_fast<true, true, 10><<<grid, 32 * kConeWarps, 0, s>>>(a);
         else cone_kernel_fast<false, false, 7><<<grid, 32 * kConeWarps, 0, s>>>(a);
       }

@@ -20,7 +20,8 @@ constexpr int kSmallCamPixels = 36;
 __global__ void __launch_bounds__(kSetupThreads)
 cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ draws,
                  uint32_t n_draws, uint32_t n_tris, Mat4 pv, int W, int H, CamTri* __restrict__ out, uint32_t* __restrict__ item_local,
-                 uint32_t* __restrict__ item_block, unsigned long long* __restrict__ vis, int tile_rank, int tile_nranks, int small_limit) {
+                 uint32_t* __restrict__ item_block, unsigned long long* __restrict__ vis, int tile_rank, int tile_nranks, int small_limit,
+                 uint32_t* scan_ticket, uint32_t* scan_total) {
   uint32_t t = blockIdx.x * kSetupThreads + threadIdx.x;
   uint32_t count = 0;
   RasterTri srt;   // copy for the small-triangle path below
@@ -83,7 +84,7 @@ cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
     }
   }
   if (small) count = 0;
-  block_scan_items(count, t, n_tris, item_local, item_block);
+  block_scan_items(count, t, n_tris, item_local, item_block, scan_ticket, scan_total);
 }
 
 __global__ void __launch_bounds__(256)
@@ -199,8 +200,8 @@ int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const floa
     CamTri* tris = (CamTri*)dev->rs[1].tri_recs;
     cam_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, pv, t->W, t->H, tris,
                                                         dev->rs[1].item_local, dev->rs[1].item_block, t->vis, tile_rank, tile_nranks,
-                                                        sc->n_tris >= kSmallPathMinTris ? kSmallCamPixels : 0);
-    scan_block_totals_kernel<<<1, 1024, 0, s>>>(dev->rs[1].item_block, n_blocks, dev->counters + CNT_CAM_ITEMS);
+                                                        sc->n_tris >= kSmallPathMinTris ? kSmallCamPixels : 0, dev->counters + CNT_TICKET_CAM,
+                                                        dev->counters + CNT_CAM_ITEMS);
     cam_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->rs[1].item_local, dev->rs[1].item_block, n_blocks, t->W, t->vis, dev->counters, tile_rank, tile_nranks);
     cam_resolve_kernel<<<sms * 8, 256, 0, s>>>(tris, t->vis, t->W, t->H, t->world_pos, t->normal, t->material, t->vis, tile_rank, tile_nranks);
   } else {

@@ -376,13 +376,18 @@ mip_fused_low_kernel(const __grid_constant__ CUtensorMap tmap, const LowArgs a) 
 
 // ---------------------------------------------------------------------------------------------
 // fused levels 3 -> 4,5,6.  Tile = 8^3 level-3 records, 256 threads.
-__global__ void __launch_bounds__(256)
-mip_fused_high_kernel(const uint32_t* __restrict__ l3, uint32_t* __restrict__ l4, uint32_t* __restrict__ l5, uint32_t* __restrict__ l6, int N3, const SurfSet surf) {
-  __shared__ uint32_t s3[8][8][8][6];  // 12 KB
-  __shared__ uint32_t s4[4][4][4][6];
-  __shared__ uint32_t s5[2][2][2][6];
+struct HighSmem {
+  uint32_t s3[8][8][8][6];  // 12 KB
+  uint32_t s4[4][4][4][6];
+  uint32_t s5[2][2][2][6];
+};
+__device__ __forceinline__ void mip_high_tile(HighSmem& sm, int block, const uint32_t* __restrict__ l3, uint32_t* __restrict__ l4, uint32_t* __restrict__ l5,
+                                              uint32_t* __restrict__ l6, int N3, const SurfSet& surf) {
+  uint32_t (&s3)[8][8][8][6] = sm.s3;
+  uint32_t (&s4)[4][4][4][6] = sm.s4;
+  uint32_t (&s5)[2][2][2][6] = sm.s5;
   const int tiles = N3 / 8;
-  const int bx = blockIdx.x % tiles, by = (blockIdx.x / tiles) % tiles, bz = blockIdx.x / (tiles * tiles);
+  const int bx = block % tiles, by = (block / tiles) % tiles, bz = block / (tiles * tiles);
   const int t = threadIdx.x;
   // 64 rows (z,y) of 48 words
   for (int u = t; u < 64 * 48; u += 256) {
@@ -451,6 +456,12 @@ mip_fused_high_kernel(const uint32_t* __restrict__ l3, uint32_t* __restrict__ l4
   }
 }
 
+__global__ void __launch_bounds__(256)
+mip_fused_high_kernel(const uint32_t* __restrict__ l3, uint32_t* __restrict__ l4, uint32_t* __restrict__ l5, uint32_t* __restrict__ l6, int N3, const SurfSet surf) {
+  __shared__ HighSmem sm;
+  mip_high_tile(sm, (int)blockIdx.x, l3, l4, l5, l6, N3, surf);
+}
+
 // ---------------------------------------------------------------------------------------------
 // occupancy bits
 struct OccArgs {
@@ -515,8 +526,7 @@ occ_reduce_level_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__
 }
 
 // the small levels (N <= 32) depend on each other and are tiny: ONE CTA walks them in order
-__global__ void __launch_bounds__(1024)
-occ_reduce_kernel(const OccArgs a, int first_level, int levels) {
+__device__ __forceinline__ void occ_reduce_small(const OccArgs& a, int first_level, int levels) {
   for (int level = first_level; level < levels; level++) {
     const int N = a.R >> level;
     int logN = 0;
@@ -535,9 +545,11 @@ occ_reduce_kernel(const OccArgs a, int first_level, int levels) {
         if ((threadIdx.x & 31) == 0 && i < n) dst[i >> 5] = bal;
       }
     }
-    __syncthreads();   // the next level reads what this CTA just wrote
+    __syncthreads();   // the next level (and the dilation below) reads what this CTA just wrote
   }
 }
+__global__ void __launch_bounds__(1024)
+occ_reduce_kernel(const OccArgs a, int first_level, int levels) { occ_reduce_small(a, first_level, levels); }
 
 // 32 occupancy bits of row (y,z) starting at x = 32*k; rows outside the level read as zero
 __device__ __forceinline__ uint32_t occ_row_bits(const uint32_t* __restrict__ occ, int N, int y, int z, int k) {
@@ -547,15 +559,12 @@ __device__ __forceinline__ uint32_t occ_row_bits(const uint32_t* __restrict__ oc
   return (occ[flat >> 5] >> (flat & 31)) & ((1u << N) - 1u);
 }
 
-// dilation: docc bit (x+1,y+1,z+1) = OR of occ over [x,x+1]x[y,y+1]x[z,z+1].  One thread per output ROW (y,z): walks the
-// row's words carrying the top bit of the previous word.  grid: x = rows of one z-slice, y = z-slice, z = level
-__global__ void __launch_bounds__(128)
-occ_dilate_kernel(const OccArgs a) {
-  const int level = (int)blockIdx.z;
+// dilation: docc bit (x+1,y+1,z+1) = OR of occ over [x,x+1]x[y,y+1]x[z,z+1].  One thread per output ROW (yy,zz) of a level:
+// walks the row's words carrying the top bit of the previous word.  PLAIN loads: in the merged tail kernel the small levels are
+// written by the same launch.
+__device__ __forceinline__ void occ_dilate_row(const OccArgs& a, int level, int yy, int zz) {
   const int N = a.R >> level, D = N + 1, wpr = occ_wpr(N);
-  const int zz = (int)blockIdx.y, yy = (int)(blockIdx.x * blockDim.x + threadIdx.x);
-  if (zz >= D || yy >= D) return;
-  const uint32_t* __restrict__ occ = a.occ[level];
+  const uint32_t* occ = a.occ[level];
   uint32_t* __restrict__ out = a.docc[level] + ((size_t)zz * D + yy) * wpr;
   const int y = yy - 1, z = zz - 1;
   if (N >= 32) {
@@ -573,7 +582,7 @@ occ_dilate_kernel(const OccArgs a) {
       uint32_t r = 0;
       if (k < nw) {
 #pragma unroll
-        for (int q = 0; q < 4; q++) r |= ok[q] ? __ldg(rows[q] + k) : 0u;
+        for (int q = 0; q < 4; q++) r |= ok[q] ? rows[q][k] : 0u;
       }
       out[k] = (r << 1) | carry | r;
       carry = r >> 31;
@@ -585,6 +594,53 @@ occ_dilate_kernel(const OccArgs a) {
 #pragma unroll
       for (int dy = 0; dy < 2; dy++) r |= occ_row_bits(occ, N, y + dy, z + dz, 0);
     out[0] = (r << 1) | r;
+  }
+}
+
+// grid: x = rows of one z-slice, y = z-slice, z = level
+__global__ void __launch_bounds__(128)
+occ_dilate_kernel(const OccArgs a) {
+  const int level = (int)blockIdx.z;
+  const int D = (a.R >> level) + 1;
+  const int zz = (int)blockIdx.y, yy = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (zz >= D || yy >= D) return;
+  occ_dilate_row(a, level, yy, zz);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Everything that follows the fused low kernel, in ONE launch (three independent jobs that each depend on the low kernel only;
+// as three launches they cost 13 + 6 + 8 us at 256^3, most of it launch and tail latency):
+//   blocks [0, n_high)            levels 3 -> 4, 5, 6 of the colour pyramid (mip_high_tile)
+//   block  n_high                 occupancy bits of the small levels (N <= 32) + their dilation
+//   blocks (n_high, ...)          dilation of the large levels, 256 rows per block
+struct TailArgs {
+  const uint32_t* l3; uint32_t *l4, *l5, *l6;
+  int N3, n_high;
+  OccArgs occ;
+  int small_first, levels;      // the small levels are small_first .. levels-1
+  int dil_start[VCT_MAX_LEVELS + 1];   // first block (relative to n_high + 1) of the dilation of each large level 0 .. small_first-1
+  SurfSet surf;
+};
+
+__global__ void __launch_bounds__(256)
+mip_tail_kernel(const TailArgs a) {
+  __shared__ HighSmem sm;
+  const int b = (int)blockIdx.x;
+  if (b < a.n_high) {
+    mip_high_tile(sm, b, a.l3, a.l4, a.l5, a.l6, a.N3, a.surf);
+  } else if (b == a.n_high) {
+    occ_reduce_small(a.occ, a.small_first, a.levels);
+    for (int level = a.small_first; level < a.levels; level++) {
+      const int D = (a.occ.R >> level) + 1;
+      for (int r = threadIdx.x; r < D * D; r += blockDim.x) occ_dilate_row(a.occ, level, r % D, r / D);
+    }
+  } else {
+    const int rb = b - a.n_high - 1;
+    int level = 0;
+    while (level + 1 < a.small_first && rb >= a.dil_start[level + 1]) level++;
+    const int D = (a.occ.R >> level) + 1;
+    const int r = (rb - a.dil_start[level]) * 256 + (int)threadIdx.x;
+    if (r < D * D) occ_dilate_row(a.occ, level, r % D, r / D);
   }
 }
 
@@ -639,11 +695,41 @@ int launch_mipmap(vct_device* dev, vct_grid* g) {
     mip_fused_low_kernel<<<ctas, 256, sizeof(LowSmem), s>>>(*reinterpret_cast<const CUtensorMap*>(g->tmap_storage[buf]), la);
     level = 3;
     occ_from_data = 3;  // levels 0..2 got their occupancy bits from the fused kernel
-    if (g->levels >= 7 && (R >> 3) % 8 == 0) {
-      const int tiles = (R >> 3) / 8;
-      mip_fused_high_kernel<<<tiles * tiles * tiles, 256, 0, s>>>(g->lvl[3], g->lvl[4], g->lvl[5], g->lvl[6], R >> 3, g->surf);
-      level = 6;
+  }
+  OccArgs oa;
+  oa.R = R; oa.first_level = occ_from_data;
+  for (int l = 0; l < VCT_MAX_LEVELS; l++) { oa.src[l] = l == 0 ? g->base : g->lvl[l]; oa.occ[l] = g->occ[l]; oa.docc[l] = g->docc[l]; }
+  if (occ_from_data == 0) {
+    occ_bits_kernel<<<grid_for((size_t)R * R * R, 256, 148 * 8), 256, 0, s>>>(oa);
+    oa.first_level = 1;
+  }
+  // occupancy bits of the large levels (N >= 64) that the fused kernel did not produce: one grid-wide launch each
+  int small_first = oa.first_level;
+  for (; small_first < g->levels && (R >> small_first) >= 64; small_first++) {
+    int logN = 0;
+    while ((1 << logN) < (R >> small_first)) logN++;
+    const size_t n_words = (size_t)1 << (3 * logN - 5);
+    occ_reduce_level_kernel<<<grid_for(n_words), 256, 0, s>>>(g->occ[small_first - 1], g->occ[small_first], logN);
+  }
+  bool occ_done = false;
+  if (level == 3 && g->levels >= 7 && (R >> 3) % 8 == 0) {
+    // levels 3 -> 6, the small occupancy levels and every dilation in one launch
+    const int tiles = (R >> 3) / 8;
+    TailArgs ta;
+    ta.l3 = g->lvl[3]; ta.l4 = g->lvl[4]; ta.l5 = g->lvl[5]; ta.l6 = g->lvl[6];
+    ta.N3 = R >> 3; ta.n_high = tiles * tiles * tiles;
+    ta.occ = oa; ta.small_first = small_first; ta.levels = g->levels; ta.surf = g->surf;
+    int blocks = 0;
+    for (int l = 0; l <= VCT_MAX_LEVELS; l++) ta.dil_start[l] = 0;
+    for (int l = 0; l < small_first; l++) {
+      const int D = (R >> l) + 1;
+      ta.dil_start[l] = blocks;
+      blocks += (D * D + 255) / 256;
     }
+    ta.dil_start[small_first] = blocks;
+    mip_tail_kernel<<<ta.n_high + 1 + blocks, 256, 0, s>>>(ta);
+    level = 6;
+    occ_done = true;
   }
   for (int l = level; l + 1 < g->levels; l++) {
     const int Ns = max(R >> l, 1), Nd = R >> (l + 1);
@@ -652,25 +738,10 @@ int launch_mipmap(vct_device* dev, vct_grid* g) {
     const int blocks = (int)grid_for(n);
     mip_generic_kernel<<<blocks, 256, 0, s>>>(l == 0 ? g->base : g->lvl[l], g->lvl[l + 1], Ns, Nd, l == 0, g->surf, l + 1);
   }
-  // occupancy masks for the cone tracer's zero-footprint skip
-  OccArgs oa;
-  oa.R = R; oa.first_level = occ_from_data;
-  for (int l = 0; l < VCT_MAX_LEVELS; l++) { oa.src[l] = l == 0 ? g->base : g->lvl[l]; oa.occ[l] = g->occ[l]; oa.docc[l] = g->docc[l]; }
-  if (occ_from_data == 0) {
-    occ_bits_kernel<<<grid_for((size_t)R * R * R, 256, 148 * 8), 256, 0, s>>>(oa);
-    oa.first_level = 1;
+  if (!occ_done) {   // occupancy masks for the cone tracer's zero-footprint skip
+    if (small_first < g->levels) occ_reduce_kernel<<<1, 1024, 0, s>>>(oa, small_first, g->levels);
+    occ_dilate_kernel<<<dim3((R + 1 + 127) / 128, R + 1, g->levels), 128, 0, s>>>(oa);
   }
-  {
-    int l = oa.first_level;
-    for (; l < g->levels && (R >> l) >= 64; l++) {   // large levels: one grid-wide launch each
-      int logN = 0;
-      while ((1 << logN) < (R >> l)) logN++;
-      const size_t n_words = (size_t)1 << (3 * logN - 5);
-      occ_reduce_level_kernel<<<grid_for(n_words), 256, 0, s>>>(g->occ[l - 1], g->occ[l], logN);
-    }
-    if (l < g->levels) occ_reduce_kernel<<<1, 1024, 0, s>>>(oa, l, g->levels);
-  }
-  occ_dilate_kernel<<<dim3((R + 1 + 127) / 128, R + 1, g->levels), 128, 0, s>>>(oa);
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;
 }

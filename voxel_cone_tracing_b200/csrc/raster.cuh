@@ -118,10 +118,15 @@ __device__ __forceinline__ float interp3(const float b[3], float a0, float a1, f
   return (b[0] * a0 + b[1] * a1) + b[2] * a2;  // compiled with -fmad=false: two roundings per term, like the oracle
 }
 
-// ---- block-local exclusive scan of per-triangle item counts (used inside the setup kernels) ----
-// Writes local[t] (exclusive prefix inside the 256-thread block) and block_total[blockIdx.x].
-__device__ __forceinline__ void block_scan_items(uint32_t count, uint32_t t, uint32_t n_tris, uint32_t* local, uint32_t* block_total) {
+// ---- exclusive scan of per-triangle item counts, inside the setup kernels ----
+// Every block writes local[t] (exclusive prefix inside the 256-thread block) and block_total[blockIdx.x]; the LAST block to
+// finish (ticket counter, reset for the next launch) turns the block totals into exclusive prefixes in place and stores the
+// grand total -- the work of a separate one-block kernel (4.5 us of launch + tail per rasteriser) folded into the setup kernel.
+__device__ __forceinline__ void block_scan_items(uint32_t count, uint32_t t, uint32_t n_tris, uint32_t* local, uint32_t* block_total, uint32_t* ticket,
+                                                 uint32_t* total) {
   __shared__ uint32_t warp_sums[kSetupThreads / 32];
+  __shared__ uint32_t carry_s, is_last;
+  constexpr int kWarps = kSetupThreads / 32;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   uint32_t v = count;
 #pragma unroll
@@ -132,55 +137,56 @@ __device__ __forceinline__ void block_scan_items(uint32_t count, uint32_t t, uin
   if (lane == 31) warp_sums[wid] = v;
   __syncthreads();
   if (wid == 0) {
-    uint32_t w = lane < kSetupThreads / 32 ? warp_sums[lane] : 0u;
+    uint32_t w = lane < kWarps ? warp_sums[lane] : 0u;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       uint32_t n = __shfl_up_sync(0xffffffffu, w, o);
       if (lane >= o) w += n;
     }
-    if (lane < kSetupThreads / 32) warp_sums[lane] = w;  // inclusive
+    if (lane < kWarps) warp_sums[lane] = w;  // inclusive
   }
   __syncthreads();
   uint32_t warp_off = wid ? warp_sums[wid - 1] : 0u;
   if (t < n_tris) local[t] = warp_off + v - count;
-  if (threadIdx.x == kSetupThreads - 1) block_total[blockIdx.x] = warp_off + v;
-}
-
-// one block: exclusive scan of block totals in place, grand total -> *total
-static __global__ void scan_block_totals_kernel(uint32_t* __restrict__ block_total, uint32_t n_blocks, uint32_t* __restrict__ total) {
-  __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry_s;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  if (threadIdx.x == 0) carry_s = 0;
+  if (threadIdx.x == kSetupThreads - 1) {
+    block_total[blockIdx.x] = warp_off + v;
+    __threadfence();                                       // the total is visible before the ticket is taken
+    is_last = atomicAdd(ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    carry_s = 0;
+  }
   __syncthreads();
-  for (uint32_t base = 0; base < n_blocks; base += blockDim.x) {
-    uint32_t i = base + threadIdx.x;
-    uint32_t c = i < n_blocks ? block_total[i] : 0u, v = c;
+  if (!is_last) return;
+  __threadfence();
+  const uint32_t n_blocks = gridDim.x;
+  for (uint32_t base = 0; base < n_blocks; base += kSetupThreads) {
+    const uint32_t i = base + threadIdx.x;
+    const uint32_t c = i < n_blocks ? __ldcg(block_total + i) : 0u;   // written by other blocks: read from L2
+    uint32_t x = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
-      uint32_t n = __shfl_up_sync(0xffffffffu, v, o);
-      if (lane >= o) v += n;
+      uint32_t n = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += n;
     }
-    if (lane == 31) warp_sums[wid] = v;
+    __syncthreads();                                       // warp_sums of the previous round / of the block scan are consumed
+    if (lane == 31) warp_sums[wid] = x;
     __syncthreads();
     if (wid == 0) {
-      uint32_t w = warp_sums[lane];
+      uint32_t w = lane < kWarps ? warp_sums[lane] : 0u;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         uint32_t n = __shfl_up_sync(0xffffffffu, w, o);
         if (lane >= o) w += n;
       }
-      warp_sums[lane] = w;
+      if (lane < kWarps) warp_sums[lane] = w;
     }
     __syncthreads();
-    uint32_t carry = carry_s;
-    uint32_t off = carry + (wid ? warp_sums[wid - 1] : 0u);
-    if (i < n_blocks) block_total[i] = off + v - c;
+    const uint32_t off = carry_s + (wid ? warp_sums[wid - 1] : 0u);
+    if (i < n_blocks) block_total[i] = off + x - c;
     __syncthreads();
-    if (threadIdx.x == blockDim.x - 1) carry_s = off + v;
+    if (threadIdx.x == kSetupThreads - 1) carry_s = off + x;
     __syncthreads();
   }
-  if (threadIdx.x == 0) *total = carry_s;
+  if (threadIdx.x == 0) { *total = carry_s; *ticket = 0u; }
 }
 
 // item index -> (triangle, tile).  item_block: exclusive prefix per setup block; item_local: exclusive

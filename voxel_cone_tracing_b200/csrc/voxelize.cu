@@ -5,7 +5,7 @@
 //   1. vox_setup_kernel   triangle-parallel: vertex transform (voxelize.vert:24-30), dominant-axis
 //                         selection (voxelize.geom:25-55), 1/256-pixel snapping, 8x8-pixel item count,
 //                         block-local scan
-//   2. scan_block_totals  one block: global item offsets (no host round trip)
+//   2. (inside 1.)        the last block to finish scans the block totals: global item offsets (no host round trip, no extra launch)
 //   3. vox_raster_kernel  one warp per 8x8 item: coverage, fragment shading (voxelize.frag:122-157),
 //                         append of a 32-byte fragment record to a per-voxel linked list whose head
 //                         lives in the grid word itself (atomicExch), occupied-voxel list
@@ -73,39 +73,75 @@ struct FragCtx {
   uint32_t* counters;
 };
 
-// One fragment candidate per lane (covered = the pixel centre is inside the triangle): shade it, find its voxel
-// (voxelize.frag:156-157: truncation, then the image bounds check; multi-GPU: the z-slab test) and append it to the voxel's list.
-// Must be called by all 32 lanes of the warp (warp-aggregated arena allocation).
-__device__ __forceinline__ void emit_fragment(const FragCtx& c, const VoxTri& v, uint32_t ti, int i, int j, const float b[3], bool covered, int lane) {
-  uint32_t voxel = 0;
-  float val[4];
-  if (covered) {
-    F3 pos;
-    shade_fragment(v, b, c.mats, c.L, c.cube_size, pos, val);
-    const float fR = (float)c.R;
-    int vx = (int)(fR * (0.5f * pos.x + 0.5f)), vy = (int)(fR * (0.5f * pos.y + 0.5f)), vz = (int)(fR * (0.5f * pos.z + 0.5f));
-    covered = vx >= 0 && vy >= 0 && vz >= 0 && vx < c.R && vy < c.R && vz < c.R && vz >= c.z0 && vz < c.z1;
-    voxel = ((uint32_t)vz * (uint32_t)c.R + (uint32_t)vy) * (uint32_t)c.R + (uint32_t)vx;
-  }
-  const uint32_t mask = __ballot_sync(0xffffffffu, covered);
-  if (!mask) return;
-  uint32_t basei = 0;
-  const int leader = __ffs(mask) - 1;
-  if (lane == leader) basei = atomicAdd(&c.counters[CNT_FRAGS], (uint32_t)__popc(mask));
-  basei = __shfl_sync(0xffffffffu, basei, leader);
-  if (covered) {
-    const uint32_t idx = basei + (uint32_t)__popc(mask & ((1u << lane) - 1u));
-    if (idx < c.frag_capacity) {
-      const uint32_t prev = atomicExch(&c.base[voxel], idx + 1u);
-      FragRec r;
-      r.next = prev;
-      r.voxel = voxel;
-      r.key = ((unsigned long long)ti << 24) | ((unsigned long long)j << 12) | (unsigned long long)i;
-      r.val[0] = val[0]; r.val[1] = val[1]; r.val[2] = val[2]; r.val[3] = val[3];
-      c.frags[idx] = r;
-      if (prev == 0u) c.occupied[atomicAdd(&c.counters[CNT_OCCUPIED], 1u)] = voxel;
+// Fragment candidates of a warp, K per lane (covered = the pixel centre is inside the triangle): shade them, find their voxels
+// (voxelize.frag:156-157: truncation, then the image bounds check; multi-GPU: the z-slab test) and append them to the voxels' lists.
+// Must be called by all 32 lanes of the warp.  The arena slots of all K*32 candidates are reserved with ONE atomicAdd and the
+// newly occupied voxels are appended to the occupied list with ONE more: both counters are single addresses, and one atomic
+// per fragment group (54 k same-address atomics per frame at 256^3) was what the raster kernel spent its time on.
+template <int K>
+__device__ __forceinline__ void emit_fragments(const FragCtx& c, const VoxTri& v, uint32_t ti, const int (&pi)[K], const int (&pj)[K], const float (&pb)[K][3],
+                                               bool (&covered)[K], int lane) {
+  uint32_t voxel[K];
+  float val[K][4];
+  uint32_t mask[K];
+  uint32_t total = 0;
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    voxel[k] = 0;
+    if (covered[k]) {
+      F3 pos;
+      shade_fragment(v, pb[k], c.mats, c.L, c.cube_size, pos, val[k]);
+      const float fR = (float)c.R;
+      int vx = (int)(fR * (0.5f * pos.x + 0.5f)), vy = (int)(fR * (0.5f * pos.y + 0.5f)), vz = (int)(fR * (0.5f * pos.z + 0.5f));
+      covered[k] = vx >= 0 && vy >= 0 && vz >= 0 && vx < c.R && vy < c.R && vz < c.R && vz >= c.z0 && vz < c.z1;
+      voxel[k] = ((uint32_t)vz * (uint32_t)c.R + (uint32_t)vy) * (uint32_t)c.R + (uint32_t)vx;
     }
+    mask[k] = __ballot_sync(0xffffffffu, covered[k]);
+    total += (uint32_t)__popc(mask[k]);
   }
+  if (!total) return;
+  uint32_t basei = 0;
+  if (lane == 0) basei = atomicAdd(&c.counters[CNT_FRAGS], total);
+  basei = __shfl_sync(0xffffffffu, basei, 0);
+  bool fresh[K];
+  uint32_t n_fresh = 0, fmask[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    fresh[k] = false;
+    if (covered[k]) {
+      const uint32_t idx = basei + (uint32_t)__popc(mask[k] & ((1u << lane) - 1u));
+      if (idx < c.frag_capacity) {
+        const uint32_t prev = atomicExch(&c.base[voxel[k]], idx + 1u);
+        FragRec r;
+        r.next = prev;
+        r.voxel = voxel[k];
+        r.key = ((unsigned long long)ti << 24) | ((unsigned long long)pj[k] << 12) | (unsigned long long)pi[k];
+        r.val[0] = val[k][0]; r.val[1] = val[k][1]; r.val[2] = val[k][2]; r.val[3] = val[k][3];
+        c.frags[idx] = r;
+        fresh[k] = prev == 0u;
+      }
+    }
+    basei += (uint32_t)__popc(mask[k]);
+    fmask[k] = __ballot_sync(0xffffffffu, fresh[k]);
+    n_fresh += (uint32_t)__popc(fmask[k]);
+  }
+  if (!n_fresh) return;
+  uint32_t obase = 0;
+  if (lane == 0) obase = atomicAdd(&c.counters[CNT_OCCUPIED], n_fresh);
+  obase = __shfl_sync(0xffffffffu, obase, 0);
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    if (fresh[k]) c.occupied[obase + (uint32_t)__popc(fmask[k] & ((1u << lane) - 1u))] = voxel[k];
+    obase += (uint32_t)__popc(fmask[k]);
+  }
+}
+
+// one candidate per lane
+__device__ __forceinline__ void emit_fragment(const FragCtx& c, const VoxTri& v, uint32_t ti, int i, int j, const float b[3], bool covered, int lane) {
+  const int pi[1] = {i}, pj[1] = {j};
+  const float pb[1][3] = {{b[0], b[1], b[2]}};
+  bool cov[1] = {covered};
+  emit_fragments<1>(c, v, ti, pi, pj, pb, cov, lane);
 }
 
 // triangles whose bounding box holds at most this many pixel centres are rasterised inside the setup kernel (one lane
@@ -116,7 +152,7 @@ constexpr int kSmallPixels = 36;
 __global__ void __launch_bounds__(kSetupThreads)
 vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ draws,
                  uint32_t n_draws, uint32_t n_tris, float cube_size, int R, int z0, int z1, VoxTri* __restrict__ out, uint32_t* __restrict__ item_local,
-                 uint32_t* __restrict__ item_block, const FragCtx ctx, int small_limit) {
+                 uint32_t* __restrict__ item_block, const FragCtx ctx, int small_limit, uint32_t* scan_ticket, uint32_t* scan_total) {
   uint32_t t = blockIdx.x * kSetupThreads + threadIdx.x;
   uint32_t count = 0;
   VoxTri v;
@@ -184,7 +220,7 @@ vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
   }
   if (small) count = 0;
   else if (t < n_tris) out[t] = v;   // only triangles that become work items are read again
-  block_scan_items(count, t, n_tris, item_local, item_block);
+  block_scan_items(count, t, n_tris, item_local, item_block, scan_ticket, scan_total);
 }
 
 __global__ void __launch_bounds__(256)
@@ -204,14 +240,16 @@ vox_raster_kernel(const VoxTri* __restrict__ tris, uint32_t n_tris, const uint32
     const int tx = (rt.imin >> 3) + (int)(rank % (uint32_t)tiles_x), ty = (rt.jmin >> 3) + (int)(rank / (uint32_t)tiles_x);
     EdgeBlock eb;
     edge_block_setup(rt, tx * kTile, ty * kTile, eb);
+    int pi[2], pj[2];
+    float pb[2][3];
+    bool covered[2];
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
+    for (int h = 0; h < 2; h++) {   // the 64 pixels of the item: two per lane
       const int p = lane + 32 * h;
-      const int i = tx * kTile + (p & 7), j = ty * kTile + (p >> 3);
-      float b[3];
-      const bool covered = i >= rt.imin && i <= rt.imax && j >= rt.jmin && j <= rt.jmax && edge_block_sample(eb, p & 7, p >> 3, b);
-      emit_fragment(ctx, v, ti, i, j, b, covered, lane);
+      pi[h] = tx * kTile + (p & 7); pj[h] = ty * kTile + (p >> 3);
+      covered[h] = pi[h] >= rt.imin && pi[h] <= rt.imax && pj[h] >= rt.jmin && pj[h] <= rt.jmax && edge_block_sample(eb, p & 7, p >> 3, pb[h]);
     }
+    emit_fragments<2>(ctx, v, ti, pi, pj, pb, covered, lane);
   }
 }
 
@@ -336,8 +374,8 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
     ctx.mats = sc->mats; ctx.L = sc->lights; ctx.cube_size = sc->cube_size; ctx.R = g->R; ctx.z0 = z0; ctx.z1 = z1;
     ctx.base = g->base; ctx.frags = dev->frags; ctx.frag_capacity = (uint32_t)dev->frag_capacity; ctx.occupied = dev->occupied; ctx.counters = dev->counters;
     vox_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, sc->cube_size, g->R, z0, z1, tris,
-                                                          dev->rs[0].item_local, dev->rs[0].item_block, ctx, sc->n_tris >= kSmallPathMinTris ? kSmallPixels : 0);
-    scan_block_totals_kernel<<<1, 1024, 0, s>>>(dev->rs[0].item_block, n_blocks, dev->counters + CNT_ITEMS);
+                                                          dev->rs[0].item_local, dev->rs[0].item_block, ctx, sc->n_tris >= kSmallPathMinTris ? kSmallPixels : 0,
+                                                          dev->counters + CNT_TICKET_VOX, dev->counters + CNT_ITEMS);
     vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->rs[0].item_local, dev->rs[0].item_block, n_blocks, ctx);
   }
   vox_resolve_kernel<<<sms * 4, 128, 0, s>>>(g->base, dev->frags, dev->occupied, dev->counters, (uint32_t)dev->frag_capacity, pv);
