@@ -319,23 +319,26 @@ def test_frame_config2_cornell_256_1080p(sampler):
 
 
 def test_cone_kernel_variants_agree(monkeypatch):
-    """the production march (one-level fetches through the nearest-mip texture objects, VCT_CONE_VARIANT=2) against the march
-    that blends two levels in every fetch (1) and the literal loop (0): same frame within 1/255, and each inside the oracle gate"""
+    """the production march (3: one-level fetches through the nearest-mip texture object, all diffuse cones of a tile in one warp)
+    against one warp per cone slot (2), the march that blends two levels in every fetch (1) and the literal loop (0): same frame
+    within 1/255, and each inside the oracle gate; both samplers"""
     sc = S.cornell_scene(with_suzanne=True)
     R, W, H = 128, 480, 270
     view, proj = S.reference_camera(W / H)
     ref = orc.render_frame(sc, view, proj, R, W, H, orc.default_params(), 7)
     p = capi.Pipeline(sc, R, W, H)
-    prm = capi.default_params(sampler=capi.SAMPLER_TEX)
-    frames = {}
-    for v in ("2", "1", "0"):
-        monkeypatch.setenv("VCT_CONE_VARIANT", v)
-        p.render_frame(view, proj, prm)
-        frames[v] = p.target.frame().copy()
-        _check_frame(frames[v], ref)
+    for sampler in SAMPLERS:
+        prm = capi.default_params(sampler=sampler)
+        frames = {}
+        for v in ("3", "2", "1", "0"):
+            monkeypatch.setenv("VCT_CONE_VARIANT", v)
+            p.render_frame(view, proj, prm)
+            frames[v] = p.target.frame().copy()
+            _check_frame(frames[v], ref)
+        assert np.array_equal(frames["3"], frames["2"]) or max_abs(frames["3"], frames["2"]) <= 1
+        assert max_abs(frames["2"], frames["1"]) <= 1
+        assert max_abs(frames["1"], frames["0"]) <= 1
     p.close()
-    assert max_abs(frames["2"], frames["1"]) <= 1
-    assert max_abs(frames["1"], frames["0"]) <= 1
 
 
 def test_async_readback_equals_blocking_readback():
@@ -360,6 +363,57 @@ def test_async_readback_equals_blocking_readback():
         p.render_frame(view, proj)
         assert np.array_equal(p.target.frame(), host[i]), f"frame {i}"
     assert not np.array_equal(host[0], host[1])
+    p.close()
+
+
+def test_sparse_frame_sequence_matches_fresh_builds():
+    """Frame-to-frame bookkeeping (sparse clear of the occupied list, mip build that skips untouched tiles): a moving object, an
+    emptied scene, a grid overwritten behind the voxelizer's back (upload) and a slab-wise voxelization, all on ONE grid -- level 0,
+    the whole pyramid (records + arrays) and the occupancy masks must equal fresh oracle builds after every step"""
+    R, W, H, levels = 64, 64, 48, 7
+    view, proj = S.reference_camera(W / H)
+    p = capi.Pipeline(S.cornell_scene(with_suzanne=True), R, W, H, levels)
+    rng = np.random.default_rng(5)
+
+    def check(base_exp):
+        assert np.array_equal(p.grid.download(0), base_exp)
+        pyr = orc.mipmap(base_exp, levels)
+        assert_pyramid_equal(p.grid, pyr)
+        for l in range(levels):
+            occ, dil = _expected_occupancy(pyr, l)
+            assert np.array_equal(p.grid.occupancy(l, False), occ) and np.array_equal(p.grid.occupancy(l, True), dil), f"occupancy level {l}"
+
+    for step, theta in enumerate((0.0, 0.9, 1.8, 0.9)):
+        sc = S.cornell_scene(with_suzanne=True, theta=theta)
+        p.scene.upload(sc)
+        p.render_frame(view, proj)                      # clear (sparse from the second frame on) + voxelize + mip
+        check(orc.voxelize(sc, R)[0])
+    # the Cornell box alone: Suzanne's tiles must go back to zero
+    sc = S.cornell_scene()
+    p.scene.upload(sc)
+    p.render_frame(view, proj)
+    check(orc.voxelize(sc, R)[0])
+    # level 0 written behind the voxelizer's back: dense paths
+    base = rng.integers(0, 2 ** 32, (R, R, R), dtype=np.uint64).astype(np.uint32)
+    base[rng.random((R, R, R)) >= 0.01] = 0
+    p.grid.upload_base(base)
+    p.mipmap()
+    check(base)
+    # back to voxelization: dense clear, then sparse again
+    for theta in (0.3, 1.2):
+        sc = S.cornell_scene(with_suzanne=True, theta=theta)
+        p.scene.upload(sc)
+        p.render_frame(view, proj)
+        check(orc.voxelize(sc, R)[0])
+    # two slabs voxelized one after the other without a clear in between, then a clear + a full voxelization
+    p.clear()
+    p.voxelize(0, R // 2); p.voxelize(R // 2, R); p.mipmap()
+    check(orc.voxelize(sc, R)[0])
+    p.clear(); p.clear()
+    p.mipmap()
+    check(np.zeros((R, R, R), np.uint32))
+    p.voxelize(); p.mipmap()
+    check(orc.voxelize(sc, R)[0])
     p.close()
 
 

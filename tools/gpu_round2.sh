@@ -3,11 +3,11 @@
 mkdir -p gpurun_out
 O=gpurun_out
 ( time timeout 1200 python -m pytest tests -m gpu -x -q ) > $O/pytest_gpu.log 2>&1; tail -5 $O/pytest_gpu.log
-for v in 1 2; do VCT_CONE_VARIANT=$v timeout 300 python tools/cone_variants.py > $O/variant_$v.txt 2>&1; cat $O/variant_$v.txt; done
+for v in 2 3; do VCT_CONE_VARIANT=$v timeout 300 python tools/cone_variants.py > $O/variant_$v.txt 2>&1; cat $O/variant_$v.txt; done
 timeout 600 python bench.py --steps 200 --warmup 10 > $O/bench.json 2> $O/bench.err; cut -c1-600 $O/bench.json; tail -3 $O/bench.err
 timeout 300 python tools/quick_time.py > $O/quick_time.txt 2>&1; cat $O/quick_time.txt
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/launches.csv python bench.py --steps 5 --warmup 3 --no-cpu > $O/launch_bench.log 2>&1
 python tools/launch_summary.py $O/launches.csv > $O/launch_summary.txt 2>&1; cat $O/launch_summary.txt
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:cone_kernel -s 3 -c 1 -f -o $O/cone_full python bench.py --steps 1 --warmup 3 --no-cpu > $O/ncu_cone.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:"mip_|occ_" -s 12 -c 4 -f -o $O/mip_full python bench.py --steps 1 --warmup 3 --no-cpu > $O/ncu_mip.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:"mip_" -s 6 -c 2 -f -o $O/mip_full python bench.py --steps 1 --warmup 3 --no-cpu > $O/ncu_mip.log 2>&1
 ls -la $O

@@ -242,6 +242,11 @@ int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) {
     g->bytes += n * 24;
   }
   // occupancy bit masks (plain + 2x2x2-dilated) per level, written by the mip stage
+  if (levels >= 4 && R % 32 == 0) {   // the fused mip path: one flag per 32x8x8 tile
+    const size_t n_tiles = (size_t)(R / 32) * (R / 8) * (R / 8);
+    if (e == cudaSuccess) e = cudaMalloc(&g->tile_touched, n_tiles);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->tile_touched, 0, n_tiles, dev->stream);
+  }
   size_t docc_total = 0;   // the dilated bits of all levels share one allocation (256-byte aligned parts)
   for (int l = 0; l < levels; l++) {
     g->docc_off[l] = (uint32_t)docc_total;
@@ -333,7 +338,8 @@ int vct_grid_destroy(vct_grid_t* g) {
   if (!g) return VCT_OK;
   if (g->dev->peer_grid == g) vct_peer_disconnect(g->dev);
   cudaStreamSynchronize(g->dev->stream);
-  cudaFree(g->base_buf[0]); cudaFree(g->base_buf[1]); cudaFree(g->tile_zero);
+  cudaFree(g->base_buf[0]); cudaFree(g->base_buf[1]); cudaFree(g->tile_zero); cudaFree(g->tile_touched);
+  if (g->dev->vox_owner == g) g->dev->vox_owner = nullptr;
   for (int l = 0; l < VCT_MAX_LEVELS; l++) { cudaFree(g->lvl[l]); cudaFree(g->occ[l]); }
   cudaFree(g->docc_all);
   if (g->tex_lin) cudaDestroyTextureObject(g->tex_lin);
@@ -346,12 +352,25 @@ int vct_grid_destroy(vct_grid_t* g) {
 
 int vct_grid_clear(vct_grid_t* g) {
   VCT_REQUIRE(g, "grid is null");
-  VCT_CUDA(cudaMemsetAsync(g->base, 0, (size_t)g->R * g->R * g->R * 4, g->dev->stream));
+  vct_device* dev = g->dev;
+  if (g->base_zero && !g->external) return VCT_OK;                       // nothing has been written since the last clear
+  if (g->sparse_clear_ok && !g->external && dev->vox_owner == g) {
+    // the non-zero words are exactly the occupied list of the last voxelization: zero those (and their tile flags)
+    int rc = launch_sparse_clear(dev, g);
+    if (rc) return rc;
+  } else {
+    VCT_CUDA(cudaMemsetAsync(g->base, 0, (size_t)g->R * g->R * g->R * 4, dev->stream));
+    if (g->tile_touched) VCT_CUDA(cudaMemsetAsync(g->tile_touched, 0, (size_t)(g->R / 32) * (g->R / 8) * (g->R / 8), dev->stream));
+  }
+  g->sparse_clear_ok = false;
+  g->flags_valid = g->tile_touched != nullptr && !g->external;
+  g->base_zero = !g->external;
   return VCT_OK;
 }
 
 int vct_grid_upload_base(vct_grid_t* g, const uint32_t* host) {
   VCT_REQUIRE(g && host, "null argument");
+  g->untrack();
   VCT_CUDA(cudaMemcpyAsync(g->base, host, (size_t)g->R * g->R * g->R * 4, cudaMemcpyHostToDevice, g->dev->stream));
   VCT_CUDA(cudaStreamSynchronize(g->dev->stream));
   return VCT_OK;
@@ -406,7 +425,12 @@ int vct_grid_download_occupancy(vct_grid_t* g, int level, int dilated, uint32_t*
   return VCT_OK;
 }
 
-void* vct_grid_base_device_ptr(vct_grid_t* g) { return g ? (void*)g->base : nullptr; }
+void* vct_grid_base_device_ptr(vct_grid_t* g) {
+  if (!g) return nullptr;
+  g->external = true;   // the caller may write level 0 (NCCL all-gather of the z-slabs): no sparse bookkeeping from here on
+  g->untrack();
+  return (void*)g->base;
+}
 size_t vct_grid_bytes(const vct_grid_t* g) { return g ? g->bytes : 0; }
 
 // ------------------------------------------------------------------ target
@@ -513,6 +537,7 @@ int vct_voxelize_reserve(vct_device_t* dev, uint64_t max_fragments) {
   VCT_CUDA(cudaStreamSynchronize(dev->stream));
   cudaFree(dev->frags); cudaFree(dev->occupied);
   dev->frags = nullptr; dev->occupied = nullptr; dev->frag_capacity = 0;
+  dev->vox_owner = nullptr;   // the occupied list is gone: the next clear is dense
   VCT_CUDA(cudaMalloc(&dev->frags, max_fragments * sizeof(FragRec)));
   VCT_CUDA(cudaMalloc(&dev->occupied, max_fragments * sizeof(uint32_t)));
   dev->frag_capacity = max_fragments;

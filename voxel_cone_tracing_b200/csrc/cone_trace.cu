@@ -61,6 +61,7 @@ struct TraceArgs {
   vct_trace_params_t prm;
   unsigned long long* counts;  // [4] diffuse, shadow, specular, refraction (+[4] shaded pixels)
   int n_diffuse, n_slots;
+  int grouped;                 // cone_out layout: 0 = [slot][pixel]; 1 = [job][pixel] with job 0 = SUM of the diffuse cones, 1 specular, 2 refraction, 3 + i shadow of light i
   const uint32_t* tile_list;   // live 8x4 tiles (tile_y * tiles_x + tile_x), built by tile_list_kernel
   uint32_t* tile_count;
   float4* cone_out;            // [slot][pixel] cone results (rgba)
@@ -536,6 +537,21 @@ cone_kernel(const TraceArgs a) {
 }
 
 
+// direction of diffuse cone `slot` (voxel_cone_tracing.frag:153-165) from the tangent frame
+__device__ __forceinline__ F3 diffuse_dir(F3 normal, F3 o1, F3 o2, int slot) {
+  switch (slot) {
+    case 0: return normal;
+    case 1: return mix(normal, o1, 0.5f);
+    case 2: return mix(normal, -o1, 0.5f);
+    case 3: return mix(normal, o2, 0.5f);
+    case 4: return mix(normal, -o2, 0.5f);
+    case 5: return mix(normal, (o1 + o2) * 0.5f, 0.5f);
+    case 6: return mix(normal, -((o1 + o2) * 0.5f), 0.5f);
+    case 7: return mix(normal, (o1 - o2) * 0.5f, 0.5f);
+    default: return mix(normal, -((o1 - o2) * 0.5f), 0.5f);
+  }
+}
+
 // cone parameters of one (pixel, slot): direction, aperture, max distance; false = this slot traces nothing for the pixel
 __device__ __forceinline__ bool cone_setup(const TraceArgs& a, const Pixel& p, int slot, F3& d, float& aperture, float& max_dist) {
   const int nd = a.n_diffuse;
@@ -548,17 +564,7 @@ __device__ __forceinline__ bool cone_setup(const TraceArgs& a, const Pixel& p, i
     if (!a.prm.enable_diffuse) return false;
     const F3 o1 = tangent_fast(normal);   // (the reference normalises it twice: a no-op up to an ulp)
     const F3 o2 = normalize_fast(cross(o1, normal));
-    switch (slot) {
-      case 0: d = normal; break;
-      case 1: d = mix(normal, o1, 0.5f); break;
-      case 2: d = mix(normal, -o1, 0.5f); break;
-      case 3: d = mix(normal, o2, 0.5f); break;
-      case 4: d = mix(normal, -o2, 0.5f); break;
-      case 5: d = mix(normal, (o1 + o2) * 0.5f, 0.5f); break;
-      case 6: d = mix(normal, -((o1 + o2) * 0.5f), 0.5f); break;
-      case 7: d = mix(normal, (o1 - o2) * 0.5f, 0.5f); break;
-      default: d = mix(normal, -((o1 - o2) * 0.5f), 0.5f); break;
-    }
+    d = diffuse_dir(normal, o1, o2, slot);
     return true;
   }
   const F3 cam = f3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]);
@@ -590,25 +596,52 @@ __device__ __forceinline__ bool cone_setup(const TraceArgs& a, const Pixel& p, i
   return true;
 }
 
-template <bool TEX, bool SPLIT, int MIN_CTAS>
+// GROUP: one warp marches ALL diffuse cones of its tile one after the other and stores their sum (added in slot order, as
+// trace_diffuse does): the G-buffer fetch and the tangent frame are paid once instead of nine times (12 % of the kernel's
+// instructions) and the cone-result buffer shrinks from 12 to 4 float4 per pixel (142 -> 47 MB written here and read by shade_kernel
+// at 1080p).  The long job (blockIdx.y = 0) is scheduled first.
+template <bool TEX, bool SPLIT, int MIN_CTAS, bool GROUP>
 __global__ void __launch_bounds__(32 * kConeWarps, MIN_CTAS)
 cone_kernel_fast(const TraceArgs a) {
   const int lane = threadIdx.x & 31;
   const uint32_t t = blockIdx.x * kConeWarps + (threadIdx.x >> 5);
   if (t >= *a.tile_count) return;
-  // long cones first: blockIdx.y = 0 is the last slot (shadow cones, up to ~5x more steps than diffuse)
-  const int slot = a.n_slots - 1 - (int)blockIdx.y;
   const uint32_t tile = a.tile_list[t];
   const int tiles_x = (a.W + 7) / 8;
   const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
   const Pixel p = load_pixel(a, tile_x * 8 + (lane & 7), tile_y * 4 + (lane >> 3));
   if (!p.live) return;
-  F3 d = f3(0.f, 0.f, 1.f);
-  float aperture = kTan22_5, max_dist = 0.f;
-  const bool on = cone_setup(a, p, slot, d, aperture, max_dist);
   float r[4];
-  trace_cone_fast<TEX, SPLIT>(a.grid, on, p.pos, d, aperture, max_dist, r);
-  a.cone_out[(size_t)slot * a.npix + p.pix] = make_float4(r[0], r[1], r[2], r[3]);
+  if (GROUP) {
+    const int job = (int)blockIdx.y;
+    if (job == 0) {
+      float sum[3] = {0.f, 0.f, 0.f};
+      if (a.prm.enable_diffuse) {
+        const F3 o1 = tangent_fast(p.normal);
+        const F3 o2 = normalize_fast(cross(o1, p.normal));
+#pragma unroll 1
+        for (int i = 0; i < a.n_diffuse; i++) {
+          trace_cone_fast<TEX, SPLIT>(a.grid, true, p.pos, diffuse_dir(p.normal, o1, o2, i), kTan22_5, kMaxDistance, r);
+          sum[0] = sum[0] + r[0]; sum[1] = sum[1] + r[1]; sum[2] = sum[2] + r[2];
+        }
+      }
+      a.cone_out[p.pix] = make_float4(sum[0], sum[1], sum[2], 0.f);
+      return;
+    }
+    F3 d = f3(0.f, 0.f, 1.f);
+    float aperture = kTan22_5, max_dist = 0.f;
+    const bool on = cone_setup(a, p, a.n_diffuse + job - 1, d, aperture, max_dist);
+    trace_cone_fast<TEX, SPLIT>(a.grid, on, p.pos, d, aperture, max_dist, r);
+    a.cone_out[(size_t)job * a.npix + p.pix] = make_float4(r[0], r[1], r[2], r[3]);
+  } else {
+    // long cones first: blockIdx.y = 0 is the last slot (shadow cones, up to ~5x more steps than diffuse)
+    const int slot = a.n_slots - 1 - (int)blockIdx.y;
+    F3 d = f3(0.f, 0.f, 1.f);
+    float aperture = kTan22_5, max_dist = 0.f;
+    const bool on = cone_setup(a, p, slot, d, aperture, max_dist);
+    trace_cone_fast<TEX, SPLIT>(a.grid, on, p.pos, d, aperture, max_dist, r);
+    a.cone_out[(size_t)slot * a.npix + p.pix] = make_float4(r[0], r[1], r[2], r[3]);
+  }
 }
 
 // main() (voxel_cone_tracing.frag:246-275) for one pixel
@@ -649,9 +682,14 @@ __device__ void shade_pixel(const TraceArgs& a, int tile_x, int tile_y, int lane
   F3 fdiff = f3(0.f, 0.f, 0.f), fdir = f3(0.f, 0.f, 0.f), fspec = f3(0.f, 0.f, 0.f);
   if (a.prm.enable_diffuse) {
     F3 s = f3(0.f, 0.f, 0.f);
-    for (int i = 0; i < nd; i++) {
-      const float4 c = a.cone_out[(size_t)i * a.npix + p.pix];
-      s = s + f3(c.x, c.y, c.z);
+    if (a.grouped) {
+      const float4 c = a.cone_out[p.pix];   // the cone kernel already added the nd cones, in the same order
+      s = f3(c.x, c.y, c.z);
+    } else {
+      for (int i = 0; i < nd; i++) {
+        const float4 c = a.cone_out[(size_t)i * a.npix + p.pix];
+        s = s + f3(c.x, c.y, c.z);
+      }
     }
     fdiff = kd * (s * (1.0f / (float)nd));
   }
@@ -668,7 +706,7 @@ __device__ void shade_pixel(const TraceArgs& a, int tile_x, int tile_y, int lane
       const float att = 1.0f / (1.0f + d * d);
       const F3 light_color = f3(L.color[0], L.color[1], L.color[2]) * (att * cos_surf) * L.intensity;
       float shadow_level = 1.0f;
-      if (a.prm.enable_shadow) shadow_level = fmaxf(0.0f, 1.0f - a.cone_out[(size_t)(nd + 2 + i) * a.npix + p.pix].w);
+      if (a.prm.enable_shadow) shadow_level = fmaxf(0.0f, 1.0f - a.cone_out[(size_t)((a.grouped ? 3 : nd + 2) + i) * a.npix + p.pix].w);
       const float lambertian = fmaxf(dot(ld, normal), 0.0f);
       float refract_angle = 0.0f;
       if (m->dissolve <= 0.1f) {
@@ -685,13 +723,13 @@ __device__ void shade_pixel(const TraceArgs& a, int tile_x, int tile_y, int lane
     fdir = result + f3(clamp01(m->emission[0]), clamp01(m->emission[1]), clamp01(m->emission[2]));
   }
   if (a.prm.enable_specular) {
-    const float4 c = a.cone_out[(size_t)nd * a.npix + p.pix];
+    const float4 c = a.cone_out[(size_t)(a.grouped ? 1 : nd) * a.npix + p.pix];
     fspec = ks * f3(c.x, c.y, c.z);
   }
   F3 rgb = (fspec + fdiff) + fdir;
   const bool transmissive = m->illum == 4 || m->illum == 6 || m->illum == 7 || m->illum == 9;
   if (transmissive && a.prm.enable_specular) {
-    const float4 c = a.cone_out[(size_t)(nd + 1) * a.npix + p.pix];
+    const float4 c = a.cone_out[(size_t)(a.grouped ? 2 : nd + 1) * a.npix + p.pix];
     const F3 rr = f3(m->transmittance[0], m->transmittance[1], m->transmittance[2]) * f3(c.x, c.y, c.z);
     rgb = mix(rr, rgb, m->dissolve);
   }
@@ -756,6 +794,7 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
   a.counts = (unsigned long long*)(dev->counters + 16);
   a.n_diffuse = p->n_diffuse_cones == 5 ? 5 : 9;
   a.n_slots = a.n_diffuse + 2 + sc->lights.n;
+  a.grouped = 0;
   a.npix = (size_t)t->W * t->H;
   const int n_tiles = ((t->W + 7) / 8) * ((t->H + 3) / 4);
   // cone result buffer [slot][pixel] and the live-tile list, grown on demand
@@ -779,23 +818,39 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
     VCT_CUDA(cudaMemsetAsync(t->tile_list, 0, sizeof(uint32_t), s));
     tile_list_kernel<<<(n_tiles + 8 * kTilesPerWarp - 1) / (8 * kTilesPerWarp), 256, 0, s>>>(a, t->tile_list + 1, t->tile_list);
     const dim3 grid((n_tiles + kConeWarps - 1) / kConeWarps, a.n_slots);
+    const dim3 grid_jobs(grid.x, 3 + sc->lights.n);   // GROUP: the diffuse cones are one job
     const bool tex = p->sampler == VCT_SAMPLER_TEX && g->levels >= 2;
+    // 3 = production (one-level fetches through the nearest-mip texture object, all diffuse cones of a tile in one warp), 2 = one warp per
+    // cone slot, 1 = every fetch blends two levels, 0 = literal loop; read per call so that tests can compare them
+    const char* ev = getenv("VCT_CONE_VARIANT");
+    int variant = ev ? atoi(ev) : 3;
+    // grouping makes the diffuse warps nine times longer: with few tiles per GPU (small frames, many ranks) the tail of the launch costs
+    // more than the shared set-up saves (512x512: 200 -> 224 us; 1920x1080: 887 -> 863 us)
+    // (and the fp32 software sampler, 72 registers, spills in the grouped form: 3.7 -> 4.6 ms at 1080p)
+    if (!ev && (n_tiles / a.prm.tile_nranks < 32768 || !tex)) variant = 2;
+    a.grouped = (!count_samples && variant >= 3) ? 1 : 0;
     VCT_CUDA(cudaEventRecord(dev->ev[6], s));
     if (count_samples) {
       VCT_CUDA(cudaMemsetAsync(dev->counters + 16, 0, 8 * sizeof(unsigned long long), s));
       cone_kernel<true, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
+    } else if (variant == 0) {
+      if (tex) cone_kernel<false, true><<<grid, 32 * kConeWarps, 0, s>>>(a);
+      else cone_kernel<false, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
+    } else if (variant == 1) {
+      if (tex) cone_kernel_fast<true, false, 9, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
+      else cone_kernel_fast<false, false, 7, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
+    } else if (variant == 2) {
+      if (tex) cone_kernel_fast<true, true, 10, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
+      else cone_kernel_fast<false, false, 7, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
+    } else if (variant == 5) {
+      if (tex) cone_kernel_fast<true, true, 8, true><<<grid_jobs, 32 * kConeWarps, 0, s>>>(a);
+      else cone_kernel_fast<false, false, 7, true><<<grid_jobs, 32 * kConeWarps, 0, s>>>(a);
+    } else if (variant == 4) {
+      if (tex) cone_kernel_fast<true, true, 9, true><<<grid_jobs, 32 * kConeWarps, 0, s>>>(a);
+      else cone_kernel_fast<false, false, 7, true><<<grid_jobs, 32 * kConeWarps, 0, s>>>(a);
     } else {
-      // 2 = production (one-level fetches through the nearest-mip texture objects), 1 = every fetch blends two levels, 0 = literal loop; read per call so that tests can compare them
-      const char* ev = getenv("VCT_CONE_VARIANT");
-      const int variant = ev ? atoi(ev) : 2;
-      if (variant == 0) {
-        if (tex) cone_kernel<false, true><<<grid, 32 * kConeWarps, 0, s>>>(a);
-        else cone_kernel<false, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
-      } else {
-        if (tex && variant == 1) cone_kernel_fast<true, false, 9><<<grid, 32 * kConeWarps, 0, s>>>(a);
-        else if (tex) cone_kernel_fast<true, true, 10><<<grid, 32 * kConeWarps, 0, s>>>(a);
-        else cone_kernel_fast<false, false, 7><<<grid, 32 * kConeWarps, 0, s>>>(a);
-      }
+      if (tex) cone_kernel_fast<true, true, 10, true><<<grid_jobs, 32 * kConeWarps, 0, s>>>(a);
+      else cone_kernel_fast<false, false, 7, true><<<grid_jobs, 32 * kConeWarps, 0, s>>>(a);
     }
     VCT_CUDA(cudaEventRecord(dev->ev[7], s));
   }

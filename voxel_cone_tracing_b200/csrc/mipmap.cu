@@ -125,6 +125,7 @@ __global__ void mip_generic_kernel(const uint32_t* __restrict__ src, uint32_t* _
 // kLowStages-1 tiles per CTA are in flight while one is being reduced -- the HBM stream never waits for the arithmetic.
 constexpr int TX = 32, TY = 8, TZ = 8;
 constexpr int kLowStages = 4;
+constexpr int kLowListMax = 1024;              // tiles of one CTA examined per round
 constexpr uint32_t kLowTileBytes = TX * TY * TZ * 4;
 
 struct LowArgs {
@@ -132,6 +133,7 @@ struct LowArgs {
   uint32_t* occ0; uint16_t* occ1; uint8_t* occ2;
   int R, n_tiles, log_tiles_x, log_tiles_y;
   uint8_t* tile_zero;   // per tile: 1 = every output of this tile (levels 1-3, both copies, occupancy bits) is known to be zero
+  const uint8_t* touched;   // per tile: the voxelizer wrote into it since the last clear (nullptr: unknown, every tile is read)
   SurfSet surf;
 };
 
@@ -141,7 +143,8 @@ struct LowSmem {
   uint32_t s2[TZ / 4][TY / 4][TX / 4][6];      // 768 B
   uint32_t s3[TX / 8][6];                      // 96 B
   uint32_t occ_l1[8];                          // per warp of the level-1 step: 8 bits = (x pairs) of its two rows with a non-zero voxel below
-  uint32_t zero_flag[kLowStages];              // tile_zero[] of the tile in each stage, prefetched with the tile
+  uint32_t list[kLowListMax];                  // the tiles this CTA has to read (bit 31: tile_zero[] of the tile)
+  uint32_t list_n;
   unsigned long long full[kLowStages];         // mbarriers: "tile landed"
 };
 
@@ -324,6 +327,10 @@ __device__ __forceinline__ void low_process_tile(const uint32_t (&s0)[TZ][TY][TX
   low_store_level<TX / 8, 1, 1>(&s3[0][0], a.l3, a.surf, 3, N3, x0 / 8, y0 / 8, z0 / 8, t);
 }
 
+// The tiles of a CTA are blockIdx.x, blockIdx.x + gridDim.x, ...  In rounds of kLowListMax candidates the CTA first compacts the
+// tiles it actually has to READ -- all of them when nothing is known about level 0; with the voxelizer's tile flags only the
+// touched tiles and those whose outputs of the previous build are not zero yet (< 5 % of the tiles of the Cornell scene: the
+// level is neither read nor written elsewhere) -- and then streams that list through the TMA ring.
 __global__ void __launch_bounds__(256, 4)
 mip_fused_low_kernel(const __grid_constant__ CUtensorMap tmap, const LowArgs a) {
   extern __shared__ __align__(128) unsigned char low_smem_raw[];
@@ -334,42 +341,45 @@ mip_fused_low_kernel(const __grid_constant__ CUtensorMap tmap, const LowArgs a) 
     for (int s = 0; s < kLowStages; s++) mbar_init(&sm.full[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // make the initialised barriers visible to the async (TMA) proxy
   }
-  __syncthreads();
-  if (t == 0) {   // prologue: fill the ring
+  const int n_my = ((int)blockIdx.x < a.n_tiles) ? (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  uint32_t it = 0;   // uses of the ring so far: stage = it % kLowStages, barrier parity = (it / kLowStages) & 1
+  for (int cand0 = 0; cand0 < n_my; cand0 += kLowListMax) {
+    __syncthreads();   // the previous round is done with the list (and the barriers are initialised)
+    if (t == 0) sm.list_n = 0;
+    __syncthreads();
+    const int cand1 = min(cand0 + kLowListMax, n_my);
+    for (int k = cand0 + t; k < cand1; k += 256) {
+      const uint32_t tile = blockIdx.x + (uint32_t)k * gridDim.x;
+      const uint32_t zero = a.tile_zero[tile];
+      const bool active = a.touched ? (a.touched[tile] != 0 || zero == 0u) : true;
+      if (active) sm.list[atomicAdd(&sm.list_n, 1u)] = tile | (zero ? 0x80000000u : 0u);
+    }
+    __syncthreads();
+    const int n = (int)sm.list_n;
+    if (t == 0) {   // prologue: fill the ring
 #pragma unroll
-    for (int s = 0; s < kLowStages; s++) {
-      const int tile = blockIdx.x + s * gridDim.x;
-      if (tile < a.n_tiles) {
-        int bx, by, bz;
-        low_tile_coords(tile, a.log_tiles_x, a.log_tiles_y, bx, by, bz);
-        tma_load_tile(&tmap, &sm.s0[s][0][0][0], &sm.full[s], bx * TX, by * TY, bz * TZ);
-        sm.zero_flag[s] = a.tile_zero[tile];
+      for (int s = 0; s < kLowStages; s++) {
+        if (s < n) {
+          int bx, by, bz;
+          low_tile_coords((int)(sm.list[s] & 0x7FFFFFFFu), a.log_tiles_x, a.log_tiles_y, bx, by, bz);
+          const int stage = (int)((it + (uint32_t)s) % kLowStages);
+          tma_load_tile(&tmap, &sm.s0[stage][0][0][0], &sm.full[stage], bx * TX, by * TY, bz * TZ);
+        }
       }
     }
-  }
-  __syncthreads();
-  // thread 32 prefetches the tile_zero flag of the tile that thread 0 requests, one iteration ahead of storing it to
-  // shared memory, so that the flag's global-load latency never sits on the per-tile critical path
-  uint32_t pending_value = 0;
-  int pending_slot = -1;
-  int i = 0;
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, i++) {
-    const int stage = i % kLowStages;
-    mbar_wait(&sm.full[stage], (uint32_t)((i / kLowStages) & 1));
-    int bx, by, bz;
-    low_tile_coords(tile, a.log_tiles_x, a.log_tiles_y, bx, by, bz);
-    low_process_tile(sm.s0[stage], sm.s1, sm.s2, sm.s3, sm.occ_l1, a, tile, sm.zero_flag[stage], bx, by, bz);
-    __syncthreads();   // every read of this stage (and of s1/s2) is done: the buffer can be refilled
-    const int next = tile + kLowStages * gridDim.x;
-    if (t == 0) {
-      if (next < a.n_tiles) {
-        low_tile_coords(next, a.log_tiles_x, a.log_tiles_y, bx, by, bz);
+    for (int i = 0; i < n; i++, it++) {
+      const int stage = (int)(it % kLowStages);
+      mbar_wait(&sm.full[stage], (it / kLowStages) & 1u);
+      const uint32_t entry = sm.list[i];
+      const int tile = (int)(entry & 0x7FFFFFFFu);
+      int bx, by, bz;
+      low_tile_coords(tile, a.log_tiles_x, a.log_tiles_y, bx, by, bz);
+      low_process_tile(sm.s0[stage], sm.s1, sm.s2, sm.s3, sm.occ_l1, a, tile, entry >> 31, bx, by, bz);
+      __syncthreads();   // every read of this stage (and of s1/s2) is done: the buffer can be refilled
+      if (t == 0 && i + kLowStages < n) {
+        low_tile_coords((int)(sm.list[i + kLowStages] & 0x7FFFFFFFu), a.log_tiles_x, a.log_tiles_y, bx, by, bz);
         tma_load_tile(&tmap, &sm.s0[stage][0][0][0], &sm.full[stage], bx * TX, by * TY, bz * TZ);
       }
-    } else if (t == 32) {
-      if (pending_slot >= 0) sm.zero_flag[pending_slot] = pending_value;   // loaded one iteration ago; its stage is read >= 2 barriers from now
-      pending_slot = -1;
-      if (next < a.n_tiles) { pending_value = a.tile_zero[next]; pending_slot = stage; }
     }
   }
 }
@@ -691,6 +701,7 @@ int launch_mipmap(vct_device* dev, vct_grid* g) {
       VCT_CUDA(cudaMemsetAsync(g->tile_zero, 0, (size_t)n_tiles, s));   // unknown: the first build writes everything
     }
     la.tile_zero = g->tile_zero;
+    la.touched = (g->flags_valid && !g->external) ? g->tile_touched : nullptr;
     const int ctas = min(n_tiles, dev->prop.multiProcessorCount * 4);   // persistent: 4 CTAs of 40 KB shared memory per SM
     mip_fused_low_kernel<<<ctas, 256, sizeof(LowSmem), s>>>(*reinterpret_cast<const CUtensorMap*>(g->tmap_storage[buf]), la);
     level = 3;

@@ -56,6 +56,8 @@ int vct_peer_export(vct_device_t* dev, vct_grid_t* g, vct_target_t* t, vct_peer_
     VCT_CUDA(cudaMalloc(&g->base_buf[1], n0));
     g->bytes += n0;
   }
+  g->external = true;   // peers store into level 0: the sparse clear / sparse mip bookkeeping does not apply
+  g->untrack();
   VCT_CUDA(cudaMemsetAsync(g->base_buf[0], 0, n0, dev->stream));
   VCT_CUDA(cudaMemsetAsync(g->base_buf[1], 0, n0, dev->stream));
   if (!dev->peer_flags) VCT_CUDA(cudaMalloc(&dev->peer_flags, kFlagWords * 4));

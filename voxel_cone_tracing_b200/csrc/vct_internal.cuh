@@ -186,6 +186,7 @@ struct vct_device {
   uint32_t* counters = nullptr;      // device counters, see enum below
   uint32_t* counters_host = nullptr; // pinned mirror
   cudaEvent_t ev[8] = {};
+  vct_grid* vox_owner = nullptr;      // the grid whose occupied voxels are in `occupied` (last vct_voxelize)
   bool have_timings = false;
   bool gbuffer_overlapped = false;   // the last frame ran its G-buffer pass on stream2 (ev_g0..ev_g1)
   // multi-GPU connection (vct_peer_connect)
@@ -232,6 +233,15 @@ struct vct_grid {
   alignas(64) unsigned char tmap_storage[2][128] = {};   // CUtensorMap (TMA descriptor) of base_buf[0] / base_buf[1], built on first use
   uint32_t* tmap_base_ptr[2] = {};
   uint8_t* tile_zero = nullptr;         // mip stage: per 32x8x8 tile "levels 1-3 of this tile are known to be zero" (skip rewriting zeros)
+  // ---- sparse frame-to-frame bookkeeping (< 1 % of the voxels are occupied) ----
+  // tile_touched[tile] != 0: the last vct_voxelize wrote a voxel of this 32x8x8 tile.  While flags_valid, every non-zero word of
+  // level 0 lies in a touched tile, so the mip build skips untouched tiles whose outputs are already zero without reading them.
+  // While sparse_clear_ok (and dev->vox_owner == this), the non-zero words are exactly the device's occupied list and
+  // vct_grid_clear zeroes those instead of the whole level.  Anything that writes level 0 behind the library's back
+  // (vct_grid_upload_base, the raw pointer, peers) drops back to the dense paths.
+  uint8_t* tile_touched = nullptr;
+  bool flags_valid = false, sparse_clear_ok = false, base_zero = false, external = false;
+  void untrack() { flags_valid = sparse_clear_ok = base_zero = false; }
   uint32_t* occ[VCT_MAX_LEVELS] = {};   // non-dilated occupancy bits per level
   uint32_t* docc[VCT_MAX_LEVELS] = {};  // dilated occupancy bits per level: pointers into docc_all
   uint32_t* docc_all = nullptr;
@@ -284,6 +294,7 @@ static inline unsigned grid_for(size_t n, unsigned threads = 256, unsigned cap =
 
 // ---- stage entry points implemented in the .cu files ------------------------------------
 namespace vct {
+int launch_sparse_clear(vct_device* dev, vct_grid* g);
 int ensure_tri_scratch(vct_device* dev, int which /* 0 voxelizer, 1 G-buffer */, size_t n_tris, size_t rec_bytes);
 int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1, const PeerView* push = nullptr);
 int launch_peer_wait(vct_device* dev, int kind, uint32_t epoch);

@@ -282,9 +282,27 @@ __device__ __forceinline__ uint32_t avg_fold(uint32_t stored, const float val[4]
 
 constexpr int kSortMax = 24;
 
+// 32x8x8 tile (the unit of the fused mip kernel, mipmap.cu) of a level-0 voxel index; R = 2^logR
+__device__ __forceinline__ uint32_t tile_of_voxel(uint32_t voxel, int logR) {
+  const uint32_t m = (1u << logR) - 1u, x = voxel & m, y = (voxel >> logR) & m, z = voxel >> (2 * logR);
+  return (((z >> 3) << (logR - 3)) + (y >> 3) << (logR - 5)) + (x >> 5);
+}
+
+// vct_grid_clear, sparse form: zero the voxels (and the tile flags) of the last voxelization's occupied list
+__global__ void __launch_bounds__(256)
+sparse_clear_kernel(uint32_t* __restrict__ base, const uint32_t* __restrict__ occupied, const uint32_t* __restrict__ counters, uint32_t capacity,
+                    uint8_t* __restrict__ tile_touched, int logR) {
+  const uint32_t n = min(counters[CNT_OCCUPIED], capacity);
+  for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
+    const uint32_t voxel = occupied[o];
+    base[voxel] = 0u;
+    if (tile_touched) tile_touched[tile_of_voxel(voxel, logR)] = 0;
+  }
+}
+
 __global__ void __launch_bounds__(128)
 vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frags, const uint32_t* __restrict__ occupied,
-                   uint32_t* __restrict__ counters, uint32_t frag_capacity, const PeerView pv) {
+                   uint32_t* __restrict__ counters, uint32_t frag_capacity, const PeerView pv, uint8_t* __restrict__ tile_touched, int logR) {
   const uint32_t n_occ = counters[CNT_OCCUPIED];
   for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < n_occ; o += gridDim.x * blockDim.x) {
     const uint32_t voxel = occupied[o];
@@ -322,6 +340,7 @@ vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frag
       }
     }
     base[voxel] = stored;
+    if (tile_touched) tile_touched[tile_of_voxel(voxel, logR)] = 1;   // sparse mip build: this 32x8x8 tile has content
     // multi-GPU: the slab owner writes the resolved voxel straight into every peer's grid over NVLink (sparse
     // exchange: only occupied voxels travel; replaces the dense all-gather of the base level)
     for (int p = 0; p < pv.nranks; p++)
@@ -353,6 +372,15 @@ int ensure_tri_scratch(vct_device* dev, int which, size_t n_tris, size_t rec_byt
   return VCT_OK;
 }
 
+static int log2_int(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
+
+int launch_sparse_clear(vct_device* dev, vct_grid* g) {
+  sparse_clear_kernel<<<dev->prop.multiProcessorCount * 2, 256, 0, dev->stream>>>(g->base, dev->occupied, dev->counters, (uint32_t)dev->frag_capacity,
+                                                                                   g->tile_touched, log2_int(g->R));
+  VCT_CUDA(cudaGetLastError());
+  return VCT_OK;
+}
+
 int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1, const PeerView* push) {
   PeerView pv;
   memset(&pv, 0, sizeof pv);
@@ -365,6 +393,14 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
     if (rc) return rc;
   }
   cudaStream_t s = dev->stream;
+  // sparse bookkeeping (vct_grid in vct_internal.cuh): the occupied list written below describes level 0 completely only when the
+  // level was all zero before; the tile flags stay valid as long as every writer of level 0 marks them
+  const bool was_zero = g->base_zero;
+  g->base_zero = false;
+  g->sparse_clear_ok = was_zero && !push && !g->external;
+  dev->vox_owner = g;
+  uint8_t* touched = (g->flags_valid && !push && !g->external) ? g->tile_touched : nullptr;
+  if (!touched) g->flags_valid = false;
   VCT_CUDA(cudaMemsetAsync(dev->counters, 0, 8 * sizeof(uint32_t), s));
   const uint32_t n_blocks = (sc->n_tris + kSetupThreads - 1) / kSetupThreads;
   VoxTri* tris = (VoxTri*)dev->rs[0].tri_recs;
@@ -378,7 +414,7 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
                                                           dev->counters + CNT_TICKET_VOX, dev->counters + CNT_ITEMS);
     vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->rs[0].item_local, dev->rs[0].item_block, n_blocks, ctx);
   }
-  vox_resolve_kernel<<<sms * 4, 128, 0, s>>>(g->base, dev->frags, dev->occupied, dev->counters, (uint32_t)dev->frag_capacity, pv);
+  vox_resolve_kernel<<<sms * 4, 128, 0, s>>>(g->base, dev->frags, dev->occupied, dev->counters, (uint32_t)dev->frag_capacity, pv, touched, log2_int(g->R));
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;
 }
