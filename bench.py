@@ -38,10 +38,10 @@ CONFIGS = {
     2: dict(name="CornellBox-Glossy 256^3 1920x1080", R=256, W=1920, H=1080, scene="cornell"),
     3: dict(name="CornellBox+Suzanne 512^3 2560x1440 (dynamic object)", R=512, W=2560, H=1440, scene="cornell+suzanne"),
     4: dict(name="synthetic 1M triangles 512^3 3840x2160", R=512, W=3840, H=2160, scene="synthetic", tris=1_000_012, seed=0x5EED0001),
-    5: dict(name="synthetic 4M triangles 1024^3 7680x4320 (RGBA8, 7 levels, 9 cones: reference mode)", R=1024, W=7680, H=4320,
-            scene="synthetic", tris=4_000_000, seed=0x5EED0002),
+    5: dict(name="synthetic 4M triangles 1024^3 7680x4320 (RGBA8, 7 levels; 16 diffuse cones: BASELINE config 5's cone variant)", R=1024, W=7680, H=4320,
+            scene="synthetic", tris=4_000_000, seed=0x5EED0002, cones=16),
 }
-KERNELS_PER_FRAME = 12  # voxelize 3 (setup+scan, raster, resolve) + mip 2 (fused low; tail = levels 4-6 + occupancy + dilation) + gbuffer 4 (clear, setup+scan, raster, resolve) + trace 3 (tile list, cones, shade)
+KERNELS_PER_FRAME = 13  # clear 1 (sparse: the previous frame's occupied voxels) + voxelize 3 (setup+scan, raster, resolve) + mip 2 (fused low; tail = levels 4-6 + occupancy + dilation) + gbuffer 4 (clear, setup+scan, raster, resolve) + trace 3 (tile list, cones, shade)
 # ncu --set full capture of cone_kernel on this workload (profiles/r01_cone_kernel_ncu.md): dram__bytes_read.sum + dram__bytes_write.sum per launch
 CONE_KERNEL_DRAM_TRAFFIC = {1: 31.4e6 + 97.0e6, 0: 31.1e6 + 99.5e6}
 
@@ -131,7 +131,7 @@ class CpuWorkload:
 
     def trace_step(self, stride: int, phase: int):
         t0 = time.perf_counter()
-        _, st = self.orc.trace(self.sc, self.view, self.g, self.pyr, None, stride, phase % stride, self.frame)
+        _, st = self.orc.trace(self.sc, self.view, self.g, self.pyr, self.orc.default_params(n_diffuse_cones=self.cfg.get("cones", 9)), stride, phase % stride, self.frame)
         dt = time.perf_counter() - t0
         return dt, int(st.samples)
 
@@ -167,7 +167,7 @@ def run_reference(args, cfg, rank: int):
     print(json.dumps({
         "impl": "reference", "metric": "frames_per_sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 RGBA storage)", "data": "synthetic",
-        "config": {"workload": cfg["name"] + ", revoxelize+mip+gbuffer+trace per frame, 9 diffuse + 1 specular + 1 shadow cone"},
+        "config": {"workload": cfg["name"] + ", revoxelize+mip+gbuffer+trace per frame, %d diffuse + 1 specular + 1 shadow cone" % cfg.get("cones", 9)},
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": wl.cores, "kind": "port", "sample": wl.sample_text(stride),
                          "voxelize_s": wl.t_vox, "mip_s": wl.t_mip, "gbuffer_s": wl.t_gbuf},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -196,7 +196,7 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
     pipe = capi.Pipeline(sc, R, W, H, 7, ordinal=local_rank, reserve=max(1 << 20, 8 * sc.n_triangles))
     L, dev = pipe.dev.L, pipe.dev
     stream = torch.cuda.ExternalStream(int(L.vct_device_stream(dev.h)), device=torch.device("cuda", local_rank))
-    prm = capi.default_params(tile_rank=rank, tile_nranks=world, sampler=args.sampler)
+    prm = capi.default_params(tile_rank=rank, tile_nranks=world, sampler=args.sampler, n_diffuse_cones=cfg.get("cones", 9))
     z0, z1 = rank * R // world, (rank + 1) * R // world
     base_t = frame_t = None
     if world > 1:
@@ -363,7 +363,7 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
         out = {"metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 RGBA storage)",
                "data": "synthetic",
-               "config": {"workload": cfg["name"] + ", revoxelize+mip+gbuffer+trace per frame, 9 diffuse + 1 specular + 1 shadow cone",
+               "config": {"workload": cfg["name"] + ", revoxelize+mip+gbuffer+trace per frame, %d diffuse + 1 specular + 1 shadow cone" % cfg.get("cones", 9),
                           "sampler": "texture units (levels >= 1), software level 0" if args.sampler == 1 else "software fp32 trilinear",
                           "grid": R, "frame": [W, H], "triangles": sc.n_triangles, "parallelism": f"z-slab voxelize + screen-tile trace x{world}" + ("" if world == 1 else (", sparse NVLink peer-store exchange fused into the resolve/shade kernels (CUDA IPC, no collective)" if p2p else ", NCCL all-gather of the base level + all-reduce of the frame")),
                           "l2": "no explicit flush: grid + G-buffer + frame working set (%.0f MB) exceeds the 126 MB L2 and is rewritten every frame"

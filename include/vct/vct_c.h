@@ -62,7 +62,8 @@ typedef struct {
   int32_t enable_direct, enable_diffuse, enable_specular, enable_shadow; /* set_rendering_phases, renderer.cpp:195-201 */
   int32_t view_voxel_dir; /* set_voxel_view_dir, renderer.cpp:203-207; >= 7 = shade normally */
   float view_voxel_lod;
-  int32_t n_diffuse_cones; /* 9 = reference (voxel_cone_tracing.frag:153-165); 5 = normal + 4 side cones */
+  int32_t n_diffuse_cones; /* 9 = reference (voxel_cone_tracing.frag:153-165); 5 = normal + 4 side cones (BASELINE.json config 1);
+                            * 16 = normal + 5 at 30 deg + 10 at 60 deg, aperture 2 tan 15 deg (config 5); non-reference variants */
   int32_t tile_rank, tile_nranks; /* this call shades 32x32 screen tiles t with t % tile_nranks == tile_rank */
   int32_t sampler; /* VCT_SAMPLER_*: how textureLod is evaluated */
 } vct_trace_params_t;

@@ -349,10 +349,43 @@ struct ShadeCtx {
 
 struct SampleCount { uint64_t diffuse = 0, shadow = 0, specular = 0, refraction = 0; };
 
+// NON-REFERENCE VARIANT (BASELINE.json config 5): 16 diffuse cones = the normal + a ring of 5 at 30 degrees + a ring of
+// 10 at 60 degrees (azimuth 72 k and 36 k + 18 degrees), direction = n * cos(t) + (o1 * cos(p) + o2 * sin(p)) * sin(t) with the
+// reference's tangent frame, aperture 2 tan(15 degrees), equal weights.  Coefficients {cos t, sin t cos p, sin t sin p} rounded to float.
+static const float kCone16[16][3] = {
+    {1.0f, 0.0f, 0.0f},
+    {0.8660253882408142f, 0.5f, 0.0f},
+    {0.8660253882408142f, 0.15450850129127502f, 0.4755282700061798f},
+    {0.8660253882408142f, -0.404508501291275f, 0.29389262199401855f},
+    {0.8660253882408142f, -0.404508501291275f, -0.29389262199401855f},
+    {0.8660253882408142f, 0.15450850129127502f, -0.4755282700061798f},
+    {0.5f, 0.8236390948295593f, 0.2676165699958801f},
+    {0.5f, 0.5090369582176208f, 0.7006292939186096f},
+    {0.5f, 0.0f, 0.8660253882408142f},
+    {0.5f, -0.5090369582176208f, 0.7006292939186096f},
+    {0.5f, -0.8236390948295593f, 0.2676165699958801f},
+    {0.5f, -0.8236390948295593f, -0.2676165699958801f},
+    {0.5f, -0.5090369582176208f, -0.7006292939186096f},
+    {0.5f, 0.0f, -0.8660253882408142f},
+    {0.5f, 0.5090369582176208f, -0.7006292939186096f},
+    {0.5f, 0.8236390948295593f, -0.2676165699958801f},
+};
+static const float kAperture16 = 0.5358983874320984f;
+
 inline V3 trace_diffuse(const ShadeCtx& c, V3 origin, V3 normal, SampleCount& sc) { /* :140-168 */
   const float angle_mix = 0.5f;
   V3 o1 = normalize(tangent(normal));
   V3 o2 = normalize(cross(o1, normal));
+  if (c.prm->n_diffuse_cones == 16) {
+    float acc[3] = {0, 0, 0};
+    for (int i = 0; i < 16; i++) {
+      V3 d = add(add(mul(normal, kCone16[i][0]), mul(o1, kCone16[i][1])), mul(o2, kCone16[i][2]));
+      float r[4];
+      sc.diffuse += (uint64_t)trace_cone(c.pyr, origin, d, kAperture16, MAX_DISTANCE, r);
+      acc[0] = acc[0] + r[0]; acc[1] = acc[1] + r[1]; acc[2] = acc[2] + r[2];
+    }
+    return v3(acc[0] / 16.0f, acc[1] / 16.0f, acc[2] / 16.0f);
+  }
   V3 c1 = mul(add(o1, o2), 0.5f);
   V3 c2 = mul(sub(o1, o2), 0.5f);
   V3 dirs[9] = {normal,

@@ -302,7 +302,7 @@ def test_frame_other_cameras(sampler, camera):
     _check_frame(got, ref)
 
 
-@pytest.mark.parametrize("kw", [dict(n_diffuse_cones=5), dict(enable_shadow=0), dict(enable_diffuse=0, enable_specular=0),
+@pytest.mark.parametrize("kw", [dict(n_diffuse_cones=5), dict(n_diffuse_cones=16), dict(enable_shadow=0), dict(enable_diffuse=0, enable_specular=0),
                                 dict(enable_direct=0), dict(view_voxel_dir=1, view_voxel_lod=1.5), dict(view_voxel_dir=4, view_voxel_lod=0.0)])
 @pytest.mark.parametrize("sampler", SAMPLERS)
 def test_frame_variants(kw, sampler):
@@ -364,6 +364,13 @@ def test_async_readback_equals_blocking_readback():
         assert np.array_equal(p.target.frame(), host[i]), f"frame {i}"
     assert not np.array_equal(host[0], host[1])
     p.close()
+
+
+def test_frame_16_cone_variant_large_frame():
+    """BASELINE config 5's 16-cone variant at a frame large enough for the grouped-diffuse kernel (all cones of a tile in one warp)"""
+    got, ref, cnt = _frame_pair(S.cornell_scene(with_suzanne=True), 128, 1920, 1080, dict(n_diffuse_cones=16), sampler=capi.SAMPLER_TEX)
+    _check_frame(got, ref)
+    assert abs(cnt.samples_diffuse - ref["trace_stats"].samples_diffuse) <= 5e-2 * ref["trace_stats"].samples_diffuse
 
 
 def test_sparse_frame_sequence_matches_fresh_builds():

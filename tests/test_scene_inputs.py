@@ -59,9 +59,9 @@ def test_oracle_regression_digests():
     gold = json.load(open(os.path.join(ROOT, "tests", "golden", "oracle_regression.json")))
     now = oracle_digests()
     for k, v in gold.items():
-        if k == "frame_mean_rgba":
+        if k.startswith("frame_mean_rgba"):
             assert np.allclose(now[k], v, atol=0.05)
-        elif k == "samples":
+        elif k.startswith("samples"):
             assert abs(now[k] - v) <= 1e-3 * v
         else:
             assert now[k] == v, k

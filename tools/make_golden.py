@@ -75,6 +75,11 @@ def oracle_digests():
             d[f"mip_l{l}_d{dr}"] = hashlib.sha256(r["pyramid"].levels[dr][l].tobytes()).hexdigest()
     # the frame depends on libm (log2f/powf/tanf): keep a coarse digest only (mean colour)
     d["frame_mean_rgba"] = [float(x) for x in r["frame"].view(np.uint8).reshape(-1, 4).mean(axis=0)]
+    # non-reference diffuse variants (BASELINE.json configs 1 and 5): 5 and 16 cones on the same pyramid / G-buffer
+    for n in (5, 16):
+        f, st = orc.trace(sc, view, r["gbuffer"], r["pyramid"], orc.default_params(n_diffuse_cones=n))
+        d[f"samples_diffuse_{n}"] = int(st.samples_diffuse)
+        d[f"frame_mean_rgba_{n}"] = [float(x) for x in f.view(np.uint8).reshape(-1, 4).mean(axis=0)]
     return d
 
 

@@ -389,6 +389,46 @@ constexpr float kMaxDistance = 1.73205080757f;
 constexpr uint32_t kBackground = 0xFF404026u;  // (0.15,0.25,0.25,1) -> (38,64,64,255), renderer.cpp:398
 constexpr int kConeWarps = 4;                  // warps (= tiles) per cone_kernel CTA
 
+// NON-REFERENCE VARIANT (BASELINE.json config 5): 16 diffuse cones = the normal + a ring of 5 at 30 degrees + a ring of
+// 10 at 60 degrees (azimuth 72 k and 36 k + 18 degrees), direction = n * cos(t) + (o1 * cos(p) + o2 * sin(p)) * sin(t), aperture
+// 2 tan(15 degrees), equal weights.  Coefficients {cos t, sin t cos p, sin t sin p} rounded to float, the same literals as the oracle's.
+__device__ constexpr float kCone16[16][3] = {
+    {1.0f, 0.0f, 0.0f},
+    {0.8660253882408142f, 0.5f, 0.0f},
+    {0.8660253882408142f, 0.15450850129127502f, 0.4755282700061798f},
+    {0.8660253882408142f, -0.404508501291275f, 0.29389262199401855f},
+    {0.8660253882408142f, -0.404508501291275f, -0.29389262199401855f},
+    {0.8660253882408142f, 0.15450850129127502f, -0.4755282700061798f},
+    {0.5f, 0.8236390948295593f, 0.2676165699958801f},
+    {0.5f, 0.5090369582176208f, 0.7006292939186096f},
+    {0.5f, 0.0f, 0.8660253882408142f},
+    {0.5f, -0.5090369582176208f, 0.7006292939186096f},
+    {0.5f, -0.8236390948295593f, 0.2676165699958801f},
+    {0.5f, -0.8236390948295593f, -0.2676165699958801f},
+    {0.5f, -0.5090369582176208f, -0.7006292939186096f},
+    {0.5f, 0.0f, -0.8660253882408142f},
+    {0.5f, 0.5090369582176208f, -0.7006292939186096f},
+    {0.5f, 0.8236390948295593f, -0.2676165699958801f},
+};
+constexpr float kAperture16 = 0.5358983874320984f;
+
+// direction of diffuse cone `slot` from the tangent frame: the nine cones of voxel_cone_tracing.frag:153-165 (and their first five),
+// or the 16-cone variant
+__device__ __forceinline__ F3 diffuse_dir(F3 normal, F3 o1, F3 o2, int slot, int n_cones = 9) {
+  if (n_cones == 16) return (normal * kCone16[slot][0] + o1 * kCone16[slot][1]) + o2 * kCone16[slot][2];
+  switch (slot) {
+    case 0: return normal;
+    case 1: return mix(normal, o1, 0.5f);
+    case 2: return mix(normal, -o1, 0.5f);
+    case 3: return mix(normal, o2, 0.5f);
+    case 4: return mix(normal, -o2, 0.5f);
+    case 5: return mix(normal, (o1 + o2) * 0.5f, 0.5f);
+    case 6: return mix(normal, -((o1 + o2) * 0.5f), 0.5f);
+    case 7: return mix(normal, (o1 - o2) * 0.5f, 0.5f);
+    default: return mix(normal, -((o1 - o2) * 0.5f), 0.5f);
+  }
+}
+
 struct Pixel {
   size_t pix;
   uint32_t mat_id;
@@ -476,19 +516,8 @@ cone_kernel(const TraceArgs a) {
       if (a.prm.enable_diffuse) {
         const F3 o1 = normalize(tangent(normal));
         const F3 o2 = normalize(cross(o1, normal));
-        F3 d;
-        switch (slot) {
-          case 0: d = normal; break;
-          case 1: d = mix(normal, o1, 0.5f); break;
-          case 2: d = mix(normal, -o1, 0.5f); break;
-          case 3: d = mix(normal, o2, 0.5f); break;
-          case 4: d = mix(normal, -o2, 0.5f); break;
-          case 5: d = mix(normal, (o1 + o2) * 0.5f, 0.5f); break;
-          case 6: d = mix(normal, -((o1 + o2) * 0.5f), 0.5f); break;
-          case 7: d = mix(normal, (o1 - o2) * 0.5f, 0.5f); break;
-          default: d = mix(normal, -((o1 - o2) * 0.5f), 0.5f); break;
-        }
-        iters = trace_cone<COUNT, TEX>(a.grid, pos, d, kTan22_5, kMaxDistance, r);
+        const F3 d = diffuse_dir(normal, o1, o2, slot, nd);
+        iters = trace_cone<COUNT, TEX>(a.grid, pos, d, nd == 16 ? kAperture16 : kTan22_5, kMaxDistance, r);
         kind = 0;
       }
     } else if (slot == nd) {
@@ -537,21 +566,6 @@ cone_kernel(const TraceArgs a) {
 }
 
 
-// direction of diffuse cone `slot` (voxel_cone_tracing.frag:153-165) from the tangent frame
-__device__ __forceinline__ F3 diffuse_dir(F3 normal, F3 o1, F3 o2, int slot) {
-  switch (slot) {
-    case 0: return normal;
-    case 1: return mix(normal, o1, 0.5f);
-    case 2: return mix(normal, -o1, 0.5f);
-    case 3: return mix(normal, o2, 0.5f);
-    case 4: return mix(normal, -o2, 0.5f);
-    case 5: return mix(normal, (o1 + o2) * 0.5f, 0.5f);
-    case 6: return mix(normal, -((o1 + o2) * 0.5f), 0.5f);
-    case 7: return mix(normal, (o1 - o2) * 0.5f, 0.5f);
-    default: return mix(normal, -((o1 - o2) * 0.5f), 0.5f);
-  }
-}
-
 // cone parameters of one (pixel, slot): direction, aperture, max distance; false = this slot traces nothing for the pixel
 __device__ __forceinline__ bool cone_setup(const TraceArgs& a, const Pixel& p, int slot, F3& d, float& aperture, float& max_dist) {
   const int nd = a.n_diffuse;
@@ -564,7 +578,8 @@ __device__ __forceinline__ bool cone_setup(const TraceArgs& a, const Pixel& p, i
     if (!a.prm.enable_diffuse) return false;
     const F3 o1 = tangent_fast(normal);   // (the reference normalises it twice: a no-op up to an ulp)
     const F3 o2 = normalize_fast(cross(o1, normal));
-    d = diffuse_dir(normal, o1, o2, slot);
+    d = diffuse_dir(normal, o1, o2, slot, nd);
+    if (nd == 16) aperture = kAperture16;
     return true;
   }
   const F3 cam = f3(a.cam_pos[0], a.cam_pos[1], a.cam_pos[2]);
@@ -621,7 +636,7 @@ cone_kernel_fast(const TraceArgs a) {
         const F3 o2 = normalize_fast(cross(o1, p.normal));
 #pragma unroll 1
         for (int i = 0; i < a.n_diffuse; i++) {
-          trace_cone_fast<TEX, SPLIT>(a.grid, true, p.pos, diffuse_dir(p.normal, o1, o2, i), kTan22_5, kMaxDistance, r);
+          trace_cone_fast<TEX, SPLIT>(a.grid, true, p.pos, diffuse_dir(p.normal, o1, o2, i, a.n_diffuse), a.n_diffuse == 16 ? kAperture16 : kTan22_5, kMaxDistance, r);
           sum[0] = sum[0] + r[0]; sum[1] = sum[1] + r[1]; sum[2] = sum[2] + r[2];
         }
       }
@@ -792,13 +807,23 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
   a.prm = *p;
   if (a.prm.tile_nranks < 1) { a.prm.tile_nranks = 1; a.prm.tile_rank = 0; }
   a.counts = (unsigned long long*)(dev->counters + 16);
-  a.n_diffuse = p->n_diffuse_cones == 5 ? 5 : 9;
+  a.n_diffuse = p->n_diffuse_cones == 5 ? 5 : (p->n_diffuse_cones == 16 ? 16 : 9);
   a.n_slots = a.n_diffuse + 2 + sc->lights.n;
   a.grouped = 0;
   a.npix = (size_t)t->W * t->H;
   const int n_tiles = ((t->W + 7) / 8) * ((t->H + 3) / 4);
-  // cone result buffer [slot][pixel] and the live-tile list, grown on demand
-  const size_t need = (size_t)a.n_slots * a.npix;
+  // which march: 3 = production (one-level fetches through the nearest-mip texture object, all diffuse cones of a tile in one warp), 2 = one
+  // warp per cone slot, 1 = every fetch blends two levels, 0 = literal loop; VCT_CONE_VARIANT is read per call so that tests can compare them
+  const bool tex = p->sampler == VCT_SAMPLER_TEX && g->levels >= 2;
+  const char* ev = getenv("VCT_CONE_VARIANT");
+  int variant = ev ? atoi(ev) : 3;
+  // grouping makes the diffuse warps nine times longer: with few tiles per GPU (small frames, many ranks) the tail of the launch costs
+  // more than the shared set-up saves (512x512: 200 -> 224 us; 1920x1080: 887 -> 863 us)
+  // (and the fp32 software sampler, 72 registers, spills in the grouped form: 3.7 -> 4.6 ms at 1080p)
+  if (!ev && (n_tiles / a.prm.tile_nranks < 32768 || !tex)) variant = 2;
+  a.grouped = (!count_samples && variant >= 3) ? 1 : 0;
+  // cone result buffer [slot or job][pixel] and the live-tile list, grown on demand
+  const size_t need = (size_t)(a.grouped ? 3 + sc->lights.n : a.n_slots) * a.npix;
   if (need > t->cone_out_elems) {
     VCT_CUDA(cudaStreamSynchronize(dev->stream));
     cudaFree(t->cone_out);
@@ -819,16 +844,6 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
     tile_list_kernel<<<(n_tiles + 8 * kTilesPerWarp - 1) / (8 * kTilesPerWarp), 256, 0, s>>>(a, t->tile_list + 1, t->tile_list);
     const dim3 grid((n_tiles + kConeWarps - 1) / kConeWarps, a.n_slots);
     const dim3 grid_jobs(grid.x, 3 + sc->lights.n);   // GROUP: the diffuse cones are one job
-    const bool tex = p->sampler == VCT_SAMPLER_TEX && g->levels >= 2;
-    // 3 = production (one-level fetches through the nearest-mip texture object, all diffuse cones of a tile in one warp), 2 = one warp per
-    // cone slot, 1 = every fetch blends two levels, 0 = literal loop; read per call so that tests can compare them
-    const char* ev = getenv("VCT_CONE_VARIANT");
-    int variant = ev ? atoi(ev) : 3;
-    // grouping makes the diffuse warps nine times longer: with few tiles per GPU (small frames, many ranks) the tail of the launch costs
-    // more than the shared set-up saves (512x512: 200 -> 224 us; 1920x1080: 887 -> 863 us)
-    // (and the fp32 software sampler, 72 registers, spills in the grouped form: 3.7 -> 4.6 ms at 1080p)
-    if (!ev && (n_tiles / a.prm.tile_nranks < 32768 || !tex)) variant = 2;
-    a.grouped = (!count_samples && variant >= 3) ? 1 : 0;
     VCT_CUDA(cudaEventRecord(dev->ev[6], s));
     if (count_samples) {
       VCT_CUDA(cudaMemsetAsync(dev->counters + 16, 0, 8 * sizeof(unsigned long long), s));
