@@ -42,8 +42,11 @@ CONFIGS = {
             scene="synthetic", tris=4_000_000, seed=0x5EED0002, cones=16),
 }
 KERNELS_PER_FRAME = 13  # clear 1 (sparse: the previous frame's occupied voxels) + voxelize 3 (setup+scan, raster, resolve) + mip 2 (fused low; tail = levels 4-6 + occupancy + dilation) + gbuffer 4 (clear, setup+scan, raster, resolve) + trace 3 (tile list, cones, shade)
-# ncu --set full capture of cone_kernel on this workload (profiles/r01_cone_kernel_ncu.md): dram__bytes_read.sum + dram__bytes_write.sum per launch
-CONE_KERNEL_DRAM_TRAFFIC = {1: 31.4e6 + 97.0e6, 0: 31.1e6 + 99.5e6}
+# ncu --set full capture of cone_kernel_fast on this workload (profiles/r01_cone_kernel_ncu_s7.md), per launch:
+# dram__bytes_read.sum + dram__bytes_write.sum, and the two units that bind the kernel
+CONE_KERNEL_DRAM_TRAFFIC = {1: 28.3e6 + 31.4e6}
+CONE_KERNEL_NCU = {"tex_wavefront_frac": 0.755, "issue_frac": 0.651, "tex_wavefronts_per_launch": 192.4e6, "warp_instructions_per_launch": 639.6e6,
+                   "l1tex_sectors_per_launch": 649.9e6, "source": "profiles/r01_cone_kernel_ncu_s7.md (ncu --set full, one launch of this command)"}
 
 
 def build_scene(cfg, frame: int = 0):
@@ -336,13 +339,32 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
                 "traffic": CONE_KERNEL_DRAM_TRAFFIC.get(args.sampler) if args.config == 2 else None,
                 "peak_source": peak_src, "algorithmic_bytes_per_launch": gather_bytes, "samples_per_launch": int(cnt.samples),
                 "gsamples_per_s": cnt.samples / t_trace / 1e9,
+                "binding_units": CONE_KERNEL_NCU if (args.config == 2 and args.sampler == 1) else None,
                 "note": "algorithmic gather bytes (192 B per sample_voxel: 3 directions x 2 levels x 8 texels x 4 B) / CUDA-event kernel time. The gathers are "
-                        "served by the texture units / L1 and the 126 MB L2 (the pyramid fits), DRAM traffic is ~0.13 GB per launch, so frac > 1 against "
-                        "the HBM copy peak is expected; the binding unit is the TEX pipe (ncu l1tex__throughput 85 % of peak, profiles/)"}
+                        "served by the texture units / L1 (20.8 GB of L1TEX sectors per launch, 99 % hit) and the 126 MB L2, DRAM traffic is 0.06 GB per launch, "
+                        "so frac > 1 against the HBM copy peak is expected; the kernel is bound by the TEX pipe (75 % of one wavefront/clk/SM) and the "
+                        "issue slots (65 %), see binding_units and DESIGN.md 3.3"}
         mip_bytes = 7.4286 * R ** 3
         stages = {k + "_us": v * 1e3 for k, v in stage_acc.items()}
         stages["mip_roofline"] = {"bound": "hbm", "achieved": mip_bytes / (stage_acc["mipmap"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                  "frac": mip_bytes / (stage_acc["mipmap"] * 1e-3) / 1e9 / peak, "algorithmic_bytes": mip_bytes}
+                                  "frac": mip_bytes / (stage_acc["mipmap"] * 1e-3) / 1e9 / peak, "algorithmic_bytes": mip_bytes,
+                                  "note": "dense algorithmic bytes (7.4286 R^3) / mip stage time of the running frame loop, where tiles that the voxelizer "
+                                          "did not touch and whose outputs are already zero are neither read nor written (DESIGN.md 3.2); dense build: "
+                                          "mip_dense_us"}
+        # the dense mip build (every tile read and written: first frame, uploads), CUDA events on the library's stream
+        os.environ["VCT_MIP_DENSE"] = "1"
+        pipe.mipmap(); pipe.sync()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with torch.cuda.stream(stream):
+            d0.record(stream)
+            for _ in range(10):
+                pipe.mipmap()
+            d1.record(stream)
+        pipe.sync()
+        del os.environ["VCT_MIP_DENSE"]
+        pipe.render_frame(view, proj, prm); pipe.sync()      # back to the tracked state
+        stages["mip_dense_us"] = d0.elapsed_time(d1) * 100.0  # ms per 10 builds -> us per build
+        stages["mip_roofline"]["dense_frac"] = mip_bytes / (stages["mip_dense_us"] * 1e-6) / 1e9 / peak
         stages["note"] = ("gbuffer_us = the part of the G-buffer pass on the critical path: the pass (gbuffer_pass_us) runs on a second stream "
                           "beside clear + voxelize + mip and joins before the trace, so the stage times overlap and need not add up to total_us")
         stages["clear_gbs"] = 4.0 * R ** 3 / (stage_acc["clear"] * 1e-3) / 1e9

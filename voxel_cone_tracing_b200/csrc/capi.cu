@@ -103,12 +103,16 @@ int vct_device_create(int ordinal, vct_device_t** out) {
     delete d;
     return VCT_ERR_CUDA;
   }
-  VCT_CUDA(cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking));
+  // the frame's critical path (clear -> voxelize -> mip -> trace) runs on a high-priority stream, the G-buffer pass beside it on a
+  // low-priority one: when both have blocks ready the scheduler serves the critical path first
+  int prio_lo = 0, prio_hi = 0;
+  VCT_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  VCT_CUDA(cudaStreamCreateWithPriority(&d->stream, cudaStreamNonBlocking, prio_hi));
   VCT_CUDA(cudaMalloc(&d->counters, CNT_TOTAL * sizeof(uint32_t)));
   VCT_CUDA(cudaMemset(d->counters, 0, CNT_TOTAL * sizeof(uint32_t)));
   VCT_CUDA(cudaMallocHost(&d->counters_host, CNT_TOTAL * sizeof(uint32_t)));
   for (int i = 0; i < 8; i++) VCT_CUDA(cudaEventCreate(&d->ev[i]));
-  VCT_CUDA(cudaStreamCreateWithFlags(&d->stream2, cudaStreamNonBlocking));
+  VCT_CUDA(cudaStreamCreateWithPriority(&d->stream2, cudaStreamNonBlocking, prio_lo));
   VCT_CUDA(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
   VCT_CUDA(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
   VCT_CUDA(cudaEventCreate(&d->ev_g0));
@@ -648,23 +652,24 @@ int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_targ
   // The G-buffer pass needs the scene and the camera, not the voxel grid: it runs on a second stream beside
   // clear + voxelize + mip (chains of small, latency-bound kernels that leave most SMs idle) and joins before the trace.
   VCT_CUDA(cudaEventRecord(dev->ev_fork, s));               // everything queued so far (scene uploads, the previous frame's read-back)
+  if ((rc = vct_grid_clear(g))) return rc;                  // the critical path is submitted first, the G-buffer launches fill in behind it
+  VCT_CUDA(cudaEventRecord(dev->ev[1], s));
+  if ((rc = launch_voxelize(dev, sc, g, 0, g->R))) return rc;
+  VCT_CUDA(cudaEventRecord(dev->ev[2], s));
   VCT_CUDA(cudaStreamWaitEvent(dev->stream2, dev->ev_fork, 0));
   dev->stream = dev->stream2;
   VCT_CUDA(cudaEventRecord(dev->ev_g0, dev->stream2));
   rc = launch_gbuffer(dev, sc, view, proj, t);
+  if (!rc) rc = launch_cone_trace(dev, sc, g, view, p, t, false, nullptr, 1);   // the live-tile list needs the G-buffer only
   dev->stream = s;
   if (rc) return rc;
   VCT_CUDA(cudaEventRecord(dev->ev_g1, dev->stream2));
   VCT_CUDA(cudaEventRecord(dev->ev_join, dev->stream2));
-  if ((rc = vct_grid_clear(g))) return rc;
-  VCT_CUDA(cudaEventRecord(dev->ev[1], s));
-  if ((rc = launch_voxelize(dev, sc, g, 0, g->R))) return rc;
-  VCT_CUDA(cudaEventRecord(dev->ev[2], s));
   if ((rc = launch_mipmap(dev, g))) return rc;
   VCT_CUDA(cudaEventRecord(dev->ev[3], s));
   VCT_CUDA(cudaStreamWaitEvent(s, dev->ev_join, 0));
   VCT_CUDA(cudaEventRecord(dev->ev[4], s));                 // ev[3]..ev[4] = what is left of the G-buffer pass after the mip build
-  if ((rc = launch_cone_trace(dev, sc, g, view, p, t, false))) return rc;
+  if ((rc = launch_cone_trace(dev, sc, g, view, p, t, false, nullptr, 2))) return rc;
   VCT_CUDA(cudaEventRecord(dev->ev[5], s));
   dev->have_timings = true;
   dev->gbuffer_overlapped = true;

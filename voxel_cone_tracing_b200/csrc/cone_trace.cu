@@ -792,7 +792,7 @@ frame_push_kernel(const TraceArgs a) {
 }
 
 int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* view, const vct_trace_params_t* p, vct_target_t_* t,
-                      bool count_samples, const PeerView* push) {
+                      bool count_samples, const PeerView* push, int phase) {
   TraceArgs a;
   memset(&a.pv, 0, sizeof a.pv);
   if (push) a.pv = *push;
@@ -839,9 +839,15 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
   a.cone_out = (float4*)t->cone_out;
   cudaStream_t s = dev->stream;
   const bool debug_view = p->view_voxel_dir < 7;
-  if (!debug_view) {
+  if (!debug_view && phase != 2) {
     VCT_CUDA(cudaMemsetAsync(t->tile_list, 0, sizeof(uint32_t), s));
     tile_list_kernel<<<(n_tiles + 8 * kTilesPerWarp - 1) / (8 * kTilesPerWarp), 256, 0, s>>>(a, t->tile_list + 1, t->tile_list);
+  }
+  if (phase == 1) {
+    VCT_CUDA(cudaGetLastError());
+    return VCT_OK;
+  }
+  if (!debug_view) {
     const dim3 grid((n_tiles + kConeWarps - 1) / kConeWarps, a.n_slots);
     const dim3 grid_jobs(grid.x, 3 + sc->lights.n);   // GROUP: the diffuse cones are one job
     VCT_CUDA(cudaEventRecord(dev->ev[6], s));

@@ -15,6 +15,8 @@
 // mipmap.comp:40-43, sum of the four pairs in order, /4, rint(clamp*255) -> bit-exact vs the oracle.
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "vct_internal.cuh"
 
 namespace vct {
@@ -702,6 +704,10 @@ int launch_mipmap(vct_device* dev, vct_grid* g) {
     }
     la.tile_zero = g->tile_zero;
     la.touched = (g->flags_valid && !g->external) ? g->tile_touched : nullptr;
+    if (const char* dense = getenv("VCT_MIP_DENSE"); dense && dense[0] == '1') {   // measurement switch: the dense build (every tile read and written)
+      la.touched = nullptr;
+      VCT_CUDA(cudaMemsetAsync(g->tile_zero, 0, (size_t)n_tiles, s));
+    }
     const int ctas = min(n_tiles, dev->prop.multiProcessorCount * 4);   // persistent: 4 CTAs of 40 KB shared memory per SM
     mip_fused_low_kernel<<<ctas, 256, sizeof(LowSmem), s>>>(*reinterpret_cast<const CUtensorMap*>(g->tmap_storage[buf]), la);
     level = 3;

@@ -300,8 +300,10 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
 int launch_peer_wait(vct_device* dev, int kind, uint32_t epoch);
 int launch_mipmap(vct_device* dev, vct_grid* g);
 int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const float* proj, vct_target_t_* t, int tile_rank = 0, int tile_nranks = 1);
+// phase: 0 = tile list + cones + shade; 1 = the live-tile list only (depends on the G-buffer alone: vct_render_frame builds it on the
+// G-buffer stream); 2 = cones + shade with the list of a preceding phase-1 call
 int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* view, const vct_trace_params_t* p, vct_target_t_* t,
-                      bool count_samples, const PeerView* push = nullptr);
+                      bool count_samples, const vct::PeerView* push = nullptr, int phase = 0);
 int launch_fill_u32(cudaStream_t s, uint32_t* p, size_t n, uint32_t v);
 int launch_tex3d_mip(vct_tex3d* t);
 }  // namespace vct
