@@ -35,9 +35,8 @@ def run(name, upload, readback):
     dt = time.perf_counter() - t0
     print(f"{name:40s} {1e3*dt/N:.3f} ms/frame   host enqueue time {1e3*cpu/N:.3f} ms/frame", flush=True)
 
-run("render only", False, None)
-run("upload + render", True, None)
-run("render + async readback", False, "async")
-run("upload + render + async readback", True, "async")
-run("upload + render + blocking readback", True, "blocking")
+mode = os.environ.get("VCT_ASYNC_MODE", "0")
+run(f"[mode {mode}] render only", False, None)
+run(f"[mode {mode}] render + async readback", False, "async")
+run(f"[mode {mode}] upload + render + async readback", True, "async")
 p.close()

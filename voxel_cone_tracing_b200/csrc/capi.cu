@@ -467,7 +467,9 @@ int vct_target_destroy(vct_target_t* t) {
   cudaStreamSynchronize(t->dev->stream);
   cudaFree(t->vis); cudaFree(t->world_pos); cudaFree(t->normal); cudaFree(t->material); cudaFree(t->frame);
   cudaFree(t->cone_out); cudaFree(t->tile_list);
+  t->pending_host = nullptr;
   if (t->copy_stream) { cudaStreamSynchronize(t->copy_stream); cudaStreamDestroy(t->copy_stream); }
+  if (t->copy_gate) cudaEventDestroy(t->copy_gate);
   for (int i = 0; i < 2; i++) {
     cudaFree(t->snap[i]);
     if (t->snap_ready[i]) cudaEventDestroy(t->snap_ready[i]);
@@ -484,28 +486,47 @@ int vct_target_download_frame(vct_target_t* t, uint32_t* host) {
   return VCT_OK;
 }
 
-// Asynchronous read-back.  The finished frame is snapshotted on the device stream (8 MB device-to-device at 1080p, a few us),
-// the snapshot is copied to the host on a second stream, and the call returns at once: the next vct_render_frame overlaps the
-// PCIe transfer.  Two snapshots alternate; the device stream waits for the copy that last read the one it is about to overwrite.
+// Asynchronous read-back.  The finished frame is snapshotted on the device stream by a kernel (8 MB at 1080p, a few us), the
+// snapshot is copied to the host on a second stream, and the call returns at once.  Two snapshots alternate; the device stream
+// waits for the copy that last read the one it is about to overwrite.
+// WHEN the copy runs matters: a device-to-host transfer in flight slows down the start of the next frame -- a chain of a dozen
+// small kernels whose command fetches are PCIe reads that queue behind the posted writes of the transfer (measured: +83 us per
+// frame for 8 MB, +5 us for 4 KB).  So the copy is not enqueued here: the next vct_render_frame on this target starts it
+// together with its cone kernel (one 0.85 ms launch that needs nothing from the host), and vct_target_download_wait /
+// a blocking download start it at once if no frame came in between.
+static int start_pending_readback(vct_target_t_* t, cudaEvent_t gate) {
+  if (!t->pending_host) return VCT_OK;
+  const int b = t->pending_slot;
+  const size_t bytes = (size_t)t->W * t->H * 4;
+  VCT_CUDA(cudaStreamWaitEvent(t->copy_stream, t->snap_ready[b], 0));
+  if (gate) VCT_CUDA(cudaStreamWaitEvent(t->copy_stream, gate, 0));
+  VCT_CUDA(cudaMemcpyAsync(t->pending_host, t->snap[b], bytes, cudaMemcpyDeviceToHost, t->copy_stream));
+  VCT_CUDA(cudaEventRecord(t->copy_done[b], t->copy_stream));
+  t->pending_host = nullptr;
+  return VCT_OK;
+}
+
 int vct_target_download_frame_async(vct_target_t* t, uint32_t* host, uint64_t* ticket) {
   VCT_REQUIRE(t && host && ticket, "null argument");
   cudaStream_t s = t->dev->stream;
   const size_t bytes = (size_t)t->W * t->H * 4;
   if (!t->copy_stream) {
     VCT_CUDA(cudaStreamCreateWithFlags(&t->copy_stream, cudaStreamNonBlocking));
+    VCT_CUDA(cudaEventCreateWithFlags(&t->copy_gate, cudaEventDisableTiming));
     for (int i = 0; i < 2; i++) {
       VCT_CUDA(cudaMalloc(&t->snap[i], bytes));
       VCT_CUDA(cudaEventCreateWithFlags(&t->snap_ready[i], cudaEventDisableTiming));
       VCT_CUDA(cudaEventCreateWithFlags(&t->copy_done[i], cudaEventDisableTiming));
     }
   }
+  int rc = start_pending_readback(t, nullptr);   // two read-backs without a frame in between: the older one goes now
+  if (rc) return rc;
   const int b = (int)(t->n_async & 1);
   if (t->n_async >= 2) VCT_CUDA(cudaStreamWaitEvent(s, t->copy_done[b], 0));
-  VCT_CUDA(cudaMemcpyAsync(t->snap[b], t->frame, bytes, cudaMemcpyDeviceToDevice, s));
+  if ((rc = launch_copy_u32(s, t->snap[b], t->frame, (size_t)t->W * t->H))) return rc;
   VCT_CUDA(cudaEventRecord(t->snap_ready[b], s));
-  VCT_CUDA(cudaStreamWaitEvent(t->copy_stream, t->snap_ready[b], 0));
-  VCT_CUDA(cudaMemcpyAsync(host, t->snap[b], bytes, cudaMemcpyDeviceToHost, t->copy_stream));
-  VCT_CUDA(cudaEventRecord(t->copy_done[b], t->copy_stream));
+  t->pending_host = host;
+  t->pending_slot = b;
   *ticket = ++t->n_async;
   return VCT_OK;
 }
@@ -513,6 +534,10 @@ int vct_target_download_frame_async(vct_target_t* t, uint32_t* host, uint64_t* t
 int vct_target_download_wait(vct_target_t* t, uint64_t ticket) {
   VCT_REQUIRE(t, "target is null");
   VCT_REQUIRE(ticket >= 1 && ticket <= t->n_async, "unknown ticket");
+  if (t->pending_host && ticket == t->n_async) {   // its copy has not been started yet
+    int rc = start_pending_readback(t, nullptr);
+    if (rc) return rc;
+  }
   // copy_done[b] always carries the newest copy out of snapshot b, issued at or after `ticket` on the same (ordered) copy stream
   VCT_CUDA(cudaEventSynchronize(t->copy_done[(ticket - 1) & 1]));
   return VCT_OK;
@@ -669,6 +694,10 @@ int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_targ
   VCT_CUDA(cudaEventRecord(dev->ev[3], s));
   VCT_CUDA(cudaStreamWaitEvent(s, dev->ev_join, 0));
   VCT_CUDA(cudaEventRecord(dev->ev[4], s));                 // ev[3]..ev[4] = what is left of the G-buffer pass after the mip build
+  if (t->pending_host) {   // the previous frame's read-back crosses PCIe while the cone kernel runs (see vct_target_download_frame_async)
+    VCT_CUDA(cudaEventRecord(t->copy_gate, s));
+    if ((rc = start_pending_readback(t, t->copy_gate))) return rc;
+  }
   if ((rc = launch_cone_trace(dev, sc, g, view, p, t, false, nullptr, 2))) return rc;
   VCT_CUDA(cudaEventRecord(dev->ev[5], s));
   dev->have_timings = true;

@@ -840,7 +840,7 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
   cudaStream_t s = dev->stream;
   const bool debug_view = p->view_voxel_dir < 7;
   if (!debug_view && phase != 2) {
-    VCT_CUDA(cudaMemsetAsync(t->tile_list, 0, sizeof(uint32_t), s));
+    { int rc = launch_fill_u32(s, t->tile_list, 1, 0u); if (rc) return rc; }
     tile_list_kernel<<<(n_tiles + 8 * kTilesPerWarp - 1) / (8 * kTilesPerWarp), 256, 0, s>>>(a, t->tile_list + 1, t->tile_list);
   }
   if (phase == 1) {

@@ -166,6 +166,18 @@ __global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long l
 __global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
+__global__ void copy_u32x4_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n4, uint32_t* dst_tail, const uint32_t* src_tail, int n_tail) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+  if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+// device-to-device copy of n words by a kernel (16-byte accesses): a cudaMemcpyAsync would go through a copy engine
+int launch_copy_u32(cudaStream_t s, uint32_t* dst, const uint32_t* src, size_t n) {
+  if (n == 0) return VCT_OK;
+  const size_t n4 = n / 4;
+  copy_u32x4_kernel<<<grid_for(n4 ? n4 : 1, 256, 148 * 8), 256, 0, s>>>((uint4*)dst, (const uint4*)src, n4, dst + 4 * n4, src + 4 * n4, (int)(n - 4 * n4));
+  VCT_CUDA(cudaGetLastError());
+  return VCT_OK;
+}
 int launch_fill_u32(cudaStream_t s, uint32_t* p, size_t n, uint32_t v) {
   if (n == 0) return VCT_OK;
   fill_u32_kernel<<<grid_for(n), 256, 0, s>>>(p, n, v);

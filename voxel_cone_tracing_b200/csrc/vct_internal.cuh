@@ -279,6 +279,10 @@ struct vct_target_t_ {
   cudaStream_t copy_stream = nullptr;
   cudaEvent_t snap_ready[2] = {}, copy_done[2] = {};
   uint64_t n_async = 0;               // tickets issued
+  // a read-back whose device-to-host copy has not been enqueued yet: vct_render_frame starts it together with its cone kernel
+  uint32_t* pending_host = nullptr;
+  int pending_slot = 0;
+  cudaEvent_t copy_gate = nullptr;    // "the next frame's cone kernel is about to start"
 };
 
 struct vct_tex3d {
@@ -295,6 +299,7 @@ static inline unsigned grid_for(size_t n, unsigned threads = 256, unsigned cap =
 // ---- stage entry points implemented in the .cu files ------------------------------------
 namespace vct {
 int launch_sparse_clear(vct_device* dev, vct_grid* g);
+int launch_copy_u32(cudaStream_t s, uint32_t* dst, const uint32_t* src, size_t n);
 int ensure_tri_scratch(vct_device* dev, int which /* 0 voxelizer, 1 G-buffer */, size_t n_tris, size_t rec_bytes);
 int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1, const PeerView* push = nullptr);
 int launch_peer_wait(vct_device* dev, int kind, uint32_t epoch);

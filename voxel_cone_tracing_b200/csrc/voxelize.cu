@@ -401,7 +401,7 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
   dev->vox_owner = g;
   uint8_t* touched = (g->flags_valid && !push && !g->external) ? g->tile_touched : nullptr;
   if (!touched) g->flags_valid = false;
-  VCT_CUDA(cudaMemsetAsync(dev->counters, 0, 8 * sizeof(uint32_t), s));
+  { int rc2 = launch_fill_u32(s, dev->counters, 8, 0u); if (rc2) return rc2; }   // a kernel, not a memset: no copy-engine work on the frame's critical path
   const uint32_t n_blocks = (sc->n_tris + kSetupThreads - 1) / kSetupThreads;
   VoxTri* tris = (VoxTri*)dev->rs[0].tri_recs;
   const int sms = dev->prop.multiProcessorCount;
