@@ -45,10 +45,10 @@ static int ensure_capacity(T** p, size_t* cap, size_t n) {
 
 // Host -> device copy of `bytes` through pinned staging, asynchronous on the device stream.  The staging memory is a ring of
 // slots filled front to back; a slot is reused only after the event recorded behind its last copy has completed (normally
-// long ago), so per-frame scene updates do not serialise the host with the frames queued on the stream.
+// long ago), so per-frame scene updates do not serialise the host with the frames queued on the device.
 static int stage_upload(vct_scene* sc, void* dst, const void* src, size_t bytes) {
   if (bytes == 0) return VCT_OK;
-  cudaStream_t s = sc->dev->stream;
+  cudaStream_t s = sc->upload_stream;
   vct_scene::StageSlot* slot = &sc->stage[sc->stage_cur];
   const size_t need = (bytes + 255) & ~(size_t)255;
   if (slot->used + need > slot->cap) {
@@ -70,6 +70,38 @@ static int stage_upload(vct_scene* sc, void* dst, const void* src, size_t bytes)
   VCT_CUDA(cudaEventRecord(slot->done, s));
   slot->pending = true;
   slot->used += need;
+  return VCT_OK;
+}
+
+// Uploads `bytes` into the idle half of double buffer `which` on the upload stream and makes it the current half.
+static int upload_array(vct_scene* sc, int which, const void* src, size_t bytes, void** current) {
+  vct_scene::DBuf& d = sc->db[which];
+  const int nb = d.cur ^ 1;
+  if (bytes > d.cap_bytes[nb]) {
+    if (d.buf[nb]) cudaFree(d.buf[nb]);   // (cudaFree waits for the device: no queued frame can still read it)
+    d.buf[nb] = nullptr; d.cap_bytes[nb] = 0;
+    const size_t want = bytes + bytes / 4 + 256;
+    VCT_CUDA(cudaMalloc(&d.buf[nb], want));
+    d.cap_bytes[nb] = want;
+  }
+  // the idle half was read by the frames queued before it was retired: the copy waits for them, not for the frames queued since
+  if (d.retired[nb]) VCT_CUDA(cudaStreamWaitEvent(sc->upload_stream, d.retired[nb], 0));
+  int rc = stage_upload(sc, d.buf[nb], src, bytes);
+  if (rc) return rc;
+  if (!d.retired[d.cur]) VCT_CUDA(cudaEventCreateWithFlags(&d.retired[d.cur], cudaEventDisableTiming));
+  VCT_CUDA(cudaEventRecord(d.retired[d.cur], sc->dev->stream));   // everything queued so far may read the half being retired
+  d.cur = nb;
+  *current = d.buf[nb];
+  VCT_CUDA(cudaEventRecord(sc->uploaded, sc->upload_stream));
+  sc->upload_pending = true;
+  return VCT_OK;
+}
+
+// called by every entry point that launches kernels reading the scene: the frame stream waits for the uploads in flight
+int scene_ready(vct_scene* sc) {
+  if (!sc->upload_pending) return VCT_OK;
+  VCT_CUDA(cudaStreamWaitEvent(sc->dev->stream, sc->uploaded, 0));
+  sc->upload_pending = false;
   return VCT_OK;
 }
 
@@ -152,14 +184,25 @@ int vct_scene_create(vct_device_t* dev, vct_scene_t** out) {
   vct_scene* s = new (std::nothrow) vct_scene();
   if (!s) { set_error("out of host memory"); return VCT_ERR_OOM; }
   s->dev = dev;
+  if (cudaStreamCreateWithFlags(&s->upload_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&s->uploaded, cudaEventDisableTiming) != cudaSuccess) {
+    set_error("scene: stream/event creation failed");
+    delete s;
+    return VCT_ERR_CUDA;
+  }
   *out = s;
   return VCT_OK;
 }
 
 int vct_scene_destroy(vct_scene_t* s) {
   if (!s) return VCT_OK;
+  cudaStreamSynchronize(s->upload_stream);
   cudaStreamSynchronize(s->dev->stream);
-  cudaFree(s->verts); cudaFree(s->indices); cudaFree(s->mats); cudaFree(s->draws);
+  cudaStreamSynchronize(s->dev->stream2);
+  for (auto& d : s->db)
+    for (int i = 0; i < 2; i++) { cudaFree(d.buf[i]); if (d.retired[i]) cudaEventDestroy(d.retired[i]); }
+  cudaStreamDestroy(s->upload_stream);
+  cudaEventDestroy(s->uploaded);
   for (auto& slot : s->stage) {
     if (slot.buf) cudaFreeHost(slot.buf);
     if (slot.done) cudaEventDestroy(slot.done);
@@ -172,10 +215,8 @@ int vct_scene_set_geometry(vct_scene_t* s, const vct_vertex_t* verts, uint32_t n
   VCT_REQUIRE(s, "scene is null");
   VCT_REQUIRE((verts || !n_verts) && (indices || !n_indices), "null geometry");
   int rc;
-  if ((rc = ensure_capacity(&s->verts, &s->verts_cap, n_verts))) return rc;
-  if ((rc = ensure_capacity(&s->indices, &s->indices_cap, n_indices))) return rc;
-  if ((rc = stage_upload(s, s->verts, verts, (size_t)n_verts * sizeof(vct_vertex_t)))) return rc;
-  if ((rc = stage_upload(s, s->indices, indices, (size_t)n_indices * sizeof(uint32_t)))) return rc;
+  if ((rc = upload_array(s, vct_scene::DB_VERTS, verts, (size_t)n_verts * sizeof(vct_vertex_t), (void**)&s->verts))) return rc;
+  if ((rc = upload_array(s, vct_scene::DB_INDICES, indices, (size_t)n_indices * sizeof(uint32_t), (void**)&s->indices))) return rc;
   s->n_verts = n_verts; s->n_indices = n_indices;
   return VCT_OK;
 }
@@ -183,8 +224,7 @@ int vct_scene_set_geometry(vct_scene_t* s, const vct_vertex_t* verts, uint32_t n
 int vct_scene_set_materials(vct_scene_t* s, const vct_material_t* mats, uint32_t n) {
   VCT_REQUIRE(s && (mats || !n), "null argument");
   int rc;
-  if ((rc = ensure_capacity(&s->mats, &s->mats_cap, n))) return rc;
-  if ((rc = stage_upload(s, s->mats, mats, (size_t)n * sizeof(vct_material_t)))) return rc;
+  if ((rc = upload_array(s, vct_scene::DB_MATS, mats, (size_t)n * sizeof(vct_material_t), (void**)&s->mats))) return rc;
   s->n_mats = n;
   return VCT_OK;
 }
@@ -206,8 +246,7 @@ int vct_scene_set_draws(vct_scene_t* s, const vct_draw_t* draws, uint32_t n) {
     tri += d.index_count / 3;
   }
   int rc;
-  if ((rc = ensure_capacity(&s->draws, &s->draws_cap, n))) return rc;
-  if ((rc = stage_upload(s, s->draws, recs.data(), (size_t)n * sizeof(DrawRec)))) return rc;
+  if ((rc = upload_array(s, vct_scene::DB_DRAWS, recs.data(), (size_t)n * sizeof(DrawRec), (void**)&s->draws))) return rc;
   s->n_draws = n;
   s->n_tris = tri;
   return VCT_OK;
@@ -576,6 +615,7 @@ int vct_voxelize_reserve(vct_device_t* dev, uint64_t max_fragments) {
 int vct_voxelize(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, int z0, int z1) {
   VCT_REQUIRE(dev && sc && g, "null argument");
   VCT_REQUIRE(z0 >= 0 && z1 <= g->R && z0 <= z1, "bad z slab");
+  if (int rc = scene_ready(sc)) return rc;
   return launch_voxelize(dev, sc, g, z0, z1);
 }
 
@@ -606,18 +646,22 @@ int vct_mipmap(vct_device_t* dev, vct_grid_t* g) {
 
 int vct_gbuffer(vct_device_t* dev, vct_scene_t* sc, const float view[16], const float proj[16], vct_target_t* t) {
   VCT_REQUIRE(dev && sc && view && proj && t, "null argument");
+  if (int rc = scene_ready(sc)) return rc;
   return launch_gbuffer(dev, sc, view, proj, t);
 }
 
 int vct_cone_trace(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, const float view[16], const vct_trace_params_t* p, vct_target_t* t) {
   VCT_REQUIRE(dev && sc && g && view && p && t, "null argument");
+  if (int rc = scene_ready(sc)) return rc;
   return launch_cone_trace(dev, sc, g, view, p, t, false);
 }
 
 int vct_cone_trace_count(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, const float view[16], const vct_trace_params_t* p, vct_target_t* t,
                          vct_trace_stats_t* out) {
   VCT_REQUIRE(dev && sc && g && view && p && t && out, "null argument");
-  int rc = launch_cone_trace(dev, sc, g, view, p, t, true);
+  int rc = scene_ready(sc);
+  if (rc) return rc;
+  rc = launch_cone_trace(dev, sc, g, view, p, t, true);
   if (rc) return rc;
   unsigned long long h[8];
   VCT_CUDA(cudaMemcpyAsync(h, dev->counters + 16, sizeof h, cudaMemcpyDeviceToHost, dev->stream));
@@ -670,6 +714,7 @@ static int render_frame_sharded(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* 
 int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_target_t* t, const float view[16], const float proj[16],
                      const vct_trace_params_t* p) {
   VCT_REQUIRE(dev && sc && g && t && view && proj && p, "null argument");
+  if (int rc0 = scene_ready(sc)) return rc0;   // the frame stream waits for the scene uploads in flight (they run on their own stream)
   if (dev->peers.nranks > 1 && dev->peer_grid == g && dev->peer_target == t) return render_frame_sharded(dev, sc, g, t, view, proj, p);
   cudaStream_t s = dev->stream;
   int rc;

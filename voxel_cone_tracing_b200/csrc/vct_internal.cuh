@@ -203,10 +203,21 @@ enum { CNT_ITEMS = 0, CNT_FRAGS = 1, CNT_OCCUPIED = 2, CNT_MAXLIST = 3, CNT_CAM_
 
 struct vct_scene {
   vct_device* dev = nullptr;
-  vct_vertex_t* verts = nullptr;  uint32_t n_verts = 0;   size_t verts_cap = 0;
-  uint32_t* indices = nullptr;    uint32_t n_indices = 0; size_t indices_cap = 0;
-  vct_material_t* mats = nullptr; uint32_t n_mats = 0;    size_t mats_cap = 0;
-  vct::DrawRec* draws = nullptr;  uint32_t n_draws = 0;   size_t draws_cap = 0;
+  // the arrays the kernels read (= the current halves of the double buffers below)
+  vct_vertex_t* verts = nullptr;  uint32_t n_verts = 0;
+  uint32_t* indices = nullptr;    uint32_t n_indices = 0;
+  vct_material_t* mats = nullptr; uint32_t n_mats = 0;
+  vct::DrawRec* draws = nullptr;  uint32_t n_draws = 0;
+  // Every array is double buffered and uploaded on its own stream: vct_scene_set_* writes the half that no queued frame reads
+  // (it waits for the event recorded when that half was retired) and flips, so the host-to-device copies of frame i+1 run while
+  // frame i renders instead of at the head of frame i+1 (54 us per frame in bench.py's end-to-end loop).  The frame stream
+  // waits for `uploaded` before its next use of the scene (scene_ready()).
+  struct DBuf { void* buf[2] = {}; size_t cap_bytes[2] = {}; int cur = 0; cudaEvent_t retired[2] = {}; };
+  enum { DB_VERTS = 0, DB_INDICES = 1, DB_MATS = 2, DB_DRAWS = 3, DB_COUNT = 4 };
+  DBuf db[DB_COUNT];
+  cudaStream_t upload_stream = nullptr;
+  cudaEvent_t uploaded = nullptr;
+  bool upload_pending = false;
   uint32_t n_tris = 0;
   vct::Lights lights{};
   float cube_size = 1.0f;
@@ -299,6 +310,7 @@ static inline unsigned grid_for(size_t n, unsigned threads = 256, unsigned cap =
 // ---- stage entry points implemented in the .cu files ------------------------------------
 namespace vct {
 int launch_sparse_clear(vct_device* dev, vct_grid* g);
+int scene_ready(vct_scene* sc);
 int launch_copy_u32(cudaStream_t s, uint32_t* dst, const uint32_t* src, size_t n);
 int ensure_tri_scratch(vct_device* dev, int which /* 0 voxelizer, 1 G-buffer */, size_t n_tris, size_t rec_bytes);
 int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1, const PeerView* push = nullptr);
