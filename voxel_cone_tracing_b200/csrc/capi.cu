@@ -693,21 +693,33 @@ static int render_frame_sharded(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* 
   prm.tile_rank = pv.rank; prm.tile_nranks = pv.nranks;
   int rc;
   VCT_CUDA(cudaEventRecord(dev->ev[0], s));
+  VCT_CUDA(cudaEventRecord(dev->ev_fork, s));
   VCT_CUDA(cudaMemsetAsync(g->base_buf[b ^ 1], 0, (size_t)g->R * g->R * g->R * 4, s));   // clear the NEXT frame's buffer
   VCT_CUDA(cudaEventRecord(dev->ev[1], s));
   if ((rc = launch_voxelize(dev, sc, g, z0, z1, &pv))) return rc;   // + push of the slab to the peers
   VCT_CUDA(cudaEventRecord(dev->ev[2], s));
+  // visibility of this rank's tiles + their live-tile list on the second stream, beside the voxelization, the wait for the peers' slabs
+  // and the mip build (as in the single-GPU frame)
+  VCT_CUDA(cudaStreamWaitEvent(dev->stream2, dev->ev_fork, 0));
+  dev->stream = dev->stream2;
+  VCT_CUDA(cudaEventRecord(dev->ev_g0, dev->stream2));
+  rc = launch_gbuffer(dev, sc, view, proj, t, pv.rank, pv.nranks);
+  if (!rc) rc = launch_cone_trace(dev, sc, g, view, &prm, t, false, &pv, 1);
+  dev->stream = s;
+  if (rc) return rc;
+  VCT_CUDA(cudaEventRecord(dev->ev_g1, dev->stream2));
+  VCT_CUDA(cudaEventRecord(dev->ev_join, dev->stream2));
   if ((rc = launch_peer_wait(dev, PEER_FLAG_PUSHED, epoch))) return rc;                     // every slab has arrived
   if ((rc = launch_mipmap(dev, g))) return rc;
   VCT_CUDA(cudaEventRecord(dev->ev[3], s));
-  if ((rc = launch_gbuffer(dev, sc, view, proj, t, pv.rank, pv.nranks))) return rc;                // visibility of this rank's tiles only
+  VCT_CUDA(cudaStreamWaitEvent(s, dev->ev_join, 0));
   VCT_CUDA(cudaEventRecord(dev->ev[4], s));
-  if ((rc = launch_cone_trace(dev, sc, g, view, &prm, t, false, &pv))) return rc;            // + push of the tiles to the root
+  if ((rc = launch_cone_trace(dev, sc, g, view, &prm, t, false, &pv, 2))) return rc;         // + push of the tiles to the root
   if (pv.frame_root < 0 || pv.frame_root == pv.rank)
     if ((rc = launch_peer_wait(dev, PEER_FLAG_FRAME, epoch))) return rc;                    // every tile has arrived
   VCT_CUDA(cudaEventRecord(dev->ev[5], s));
   dev->have_timings = true;
-  dev->gbuffer_overlapped = false;
+  dev->gbuffer_overlapped = true;
   return VCT_OK;
 }
 
