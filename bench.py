@@ -41,12 +41,12 @@ CONFIGS = {
     5: dict(name="synthetic 4M triangles 1024^3 7680x4320 (RGBA8, 7 levels; 16 diffuse cones: BASELINE config 5's cone variant)", R=1024, W=7680, H=4320,
             scene="synthetic", tris=4_000_000, seed=0x5EED0002, cones=16),
 }
-KERNELS_PER_FRAME = 13  # clear 1 (sparse: the previous frame's occupied voxels) + voxelize 3 (setup+scan, raster, resolve) + mip 2 (fused low; tail = levels 4-6 + occupancy + dilation) + gbuffer 4 (clear, setup+scan, raster, resolve) + trace 3 (tile list, cones, shade)
-# ncu --set full capture of cone_kernel_fast on this workload (profiles/r01_cone_kernel_ncu_s7.md), per launch:
+KERNELS_PER_FRAME = 15  # clear 1 (sparse: the previous frame's occupied voxels) + voxelize 4 (counter reset, setup+scan, raster, resolve) + mip 2 (fused low; tail = levels 4-6 + occupancy + dilation) + gbuffer 4 (clear, setup+scan, raster, resolve) + trace 4 (list reset, tile list, cones, shade)
+# ncu --set full capture of cone_kernel_fast on this workload (profiles/r01_ncu_s7.md), per launch:
 # dram__bytes_read.sum + dram__bytes_write.sum, and the two units that bind the kernel
-CONE_KERNEL_DRAM_TRAFFIC = {1: 28.3e6 + 31.4e6}
-CONE_KERNEL_NCU = {"tex_wavefront_frac": 0.755, "issue_frac": 0.651, "tex_wavefronts_per_launch": 192.4e6, "warp_instructions_per_launch": 639.6e6,
-                   "l1tex_sectors_per_launch": 649.9e6, "source": "profiles/r01_cone_kernel_ncu_s7.md (ncu --set full, one launch of this command)"}
+CONE_KERNEL_DRAM_TRAFFIC = {1: 24.6e6 + 10.4e6}
+CONE_KERNEL_NCU = {"tex_wavefront_frac": 0.764, "issue_frac": 0.662, "tex_wavefronts_per_launch": 192.4e6, "warp_instructions_per_launch": 643.4e6,
+                   "l1tex_sectors_per_launch": 649.9e6, "source": "profiles/r01_ncu_s7.md (ncu --set full, one launch of this command)"}
 
 
 def build_scene(cfg, frame: int = 0):
@@ -341,9 +341,9 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
                 "gsamples_per_s": cnt.samples / t_trace / 1e9,
                 "binding_units": CONE_KERNEL_NCU if (args.config == 2 and args.sampler == 1) else None,
                 "note": "algorithmic gather bytes (192 B per sample_voxel: 3 directions x 2 levels x 8 texels x 4 B) / CUDA-event kernel time. The gathers are "
-                        "served by the texture units / L1 (20.8 GB of L1TEX sectors per launch, 99 % hit) and the 126 MB L2, DRAM traffic is 0.06 GB per launch, "
-                        "so frac > 1 against the HBM copy peak is expected; the kernel is bound by the TEX pipe (75 % of one wavefront/clk/SM) and the "
-                        "issue slots (65 %), see binding_units and DESIGN.md 3.3"}
+                        "served by the texture units / L1 (20.8 GB of L1TEX sectors per launch, 99 % hit) and the 126 MB L2, DRAM traffic is 0.035 GB per launch, "
+                        "so frac > 1 against the HBM copy peak is expected; the kernel is bound by the TEX pipe (76 % of one wavefront/clk/SM) and the "
+                        "issue slots (66 %), see binding_units and DESIGN.md 3.3"}
         mip_bytes = 7.4286 * R ** 3
         stages = {k + "_us": v * 1e3 for k, v in stage_acc.items()}
         stages["mip_roofline"] = {"bound": "hbm", "achieved": mip_bytes / (stage_acc["mipmap"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
