@@ -35,7 +35,7 @@ def run(name, upload, readback):
     dt = time.perf_counter() - t0
     print(f"{name:40s} {1e3*dt/N:.3f} ms/frame   host enqueue time {1e3*cpu/N:.3f} ms/frame", flush=True)
 
-mode = os.environ.get("VCT_ASYNC_MODE", "0")
+mode = "-"
 run(f"[mode {mode}] render only", False, None)
 run(f"[mode {mode}] render + async readback", False, "async")
 run(f"[mode {mode}] upload + render + async readback", True, "async")

@@ -61,7 +61,6 @@ struct TraceArgs {
   vct_trace_params_t prm;
   unsigned long long* counts;  // [4] diffuse, shadow, specular, refraction (+[4] shaded pixels)
   int n_diffuse, n_slots;
-  int quad2x2;                 // lane -> pixel mapping of cone_kernel_fast
   int grouped;                 // cone_out layout: 0 = [slot][pixel]; 1 = [job][pixel] with job 0 = SUM of the diffuse cones, 1 specular, 2 refraction, 3 + i shadow of light i
   const uint32_t* tile_list;   // live 8x4 tiles (tile_y * tiles_x + tile_x), built by tile_list_kernel
   uint32_t* tile_count;
@@ -627,7 +626,7 @@ cone_kernel_fast(const TraceArgs a) {
   const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
   // lane -> pixel of the 8x4 tile: four consecutive lanes (one TEX quad) are a 2x2 pixel block, not a 4x1 row: the pixels of a quad then
   // agree more often on which fetch a sample needs, and the texture unit works on whole quads
-  const int lx = a.quad2x2 ? ((lane & 1) | ((lane >> 1) & 6)) : (lane & 7), ly = a.quad2x2 ? (((lane >> 1) & 1) | ((lane >> 3) & 2)) : (lane >> 3);
+  const int lx = (lane & 1) | ((lane >> 1) & 6), ly = ((lane >> 1) & 1) | ((lane >> 3) & 2);
   const Pixel p = load_pixel(a, tile_x * 8 + lx, tile_y * 4 + ly);
   if (!p.live) return;
   float r[4];
@@ -826,7 +825,6 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
   // (and the fp32 software sampler, 72 registers, spills in the grouped form: 3.7 -> 4.6 ms at 1080p)
   if (!ev && (n_tiles / a.prm.tile_nranks < 32768 || !tex)) variant = 2;
   a.grouped = (!count_samples && variant >= 3) ? 1 : 0;
-  { const char* q = getenv("VCT_QUAD"); a.quad2x2 = q ? atoi(q) : 1; }
   // cone result buffer [slot or job][pixel] and the live-tile list, grown on demand
   const size_t need = (size_t)(a.grouped ? 3 + sc->lights.n : a.n_slots) * a.npix;
   if (need > t->cone_out_elems) {
