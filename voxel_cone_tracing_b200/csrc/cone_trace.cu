@@ -2,20 +2,27 @@
 //
 // Replaces shader/voxel_cone_tracing.frag (src/renderer.cpp:355-390 binds it).  Not a port of the
 // fragment shader's one-thread-per-fragment loop.  Three launches:
-//   tile_list_kernel   compacts the 8x4 screen tiles that contain at least one shaded pixel
-//   cone_kernel        ONE WARP = one live tile x one cone slot (9 diffuse, 1 specular, 1 refraction,
-//                      1 shadow per light): all 32 lanes march the same cone of neighbouring pixels
-//                      (same aperture, near-identical direction and LOD sequence -> coherent texel
-//                      gathers, no divergence between cone types).  Warps are independent (no barrier),
-//                      long cones (shadow) are scheduled first, results go to a [slot][pixel] buffer.
+//   tile_list_kernel   compacts the 8x4 screen tiles that contain at least one shaded pixel (on the G-buffer stream)
+//   cone_kernel_fast   ONE WARP = one live tile x one job: all 32 lanes march the same cone of neighbouring pixels
+//                      (same aperture, same step and LOD sequence -> coherent fetches, no divergence between cone
+//                      types; four consecutive lanes = a 2x2 pixel block = one TEX quad).  Jobs: every cone slot on its
+//                      own (9 diffuse, 1 specular, 1 refraction, 1 shadow per light), or -- frames with >= 32 k tiles
+//                      per GPU -- all diffuse cones of the tile in one warp, which stores their sum.  Warps are
+//                      independent (no barrier), the long jobs are scheduled first, results go to a [job][pixel] buffer.
 //   shade_kernel       per pixel: Blinn-Phong / mix of main() (voxel_cone_tracing.frag:246-275).
 //
-// Texture sampling is done in software with fp32 weights (rule R7 of the oracle): textureLod =
-// trilinear in floor(lod) and floor(lod)+1, CLAMP_TO_BORDER with a zero border.  Result-preserving
-// savings over the literal shader: level 0 is fetched once for the three directions (all six level-0
-// textures are identical), the second level is skipped when the LOD fraction is exactly 0, footprints
-// wholly outside the grid are skipped, and a cone stops as soon as it has left the (border-padded)
-// cube for good -- every skipped term is exactly zero in the reference.
+// textureLod has two evaluators (vct_trace_params_t.sampler):
+//   VCT_SAMPLER_TEX    levels >= 1 through the texture units from ONE mipmapped array that stacks the six directional
+//                      volumes along z (GridView in vct_internal.cuh), level 0 in software (shared by the three
+//                      directions).  The benchmarked path; frame within 2/255, PSNR > 64 dB of the oracle.
+//   VCT_SAMPLER_FP32   software trilinear + mip-linear with fp32 weights from the 24-byte records (rule R7 of the
+//                      oracle exactly): trilinear in floor(lod) and floor(lod)+1, CLAMP_TO_BORDER with a zero border.
+// Result-preserving savings over the literal shader (every skipped term is exactly zero in the reference): level 0 is
+// fetched once for the three directions (all six level-0 textures are identical), a level whose filter footprint is empty
+// (dilated occupancy bits) or wholly outside the grid is skipped, a direction of weight 0 is skipped, a fetch that needs one
+// level goes through the nearest-mip texture object, and a cone stops once it has left the border-padded cube for good.
+// cone_kernel<COUNT, TEX> is the literal loop (VCT_CONE_VARIANT=0, and the instrumented sample counter);
+// cone_kernel_fast is the production march.  profiles/r01_ncu_s7.md, r01_cone_experiments_s7.txt: what binds it.
 // FMA contraction is allowed here: the frame is compared against the oracle with a tolerance
 // (max abs 2/255, PSNR >= 45 dB), not bit for bit.
 #include "vct_internal.cuh"

@@ -3,12 +3,20 @@
 // Replaces Renderer::filter() (src/renderer.cpp:283-314) + shader/mipmap.comp.  The reference
 // dispatches one compute pass per level, each re-reading six full textures (and launching 8x more
 // threads than texels).  Here the chain is built in TWO launches for the reference's 7 levels:
-//   mip_fused_low_kernel   one CTA per 32x8x8 tile of level 0 staged in shared memory
-//                          -> levels 1, 2, 3 for all six directions (level 0 is read ONCE, not 6x)
-//   mip_fused_high_kernel  one CTA per 8x8x8 tile of level 3 -> levels 4, 5, 6
-// so the DRAM traffic is the algorithmic minimum 4*R^3 (read) + 24*R^3*(1/8+1/64+...) (write).
-// Levels >= 1 are stored as records of six RGBA8 words per texel (direction-minor), the layout the
-// cone tracer gathers from.  All-zero child groups are skipped (exact: the filter of zeros is zero).
+//   mip_fused_low_kernel   persistent CTAs stream 32x8x8 tiles of level 0 through a 4-stage TMA ring
+//                          (cp.async.bulk.tensor.3d + mbarrier) -> levels 1, 2, 3 of all six directions
+//                          and the occupancy bits of levels 0-2 (level 0 is read ONCE, not 6x).  Per
+//                          round a CTA first compacts the tiles it has to read: with the voxelizer's
+//                          tile flags, untouched tiles whose outputs are already zero are skipped.
+//   mip_tail_kernel        one launch for everything that depends on the low kernel only: 8x8x8 tiles of
+//                          level 3 -> levels 4, 5, 6; occupancy bits of the small levels; 2x2x2 dilation
+//                          of the occupancy bits of every level
+// so the dense DRAM traffic is the algorithmic minimum 4*R^3 (read) + 24*R^3*(1/8+1/64+...) (write), and
+// the traffic of a running frame loop is proportional to the occupied tiles.
+// Levels >= 1 are stored twice: records of six RGBA8 words per texel (direction-minor; software sampler,
+// next mip level, downloads) and the stacked mipmapped array the texture units read (surface writes).
+// All-zero child groups are skipped (exact: the filter of zeros is zero); mip_generic_kernel /
+// occ_*_kernel cover grids the fused kernels do not (R < 32, fewer than 4 levels, more than 7).
 //
 // Arithmetic = oracle rules R5/R6 (built with -fmad=false): c/255.0f correctly rounded (multiply
 // by 1/255 plus one exact Newton step, verified for all 256 inputs), blend f + (1-f.a)*b per

@@ -13,6 +13,10 @@
 //                         order key (draw, triangle, row, column) and folds them with the reference's
 //                         RGBA8 running average (voxelize.frag:95-120) -> deterministic and bit-exact
 //                         against the sequential oracle, which the CAS loop of the reference is not.
+//                         Also marks the 32x8x8 tile of the voxel (sparse mip build) and, multi-GPU, stores
+//                         the voxel into every peer's grid over NVLink.
+//   sparse_clear_kernel   vct_grid_clear in a frame loop: zeroes the voxels of the previous frame's
+//                         occupied list instead of the whole level.
 // Built with -fmad=false: the arithmetic (IEEE add/mul/div/sqrt only, fixed evaluation order) is the
 // same as the oracle's so that voxel occupancy AND colour match bit for bit.
 #include "raster.cuh"
