@@ -10,7 +10,8 @@ for (R, W, H, suz) in cfgs:
     view, proj = S.reference_camera(W / H)
     p = capi.Pipeline(sc, R, W, H)
     for sampler in (1, 0):
-        prm = capi.default_params(sampler=sampler)
+        nr = int(os.environ.get("TILE_NRANKS", "1"))   # emulate one rank of an N-GPU tile split on one GPU
+        prm = capi.default_params(sampler=sampler, tile_rank=0, tile_nranks=nr)
         for _ in range(3):
             p.render_frame(view, proj, prm)
         p.sync()

@@ -68,6 +68,8 @@ struct TraceArgs {
   vct_trace_params_t prm;
   unsigned long long* counts;  // [4] diffuse, shadow, specular, refraction (+[4] shaded pixels)
   int n_diffuse, n_slots;
+  int n_jobs;                  // work items per live tile of cone_kernel_fast
+  uint32_t* work_counter;      // next (job, tile) item of the persistent cone kernel; zeroed by tile_list_kernel
   int grouped;                 // cone_out layout: 0 = [slot][pixel]; 1 = [job][pixel] with job 0 = SUM of the diffuse cones, 1 specular, 2 refraction, 3 + i shadow of light i
   const uint32_t* tile_list;   // live 8x4 tiles (tile_y * tiles_x + tile_x), built by tile_list_kernel
   uint32_t* tile_count;
@@ -475,6 +477,7 @@ constexpr int kTilesPerWarp = 4;
 __global__ void __launch_bounds__(256)
 tile_list_kernel(const TraceArgs a, uint32_t* __restrict__ tile_list, uint32_t* __restrict__ tile_count) {
   const int lane = threadIdx.x & 31;
+  if (blockIdx.x == 0 && threadIdx.x == 0) *a.work_counter = 0u;   // the cone kernel of this frame starts at item 0
   const int tiles_x = (a.W + 7) / 8, tiles_y = (a.H + 3) / 4, n_tiles = tiles_x * tiles_y;
   const int first = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kTilesPerWarp;
   if (first >= n_tiles) return;
@@ -622,12 +625,9 @@ __device__ __forceinline__ bool cone_setup(const TraceArgs& a, const Pixel& p, i
 // trace_diffuse does): the G-buffer fetch and the tangent frame are paid once instead of nine times (12 % of the kernel's
 // instructions) and the cone-result buffer shrinks from 12 to 4 float4 per pixel (142 -> 47 MB written here and read by shade_kernel
 // at 1080p).  The long job (blockIdx.y = 0) is scheduled first.
-template <bool TEX, bool SPLIT, int MIN_CTAS, bool GROUP>
-__global__ void __launch_bounds__(32 * kConeWarps, MIN_CTAS)
-cone_kernel_fast(const TraceArgs a) {
-  const int lane = threadIdx.x & 31;
-  const uint32_t t = blockIdx.x * kConeWarps + (threadIdx.x >> 5);
-  if (t >= *a.tile_count) return;
+// one work item of the production march: job `job` of live tile `t` (all 32 lanes of a warp)
+template <bool TEX, bool SPLIT, bool GROUP>
+__device__ __forceinline__ void cone_work_item(const TraceArgs& a, uint32_t t, int job, int lane) {
   const uint32_t tile = a.tile_list[t];
   const int tiles_x = (a.W + 7) / 8;
   const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
@@ -638,7 +638,6 @@ cone_kernel_fast(const TraceArgs a) {
   if (!p.live) return;
   float r[4];
   if (GROUP) {
-    const int job = (int)blockIdx.y;
     if (job == 0) {
       float sum[3] = {0.f, 0.f, 0.f};
       if (a.prm.enable_diffuse) {
@@ -659,14 +658,46 @@ cone_kernel_fast(const TraceArgs a) {
     trace_cone_fast<TEX, SPLIT>(a.grid, on, p.pos, d, aperture, max_dist, r);
     a.cone_out[(size_t)job * a.npix + p.pix] = make_float4(r[0], r[1], r[2], r[3]);
   } else {
-    // long cones first: blockIdx.y = 0 is the last slot (shadow cones, up to ~5x more steps than diffuse)
-    const int slot = a.n_slots - 1 - (int)blockIdx.y;
+    // long cones first: job 0 is the last slot (shadow cones, up to ~5x more steps than diffuse)
+    const int slot = a.n_slots - 1 - job;
     F3 d = f3(0.f, 0.f, 1.f);
     float aperture = kTan22_5, max_dist = 0.f;
     const bool on = cone_setup(a, p, slot, d, aperture, max_dist);
     trace_cone_fast<TEX, SPLIT>(a.grid, on, p.pos, d, aperture, max_dist, r);
     a.cone_out[(size_t)slot * a.npix + p.pix] = make_float4(r[0], r[1], r[2], r[3]);
   }
+}
+
+// GROUP: one warp marches ALL diffuse cones of its tile one after the other and stores their sum (added in slot order, as
+// trace_diffuse does): the G-buffer fetch and the tangent frame are paid once instead of nine times (12 % of the kernel's
+// instructions) and the cone-result buffer shrinks from 12 to 4 float4 per pixel (142 -> 47 MB written here and read by shade_kernel
+// at 1080p).
+// PERSISTENT kernel: MIN_CTAS CTAs per SM stay resident and their warps take (job, tile) items from a global counter, job-major so
+// that the long jobs start first.  The number of live tiles is only known on the device: a grid sized for every tile of the frame
+// launches mostly empty CTAs (63 % at 1080p on one GPU, 95 % on eight), and dynamic items leave no tail of half-empty CTAs.
+template <bool TEX, bool SPLIT, int MIN_CTAS, bool GROUP>
+__global__ void __launch_bounds__(32 * kConeWarps, MIN_CTAS)
+cone_kernel_fast(const TraceArgs a) {
+  const int lane = threadIdx.x & 31;
+  const uint32_t n_live = *a.tile_count;
+  const uint32_t total = n_live * (uint32_t)a.n_jobs;
+  for (;;) {
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(a.work_counter, 1u);
+    item = __shfl_sync(0xffffffffu, item, 0);
+    if (item >= total) break;
+    const uint32_t job = item / n_live;
+    cone_work_item<TEX, SPLIT, GROUP>(a, item - job * n_live, (int)job, lane);
+  }
+}
+
+// the same items with one warp per (tile of the frame, job) of a grid sized on the host (VCT_CONE_PERSIST=0)
+template <bool TEX, bool SPLIT, int MIN_CTAS, bool GROUP>
+__global__ void __launch_bounds__(32 * kConeWarps, MIN_CTAS)
+cone_kernel_grid(const TraceArgs a) {
+  const uint32_t t = blockIdx.x * kConeWarps + (threadIdx.x >> 5);
+  if (t >= *a.tile_count) return;
+  cone_work_item<TEX, SPLIT, GROUP>(a, t, (int)blockIdx.y, threadIdx.x & 31);
 }
 
 // main() (voxel_cone_tracing.frag:246-275) for one pixel
@@ -820,6 +851,8 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
   a.n_diffuse = p->n_diffuse_cones == 5 ? 5 : (p->n_diffuse_cones == 16 ? 16 : 9);
   a.n_slots = a.n_diffuse + 2 + sc->lights.n;
   a.grouped = 0;
+  a.n_jobs = a.n_slots;
+  a.work_counter = dev->counters + CNT_CONE_WORK;
   a.npix = (size_t)t->W * t->H;
   const int n_tiles = ((t->W + 7) / 8) * ((t->H + 3) / 4);
   // which march: 3 = production (one-level fetches through the nearest-mip texture object, all diffuse cones of a tile in one warp), 2 = one
@@ -867,21 +900,25 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
     } else if (variant == 0) {
       if (tex) cone_kernel<false, true><<<grid, 32 * kConeWarps, 0, s>>>(a);
       else cone_kernel<false, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
-    } else if (variant == 1) {
-      if (tex) cone_kernel_fast<true, false, 9, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
-      else cone_kernel_fast<false, false, 7, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
-    } else if (variant == 2) {
-      if (tex) cone_kernel_fast<true, true, 10, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
-      else cone_kernel_fast<false, false, 7, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
-    } else if (variant == 5) {
-      if (tex) cone_kernel_fast<true, true, 8, true><<<grid_jobs, 32 * kConeWarps, 0, s>>>(a);
-      else cone_kernel_fast<false, false, 7, true><<<grid_jobs, 32 * kConeWarps, 0, s>>>(a);
-    } else if (variant == 4) {
-      if (tex) cone_kernel_fast<true, true, 9, true><<<grid_jobs, 32 * kConeWarps, 0, s>>>(a);
-      else cone_kernel_fast<false, false, 7, true><<<grid_jobs, 32 * kConeWarps, 0, s>>>(a);
     } else {
-      if (tex) cone_kernel_fast<true, true, 10, true><<<grid_jobs, 32 * kConeWarps, 0, s>>>(a);
-      else cone_kernel_fast<false, false, 7, true><<<grid_jobs, 32 * kConeWarps, 0, s>>>(a);
+      const char* pe = getenv("VCT_CONE_PERSIST");
+      const bool persist = !(pe && pe[0] == '0');
+      const int sms = dev->prop.multiProcessorCount;
+      a.n_jobs = a.grouped ? (int)grid_jobs.y : a.n_slots;
+      // launch K<TEX, SPLIT, MIN_CTAS, GROUP>: persistent (MIN_CTAS CTAs per SM) or one warp per (tile, job) of the whole frame
+#define VCT_LAUNCH_CONE(TEXV, SPLITV, MINC, GROUPV)                                                                   \
+  do {                                                                                                                \
+    if (persist) cone_kernel_fast<TEXV, SPLITV, MINC, GROUPV><<<sms * MINC, 32 * kConeWarps, 0, s>>>(a);              \
+    else cone_kernel_grid<TEXV, SPLITV, MINC, GROUPV><<<GROUPV ? grid_jobs : grid, 32 * kConeWarps, 0, s>>>(a);       \
+  } while (0)
+      if (variant == 1) {
+        if (tex) VCT_LAUNCH_CONE(true, false, 9, false); else VCT_LAUNCH_CONE(false, false, 7, false);
+      } else if (variant == 2) {
+        if (tex) VCT_LAUNCH_CONE(true, true, 10, false); else VCT_LAUNCH_CONE(false, false, 7, false);
+      } else {
+        if (tex) VCT_LAUNCH_CONE(true, true, 10, true); else VCT_LAUNCH_CONE(false, false, 7, true);
+      }
+#undef VCT_LAUNCH_CONE
     }
     VCT_CUDA(cudaEventRecord(dev->ev[7], s));
   }

@@ -199,7 +199,7 @@ struct vct_device {
   vct_target_t_* peer_target = nullptr;
   uint32_t peer_epoch = 0;             // frames rendered since vct_peer_connect
 };
-enum { CNT_ITEMS = 0, CNT_FRAGS = 1, CNT_OCCUPIED = 2, CNT_MAXLIST = 3, CNT_CAM_ITEMS = 12 /* outside the words the voxelizer clears every frame */, CNT_TICKET_VOX = 13, CNT_TICKET_CAM = 14 /* last-block tickets of the setup kernels */, CNT_SAMPLES = 16 /* ..31, as 8 x u64 */, CNT_TOTAL = 32 };
+enum { CNT_ITEMS = 0, CNT_FRAGS = 1, CNT_OCCUPIED = 2, CNT_MAXLIST = 3, CNT_CAM_ITEMS = 12 /* outside the words the voxelizer clears every frame */, CNT_TICKET_VOX = 13, CNT_TICKET_CAM = 14 /* last-block tickets of the setup kernels */, CNT_CONE_WORK = 15 /* next item of the persistent cone kernel */, CNT_SAMPLES = 16 /* ..31, as 8 x u64 */, CNT_TOTAL = 32 };
 
 struct vct_scene {
   vct_device* dev = nullptr;
