@@ -424,6 +424,29 @@ def test_sparse_frame_sequence_matches_fresh_builds():
     p.close()
 
 
+def test_two_grids_share_one_device(dev):
+    """the occupied-voxel list lives on the device: a grid may clear sparsely only if the list is still its own.  Two grids of
+    different resolution voxelized alternately on one device must each match a fresh oracle build every time"""
+    sc_a, sc_b = S.cornell_scene(with_suzanne=True, theta=0.2), S.cornell_scene(with_suzanne=True, theta=1.4)
+    ds_a, ds_b = capi.DeviceScene(dev, sc_a), capi.DeviceScene(dev, sc_b)
+    g1, g2 = capi.Grid(dev, 64, 7), capi.Grid(dev, 32, 6)
+    L = dev.L
+
+    def vox(ds, g):
+        g.clear()
+        capi.check(L.vct_voxelize(dev.h, ds.h, g.h, 0, g.R))
+        capi.check(L.vct_mipmap(dev.h, g.h))
+
+    exp = {(id(ds), g.R): orc.voxelize(sc, g.R)[0] for ds, sc in ((ds_a, sc_a), (ds_b, sc_b)) for g in (g1, g2)}
+    for ds, g in ((ds_a, g1), (ds_b, g2), (ds_b, g1), (ds_a, g2), (ds_a, g1), (ds_a, g1), (ds_b, g2)):
+        vox(ds, g)
+        base = exp[(id(ds), g.R)]
+        assert np.array_equal(g.download(0), base)
+        assert_pyramid_equal(g, orc.mipmap(base, g.levels))
+    for o in (g1, g2, ds_a, ds_b):
+        o.close()
+
+
 def test_tile_split_equals_full_frame():
     sc = S.cornell_scene(with_suzanne=True)
     R, W, H = 64, 320, 200
