@@ -159,7 +159,7 @@ int vct_device_destroy(vct_device_t* d) {
   vct_peer_disconnect(d);
   cudaStreamSynchronize(d->stream);
   cudaFree(d->peer_flags);
-  cudaFree(d->frags); cudaFree(d->occupied);
+  cudaFree(d->frags); cudaFree(d->fresh);
   for (auto& r : d->rs) { cudaFree(r.tri_recs); cudaFree(r.item_local); cudaFree(r.item_block); }
   if (d->stream2) { cudaStreamSynchronize(d->stream2); cudaStreamDestroy(d->stream2); }
   for (cudaEvent_t e : {d->ev_fork, d->ev_join, d->ev_g0, d->ev_g1}) if (e) cudaEventDestroy(e);
@@ -603,11 +603,11 @@ int vct_voxelize_reserve(vct_device_t* dev, uint64_t max_fragments) {
   VCT_REQUIRE(max_fragments > 0 && max_fragments < 0xFFFFFFF0ull, "fragment capacity out of range");
   if (max_fragments <= dev->frag_capacity) return VCT_OK;
   VCT_CUDA(cudaStreamSynchronize(dev->stream));
-  cudaFree(dev->frags); cudaFree(dev->occupied);
-  dev->frags = nullptr; dev->occupied = nullptr; dev->frag_capacity = 0;
+  cudaFree(dev->frags); cudaFree(dev->fresh);
+  dev->frags = nullptr; dev->fresh = nullptr; dev->frag_capacity = 0;
   dev->vox_owner = nullptr;   // the occupied list is gone: the next clear is dense
   VCT_CUDA(cudaMalloc(&dev->frags, max_fragments * sizeof(FragRec)));
-  VCT_CUDA(cudaMalloc(&dev->occupied, max_fragments * sizeof(uint32_t)));
+  VCT_CUDA(cudaMalloc(&dev->fresh, max_fragments));
   dev->frag_capacity = max_fragments;
   return VCT_OK;
 }

@@ -170,7 +170,7 @@ struct vct_device {
   cudaDeviceProp prop{};
   // voxelizer arenas
   vct::FragRec* frags = nullptr;
-  uint32_t* occupied = nullptr;      // voxel indices that received >= 1 fragment
+  uint8_t* fresh = nullptr;          // per arena slot: the fragment was the first of its voxel (= one mark per occupied voxel)
   uint64_t frag_capacity = 0;
   // raster scratch (grown on demand)
   // one set per rasteriser (0 = voxelizer, 1 = G-buffer): the two run concurrently on different streams
@@ -186,7 +186,7 @@ struct vct_device {
   uint32_t* counters = nullptr;      // device counters, see enum below
   uint32_t* counters_host = nullptr; // pinned mirror
   cudaEvent_t ev[8] = {};
-  vct_grid* vox_owner = nullptr;      // the grid whose occupied voxels are in `occupied` (last vct_voxelize)
+  vct_grid* vox_owner = nullptr;      // the grid whose occupied voxels the arena's `fresh` marks describe (last vct_voxelize)
   bool have_timings = false;
   bool gbuffer_overlapped = false;   // the last frame ran its G-buffer pass on stream2 (ev_g0..ev_g1)
   // multi-GPU connection (vct_peer_connect)

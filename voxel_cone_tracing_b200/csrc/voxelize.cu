@@ -31,11 +31,9 @@ __device__ __forceinline__ F3 cross(F3 a, F3 b) { return f3(a.y * b.z - b.y * a.
 __device__ __forceinline__ F3 normalize(F3 a) { float l = sqrtf(dot(a, a)); return f3(a.x / l, a.y / l, a.z / l); }
 __device__ __forceinline__ float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 
-// fragment colour (voxelize.frag:122-153), returns colour * 255
+// fragment colour (voxelize.frag:122-153) at interpolated position `pos`, returns colour * 255
 __device__ __forceinline__ void shade_fragment(const VoxTri& v, const float b[3], const vct_material_t* __restrict__ mats, const Lights& L,
-                                               float cube_size, F3& pos, float val[4]) {
-  pos = f3(interp3(b, v.wp[0][0], v.wp[1][0], v.wp[2][0]), interp3(b, v.wp[0][1], v.wp[1][1], v.wp[2][1]),
-           interp3(b, v.wp[0][2], v.wp[1][2], v.wp[2][2]));
+                                               float cube_size, F3 pos, float val[4]) {
   F3 nrm = f3(interp3(b, v.nn[0][0], v.nn[1][0], v.nn[2][0]), interp3(b, v.nn[0][1], v.nn[1][1], v.nn[2][1]),
               interp3(b, v.nn[0][2], v.nn[1][2], v.nn[2][2]));
   F3 color = f3(0.f, 0.f, 0.f);
@@ -73,33 +71,49 @@ struct FragCtx {
   uint32_t* base;
   FragRec* frags;
   uint32_t frag_capacity;
-  uint32_t* occupied;
+  uint8_t* fresh;      // per arena slot: this fragment was the first of its voxel
   uint32_t* counters;
 };
 
-// Fragment candidates of a warp, K per lane (covered = the pixel centre is inside the triangle): shade them, find their voxels
-// (voxelize.frag:156-157: truncation, then the image bounds check; multi-GPU: the z-slab test) and append them to the voxels' lists.
-// Must be called by all 32 lanes of the warp.  The arena slots of all K*32 candidates are reserved with ONE atomicAdd and the
-// newly occupied voxels are appended to the occupied list with ONE more: both counters are single addresses, and one atomic
-// per fragment group (54 k same-address atomics per frame at 256^3) was what the raster kernel spent its time on.
+// Interpolated position of a covered pixel and its voxel (voxelize.frag:156-157: truncation, then the image bounds check;
+// multi-GPU: the z-slab test).  false = the fragment writes nothing.  The ONE place where this is decided: the counting pass and
+// the writing pass of the rasterisers must agree exactly.
+__device__ __forceinline__ bool fragment_voxel(const FragCtx& c, const VoxTri& v, const float b[3], F3& pos, uint32_t& voxel) {
+  pos = f3(interp3(b, v.wp[0][0], v.wp[1][0], v.wp[2][0]), interp3(b, v.wp[0][1], v.wp[1][1], v.wp[2][1]),
+           interp3(b, v.wp[0][2], v.wp[1][2], v.wp[2][2]));
+  const float fR = (float)c.R;
+  const int vx = (int)(fR * (0.5f * pos.x + 0.5f)), vy = (int)(fR * (0.5f * pos.y + 0.5f)), vz = (int)(fR * (0.5f * pos.z + 0.5f));
+  voxel = ((uint32_t)vz * (uint32_t)c.R + (uint32_t)vy) * (uint32_t)c.R + (uint32_t)vx;
+  return vx >= 0 && vy >= 0 && vz >= 0 && vx < c.R && vy < c.R && vz < c.R && vz >= c.z0 && vz < c.z1;
+}
+
+// Shades one fragment and appends it to its voxel's list at arena slot `idx` (reserved by the caller; slots past the capacity are
+// dropped and reported by vct_voxelize_stats).  The fragment that finds the voxel empty marks itself in `fresh`: the resolve pass
+// and the sparse clear enumerate the occupied voxels through those marks, so no second list (and no second counter) is needed.
+__device__ __forceinline__ void push_fragment(const FragCtx& c, const VoxTri& v, uint32_t ti, int i, int j, const float b[3], F3 pos, uint32_t voxel,
+                                              uint32_t idx) {
+  if (idx >= c.frag_capacity) return;
+  FragRec r;
+  shade_fragment(v, b, c.mats, c.L, c.cube_size, pos, r.val);
+  r.next = atomicExch(&c.base[voxel], idx + 1u);
+  r.voxel = voxel;
+  r.key = ((unsigned long long)ti << 24) | ((unsigned long long)j << 12) | (unsigned long long)i;
+  c.frags[idx] = r;
+  c.fresh[idx] = r.next == 0u ? 1 : 0;
+}
+
+// Fragment candidates of a warp, K per lane (covered = the pixel centre is inside the triangle).  Must be called by all 32 lanes:
+// the arena slots of all K*32 candidates are reserved with ONE atomicAdd (a counter per fragment group -- 54 k same-address
+// atomics per frame at 256^3 -- was what the raster kernel spent its time on).
 template <int K>
 __device__ __forceinline__ void emit_fragments(const FragCtx& c, const VoxTri& v, uint32_t ti, const int (&pi)[K], const int (&pj)[K], const float (&pb)[K][3],
                                                bool (&covered)[K], int lane) {
-  uint32_t voxel[K];
-  float val[K][4];
-  uint32_t mask[K];
-  uint32_t total = 0;
+  uint32_t voxel[K], mask[K], total = 0;
+  F3 pos[K];
 #pragma unroll
   for (int k = 0; k < K; k++) {
-    voxel[k] = 0;
-    if (covered[k]) {
-      F3 pos;
-      shade_fragment(v, pb[k], c.mats, c.L, c.cube_size, pos, val[k]);
-      const float fR = (float)c.R;
-      int vx = (int)(fR * (0.5f * pos.x + 0.5f)), vy = (int)(fR * (0.5f * pos.y + 0.5f)), vz = (int)(fR * (0.5f * pos.z + 0.5f));
-      covered[k] = vx >= 0 && vy >= 0 && vz >= 0 && vx < c.R && vy < c.R && vz < c.R && vz >= c.z0 && vz < c.z1;
-      voxel[k] = ((uint32_t)vz * (uint32_t)c.R + (uint32_t)vy) * (uint32_t)c.R + (uint32_t)vx;
-    }
+    voxel[k] = 0; pos[k] = f3(0.f, 0.f, 0.f);
+    if (covered[k]) covered[k] = fragment_voxel(c, v, pb[k], pos[k], voxel[k]);
     mask[k] = __ballot_sync(0xffffffffu, covered[k]);
     total += (uint32_t)__popc(mask[k]);
   }
@@ -107,45 +121,11 @@ __device__ __forceinline__ void emit_fragments(const FragCtx& c, const VoxTri& v
   uint32_t basei = 0;
   if (lane == 0) basei = atomicAdd(&c.counters[CNT_FRAGS], total);
   basei = __shfl_sync(0xffffffffu, basei, 0);
-  bool fresh[K];
-  uint32_t n_fresh = 0, fmask[K];
 #pragma unroll
   for (int k = 0; k < K; k++) {
-    fresh[k] = false;
-    if (covered[k]) {
-      const uint32_t idx = basei + (uint32_t)__popc(mask[k] & ((1u << lane) - 1u));
-      if (idx < c.frag_capacity) {
-        const uint32_t prev = atomicExch(&c.base[voxel[k]], idx + 1u);
-        FragRec r;
-        r.next = prev;
-        r.voxel = voxel[k];
-        r.key = ((unsigned long long)ti << 24) | ((unsigned long long)pj[k] << 12) | (unsigned long long)pi[k];
-        r.val[0] = val[k][0]; r.val[1] = val[k][1]; r.val[2] = val[k][2]; r.val[3] = val[k][3];
-        c.frags[idx] = r;
-        fresh[k] = prev == 0u;
-      }
-    }
+    if (covered[k]) push_fragment(c, v, ti, pi[k], pj[k], pb[k], pos[k], voxel[k], basei + (uint32_t)__popc(mask[k] & ((1u << lane) - 1u)));
     basei += (uint32_t)__popc(mask[k]);
-    fmask[k] = __ballot_sync(0xffffffffu, fresh[k]);
-    n_fresh += (uint32_t)__popc(fmask[k]);
   }
-  if (!n_fresh) return;
-  uint32_t obase = 0;
-  if (lane == 0) obase = atomicAdd(&c.counters[CNT_OCCUPIED], n_fresh);
-  obase = __shfl_sync(0xffffffffu, obase, 0);
-#pragma unroll
-  for (int k = 0; k < K; k++) {
-    if (fresh[k]) c.occupied[obase + (uint32_t)__popc(fmask[k] & ((1u << lane) - 1u))] = voxel[k];
-    obase += (uint32_t)__popc(fmask[k]);
-  }
-}
-
-// one candidate per lane
-__device__ __forceinline__ void emit_fragment(const FragCtx& c, const VoxTri& v, uint32_t ti, int i, int j, const float b[3], bool covered, int lane) {
-  const int pi[1] = {i}, pj[1] = {j};
-  const float pb[1][3] = {{b[0], b[1], b[2]}};
-  bool cov[1] = {covered};
-  emit_fragments<1>(c, v, ti, pi, pj, pb, cov, lane);
 }
 
 // triangles whose bounding box holds at most this many pixel centres are rasterised inside the setup kernel (one lane
@@ -210,17 +190,33 @@ vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
   const int bw = v.rt.imax - v.rt.imin + 1, bh = v.rt.jmax - v.rt.jmin + 1;
   const bool small = count > 0 && bw * bh <= small_limit;
   const int npx = small ? bw * bh : 0;
-  const int maxpx = __reduce_max_sync(0xffffffffu, npx);
+  // pass 1: every lane counts the fragments of its own triangle; pass 2: it writes them at consecutive slots of the warp's
+  // reservation -- ONE arena atomic per warp of 32 triangles (one per pixel step of the lock-stepped walk before: 9 M same-address
+  // atomics per frame on the 4 M-triangle scene)
   const int lane = threadIdx.x & 31;
-  for (int p = 0; p < maxpx; p++) {
+  uint32_t mine = 0;
+  for (int p = 0; p < npx; p++) {
     float b[3];
-    int i = 0, j = 0;
-    bool covered = false;
-    if (p < npx) {
-      i = v.rt.imin + p % bw; j = v.rt.jmin + p / bw;
-      covered = raster_sample(v.rt, i, j, b);
-    }
-    emit_fragment(ctx, v, t, i, j, b, covered, lane);
+    F3 pos; uint32_t voxel;
+    if (raster_sample(v.rt, v.rt.imin + p % bw, v.rt.jmin + p / bw, b) && fragment_voxel(ctx, v, b, pos, voxel)) mine++;
+  }
+  uint32_t incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += n;
+  }
+  const uint32_t warp_total = __shfl_sync(0xffffffffu, incl, 31);
+  uint32_t slot = 0;
+  if (warp_total) {
+    if (lane == 0) slot = atomicAdd(&ctx.counters[CNT_FRAGS], warp_total);
+    slot = __shfl_sync(0xffffffffu, slot, 0) + (incl - mine);
+  }
+  for (int p = 0; p < npx; p++) {
+    float b[3];
+    F3 pos; uint32_t voxel;
+    const int i = v.rt.imin + p % bw, j = v.rt.jmin + p / bw;
+    if (raster_sample(v.rt, i, j, b) && fragment_voxel(ctx, v, b, pos, voxel)) push_fragment(ctx, v, t, i, j, b, pos, voxel, slot++);
   }
   if (small) count = 0;
   else if (t < n_tris) out[t] = v;   // only triangles that become work items are read again
@@ -292,24 +288,29 @@ __device__ __forceinline__ uint32_t tile_of_voxel(uint32_t voxel, int logR) {
   return (((z >> 3) << (logR - 3)) + (y >> 3) << (logR - 5)) + (x >> 5);
 }
 
-// vct_grid_clear, sparse form: zero the voxels (and the tile flags) of the last voxelization's occupied list
+// vct_grid_clear, sparse form: zero the voxels (and the tile flags) the last voxelization occupied = the voxels of its `fresh` fragments
 __global__ void __launch_bounds__(256)
-sparse_clear_kernel(uint32_t* __restrict__ base, const uint32_t* __restrict__ occupied, const uint32_t* __restrict__ counters, uint32_t capacity,
-                    uint8_t* __restrict__ tile_touched, int logR) {
-  const uint32_t n = min(counters[CNT_OCCUPIED], capacity);
-  for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < n; o += gridDim.x * blockDim.x) {
-    const uint32_t voxel = occupied[o];
+sparse_clear_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frags, const uint8_t* __restrict__ fresh, const uint32_t* __restrict__ counters,
+                    uint32_t capacity, uint8_t* __restrict__ tile_touched, int logR) {
+  const uint32_t n = min(counters[CNT_FRAGS], capacity);
+  for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < n; f += gridDim.x * blockDim.x) {
+    if (!fresh[f]) continue;
+    const uint32_t voxel = frags[f].voxel;
     base[voxel] = 0u;
     if (tile_touched) tile_touched[tile_of_voxel(voxel, logR)] = 0;
   }
 }
 
+// One thread per arena slot; the thread of a voxel's FIRST fragment (`fresh`) resolves the voxel.
 __global__ void __launch_bounds__(128)
-vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frags, const uint32_t* __restrict__ occupied,
+vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frags, const uint8_t* __restrict__ fresh,
                    uint32_t* __restrict__ counters, uint32_t frag_capacity, const PeerView pv, uint8_t* __restrict__ tile_touched, int logR) {
-  const uint32_t n_occ = counters[CNT_OCCUPIED];
-  for (uint32_t o = blockIdx.x * blockDim.x + threadIdx.x; o < n_occ; o += gridDim.x * blockDim.x) {
-    const uint32_t voxel = occupied[o];
+  const uint32_t n_frags = min(counters[CNT_FRAGS], frag_capacity);
+  uint32_t n_mine = 0, max_list = 0;
+  for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < n_frags; f += gridDim.x * blockDim.x) {
+    if (!fresh[f]) continue;
+    n_mine++;
+    const uint32_t voxel = frags[f].voxel;
     const uint32_t head = base[voxel];
     unsigned long long keys[kSortMax];
     uint32_t ids[kSortMax];
@@ -349,8 +350,12 @@ vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frag
     // exchange: only occupied voxels travel; replaces the dense all-gather of the base level)
     for (int p = 0; p < pv.nranks; p++)
       if (p != pv.rank) pv.base[p][voxel] = stored;
-    atomicMax(&counters[CNT_MAXLIST], n);
+    max_list = max(max_list, n);
   }
+  // statistics (vct_voxelize_stats): occupied voxels and the longest list, one atomic each per warp
+  n_mine = __reduce_add_sync(0xffffffffu, n_mine);
+  max_list = __reduce_max_sync(0xffffffffu, max_list);
+  if ((threadIdx.x & 31) == 0 && n_mine) { atomicAdd(&counters[CNT_OCCUPIED], n_mine); atomicMax(&counters[CNT_MAXLIST], max_list); }
   if (pv.nranks > 1) peer_signal_last_block(pv, PEER_FLAG_PUSHED, -1);
 }
 
@@ -379,7 +384,7 @@ int ensure_tri_scratch(vct_device* dev, int which, size_t n_tris, size_t rec_byt
 static int log2_int(int v) { int l = 0; while ((1 << l) < v) l++; return l; }
 
 int launch_sparse_clear(vct_device* dev, vct_grid* g) {
-  sparse_clear_kernel<<<dev->prop.multiProcessorCount * 2, 256, 0, dev->stream>>>(g->base, dev->occupied, dev->counters, (uint32_t)dev->frag_capacity,
+  sparse_clear_kernel<<<dev->prop.multiProcessorCount * 4, 256, 0, dev->stream>>>(g->base, dev->frags, dev->fresh, dev->counters, (uint32_t)dev->frag_capacity,
                                                                                    g->tile_touched, log2_int(g->R));
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;
@@ -412,13 +417,13 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
   if (sc->n_tris) {   // an empty scene still runs the resolve kernel in multi-GPU mode: the peers wait for its signal
     FragCtx ctx;
     ctx.mats = sc->mats; ctx.L = sc->lights; ctx.cube_size = sc->cube_size; ctx.R = g->R; ctx.z0 = z0; ctx.z1 = z1;
-    ctx.base = g->base; ctx.frags = dev->frags; ctx.frag_capacity = (uint32_t)dev->frag_capacity; ctx.occupied = dev->occupied; ctx.counters = dev->counters;
+    ctx.base = g->base; ctx.frags = dev->frags; ctx.frag_capacity = (uint32_t)dev->frag_capacity; ctx.fresh = dev->fresh; ctx.counters = dev->counters;
     vox_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, sc->cube_size, g->R, z0, z1, tris,
                                                           dev->rs[0].item_local, dev->rs[0].item_block, ctx, sc->n_tris >= kSmallPathMinTris ? kSmallPixels : 0,
                                                           dev->counters + CNT_TICKET_VOX, dev->counters + CNT_ITEMS);
     vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->rs[0].item_local, dev->rs[0].item_block, n_blocks, ctx);
   }
-  vox_resolve_kernel<<<sms * 4, 128, 0, s>>>(g->base, dev->frags, dev->occupied, dev->counters, (uint32_t)dev->frag_capacity, pv, touched, log2_int(g->R));
+  vox_resolve_kernel<<<sms * 8, 128, 0, s>>>(g->base, dev->frags, dev->fresh, dev->counters, (uint32_t)dev->frag_capacity, pv, touched, log2_int(g->R));
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;
 }
