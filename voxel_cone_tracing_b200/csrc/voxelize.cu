@@ -8,15 +8,17 @@
 //   2. (inside 1.)        the last block to finish scans the block totals: global item offsets (no host round trip, no extra launch)
 //   3. vox_raster_kernel  one warp per 8x8 item: coverage, fragment shading (voxelize.frag:122-157),
 //                         append of a 32-byte fragment record to a per-voxel linked list whose head
-//                         lives in the grid word itself (atomicExch), occupied-voxel list
-//   4. vox_resolve_kernel one thread per occupied voxel: sorts the voxel's fragments by the canonical
+//                         lives in the grid word itself (atomicExch); the fragment that finds the voxel
+//                         empty marks its arena slot (`fresh`).  Triangles of <= 36 pixels are rasterised
+//                         inside 1. (count pass, one arena atomic per warp, write pass).
+//   4. vox_resolve_kernel one thread per arena slot, the `fresh` ones resolve their voxel: sorts the voxel's fragments by the canonical
 //                         order key (draw, triangle, row, column) and folds them with the reference's
 //                         RGBA8 running average (voxelize.frag:95-120) -> deterministic and bit-exact
 //                         against the sequential oracle, which the CAS loop of the reference is not.
 //                         Also marks the 32x8x8 tile of the voxel (sparse mip build) and, multi-GPU, stores
 //                         the voxel into every peer's grid over NVLink.
 //   sparse_clear_kernel   vct_grid_clear in a frame loop: zeroes the voxels of the previous frame's
-//                         occupied list instead of the whole level.
+//                         `fresh` fragments instead of the whole level.
 // Built with -fmad=false: the arithmetic (IEEE add/mul/div/sqrt only, fixed evaluation order) is the
 // same as the oracle's so that voxel occupancy AND colour match bit for bit.
 #include "raster.cuh"
