@@ -10,9 +10,9 @@ NVFLAGS  := -O3 -std=c++17 $(ARCH) -lineinfo -Iinclude -I$(CSRC) -Xcompiler -fPI
 # bit-exact units (same arithmetic as the oracle: no FMA contraction)
 EXACT    := -fmad=false
 OBJS     := $(CSRC)/capi.o $(CSRC)/tex3d.o $(CSRC)/voxelize.o $(CSRC)/mipmap.o $(CSRC)/gbuffer.o $(CSRC)/cone_trace.o $(CSRC)/peer.o
-HDRS     := include/vct/vct_c.h $(CSRC)/vct_internal.cuh $(CSRC)/raster.cuh
+HDRS     := include/vct/vct_c.h $(CSRC)/vct_internal.cuh $(CSRC)/raster.cuh $(CSRC)/mip_arith.cuh
 
-all: $(OUT)/libvct_cuda.so oracle host
+all: $(OUT)/libvct_cuda.so oracle host hosttest
 
 $(CSRC)/voxelize.o: $(CSRC)/voxelize.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) $(EXACT) -c $< -o $@
@@ -38,7 +38,12 @@ oracle:
 host: $(OUT)/libvct_cuda.so
 	@if [ -f $(HOST)/Makefile ]; then $(MAKE) -C $(HOST); fi
 
+# host (g++) build of the arithmetic headers the kernels share, for the CPU test suite (tests/test_mip_arith.py)
+hosttest: tests/native/libvct_hosttest.so
+tests/native/libvct_hosttest.so: tests/native/mip_arith_host.cpp $(CSRC)/mip_arith.cuh
+	$(CXX) -O2 -std=c++17 -ffp-contract=off -fPIC -shared -I$(CSRC) -o $@ $<
+
 clean:
 	rm -f $(OBJS) $(OUT)/libvct_cuda.so
 	$(MAKE) -C oracle clean
-.PHONY: all oracle host clean
+.PHONY: all oracle host hosttest clean

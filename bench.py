@@ -5,11 +5,14 @@ Metric (BASELINE.json): frames/s of a full frame = clear + revoxelize + six-dire
 G-buffer + cone trace, on configs[1]: CornellBox-Glossy, 256^3 grid, 1920x1080, 9 diffuse + 1 specular
 + 1 shadow cone per pixel, 1 light.  One "step" = one frame.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1..5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1..5] [--no-extra]
 
-N > 1 is launched by the driver under torchrun (one rank per GPU): voxelization is sharded by z-slab,
-the base level is all-gathered in place over NCCL, every rank builds the mip chain locally, cone
-tracing is split by 32x32 screen tiles and the frame is merged with one NCCL reduction.
+N > 1 is launched by the driver under torchrun (one rank per GPU): voxelization is sharded by z-slab and
+every rank stores its resolved voxels into the peers' grids over NVLink, every rank builds the mip chain
+locally, cone tracing is split by 32x32 screen tiles whose pixels are stored into the root's frame.
+Besides the headline config the line carries `extra_configs`: BASELINE.json's configs 4 (1 M triangles,
+512^3, 3840x2160) and 5 (4 M triangles, 1024^3, 7680x4320, 16 cones) device-timed at the same N, so that
+the driver's 1/2/4/8 runs hold the scaling curves north_star asks for.
 
 `--impl reference` times the CPU oracle (the reference's GLSL needs an OpenGL 4.5 driver that does not
 exist in this image -- see DESIGN.md) on the host cores on a bounded sample of the same workload.
@@ -18,6 +21,7 @@ Prints ONE JSON line on rank 0.
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -41,12 +45,12 @@ CONFIGS = {
     5: dict(name="synthetic 4M triangles 1024^3 7680x4320 (RGBA8, 7 levels; 16 diffuse cones: BASELINE config 5's cone variant)", R=1024, W=7680, H=4320,
             scene="synthetic", tris=4_000_000, seed=0x5EED0002, cones=16),
 }
-KERNELS_PER_FRAME = 15  # clear 1 (sparse: the previous frame's occupied voxels) + voxelize 4 (counter reset, setup+scan, raster, resolve) + mip 2 (fused low; tail = levels 4-6 + occupancy + dilation) + gbuffer 4 (clear, setup+scan, raster, resolve) + trace 4 (list reset, tile list, cones, shade)
-# ncu --set full capture of cone_kernel_fast on this workload (profiles/r01_ncu_s7.md), per launch:
-# dram__bytes_read.sum + dram__bytes_write.sum, and the two units that bind the kernel
-CONE_KERNEL_DRAM_TRAFFIC = {1: 24.6e6 + 10.4e6}
-CONE_KERNEL_NCU = {"tex_wavefront_frac": 0.764, "issue_frac": 0.662, "tex_wavefronts_per_launch": 192.4e6, "warp_instructions_per_launch": 643.4e6,
-                   "l1tex_sectors_per_launch": 649.9e6, "source": "profiles/r01_ncu_s7.md (ncu --set full, one launch of this command)"}
+# kernels per frame (one GPU): clear 1 (sparse: the previous frame's occupied voxels) + voxelize 4 (counter reset, setup+scan, raster, resolve)
+# + mip 2 (fused levels 1-3; tail = levels 4.. + occupancy dilation) + G-buffer 5 (clear, record counter reset, setup+scan, raster, resolve)
+# + trace 4 (list reset, tile list, cones, shade); checked against the ncu launch list (profiles/r02_launch_summary_c2.txt)
+KERNELS_PER_FRAME = 16
+# ncu --set full counters of the dominant kernel on the headline workload, extracted by tools/ncu_to_json.py from a capture of THIS tree
+CONE_PROFILE = os.path.join(ROOT, "profiles", "r02_cone_kernel_ncu.json")
 
 
 def build_scene(cfg, frame: int = 0):
@@ -55,6 +59,20 @@ def build_scene(cfg, frame: int = 0):
     if cfg["scene"] == "cornell+suzanne":
         return S.cornell_scene(with_suzanne=True, theta=0.05 * frame)
     return S.synthetic_scene(cfg["tris"], cfg["seed"])
+
+
+def config_dict(cfg, world: int, sampler: int, exchange: str, n_tris: int) -> dict:
+    """identical for both arms (the driver compares them)"""
+    R, W, H = cfg["R"], cfg["W"], cfg["H"]
+    par = f"z-slab voxelize + screen-tile trace x{world}"
+    if world > 1:
+        par += (", sparse NVLink peer-store exchange fused into the resolve/shade kernels (CUDA IPC, no collective)" if exchange == "p2p"
+                else ", NCCL all-gather of the base level + all-reduce of the frame")
+    ws = (7.43 * R ** 3 + W * H * 40) / 1e6
+    return {"workload": cfg["name"] + ", revoxelize+mip+gbuffer+trace per frame, %d diffuse + 1 specular + 1 shadow cone" % cfg.get("cones", 9),
+            "sampler": "texture units (levels >= 1), software level 0" if sampler == 1 else "software fp32 trilinear",
+            "grid": R, "frame": [W, H], "triangles": n_tris, "parallelism": par,
+            "l2": "no explicit flush: pyramid + G-buffer + frame working set (%.0f MB) exceeds the 126 MB L2 and is rewritten every frame" % ws}
 
 
 def measured_peaks():
@@ -113,12 +131,15 @@ class ClockSampler:
 # ----------------------------------------------------------------------------- CPU oracle legs
 class CpuWorkload:
     """The same frame on the host cores with the oracle.  voxelize + mip + G-buffer are run (and timed) in
-    full once; a "step" then traces every `stride`-th 32x32 screen tile (a different phase each step) and
-    the frame time is estimated as t_voxelize + t_mip + t_gbuffer + stride * t_trace_step."""
+    full once; a "step" then traces every `stride`-th 32x32 screen tile (a different phase each step).  With
+    stride 1 a step IS the full trace; with stride > 1 the frame time is t_voxelize + t_mip + t_gbuffer +
+    stride * t_trace_step and the line says that it is extrapolated."""
 
     def __init__(self, cfg):
         from oracle import orc
         self.orc, self.cfg = orc, cfg
+        # torchrun exports OMP_NUM_THREADS=1 to every rank: the baseline uses all the cores whoever launched it
+        orc.set_num_threads(os.cpu_count() or 1)
         self.sc = build_scene(cfg)
         R, W, H = cfg["R"], cfg["W"], cfg["H"]
         self.view, self.proj = S.reference_camera(W / H)
@@ -139,7 +160,7 @@ class CpuWorkload:
         return dt, int(st.samples)
 
     def pick_stride(self, steps: int, budget_s: float) -> int:
-        """largest power-of-two-ish thinning so that `steps` steps fit in the budget"""
+        """smallest power-of-two thinning so that `steps` steps fit in the budget"""
         dt, _ = self.trace_step(64, 0)              # calibration: 1/64 of the tiles
         full = dt * 64.0
         per_step = max(budget_s / max(steps, 1), 0.05)
@@ -152,12 +173,13 @@ class CpuWorkload:
         return self.t_vox + self.t_mip + self.t_gbuf + t_trace_step * stride
 
     def sample_text(self, stride: int) -> str:
+        how = ("each step cone-traces the whole frame" if stride == 1 else
+               f"each step cone-traces every {stride}th 32x32 tile; the frame time is EXTRAPOLATED: voxelize + mip + G-buffer + {stride} x the step's trace time")
         return (f"oracle = CPU restatement of the GLSL (C++/OpenMP, {self.cores} threads; Mesa llvmpipe is unavailable in this image): "
-                f"voxelize+mip+G-buffer of '{self.cfg['name']}' in full (timed once), each step cone-traces every {stride}th 32x32 tile "
-                f"and scales the trace time x{stride}")
+                f"voxelize+mip+G-buffer of '{self.cfg['name']}' in full (timed once), {how}")
 
 
-def run_reference(args, cfg, rank: int):
+def run_reference(args, cfg, rank: int, world: int):
     if rank != 0:
         return
     wl = CpuWorkload(cfg)
@@ -165,12 +187,15 @@ def run_reference(args, cfg, rank: int):
     for i in range(args.warmup):
         wl.trace_step(stride, i)
     ts = [wl.trace_step(stride, args.warmup + i)[0] for i in range(args.steps)]
-    ms = 1e3 * sum(wl.frame_seconds(t, stride) for t in ts) / len(ts)
-    v = 1e3 / ms
+    frame_ms = 1e3 * sum(wl.frame_seconds(t, stride) for t in ts) / len(ts)
+    # what one step really took on the wall: the shared stages are run once, outside the steps
+    step_ms = frame_ms if stride == 1 else 1e3 * sum(ts) / len(ts)
+    v = 1e3 / frame_ms
     print(json.dumps({
         "impl": "reference", "metric": "frames_per_sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 RGBA storage)", "data": "synthetic",
-        "config": {"workload": cfg["name"] + ", revoxelize+mip+gbuffer+trace per frame, %d diffuse + 1 specular + 1 shadow cone" % cfg.get("cones", 9)},
+        "ms_per_step": step_ms, "frame_ms": frame_ms, "extrapolated": stride != 1, "tile_stride": stride,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 RGBA storage)", "data": "synthetic",
+        "config": config_dict(cfg, world, args.sampler, args.exchange, wl.sc.n_triangles),
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": wl.cores, "kind": "port", "sample": wl.sample_text(stride),
                          "voxelize_s": wl.t_vox, "mip_s": wl.t_mip, "gbuffer_s": wl.t_gbuf},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -185,227 +210,295 @@ class CudaArray:
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None}
 
 
+class Rig:
+    """one config on this rank's GPU: pipeline + the frame function of the chosen exchange"""
+
+    def __init__(self, cfg, args, rank, world, local_rank, torch, dist):
+        from voxel_cone_tracing_b200 import capi
+        self.capi, self.torch, self.dist = capi, torch, dist
+        self.cfg, self.args, self.rank, self.world, self.local_rank = cfg, args, rank, world, local_rank
+        R, W, H = cfg["R"], cfg["W"], cfg["H"]
+        self.sc = build_scene(cfg)
+        self.view, self.proj = S.reference_camera(W / H)
+        self.pipe = capi.Pipeline(self.sc, R, W, H, 7, ordinal=local_rank, reserve=max(1 << 20, 8 * self.sc.n_triangles))
+        self.stream = torch.cuda.ExternalStream(int(self.pipe.dev.L.vct_device_stream(self.pipe.dev.h)), device=torch.device("cuda", local_rank))
+        self.prm = capi.default_params(tile_rank=rank, tile_nranks=world, sampler=args.sampler, n_diffuse_cones=cfg.get("cones", 9))
+        self.z0, self.z1 = rank * R // world, (rank + 1) * R // world
+        self.p2p = world > 1 and args.exchange == "p2p"
+        pipe = self.pipe
+        # size the fragment arena for this rank's slab before anything is timed (the library grows it on overflow and asks for a re-run)
+        for _ in range(4):
+            pipe.clear(); pipe.voxelize(self.z0, self.z1)
+            try:
+                pipe.voxel_stats()
+                break
+            except capi.VctError as e:
+                if "overflow" not in str(e):
+                    raise
+        pipe.clear()
+        self.base_t = self.frame_t = None
+        if world > 1 and not self.p2p:
+            self.base_t = torch.as_tensor(CudaArray(pipe.grid.base_ptr, (R * R * R,), "<i4"), device=torch.device("cuda", local_rank))
+            self.frame_t = torch.as_tensor(CudaArray(pipe.target.frame_ptr, (W * H,), "<i4"), device=torch.device("cuda", local_rank))
+        if self.p2p:
+            # NVLink peer-memory exchange fused into the resolve / shade kernels (csrc/peer.cu): handles travel once, here
+            handles = [None] * world
+            dist.all_gather_object(handles, pipe.peer_export())
+            pipe.peer_connect(rank, world, handles, frame_root=0)
+            dist.barrier()
+
+    def frame(self):
+        pipe, dist, torch = self.pipe, self.dist, self.torch
+        if self.world == 1 or self.p2p:
+            pipe.render_frame(self.view, self.proj, self.prm)
+            return
+        R = self.cfg["R"]
+        per_rank = R * R * R // self.world
+        with torch.cuda.stream(self.stream):
+            pipe.clear()
+            pipe.voxelize(self.z0, self.z1)
+            dist.all_gather_into_tensor(self.base_t, self.base_t[self.rank * per_rank:(self.rank + 1) * per_rank])   # in place, z-major slabs
+            pipe.mipmap()
+            pipe.gbuffer(self.view, self.proj)
+            self.frame_t.zero_()
+            pipe.trace(self.view, self.prm)
+            dist.all_reduce(self.frame_t)   # tiles are disjoint: integer sum == merge
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.pipe.sync()
+        self.torch.cuda.synchronize()
+
+    def timed(self, steps: int, warmup: int) -> float:
+        """ms per frame, device-timed with CUDA events on the launching stream, max over ranks"""
+        torch = self.torch
+        for _ in range(max(warmup, 3)):
+            self.frame()
+        self.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record(self.stream)
+        for _ in range(steps):
+            self.frame()
+        e1.record(self.stream)
+        self.barrier()
+        ms = e0.elapsed_time(e1)
+        if self.world > 1:
+            t = torch.tensor([ms], device=f"cuda:{self.local_rank}")
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps
+
+    def stage_times(self, n: int) -> dict:
+        """per-stage device times of this rank in us (CUDA events inside vct_render_frame), averaged over n frames"""
+        acc = {}
+        for _ in range(n):
+            self.pipe.render_frame(self.view, self.proj, self.prm)
+            for k, v in self.pipe.timings().items():
+                acc[k] = acc.get(k, 0.0) + v * 1e3 / n
+        return acc
+
+    def close(self):
+        if self.p2p:
+            self.pipe.peer_check()        # raises if a flag wait ever timed out
+            self.barrier()                # nobody unmaps while a peer may still be storing into it
+            self.pipe.peer_disconnect()
+            self.barrier()
+        self.pipe.close()
+
+
+def h2d_bytes(sc) -> int:
+    return int(sc.verts.nbytes + sc.indices.nbytes + sc.materials.nbytes + sc.draws.nbytes + sc.lights.nbytes + 128 + 36)
+
+
+def e2e_loop(rig: Rig, steps: int):
+    """the frame through the public C ABI with HOST buffers: every step uploads the scene (geometry, materials, draw list, lights)
+    from host memory and reads the finished frame back into pinned host memory; wall clock, max over ranks"""
+    torch, pipe, sc, rank, world = rig.torch, rig.pipe, rig.sc, rig.rank, rig.world
+    W, H = rig.cfg["W"], rig.cfg["H"]
+    host_frames = [torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(2)] if rank == 0 else None
+    for i in range(2):
+        pipe.scene.upload(sc); pipe.render_frame(rig.view, rig.proj, rig.prm)
+        if rank == 0:
+            pipe.target.wait(pipe.target.frame_async(host_frames[i]))
+    rig.barrier()
+    t0 = time.perf_counter()
+    prev = None
+    for i in range(steps):
+        pipe.scene.upload(sc)                                # H2D: geometry, materials, draw list (pinned staging ring, async)
+        pipe.render_frame(rig.view, rig.proj, rig.prm)
+        if rank == 0:
+            tk = pipe.target.frame_async(host_frames[i & 1])  # D2H of this frame, asynchronous: overlaps the next frame
+            if prev is not None:
+                pipe.target.wait(prev)                        # frame i-1 is in host memory
+            prev = tk
+    if rank == 0 and prev is not None:
+        pipe.target.wait(prev)
+    pipe.sync()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([dt], device=f"cuda:{rig.local_rank}")
+        rig.dist.all_reduce(tt, op=rig.dist.ReduceOp.MAX)
+        dt = float(tt.item())
+    out = {"value": steps / dt, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes(sc) * world, "d2h_bytes_per_step": int(W * H * 4),
+           "ms_per_step": 1e3 * dt / steps,
+           "note": ("every rank uploads the scene from host memory and renders its share every step, the root reads the merged frame back to pinned host "
+                    "memory" if world > 1 else "scene uploaded from host memory and the finished frame read back to pinned host memory EVERY step through the C ABI")
+                   + "; the read-back of frame i overlaps the rendering of frame i+1 (vct_target_download_frame_async); wall clock"}
+    if world == 1:   # the same loop fully serialised (blocking read-back each step), for reference
+        n = min(steps, 50)
+        pipe.sync()
+        t0 = time.perf_counter()
+        for i in range(n):
+            pipe.scene.upload(sc); pipe.render_frame(rig.view, rig.proj, rig.prm); pipe.target.frame(host_frames[0])
+        pipe.sync()
+        out["blocking_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / n
+    return out
+
+
+def cone_roofline(rig: Rig, cone_us: float, sm_mhz, cnt):
+    """The dominant kernel against the unit that binds it.  The pyramid it gathers from is L1/L2 resident (DRAM traffic is < 1 % of the
+    HBM peak), so an HBM roofline says nothing; the binding unit is the texture pipe: one TEX wavefront per clock per SM.  The number
+    of wavefronts of one launch is a property of the workload (same frame, same kernel) and is read from the ncu capture of this tree
+    (path and hash printed); the time is the live CUDA-event time of this run."""
+    peak_hbm, peak_src = measured_peaks()
+    out = {"kernel": "cone_kernel_fast", "bound": "l1tex", "unit": "Gwavefronts/s", "achieved": None, "peak": None, "frac": None, "traffic": None,
+           "samples_per_launch": int(cnt.samples), "gsamples_per_s": cnt.samples / (cone_us * 1e-6) / 1e9, "kernel_us": cone_us,
+           "hbm_peak_gbs": peak_hbm, "hbm_peak_source": peak_src}
+    key = f"config{rig.args.config}_sampler{rig.args.sampler}"
+    try:
+        raw = open(CONE_PROFILE, "rb").read()
+        prof = json.loads(raw)[key]
+    except Exception as ex:
+        out["note"] = f"no ncu capture for {key} in {os.path.relpath(CONE_PROFILE, ROOT)} ({type(ex).__name__}): only Gsamples/s is reported"
+        return out
+    wf = float(prof["tex_wavefronts"])
+    sms = 148
+    clk = (sm_mhz or 1965.0) * 1e6
+    dram = float(prof["dram_bytes_read"]) + float(prof["dram_bytes_write"])
+    out.update({
+        "achieved": wf / (cone_us * 1e-6) / 1e9, "peak": sms * clk / 1e9, "frac": wf / (cone_us * 1e-6) / (sms * clk),
+        "traffic": dram, "tex_wavefronts_per_launch": wf, "warp_instructions_per_launch": prof.get("warp_instructions"),
+        "hbm_frac": dram / (cone_us * 1e-6) / 1e9 / peak_hbm,
+        "ncu": {"file": os.path.relpath(CONE_PROFILE, ROOT), "sha256": hashlib.sha256(raw).hexdigest()[:16], "kernel_us_under_ncu": prof.get("time_us"),
+                "tex_pipe_pct_under_ncu": prof.get("tex_wavefront_pct")},
+        "note": "achieved = TEX wavefronts of one launch (ncu capture of this tree, same workload) / CUDA-event kernel time of this run; "
+                "peak = 148 SMs x 1 wavefront per clock x the SM clock sampled during the run; traffic = DRAM bytes per launch (ncu)"})
+    return out
+
+
+def mip_stage(rig: Rig, stage_acc: dict) -> dict:
+    """mip stage against its HBM roofline (7.4286 R^3 algorithmic bytes).  The roofline fraction is the DENSE build
+    (every tile read and written); the running frame loop moves far less (untouched all-zero tiles are skipped) and is reported in us."""
+    torch, pipe, capi = rig.torch, rig.pipe, rig.capi
+    R = rig.cfg["R"]
+    peak, peak_src = measured_peaks()
+    alg = 7.4286 * R ** 3
+
+    def dense_us(n=10):
+        pipe.dev.debug_set(capi.DEBUG_MIP_DENSE, 1)
+        pipe.mipmap(); pipe.sync()
+        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        d0.record(rig.stream)
+        for _ in range(n):
+            pipe.mipmap()
+        d1.record(rig.stream)
+        pipe.sync()
+        pipe.dev.debug_set(capi.DEBUG_MIP_DENSE, 0)
+        return d0.elapsed_time(d1) * 1e3 / n
+
+    scene_us = dense_us()
+    out = {"bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src, "algorithmic_bytes": alg,
+           "achieved": alg / (scene_us * 1e-6) / 1e9, "frac": alg / (scene_us * 1e-6) / 1e9 / peak, "dense_us": scene_us,
+           "frame_loop_us": stage_acc["mipmap"],
+           "note": "frac = dense algorithmic bytes / time of the DENSE build of this frame's grid (every tile read, every output written; "
+                   "vct_debug_set(VCT_DEBUG_MIP_DENSE)); frame_loop_us = the stage inside the running frame loop, where untouched all-zero tiles are skipped"}
+    if R <= 256:   # the same build on a uniform-random grid (SURVEY 8(d) micro-input): every texel takes the arithmetic path
+        g2 = capi.Grid(pipe.dev, R, 7)
+        rng = np.random.default_rng(1)
+        g2.upload_base(rng.integers(0, 2 ** 32, (R, R, R), dtype=np.uint64).astype(np.uint32))
+        keep = pipe.grid
+        pipe.grid = g2
+        rnd = dense_us()
+        pipe.grid = keep
+        g2.close()
+        out["dense_random_us"] = rnd
+        out["dense_random_frac"] = alg / (rnd * 1e-6) / 1e9 / peak
+    pipe.render_frame(rig.view, rig.proj, rig.prm); pipe.sync()      # back to the tracked state
+    return out
+
+
+def run_extra(cfg_id, args, rank, world, local_rank, torch, dist):
+    """one of the large configs, device-timed at this N (no end-to-end leg, no CPU leg)"""
+    cfg = CONFIGS[cfg_id]
+    steps = 10 if cfg_id == 4 else 5
+    try:
+        rig = Rig(cfg, args, rank, world, local_rank, torch, dist)
+        ms = rig.timed(steps, 3)
+        st = rig.stage_times(3) if (world == 1 or rig.p2p) else None
+        per_rank = None
+        if world > 1 and st is not None:
+            per_rank = [None] * world
+            dist.all_gather_object(per_rank, {k: round(v, 1) for k, v in st.items()})
+        out = {"workload": config_dict(cfg, world, args.sampler, args.exchange, rig.sc.n_triangles)["workload"], "ms_per_frame": ms, "frames_per_s": 1e3 / ms,
+               "steps": steps, "grid": cfg["R"], "frame": [cfg["W"], cfg["H"]], "triangles": rig.sc.n_triangles}
+        if world == 1:
+            out["stages_us"] = {k: round(v, 1) for k, v in st.items()}
+            out["fragments"] = int(rig.pipe.voxel_stats().fragments)
+        elif per_rank:
+            out["stages_us_per_rank"] = per_rank
+        rig.close()
+        return out
+    except Exception as ex:   # never lose the headline line to an extra config
+        return {"error": f"{type(ex).__name__}: {ex}"}
+
+
 def run_ours(args, cfg, rank: int, world: int, local_rank: int):
     import torch
-    from voxel_cone_tracing_b200 import capi
     dist = None
     if world > 1:
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    R, W, H = cfg["R"], cfg["W"], cfg["H"]
-    sc = build_scene(cfg)
-    view, proj = S.reference_camera(W / H)
-    pipe = capi.Pipeline(sc, R, W, H, 7, ordinal=local_rank, reserve=max(1 << 20, 8 * sc.n_triangles))
-    L, dev = pipe.dev.L, pipe.dev
-    stream = torch.cuda.ExternalStream(int(L.vct_device_stream(dev.h)), device=torch.device("cuda", local_rank))
-    prm = capi.default_params(tile_rank=rank, tile_nranks=world, sampler=args.sampler, n_diffuse_cones=cfg.get("cones", 9))
-    z0, z1 = rank * R // world, (rank + 1) * R // world
-    base_t = frame_t = None
-    if world > 1:
-        base_t = torch.as_tensor(CudaArray(pipe.grid.base_ptr, (R * R * R,), "<i4"), device=torch.device("cuda", local_rank))
-        frame_t = torch.as_tensor(CudaArray(pipe.target.frame_ptr, (W * H,), "<i4"), device=torch.device("cuda", local_rank))
-    per_rank = R * R * R // world
-    # size the fragment arena for this rank's slab before anything is timed (the library grows it on overflow and asks for a re-run)
-    for _ in range(4):
-        pipe.clear(); pipe.voxelize(z0, z1)
-        try:
-            pipe.voxel_stats()
-            break
-        except capi.VctError as e:
-            if "overflow" not in str(e):
-                raise
-    pipe.clear()
-    p2p = world > 1 and args.exchange == "p2p"
-    if p2p:
-        # NVLink peer-memory exchange fused into the resolve / shade kernels (csrc/peer.cu): handles travel once, here
-        handles = [None] * world
-        dist.all_gather_object(handles, pipe.peer_export())
-        pipe.peer_connect(rank, world, handles, frame_root=0)
-        dist.barrier()
-
-    def frame_device():
-        if world == 1 or p2p:
-            pipe.render_frame(view, proj, prm)
-            return
-        with torch.cuda.stream(stream):
-            pipe.clear()
-            pipe.voxelize(z0, z1)
-            dist.all_gather_into_tensor(base_t, base_t[rank * per_rank:(rank + 1) * per_rank])   # in place, z-major slabs
-            pipe.mipmap()
-            pipe.gbuffer(view, proj)
-            frame_t.zero_()
-            pipe.trace(view, prm)
-            dist.all_reduce(frame_t)   # tiles are disjoint: integer sum == merge
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        pipe.sync()
-        torch.cuda.synchronize()
-
-    # ---- warm-up, sanity ----
-    for _ in range(max(args.warmup, 3)):
-        frame_device()
-    barrier()
-    st = pipe.voxel_stats()
-    # ---- timed region: exactly K frames, CUDA events on the launching stream ----
+    rig = Rig(cfg, args, rank, world, local_rank, torch, dist)
+    pipe = rig.pipe
+    # ---- timed region: exactly K frames after >= 3 warm-up frames, CUDA events on the launching stream, max over ranks ----
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    stage_acc = {}
-    barrier()
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-    for _ in range(args.steps):
-        frame_device()
-    with torch.cuda.stream(stream):
-        e1.record(stream)
-    barrier()
-    ms_total = e0.elapsed_time(e1)
+    ms_step = rig.timed(args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    # per-stage device times (events around each stage; separate untimed pass so that the headline has no extra events... they are cheap, but keep it clean)
-    n_stage = 0
-    if world == 1:
-        for _ in range(min(args.steps, 20)):
-            pipe.render_frame(view, proj, prm)
-            for k, v in pipe.timings().items():
-                stage_acc[k] = stage_acc.get(k, 0.0) + v
-            n_stage += 1
-        stage_acc = {k: v / n_stage for k, v in stage_acc.items()}
-    rank_stages = None
-    if world > 1:
-        t = torch.tensor([ms_total], device=f"cuda:{local_rank}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total = float(t.item())
-        if p2p:   # per-rank stage times of the last frames (CUDA events inside vct_render_frame), for the scaling analysis
-            acc = {}
-            for _ in range(10):
-                pipe.render_frame(view, proj, prm)
-                for k, v in pipe.timings().items():
-                    acc[k] = acc.get(k, 0.0) + v * 100.0     # -> us, averaged over 10
-            rank_stages = [None] * world
-            dist.all_gather_object(rank_stages, {k: round(v, 1) for k, v in acc.items()})
-    ms_step = ms_total / args.steps
     value = 1e3 / ms_step
+    st = pipe.voxel_stats()
 
-    # ---- end-to-end through the public C-ABI with HOST buffers: per step upload the whole scene from host
-    # memory (geometry, materials, draw list, lights) and read the finished frame back into pinned host memory ----
+    stage_acc, rank_stages = None, None
+    if world == 1 or rig.p2p:
+        stage_acc = rig.stage_times(min(args.steps, 20))
+        if world > 1:
+            rank_stages = [None] * world
+            dist.all_gather_object(rank_stages, {k: round(v, 1) for k, v in stage_acc.items()})
+
     e2e = None
-    if world == 1:
-        # two pinned host frames: the read-back of frame i (copy stream) overlaps the rendering of frame i+1 (device stream);
-        # every frame's pixels have landed in host memory before the clock stops
-        host_frames = [torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(2)]
-        h2d = sc.verts.nbytes + sc.indices.nbytes + sc.materials.nbytes + sc.draws.nbytes + sc.lights.nbytes + 128 + 36
-        d2h = host_frames[0].nbytes
-        for i in range(2):
-            pipe.scene.upload(sc); pipe.render_frame(view, proj, prm); pipe.target.wait(pipe.target.frame_async(host_frames[i]))
-        pipe.sync()
-        t0 = time.perf_counter()
-        prev = None
-        for i in range(args.steps):
-            pipe.scene.upload(sc)                                # H2D: geometry, materials, draw list (pinned staging ring, async)
-            pipe.render_frame(view, proj, prm)
-            tk = pipe.target.frame_async(host_frames[i & 1])     # D2H of this frame, asynchronous
-            if prev is not None:
-                pipe.target.wait(prev)                           # frame i-1 is in host memory
-            prev = tk
-        pipe.target.wait(prev)
-        pipe.sync()
-        dt = time.perf_counter() - t0
-        e2e = {"value": args.steps / dt, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "ms_per_step": 1e3 * dt / args.steps,
-               "note": "scene uploaded from host memory and the finished frame read back to pinned host memory EVERY step through the C ABI; "
-                       "the read-back of frame i overlaps the rendering of frame i+1 (vct_target_download_frame_async)"}
-        # the same loop fully serialised (blocking read-back each step), for reference
-        pipe.sync()
-        t0 = time.perf_counter()
-        for i in range(min(args.steps, 50)):
-            pipe.scene.upload(sc); pipe.render_frame(view, proj, prm); pipe.target.frame(host_frames[0])
-        pipe.sync()
-        e2e["blocking_ms_per_step"] = 1e3 * (time.perf_counter() - t0) / min(args.steps, 50)
-
-    if world > 1 and p2p:
-        # N GPUs, same loop: every rank uploads the scene and renders its share through the C ABI every step; the root (which receives
-        # the other ranks' tiles over NVLink) reads the merged frame back to pinned host memory.  Wall clock, max over ranks.
+    if world == 1 or rig.p2p:
         try:
-            h2d = sc.verts.nbytes + sc.indices.nbytes + sc.materials.nbytes + sc.draws.nbytes + sc.lights.nbytes + 128 + 36
-            host_frames = [torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(2)] if rank == 0 else None
-            for i in range(2):
-                pipe.scene.upload(sc); pipe.render_frame(view, proj, prm)
-                if rank == 0:
-                    pipe.target.wait(pipe.target.frame_async(host_frames[i]))
-            barrier()
-            t0 = time.perf_counter()
-            prev = None
-            for i in range(args.steps):
-                pipe.scene.upload(sc)
-                pipe.render_frame(view, proj, prm)
-                if rank == 0:
-                    tk = pipe.target.frame_async(host_frames[i & 1])
-                    if prev is not None:
-                        pipe.target.wait(prev)
-                    prev = tk
-            if rank == 0 and prev is not None:
-                pipe.target.wait(prev)
-            pipe.sync()
-            tt = torch.tensor([time.perf_counter() - t0], device=f"cuda:{local_rank}")
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-            dt = float(tt.item())
-            e2e = {"value": args.steps / dt, "unit": "frames/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(W * H * 4),
-                   "ms_per_step": 1e3 * dt / args.steps,
-                   "note": "every rank uploads the scene from host memory and renders its share every step, the root reads the merged frame back to "
-                           "pinned host memory (asynchronously, overlapped with the next frame); wall clock, max over ranks"}
+            e2e = e2e_loop(rig, args.steps)
         except Exception as ex:   # never lose the device-timed line to the end-to-end leg
-            e2e = None
             if rank == 0:
                 print(f"e2e leg failed: {ex}", file=sys.stderr)
 
-    # ---- roofline of the dominant kernel (cone_kernel, timed alone with CUDA events on its stream) ----
-    peak, peak_src = measured_peaks()
-    roof = None
-    stages = None
+    roof, stages = None, None
     if world == 1:
-        cnt = pipe.trace_count(view, prm)
-        t_trace = stage_acc["cone_kernel"] * 1e-3
-        gather_bytes = 192.0 * cnt.samples     # 3 directions x 2 levels x 8 texels x 4 B per sample_voxel
-        ach = gather_bytes / t_trace / 1e9
-        roof = {"kernel": "cone_kernel", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": CONE_KERNEL_DRAM_TRAFFIC.get(args.sampler) if args.config == 2 else None,
-                "peak_source": peak_src, "algorithmic_bytes_per_launch": gather_bytes, "samples_per_launch": int(cnt.samples),
-                "gsamples_per_s": cnt.samples / t_trace / 1e9,
-                "binding_units": CONE_KERNEL_NCU if (args.config == 2 and args.sampler == 1) else None,
-                "note": "algorithmic gather bytes (192 B per sample_voxel: 3 directions x 2 levels x 8 texels x 4 B) / CUDA-event kernel time. The gathers are "
-                        "served by the texture units / L1 (20.8 GB of L1TEX sectors per launch, 99 % hit) and the 126 MB L2, DRAM traffic is 0.035 GB per launch, "
-                        "so frac > 1 against the HBM copy peak is expected; the kernel is bound by the TEX pipe (76 % of one wavefront/clk/SM) and the "
-                        "issue slots (66 %), see binding_units and DESIGN.md 3.3"}
-        mip_bytes = 7.4286 * R ** 3
-        stages = {k + "_us": v * 1e3 for k, v in stage_acc.items()}
-        stages["mip_roofline"] = {"bound": "hbm", "achieved": mip_bytes / (stage_acc["mipmap"] * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-                                  "frac": mip_bytes / (stage_acc["mipmap"] * 1e-3) / 1e9 / peak, "algorithmic_bytes": mip_bytes,
-                                  "note": "dense algorithmic bytes (7.4286 R^3) / mip stage time of the running frame loop, where tiles that the voxelizer "
-                                          "did not touch and whose outputs are already zero are neither read nor written (DESIGN.md 3.2); dense build: "
-                                          "mip_dense_us"}
-        # the dense mip build (every tile read and written: first frame, uploads), CUDA events on the library's stream
-        os.environ["VCT_MIP_DENSE"] = "1"
-        pipe.mipmap(); pipe.sync()
-        d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(stream):
-            d0.record(stream)
-            for _ in range(10):
-                pipe.mipmap()
-            d1.record(stream)
-        pipe.sync()
-        del os.environ["VCT_MIP_DENSE"]
-        pipe.render_frame(view, proj, prm); pipe.sync()      # back to the tracked state
-        stages["mip_dense_us"] = d0.elapsed_time(d1) * 100.0  # ms per 10 builds -> us per build
-        stages["mip_roofline"]["dense_frac"] = mip_bytes / (stages["mip_dense_us"] * 1e-6) / 1e9 / peak
+        cnt = pipe.trace_count(rig.view, rig.prm)
+        roof = cone_roofline(rig, stage_acc["cone_kernel"], (clocks or {}).get("sm_mhz"), cnt)
+        stages = {k + "_us": v for k, v in stage_acc.items()}
+        stages["mip_roofline"] = mip_stage(rig, stage_acc)
         stages["note"] = ("gbuffer_us = the part of the G-buffer pass on the critical path: the pass (gbuffer_pass_us) runs on a second stream "
-                          "beside clear + voxelize + mip and joins before the trace, so the stage times overlap and need not add up to total_us")
-        stages["clear_gbs"] = 4.0 * R ** 3 / (stage_acc["clear"] * 1e-3) / 1e9
-        stages["voxelize_mfrag_per_s"] = st.fragments / (stage_acc["voxelize"] * 1e-3) / 1e6
+                          "beside clear + voxelize + mip and joins before the trace, so the stage times overlap and need not add up to total_us; "
+                          "clear_us = the sparse clear of the previous frame's occupied voxels (occupied_voxels words), not a bandwidth figure")
+        stages["voxelize_mfrag_per_s"] = st.fragments / (stage_acc["voxelize"] * 1e-6) / 1e6
         stages["fragments"] = int(st.fragments)
+        stages["occupied_voxels"] = int(st.occupied)
         stages["shaded_pixels"] = int(cnt.shaded_pixels)
 
     cpu = None
@@ -417,27 +510,24 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
         cpu = {"value": 1.0 / fs, "unit": "frames/s", "cores": wl.cores, "kind": "port", "sample": wl.sample_text(stride) + " (4 steps)",
                "frame_s": fs, "voxelize_s": wl.t_vox, "mip_s": wl.t_mip, "gbuffer_s": wl.t_gbuf}
 
+    n_tris = rig.sc.n_triangles
+    rig.close()
+    extra = None
+    if not args.no_extra and args.config == 2 and (world == 1 or args.exchange == "p2p"):
+        extra = {str(c): run_extra(c, args, rank, world, local_rank, torch, dist) for c in (4, 5)}
+
     if rank == 0:
         out = {"metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 RGBA storage)",
-               "data": "synthetic",
-               "config": {"workload": cfg["name"] + ", revoxelize+mip+gbuffer+trace per frame, %d diffuse + 1 specular + 1 shadow cone" % cfg.get("cones", 9),
-                          "sampler": "texture units (levels >= 1), software level 0" if args.sampler == 1 else "software fp32 trilinear",
-                          "grid": R, "frame": [W, H], "triangles": sc.n_triangles, "parallelism": f"z-slab voxelize + screen-tile trace x{world}" + ("" if world == 1 else (", sparse NVLink peer-store exchange fused into the resolve/shade kernels (CUDA IPC, no collective)" if p2p else ", NCCL all-gather of the base level + all-reduce of the frame")),
-                          "l2": "no explicit flush: grid + G-buffer + frame working set (%.0f MB) exceeds the 126 MB L2 and is rewritten every frame"
-                                % ((pipe.grid.nbytes + W * H * 40) / 1e6)},
+               "data": "synthetic", "config": config_dict(cfg, world, args.sampler, args.exchange, n_tris),
                "clocks": clocks, "e2e": e2e, "gpu_launches": KERNELS_PER_FRAME * args.steps, "roofline": roof, "cpu_baseline": cpu}
         if stages:
             out["stages"] = stages
         if rank_stages:
             out["stages_us_per_rank"] = rank_stages
+        if extra:
+            out["extra_configs"] = extra
         print(json.dumps(out), flush=True)
-    if p2p:
-        pipe.peer_check()        # raises if a flag wait ever timed out
-        barrier()                # nobody unmaps while a peer may still be storing into it
-        pipe.peer_disconnect()
-        barrier()
-    pipe.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -450,6 +540,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the device-timed runs of configs 4 and 5 (extra_configs)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
                     help="multi-GPU exchange: p2p = sparse voxel push + tile push over NVLink peer memory, fused into the kernels (default); "
                          "nccl = dense in-place all-gather of the base level + all-reduce of the frame (the library baseline)")
@@ -459,7 +550,7 @@ def main():
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
-        run_reference(args, cfg, rank)
+        run_reference(args, cfg, rank, world)
         return
     run_ours(args, cfg, rank, world, local_rank)
 

@@ -113,16 +113,22 @@ struct Renderer {
   void set_sampler(int vct_sampler) { m_sampler = vct_sampler; }  // VCT_SAMPLER_FP32 / VCT_SAMPLER_TEX
   void set_diffuse_cone_count(int n) { m_diffuse_cones = n; }     // 9 = reference, 5 = BASELINE.json variant
   void set_rank(int rank, int nranks) { m_rank = rank; m_nranks = nranks; }  // multi-GPU: z-slab / screen-tile share of this process
+  void set_staged_passes(bool on) { m_staged = on; }   // render() = voxelize(); visualize() as separate stage calls instead of one vct_render_frame
+  int last_error() const { return m_last_rc; }         // VCT_OK or the error code of the last render()
   const material_data_t& get_material_data(material_id_t id) const { return m_material_data[id]; }
   size_t triangle_count() const { return m_indices.size() / 3; }
 
  private:
   void draw_models();   // flattens m_draw_queue into the device draw list (renderer.cpp:240-257)
-  void filter();        // renderer.cpp:283-314
   void upload_lights(); // renderer.cpp:259-273
-  void upload_camera(); // renderer.cpp:275-281
-  void voxelize();      // renderer.cpp:316-353
-  void visualize();     // renderer.cpp:355-390
+  // The reference's private passes, kept as the stage-by-stage path (set_staged_passes(true): each is one C-ABI stage call, the
+  // G-buffer pass runs in line).  render() otherwise issues ONE vct_render_frame, which overlaps the G-buffer pass with
+  // clear + voxelize + filter on a second stream.  (upload_camera, renderer.cpp:275-281, has no counterpart: the matrices are
+  // kernel arguments, there is no UBO.)
+  bool voxelize();      // renderer.cpp:316-353: clear + scatter, then filter()
+  bool filter();        // renderer.cpp:283-314
+  bool visualize();     // renderer.cpp:355-390
+  vct_trace_params_t trace_params() const;
   bool upload_geometry();
   bool upload_materials();
 
@@ -148,6 +154,8 @@ struct Renderer {
   int m_view_voxel_dir = 7;
   float m_view_voxel_lod = 0.0f;
   int m_sampler = VCT_SAMPLER_TEX, m_diffuse_cones = 9, m_rank = 0, m_nranks = 1;
+  bool m_staged = false;
+  int m_last_rc = 0;
 
   // Per frame
   std::vector<model_t> m_draw_queue;

@@ -110,7 +110,7 @@ int vct_grid_destroy(vct_grid_t* g);
 int vct_grid_clear(vct_grid_t* g);                                        /* clear_tex_3d x6, renderer.cpp:320-321 */
 int vct_grid_upload_base(vct_grid_t* g, const uint32_t* host_rgba8);      /* R^3 texels, [z][y][x] */
 int vct_grid_download(vct_grid_t* g, int level, int dir, uint32_t* host); /* glGetTexImage equivalent; level 0 ignores dir */
-int vct_grid_download_array(vct_grid_t* g, int level, int dir, uint32_t* host); /* level >= 1 read back from the mipmapped CUDA array the texture units sample (must equal vct_grid_download) */
+int vct_grid_download_array(vct_grid_t* g, int level, int dir, uint32_t* host); /* level >= 1; same as vct_grid_download (levels >= 1 live only in the mipmapped CUDA array the texture units sample) */
 /* occupancy bit masks written by vct_mipmap and read by the cone tracer to skip all-zero filter footprints (no reference
  * counterpart; inspection only).  dilated = 0: bit (z*N + y)*N + x = texel non-zero in any direction; dilated = 1: volume of
  * (N+1)^3 bits in rows of (N+32)/32 words, bit (x+1,y+1,z+1) = any texel of [x,x+1]x[y,y+1]x[z,z+1] non-zero. */
@@ -158,6 +158,16 @@ int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_targ
  * beside [0]-[2], this is what is left of it after the mip build) [4] trace (tile list + cones + shade) [5] total
  * [6] cone kernel alone [7] the G-buffer pass itself on its own stream (0 when it ran in line); synchronises */
 int vct_last_frame_timings(vct_device_t* dev, float out_ms[8]);
+
+/* measurement / test switches (replace the environment variables of round 1; nothing on the launch path reads the environment):
+ *   VCT_DEBUG_MIP_DENSE    1 = every vct_mipmap reads and writes every tile (the dense build a first frame or an upload pays)
+ *   VCT_DEBUG_CONE_VARIANT -1 = automatic, 0 = literal shader loop, 1 = every fetch blends two levels, 2 = one warp per cone slot,
+ *                          3 = all diffuse cones of a tile in one warp
+ *   VCT_DEBUG_CONE_GRID    1 = cone kernel on a grid sized by the host instead of the persistent work queue */
+#define VCT_DEBUG_MIP_DENSE 1
+#define VCT_DEBUG_CONE_VARIANT 2
+#define VCT_DEBUG_CONE_GRID 3
+int vct_debug_set(vct_device_t* dev, int key, int value);
 
 /* ---- multi-GPU (no reference counterpart: the reference is single-GPU).  One process per GPU on one node; the exchange
  *      runs over NVLink peer memory (CUDA IPC), fused into the producing kernels -- see csrc/peer.cu.  Protocol:

@@ -21,7 +21,10 @@
  *      an edge is covered iff the edge is a left edge (dy < 0 for the counter-clockwise
  *      orientation in y-up window space) or a top edge (dy == 0 && dx < 0); zero-area
  *      triangles produce nothing; x/y clipping = scissor to the viewport; triangles with a
- *      vertex beyond a +-2^21 pixel guard band, or (camera pass) with any w <= 0, are dropped.
+ *      vertex beyond a +-2^21 pixel guard band are dropped.
+ *   R2c camera pass: a triangle with a vertex in front of the near plane (z_c < -w_c) is clipped
+ *      against that plane in clip space before the divide (see orc_gbuffer); the far plane is
+ *      the per-fragment test of R3.
  *   R3 interpolation: b_k = float(E_k) / float(2A) from the SNAPPED positions; affine
  *      attributes ((b0*a0 + b1*a1) + b2*a2); perspective attributes
  *      ((q0*a0 + q1*a1) + q2*a2) / ((q0 + q1) + q2) with q_k = b_k * (1 / w_k);
@@ -689,6 +692,7 @@ int orc_gbuffer(const orc_scene_t* sc, const float view[16], const float proj[16
   mat4_mul(proj, view, pv); /* projection * view, voxel_cone_tracing.vert:25 */
 
   struct TriRec { RasterTri rt; V3 world[3], nrm[3]; float iw[3], zw[3]; uint32_t material; uint32_t seq; };
+  struct ClipVert { V4 clip; V3 world, nrm; };
   std::vector<TriRec> tris;
   uint32_t seq = 0;
   for (uint32_t d = 0; d < sc->n_draws; d++) {
@@ -696,29 +700,70 @@ int orc_gbuffer(const orc_scene_t* sc, const float view[16], const float proj[16
     float nm[9];
     normal_matrix(dr.model, nm);
     for (uint32_t t = 0; t + 3 <= dr.index_count; t += 3, seq++) {
-      TriRec r;
-      r.seq = seq;
-      r.material = dr.material;
-      float xw[3], yw[3];
-      bool ok = true;
+      ClipVert in[3];
+      float dn[3]; /* signed distance to the near plane in clip space: z_c + w_c >= 0 is inside (-w <= z) */
+      int n_out = 0;
       for (int k = 0; k < 3; k++) {
         const orc_vertex_t& v = sc->verts[dr.vertex_base + sc->indices[dr.first_index + t + k]];
         V4 w = mat4_mul_point(dr.model, v3(v.pos[0], v.pos[1], v.pos[2])); /* :24 */
-        r.world[k] = v3(w.x, w.y, w.z);
-        r.nrm[k] = normalize(mat3_mul(nm, v3(v.norm[0], v.norm[1], v.norm[2]))); /* :26 */
-        V4 clip = mat4_mul_v4(pv, w);
-        if (!(clip.w > 0.0f)) { ok = false; break; } /* R2 */
-        float iw = 1.0f / clip.w;
-        r.iw[k] = iw;
-        float xn = clip.x * iw, yn = clip.y * iw, zn = clip.z * iw;
-        xw[k] = (xn + 1.0f) * ((float)W * 0.5f);
-        yw[k] = (yn + 1.0f) * ((float)H * 0.5f);
-        r.zw[k] = (zn + 1.0f) * 0.5f;
+        in[k].world = v3(w.x, w.y, w.z);
+        in[k].nrm = normalize(mat3_mul(nm, v3(v.norm[0], v.norm[1], v.norm[2]))); /* :26 */
+        in[k].clip = mat4_mul_v4(pv, w);
+        dn[k] = in[k].clip.z + in[k].clip.w;
+        if (!(dn[k] >= 0.0f)) n_out++;   /* also NaN */
       }
-      if (!ok) continue;
-      r.rt = raster_setup(xw, yw, W, H);
-      if (!r.rt.valid) continue;
-      tris.push_back(r);
+      if (n_out == 3) continue;
+      /* R2c: near-plane clipping (GL clips primitives against -w <= z, OpenGL 4.5 13.7; src/renderer.cpp:384-388 enables nothing that
+       * would change it).  Sutherland-Hodgman on the one plane; a new vertex is always computed FROM THE INSIDE vertex of its edge
+       * (t = d_in / (d_in - d_out), P = in + t * (out - in), fp32, no FMA) so that two triangles sharing the edge get the same point.
+       * The 3- or 4-vertex polygon is drawn as the fan (p0,p1,p2), (p0,p2,p3); every piece keeps the triangle's sequence number. */
+      ClipVert poly[4];
+      int np = 0;
+      if (n_out == 0) {
+        poly[0] = in[0]; poly[1] = in[1]; poly[2] = in[2]; np = 3;
+      } else {
+        for (int k = 0; k < 3; k++) {
+          const int k1 = (k + 1) % 3;
+          const bool in_a = dn[k] >= 0.0f, in_b = dn[k1] >= 0.0f;
+          if (in_a) poly[np++] = in[k];
+          if (in_a != in_b) {
+            const ClipVert& vi = in_a ? in[k] : in[k1];
+            const ClipVert& vo = in_a ? in[k1] : in[k];
+            const float di = in_a ? dn[k] : dn[k1], dout = in_a ? dn[k1] : dn[k];
+            const float tt = di / (di - dout);
+            ClipVert c;
+            c.clip.x = vi.clip.x + tt * (vo.clip.x - vi.clip.x); c.clip.y = vi.clip.y + tt * (vo.clip.y - vi.clip.y);
+            c.clip.z = vi.clip.z + tt * (vo.clip.z - vi.clip.z); c.clip.w = vi.clip.w + tt * (vo.clip.w - vi.clip.w);
+            c.world = add(vi.world, mul(sub(vo.world, vi.world), tt));
+            c.nrm = add(vi.nrm, mul(sub(vo.nrm, vi.nrm), tt));
+            poly[np++] = c;
+          }
+        }
+      }
+      for (int piece = 0; piece + 3 <= np; piece++) {
+        const ClipVert* pvt[3] = {&poly[0], &poly[piece + 1], &poly[piece + 2]};
+        TriRec r;
+        r.seq = seq;
+        r.material = dr.material;
+        float xw[3], yw[3];
+        bool ok = true;
+        for (int k = 0; k < 3; k++) {
+          const V4 clip = pvt[k]->clip;
+          r.world[k] = pvt[k]->world;
+          r.nrm[k] = pvt[k]->nrm;
+          if (!(clip.w > 0.0f)) { ok = false; break; } /* R2: cannot happen behind a near plane with near > 0; guards general matrices */
+          float iw = 1.0f / clip.w;
+          r.iw[k] = iw;
+          float xn = clip.x * iw, yn = clip.y * iw, zn = clip.z * iw;
+          xw[k] = (xn + 1.0f) * ((float)W * 0.5f);
+          yw[k] = (yn + 1.0f) * ((float)H * 0.5f);
+          r.zw[k] = (zn + 1.0f) * 0.5f;
+        }
+        if (!ok) continue;
+        r.rt = raster_setup(xw, yw, W, H);
+        if (!r.rt.valid) continue;
+        tris.push_back(r);
+      }
     }
   }
   /* row bands in parallel; inside a band triangles are visited in draw order => GL_LESS, first wins ties */

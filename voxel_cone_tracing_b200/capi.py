@@ -22,7 +22,7 @@ EXPORTS = [
     "vct_target_create", "vct_target_destroy", "vct_target_download_frame", "vct_target_download_frame_async", "vct_target_download_wait",
     "vct_target_download_gbuffer", "vct_target_frame_device_ptr",
     "vct_voxelize", "vct_voxelize_reserve", "vct_voxelize_stats", "vct_mipmap", "vct_gbuffer", "vct_cone_trace", "vct_cone_trace_count",
-    "vct_render_frame", "vct_last_frame_timings",
+    "vct_render_frame", "vct_last_frame_timings", "vct_debug_set",
     "vct_peer_export", "vct_peer_connect", "vct_peer_disconnect", "vct_peer_error",
     "vct_tex3d_create", "vct_tex3d_destroy", "vct_tex3d_clear", "vct_tex3d_mip", "vct_tex3d_upload", "vct_tex3d_download",
 ]
@@ -59,6 +59,7 @@ def default_params(**kw) -> TraceParams:
 
 _lib = None
 PEER_HANDLE_BYTES = 320   # sizeof(vct_peer_handle_t)
+DEBUG_MIP_DENSE, DEBUG_CONE_VARIANT, DEBUG_CONE_GRID = 1, 2, 3   # vct_debug_set keys
 SAMPLER_FP32, SAMPLER_TEX = 0, 1
 DEFAULT_SAMPLER = int(os.environ.get("VCT_SAMPLER", "0"))
 
@@ -111,6 +112,7 @@ def load():
     L.vct_cone_trace_count.argtypes = [vp, vp, vp, f32p, C.POINTER(TraceParams), vp, C.POINTER(TraceStats)]
     L.vct_render_frame.argtypes = [vp, vp, vp, vp, f32p, f32p, C.POINTER(TraceParams)]
     L.vct_last_frame_timings.argtypes = [vp, f32p]
+    L.vct_debug_set.argtypes = [vp, i32, i32]
     L.vct_peer_export.argtypes = [vp, vp, vp, vp]
     L.vct_peer_connect.argtypes = [vp, vp, vp, i32, i32, vp, i32]
     L.vct_peer_disconnect.argtypes = [vp]
@@ -144,6 +146,10 @@ class Device:
 
     def sync(self):
         check(self.L.vct_device_sync(self.h))
+
+    def debug_set(self, key: int, value: int):
+        """measurement / test switches (vct_debug_set): DEBUG_MIP_DENSE, DEBUG_CONE_VARIANT, DEBUG_CONE_GRID"""
+        check(self.L.vct_debug_set(self.h, key, value))
 
     def close(self):
         if self.h:

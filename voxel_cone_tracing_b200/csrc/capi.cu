@@ -105,6 +105,33 @@ int scene_ready(vct_scene* sc) {
   return VCT_OK;
 }
 
+// What the kernels reported through the mapped status words since the last call (host-side poll, nothing is enqueued):
+//  * arena overflow: the voxelization of an earlier frame dropped fragments (which ones depends on atomic order).  The arena is
+//    grown to what that frame wanted (+25 %) and VCT_ERR_OVERFLOW is returned ONCE: the caller re-issues the frame
+//    (vct::Renderer::render does).  The frame that overflowed is reported at the next call that sees the word, i.e. one or two
+//    frames later when frames are queued asynchronously, immediately after a vct_device_sync / blocking download.
+//  * peer timeout: a flag wait of the multi-GPU exchange gave up (csrc/peer.cu): the frame was built from incomplete data.
+int check_status(vct_device* dev) {
+  if (!dev->status_host) return VCT_OK;
+  if (const uint32_t r = dev->status_host[STATUS_PEER]) {
+    dev->status_host[STATUS_PEER] = 0u;
+    set_error("peer wait timed out: rank %u never signalled (peer process dead, not connected, or frames out of step); the last frame is incomplete", r - 1u);
+    return VCT_ERR_CUDA;
+  }
+  if (const uint32_t wanted = dev->status_host[STATUS_OVERFLOW]) {
+    dev->status_host[STATUS_OVERFLOW] = 0u;
+    const uint64_t cap = dev->frag_capacity, want = (uint64_t)wanted + wanted / 4;
+    set_error("fragment arena overflow: a voxelization produced %u fragments, capacity %llu; the arena has been grown, re-issue the frame", wanted,
+              (unsigned long long)cap);
+    if (want > cap) {
+      int rc = vct_voxelize_reserve(dev, want < 0xFFFFFFF0ull ? want : 0xFFFFFFEFull);
+      if (rc) return rc;
+    }
+    return VCT_ERR_OVERFLOW;
+  }
+  return VCT_OK;
+}
+
 }  // namespace vct
 
 using namespace vct;
@@ -143,6 +170,9 @@ int vct_device_create(int ordinal, vct_device_t** out) {
   VCT_CUDA(cudaMalloc(&d->counters, CNT_TOTAL * sizeof(uint32_t)));
   VCT_CUDA(cudaMemset(d->counters, 0, CNT_TOTAL * sizeof(uint32_t)));
   VCT_CUDA(cudaMallocHost(&d->counters_host, CNT_TOTAL * sizeof(uint32_t)));
+  VCT_CUDA(cudaHostAlloc((void**)&d->status_host, STATUS_WORDS * sizeof(uint32_t), cudaHostAllocMapped));
+  for (int i = 0; i < STATUS_WORDS; i++) d->status_host[i] = 0u;
+  VCT_CUDA(cudaHostGetDevicePointer((void**)&d->status_dev, (void*)d->status_host, 0));
   for (int i = 0; i < 8; i++) VCT_CUDA(cudaEventCreate(&d->ev[i]));
   VCT_CUDA(cudaStreamCreateWithPriority(&d->stream2, cudaStreamNonBlocking, prio_lo));
   VCT_CUDA(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
@@ -160,10 +190,10 @@ int vct_device_destroy(vct_device_t* d) {
   cudaStreamSynchronize(d->stream);
   cudaFree(d->peer_flags);
   cudaFree(d->frags); cudaFree(d->fresh);
-  for (auto& r : d->rs) { cudaFree(r.tri_recs); cudaFree(r.item_local); cudaFree(r.item_block); }
+  for (auto& r : d->rs) { cudaFree(r.tri_recs); cudaFree(r.item_local); cudaFree(r.item_block); cudaFree(r.big_slot); }
   if (d->stream2) { cudaStreamSynchronize(d->stream2); cudaStreamDestroy(d->stream2); }
   for (cudaEvent_t e : {d->ev_fork, d->ev_join, d->ev_g0, d->ev_g1}) if (e) cudaEventDestroy(e);
-  cudaFree(d->counters); cudaFreeHost(d->counters_host);
+  cudaFree(d->counters); cudaFreeHost(d->counters_host); cudaFreeHost((void*)d->status_host);
   for (int i = 0; i < 8; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
   cudaStreamDestroy(d->stream);
   delete d;
@@ -173,7 +203,7 @@ int vct_device_destroy(vct_device_t* d) {
 int vct_device_sync(vct_device_t* d) {
   VCT_REQUIRE(d, "device is null");
   VCT_CUDA(cudaStreamSynchronize(d->stream));
-  return VCT_OK;
+  return check_status(d);
 }
 
 void* vct_device_stream(vct_device_t* d) { return d ? (void*)d->stream : nullptr; }
@@ -270,7 +300,8 @@ int vct_scene_set_cube_size(vct_scene_t* s, float cube_size) {
 // ------------------------------------------------------------------ grid
 int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) {
   VCT_REQUIRE(dev && out, "null argument");
-  VCT_REQUIRE(R >= 2 && R <= 2048 && (R & (R - 1)) == 0, "resolution must be a power of two in [2, 2048]");
+  // 1024 = the largest size the 32-bit voxel index (fragment records, tile flags, sparse clear) addresses and the tests cover
+  VCT_REQUIRE(R >= 2 && R <= 1024 && (R & (R - 1)) == 0, "resolution must be a power of two in [2, 1024]");
   VCT_REQUIRE(levels >= 1 && levels <= VCT_MAX_LEVELS && (R >> (levels - 1)) >= 1, "levels must satisfy 1 <= levels <= log2(R)+1");
   vct_grid* g = new (std::nothrow) vct_grid();
   if (!g) { set_error("out of host memory"); return VCT_ERR_OOM; }
@@ -279,16 +310,28 @@ int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) {
   cudaError_t e = cudaMalloc(&g->base, n0 * 4);
   g->base_buf[0] = g->base;
   g->bytes = n0 * 4;
-  for (int l = 1; l < levels && e == cudaSuccess; l++) {
-    size_t n = (size_t)(R >> l) * (R >> l) * (R >> l);
-    e = cudaMalloc(&g->lvl[l], n * 24);
-    g->bytes += n * 24;
-  }
-  // occupancy bit masks (plain + 2x2x2-dilated) per level, written by the mip stage
-  if (levels >= 4 && R % 32 == 0) {   // the fused mip path: one flag per 32x8x8 tile
-    const size_t n_tiles = (size_t)(R / 32) * (R / 8) * (R / 8);
-    if (e == cudaSuccess) e = cudaMalloc(&g->tile_touched, n_tiles);
-    if (e == cudaSuccess) e = cudaMemsetAsync(g->tile_touched, 0, n_tiles, dev->stream);
+  if (mip_fused_applies(R, levels)) {
+    // the fused mip kernel (csrc/mipmap.cu): one flag pair per 32x16x8 tile, arrival counters per 32^3 block, and the small linear
+    // copies of the coarse levels that cross CTAs inside the launch
+    const size_t n_tiles = n0 / 4096, n_blocks = n0 / 32768, n3 = n0 / 512;
+    auto zalloc = [&](void** p, size_t bytes) {
+      if (e == cudaSuccess) e = cudaMalloc(p, bytes);
+      if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, bytes, dev->stream);
+      g->bytes += bytes;
+    };
+    zalloc((void**)&g->tile_touched, n_tiles);
+    zalloc((void**)&g->tile_zero, n_tiles);           // 0 = unknown: the first build writes everything
+    zalloc((void**)&g->mip_counters, (1 + n_blocks) * 4);
+    zalloc((void**)&g->rec3, n3 * 24);
+    size_t top_words = 0, occ_bytes = 0;
+    for (int l = 3; l < levels; l++) {
+      const size_t n = (size_t)(R >> l) * (R >> l) * (R >> l);
+      g->occb_off[l] = (uint32_t)occ_bytes;
+      occ_bytes += (n + 15) & ~(size_t)15;
+      if (l >= 5) { g->top_off[l] = (uint32_t)top_words; top_words += n * 6; }
+    }
+    zalloc((void**)&g->rec_top, top_words * 4);
+    zalloc((void**)&g->occb, occ_bytes);
   }
   size_t docc_total = 0;   // the dilated bits of all levels share one allocation (256-byte aligned parts)
   for (int l = 0; l < levels; l++) {
@@ -298,9 +341,27 @@ int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) {
   if (e == cudaSuccess) e = cudaMalloc(&g->docc_all, docc_total * 4);
   if (e == cudaSuccess) e = cudaMemsetAsync(g->docc_all, 0, docc_total * 4, dev->stream);
   g->bytes += docc_total * 4;
+  // plain occupancy bits: levels 0-3 on their own, levels 4.. in one allocation (the fused mip kernel zeroes that range, and the dilated
+  // bits of the same levels, every build: the tail kernel ORs the occupied texels in)
+  size_t occ_hi_total = 0;
+  for (int l = 4; l < levels; l++) occ_hi_total += (occ_words(R >> l) + 3) & ~(size_t)3;
+  if (occ_hi_total && e == cudaSuccess) {
+    e = cudaMalloc(&g->occ_hi, occ_hi_total * 4);
+    if (e == cudaSuccess) e = cudaMemsetAsync(g->occ_hi, 0, occ_hi_total * 4, dev->stream);
+    g->bytes += occ_hi_total * 4;
+  }
+  g->occ_hi_words = (uint32_t)occ_hi_total;
+  g->docc_hi_off = levels > 4 ? g->docc_off[4] : (uint32_t)docc_total;
+  g->docc_hi_words = (uint32_t)(docc_total - g->docc_hi_off);
+  size_t hi_off = 0;
   for (int l = 0; l < levels && e == cudaSuccess; l++) {
     const int N = R >> l;
     g->docc[l] = g->docc_all + g->docc_off[l];
+    if (l >= 4) {
+      g->occ[l] = g->occ_hi + hi_off;
+      hi_off += (occ_words(N) + 3) & ~(size_t)3;
+      continue;
+    }
     e = cudaMalloc(&g->occ[l], occ_words(N) * 4);
     if (e == cudaSuccess) e = cudaMemsetAsync(g->occ[l], 0, occ_words(N) * 4, dev->stream);
     g->bytes += occ_words(N) * 4;
@@ -365,6 +426,9 @@ int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) {
       e = cudaCreateTextureObject(&g->tex_lin, &rd, &td, nullptr);
       td.mipmapFilterMode = cudaFilterModePoint;   // same texels, one (the nearest) level per fetch
       if (e == cudaSuccess) e = cudaCreateTextureObject(&g->tex_one, &rd, &td, nullptr);
+      td.filterMode = cudaFilterModePoint;         // the raw texel: what the software sampler (fp32 weights, rule R7) fetches
+      td.readMode = cudaReadModeElementType;
+      if (e == cudaSuccess) e = cudaCreateTextureObject(&g->tex_pt, &rd, &td, nullptr);
       g->tex_zs = (float)n_coarse / (float)(6 * pitch_coarse);
     }
   }
@@ -382,11 +446,14 @@ int vct_grid_destroy(vct_grid_t* g) {
   if (g->dev->peer_grid == g) vct_peer_disconnect(g->dev);
   cudaStreamSynchronize(g->dev->stream);
   cudaFree(g->base_buf[0]); cudaFree(g->base_buf[1]); cudaFree(g->tile_zero); cudaFree(g->tile_touched);
+  cudaFree(g->rec3); cudaFree(g->rec_top); cudaFree(g->occb); cudaFree(g->mip_counters);
   if (g->dev->vox_owner == g) g->dev->vox_owner = nullptr;
-  for (int l = 0; l < VCT_MAX_LEVELS; l++) { cudaFree(g->lvl[l]); cudaFree(g->occ[l]); }
+  for (int l = 0; l < 4; l++) cudaFree(g->occ[l]);
+  cudaFree(g->occ_hi);
   cudaFree(g->docc_all);
   if (g->tex_lin) cudaDestroyTextureObject(g->tex_lin);
   if (g->tex_one) cudaDestroyTextureObject(g->tex_one);
+  if (g->tex_pt) cudaDestroyTextureObject(g->tex_pt);
   for (int l = 0; l < VCT_MAX_LEVELS; l++) if (g->surf.s[l]) cudaDestroySurfaceObject(g->surf.s[l]);
   if (g->marr) cudaFreeMipmappedArray(g->marr);
   delete g;
@@ -396,18 +463,19 @@ int vct_grid_destroy(vct_grid_t* g) {
 int vct_grid_clear(vct_grid_t* g) {
   VCT_REQUIRE(g, "grid is null");
   vct_device* dev = g->dev;
-  if (g->base_zero && !g->external) return VCT_OK;                       // nothing has been written since the last clear
+  if (g->base_zero && !g->external) { g->dirty_z0 = g->dirty_z1 = 0; return VCT_OK; }   // nothing has been written since the last clear
   if (g->sparse_clear_ok && !g->external && dev->vox_owner == g) {
     // the non-zero words are exactly the occupied list of the last voxelization: zero those (and their tile flags)
     int rc = launch_sparse_clear(dev, g);
     if (rc) return rc;
   } else {
     VCT_CUDA(cudaMemsetAsync(g->base, 0, (size_t)g->R * g->R * g->R * 4, dev->stream));
-    if (g->tile_touched) VCT_CUDA(cudaMemsetAsync(g->tile_touched, 0, (size_t)(g->R / 32) * (g->R / 8) * (g->R / 8), dev->stream));
+    if (g->tile_touched) VCT_CUDA(cudaMemsetAsync(g->tile_touched, 0, (size_t)g->R * g->R * g->R / 4096, dev->stream));
   }
   g->sparse_clear_ok = false;
   g->flags_valid = g->tile_touched != nullptr && !g->external;
   g->base_zero = !g->external;
+  g->dirty_z0 = g->dirty_z1 = 0;
   return VCT_OK;
 }
 
@@ -424,34 +492,29 @@ int vct_grid_download(vct_grid_t* g, int level, int dir, uint32_t* host) {
   VCT_REQUIRE(level >= 0 && level < g->levels, "bad level");
   VCT_REQUIRE(dir >= 0 && dir < 6, "bad direction");
   cudaStream_t s = g->dev->stream;
-  size_t N = (size_t)(g->R >> level), n = N * N * N;
+  const size_t N = (size_t)(g->R >> level);
   if (level == 0) {
-    VCT_CUDA(cudaMemcpyAsync(host, g->base, n * 4, cudaMemcpyDeviceToHost, s));
+    VCT_CUDA(cudaMemcpyAsync(host, g->base, N * N * N * 4, cudaMemcpyDeviceToHost, s));
   } else {
-    // strided gather of one direction out of the 6-word records
-    VCT_CUDA(cudaMemcpy2DAsync(host, 4, g->lvl[level] + dir, 24, 4, n, cudaMemcpyDeviceToHost, s));
+    // direction `dir` of the stacked mipmapped array (the only copy of levels >= 1)
+    cudaArray_t arr;
+    VCT_CUDA(cudaGetMipmappedArrayLevel(&arr, g->marr, (unsigned)(level - 1)));
+    cudaMemcpy3DParms p;
+    memset(&p, 0, sizeof p);
+    p.srcArray = arr;
+    p.srcPos = make_cudaPos(0, 0, (size_t)dir * g->surf.pitch[level]);
+    p.dstPtr = make_cudaPitchedPtr(host, N * 4, N, N);
+    p.extent = make_cudaExtent(N, N, N);
+    p.kind = cudaMemcpyDeviceToHost;
+    VCT_CUDA(cudaMemcpy3DAsync(&p, s));
   }
   VCT_CUDA(cudaStreamSynchronize(s));
   return VCT_OK;
 }
 
 int vct_grid_download_array(vct_grid_t* g, int level, int dir, uint32_t* host) {
-  VCT_REQUIRE(g && host, "null argument");
-  VCT_REQUIRE(level >= 1 && level < g->levels, "bad level (the arrays hold levels >= 1)");
-  VCT_REQUIRE(dir >= 0 && dir < 6, "bad direction");
-  cudaArray_t arr;
-  VCT_CUDA(cudaGetMipmappedArrayLevel(&arr, g->marr, (unsigned)(level - 1)));
-  const size_t N = (size_t)(g->R >> level);
-  cudaMemcpy3DParms p;
-  memset(&p, 0, sizeof p);
-  p.srcArray = arr;
-  p.srcPos = make_cudaPos(0, 0, (size_t)dir * g->surf.pitch[level]);   // direction `dir` of the stacked array
-  p.dstPtr = make_cudaPitchedPtr(host, N * 4, N, N);
-  p.extent = make_cudaExtent(N, N, N);
-  p.kind = cudaMemcpyDeviceToHost;
-  VCT_CUDA(cudaMemcpy3DAsync(&p, g->dev->stream));
-  VCT_CUDA(cudaStreamSynchronize(g->dev->stream));
-  return VCT_OK;
+  VCT_REQUIRE(g && level >= 1, "bad level (the array holds levels >= 1)");
+  return vct_grid_download(g, level, dir, host);
 }
 
 size_t vct_grid_occupancy_words(const vct_grid_t* g, int level, int dilated) {
@@ -522,7 +585,7 @@ int vct_target_download_frame(vct_target_t* t, uint32_t* host) {
   VCT_REQUIRE(t && host, "null argument");
   VCT_CUDA(cudaMemcpyAsync(host, t->frame, (size_t)t->W * t->H * 4, cudaMemcpyDeviceToHost, t->dev->stream));
   VCT_CUDA(cudaStreamSynchronize(t->dev->stream));
-  return VCT_OK;
+  return check_status(t->dev);   // the pixels were copied, but they come from a frame that dropped fragments / missed a peer
 }
 
 // Asynchronous read-back.  The finished frame is snapshotted on the device stream by a kernel (8 MB at 1080p, a few us), the
@@ -615,6 +678,12 @@ int vct_voxelize_reserve(vct_device_t* dev, uint64_t max_fragments) {
 int vct_voxelize(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, int z0, int z1) {
   VCT_REQUIRE(dev && sc && g, "null argument");
   VCT_REQUIRE(z0 >= 0 && z1 <= g->R && z0 <= z1, "bad z slab");
+  // The level-0 word doubles as the head of the voxel's fragment list while the slab is being voxelized: content left in the slab
+  // (an earlier vct_voxelize of an overlapping slab, vct_grid_upload_base) would be taken for list links.  The reference would
+  // keep averaging into it (voxelize.frag:95-120); here the precondition of the header ("cleared") is enforced.
+  VCT_REQUIRE(g->external || z0 >= g->dirty_z1 || z1 <= g->dirty_z0 || g->dirty_z0 >= g->dirty_z1,
+              "the z slab overlaps voxels written since the last vct_grid_clear (voxelize each slab once per clear)");
+  if (int rc = check_status(dev)) return rc;
   if (int rc = scene_ready(sc)) return rc;
   return launch_voxelize(dev, sc, g, z0, z1);
 }
@@ -628,15 +697,18 @@ int vct_voxelize_stats(vct_device_t* dev, vct_voxel_stats_t* out) {
   out->occupied = dev->counters_host[CNT_OCCUPIED];
   out->max_per_voxel = dev->counters_host[CNT_MAXLIST];
   out->capacity = dev->frag_capacity;
-  if (out->fragments > dev->frag_capacity) {
-    uint64_t want = out->fragments + out->fragments / 4;
-    set_error("fragment arena overflow: %llu fragments > capacity %llu; arena grown, re-run the frame", (unsigned long long)out->fragments,
-              (unsigned long long)dev->frag_capacity);
-    int rc = vct_voxelize_reserve(dev, want);
-    if (rc) return rc;
-    return VCT_ERR_OVERFLOW;
+  return check_status(dev);   // VCT_ERR_OVERFLOW (arena grown) if this voxelization dropped fragments
+}
+
+int vct_debug_set(vct_device_t* dev, int key, int value) {
+  VCT_REQUIRE(dev, "device is null");
+  switch (key) {
+    case VCT_DEBUG_MIP_DENSE: dev->debug_mip_dense = value != 0; return VCT_OK;
+    case VCT_DEBUG_CONE_VARIANT: VCT_REQUIRE(value >= -1 && value <= 3, "cone variant must be -1..3"); dev->debug_cone_variant = value; return VCT_OK;
+    case VCT_DEBUG_CONE_GRID: dev->debug_cone_grid = value != 0; return VCT_OK;
   }
-  return VCT_OK;
+  set_error("vct_debug_set: unknown key %d", key);
+  return VCT_ERR_INVALID;
 }
 
 int vct_mipmap(vct_device_t* dev, vct_grid_t* g) {
@@ -726,6 +798,7 @@ static int render_frame_sharded(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* 
 int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_target_t* t, const float view[16], const float proj[16],
                      const vct_trace_params_t* p) {
   VCT_REQUIRE(dev && sc && g && t && view && proj && p, "null argument");
+  if (int rc0 = check_status(dev)) return rc0;   // an earlier frame overflowed the fragment arena (grown now: re-issue) or missed a peer
   if (int rc0 = scene_ready(sc)) return rc0;   // the frame stream waits for the scene uploads in flight (they run on their own stream)
   if (dev->peers.nranks > 1 && dev->peer_grid == g && dev->peer_target == t) return render_frame_sharded(dev, sc, g, t, view, proj, p);
   cudaStream_t s = dev->stream;

@@ -21,7 +21,7 @@
 // fetched once for the three directions (all six level-0 textures are identical), a level whose filter footprint is empty
 // (dilated occupancy bits) or wholly outside the grid is skipped, a direction of weight 0 is skipped, a fetch that needs one
 // level goes through the nearest-mip texture object, and a cone stops once it has left the border-padded cube for good.
-// cone_kernel<COUNT, TEX> is the literal loop (VCT_CONE_VARIANT=0, and the instrumented sample counter);
+// cone_kernel<COUNT, TEX> is the literal loop (VCT_DEBUG_CONE_VARIANT 0, and the instrumented sample counter);
 // cone_kernel_fast is the production march.  profiles/r01_ncu_s7.md, r01_cone_experiments_s7.txt: what binds it.
 // FMA contraction is allowed here: the frame is compared against the oracle with a tolerance
 // (max abs 2/255, PSNR >= 45 dB), not bit for bit.
@@ -139,8 +139,11 @@ __device__ __forceinline__ void fetch_level(const GridView& g, int level, F3 pos
 #pragma unroll
     for (int k = 0; k < 4; k++) acc[k] = fmaf(s, t[k], acc[k]);
   } else {
+    // levels >= 1: the raw texels of the three directional volumes out of the stacked array (point fetches, exact texel centres);
+    // the weights stay fp32 (oracle rule R7)
     float tx[4] = {0.f, 0.f, 0.f, 0.f}, ty[4] = {0.f, 0.f, 0.f, 0.f}, tz[4] = {0.f, 0.f, 0.f, 0.f};
-    const uint32_t* lv = g.lvl[level];
+    const float inv_n = 1.0f / fN, inv_d = 1.0f / (float)(6 * g.pitch[level]), lod = (float)(level - 1);
+    const int pitch = g.pitch[level];
 #pragma unroll
     for (int dz = 0; dz < 2; dz++) {
       const int z = z0 + dz;
@@ -150,14 +153,17 @@ __device__ __forceinline__ void fetch_level(const GridView& g, int level, F3 pos
         const int y = y0 + dy;
         if ((unsigned)y >= (unsigned)N) continue;
         const float wyz = wys[dy] * wzs[dz];
-        const uint32_t* row = lv + ((size_t)z * N + y) * N * 6;
+        const float cy = ((float)y + 0.5f) * inv_n;
 #pragma unroll
         for (int dx = 0; dx < 2; dx++) {
           const int x = x0 + dx;
           if ((unsigned)x >= (unsigned)N) continue;
           const float w = wxs[dx] * wyz;
-          const uint32_t* rec = row + x * 6;
-          const uint32_t a = __ldg(rec + ix), b = __ldg(rec + iy), c = __ldg(rec + iz);
+          const float cx = ((float)x + 0.5f) * inv_n;
+          const uchar4 ca = tex3DLod<uchar4>(g.tex_pt, cx, cy, ((float)(z + ix * pitch) + 0.5f) * inv_d, lod);
+          const uchar4 cb = tex3DLod<uchar4>(g.tex_pt, cx, cy, ((float)(z + iy * pitch) + 0.5f) * inv_d, lod);
+          const uchar4 cc = tex3DLod<uchar4>(g.tex_pt, cx, cy, ((float)(z + iz * pitch) + 0.5f) * inv_d, lod);
+          const uint32_t a = *reinterpret_cast<const uint32_t*>(&ca), b = *reinterpret_cast<const uint32_t*>(&cb), c = *reinterpret_cast<const uint32_t*>(&cc);
           if (a) madd4(tx, w, a);
           if (b) madd4(ty, w, b);
           if (c) madd4(tz, w, c);
@@ -691,7 +697,7 @@ cone_kernel_fast(const TraceArgs a) {
   }
 }
 
-// the same items with one warp per (tile of the frame, job) of a grid sized on the host (VCT_CONE_PERSIST=0)
+// the same items with one warp per (tile of the frame, job) of a grid sized on the host (VCT_DEBUG_CONE_GRID)
 template <bool TEX, bool SPLIT, int MIN_CTAS, bool GROUP>
 __global__ void __launch_bounds__(32 * kConeWarps, MIN_CTAS)
 cone_kernel_grid(const TraceArgs a) {
@@ -856,10 +862,10 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
   a.npix = (size_t)t->W * t->H;
   const int n_tiles = ((t->W + 7) / 8) * ((t->H + 3) / 4);
   // which march: 3 = production (one-level fetches through the nearest-mip texture object, all diffuse cones of a tile in one warp), 2 = one
-  // warp per cone slot, 1 = every fetch blends two levels, 0 = literal loop; VCT_CONE_VARIANT is read per call so that tests can compare them
+  // warp per cone slot, 1 = every fetch blends two levels, 0 = literal loop; vct_debug_set(VCT_DEBUG_CONE_VARIANT) lets tests compare them
   const bool tex = p->sampler == VCT_SAMPLER_TEX && g->levels >= 2;
-  const char* ev = getenv("VCT_CONE_VARIANT");
-  int variant = ev ? atoi(ev) : 3;
+  const bool ev = dev->debug_cone_variant >= 0;
+  int variant = ev ? dev->debug_cone_variant : 3;
   // grouping makes the diffuse warps nine times longer: with few tiles per GPU (small frames, many ranks) the tail of the launch costs
   // more than the shared set-up saves (512x512: 200 -> 224 us; 1920x1080: 887 -> 863 us)
   // (and the fp32 software sampler, 72 registers, spills in the grouped form: 3.7 -> 4.6 ms at 1080p)
@@ -901,8 +907,7 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
       if (tex) cone_kernel<false, true><<<grid, 32 * kConeWarps, 0, s>>>(a);
       else cone_kernel<false, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
     } else {
-      const char* pe = getenv("VCT_CONE_PERSIST");
-      const bool persist = !(pe && pe[0] == '0');
+      const bool persist = !dev->debug_cone_grid;
       const int sms = dev->prop.multiProcessorCount;
       a.n_jobs = a.grouped ? (int)grid_jobs.y : a.n_slots;
       // launch K<TEX, SPLIT, MIN_CTAS, GROUP>: persistent (MIN_CTAS CTAs per SM) or one warp per (tile, job) of the whole frame

@@ -1,15 +1,21 @@
 // gbuffer.cu -- camera visibility pass producing the G-buffer the cone tracer shades.
 //
-// Replaces voxel_cone_tracing.vert + the fixed-function raster / GL_LESS depth test of
+// Replaces voxel_cone_tracing.vert + the fixed-function clip / raster / GL_LESS depth test of
 // Renderer::visualize() (src/renderer.cpp:355-390).  The reference is a forward renderer that
 // shades every overdrawn fragment; the last writer of a pixel is the GL_LESS winner, so shading
 // only that fragment gives the same image.  Three launches:
-//   cam_setup_kernel    triangle-parallel vertex shader + projection + snapping + item count
-//   cam_raster_kernel   one warp per 8x8 item; 64-bit atomicMin of (depth bits << 32 | triangle
-//                       sequence) = GL_LESS with "first drawn wins ties"
-//   cam_resolve_kernel  per pixel: perspective-correct world position and (un-renormalised)
-//                       normal of the winning triangle (voxel_cone_tracing.vert:22-28)
-// Built with -fmad=false; same evaluation order as the oracle (rules R1-R3, R8).
+//   cam_setup_kernel    triangle-parallel vertex shader + NEAR-PLANE CLIPPING (a triangle becomes 0, 1 or 2
+//                       pieces, rule R2c of the oracle) + projection + snapping.  Pieces whose bounding box
+//                       holds a few dozen pixel centres are depth-tested right there (one lane per triangle);
+//                       the others get a record in a compact array and 64x64-pixel work items.
+//   cam_raster_kernel   one warp per work item (8x8 blocks culled by the edge functions, then two pixels per
+//                       lane); 64-bit atomicMin of (depth bits << 32 | triangle sequence) = GL_LESS with
+//                       "first drawn wins ties"
+//   cam_resolve_kernel  per pixel: perspective-correct world position and (un-renormalised) normal of the
+//                       winning triangle (voxel_cone_tracing.vert:22-28) -- from its record, or, for the
+//                       triangles that never got one (the millions of sub-tile triangles of a large scene),
+//                       by running the vertex stage again for that one triangle.
+// Built with -fmad=false; same evaluation order as the oracle (rules R1-R3, R2c, R8).
 #include "raster.cuh"
 
 namespace vct {
@@ -17,106 +23,187 @@ namespace vct {
 struct Mat4 { float m[16]; };
 constexpr int kSmallCamPixels = 36;
 
-__global__ void __launch_bounds__(kSetupThreads)
-cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ draws,
-                 uint32_t n_draws, uint32_t n_tris, Mat4 pv, int W, int H, CamTri* __restrict__ out, uint32_t* __restrict__ item_local,
-                 uint32_t* __restrict__ item_block, unsigned long long* __restrict__ vis, int tile_rank, int tile_nranks, int small_limit,
-                 uint32_t* scan_ticket, uint32_t* scan_total) {
-  uint32_t t = blockIdx.x * kSetupThreads + threadIdx.x;
-  uint32_t count = 0;
-  RasterTri srt;   // copy for the small-triangle path below
-  srt.sign = 0; srt.imin = 0; srt.imax = -1; srt.jmin = 0; srt.jmax = -1;
-  float sz0 = 0.f, sz1 = 0.f, sz2 = 0.f;
-  if (t < n_tris) {
-    const DrawRec& d = draws[find_draw(t, draws, n_draws)];
-    uint32_t first = d.first_index + 3u * (t - d.tri_base);
-    CamTri v;
-    const float* m = d.model;
-    const float* p = pv.m;
+// one clip-space vertex with the attributes the fragment stage interpolates
+struct ClipVert { float cx, cy, cz, cw; float world[3], nn[3]; };
+
+// a + t * (b - a), fp32, no FMA (gbuffer.o is built with -fmad=false): the oracle's clip interpolation
+__device__ __forceinline__ float clip_lerp(float a, float b, float t) { return a + t * (b - a); }
+
+// Vertex stage + near-plane clip + projection of triangle t: up to two rasterisable pieces (fan (p0,p1,p2), (p0,p2,p3) of the
+// clipped polygon).  Used by the set-up kernel AND by the resolve kernel (same code, same inputs -> the same bits).
+__device__ __forceinline__ int cam_triangle_pieces(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec& d, uint32_t t,
+                                                   const float* __restrict__ p, int W, int H, CamTri (&out)[2]) {
+  const uint32_t first = d.first_index + 3u * (t - d.tri_base);
+  const float* m = d.model;
+  ClipVert in[3];
+  float dn[3];
+  int n_out = 0;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const vct_vertex_t vx = verts[d.vertex_base + indices[first + k]];
+    const float px = vx.pos[0], py = vx.pos[1], pz = vx.pos[2];
+    const float wx = ((m[0] * px + m[4] * py) + m[8] * pz) + m[12];
+    const float wy = ((m[1] * px + m[5] * py) + m[9] * pz) + m[13];
+    const float wz = ((m[2] * px + m[6] * py) + m[10] * pz) + m[14];
+    const float ww = ((m[3] * px + m[7] * py) + m[11] * pz) + m[15];
+    in[k].world[0] = wx; in[k].world[1] = wy; in[k].world[2] = wz;
+    const float* nm = d.nmat;
+    const float nx = (nm[0] * vx.norm[0] + nm[3] * vx.norm[1]) + nm[6] * vx.norm[2];
+    const float ny = (nm[1] * vx.norm[0] + nm[4] * vx.norm[1]) + nm[7] * vx.norm[2];
+    const float nz = (nm[2] * vx.norm[0] + nm[5] * vx.norm[1]) + nm[8] * vx.norm[2];
+    const float nl = sqrtf((nx * nx + ny * ny) + nz * nz);
+    in[k].nn[0] = nx / nl; in[k].nn[1] = ny / nl; in[k].nn[2] = nz / nl;
+    in[k].cx = ((p[0] * wx + p[4] * wy) + p[8] * wz) + p[12] * ww;
+    in[k].cy = ((p[1] * wx + p[5] * wy) + p[9] * wz) + p[13] * ww;
+    in[k].cz = ((p[2] * wx + p[6] * wy) + p[10] * wz) + p[14] * ww;
+    in[k].cw = ((p[3] * wx + p[7] * wy) + p[11] * wz) + p[15] * ww;
+    dn[k] = in[k].cz + in[k].cw;          // >= 0: inside the near plane (-w <= z)
+    if (!(dn[k] >= 0.0f)) n_out++;        // also NaN
+  }
+  if (n_out == 3) return 0;
+  // R2c: Sutherland-Hodgman against the near plane; a new vertex is always computed from the INSIDE vertex of its edge
+  ClipVert poly[4];
+  int np = 0;
+  if (n_out == 0) {
+    poly[0] = in[0]; poly[1] = in[1]; poly[2] = in[2]; np = 3;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      const int k1 = (k + 1) % 3;
+      const bool in_a = dn[k] >= 0.0f, in_b = dn[k1] >= 0.0f;
+      if (in_a) poly[np++] = in[k];
+      if (in_a != in_b) {
+        const ClipVert& vi = in_a ? in[k] : in[k1];
+        const ClipVert& vo = in_a ? in[k1] : in[k];
+        const float di = in_a ? dn[k] : dn[k1], dout = in_a ? dn[k1] : dn[k];
+        const float tt = di / (di - dout);
+        ClipVert c;
+        c.cx = clip_lerp(vi.cx, vo.cx, tt); c.cy = clip_lerp(vi.cy, vo.cy, tt); c.cz = clip_lerp(vi.cz, vo.cz, tt); c.cw = clip_lerp(vi.cw, vo.cw, tt);
+#pragma unroll
+        for (int a = 0; a < 3; a++) { c.world[a] = clip_lerp(vi.world[a], vo.world[a], tt); c.nn[a] = clip_lerp(vi.nn[a], vo.nn[a], tt); }
+        poly[np++] = c;
+      }
+    }
+  }
+  int n_pieces = 0;
+  for (int piece = 0; piece + 3 <= np; piece++) {
+    CamTri& v = out[n_pieces];
     float xw[3], yw[3];
     bool ok = true;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-      const vct_vertex_t vx = verts[d.vertex_base + indices[first + k]];
-      float px = vx.pos[0], py = vx.pos[1], pz = vx.pos[2];
-      float wx = ((m[0] * px + m[4] * py) + m[8] * pz) + m[12];
-      float wy = ((m[1] * px + m[5] * py) + m[9] * pz) + m[13];
-      float wz = ((m[2] * px + m[6] * py) + m[10] * pz) + m[14];
-      float ww = ((m[3] * px + m[7] * py) + m[11] * pz) + m[15];
-      v.world[k][0] = wx; v.world[k][1] = wy; v.world[k][2] = wz;
-      const float* nm = d.nmat;
-      float nx = (nm[0] * vx.norm[0] + nm[3] * vx.norm[1]) + nm[6] * vx.norm[2];
-      float ny = (nm[1] * vx.norm[0] + nm[4] * vx.norm[1]) + nm[7] * vx.norm[2];
-      float nz = (nm[2] * vx.norm[0] + nm[5] * vx.norm[1]) + nm[8] * vx.norm[2];
-      float nl = sqrtf((nx * nx + ny * ny) + nz * nz);
-      v.nn[k][0] = nx / nl; v.nn[k][1] = ny / nl; v.nn[k][2] = nz / nl;
-      float cx = ((p[0] * wx + p[4] * wy) + p[8] * wz) + p[12] * ww;
-      float cy = ((p[1] * wx + p[5] * wy) + p[9] * wz) + p[13] * ww;
-      float cz = ((p[2] * wx + p[6] * wy) + p[10] * wz) + p[14] * ww;
-      float cw = ((p[3] * wx + p[7] * wy) + p[11] * wz) + p[15] * ww;
-      if (!(cw > 0.0f)) ok = false;
-      float iw = 1.0f / cw;
+      const ClipVert& c = poly[k == 0 ? 0 : piece + k];
+#pragma unroll
+      for (int a = 0; a < 3; a++) { v.world[k][a] = c.world[a]; v.nn[k][a] = c.nn[a]; }
+      if (!(c.cw > 0.0f)) ok = false;   // cannot happen behind a near plane with near > 0; guards general matrices
+      const float iw = 1.0f / c.cw;
       v.iw[k] = iw;
-      xw[k] = (cx * iw + 1.0f) * ((float)W * 0.5f);
-      yw[k] = (cy * iw + 1.0f) * ((float)H * 0.5f);
-      v.zw[k] = (cz * iw + 1.0f) * 0.5f;
+      xw[k] = (c.cx * iw + 1.0f) * ((float)W * 0.5f);
+      yw[k] = (c.cy * iw + 1.0f) * ((float)H * 0.5f);
+      v.zw[k] = (c.cz * iw + 1.0f) * 0.5f;
     }
-    if (ok) raster_setup(xw, yw, W, H, v.rt);
-    else { v.rt.sign = 0; v.rt.imin = 0; v.rt.imax = -1; v.rt.jmin = 0; v.rt.jmax = -1; v.rt.area = 0; }
+    if (!ok || !raster_setup(xw, yw, W, H, v.rt)) continue;
     v.material = d.material;
     v.pad = 0;
-    out[t] = v;   // always: the resolve kernel reads the record of whichever triangle wins a pixel
-    count = raster_item_count(v.rt);
-    srt = v.rt; sz0 = v.zw[0]; sz1 = v.zw[1]; sz2 = v.zw[2];
+    n_pieces++;
   }
-  // ---- small triangles (bounding box of at most kSmallCamPixels pixel centres): depth-tested right here, one lane per
-  //      triangle, instead of one warp per 8x8 item ----
-  const int bw = srt.imax - srt.imin + 1, bh = srt.jmax - srt.jmin + 1;
-  const bool small = count > 0 && bw * bh <= small_limit;
-  const int npx = small ? bw * bh : 0;
-  for (int p = 0; p < npx; p++) {
-    const int i = srt.imin + p % bw, j = srt.jmin + p / bw;
-    if (tile_nranks > 1 && ((j >> 5) * ((W + 31) >> 5) + (i >> 5)) % tile_nranks != tile_rank) continue;   // multi-GPU: not this rank's screen tile
-    float b[3];
-    if (raster_sample(srt, i, j, b)) {
-      const float zw = interp3(b, sz0, sz1, sz2);
-      if (zw >= 0.0f && zw <= 1.0f) atomicMin(&vis[(size_t)j * W + i], ((unsigned long long)__float_as_uint(zw) << 32) | (unsigned long long)t);
+  return n_pieces;
+}
+
+__device__ __forceinline__ bool tile_owned(int i, int j, int W, int tile_rank, int tile_nranks) {
+  return tile_nranks <= 1 || ((j >> 5) * ((W + 31) >> 5) + (i >> 5)) % tile_nranks == tile_rank;
+}
+
+// depth test of every covered pixel of a piece, one lane per piece (the sub-tile triangles of a large scene)
+__device__ __forceinline__ void raster_piece_inline(const CamTri& v, uint32_t t, int W, unsigned long long* __restrict__ vis, int tile_rank, int tile_nranks) {
+  const int bw = v.rt.imax - v.rt.imin + 1, bh = v.rt.jmax - v.rt.jmin + 1;
+  for (int j = v.rt.jmin; j < v.rt.jmin + bh; j++)
+    for (int i = v.rt.imin; i < v.rt.imin + bw; i++) {
+      if (!tile_owned(i, j, W, tile_rank, tile_nranks)) continue;   // multi-GPU: not this rank's screen tile
+      float b[3];
+      if (raster_sample(v.rt, i, j, b)) {
+        const float zw = interp3(b, v.zw[0], v.zw[1], v.zw[2]);
+        if (zw >= 0.0f && zw <= 1.0f) atomicMin(&vis[(size_t)j * W + i], ((unsigned long long)__float_as_uint(zw) << 32) | (unsigned long long)t);
+      }
+    }
+}
+
+// big_slot[t]: 0 = the triangle has no records (culled, or rasterised in line: the resolve kernel re-runs the vertex stage);
+// else 1 + index of its first record in `recs` | (number of records - 1) << 31.  recs[slot].pad = work items of that record.
+__global__ void __launch_bounds__(kSetupThreads)
+cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ draws,
+                 uint32_t n_draws, uint32_t n_tris, Mat4 pv, int W, int H, CamTri* __restrict__ recs, uint32_t rec_capacity, uint32_t* __restrict__ rec_count,
+                 uint32_t* __restrict__ big_slot, uint32_t* __restrict__ item_local, uint32_t* __restrict__ item_block, unsigned long long* __restrict__ vis,
+                 int tile_rank, int tile_nranks, int small_limit, uint32_t* scan_ticket, uint32_t* scan_total) {
+  const uint32_t t = blockIdx.x * kSetupThreads + threadIdx.x;
+  uint32_t count = 0;
+  if (t < n_tris) {
+    const DrawRec& d = draws[find_draw(t, draws, n_draws)];
+    CamTri pc[2];
+    const int n = cam_triangle_pieces(verts, indices, d, t, pv.m, W, H, pc);
+    bool big[2] = {false, false};
+    int n_big = 0;
+    for (int q = 0; q < n; q++) {
+      const int bw = pc[q].rt.imax - pc[q].rt.imin + 1, bh = pc[q].rt.jmax - pc[q].rt.jmin + 1;
+      big[q] = bw * bh > small_limit;
+      n_big += big[q] ? 1 : 0;
+    }
+    uint32_t slot = 0;
+    if (n_big) {
+      slot = atomicAdd(rec_count, (uint32_t)n_big);
+      if (slot + (uint32_t)n_big > rec_capacity) { big[0] = big[1] = false; n_big = 0; }   // record array full: every piece goes the in-line way (slow, still exact)
+    }
+    big_slot[t] = n_big ? ((slot + 1u) | ((uint32_t)(n_big - 1) << 31)) : 0u;
+    for (int q = 0; q < n; q++) {
+      if (big[q]) {
+        pc[q].pad = raster_item_count(pc[q].rt);
+        count += pc[q].pad;
+        recs[slot++] = pc[q];
+      } else {
+        raster_piece_inline(pc[q], t, W, vis, tile_rank, tile_nranks);
+      }
     }
   }
-  if (small) count = 0;
   block_scan_items(count, t, n_tris, item_local, item_block, scan_ticket, scan_total);
 }
 
 __global__ void __launch_bounds__(256)
-cam_raster_kernel(const CamTri* __restrict__ tris, uint32_t n_tris, const uint32_t* __restrict__ item_local,
+cam_raster_kernel(const CamTri* __restrict__ recs, const uint32_t* __restrict__ big_slot, uint32_t n_tris, const uint32_t* __restrict__ item_local,
                   const uint32_t* __restrict__ item_block, uint32_t n_blocks, int W, unsigned long long* __restrict__ vis,
                   const uint32_t* __restrict__ counters, int tile_rank, int tile_nranks) {
   const uint32_t total = counters[CNT_CAM_ITEMS];
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t g = warp; g < total; g += n_warps) {  // one warp per 8x8 item
+  for (uint32_t g = warp; g < total; g += n_warps) {  // one warp per 64x64 macro tile
     uint32_t rank;
     const uint32_t ti = find_item_triangle(g, item_block, n_blocks, item_local, n_tris, rank);
-    const CamTri& v = tris[ti];
+    uint32_t slot = (__ldg(big_slot + ti) & 0x7FFFFFFFu) - 1u;
+    const uint32_t n0 = recs[slot].pad;
+    if (rank >= n0) { rank -= n0; slot++; }   // the second piece of a clipped triangle
+    const CamTri& v = recs[slot];
     const RasterTri rt = v.rt;
     const float z0 = v.zw[0], z1 = v.zw[1], z2 = v.zw[2];
-    const int tiles_x = (rt.imax >> 3) - (rt.imin >> 3) + 1;
-    const int tx = (rt.imin >> 3) + (int)(rank % (uint32_t)tiles_x), ty = (rt.jmin >> 3) + (int)(rank / (uint32_t)tiles_x);
-    // multi-GPU: only the 32x32 screen tiles this rank shades need visibility
-    if (tile_nranks > 1 && ((ty >> 2) * ((W + 31) >> 5) + (tx >> 2)) % tile_nranks != tile_rank) continue;
-    EdgeBlock eb;
-    edge_block_setup(rt, tx * kTile, ty * kTile, eb);
+    MacroItem mi;
+    macro_item_setup(rt, rank, lane, mi);
+    for (unsigned long long live = mi.live; live; live &= live - 1ull) {
+      const int b = __ffsll((long long)live) - 1;
+      const int bx0 = mi.x0 + 8 * (b & 7), by0 = mi.y0 + 8 * (b >> 3);
+      // multi-GPU: only the 32x32 screen tiles this rank shades need visibility (an 8x8 block lies inside one of them)
+      if (!tile_owned(bx0, by0, W, tile_rank, tile_nranks)) continue;
+      EdgeBlock eb;
+      macro_block_edges(mi, b, eb);
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int p = lane + 32 * h;
-      const int i = tx * kTile + (p & 7), j = ty * kTile + (p >> 3);
-      float b[3];
-      if (i >= rt.imin && i <= rt.imax && j >= rt.jmin && j <= rt.jmax && edge_block_sample(eb, p & 7, p >> 3, b)) {
-        const float zw = interp3(b, z0, z1, z2);
-        if (zw >= 0.0f && zw <= 1.0f) {  // near / far (R3); also rejects NaN
-          const unsigned long long key = ((unsigned long long)__float_as_uint(zw) << 32) | (unsigned long long)ti;
-          atomicMin(&vis[(size_t)j * W + i], key);
+      for (int h = 0; h < 2; h++) {
+        const int p = lane + 32 * h;
+        const int i = bx0 + (p & 7), j = by0 + (p >> 3);
+        float bc[3];
+        if (i >= rt.imin && i <= rt.imax && j >= rt.jmin && j <= rt.jmax && edge_block_sample(eb, p & 7, p >> 3, bc)) {
+          const float zw = interp3(bc, z0, z1, z2);
+          if (zw >= 0.0f && zw <= 1.0f) {  // near / far (R3); also rejects NaN
+            const unsigned long long key = ((unsigned long long)__float_as_uint(zw) << 32) | (unsigned long long)ti;
+            atomicMin(&vis[(size_t)j * W + i], key);
+          }
         }
       }
     }
@@ -128,14 +215,13 @@ cam_raster_kernel(const CamTri* __restrict__ tris, uint32_t n_tris, const uint32
 constexpr unsigned long long kVisClear = ((unsigned long long)0x3F800000u << 32) | 0xFFFFFFFFull;
 
 __global__ void __launch_bounds__(256)
-cam_resolve_kernel(const CamTri* __restrict__ tris, const unsigned long long* vis, int W, int H, float* __restrict__ world_pos,
+cam_resolve_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ draws, uint32_t n_draws, Mat4 pv,
+                   const CamTri* __restrict__ recs, const uint32_t* __restrict__ big_slot, const unsigned long long* vis, int W, int H, float* __restrict__ world_pos,
                    float* __restrict__ normal, uint32_t* __restrict__ material, unsigned long long* vis_out, int tile_rank, int tile_nranks) {
   const size_t n = (size_t)W * H;
   for (size_t px = (size_t)blockIdx.x * blockDim.x + threadIdx.x; px < n; px += (size_t)gridDim.x * blockDim.x) {
-    if (tile_nranks > 1) {  // pixels of other ranks' tiles are never read by this rank's tracer
-      const int i = (int)(px % W), j = (int)(px / W);
-      if (((j >> 5) * ((W + 31) >> 5) + (i >> 5)) % tile_nranks != tile_rank) continue;
-    }
+    const int i = (int)(px % W), j = (int)(px / W);
+    if (!tile_owned(i, j, W, tile_rank, tile_nranks)) continue;   // pixels of other ranks' tiles are never read by this rank's tracer
     unsigned long long key = vis[px];
     uint32_t ti = (uint32_t)(key & 0xFFFFFFFFull);
     // GL_LESS against the cleared depth 1.0: a fragment exactly at zw == 1.0 fails
@@ -145,18 +231,48 @@ cam_resolve_kernel(const CamTri* __restrict__ tris, const unsigned long long* vi
       material[px] = VCT_NO_TRIANGLE;
       continue;
     }
-    const CamTri& v = tris[ti];
-    const int i = (int)(px % W), j = (int)(px / W);
-    float b[3];
-    raster_sample(v.rt, i, j, b);
-    float q[3] = {b[0] * v.iw[0], b[1] * v.iw[1], b[2] * v.iw[2]};
-    float qs = (q[0] + q[1]) + q[2];
+    // the piece of the winning triangle that covers this pixel: from its records, or by running the vertex stage again
+    float b[3], iw[3], world[3][3], nn[3][3];
+    uint32_t mat = 0;
+    bool found = false;
+    const uint32_t bs = __ldg(big_slot + ti);
+    if (bs) {
+      uint32_t slot = (bs & 0x7FFFFFFFu) - 1u;
+      found = raster_sample(recs[slot].rt, i, j, b);
+      if (!found && (bs >> 31)) { slot++; found = raster_sample(recs[slot].rt, i, j, b); }
+      if (found) {
+        const CamTri& v = recs[slot];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          iw[k] = v.iw[k];
+#pragma unroll
+          for (int c = 0; c < 3; c++) { world[k][c] = v.world[k][c]; nn[k][c] = v.nn[k][c]; }
+        }
+        mat = v.material;
+      }
+    }
+    if (!found) {   // no record (sub-tile triangle), or the pixel belongs to a piece that was rasterised in line
+      const DrawRec& d = draws[find_draw(ti, draws, n_draws)];
+      CamTri pc[2];
+      const int np = cam_triangle_pieces(verts, indices, d, ti, pv.m, W, H, pc);
+      const int q = (np > 1 && !raster_sample(pc[0].rt, i, j, b)) ? 1 : 0;
+      raster_sample(pc[q].rt, i, j, b);
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        iw[k] = q ? pc[1].iw[k] : pc[0].iw[k];
+#pragma unroll
+        for (int c = 0; c < 3; c++) { world[k][c] = q ? pc[1].world[k][c] : pc[0].world[k][c]; nn[k][c] = q ? pc[1].nn[k][c] : pc[0].nn[k][c]; }
+      }
+      mat = d.material;
+    }
+    const float q3[3] = {b[0] * iw[0], b[1] * iw[1], b[2] * iw[2]};
+    const float qs = (q3[0] + q3[1]) + q3[2];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
-      world_pos[px * 3 + c] = interp3(q, v.world[0][c], v.world[1][c], v.world[2][c]) / qs;
-      normal[px * 3 + c] = interp3(q, v.nn[0][c], v.nn[1][c], v.nn[2][c]) / qs;
+      world_pos[px * 3 + c] = interp3(q3, world[0][c], world[1][c], world[2][c]) / qs;
+      normal[px * 3 + c] = interp3(q3, nn[0][c], nn[1][c], nn[2][c]) / qs;
     }
-    material[px] = v.material;
+    material[px] = mat;
   }
 }
 
@@ -204,18 +320,25 @@ int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const floa
   fill_u64_kernel<<<dev->prop.multiProcessorCount * 8, 256, 0, s>>>(t->vis, npx, kVisClear);
   const int sms = dev->prop.multiProcessorCount;
   if (sc->n_tris) {
-    int rc = ensure_tri_scratch(dev, 1, sc->n_tris, sizeof(CamTri));
+    // records only for the pieces that become work items: a compact array (a quarter of the triangles, at least 64 k); a scene
+    // that fills it falls back to the in-line path for the rest
+    const size_t rec_capacity = sc->n_tris / 4 > 65536 ? sc->n_tris / 4 : 65536;
+    int rc = ensure_tri_scratch(dev, 1, sc->n_tris, rec_capacity * sizeof(CamTri));
     if (rc) return rc;
     Mat4 pv;
     mat4_mul_host(proj, view, pv.m);  // projection * view (voxel_cone_tracing.vert:25)
     const uint32_t n_blocks = (sc->n_tris + kSetupThreads - 1) / kSetupThreads;
-    CamTri* tris = (CamTri*)dev->rs[1].tri_recs;
-    cam_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, pv, t->W, t->H, tris,
-                                                        dev->rs[1].item_local, dev->rs[1].item_block, t->vis, tile_rank, tile_nranks,
+    CamTri* recs = (CamTri*)dev->rs[1].tri_recs;
+    uint32_t* rec_count = dev->counters + CNT_CAM_RECS;
+    { int rc2 = launch_fill_u32(s, rec_count, 1, 0u); if (rc2) return rc2; }
+    cam_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, pv, t->W, t->H, recs, (uint32_t)rec_capacity, rec_count,
+                                                        dev->rs[1].big_slot, dev->rs[1].item_local, dev->rs[1].item_block, t->vis, tile_rank, tile_nranks,
                                                         sc->n_tris >= kSmallPathMinTris ? kSmallCamPixels : 0, dev->counters + CNT_TICKET_CAM,
                                                         dev->counters + CNT_CAM_ITEMS);
-    cam_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->rs[1].item_local, dev->rs[1].item_block, n_blocks, t->W, t->vis, dev->counters, tile_rank, tile_nranks);
-    cam_resolve_kernel<<<sms * 8, 256, 0, s>>>(tris, t->vis, t->W, t->H, t->world_pos, t->normal, t->material, t->vis, tile_rank, tile_nranks);
+    cam_raster_kernel<<<sms * 8, 256, 0, s>>>(recs, dev->rs[1].big_slot, sc->n_tris, dev->rs[1].item_local, dev->rs[1].item_block, n_blocks, t->W, t->vis, dev->counters,
+                                              tile_rank, tile_nranks);
+    cam_resolve_kernel<<<sms * 8, 256, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, pv, recs, dev->rs[1].big_slot, t->vis, t->W, t->H, t->world_pos, t->normal,
+                                               t->material, t->vis, tile_rank, tile_nranks);
   } else {
     launch_fill_u32(s, t->material, npx, VCT_NO_TRIANGLE);
   }

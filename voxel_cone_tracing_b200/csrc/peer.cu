@@ -25,19 +25,24 @@ static_assert(sizeof(PeerHandlePack) <= sizeof(vct_peer_handle_t), "vct_peer_han
 constexpr uint32_t kPeerMagic = 0x56435450u;   // "VCTP"
 constexpr size_t kFlagWords = PEER_FLAG_KINDS * VCT_MAX_RANKS + 8;   // flags + done counters [PEER_FLAG_KINDS] + error word
 
-__global__ void peer_wait_kernel(const uint32_t* flags, int kind, int nranks, uint32_t epoch, uint32_t* error_word, long long timeout_cycles) {
+__global__ void peer_wait_kernel(const uint32_t* flags, int kind, int nranks, uint32_t epoch, uint32_t* error_word, uint32_t* status, long long timeout_cycles) {
   const int p = threadIdx.x;
   if (p >= nranks) return;
   const long long t0 = clock64();
   while ((int32_t)(ld_acquire_sys(flags + kind * VCT_MAX_RANKS + p) - epoch) < 0) {
-    if (clock64() - t0 > timeout_cycles) { atomicExch(error_word, 1u + (uint32_t)p); return; }   // a peer died or never connected
+    if (clock64() - t0 > timeout_cycles) {   // a peer died or never connected: the next host call on this device returns an error
+      atomicExch(error_word, 1u + (uint32_t)p);
+      *reinterpret_cast<volatile uint32_t*>(status + STATUS_PEER) = 1u + (uint32_t)p;
+      __threadfence_system();
+      return;
+    }
     __nanosleep(100);
   }
 }
 
 int launch_peer_wait(vct_device* dev, int kind, uint32_t epoch) {
   const long long timeout = (long long)dev->prop.clockRate * 1000ll * 5ll;   // ~5 s of SM clock (clockRate is in kHz)
-  peer_wait_kernel<<<1, 32, 0, dev->stream>>>(dev->peer_flags, kind, dev->peers.nranks, epoch, dev->peer_flags + kFlagWords - 1, timeout);
+  peer_wait_kernel<<<1, 32, 0, dev->stream>>>(dev->peer_flags, kind, dev->peers.nranks, epoch, dev->peer_flags + kFlagWords - 1, dev->status_dev, timeout);
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;
 }
@@ -70,6 +75,7 @@ int vct_peer_export(vct_device_t* dev, vct_grid_t* g, vct_target_t* t, vct_peer_
   VCT_CUDA(cudaIpcGetMemHandle(&h.frame, t->frame));
   VCT_CUDA(cudaIpcGetMemHandle(&h.flags, dev->peer_flags));
   h.R = (uint32_t)g->R; h.W = (uint32_t)t->W; h.H = (uint32_t)t->H; h.magic = kPeerMagic;
+  dev->peer_export_fresh = true;   // the flag block is zero: epochs restart at 1 with the next connect
   memset(out, 0, sizeof *out);
   memcpy(out, &h, sizeof h);
   return VCT_OK;
@@ -93,6 +99,9 @@ int vct_peer_connect(vct_device_t* dev, vct_grid_t* g, vct_target_t* t, int rank
   VCT_REQUIRE(nranks >= 1 && nranks <= VCT_MAX_RANKS && rank >= 0 && rank < nranks, "bad rank / nranks");
   VCT_REQUIRE(frame_root >= -1 && frame_root < nranks, "bad frame_root");
   VCT_REQUIRE(g->base_buf[1] && dev->peer_flags, "call vct_peer_export first");
+  // a connect restarts the epochs at 1; flags left over from an earlier connection would let the first waits pass at once
+  VCT_REQUIRE(dev->peer_export_fresh, "vct_peer_connect needs a fresh vct_peer_export (it zeroes the flag block) on every rank");
+  dev->peer_export_fresh = false;
   VCT_REQUIRE(g->R >= nranks, "more ranks than z-slices");
   VCT_CUDA(cudaSetDevice(dev->ordinal));
   vct_peer_disconnect(dev);

@@ -4,11 +4,13 @@
 // b_k = float(E_k) / float(2A).  Replaces the fixed-function rasteriser the reference drives at
 // src/renderer.cpp:339-347 (voxelization viewport 2R x 2R) and :358-389 (camera viewport).
 //
-// Work distribution: every triangle's bounding box is cut into 8x8-pixel tiles ("items");
+// Work distribution: every triangle's bounding box is cut into 64x64-pixel macro tiles ("items");
 // a block-local scan in the setup kernel plus a one-block scan of the block totals give every
 // item a global index without a host round trip; the raster kernel walks items with one warp
-// per item (2 pixels per lane), so a wall-sized triangle and a sub-pixel sliver cost the same
-// per covered tile.
+// per item: the warp first rejects the 8x8-pixel blocks of the macro tile that no edge function
+// can reach (two blocks per lane, one ballot), then visits the live blocks with 2 pixels per lane.
+// (Round 1 used the 8x8 block itself as the item: a wall at 8K is half a million items, each paying
+// two binary searches through the prefix arrays -- 17 of the 33 ms of the config-5 G-buffer pass.)
 #pragma once
 
 #include "vct_internal.cuh"
@@ -16,7 +18,8 @@
 namespace vct {
 
 constexpr int kSetupThreads = 256;
-constexpr int kTile = 8;  // 8x8 pixels per item
+constexpr int kTile = 8;  // 8x8 pixels per block: 2 pixels per lane
+constexpr int kMacroShift = 6, kMacro = 1 << kMacroShift;  // 64x64 pixels per work item = 8x8 blocks
 // The in-thread small-triangle path of the setup kernels pays off when there are many triangles; a scene of a few thousand
 // triangles has too few setup threads to hide the fragment work there, its 8x8 items parallelise better.
 constexpr uint32_t kSmallPathMinTris = 32768;
@@ -54,7 +57,7 @@ __device__ __forceinline__ bool raster_setup(const float xw[3], const float yw[3
 
 __device__ __forceinline__ uint32_t raster_item_count(const RasterTri& t) {
   if (t.sign == 0) return 0u;
-  int tx = (t.imax >> 3) - (t.imin >> 3) + 1, ty = (t.jmax >> 3) - (t.jmin >> 3) + 1;
+  int tx = (t.imax >> kMacroShift) - (t.imin >> kMacroShift) + 1, ty = (t.jmax >> kMacroShift) - (t.jmin >> kMacroShift) + 1;
   return (uint32_t)tx * (uint32_t)ty;
 }
 
@@ -112,6 +115,46 @@ __device__ __forceinline__ bool edge_block_sample(const EdgeBlock& q, int ox, in
   b[1] = (float)E[1] / q.fa;
   b[2] = (float)E[2] / q.fa;
   return true;
+}
+
+// ---- one work item = macro tile `rank` of the triangle's bounding box ----
+struct MacroItem {
+  int x0, y0;              // pixel origin of the macro tile
+  EdgeBlock em;            // edge functions at that origin
+  unsigned long long live; // bit (by * 8 + bx): block (bx, by) may hold covered pixel centres
+};
+// all 32 lanes call it
+__device__ __forceinline__ void macro_item_setup(const RasterTri& rt, uint32_t rank, int lane, MacroItem& m) {
+  const int tiles_x = (rt.imax >> kMacroShift) - (rt.imin >> kMacroShift) + 1;
+  const int tx = (rt.imin >> kMacroShift) + (int)(rank % (uint32_t)tiles_x), ty = (rt.jmin >> kMacroShift) + (int)(rank / (uint32_t)tiles_x);
+  m.x0 = tx * kMacro; m.y0 = ty * kMacro;
+  edge_block_setup(rt, m.x0, m.y0, m.em);
+  uint32_t mask[2];
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const int b = lane + 32 * h, bx = b & 7, by = b >> 3;
+    const int ox = m.x0 + 8 * bx, oy = m.y0 + 8 * by;
+    bool ok = ox <= rt.imax && ox + 7 >= rt.imin && oy <= rt.jmax && oy + 7 >= rt.jmin;
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      // the largest value edge k takes on the pixel centres of the block (corners): negative = the block is outside
+      const long long e = m.em.e0[k] + (long long)m.em.dx[k] * (256 * 8 * by) - (long long)m.em.dy[k] * (256 * 8 * bx);
+      const long long emax = e + (m.em.dx[k] > 0 ? (long long)m.em.dx[k] * (256 * 7) : 0ll) + (m.em.dy[k] < 0 ? -(long long)m.em.dy[k] * (256 * 7) : 0ll);
+      ok = ok && emax >= 0;
+    }
+    mask[h] = __ballot_sync(0xffffffffu, ok);
+  }
+  m.live = ((unsigned long long)mask[1] << 32) | mask[0];
+}
+// edge functions at the origin of block b of the macro tile
+__device__ __forceinline__ void macro_block_edges(const MacroItem& m, int b, EdgeBlock& eb) {
+  const int bx = b & 7, by = b >> 3;
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    eb.e0[k] = m.em.e0[k] + (long long)m.em.dx[k] * (256 * 8 * by) - (long long)m.em.dy[k] * (256 * 8 * bx);
+    eb.dx[k] = m.em.dx[k]; eb.dy[k] = m.em.dy[k];
+  }
+  eb.fa = m.em.fa;
 }
 
 __device__ __forceinline__ float interp3(const float b[3], float a0, float a1, float a2) {

@@ -87,15 +87,16 @@ struct Lights {
 #define VCT_MAX_LEVELS 12
 struct GridView {
   uint32_t* base;                 // level 0: R^3 u32, [z][y][x]
-  uint32_t* lvl[VCT_MAX_LEVELS];  // level l >= 1: (R>>l)^3 records of 6 u32 (direction-minor)
-  // Hardware-filtered copy of levels 1..: ONE mipmapped 3-D RGBA8 array (array level k = grid level k+1) that holds the six
+  // Levels 1..: ONE mipmapped 3-D RGBA8 array (array level k = grid level k+1) that holds the six
   // directional volumes stacked along z, each followed by a pad of zero texels (>= 1 texel at every level = the zero border of
   // CLAMP_TO_BORDER, texture_3d.cpp:10-12): direction d occupies z' in [d/6, d/6 + tex_zs) of the normalised depth.  One array
   // means ONE texture object for every fetch -- a warp-uniform handle, so a fetch is a plain TEX instead of a per-lane handle
   // "waterfall" loop -- and the direction is chosen by the z coordinate.
   cudaTextureObject_t tex_lin;    // trilinear + mip-linear (GL_LINEAR_MIPMAP_LINEAR, texture_3d.cpp:14)
   cudaTextureObject_t tex_one;    // same texels, NEAREST mip level: one level per fetch, half the filter work when the LOD is integral
+  cudaTextureObject_t tex_pt;     // same texels, unfiltered (point, nearest mip, raw bytes): the software sampler's texel fetch
   float tex_zs;                   // z' = z * tex_zs + d / 6
+  int pitch[VCT_MAX_LEVELS];      // level l >= 1: direction d starts at array slice d * pitch[l]; the array level is 6 * pitch[l] deep
   const uint32_t* docc[VCT_MAX_LEVELS];  // per level: dilated occupancy bits, see occ_word_index()
   // the same bits for the production march: all levels live in ONE allocation, docc[l] == docc_all + occ_tab[l].x, and the
   // per-level constants of the lookup come with one 16-byte load: {word offset, N + 1, words per row, float bits of N}
@@ -178,6 +179,7 @@ struct vct_device {
     void* tri_recs = nullptr;  size_t tri_recs_bytes = 0;
     uint32_t* item_local = nullptr;    // per-triangle exclusive prefix inside its 256-block
     uint32_t* item_block = nullptr;    // per-block exclusive prefix
+    uint32_t* big_slot = nullptr;      // camera pass: where a triangle's records are (see cam_setup_kernel)
     size_t item_capacity_tris = 0;
   } rs[2];
   // second stream: the G-buffer pass of a frame does not depend on the voxel grid and runs beside clear + voxelize + mip
@@ -185,10 +187,20 @@ struct vct_device {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_g0 = nullptr, ev_g1 = nullptr;
   uint32_t* counters = nullptr;      // device counters, see enum below
   uint32_t* counters_host = nullptr; // pinned mirror
+  // Status words in MAPPED pinned host memory, written by kernels only when something went wrong (no traffic otherwise) and
+  // polled by the host at the top of every frame / download call without touching the stream:
+  //   [STATUS_OVERFLOW] fragments the last voxelization wanted when the arena was too small   [STATUS_PEER] 1 + rank a flag wait timed out on
+  volatile uint32_t* status_host = nullptr;
+  uint32_t* status_dev = nullptr;
   cudaEvent_t ev[8] = {};
   vct_grid* vox_owner = nullptr;      // the grid whose occupied voxels the arena's `fresh` marks describe (last vct_voxelize)
   bool have_timings = false;
   bool gbuffer_overlapped = false;   // the last frame ran its G-buffer pass on stream2 (ev_g0..ev_g1)
+  // measurement / test switches (vct_debug_set); never read from the environment
+  bool debug_mip_dense = false;      // every mip build reads and writes every tile
+  int debug_cone_variant = -1;       // -1 = automatic; 0 literal loop, 1 two-level fetches, 2 one warp per cone slot, 3 grouped diffuse cones
+  bool debug_cone_grid = false;      // cone kernel on a host-sized grid instead of the persistent work queue
+  bool mip_attr_set = false;
   // multi-GPU connection (vct_peer_connect)
   vct::PeerView peers{};               // peers.nranks <= 1 when not connected
   uint32_t* peer_flags = nullptr;      // local flag block [PEER_FLAG_KINDS][VCT_MAX_RANKS] + done counters + error word
@@ -198,8 +210,10 @@ struct vct_device {
   vct_grid* peer_grid = nullptr;
   vct_target_t_* peer_target = nullptr;
   uint32_t peer_epoch = 0;             // frames rendered since vct_peer_connect
+  bool peer_export_fresh = false;      // vct_peer_export ran (flag block zeroed) and no connect has consumed it yet
 };
-enum { CNT_ITEMS = 0, CNT_FRAGS = 1, CNT_OCCUPIED = 2, CNT_MAXLIST = 3, CNT_CAM_ITEMS = 12 /* outside the words the voxelizer clears every frame */, CNT_TICKET_VOX = 13, CNT_TICKET_CAM = 14 /* last-block tickets of the setup kernels */, CNT_CONE_WORK = 15 /* next item of the persistent cone kernel */, CNT_SAMPLES = 16 /* ..31, as 8 x u64 */, CNT_TOTAL = 32 };
+enum { STATUS_OVERFLOW = 0, STATUS_PEER = 1, STATUS_WORDS = 4 };
+enum { CNT_ITEMS = 0, CNT_FRAGS = 1, CNT_OCCUPIED = 2, CNT_MAXLIST = 3, CNT_CAM_RECS = 11 /* records of the camera pass */, CNT_CAM_ITEMS = 12 /* outside the words the voxelizer clears every frame */, CNT_TICKET_VOX = 13, CNT_TICKET_CAM = 14 /* last-block tickets of the setup kernels */, CNT_CONE_WORK = 15 /* next item of the persistent cone kernel */, CNT_SAMPLES = 16 /* ..31, as 8 x u64 */, CNT_TOTAL = 32 };
 
 struct vct_scene {
   vct_device* dev = nullptr;
@@ -234,34 +248,43 @@ struct vct_grid {
   int R = 0, levels = 0;
   uint32_t* base = nullptr;             // level 0 of the current frame
   uint32_t* base_buf[2] = {};           // base_buf[0] == the allocation; base_buf[1] only in multi-GPU mode (double buffering)
-  uint32_t* lvl[VCT_MAX_LEVELS] = {};
   size_t bytes = 0;
-  // hardware-filtered copy of levels 1.. (written by the mip kernels through surfaces)
-  cudaMipmappedArray_t marr = nullptr;   // the six directions stacked along z (see GridView)
-  cudaTextureObject_t tex_lin = 0, tex_one = 0;
+  // levels 1..: ONE mipmapped array, the six directions stacked along z (see GridView); written by the mip kernels through surfaces
+  cudaMipmappedArray_t marr = nullptr;
+  cudaTextureObject_t tex_lin = 0, tex_one = 0, tex_pt = 0;
   float tex_zs = 0.0f;
   vct::SurfSet surf{};
   alignas(64) unsigned char tmap_storage[2][128] = {};   // CUtensorMap (TMA descriptor) of base_buf[0] / base_buf[1], built on first use
   uint32_t* tmap_base_ptr[2] = {};
-  uint8_t* tile_zero = nullptr;         // mip stage: per 32x8x8 tile "levels 1-3 of this tile are known to be zero" (skip rewriting zeros)
+  // ---- scratch of the fused mip kernel (csrc/mipmap.cu): small linear copies of the coarse levels that cross CTAs ----
+  uint32_t* rec3 = nullptr;             // level 3 as records of six words per texel: what a 32^3 block's last tile needs of the other tiles
+  uint32_t* rec_top = nullptr;          // levels 5.. as records (level l at rec_top + top_off[l]): input of the single-CTA top of the chain
+  uint32_t top_off[VCT_MAX_LEVELS] = {};
+  uint8_t* occb = nullptr;              // levels 3..: one occupancy byte per texel (level l at occb + occb_off[l])
+  uint32_t occb_off[VCT_MAX_LEVELS] = {};
+  uint32_t* mip_counters = nullptr;     // [0] = blocks finished, [1 + b] = tiles of 32^3 block b that have arrived
+  uint8_t* tile_zero = nullptr;         // mip stage: per 32x16x8 tile "every output of this tile is known to be zero" (skip rewriting zeros)
   // ---- sparse frame-to-frame bookkeeping (< 1 % of the voxels are occupied) ----
-  // tile_touched[tile] != 0: the last vct_voxelize wrote a voxel of this 32x8x8 tile.  While flags_valid, every non-zero word of
+  // tile_touched[tile] != 0: the last vct_voxelize wrote a voxel of this 32x16x8 tile.  While flags_valid, every non-zero word of
   // level 0 lies in a touched tile, so the mip build skips untouched tiles whose outputs are already zero without reading them.
   // While sparse_clear_ok (and dev->vox_owner == this), the non-zero words are exactly the device's occupied list and
   // vct_grid_clear zeroes those instead of the whole level.  Anything that writes level 0 behind the library's back
-  // (vct_grid_upload_base, the raw pointer, peers) drops back to the dense paths.
+  // (vct_grid_upload_base, the raw pointer) drops back to the dense paths.
   uint8_t* tile_touched = nullptr;
   bool flags_valid = false, sparse_clear_ok = false, base_zero = false, external = false;
-  void untrack() { flags_valid = sparse_clear_ok = base_zero = false; }
-  uint32_t* occ[VCT_MAX_LEVELS] = {};   // non-dilated occupancy bits per level
+  int dirty_z0 = 0, dirty_z1 = 0;       // z range voxelized (or uploaded) since the last clear: vct_voxelize refuses a slab that overlaps it
+  void untrack() { flags_valid = sparse_clear_ok = base_zero = false; dirty_z0 = 0; dirty_z1 = R; }
+  uint32_t* occ[VCT_MAX_LEVELS] = {};   // non-dilated occupancy bits per level (levels 4.. point into occ_hi)
+  uint32_t* occ_hi = nullptr;
+  uint32_t occ_hi_words = 0, docc_hi_off = 0, docc_hi_words = 0;   // what the fused mip kernel zeroes every build: plain / dilated bits of levels 4..
   uint32_t* docc[VCT_MAX_LEVELS] = {};  // dilated occupancy bits per level: pointers into docc_all
   uint32_t* docc_all = nullptr;
   uint32_t docc_off[VCT_MAX_LEVELS] = {};   // word offset of each level in docc_all
   vct::GridView view() const {
     vct::GridView v;
     v.base = base; v.R = R; v.levels = levels;
-    for (int i = 0; i < VCT_MAX_LEVELS; i++) { v.lvl[i] = lvl[i]; v.docc[i] = docc[i]; }
-    v.tex_lin = tex_lin; v.tex_one = tex_one; v.tex_zs = tex_zs;
+    for (int i = 0; i < VCT_MAX_LEVELS; i++) { v.docc[i] = docc[i]; v.pitch[i] = surf.pitch[i]; }
+    v.tex_lin = tex_lin; v.tex_one = tex_one; v.tex_pt = tex_pt; v.tex_zs = tex_zs;
     v.docc_all = docc_all;
     for (int l = 0; l < VCT_MAX_LEVELS; l++) {
       const int N = l < levels ? (R >> l) : 0;
@@ -312,10 +335,12 @@ namespace vct {
 int launch_sparse_clear(vct_device* dev, vct_grid* g);
 int scene_ready(vct_scene* sc);
 int launch_copy_u32(cudaStream_t s, uint32_t* dst, const uint32_t* src, size_t n);
-int ensure_tri_scratch(vct_device* dev, int which /* 0 voxelizer, 1 G-buffer */, size_t n_tris, size_t rec_bytes);
+int ensure_tri_scratch(vct_device* dev, int which /* 0 voxelizer, 1 G-buffer */, size_t n_tris, size_t rec_bytes_total);
 int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1, const PeerView* push = nullptr);
 int launch_peer_wait(vct_device* dev, int kind, uint32_t epoch);
+int check_status(vct_device* dev);   // VCT_ERR_OVERFLOW / VCT_ERR_CUDA if a kernel reported an arena overflow / a peer timeout since the last check
 int launch_mipmap(vct_device* dev, vct_grid* g);
+bool mip_fused_applies(int R, int levels);   // the fused mip kernel (32x16x8 tiles, 32^3 blocks) handles this grid
 int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const float* proj, vct_target_t_* t, int tile_rank = 0, int tile_nranks = 1);
 // phase: 0 = tile list + cones + shade; 1 = the live-tile list only (depends on the G-buffer alone: vct_render_frame builds it on the
 // G-buffer stream); 2 = cones + shade with the list of a preceding phase-1 call

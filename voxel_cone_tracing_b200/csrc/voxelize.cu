@@ -6,7 +6,7 @@
 //                         selection (voxelize.geom:25-55), 1/256-pixel snapping, 8x8-pixel item count,
 //                         block-local scan
 //   2. (inside 1.)        the last block to finish scans the block totals: global item offsets (no host round trip, no extra launch)
-//   3. vox_raster_kernel  one warp per 8x8 item: coverage, fragment shading (voxelize.frag:122-157),
+//   3. vox_raster_kernel  one warp per 64x64 macro tile (8x8 blocks culled by the edge functions): coverage, fragment shading (voxelize.frag:122-157),
 //                         append of a 32-byte fragment record to a per-voxel linked list whose head
 //                         lives in the grid word itself (atomicExch); the fragment that finds the voxel
 //                         empty marks its arena slot (`fresh`).  Triangles of <= 36 pixels are rasterised
@@ -232,26 +232,31 @@ vox_raster_kernel(const VoxTri* __restrict__ tris, uint32_t n_tris, const uint32
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-  // one warp per 8x8 item (grid-stride): every lane runs the same two binary searches (broadcast loads)
+  // one warp per 64x64 macro tile (grid-stride): every lane runs the same two binary searches (broadcast loads), the warp rejects
+  // the 8x8 blocks no edge reaches and rasterises the rest, two pixels per lane
   for (uint32_t g = warp; g < total; g += n_warps) {
     uint32_t rank;
     const uint32_t ti = find_item_triangle(g, item_block, n_blocks, item_local, n_tris, rank);
     const VoxTri& v = tris[ti];
     const RasterTri rt = v.rt;
-    const int tiles_x = (rt.imax >> 3) - (rt.imin >> 3) + 1;
-    const int tx = (rt.imin >> 3) + (int)(rank % (uint32_t)tiles_x), ty = (rt.jmin >> 3) + (int)(rank / (uint32_t)tiles_x);
-    EdgeBlock eb;
-    edge_block_setup(rt, tx * kTile, ty * kTile, eb);
-    int pi[2], pj[2];
-    float pb[2][3];
-    bool covered[2];
+    MacroItem mi;
+    macro_item_setup(rt, rank, lane, mi);
+    for (unsigned long long live = mi.live; live; live &= live - 1ull) {
+      const int b = __ffsll((long long)live) - 1;
+      EdgeBlock eb;
+      macro_block_edges(mi, b, eb);
+      const int bx0 = mi.x0 + 8 * (b & 7), by0 = mi.y0 + 8 * (b >> 3);
+      int pi[2], pj[2];
+      float pb[2][3];
+      bool covered[2];
 #pragma unroll
-    for (int h = 0; h < 2; h++) {   // the 64 pixels of the item: two per lane
-      const int p = lane + 32 * h;
-      pi[h] = tx * kTile + (p & 7); pj[h] = ty * kTile + (p >> 3);
-      covered[h] = pi[h] >= rt.imin && pi[h] <= rt.imax && pj[h] >= rt.jmin && pj[h] <= rt.jmax && edge_block_sample(eb, p & 7, p >> 3, pb[h]);
+      for (int h = 0; h < 2; h++) {   // the 64 pixels of the block: two per lane
+        const int p = lane + 32 * h;
+        pi[h] = bx0 + (p & 7); pj[h] = by0 + (p >> 3);
+        covered[h] = pi[h] >= rt.imin && pi[h] <= rt.imax && pj[h] >= rt.jmin && pj[h] <= rt.jmax && edge_block_sample(eb, p & 7, p >> 3, pb[h]);
+      }
+      emit_fragments<2>(ctx, v, ti, pi, pj, pb, covered, lane);
     }
-    emit_fragments<2>(ctx, v, ti, pi, pj, pb, covered, lane);
   }
 }
 
@@ -284,10 +289,10 @@ __device__ __forceinline__ uint32_t avg_fold(uint32_t stored, const float val[4]
 
 constexpr int kSortMax = 24;
 
-// 32x8x8 tile (the unit of the fused mip kernel, mipmap.cu) of a level-0 voxel index; R = 2^logR
+// 32x16x8 tile (the unit of the fused mip kernel, mipmap.cu) of a level-0 voxel index; R = 2^logR >= 32
 __device__ __forceinline__ uint32_t tile_of_voxel(uint32_t voxel, int logR) {
   const uint32_t m = (1u << logR) - 1u, x = voxel & m, y = (voxel >> logR) & m, z = voxel >> (2 * logR);
-  return (((z >> 3) << (logR - 3)) + (y >> 3) << (logR - 5)) + (x >> 5);
+  return ((((z >> 3) << (logR - 4)) + (y >> 4)) << (logR - 5)) + (x >> 5);
 }
 
 // vct_grid_clear, sparse form: zero the voxels (and the tile flags) the last voxelization occupied = the voxels of its `fresh` fragments
@@ -306,7 +311,13 @@ sparse_clear_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ fra
 // One thread per arena slot; the thread of a voxel's FIRST fragment (`fresh`) resolves the voxel.
 __global__ void __launch_bounds__(128)
 vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frags, const uint8_t* __restrict__ fresh,
-                   uint32_t* __restrict__ counters, uint32_t frag_capacity, const PeerView pv, uint8_t* __restrict__ tile_touched, int logR) {
+                   uint32_t* __restrict__ counters, uint32_t frag_capacity, const PeerView pv, uint8_t* __restrict__ tile_touched, int logR,
+                   uint32_t* __restrict__ status) {
+  // arena too small: fragments were dropped.  Tell the host through the mapped status word (the only time this kernel touches host memory)
+  if (blockIdx.x == 0 && threadIdx.x == 0 && counters[CNT_FRAGS] > frag_capacity) {
+    *reinterpret_cast<volatile uint32_t*>(status + STATUS_OVERFLOW) = counters[CNT_FRAGS];
+    __threadfence_system();
+  }
   const uint32_t n_frags = min(counters[CNT_FRAGS], frag_capacity);
   uint32_t n_mine = 0, max_list = 0;
   for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < n_frags; f += gridDim.x * blockDim.x) {
@@ -347,7 +358,7 @@ vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frag
       }
     }
     base[voxel] = stored;
-    if (tile_touched) tile_touched[tile_of_voxel(voxel, logR)] = 1;   // sparse mip build: this 32x8x8 tile has content
+    if (tile_touched) tile_touched[tile_of_voxel(voxel, logR)] = 1;   // sparse mip build: this 32x16x8 tile has content
     // multi-GPU: the slab owner writes the resolved voxel straight into every peer's grid over NVLink (sparse
     // exchange: only occupied voxels travel; replaces the dense all-gather of the base level)
     for (int p = 0; p < pv.nranks; p++)
@@ -361,9 +372,9 @@ vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frag
   if (pv.nranks > 1) peer_signal_last_block(pv, PEER_FLAG_PUSHED, -1);
 }
 
-int ensure_tri_scratch(vct_device* dev, int which, size_t n_tris, size_t rec_bytes) {
+int ensure_tri_scratch(vct_device* dev, int which, size_t n_tris, size_t rec_bytes_total) {
   vct_device::RasterScratch& r = dev->rs[which];
-  size_t need = n_tris * rec_bytes;
+  size_t need = rec_bytes_total;
   if (need > r.tri_recs_bytes) {
     if (r.tri_recs) cudaFree(r.tri_recs);
     r.tri_recs = nullptr; r.tri_recs_bytes = 0;
@@ -374,9 +385,11 @@ int ensure_tri_scratch(vct_device* dev, int which, size_t n_tris, size_t rec_byt
   if (n_tris > r.item_capacity_tris) {
     if (r.item_local) cudaFree(r.item_local);
     if (r.item_block) cudaFree(r.item_block);
-    r.item_local = r.item_block = nullptr; r.item_capacity_tris = 0;
+    if (r.big_slot) cudaFree(r.big_slot);
+    r.item_local = r.item_block = r.big_slot = nullptr; r.item_capacity_tris = 0;
     size_t cap = n_tris + n_tris / 4 + 1024;
     VCT_CUDA(cudaMalloc(&r.item_local, cap * sizeof(uint32_t)));
+    if (which == 1) VCT_CUDA(cudaMalloc(&r.big_slot, cap * sizeof(uint32_t)));
     VCT_CUDA(cudaMalloc(&r.item_block, (cap / kSetupThreads + 2) * sizeof(uint32_t)));
     r.item_capacity_tris = cap;
   }
@@ -397,7 +410,7 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
   memset(&pv, 0, sizeof pv);
   if (push) pv = *push;
   if (sc->n_tris == 0 && !push) return VCT_OK;
-  int rc = ensure_tri_scratch(dev, 0, sc->n_tris, sizeof(VoxTri));
+  int rc = ensure_tri_scratch(dev, 0, sc->n_tris, (size_t)sc->n_tris * sizeof(VoxTri));
   if (rc) return rc;
   if (dev->frag_capacity == 0) {
     rc = vct_voxelize_reserve(dev, 1u << 20);
@@ -408,6 +421,8 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
   // level was all zero before; the tile flags stay valid as long as every writer of level 0 marks them
   const bool was_zero = g->base_zero;
   g->base_zero = false;
+  if (g->dirty_z0 >= g->dirty_z1) { g->dirty_z0 = z0; g->dirty_z1 = z1; }
+  else { g->dirty_z0 = min(g->dirty_z0, z0); g->dirty_z1 = max(g->dirty_z1, z1); }
   g->sparse_clear_ok = was_zero && !push && !g->external;
   dev->vox_owner = g;
   uint8_t* touched = (g->flags_valid && !push && !g->external) ? g->tile_touched : nullptr;
@@ -425,7 +440,8 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
                                                           dev->counters + CNT_TICKET_VOX, dev->counters + CNT_ITEMS);
     vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->rs[0].item_local, dev->rs[0].item_block, n_blocks, ctx);
   }
-  vox_resolve_kernel<<<sms * 8, 128, 0, s>>>(g->base, dev->frags, dev->fresh, dev->counters, (uint32_t)dev->frag_capacity, pv, touched, log2_int(g->R));
+  vox_resolve_kernel<<<sms * 8, 128, 0, s>>>(g->base, dev->frags, dev->fresh, dev->counters, (uint32_t)dev->frag_capacity, pv, touched, log2_int(g->R),
+                                             dev->status_dev);
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;
 }

@@ -179,11 +179,32 @@ void Renderer::upload_lights() {
         "vct_scene_set_lights");
 }
 
-void Renderer::upload_camera() {}   // the camera matrices travel with the launch (kernel arguments), there is no UBO
+vct_trace_params_t Renderer::trace_params() const {
+  vct_trace_params_t p;
+  std::memset(&p, 0, sizeof p);
+  p.enable_direct = m_enable_direct; p.enable_diffuse = m_enable_indirect_diffuse;
+  p.enable_specular = m_enable_indirect_specular; p.enable_shadow = m_enable_shadows;
+  p.view_voxel_dir = m_view_voxel_dir; p.view_voxel_lod = m_view_voxel_lod;
+  p.n_diffuse_cones = m_diffuse_cones;
+  p.tile_rank = m_rank; p.tile_nranks = m_nranks;
+  p.sampler = m_sampler;
+  return p;
+}
 
-void Renderer::voxelize() {}        // folded into render(): one stream-ordered sequence through vct_render_frame
-void Renderer::filter() {}
-void Renderer::visualize() {}
+// voxelize() (renderer.cpp:316-353): clear the voxel textures, scatter the scene into them, build the mip chains
+bool Renderer::voxelize() {
+  const int R = (int)m_resolution;
+  if ((m_last_rc = vct_grid_clear(m_grid)) != VCT_OK) return false;
+  if ((m_last_rc = vct_voxelize(m_device.handle(), m_scene, m_grid, 0, R)) != VCT_OK) return false;
+  return filter();
+}
+bool Renderer::filter() { return (m_last_rc = vct_mipmap(m_device.handle(), m_grid)) == VCT_OK; }
+// visualize() (renderer.cpp:355-390): visibility pass + the fragment shader's cone tracing
+bool Renderer::visualize() {
+  const vct_trace_params_t p = trace_params();
+  if ((m_last_rc = vct_gbuffer(m_device.handle(), m_scene, m_camera.view.m, m_camera.projection.m, m_target)) != VCT_OK) return false;
+  return (m_last_rc = vct_cone_trace(m_device.handle(), m_scene, m_grid, m_camera.view.m, &p, m_target)) == VCT_OK;
+}
 
 void Renderer::render() {
   if (!ok()) {
@@ -196,16 +217,15 @@ void Renderer::render() {
   check(vct_scene_set_cube_size(m_scene, m_cube_size), "vct_scene_set_cube_size");
   draw_models();
   upload_lights();
-  vct_trace_params_t p;
-  std::memset(&p, 0, sizeof p);
-  p.enable_direct = m_enable_direct; p.enable_diffuse = m_enable_indirect_diffuse;
-  p.enable_specular = m_enable_indirect_specular; p.enable_shadow = m_enable_shadows;
-  p.view_voxel_dir = m_view_voxel_dir; p.view_voxel_lod = m_view_voxel_lod;
-  p.n_diffuse_cones = m_diffuse_cones;
-  p.tile_rank = m_rank; p.tile_nranks = m_nranks;
-  p.sampler = m_sampler;
-  // clear -> voxelize -> filter -> visualize (renderer.cpp:392-402), asynchronous on the device stream
-  check(vct_render_frame(m_device.handle(), m_scene, m_grid, m_target, m_camera.view.m, m_camera.projection.m, &p), "vct_render_frame");
+  const vct_trace_params_t p = trace_params();
+  // clear -> voxelize -> filter -> visualize (renderer.cpp:392-402), asynchronous on the device stream.  VCT_ERR_OVERFLOW = an
+  // earlier frame's voxelization did not fit the fragment arena; the library has grown it, the frame is simply issued again.
+  for (int attempt = 0; attempt < 4; attempt++) {
+    if (m_staged) { if (voxelize()) visualize(); }
+    else m_last_rc = vct_render_frame(m_device.handle(), m_scene, m_grid, m_target, m_camera.view.m, m_camera.projection.m, &p);
+    if (m_last_rc != VCT_ERR_OVERFLOW) break;
+  }
+  check(m_last_rc, m_staged ? "voxelize/visualize" : "vct_render_frame");
   m_draw_queue.clear();      // renderer.cpp:403-404
   m_point_lights.clear();
 }
