@@ -54,6 +54,9 @@ def main():
             p1.render_frame(view, proj, prm)
             ref_frame, ref_base, ref_l2 = p1.target.frame().copy(), p1.grid.download(0), p1.grid.download(2, 3)
             p1.close()
+        rb = torch.from_numpy(ref_base.astype(np.int64)) if rank == 0 else torch.zeros((R, R, R), dtype=torch.int64)
+        dist.broadcast(rb, 0)                   # every rank checks its gathered grid against the single-GPU grid, every frame
+        ref_base = rb.numpy().astype(np.uint32)
         pipe = capi.Pipeline(sc, R, W, H, ordinal=ordinal)
         handles = [None] * world
         dist.all_gather_object(handles, pipe.peer_export())
@@ -65,7 +68,7 @@ def main():
             pipe.sync()
             if rank == 0:
                 ok &= bool(np.array_equal(pipe.target.frame(), ref_frame))
-            ok &= bool(np.array_equal(pipe.grid.download(0), ref_base if rank == 0 else pipe.grid.download(0)))
+            ok &= bool(np.array_equal(pipe.grid.download(0), ref_base))
         base = pipe.grid.download(0)
         bt = torch.from_numpy(base.astype(np.int64)); b0 = bt.clone()
         dist.broadcast(b0, 0)

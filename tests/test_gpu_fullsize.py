@@ -1,0 +1,143 @@
+"""GPU parity at the FULL sizes of BASELINE.json's configs 3, 4 and 5 (512^3 .. 1024^3 grids, 1440p .. 8K frames, 1 M / 4 M
+triangles) and of the SURVEY 8(d) mip micro-inputs (random 512^3 / 1024^3 grids).  What breaks only at these sizes: the 32-bit
+voxel index / key packing of the voxelizer, the tile arithmetic of the streaming mip kernel, per-triangle work-item sizes of the
+rasterisers, and the grouped-diffuse cone path at 8K.
+
+Bars as in test_gpu_parity.py: voxels, all 36 mip volumes, visibility and G-buffer attributes BIT-EXACT against the oracle; the
+frame within 2/255 and 45 dB, compared on the 32x32 screen tiles the oracle traces (`orc.trace(stride, phase)`; tracing an 8K
+frame in full on the host would take minutes).  Oracle = CPU restatement, parity unpinned."""
+import numpy as np
+import pytest
+
+from oracle import orc
+from voxel_cone_tracing_b200 import capi
+from voxel_cone_tracing_b200 import scene as S
+
+pytestmark = pytest.mark.gpu
+
+FRAME_MAX_ABS = 2
+FRAME_MIN_PSNR = 45.0
+
+
+def _tile_mask(W, H, stride, phase):
+    ty, tx = np.meshgrid(np.arange(H) // 32, np.arange(W) // 32, indexing="ij")
+    return (ty * ((W + 31) // 32) + tx) % stride == phase
+
+
+def _check_frame_tiles(got, exp, mask):
+    a = got.view(np.uint8).reshape(got.shape + (4,))[mask].astype(np.int32)
+    b = exp.view(np.uint8).reshape(exp.shape + (4,))[mask].astype(np.int32)
+    assert a.size > 100_000
+    d = np.abs(a - b)
+    mse = float(np.mean((a - b).astype(np.float64) ** 2))
+    ps = 99.0 if mse == 0 else 10.0 * np.log10(255.0 ** 2 / mse)
+    assert d.max() <= FRAME_MAX_ABS, f"max abs {d.max()}/255"
+    assert ps >= FRAME_MIN_PSNR, f"PSNR {ps:.2f} dB"
+    return int(d.max()), ps
+
+
+def _check_pyramid(grid, base, levels=7):
+    pyr = orc.mipmap(base, levels)
+    for l in range(1, levels):
+        for d in range(6):
+            got = grid.download(l, d)
+            exp = pyr.levels[d][l]
+            assert np.array_equal(got, exp), f"level {l} dir {d}: {(got != exp).sum()} of {exp.size} texels differ"
+    return pyr
+
+
+def _full_size_config(sc, R, W, H, stride, cones, check_gbuffer_attrs=True):
+    """one frame through vct_render_frame; returns a dict of what was compared (printed with -s)"""
+    view, proj = S.reference_camera(W / H)
+    exp_base, st = orc.voxelize(sc, R)
+    p = capi.Pipeline(sc, R, W, H, 7, reserve=max(1 << 22, int(st.fragments) + (1 << 16)))
+    prm = capi.default_params(sampler=capi.SAMPLER_TEX, n_diffuse_cones=cones)
+    p.render_frame(view, proj, prm)
+    gst = p.voxel_stats()
+    assert (gst.fragments, gst.occupied, gst.max_per_voxel) == (st.fragments, st.occupied, st.max_per_voxel)
+    got_base = p.grid.download(0)
+    assert np.array_equal(got_base != 0, exp_base != 0), "voxel occupancy differs"
+    assert np.array_equal(got_base, exp_base), f"{(got_base != exp_base).sum()} voxel colours differ"
+    del got_base
+    pyr = _check_pyramid(p.grid, exp_base)
+    eg = orc.gbuffer(sc, view, proj, W, H)
+    gg = p.target.gbuffer()
+    assert np.array_equal(gg["tri_id"], eg.tri_id), f"{(gg['tri_id'] != eg.tri_id).sum()} pixels see another triangle"
+    hit = eg.tri_id != 0xFFFFFFFF
+    if check_gbuffer_attrs:
+        assert np.array_equal(gg["depth"][hit], eg.depth[hit])
+        assert np.array_equal(gg["world_pos"][hit], eg.world_pos[hit]) and np.array_equal(gg["normal"][hit], eg.normal[hit])
+    del gg
+    exp_frame, ts = orc.trace(sc, view, eg, pyr, orc.default_params(n_diffuse_cones=cones), stride, 1 % stride)
+    mx, ps = _check_frame_tiles(p.target.frame(), exp_frame, _tile_mask(W, H, stride, 1 % stride))
+    p.close()
+    return dict(fragments=int(st.fragments), occupied=int(st.occupied), wrapped_voxels=int(st.wrapped_voxels), max_per_voxel=int(st.max_per_voxel),
+                shaded=float(hit.mean()), frame_max_abs=mx, frame_psnr=round(ps, 1), oracle_samples_on_subset=int(ts.samples))
+
+
+@pytest.mark.parametrize("frame_no", [0, 21, 63])
+def test_config3_suzanne_512_1440p(frame_no):
+    """BASELINE config 3: Cornell box + Suzanne rotating 0.05 rad per frame, 512^3, 2560x1440; frames 0, 21 and 63 of the 64"""
+    info = _full_size_config(S.cornell_scene(with_suzanne=True, theta=0.05 * frame_no), 512, 2560, 1440, 8, 9)
+    print("config 3 frame", frame_no, info)
+    assert info["wrapped_voxels"] == 0 and info["max_per_voxel"] < 16    # the reference scene never wraps the count nibble
+
+
+def test_config4_one_million_triangles_512_4k():
+    """BASELINE config 4: seeded synthetic scene of ~1 M triangles, 512^3, 3840x2160"""
+    sc = S.synthetic_scene(1_000_012, 0x5EED0001)
+    info = _full_size_config(sc, 512, 3840, 2160, 32, 9)
+    print("config 4", info)
+    assert info["fragments"] > 5_000_000
+
+
+def test_config5_four_million_triangles_1024_8k_16_cones():
+    """BASELINE config 5 (RGBA8 storage, 7 levels): ~4 M triangles, 1024^3, 7680x4320, 16 diffuse cones"""
+    sc = S.synthetic_scene(4_000_000, 0x5EED0002)
+    info = _full_size_config(sc, 1024, 7680, 4320, 128, 16)
+    print("config 5", info)
+    assert info["fragments"] > 20_000_000
+
+
+def _tiled_random_grid(R, seed=1):
+    """R^3 words that differ everywhere but cost one 256^3 draw: a random 256^3 block repeated with a per-block XOR constant"""
+    rng = np.random.default_rng(seed)
+    B = min(R, 256)
+    blk = rng.integers(0, 2 ** 32, (B, B, B), dtype=np.uint64).astype(np.uint32)
+    n = R // B
+    base = np.empty((R, R, R), np.uint32)
+    keys = rng.integers(0, 2 ** 32, (n, n, n), dtype=np.uint64).astype(np.uint32)
+    for bz in range(n):
+        for by in range(n):
+            for bx in range(n):
+                np.bitwise_xor(blk, keys[bz, by, bx], out=base[bz * B:(bz + 1) * B, by * B:(by + 1) * B, bx * B:(bx + 1) * B])
+    return base
+
+
+@pytest.mark.parametrize("R", [512, 1024])
+def test_mip_random_grid_full_size(R):
+    """SURVEY 8(d) mip micro-input at 512^3 and 1024^3: every texel non-zero, all 36 volumes bit-exact"""
+    dev = capi.Device(0)
+    base = _tiled_random_grid(R)
+    g = capi.Grid(dev, R, 7)
+    g.upload_base(base)
+    capi.check(dev.L.vct_mipmap(dev.h, g.h))
+    _check_pyramid(g, base)
+    g.close()
+    dev.close()
+
+
+def test_mip_sparse_and_opaque_grid_512():
+    """1 % occupancy with opaque voxels (alpha 255: a quarter of the channels are exact rounding ties, the replay path) at 512^3"""
+    R = 512
+    dev = capi.Device(0)
+    base = _tiled_random_grid(R, seed=3) | np.uint32(0xFF000000)
+    rng = np.random.default_rng(4)
+    keep = rng.random((R // 4, R // 4, R // 4)) < 0.01
+    base[~np.repeat(np.repeat(np.repeat(keep, 4, 0), 4, 1), 4, 2)] = 0
+    g = capi.Grid(dev, R, 7)
+    g.upload_base(base)
+    capi.check(dev.L.vct_mipmap(dev.h, g.h))
+    _check_pyramid(g, base)
+    g.close()
+    dev.close()

@@ -7,7 +7,7 @@
 //   cam_setup_kernel    triangle-parallel vertex shader + NEAR-PLANE CLIPPING (a triangle becomes 0, 1 or 2
 //                       pieces, rule R2c of the oracle) + projection + snapping.  Pieces whose bounding box
 //                       holds a few dozen pixel centres are depth-tested right there (one lane per triangle);
-//                       the others get a record in a compact array and 64x64-pixel work items.
+//                       the others get a record in a compact array and 8x8 .. 64x64-pixel work items (size per triangle, raster.cuh).
 //   cam_raster_kernel   one warp per work item (8x8 blocks culled by the edge functions, then two pixels per
 //                       lane); 64-bit atomicMin of (depth bits << 32 | triangle sequence) = GL_LESS with
 //                       "first drawn wins ties"
@@ -175,7 +175,7 @@ cam_raster_kernel(const CamTri* __restrict__ recs, const uint32_t* __restrict__ 
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t g = warp; g < total; g += n_warps) {  // one warp per 64x64 macro tile
+  for (uint32_t g = warp; g < total; g += n_warps) {  // one warp per macro tile (8x8 .. 64x64 pixels, per triangle)
     uint32_t rank;
     const uint32_t ti = find_item_triangle(g, item_block, n_blocks, item_local, n_tris, rank);
     uint32_t slot = (__ldg(big_slot + ti) & 0x7FFFFFFFu) - 1u;

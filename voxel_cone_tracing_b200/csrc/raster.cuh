@@ -4,13 +4,16 @@
 // b_k = float(E_k) / float(2A).  Replaces the fixed-function rasteriser the reference drives at
 // src/renderer.cpp:339-347 (voxelization viewport 2R x 2R) and :358-389 (camera viewport).
 //
-// Work distribution: every triangle's bounding box is cut into 64x64-pixel macro tiles ("items");
-// a block-local scan in the setup kernel plus a one-block scan of the block totals give every
-// item a global index without a host round trip; the raster kernel walks items with one warp
-// per item: the warp first rejects the 8x8-pixel blocks of the macro tile that no edge function
-// can reach (two blocks per lane, one ballot), then visits the live blocks with 2 pixels per lane.
-// (Round 1 used the 8x8 block itself as the item: a wall at 8K is half a million items, each paying
-// two binary searches through the prefix arrays -- 17 of the 33 ms of the config-5 G-buffer pass.)
+// Work distribution: every triangle's bounding box is cut into square macro tiles ("items") of 2^s pixels,
+// s = 3..6 chosen PER TRIANGLE as the smallest size that gives it at most kMaxItemsPerTri items; a block-local
+// scan in the setup kernel plus a one-block scan of the block totals give every item a global index
+// without a host round trip; the raster kernel walks items with one warp per item: the warp first
+// rejects the 8x8-pixel blocks of the macro tile that no edge function can reach (two blocks per lane,
+// one ballot), then visits the live blocks with 2 pixels per lane.
+// Why per triangle: with 8x8 items only, a wall at 8K is half a million items, each paying two binary
+// searches through the prefix arrays (17 of the 33 ms of the config-5 G-buffer pass in round 1); with
+// 64x64 items only, the 1112 triangles of the Cornell box are ~200 items of up to 64 serial blocks and
+// nine tenths of the resident warps idle (vox_raster_kernel 25 -> 298 us at 256^3).
 #pragma once
 
 #include "vct_internal.cuh"
@@ -19,7 +22,8 @@ namespace vct {
 
 constexpr int kSetupThreads = 256;
 constexpr int kTile = 8;  // 8x8 pixels per block: 2 pixels per lane
-constexpr int kMacroShift = 6, kMacro = 1 << kMacroShift;  // 64x64 pixels per work item = 8x8 blocks
+constexpr int kMacroShiftMin = 3, kMacroShiftMax = 6;  // a work item is 8x8 .. 64x64 pixels = 1 .. 64 blocks
+constexpr uint32_t kMaxItemsPerTri = 1024;
 // The in-thread small-triangle path of the setup kernels pays off when there are many triangles; a scene of a few thousand
 // triangles has too few setup threads to hide the fragment work there, its 8x8 items parallelise better.
 constexpr uint32_t kSmallPathMinTris = 32768;
@@ -31,7 +35,7 @@ __device__ __forceinline__ bool raster_setup(const float xw[3], const float yw[3
   t.sign = 0;
   t.imin = 0; t.imax = -1; t.jmin = 0; t.jmax = -1;
   t.area = 0;
-  t.inv_unused = 0.f;
+  t.mshift = kMacroShiftMin;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     if (!(fabsf(xw[k]) <= 2097152.0f) || !(fabsf(yw[k]) <= 2097152.0f)) return false;  // guard band / NaN
@@ -52,12 +56,16 @@ __device__ __forceinline__ bool raster_setup(const float xw[3], const float yw[3
   t.imin = i0; t.imax = i1; t.jmin = j0; t.jmax = j1;
   t.area = a > 0 ? a : -a;
   t.sign = a > 0 ? 1 : -1;
+  int ms = kMacroShiftMin;
+  while (ms < kMacroShiftMax && (uint32_t)((i1 >> ms) - (i0 >> ms) + 1) * (uint32_t)((j1 >> ms) - (j0 >> ms) + 1) > kMaxItemsPerTri) ms++;
+  t.mshift = ms;
   return true;
 }
 
 __device__ __forceinline__ uint32_t raster_item_count(const RasterTri& t) {
   if (t.sign == 0) return 0u;
-  int tx = (t.imax >> kMacroShift) - (t.imin >> kMacroShift) + 1, ty = (t.jmax >> kMacroShift) - (t.jmin >> kMacroShift) + 1;
+  const int ms = t.mshift;
+  int tx = (t.imax >> ms) - (t.imin >> ms) + 1, ty = (t.jmax >> ms) - (t.jmin >> ms) + 1;
   return (uint32_t)tx * (uint32_t)ty;
 }
 
@@ -125,16 +133,17 @@ struct MacroItem {
 };
 // all 32 lanes call it
 __device__ __forceinline__ void macro_item_setup(const RasterTri& rt, uint32_t rank, int lane, MacroItem& m) {
-  const int tiles_x = (rt.imax >> kMacroShift) - (rt.imin >> kMacroShift) + 1;
-  const int tx = (rt.imin >> kMacroShift) + (int)(rank % (uint32_t)tiles_x), ty = (rt.jmin >> kMacroShift) + (int)(rank / (uint32_t)tiles_x);
-  m.x0 = tx * kMacro; m.y0 = ty * kMacro;
+  const int ms = rt.mshift, nb = 1 << (ms - 3);   // the macro tile is nb x nb blocks; block index b = by * 8 + bx whatever nb is
+  const int tiles_x = (rt.imax >> ms) - (rt.imin >> ms) + 1;
+  const int tx = (rt.imin >> ms) + (int)(rank % (uint32_t)tiles_x), ty = (rt.jmin >> ms) + (int)(rank / (uint32_t)tiles_x);
+  m.x0 = tx << ms; m.y0 = ty << ms;
   edge_block_setup(rt, m.x0, m.y0, m.em);
   uint32_t mask[2];
 #pragma unroll
   for (int h = 0; h < 2; h++) {
     const int b = lane + 32 * h, bx = b & 7, by = b >> 3;
     const int ox = m.x0 + 8 * bx, oy = m.y0 + 8 * by;
-    bool ok = ox <= rt.imax && ox + 7 >= rt.imin && oy <= rt.jmax && oy + 7 >= rt.jmin;
+    bool ok = bx < nb && by < nb && ox <= rt.imax && ox + 7 >= rt.imin && oy <= rt.jmax && oy + 7 >= rt.jmin;
 #pragma unroll
     for (int k = 0; k < 3; k++) {
       // the largest value edge k takes on the pixel centres of the block (corners): negative = the block is outside

@@ -49,7 +49,7 @@ struct RasterTri {
   int32_t X[3], Y[3];   // 24.8 fixed-point window coordinates
   int32_t sign;         // orientation (+1 / -1), 0 = rejected
   int32_t imin, imax, jmin, jmax;
-  float inv_unused;
+  int32_t mshift;       // log2 of this triangle's work-item size in pixels (raster.cuh)
   long long area;       // > 0
 };
 

@@ -6,7 +6,7 @@
 //                         selection (voxelize.geom:25-55), 1/256-pixel snapping, 8x8-pixel item count,
 //                         block-local scan
 //   2. (inside 1.)        the last block to finish scans the block totals: global item offsets (no host round trip, no extra launch)
-//   3. vox_raster_kernel  one warp per 64x64 macro tile (8x8 blocks culled by the edge functions): coverage, fragment shading (voxelize.frag:122-157),
+//   3. vox_raster_kernel  one warp per macro tile (8x8 .. 64x64 pixels, per triangle) (8x8 blocks culled by the edge functions): coverage, fragment shading (voxelize.frag:122-157),
 //                         append of a 32-byte fragment record to a per-voxel linked list whose head
 //                         lives in the grid word itself (atomicExch); the fragment that finds the voxel
 //                         empty marks its arena slot (`fresh`).  Triangles of <= 36 pixels are rasterised
@@ -232,7 +232,7 @@ vox_raster_kernel(const VoxTri* __restrict__ tris, uint32_t n_tris, const uint32
   const int lane = threadIdx.x & 31;
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
-  // one warp per 64x64 macro tile (grid-stride): every lane runs the same two binary searches (broadcast loads), the warp rejects
+  // one warp per macro tile (8x8 .. 64x64 pixels, per triangle) (grid-stride): every lane runs the same two binary searches (broadcast loads), the warp rejects
   // the 8x8 blocks no edge reaches and rasterises the rest, two pixels per lane
   for (uint32_t g = warp; g < total; g += n_warps) {
     uint32_t rank;
