@@ -1,23 +1,31 @@
-"""Print the key metrics of an ncu report (raw page) for every captured kernel."""
-import csv, subprocess, sys
-out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-rows = list(csv.reader(out.splitlines()))
-h = rows[0]
-want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
-        "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
-        "l1tex__t_requests_pipe_tex_mem_texture.sum", "l1tex__data_pipe_tex_wavefronts.avg.pct_of_peak_sustained_elapsed",
-        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active",
-        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
-        "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_tex_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio", "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
-        "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio", "smsp__average_warps_issue_stalled_dispatch_stall_per_issue_active.ratio"]
-idx = [(n, h.index(n)) for n in want if n in h]
-for r in rows[2:]:
-    print("-" * 60)
-    for n, i in idx:
-        print(f"{n:85s} {rows[1][i]:>10s} {r[i]}")
+"""Key metrics of every kernel of an .ncu-rep (ncu --set full), one block per launch.   python tools/ncu_key.py file.ncu-rep [name-filter]"""
+import csv
+import subprocess
+import sys
+
+WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'dram__throughput.avg.pct_of_peak_sustained_elapsed',
+        'lts__t_bytes.sum', 'smsp__inst_executed.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'smsp__cycles_active.avg', 'sm__cycles_elapsed.max',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'lts__t_sectors_op_atom.sum', 'lts__t_sectors_op_red.sum',
+        'sm__inst_executed_pipe_tex.sum', 'l1tex__texin_sm2tex_req_cycles_active.avg.pct_of_peak_sustained_elapsed']
+STALL = 'smsp__average_warps_issue_stalled_'
+
+
+def main():
+    rows = list(csv.reader(subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout.splitlines()))
+    hdr, units = rows[0], rows[1]
+    flt = sys.argv[2] if len(sys.argv) > 2 else ''
+    ki = hdr.index('Kernel Name')
+    for r in rows[2:]:
+        if flt not in r[ki]:
+            continue
+        print('---', r[ki][:90])
+        for w in WANT:
+            if w in hdr:
+                print(f'  {w:75s} {r[hdr.index(w)]:>16s} {units[hdr.index(w)]}')
+        st = [(float(r[i] or 0), hdr[i][len(STALL):-len('_per_issue_active.ratio')]) for i in range(len(hdr)) if hdr[i].startswith(STALL) and hdr[i].endswith('_per_issue_active.ratio')]
+        print('  stalls per issue:', ', '.join(f'{n} {v:.2f}' for v, n in sorted(st, reverse=True)[:7]))
+
+
+if __name__ == '__main__':
+    main()

@@ -311,9 +311,9 @@ int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) {
   g->base_buf[0] = g->base;
   g->bytes = n0 * 4;
   if (mip_fused_applies(R, levels)) {
-    // the fused mip kernel (csrc/mipmap.cu): one flag pair per 32x16x8 tile, arrival counters per 32^3 block, and the small linear
-    // copies of the coarse levels that cross CTAs inside the launch
-    const size_t n_tiles = n0 / 4096, n_blocks = n0 / 32768, n3 = n0 / 512;
+    // the streaming mip kernel (csrc/mipmap.cu): one flag pair per 32x8x8 warp-tile, and the small linear copies of the coarse
+    // levels that the tail kernel folds
+    const size_t n_tiles = n0 / 2048, n_blocks = n0 / 32768, n3 = n0 / 512;
     auto zalloc = [&](void** p, size_t bytes) {
       if (e == cudaSuccess) e = cudaMalloc(p, bytes);
       if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, bytes, dev->stream);
@@ -322,6 +322,7 @@ int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) {
     zalloc((void**)&g->tile_touched, n_tiles);
     zalloc((void**)&g->tile_zero, n_tiles);           // 0 = unknown: the first build writes everything
     zalloc((void**)&g->mip_counters, (1 + n_blocks) * 4);
+    zalloc((void**)&g->sb_epoch, (n0 / 262144 + 1) * 4);
     zalloc((void**)&g->rec3, n3 * 24);
     size_t top_words = 0, occ_bytes = 0;
     for (int l = 3; l < levels; l++) {
@@ -446,7 +447,7 @@ int vct_grid_destroy(vct_grid_t* g) {
   if (g->dev->peer_grid == g) vct_peer_disconnect(g->dev);
   cudaStreamSynchronize(g->dev->stream);
   cudaFree(g->base_buf[0]); cudaFree(g->base_buf[1]); cudaFree(g->tile_zero); cudaFree(g->tile_touched);
-  cudaFree(g->rec3); cudaFree(g->rec_top); cudaFree(g->occb); cudaFree(g->mip_counters);
+  cudaFree(g->rec3); cudaFree(g->rec_top); cudaFree(g->occb); cudaFree(g->mip_counters); cudaFree(g->sb_epoch);
   if (g->dev->vox_owner == g) g->dev->vox_owner = nullptr;
   for (int l = 0; l < 4; l++) cudaFree(g->occ[l]);
   cudaFree(g->occ_hi);
@@ -470,7 +471,7 @@ int vct_grid_clear(vct_grid_t* g) {
     if (rc) return rc;
   } else {
     VCT_CUDA(cudaMemsetAsync(g->base, 0, (size_t)g->R * g->R * g->R * 4, dev->stream));
-    if (g->tile_touched) VCT_CUDA(cudaMemsetAsync(g->tile_touched, 0, (size_t)g->R * g->R * g->R / 4096, dev->stream));
+    if (g->tile_touched) VCT_CUDA(cudaMemsetAsync(g->tile_touched, 0, (size_t)g->R * g->R * g->R / 2048, dev->stream));
   }
   g->sparse_clear_ok = false;
   g->flags_valid = g->tile_touched != nullptr && !g->external;

@@ -136,58 +136,66 @@ VCT_HD Face face_bytes(const BytePair& ab, const BytePair& ce) {
   return f;
 }
 
-VCT_HD uint32_t mul_hi_u32(uint32_t a, uint32_t b) {
+// saturating pack of four non-negative ints into bytes: q0 | q1 << 8 | q2 << 16 | q3 << 24, each clamped to 255 (two I2IP instructions)
+VCT_HD uint32_t pack4_sat_u8(uint32_t q0, uint32_t q1, uint32_t q2, uint32_t q3) {
 #if defined(__CUDA_ARCH__)
-  return __umulhi(a, b);
+  uint32_t hi, r;
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(hi) : "r"(q3), "r"(q2), "r"(0u));
+  asm("cvt.pack.sat.u8.s32.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(q1), "r"(q0), "r"(hi));
+  return r;
 #else
-  return (uint32_t)(((uint64_t)a * b) >> 32);
+  const uint32_t c0 = q0 < 255u ? q0 : 255u, c1 = q1 < 255u ? q1 : 255u, c2 = q2 < 255u ? q2 : 255u, c3 = q3 < 255u ? q3 : 255u;
+  return c0 | (c1 << 8) | (c2 << 16) | (c3 << 24);
 #endif
 }
 
 // One direction: front face F, back face B (children in the same pair order) -> destination word, plus a 4-bit mask of
 // the channels that are exact ties (to be replayed with mip_replay_channel).  N = 255 * sum(F_k) + sum((255 - F_a) * B_k);
-// round(N / 1020) = floor((N + 510) / 1020), the division by multiply-high (exact for every N this formula can produce,
-// checked exhaustively), tie <=> the remainder is 0.  The clamp is the oracle's clamp(., 0, 1).
+// round(N / 1020) = floor(M / 1020) with M = N + 510 <= 520710.  One 32 x 32 -> 64 multiply gives both the quotient and the tie test:
+// 4210753 * 1020 = 2^32 + 764, so for M = 1020 q + r the product is q * 2^32 + (764 q + r * 4210753) with the bracket < 2^32
+// (<= 389640 + 1019 * 4210753): the high word IS q, and the low word is < 4210753 exactly when r = 0, i.e. on a tie.
+// The clamp is the oracle's clamp(., 0, 1).
+constexpr uint32_t kDiv1020 = 4210753u;
 VCT_HD uint32_t mip_filter_faces(const Face& F, const Face& B, uint32_t& tie_mask) {
   const uint32_t W = ~F.ch[3];   // 255 - alpha of the four front children
-  uint32_t q[4], rem[4];
+  uint32_t q[4], lo[4];
 #pragma unroll
   for (int k = 0; k < 4; k++) {
-    const uint32_t M = dot4_u8(W, B.ch[k], dot4_u8(0xFFFFFFFFu, F.ch[k], 510u));   // N + 510 <= 520710
-    const uint32_t qq = mul_hi_u32(M, 4210753u);                                   // floor(M / 1020)
-    rem[k] = M - qq * 1020u;
-    q[k] = qq < 255u ? qq : 255u;
+    const uint32_t M = dot4_u8(W, B.ch[k], dot4_u8(0xFFFFFFFFu, F.ch[k], 510u));
+    const unsigned long long p = (unsigned long long)M * kDiv1020;
+    q[k] = (uint32_t)(p >> 32);
+    lo[k] = (uint32_t)p;
   }
   tie_mask = 0u;
-  const uint32_t m01 = rem[0] < rem[1] ? rem[0] : rem[1], m23 = rem[2] < rem[3] ? rem[2] : rem[3];
-  if ((m01 < m23 ? m01 : m23) == 0u)   // rare: one branch per direction instead of a mask update per channel
-    tie_mask = (rem[0] == 0u ? 1u : 0u) | (rem[1] == 0u ? 2u : 0u) | (rem[2] == 0u ? 4u : 0u) | (rem[3] == 0u ? 8u : 0u);
-  const uint32_t lo = byte_perm(q[0], q[1], 0x0040u);   // [q0.b0, q1.b0, ., .]
-  const uint32_t hi = byte_perm(q[2], q[3], 0x0040u);
-  return byte_perm(lo, hi, 0x5410u);
+  const uint32_t m01 = lo[0] < lo[1] ? lo[0] : lo[1], m23 = lo[2] < lo[3] ? lo[2] : lo[3];
+  if ((m01 < m23 ? m01 : m23) < kDiv1020)   // rare: one branch per direction instead of a mask update per channel
+    tie_mask = (lo[0] < kDiv1020 ? 1u : 0u) | (lo[1] < kDiv1020 ? 2u : 0u) | (lo[2] < kDiv1020 ? 4u : 0u) | (lo[3] < kDiv1020 ? 8u : 0u);
+  return pack4_sat_u8(q[0], q[1], q[2], q[3]);
 }
 
 // All six directions of one destination texel whose eight children are the SAME words in every direction
 // (level 0 -> 1: the reference writes the same value into all six level-0 textures, voxelize.frag:159-160).
 // w[i] = child i.  out[d], and ties |= (channel mask) << (4 * d).
 VCT_HD void mip_filter6_shared(const uint32_t (&w)[8], uint32_t (&out)[6], uint32_t& ties) {
-  // z-pairs (0,1) (2,3) (4,5) (6,7) serve the x and y faces, y-pairs (0,2) (4,6) (1,3) (5,7) the z faces
+  // x faces by a two-stage byte transpose of the z-pairs (0,1) (2,3) | (4,5) (6,7); the y and z faces are byte selections of the
+  // two x faces (one PRMT per channel): y = 1: (0,1,4,5), y = 0: (2,3,6,7); z = 1: (0,2,4,6), z = 0: (1,3,5,7).  32 PRMT in all.
   const BytePair p01 = pair_bytes(w[0], w[1]), p23 = pair_bytes(w[2], w[3]), p45 = pair_bytes(w[4], w[5]), p67 = pair_bytes(w[6], w[7]);
+  const Face x1 = face_bytes(p01, p23), x0 = face_bytes(p45, p67);   // pairs (0,4) (1,5) (2,6) (3,7)
   uint32_t tm;
   ties = 0u;
+  out[0] = mip_filter_faces(x1, x0, tm); ties |= tm;
+  out[1] = mip_filter_faces(x0, x1, tm); ties |= tm << 4;
   {
-    const Face x1 = face_bytes(p01, p23), x0 = face_bytes(p45, p67);   // x = 1: (0,1,2,3), x = 0: (4,5,6,7) -> pairs (0,4) (1,5) (2,6) (3,7)
-    out[0] = mip_filter_faces(x1, x0, tm); ties |= tm;
-    out[1] = mip_filter_faces(x0, x1, tm); ties |= tm << 4;
-  }
-  {
-    const Face y1 = face_bytes(p01, p45), y0 = face_bytes(p23, p67);   // y = 1: (0,1,4,5), y = 0: (2,3,6,7) -> pairs (0,2) (1,3) (4,6) (5,7)
+    Face y1, y0;   // pairs (0,2) (1,3) (4,6) (5,7)
+#pragma unroll
+    for (int k = 0; k < 4; k++) { y1.ch[k] = byte_perm(x1.ch[k], x0.ch[k], 0x5410u); y0.ch[k] = byte_perm(x1.ch[k], x0.ch[k], 0x7632u); }
     out[2] = mip_filter_faces(y1, y0, tm); ties |= tm << 8;
     out[3] = mip_filter_faces(y0, y1, tm); ties |= tm << 12;
   }
   {
-    const BytePair p02 = pair_bytes(w[0], w[2]), p46 = pair_bytes(w[4], w[6]), p13 = pair_bytes(w[1], w[3]), p57 = pair_bytes(w[5], w[7]);
-    const Face z1 = face_bytes(p02, p46), z0 = face_bytes(p13, p57);   // z = 1: (0,2,4,6), z = 0: (1,3,5,7) -> pairs (0,1) (2,3) (4,5) (6,7)
+    Face z1, z0;   // pairs (0,1) (2,3) (4,5) (6,7)
+#pragma unroll
+    for (int k = 0; k < 4; k++) { z1.ch[k] = byte_perm(x1.ch[k], x0.ch[k], 0x6420u); z0.ch[k] = byte_perm(x1.ch[k], x0.ch[k], 0x7531u); }
     out[4] = mip_filter_faces(z1, z0, tm); ties |= tm << 16;
     out[5] = mip_filter_faces(z0, z1, tm); ties |= tm << 20;
   }

@@ -254,18 +254,18 @@ struct vct_grid {
   cudaTextureObject_t tex_lin = 0, tex_one = 0, tex_pt = 0;
   float tex_zs = 0.0f;
   vct::SurfSet surf{};
-  alignas(64) unsigned char tmap_storage[2][128] = {};   // CUtensorMap (TMA descriptor) of base_buf[0] / base_buf[1], built on first use
-  uint32_t* tmap_base_ptr[2] = {};
-  // ---- scratch of the fused mip kernel (csrc/mipmap.cu): small linear copies of the coarse levels that cross CTAs ----
+  // ---- scratch of the mip kernels (csrc/mipmap.cu): small linear copies of the coarse levels that cross warps / CTAs ----
   uint32_t* rec3 = nullptr;             // level 3 as records of six words per texel: what a 32^3 block's last tile needs of the other tiles
   uint32_t* rec_top = nullptr;          // levels 5.. as records (level l at rec_top + top_off[l]): input of the single-CTA top of the chain
   uint32_t top_off[VCT_MAX_LEVELS] = {};
   uint8_t* occb = nullptr;              // levels 3..: one occupancy byte per texel (level l at occb + occb_off[l])
   uint32_t occb_off[VCT_MAX_LEVELS] = {};
+  uint32_t* sb_epoch = nullptr;         // per 64^3 super-block: the last mip build (mip_build) that processed one of its tiles
+  uint32_t mip_build = 0;
   uint32_t* mip_counters = nullptr;     // [0] = blocks finished, [1 + b] = tiles of 32^3 block b that have arrived
-  uint8_t* tile_zero = nullptr;         // mip stage: per 32x16x8 tile "every output of this tile is known to be zero" (skip rewriting zeros)
+  uint8_t* tile_zero = nullptr;         // mip stage: per 32x8x8 tile "every output of this tile is known to be zero" (skip rewriting zeros)
   // ---- sparse frame-to-frame bookkeeping (< 1 % of the voxels are occupied) ----
-  // tile_touched[tile] != 0: the last vct_voxelize wrote a voxel of this 32x16x8 tile.  While flags_valid, every non-zero word of
+  // tile_touched[tile] != 0: the last vct_voxelize wrote a voxel of this 32x8x8 tile.  While flags_valid, every non-zero word of
   // level 0 lies in a touched tile, so the mip build skips untouched tiles whose outputs are already zero without reading them.
   // While sparse_clear_ok (and dev->vox_owner == this), the non-zero words are exactly the device's occupied list and
   // vct_grid_clear zeroes those instead of the whole level.  Anything that writes level 0 behind the library's back
@@ -340,7 +340,7 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
 int launch_peer_wait(vct_device* dev, int kind, uint32_t epoch);
 int check_status(vct_device* dev);   // VCT_ERR_OVERFLOW / VCT_ERR_CUDA if a kernel reported an arena overflow / a peer timeout since the last check
 int launch_mipmap(vct_device* dev, vct_grid* g);
-bool mip_fused_applies(int R, int levels);   // the fused mip kernel (32x16x8 tiles, 32^3 blocks) handles this grid
+bool mip_fused_applies(int R, int levels);   // the fused mip kernel (32x8x8 tiles, 32^3 blocks) handles this grid
 int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const float* proj, vct_target_t_* t, int tile_rank = 0, int tile_nranks = 1);
 // phase: 0 = tile list + cones + shade; 1 = the live-tile list only (depends on the G-buffer alone: vct_render_frame builds it on the
 // G-buffer stream); 2 = cones + shade with the list of a preceding phase-1 call

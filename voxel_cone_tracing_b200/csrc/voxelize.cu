@@ -289,10 +289,10 @@ __device__ __forceinline__ uint32_t avg_fold(uint32_t stored, const float val[4]
 
 constexpr int kSortMax = 24;
 
-// 32x16x8 tile (the unit of the fused mip kernel, mipmap.cu) of a level-0 voxel index; R = 2^logR >= 32
+// 32x8x8 warp-tile (the unit of the streaming mip kernel, mipmap.cu) of a level-0 voxel index; R = 2^logR >= 32
 __device__ __forceinline__ uint32_t tile_of_voxel(uint32_t voxel, int logR) {
   const uint32_t m = (1u << logR) - 1u, x = voxel & m, y = (voxel >> logR) & m, z = voxel >> (2 * logR);
-  return ((((z >> 3) << (logR - 4)) + (y >> 4)) << (logR - 5)) + (x >> 5);
+  return ((((z >> 3) << (logR - 3)) + (y >> 3)) << (logR - 5)) + (x >> 5);
 }
 
 // vct_grid_clear, sparse form: zero the voxels (and the tile flags) the last voxelization occupied = the voxels of its `fresh` fragments
@@ -358,7 +358,7 @@ vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frag
       }
     }
     base[voxel] = stored;
-    if (tile_touched) tile_touched[tile_of_voxel(voxel, logR)] = 1;   // sparse mip build: this 32x16x8 tile has content
+    if (tile_touched) tile_touched[tile_of_voxel(voxel, logR)] = 1;   // sparse mip build: this 32x8x8 tile has content
     // multi-GPU: the slab owner writes the resolved voxel straight into every peer's grid over NVLink (sparse
     // exchange: only occupied voxels travel; replaces the dense all-gather of the base level)
     for (int p = 0; p < pv.nranks; p++)
