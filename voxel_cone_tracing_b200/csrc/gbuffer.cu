@@ -22,6 +22,11 @@ namespace vct {
 
 struct Mat4 { float m[16]; };
 constexpr int kSmallCamPixels = 36;
+// Pieces with up to this many pixel centres in their bounding box (and more than kSmallCamPixels) are rasterised by the whole warp
+// inside the set-up kernel, one piece after the other, 8 x 4 pixels per step: no record, no work item, no prefix search.  At 8K with
+// 4 M triangles nearly every triangle is of this size (a few dozen to a few hundred pixels); round 1 gave each of them a record + items
+// (or, once the record array was full, one lane walking the whole box): 29 + 13 ms of the 33 ms frame share of this pass.
+constexpr int kMidCamPixels = 4096;
 
 // one clip-space vertex with the attributes the fragment stage interpolates
 struct ClipVert { float cx, cy, cz, cw; float world[3], nn[3]; };
@@ -117,12 +122,43 @@ __device__ __forceinline__ bool tile_owned(int i, int j, int W, int tile_rank, i
 // depth test of every covered pixel of a piece, one lane per piece (the sub-tile triangles of a large scene)
 __device__ __forceinline__ void raster_piece_inline(const CamTri& v, uint32_t t, int W, unsigned long long* __restrict__ vis, int tile_rank, int tile_nranks) {
   const int bw = v.rt.imax - v.rt.imin + 1, bh = v.rt.jmax - v.rt.jmin + 1;
+  EdgeBlock eb;   // edge functions once at the box origin; a pixel then costs two 32 x 32 -> 64 multiply-adds per edge (same integers as raster_sample)
+  edge_block_setup(v.rt, v.rt.imin, v.rt.jmin, eb);
   for (int j = v.rt.jmin; j < v.rt.jmin + bh; j++)
     for (int i = v.rt.imin; i < v.rt.imin + bw; i++) {
       if (!tile_owned(i, j, W, tile_rank, tile_nranks)) continue;   // multi-GPU: not this rank's screen tile
       float b[3];
-      if (raster_sample(v.rt, i, j, b)) {
+      if (edge_block_sample(eb, i - v.rt.imin, j - v.rt.jmin, b)) {
         const float zw = interp3(b, v.zw[0], v.zw[1], v.zw[2]);
+        if (zw >= 0.0f && zw <= 1.0f) atomicMin(&vis[(size_t)j * W + i], ((unsigned long long)__float_as_uint(zw) << 32) | (unsigned long long)t);
+      }
+    }
+}
+
+// depth test of every covered pixel of ONE piece by all 32 lanes: the owner lane's set-up travels by shuffles, the lanes sweep the
+// bounding box in 8 x 4 pixel steps.  Called by the whole warp (src = owner lane); same arithmetic as raster_piece_inline.
+__device__ __forceinline__ void raster_piece_warp(const CamTri& mine, uint32_t my_tri, int src, int lane, int W, unsigned long long* __restrict__ vis,
+                                                  int tile_rank, int tile_nranks) {
+  RasterTri rt;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { rt.X[k] = __shfl_sync(0xffffffffu, mine.rt.X[k], src); rt.Y[k] = __shfl_sync(0xffffffffu, mine.rt.Y[k], src); }
+  rt.sign = __shfl_sync(0xffffffffu, mine.rt.sign, src);
+  rt.imin = __shfl_sync(0xffffffffu, mine.rt.imin, src); rt.imax = __shfl_sync(0xffffffffu, mine.rt.imax, src);
+  rt.jmin = __shfl_sync(0xffffffffu, mine.rt.jmin, src); rt.jmax = __shfl_sync(0xffffffffu, mine.rt.jmax, src);
+  rt.mshift = 0;
+  rt.area = __shfl_sync(0xffffffffu, mine.rt.area, src);
+  const float z0 = __shfl_sync(0xffffffffu, mine.zw[0], src), z1 = __shfl_sync(0xffffffffu, mine.zw[1], src), z2 = __shfl_sync(0xffffffffu, mine.zw[2], src);
+  const uint32_t t = __shfl_sync(0xffffffffu, my_tri, src);
+  const int lx = lane & 7, ly = lane >> 3;
+  EdgeBlock eb;
+  edge_block_setup(rt, rt.imin, rt.jmin, eb);
+  for (int j0 = rt.jmin; j0 <= rt.jmax; j0 += 4)
+    for (int i0 = rt.imin; i0 <= rt.imax; i0 += 8) {
+      const int i = i0 + lx, j = j0 + ly;
+      if (i > rt.imax || j > rt.jmax || !tile_owned(i, j, W, tile_rank, tile_nranks)) continue;
+      float b[3];
+      if (edge_block_sample(eb, i - rt.imin, j - rt.jmin, b)) {
+        const float zw = interp3(b, z0, z1, z2);
         if (zw >= 0.0f && zw <= 1.0f) atomicMin(&vis[(size_t)j * W + i], ((unsigned long long)__float_as_uint(zw) << 32) | (unsigned long long)t);
       }
     }
@@ -134,24 +170,31 @@ __global__ void __launch_bounds__(kSetupThreads)
 cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ draws,
                  uint32_t n_draws, uint32_t n_tris, Mat4 pv, int W, int H, CamTri* __restrict__ recs, uint32_t rec_capacity, uint32_t* __restrict__ rec_count,
                  uint32_t* __restrict__ big_slot, uint32_t* __restrict__ item_local, uint32_t* __restrict__ item_block, unsigned long long* __restrict__ vis,
-                 int tile_rank, int tile_nranks, int small_limit, uint32_t* scan_ticket, uint32_t* scan_total) {
+                 int tile_rank, int tile_nranks, int small_limit, int mid_limit, uint32_t* scan_ticket, uint32_t* scan_total) {
   const uint32_t t = blockIdx.x * kSetupThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31;
   uint32_t count = 0;
+  CamTri pc[2];
+  int n = 0;
+  bool mid[2] = {false, false};
   if (t < n_tris) {
     const DrawRec& d = draws[find_draw(t, draws, n_draws)];
-    CamTri pc[2];
-    const int n = cam_triangle_pieces(verts, indices, d, t, pv.m, W, H, pc);
+    n = cam_triangle_pieces(verts, indices, d, t, pv.m, W, H, pc);
     bool big[2] = {false, false};
     int n_big = 0;
     for (int q = 0; q < n; q++) {
       const int bw = pc[q].rt.imax - pc[q].rt.imin + 1, bh = pc[q].rt.jmax - pc[q].rt.jmin + 1;
-      big[q] = bw * bh > small_limit;
+      big[q] = bw * bh > mid_limit;
+      mid[q] = !big[q] && bw * bh > small_limit;
       n_big += big[q] ? 1 : 0;
     }
     uint32_t slot = 0;
     if (n_big) {
       slot = atomicAdd(rec_count, (uint32_t)n_big);
-      if (slot + (uint32_t)n_big > rec_capacity) { big[0] = big[1] = false; n_big = 0; }   // record array full: every piece goes the in-line way (slow, still exact)
+      if (slot + (uint32_t)n_big > rec_capacity) {   // record array full: the warp takes these pieces too (slow for a wall-sized piece, still exact)
+        for (int q = 0; q < n; q++) if (big[q]) { big[q] = false; mid[q] = true; }
+        n_big = 0;
+      }
     }
     big_slot[t] = n_big ? ((slot + 1u) | ((uint32_t)(n_big - 1) << 31)) : 0u;
     for (int q = 0; q < n; q++) {
@@ -159,10 +202,15 @@ cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
         pc[q].pad = raster_item_count(pc[q].rt);
         count += pc[q].pad;
         recs[slot++] = pc[q];
-      } else {
+      } else if (!mid[q]) {
         raster_piece_inline(pc[q], t, W, vis, tile_rank, tile_nranks);
       }
     }
+  }
+  // the mid-sized pieces of the warp's 32 triangles, one after the other, all lanes on each
+#pragma unroll
+  for (int q = 0; q < 2; q++) {
+    for (uint32_t m = __ballot_sync(0xffffffffu, mid[q]); m; m &= m - 1u) raster_piece_warp(pc[q], t, __ffs((int)m) - 1, lane, W, vis, tile_rank, tile_nranks);
   }
   block_scan_items(count, t, n_tris, item_local, item_block, scan_ticket, scan_total);
 }
@@ -333,7 +381,8 @@ int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const floa
     { int rc2 = launch_fill_u32(s, rec_count, 1, 0u); if (rc2) return rc2; }
     cam_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, pv, t->W, t->H, recs, (uint32_t)rec_capacity, rec_count,
                                                         dev->rs[1].big_slot, dev->rs[1].item_local, dev->rs[1].item_block, t->vis, tile_rank, tile_nranks,
-                                                        sc->n_tris >= kSmallPathMinTris ? kSmallCamPixels : 0, dev->counters + CNT_TICKET_CAM,
+                                                        sc->n_tris >= kSmallPathMinTris ? kSmallCamPixels : 0, sc->n_tris >= kSmallPathMinTris ? kMidCamPixels : 0,
+                                                        dev->counters + CNT_TICKET_CAM,
                                                         dev->counters + CNT_CAM_ITEMS);
     cam_raster_kernel<<<sms * 8, 256, 0, s>>>(recs, dev->rs[1].big_slot, sc->n_tris, dev->rs[1].item_local, dev->rs[1].item_block, n_blocks, t->W, t->vis, dev->counters,
                                               tile_rank, tile_nranks);

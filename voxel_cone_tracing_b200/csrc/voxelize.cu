@@ -134,11 +134,16 @@ __device__ __forceinline__ void emit_fragments(const FragCtx& c, const VoxTri& v
 // per triangle, the warp walks the boxes in lock-step) instead of becoming 8x8 work items: a scene of millions of
 // sub-voxel triangles would otherwise spend a whole warp on one or two fragments
 constexpr int kSmallPixels = 36;
+// ... and those with up to this many (a few 8x8 blocks) by the whole warp inside the setup kernel, one triangle after the other, 8 x 4
+// pixels per step: no VoxTri record, no work items, no prefix searches.  In the 1 M / 4 M-triangle scenes nearly every triangle is of
+// this size; as 8x8 work items they were 9.4 of the 16 ms of the voxelization at 1024^3.
+constexpr int kMidPixels = 1024;
 
 __global__ void __launch_bounds__(kSetupThreads)
 vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ draws,
                  uint32_t n_draws, uint32_t n_tris, float cube_size, int R, int z0, int z1, VoxTri* __restrict__ out, uint32_t* __restrict__ item_local,
-                 uint32_t* __restrict__ item_block, const FragCtx ctx, int small_limit, uint32_t* scan_ticket, uint32_t* scan_total) {
+                 uint32_t* __restrict__ item_block, const FragCtx ctx, int small_limit, int mid_limit, uint32_t* scan_ticket, uint32_t* scan_total) {
+  __shared__ VoxTri stage[kSetupThreads / 32];   // the triangle the warp is rasterising together
   uint32_t t = blockIdx.x * kSetupThreads + threadIdx.x;
   uint32_t count = 0;
   VoxTri v;
@@ -197,10 +202,12 @@ vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
   // atomics per frame on the 4 M-triangle scene)
   const int lane = threadIdx.x & 31;
   uint32_t mine = 0;
+  EdgeBlock eb0;   // edge functions at the box origin (same integers as raster_sample, two multiply-adds per edge and pixel)
+  edge_block_setup(v.rt, v.rt.imin, v.rt.jmin, eb0);
   for (int p = 0; p < npx; p++) {
     float b[3];
     F3 pos; uint32_t voxel;
-    if (raster_sample(v.rt, v.rt.imin + p % bw, v.rt.jmin + p / bw, b) && fragment_voxel(ctx, v, b, pos, voxel)) mine++;
+    if (edge_block_sample(eb0, p % bw, p / bw, b) && fragment_voxel(ctx, v, b, pos, voxel)) mine++;
   }
   uint32_t incl = mine;
 #pragma unroll
@@ -218,9 +225,31 @@ vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
     float b[3];
     F3 pos; uint32_t voxel;
     const int i = v.rt.imin + p % bw, j = v.rt.jmin + p / bw;
-    if (raster_sample(v.rt, i, j, b) && fragment_voxel(ctx, v, b, pos, voxel)) push_fragment(ctx, v, t, i, j, b, pos, voxel, slot++);
+    if (edge_block_sample(eb0, p % bw, p / bw, b) && fragment_voxel(ctx, v, b, pos, voxel)) push_fragment(ctx, v, t, i, j, b, pos, voxel, slot++);
   }
-  if (small) count = 0;
+  // ---- mid-sized triangles: the whole warp on one triangle at a time ----
+  const bool mid = count > 0 && !small && bw * bh <= mid_limit;
+  for (uint32_t m = __ballot_sync(0xffffffffu, mid); m; m &= m - 1u) {
+    const int src = __ffs((int)m) - 1;
+    VoxTri& sv = stage[threadIdx.x >> 5];
+    __syncwarp();
+    if (lane == src) sv = v;
+    __syncwarp();
+    const uint32_t ti = __shfl_sync(0xffffffffu, t, src);
+    const RasterTri& rt = sv.rt;
+    const int lx = lane & 7, ly = lane >> 3;
+    EdgeBlock eb;
+    edge_block_setup(rt, rt.imin, rt.jmin, eb);
+    for (int j0 = rt.jmin; j0 <= rt.jmax; j0 += 4)
+      for (int i0 = rt.imin; i0 <= rt.imax; i0 += 8) {   // uniform trip counts: every lane reaches emit_fragments (warp-wide ballots)
+        int pi[1] = {i0 + lx}, pj[1] = {j0 + ly};
+        float pb[1][3];
+        bool covered[1];
+        covered[0] = pi[0] <= rt.imax && pj[0] <= rt.jmax && edge_block_sample(eb, pi[0] - rt.imin, pj[0] - rt.jmin, pb[0]);
+        emit_fragments<1>(ctx, sv, ti, pi, pj, pb, covered, lane);
+      }
+  }
+  if (small || mid) count = 0;
   else if (t < n_tris) out[t] = v;   // only triangles that become work items are read again
   block_scan_items(count, t, n_tris, item_local, item_block, scan_ticket, scan_total);
 }
@@ -437,7 +466,7 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
     ctx.base = g->base; ctx.frags = dev->frags; ctx.frag_capacity = (uint32_t)dev->frag_capacity; ctx.fresh = dev->fresh; ctx.counters = dev->counters;
     vox_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, sc->cube_size, g->R, z0, z1, tris,
                                                           dev->rs[0].item_local, dev->rs[0].item_block, ctx, sc->n_tris >= kSmallPathMinTris ? kSmallPixels : 0,
-                                                          dev->counters + CNT_TICKET_VOX, dev->counters + CNT_ITEMS);
+                                                          sc->n_tris >= kSmallPathMinTris ? kMidPixels : 0, dev->counters + CNT_TICKET_VOX, dev->counters + CNT_ITEMS);
     vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->rs[0].item_local, dev->rs[0].item_block, n_blocks, ctx);
   }
   vox_resolve_kernel<<<sms * 8, 128, 0, s>>>(g->base, dev->frags, dev->fresh, dev->counters, (uint32_t)dev->frag_capacity, pv, touched, log2_int(g->R),
