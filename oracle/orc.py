@@ -201,3 +201,8 @@ def render_frame(scene, view, proj, R: int, W: int, H: int, params: TraceParams 
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int) -> None:
+    """OpenMP threads of the oracle (torchrun exports OMP_NUM_THREADS=1 to its ranks: bench.py's CPU legs ask for all the cores)"""
+    lib().orc_set_num_threads(int(n))
