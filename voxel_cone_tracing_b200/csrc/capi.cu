@@ -759,15 +759,31 @@ static int render_frame_sharded(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* 
   const int b = (int)(epoch & 1u);
   PeerView pv = dev->peers;
   pv.epoch = epoch;
-  for (int r = 0; r < pv.nranks; r++) pv.base[r] = dev->peer_base_all[b][r];
+  for (int r = 0; r < pv.nranks; r++) { pv.base[r] = dev->peer_base_all[b][r]; pv.touched[r] = dev->peer_touched_all[b][r]; }
   g->base = g->base_buf[b];
+  // every rank exported tile flags (same grid size everywhere: all or none); a mip tile is 8 slices deep and must belong to ONE slab
+  const bool sparse = pv.touched[pv.rank] != nullptr && g->R % (8 * pv.nranks) == 0;
+  if (!sparse) for (int r = 0; r < pv.nranks; r++) pv.touched[r] = nullptr;
+  if (sparse) {
+    if (dev->frag_capacity == 0)
+      if (int rcr = vct_voxelize_reserve(dev, 1u << 20)) return rcr;
+    if (int rcl = ensure_pushed_lists(dev)) return rcl;
+    pv.pushed = dev->pushed_list[b]; pv.pushed_n = dev->pushed_n + (epoch & 3u); pv.pushed_capacity = (uint32_t)dev->pushed_capacity;
+  }
+  g->peer_touched = sparse ? pv.touched[pv.rank] : nullptr;
   const int z0 = (int)((long long)pv.rank * g->R / pv.nranks), z1 = (int)((long long)(pv.rank + 1) * g->R / pv.nranks);
   vct_trace_params_t prm = *p;
   prm.tile_rank = pv.rank; prm.tile_nranks = pv.nranks;
   int rc;
   VCT_CUDA(cudaEventRecord(dev->ev[0], s));
   VCT_CUDA(cudaEventRecord(dev->ev_fork, s));
-  VCT_CUDA(cudaMemsetAsync(g->base_buf[b ^ 1], 0, (size_t)g->R * g->R * g->R * 4, s));   // clear the NEXT frame's buffer
+  if (sparse) {
+    int logR = 0;
+    while ((1 << logR) < g->R) logR++;
+    if ((rc = launch_peer_unpush(dev, pv, logR))) return rc;   // this frame's buffer: zero what this rank stored into it two frames ago, everywhere
+  } else {
+    VCT_CUDA(cudaMemsetAsync(g->base_buf[b ^ 1], 0, (size_t)g->R * g->R * g->R * 4, s));   // clear the NEXT frame's buffer
+  }
   VCT_CUDA(cudaEventRecord(dev->ev[1], s));
   if ((rc = launch_voxelize(dev, sc, g, z0, z1, &pv))) return rc;   // + push of the slab to the peers
   VCT_CUDA(cudaEventRecord(dev->ev[2], s));

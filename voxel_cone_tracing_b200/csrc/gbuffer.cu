@@ -152,16 +152,29 @@ __device__ __forceinline__ void raster_piece_warp(const CamTri& mine, uint32_t m
   const int lx = lane & 7, ly = lane >> 3;
   EdgeBlock eb;
   edge_block_setup(rt, rt.imin, rt.jmin, eb);
-  for (int j0 = rt.jmin; j0 <= rt.jmax; j0 += 4)
-    for (int i0 = rt.imin; i0 <= rt.imax; i0 += 8) {
+  // steps aligned to the 8 x 4 grid: a step lies inside one 32 x 32 screen tile, so "is it this rank's tile" is one test per step
+  for (int j0 = rt.jmin & ~3; j0 <= rt.jmax; j0 += 4)
+    for (int i0 = rt.imin & ~7; i0 <= rt.imax; i0 += 8) {
+      if (!tile_owned(i0, j0, W, tile_rank, tile_nranks)) continue;   // multi-GPU: another rank shades (and rasterises) this tile
       const int i = i0 + lx, j = j0 + ly;
-      if (i > rt.imax || j > rt.jmax || !tile_owned(i, j, W, tile_rank, tile_nranks)) continue;
+      if (i < rt.imin || i > rt.imax || j < rt.jmin || j > rt.jmax) continue;
       float b[3];
       if (edge_block_sample(eb, i - rt.imin, j - rt.jmin, b)) {
         const float zw = interp3(b, z0, z1, z2);
         if (zw >= 0.0f && zw <= 1.0f) atomicMin(&vis[(size_t)j * W + i], ((unsigned long long)__float_as_uint(zw) << 32) | (unsigned long long)t);
       }
     }
+}
+
+// does the pixel box [i0,i1] x [j0,j1] touch a 32 x 32 screen tile of this rank?  (boxes of up to 3 x 3 tiles are tested exactly, larger ones kept)
+__device__ __forceinline__ bool box_touches_owned_tile(int i0, int i1, int j0, int j1, int W, int tile_rank, int tile_nranks) {
+  if (tile_nranks <= 1) return true;
+  const int tx0 = i0 >> 5, tx1 = i1 >> 5, ty0 = j0 >> 5, ty1 = j1 >> 5;
+  if (tx1 - tx0 > 2 || ty1 - ty0 > 2) return true;
+  for (int ty = ty0; ty <= ty1; ty++)
+    for (int tx = tx0; tx <= tx1; tx++)
+      if (tile_owned(tx << 5, ty << 5, W, tile_rank, tile_nranks)) return true;
+  return false;
 }
 
 // big_slot[t]: 0 = the triangle has no records (culled, or rasterised in line: the resolve kernel re-runs the vertex stage);
@@ -180,6 +193,13 @@ cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
   if (t < n_tris) {
     const DrawRec& d = draws[find_draw(t, draws, n_draws)];
     n = cam_triangle_pieces(verts, indices, d, t, pv.m, W, H, pc);
+    // multi-GPU: a piece whose bounding box touches none of this rank's screen tiles is somebody else's work (a sub-tile triangle of a
+    // 4 M-triangle scene touches one or two tiles: seven eighths of them end here on each of eight ranks)
+    if (n == 2 && !box_touches_owned_tile(pc[1].rt.imin, pc[1].rt.imax, pc[1].rt.jmin, pc[1].rt.jmax, W, tile_rank, tile_nranks)) n = 1;
+    if (n >= 1 && !box_touches_owned_tile(pc[0].rt.imin, pc[0].rt.imax, pc[0].rt.jmin, pc[0].rt.jmax, W, tile_rank, tile_nranks)) {
+      if (n == 2) pc[0] = pc[1];
+      n--;
+    }
     bool big[2] = {false, false};
     int n_big = 0;
     for (int q = 0; q < n; q++) {

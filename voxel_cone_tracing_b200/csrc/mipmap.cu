@@ -1171,6 +1171,7 @@ int launch_mipmap(vct_device* dev, vct_grid* g) {
     g->mip_build++;
     fa.sb_epoch = g->sb_epoch; fa.build = g->mip_build; fa.log_nsb = log_nsb;
     fa.touched = (g->flags_valid && !g->external) ? g->tile_touched : nullptr;
+    if (g->peer_touched) fa.touched = g->peer_touched;   // multi-GPU frame: flags kept by the ranks that stored the voxels (peer.cu)
     if (dev->debug_mip_dense) {   // measurement switch (vct_debug_set): the dense build, every tile read and written
       fa.touched = nullptr;
       fa.dense = 1;

@@ -20,6 +20,7 @@ namespace vct {
 struct PeerHandlePack {   // the payload of vct_peer_handle_t
   cudaIpcMemHandle_t base[2], frame, flags;
   uint32_t R, W, H, magic;
+  uint32_t n_tiles;         // > 0: the flag block is followed by the mip tile flags of the two level-0 buffers (n_tiles bytes each)
 };
 static_assert(sizeof(PeerHandlePack) <= sizeof(vct_peer_handle_t), "vct_peer_handle_t too small");
 constexpr uint32_t kPeerMagic = 0x56435450u;   // "VCTP"
@@ -38,6 +39,56 @@ __global__ void peer_wait_kernel(const uint32_t* flags, int kind, int nranks, ui
     }
     __nanosleep(100);
   }
+}
+
+// Zero, on EVERY rank, the voxels this rank stored into this frame's level-0 buffer the last time it was in use (two frames ago), and
+// un-mark their mip tiles: the sparse counterpart of every rank clearing 4 R^3 bytes.  A voxel belongs to the slab of exactly one rank,
+// a tile (8 slices) to one slab, so no two ranks ever write the same word or flag.
+// Counts live in a ring of four slots indexed by the frame number: frame e appends under slot e & 3, reads (here) the count of frame e - 2 and
+// zeroes the slot of frame e + 1 -- no separate reset launch, and nobody reads a slot while it is being zeroed.
+__global__ void __launch_bounds__(256)
+peer_unpush_kernel(const PeerView pv, int logR, const uint32_t* old_count, uint32_t* next_count) {
+  const uint32_t n = min(*old_count, pv.pushed_capacity);
+  if (blockIdx.x == 0 && threadIdx.x == 0) *next_count = 0u;
+  const uint32_t m = (1u << logR) - 1u;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t voxel = pv.pushed[i];
+    const uint32_t x = voxel & m, y = (voxel >> logR) & m, z = voxel >> (2 * logR);
+    const uint32_t tile = ((((z >> 3) << (logR - 3)) + (y >> 3)) << (logR - 5)) + (x >> 5);   // tile_of_voxel (voxelize.cu)
+    for (int p = 0; p < pv.nranks; p++) {
+      pv.base[p][voxel] = 0u;
+      pv.touched[p][tile] = 0;
+    }
+  }
+  __threadfence_system();   // performed on the peers before this rank's next flag goes out (the resolve kernel that follows publishes it)
+}
+int launch_peer_unpush(vct_device* dev, const PeerView& pv, int logR) {
+  const uint32_t e = pv.epoch;
+  peer_unpush_kernel<<<dev->prop.multiProcessorCount * 2, 256, 0, dev->stream>>>(pv, logR, dev->pushed_n + ((e + 2u) & 3u), dev->pushed_n + ((e + 1u) & 3u));
+  VCT_CUDA(cudaGetLastError());
+  return VCT_OK;
+}
+
+// the lists hold at most one entry per fragment slot; they follow the arena when it grows (content kept: an un-push may be pending)
+int ensure_pushed_lists(vct_device* dev) {
+  if (dev->pushed_capacity >= dev->frag_capacity && dev->pushed_n) return VCT_OK;
+  const size_t cap = dev->frag_capacity;
+  if (!dev->pushed_n) {
+    VCT_CUDA(cudaMalloc(&dev->pushed_n, 4 * sizeof(uint32_t)));
+    VCT_CUDA(cudaMemsetAsync(dev->pushed_n, 0, 4 * sizeof(uint32_t), dev->stream));
+  }
+  for (int b = 0; b < 2; b++) {
+    uint32_t* nl = nullptr;
+    VCT_CUDA(cudaMalloc(&nl, cap * sizeof(uint32_t)));
+    if (dev->pushed_list[b]) {
+      VCT_CUDA(cudaMemcpyAsync(nl, dev->pushed_list[b], dev->pushed_capacity * sizeof(uint32_t), cudaMemcpyDeviceToDevice, dev->stream));
+      VCT_CUDA(cudaStreamSynchronize(dev->stream));
+      cudaFree(dev->pushed_list[b]);
+    }
+    dev->pushed_list[b] = nl;
+  }
+  dev->pushed_capacity = cap;
+  return VCT_OK;
 }
 
 int launch_peer_wait(vct_device* dev, int kind, uint32_t epoch) {
@@ -65,8 +116,14 @@ int vct_peer_export(vct_device_t* dev, vct_grid_t* g, vct_target_t* t, vct_peer_
   g->untrack();
   VCT_CUDA(cudaMemsetAsync(g->base_buf[0], 0, n0, dev->stream));
   VCT_CUDA(cudaMemsetAsync(g->base_buf[1], 0, n0, dev->stream));
-  if (!dev->peer_flags) VCT_CUDA(cudaMalloc(&dev->peer_flags, kFlagWords * 4));
-  VCT_CUDA(cudaMemsetAsync(dev->peer_flags, 0, kFlagWords * 4, dev->stream));
+  // the flag block, followed (grids the streaming mip kernel handles) by the mip tile flags of the two level-0 buffers: the peers mark them
+  const size_t n_tiles = g->tile_touched ? (size_t)g->R * g->R * g->R / 2048 : 0;
+  const size_t flag_bytes = kFlagWords * 4 + 2 * n_tiles;
+  if (dev->peer_flags && dev->peer_flag_bytes != flag_bytes) { cudaFree(dev->peer_flags); dev->peer_flags = nullptr; }
+  if (!dev->peer_flags) VCT_CUDA(cudaMalloc(&dev->peer_flags, flag_bytes));
+  dev->peer_flag_bytes = flag_bytes;
+  VCT_CUDA(cudaMemsetAsync(dev->peer_flags, 0, flag_bytes, dev->stream));
+  if (dev->pushed_n) VCT_CUDA(cudaMemsetAsync(dev->pushed_n, 0, 4 * sizeof(uint32_t), dev->stream));   // both buffers are zero again: nothing to un-push
   VCT_CUDA(cudaStreamSynchronize(dev->stream));
   PeerHandlePack h;
   memset(&h, 0, sizeof h);
@@ -75,6 +132,7 @@ int vct_peer_export(vct_device_t* dev, vct_grid_t* g, vct_target_t* t, vct_peer_
   VCT_CUDA(cudaIpcGetMemHandle(&h.frame, t->frame));
   VCT_CUDA(cudaIpcGetMemHandle(&h.flags, dev->peer_flags));
   h.R = (uint32_t)g->R; h.W = (uint32_t)t->W; h.H = (uint32_t)t->H; h.magic = kPeerMagic;
+  h.n_tiles = (uint32_t)n_tiles;
   dev->peer_export_fresh = true;   // the flag block is zero: epochs restart at 1 with the next connect
   memset(out, 0, sizeof *out);
   memcpy(out, &h, sizeof h);
@@ -87,7 +145,8 @@ int vct_peer_disconnect(vct_device_t* dev) {
   cudaStreamSynchronize(dev->stream);
   for (int i = 0; i < dev->n_peer_mapped; i++) cudaIpcCloseMemHandle(dev->peer_mapped[i]);
   dev->n_peer_mapped = 0;
-  if (dev->peer_grid) dev->peer_grid->base = dev->peer_grid->base_buf[0];
+  if (dev->peer_grid) { dev->peer_grid->base = dev->peer_grid->base_buf[0]; dev->peer_grid->peer_touched = nullptr; }
+  memset(dev->peer_touched_all, 0, sizeof dev->peer_touched_all);
   memset(&dev->peers, 0, sizeof dev->peers);
   dev->peer_grid = nullptr; dev->peer_target = nullptr;
   dev->peer_epoch = 0;
@@ -117,6 +176,7 @@ int vct_peer_connect(vct_device_t* dev, vct_grid_t* g, vct_target_t* t, int rank
     if (p == rank) {
       dev->peer_base_all[0][p] = g->base_buf[0]; dev->peer_base_all[1][p] = g->base_buf[1];
       pv.frame[p] = t->frame; pv.flags[p] = dev->peer_flags;
+      for (int b = 0; b < 2; b++) dev->peer_touched_all[b][p] = h.n_tiles ? (uint8_t*)(dev->peer_flags + kFlagWords) + (size_t)b * h.n_tiles : nullptr;
       continue;
     }
     void* ptr[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -132,6 +192,7 @@ int vct_peer_connect(vct_device_t* dev, vct_grid_t* g, vct_target_t* t, int rank
     }
     dev->peer_base_all[0][p] = (uint32_t*)ptr[0]; dev->peer_base_all[1][p] = (uint32_t*)ptr[1];
     pv.frame[p] = (uint32_t*)ptr[2]; pv.flags[p] = (uint32_t*)ptr[3];
+    for (int b = 0; b < 2; b++) dev->peer_touched_all[b][p] = h.n_tiles ? (uint8_t*)((uint32_t*)ptr[3] + kFlagWords) + (size_t)b * h.n_tiles : nullptr;
   }
   dev->peers = pv;
   dev->peer_grid = g; dev->peer_target = t;

@@ -125,6 +125,14 @@ struct PeerView {
   uint32_t* flags[VCT_MAX_RANKS];  // flag block of every rank: [PEER_FLAG_KINDS][VCT_MAX_RANKS] epochs, written by the source rank
   uint32_t* done_counter;        // local: blocks of the signalling kernel that have finished
   int frame_root;                // rank that receives the finished tiles (-1: every rank)
+  // sparse bookkeeping across ranks (nullptr: not in use).  touched[p] = the mip tile flags of THIS frame's level-0 buffer on rank p: the rank
+  // that stores a voxel into a peer's grid also marks the peer's tile, so every rank's mip build stays sparse; pushed / pushed_n = the
+  // voxels this rank stored this frame -- two frames later, when the same buffer comes round again, it zeroes exactly those on every rank
+  // (and un-marks their tiles) instead of every rank clearing 4 R^3 bytes.
+  uint8_t* touched[VCT_MAX_RANKS];
+  uint32_t* pushed;
+  uint32_t* pushed_n;
+  uint32_t pushed_capacity;
 };
 
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
@@ -203,10 +211,15 @@ struct vct_device {
   bool mip_attr_set = false;
   // multi-GPU connection (vct_peer_connect)
   vct::PeerView peers{};               // peers.nranks <= 1 when not connected
+  size_t peer_flag_bytes = 0;
   uint32_t* peer_flags = nullptr;      // local flag block [PEER_FLAG_KINDS][VCT_MAX_RANKS] + done counters + error word
   void* peer_mapped[3 * VCT_MAX_RANKS + VCT_MAX_RANKS] = {};  // pointers opened with cudaIpcOpenMemHandle (to close)
   int n_peer_mapped = 0;
   uint32_t* peer_base_all[2][VCT_MAX_RANKS] = {};   // both level-0 buffers of every rank
+  uint8_t* peer_touched_all[2][VCT_MAX_RANKS] = {}; // the mip tile flags of both level-0 buffers on every rank (nullptr: dense clear + dense mip)
+  uint32_t* pushed_list[2] = {};                    // voxels this rank stored into buffer 0 / 1 the last time it was the frame's buffer
+  uint32_t* pushed_n = nullptr;                     // [4]: ring of counts indexed by frame number & 3 (peer.cu)
+  size_t pushed_capacity = 0;
   vct_grid* peer_grid = nullptr;
   vct_target_t_* peer_target = nullptr;
   uint32_t peer_epoch = 0;             // frames rendered since vct_peer_connect
@@ -271,6 +284,7 @@ struct vct_grid {
   // vct_grid_clear zeroes those instead of the whole level.  Anything that writes level 0 behind the library's back
   // (vct_grid_upload_base, the raw pointer) drops back to the dense paths.
   uint8_t* tile_touched = nullptr;
+  const uint8_t* peer_touched = nullptr;   // multi-GPU frame: the tile flags of this frame's level-0 buffer, kept by the pushing ranks (peer.cu)
   bool flags_valid = false, sparse_clear_ok = false, base_zero = false, external = false;
   int dirty_z0 = 0, dirty_z1 = 0;       // z range voxelized (or uploaded) since the last clear: vct_voxelize refuses a slab that overlaps it
   void untrack() { flags_valid = sparse_clear_ok = base_zero = false; dirty_z0 = 0; dirty_z1 = R; }
@@ -338,6 +352,8 @@ int launch_copy_u32(cudaStream_t s, uint32_t* dst, const uint32_t* src, size_t n
 int ensure_tri_scratch(vct_device* dev, int which /* 0 voxelizer, 1 G-buffer */, size_t n_tris, size_t rec_bytes_total);
 int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1, const PeerView* push = nullptr);
 int launch_peer_wait(vct_device* dev, int kind, uint32_t epoch);
+int launch_peer_unpush(vct_device* dev, const PeerView& pv, int logR);   // zero the voxels this rank pushed into this frame's buffer two frames ago
+int ensure_pushed_lists(vct_device* dev);
 int check_status(vct_device* dev);   // VCT_ERR_OVERFLOW / VCT_ERR_CUDA if a kernel reported an arena overflow / a peer timeout since the last check
 int launch_mipmap(vct_device* dev, vct_grid* g);
 bool mip_fused_applies(int R, int levels);   // the fused mip kernel (32x8x8 tiles, 32^3 blocks) handles this grid

@@ -349,8 +349,20 @@ vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frag
   }
   const uint32_t n_frags = min(counters[CNT_FRAGS], frag_capacity);
   uint32_t n_mine = 0, max_list = 0;
-  for (uint32_t f = blockIdx.x * blockDim.x + threadIdx.x; f < n_frags; f += gridDim.x * blockDim.x) {
-    if (!fresh[f]) continue;
+  const int lane = threadIdx.x & 31;
+  // warp-uniform trip count: the list of pushed voxels (multi-GPU) is appended with one atomic per warp and round
+  for (uint32_t f0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; f0 < n_frags; f0 += gridDim.x * blockDim.x) {
+    const uint32_t f = f0 + lane;
+    const bool mine = f < n_frags && fresh[f];
+    uint32_t list_pos = 0;
+    if (pv.pushed) {
+      const uint32_t mm = __ballot_sync(0xffffffffu, mine);
+      if (mm) {
+        if (lane == 0) list_pos = atomicAdd(pv.pushed_n, (uint32_t)__popc(mm));
+        list_pos = __shfl_sync(0xffffffffu, list_pos, 0) + (uint32_t)__popc(mm & ((1u << lane) - 1u));
+      }
+    }
+    if (!mine) continue;
     n_mine++;
     const uint32_t voxel = frags[f].voxel;
     const uint32_t head = base[voxel];
@@ -390,8 +402,12 @@ vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frag
     if (tile_touched) tile_touched[tile_of_voxel(voxel, logR)] = 1;   // sparse mip build: this 32x8x8 tile has content
     // multi-GPU: the slab owner writes the resolved voxel straight into every peer's grid over NVLink (sparse
     // exchange: only occupied voxels travel; replaces the dense all-gather of the base level)
-    for (int p = 0; p < pv.nranks; p++)
+    const uint32_t tile = tile_of_voxel(voxel, logR);
+    for (int p = 0; p < pv.nranks; p++) {
       if (p != pv.rank) pv.base[p][voxel] = stored;
+      if (pv.touched[p]) pv.touched[p][tile] = 1;   // keeps every rank's mip build sparse (own rank included)
+    }
+    if (pv.pushed && list_pos < pv.pushed_capacity) pv.pushed[list_pos] = voxel;
     max_list = max(max_list, n);
   }
   // statistics (vct_voxelize_stats): occupied voxels and the longest list, one atomic each per warp
