@@ -762,7 +762,11 @@ static int render_frame_sharded(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* 
   for (int r = 0; r < pv.nranks; r++) { pv.base[r] = dev->peer_base_all[b][r]; pv.touched[r] = dev->peer_touched_all[b][r]; }
   g->base = g->base_buf[b];
   // every rank exported tile flags (same grid size everywhere: all or none); a mip tile is 8 slices deep and must belong to ONE slab
-  const bool sparse = pv.touched[pv.rank] != nullptr && g->R % (8 * pv.nranks) == 0;
+  // Decided once per connection, from the scene of its first frame (the same on every rank): the un-push stores nranks words + flags per
+  // occupied voxel over NVLink, which beats a 4 R^3-byte local clear + a dense mip build only while the scene is sparse.  Measured at
+  // N = 8: 256^3 / 1 k triangles 340 -> 326 us per frame, but 1024^3 / 4 M triangles (23 M occupied voxels) clear 0.60 -> 1.36 ms.
+  if (dev->peer_sparse_mode < 0) dev->peer_sparse_mode = sc->n_tris <= 65536u ? 1 : 0;
+  const bool sparse = dev->peer_sparse_mode == 1 && pv.touched[pv.rank] != nullptr && g->R % (8 * pv.nranks) == 0;
   if (!sparse) for (int r = 0; r < pv.nranks; r++) pv.touched[r] = nullptr;
   if (sparse) {
     if (dev->frag_capacity == 0)

@@ -34,14 +34,12 @@ struct ClipVert { float cx, cy, cz, cw; float world[3], nn[3]; };
 // a + t * (b - a), fp32, no FMA (gbuffer.o is built with -fmad=false): the oracle's clip interpolation
 __device__ __forceinline__ float clip_lerp(float a, float b, float t) { return a + t * (b - a); }
 
-// Vertex stage + near-plane clip + projection of triangle t: up to two rasterisable pieces (fan (p0,p1,p2), (p0,p2,p3) of the
-// clipped polygon).  Used by the set-up kernel AND by the resolve kernel (same code, same inputs -> the same bits).
-__device__ __forceinline__ int cam_triangle_pieces(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec& d, uint32_t t,
-                                                   const float* __restrict__ p, int W, int H, CamTri (&out)[2]) {
+// Vertex stage of triangle t (voxel_cone_tracing.vert:22-28): clip-space position, world position, normalised normal per vertex, and the
+// signed distance to the near plane.  Static indexing only: everything stays in registers.
+__device__ __forceinline__ int cam_vertex_stage(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec& d, uint32_t t,
+                                                const float* __restrict__ p, ClipVert (&in)[3], float (&dn)[3]) {
   const uint32_t first = d.first_index + 3u * (t - d.tri_base);
   const float* m = d.model;
-  ClipVert in[3];
-  float dn[3];
   int n_out = 0;
 #pragma unroll
   for (int k = 0; k < 3; k++) {
@@ -65,53 +63,61 @@ __device__ __forceinline__ int cam_triangle_pieces(const vct_vertex_t* __restric
     dn[k] = in[k].cz + in[k].cw;          // >= 0: inside the near plane (-w <= z)
     if (!(dn[k] >= 0.0f)) n_out++;        // also NaN
   }
-  if (n_out == 3) return 0;
-  // R2c: Sutherland-Hodgman against the near plane; a new vertex is always computed from the INSIDE vertex of its edge
+  return n_out;
+}
+
+// perspective division + viewport + snapping of one (clipped or whole) triangle; false = it produces no fragment
+__device__ __forceinline__ bool cam_make_piece(const ClipVert& c0, const ClipVert& c1, const ClipVert& c2, int W, int H, uint32_t material, CamTri& v) {
+  float xw[3], yw[3];
+  bool ok = true;
+  const ClipVert* cs[3] = {&c0, &c1, &c2};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    const ClipVert& c = *cs[k];
+#pragma unroll
+    for (int a = 0; a < 3; a++) { v.world[k][a] = c.world[a]; v.nn[k][a] = c.nn[a]; }
+    if (!(c.cw > 0.0f)) ok = false;   // cannot happen behind a near plane with near > 0; guards general matrices
+    const float iw = 1.0f / c.cw;
+    v.iw[k] = iw;
+    xw[k] = (c.cx * iw + 1.0f) * ((float)W * 0.5f);
+    yw[k] = (c.cy * iw + 1.0f) * ((float)H * 0.5f);
+    v.zw[k] = (c.cz * iw + 1.0f) * 0.5f;
+  }
+  v.material = material;
+  v.pad = 0;
+  return ok && raster_setup(xw, yw, W, H, v.rt);
+}
+
+// R2c: Sutherland-Hodgman against the near plane for a triangle that crosses it (1 or 2 vertices outside); a new vertex is always computed
+// from the INSIDE vertex of its edge.  Up to two pieces: the fan (p0,p1,p2), (p0,p2,p3) of the clipped polygon.  Rare (the triangles around
+// the camera) and deliberately NOT inlined, and it runs the vertex stage again instead of taking its results: dynamically indexed arrays and
+// anything whose address crosses a call live in local memory, and in round 1 every one of 4 M triangle set-ups paid for that 608-byte frame.
+__device__ __noinline__ int cam_clip_pieces(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ dp, uint32_t t,
+                                            const float* __restrict__ p, int W, int H, CamTri* out) {
+  const DrawRec& d = *dp;
+  ClipVert in[3];
+  float dn[3];
+  cam_vertex_stage(verts, indices, d, t, p, in, dn);
   ClipVert poly[4];
   int np = 0;
-  if (n_out == 0) {
-    poly[0] = in[0]; poly[1] = in[1]; poly[2] = in[2]; np = 3;
-  } else {
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const int k1 = (k + 1) % 3;
-      const bool in_a = dn[k] >= 0.0f, in_b = dn[k1] >= 0.0f;
-      if (in_a) poly[np++] = in[k];
-      if (in_a != in_b) {
-        const ClipVert& vi = in_a ? in[k] : in[k1];
-        const ClipVert& vo = in_a ? in[k1] : in[k];
-        const float di = in_a ? dn[k] : dn[k1], dout = in_a ? dn[k1] : dn[k];
-        const float tt = di / (di - dout);
-        ClipVert c;
-        c.cx = clip_lerp(vi.cx, vo.cx, tt); c.cy = clip_lerp(vi.cy, vo.cy, tt); c.cz = clip_lerp(vi.cz, vo.cz, tt); c.cw = clip_lerp(vi.cw, vo.cw, tt);
-#pragma unroll
-        for (int a = 0; a < 3; a++) { c.world[a] = clip_lerp(vi.world[a], vo.world[a], tt); c.nn[a] = clip_lerp(vi.nn[a], vo.nn[a], tt); }
-        poly[np++] = c;
-      }
+  for (int k = 0; k < 3; k++) {
+    const int k1 = (k + 1) % 3;
+    const bool in_a = dn[k] >= 0.0f, in_b = dn[k1] >= 0.0f;
+    if (in_a) poly[np++] = in[k];
+    if (in_a != in_b) {
+      const ClipVert& vi = in_a ? in[k] : in[k1];
+      const ClipVert& vo = in_a ? in[k1] : in[k];
+      const float di = in_a ? dn[k] : dn[k1], dout = in_a ? dn[k1] : dn[k];
+      const float tt = di / (di - dout);
+      ClipVert c;
+      c.cx = clip_lerp(vi.cx, vo.cx, tt); c.cy = clip_lerp(vi.cy, vo.cy, tt); c.cz = clip_lerp(vi.cz, vo.cz, tt); c.cw = clip_lerp(vi.cw, vo.cw, tt);
+      for (int a = 0; a < 3; a++) { c.world[a] = clip_lerp(vi.world[a], vo.world[a], tt); c.nn[a] = clip_lerp(vi.nn[a], vo.nn[a], tt); }
+      poly[np++] = c;
     }
   }
   int n_pieces = 0;
-  for (int piece = 0; piece + 3 <= np; piece++) {
-    CamTri& v = out[n_pieces];
-    float xw[3], yw[3];
-    bool ok = true;
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      const ClipVert& c = poly[k == 0 ? 0 : piece + k];
-#pragma unroll
-      for (int a = 0; a < 3; a++) { v.world[k][a] = c.world[a]; v.nn[k][a] = c.nn[a]; }
-      if (!(c.cw > 0.0f)) ok = false;   // cannot happen behind a near plane with near > 0; guards general matrices
-      const float iw = 1.0f / c.cw;
-      v.iw[k] = iw;
-      xw[k] = (c.cx * iw + 1.0f) * ((float)W * 0.5f);
-      yw[k] = (c.cy * iw + 1.0f) * ((float)H * 0.5f);
-      v.zw[k] = (c.cz * iw + 1.0f) * 0.5f;
-    }
-    if (!ok || !raster_setup(xw, yw, W, H, v.rt)) continue;
-    v.material = d.material;
-    v.pad = 0;
-    n_pieces++;
-  }
+  for (int piece = 0; piece + 3 <= np; piece++)
+    if (cam_make_piece(poly[0], poly[piece + 1], poly[piece + 2], W, H, d.material, out[n_pieces])) n_pieces++;
   return n_pieces;
 }
 
@@ -177,6 +183,41 @@ __device__ __forceinline__ bool box_touches_owned_tile(int i0, int i1, int j0, i
   return false;
 }
 
+// A triangle that crosses the near plane, start to finish (called by its own lane only): clip, cull, then every piece either gets a record
+// + work items (returned count) or is depth-tested in line.  Sets big_slot[t].
+__device__ __noinline__ uint32_t cam_setup_clipped(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ d, uint32_t t,
+                                                   const float* __restrict__ pvm, int W, int H, CamTri* __restrict__ recs, uint32_t rec_capacity,
+                                                   uint32_t* __restrict__ rec_count, uint32_t* __restrict__ big_slot, unsigned long long* __restrict__ vis,
+                                                   int tile_rank, int tile_nranks, int record_limit) {
+  CamTri pc[2];
+  const int n = cam_clip_pieces(verts, indices, d, t, pvm, W, H, pc);
+  bool big[2] = {false, false};
+  int n_big = 0;
+  for (int q = 0; q < n; q++) {
+    const RasterTri& rt = pc[q].rt;
+    if (!box_touches_owned_tile(rt.imin, rt.imax, rt.jmin, rt.jmax, W, tile_rank, tile_nranks)) { pc[q].rt.sign = 0; continue; }
+    big[q] = (rt.imax - rt.imin + 1) * (rt.jmax - rt.jmin + 1) > record_limit;
+    n_big += big[q] ? 1 : 0;
+  }
+  uint32_t slot = 0, count = 0;
+  if (n_big) {
+    slot = atomicAdd(rec_count, (uint32_t)n_big);
+    if (slot + (uint32_t)n_big > rec_capacity) { big[0] = big[1] = false; n_big = 0; }   // record array full: in line (slow, still exact)
+  }
+  big_slot[t] = n_big ? ((slot + 1u) | ((uint32_t)(n_big - 1) << 31)) : 0u;
+  for (int q = 0; q < n; q++) {
+    if (pc[q].rt.sign == 0) continue;
+    if (big[q]) {
+      pc[q].pad = raster_item_count(pc[q].rt);
+      count += pc[q].pad;
+      recs[slot++] = pc[q];
+    } else {
+      raster_piece_inline(pc[q], t, W, vis, tile_rank, tile_nranks);
+    }
+  }
+  return count;
+}
+
 // big_slot[t]: 0 = the triangle has no records (culled, or rasterised in line: the resolve kernel re-runs the vertex stage);
 // else 1 + index of its first record in `recs` | (number of records - 1) << 31.  recs[slot].pad = work items of that record.
 __global__ void __launch_bounds__(kSetupThreads)
@@ -187,51 +228,49 @@ cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
   const uint32_t t = blockIdx.x * kSetupThreads + threadIdx.x;
   const int lane = threadIdx.x & 31;
   uint32_t count = 0;
-  CamTri pc[2];
-  int n = 0;
-  bool mid[2] = {false, false};
+  CamTri pc;   // the one piece of a triangle the near plane does not cut: registers only
+  pc.rt.sign = 0; pc.rt.imin = 0; pc.rt.imax = -1; pc.rt.jmin = 0; pc.rt.jmax = -1; pc.rt.area = 0; pc.rt.mshift = kMacroShiftMin;
+#pragma unroll
+  for (int k = 0; k < 3; k++) { pc.rt.X[k] = pc.rt.Y[k] = 0; pc.zw[k] = 0.0f; }
+  bool mid = false;
   if (t < n_tris) {
-    const DrawRec& d = draws[find_draw(t, draws, n_draws)];
-    n = cam_triangle_pieces(verts, indices, d, t, pv.m, W, H, pc);
-    // multi-GPU: a piece whose bounding box touches none of this rank's screen tiles is somebody else's work (a sub-tile triangle of a
-    // 4 M-triangle scene touches one or two tiles: seven eighths of them end here on each of eight ranks)
-    if (n == 2 && !box_touches_owned_tile(pc[1].rt.imin, pc[1].rt.imax, pc[1].rt.jmin, pc[1].rt.jmax, W, tile_rank, tile_nranks)) n = 1;
-    if (n >= 1 && !box_touches_owned_tile(pc[0].rt.imin, pc[0].rt.imax, pc[0].rt.jmin, pc[0].rt.jmax, W, tile_rank, tile_nranks)) {
-      if (n == 2) pc[0] = pc[1];
-      n--;
-    }
-    bool big[2] = {false, false};
-    int n_big = 0;
-    for (int q = 0; q < n; q++) {
-      const int bw = pc[q].rt.imax - pc[q].rt.imin + 1, bh = pc[q].rt.jmax - pc[q].rt.jmin + 1;
-      big[q] = bw * bh > mid_limit;
-      mid[q] = !big[q] && bw * bh > small_limit;
-      n_big += big[q] ? 1 : 0;
-    }
-    uint32_t slot = 0;
-    if (n_big) {
-      slot = atomicAdd(rec_count, (uint32_t)n_big);
-      if (slot + (uint32_t)n_big > rec_capacity) {   // record array full: the warp takes these pieces too (slow for a wall-sized piece, still exact)
-        for (int q = 0; q < n; q++) if (big[q]) { big[q] = false; mid[q] = true; }
-        n_big = 0;
+    const DrawRec* dp = draws + find_draw(t, draws, n_draws);
+    ClipVert in[3];
+    float dn[3];
+    const int n_out = cam_vertex_stage(verts, indices, *dp, t, pv.m, in, dn);
+    if (n_out == 0) {
+      // multi-GPU: a piece whose bounding box touches none of this rank's screen tiles is somebody else's work (a sub-tile triangle of a
+      // 4 M-triangle scene touches one or two tiles: seven eighths of them end here on each of eight ranks)
+      const bool have = cam_make_piece(in[0], in[1], in[2], W, H, dp->material, pc) &&
+                        box_touches_owned_tile(pc.rt.imin, pc.rt.imax, pc.rt.jmin, pc.rt.jmax, W, tile_rank, tile_nranks);
+      uint32_t bs = 0u;
+      if (have) {
+        const int area = (pc.rt.imax - pc.rt.imin + 1) * (pc.rt.jmax - pc.rt.jmin + 1);
+        const bool big = area > mid_limit;
+        mid = !big && area > small_limit;
+        if (big) {
+          const uint32_t slot = atomicAdd(rec_count, 1u);
+          if (slot < rec_capacity) {
+            pc.pad = raster_item_count(pc.rt);
+            count = pc.pad;
+            recs[slot] = pc;
+            bs = slot + 1u;
+          } else {   // record array full: the warp takes the piece (slow for a wall-sized one, still exact)
+            mid = true;
+          }
+        } else if (!mid) {
+          raster_piece_inline(pc, t, W, vis, tile_rank, tile_nranks);
+        }
       }
-    }
-    big_slot[t] = n_big ? ((slot + 1u) | ((uint32_t)(n_big - 1) << 31)) : 0u;
-    for (int q = 0; q < n; q++) {
-      if (big[q]) {
-        pc[q].pad = raster_item_count(pc[q].rt);
-        count += pc[q].pad;
-        recs[slot++] = pc[q];
-      } else if (!mid[q]) {
-        raster_piece_inline(pc[q], t, W, vis, tile_rank, tile_nranks);
-      }
+      big_slot[t] = bs;
+    } else if (n_out < 3) {
+      count = cam_setup_clipped(verts, indices, dp, t, pv.m, W, H, recs, rec_capacity, rec_count, big_slot, vis, tile_rank, tile_nranks, mid_limit);
+    } else {
+      big_slot[t] = 0u;
     }
   }
   // the mid-sized pieces of the warp's 32 triangles, one after the other, all lanes on each
-#pragma unroll
-  for (int q = 0; q < 2; q++) {
-    for (uint32_t m = __ballot_sync(0xffffffffu, mid[q]); m; m &= m - 1u) raster_piece_warp(pc[q], t, __ffs((int)m) - 1, lane, W, vis, tile_rank, tile_nranks);
-  }
+  for (uint32_t m = __ballot_sync(0xffffffffu, mid); m; m &= m - 1u) raster_piece_warp(pc, t, __ffs((int)m) - 1, lane, W, vis, tile_rank, tile_nranks);
   block_scan_items(count, t, n_tris, item_local, item_block, scan_ticket, scan_total);
 }
 
@@ -278,6 +317,21 @@ cam_raster_kernel(const CamTri* __restrict__ recs, const uint32_t* __restrict__ 
   }
 }
 
+// the piece of a near-plane-clipped triangle that covers pixel (i, j), for the resolve kernel (rare, not inlined: see cam_clip_pieces)
+struct ResolvedPiece { float b[3], iw[3], world[3][3], nn[3][3]; };
+__device__ __noinline__ void cam_resolve_clipped(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ d, uint32_t t,
+                                                 const float* __restrict__ pvm, int W, int H, int i, int j, ResolvedPiece* out) {
+  CamTri pc[2];
+  const int np = cam_clip_pieces(verts, indices, d, t, pvm, W, H, pc);
+  float b[3] = {0.f, 0.f, 0.f};
+  const int q = (np > 1 && !raster_sample(pc[0].rt, i, j, b)) ? 1 : 0;
+  raster_sample(pc[q].rt, i, j, b);
+  for (int k = 0; k < 3; k++) {
+    out->b[k] = b[k]; out->iw[k] = pc[q].iw[k];
+    for (int c = 0; c < 3; c++) { out->world[k][c] = pc[q].world[k][c]; out->nn[k][c] = pc[q].nn[k][c]; }
+  }
+}
+
 // key of the cleared depth buffer: depth 1.0 (glClear), no triangle.  A fragment at zw == 1.0 has a
 // smaller key only if its triangle id is smaller than 0xFFFFFFFF, so mask it explicitly below.
 constexpr unsigned long long kVisClear = ((unsigned long long)0x3F800000u << 32) | 0xFFFFFFFFull;
@@ -320,18 +374,31 @@ cam_resolve_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __res
       }
     }
     if (!found) {   // no record (sub-tile triangle), or the pixel belongs to a piece that was rasterised in line
-      const DrawRec& d = draws[find_draw(ti, draws, n_draws)];
-      CamTri pc[2];
-      const int np = cam_triangle_pieces(verts, indices, d, ti, pv.m, W, H, pc);
-      const int q = (np > 1 && !raster_sample(pc[0].rt, i, j, b)) ? 1 : 0;
-      raster_sample(pc[q].rt, i, j, b);
+      const DrawRec* dp = draws + find_draw(ti, draws, n_draws);
+      ClipVert in[3];
+      float dn[3];
+      const int n_out = cam_vertex_stage(verts, indices, *dp, ti, pv.m, in, dn);
+      if (n_out == 0) {   // registers only
+        CamTri pc;
+        cam_make_piece(in[0], in[1], in[2], W, H, dp->material, pc);
+        raster_sample(pc.rt, i, j, b);
 #pragma unroll
-      for (int k = 0; k < 3; k++) {
-        iw[k] = q ? pc[1].iw[k] : pc[0].iw[k];
+        for (int k = 0; k < 3; k++) {
+          iw[k] = pc.iw[k];
 #pragma unroll
-        for (int c = 0; c < 3; c++) { world[k][c] = q ? pc[1].world[k][c] : pc[0].world[k][c]; nn[k][c] = q ? pc[1].nn[k][c] : pc[0].nn[k][c]; }
+          for (int c = 0; c < 3; c++) { world[k][c] = pc.world[k][c]; nn[k][c] = pc.nn[k][c]; }
+        }
+      } else {
+        ResolvedPiece rp;
+        cam_resolve_clipped(verts, indices, dp, ti, pv.m, W, H, i, j, &rp);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          b[k] = rp.b[k]; iw[k] = rp.iw[k];
+#pragma unroll
+          for (int c = 0; c < 3; c++) { world[k][c] = rp.world[k][c]; nn[k][c] = rp.nn[k][c]; }
+        }
       }
-      mat = d.material;
+      mat = dp->material;
     }
     const float q3[3] = {b[0] * iw[0], b[1] * iw[1], b[2] * iw[2]};
     const float qs = (q3[0] + q3[1]) + q3[2];

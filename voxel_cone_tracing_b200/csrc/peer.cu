@@ -150,6 +150,7 @@ int vct_peer_disconnect(vct_device_t* dev) {
   memset(&dev->peers, 0, sizeof dev->peers);
   dev->peer_grid = nullptr; dev->peer_target = nullptr;
   dev->peer_epoch = 0;
+  dev->peer_sparse_mode = -1;
   return VCT_OK;
 }
 

@@ -220,6 +220,7 @@ struct vct_device {
   uint32_t* pushed_list[2] = {};                    // voxels this rank stored into buffer 0 / 1 the last time it was the frame's buffer
   uint32_t* pushed_n = nullptr;                     // [4]: ring of counts indexed by frame number & 3 (peer.cu)
   size_t pushed_capacity = 0;
+  int peer_sparse_mode = -1;                        // -1 undecided, 0 dense clear + dense mip under peers, 1 sparse (decided at the first frame of a connection)
   vct_grid* peer_grid = nullptr;
   vct_target_t_* peer_target = nullptr;
   uint32_t peer_epoch = 0;             // frames rendered since vct_peer_connect
