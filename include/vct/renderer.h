@@ -111,6 +111,8 @@ struct Renderer {
   void* frame_device_ptr();                             // device pointer of the RGBA8 frame
   bool read_voxels(int level, int dir, uint32_t* rgba8); // one level of one directional texture (glGetTexImage)
   void set_sampler(int vct_sampler) { m_sampler = vct_sampler; }  // VCT_SAMPLER_FP32 / VCT_SAMPLER_TEX
+  // VCT_ACCUM_ORDERED (the reference's running average, bit-exact, default) / VCT_ACCUM_FIXED_POINT (order-independent integer mean)
+  bool set_voxel_accumulation(int vct_accum_mode) { return vct_voxelize_set_accum_mode(m_device.handle(), vct_accum_mode) == VCT_OK; }
   void set_diffuse_cone_count(int n) { m_diffuse_cones = n; }     // 9 = reference, 5 = BASELINE.json variant
   void set_rank(int rank, int nranks) { m_rank = rank; m_nranks = nranks; }  // multi-GPU: z-slab / screen-tile share of this process
   void set_staged_passes(bool on) { m_staged = on; }   // render() = voxelize(); visualize() as separate stage calls instead of one vct_render_frame

@@ -140,6 +140,16 @@ void* vct_target_frame_device_ptr(vct_target_t* t);
 int vct_voxelize(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, int z0, int z1);
 int vct_voxelize_reserve(vct_device_t* dev, uint64_t max_fragments);
 int vct_voxelize_stats(vct_device_t* dev, vct_voxel_stats_t* out);        /* synchronises */
+/* How the fragments of one voxel are combined (BASELINE.json north_star: "deterministic integer or fixed-point atomic accumulation path").
+ *   VCT_ACCUM_ORDERED      (default) the reference's imageAtomicRGBA8Avg running average (voxelize.frag:95-120: 7-bit colour, 4-bit count that
+ *                          wraps at 16) applied in canonical fragment order (draw, triangle, row, column): bit-exact against the oracle.
+ *   VCT_ACCUM_FIXED_POINT  NON-REFERENCE variant: every fragment adds (uint)(colour * 255 + 0.5) per channel to 64-bit integer accumulators
+ *                          (atomicAdd: order independent, so deterministic without sorting), the voxel stores the rounded mean in all 8 bits.
+ *                          Differs from the ordered result by at most 3/255 per channel on the benchmark scenes (profiles/); no list walk,
+ *                          no sort in the resolve pass. */
+#define VCT_ACCUM_ORDERED 0
+#define VCT_ACCUM_FIXED_POINT 1
+int vct_voxelize_set_accum_mode(vct_device_t* dev, int mode);
 /* Renderer::filter() (renderer.cpp:283-314 + mipmap.comp) */
 int vct_mipmap(vct_device_t* dev, vct_grid_t* g);
 /* vertex + raster + depth part of Renderer::visualize() (renderer.cpp:355-390, voxel_cone_tracing.vert) */

@@ -77,6 +77,7 @@ def lib():
         L.orc_texture_lod.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, C.c_float, f32p]
         L.orc_voxelize.argtypes = [C.POINTER(SceneT), C.c_int, C.c_void_p, C.POINTER(VoxelStats)]
         L.orc_voxelize_slab.argtypes = [C.POINTER(SceneT), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(VoxelStats)]
+        L.orc_voxelize_slab_mode.argtypes = [C.POINTER(SceneT), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(VoxelStats)]
         L.orc_mipmap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.orc_gbuffer.argtypes = [C.POINTER(SceneT), f32p, f32p, C.c_int, C.c_int] + [C.c_void_p] * 5
         L.orc_trace.argtypes = [C.POINTER(SceneT), f32p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_void_p, C.c_int, C.c_int,
@@ -125,11 +126,14 @@ class SceneRef:
                         l.ctypes.data if len(l) else None, len(l), float(scene.cube_size))
 
 
-def voxelize(scene, R: int, z0: int = 0, z1: int | None = None):
+ACCUM_ORDERED, ACCUM_FIXED_POINT = 0, 1
+
+
+def voxelize(scene, R: int, z0: int = 0, z1: int | None = None, accum_mode: int = ACCUM_ORDERED):
     sr = SceneRef(scene)
     base = np.zeros((R, R, R), np.uint32)
     st = VoxelStats()
-    rc = lib().orc_voxelize_slab(C.byref(sr.c), R, z0, R if z1 is None else z1, base.ctypes.data, C.byref(st))
+    rc = lib().orc_voxelize_slab_mode(C.byref(sr.c), R, z0, R if z1 is None else z1, accum_mode, base.ctypes.data, C.byref(st))
     assert rc == 0
     return base, st
 

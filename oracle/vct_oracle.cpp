@@ -538,9 +538,15 @@ void orc_texture_lod(const uint32_t* const* levels, int R, int n_levels, int dir
 }
 
 /* ---------------- voxelize (V1-V5) ---------------- */
-int orc_voxelize_slab(const orc_scene_t* sc, int R, int z0, int z1, uint32_t* base, orc_voxel_stats_t* stats) {
+/* accum_mode 0: the reference's running average (voxelize.frag:95-120) in canonical fragment order.
+ * accum_mode 1: NON-REFERENCE variant (BASELINE.json north_star "deterministic integer or fixed-point atomic accumulation"): every fragment
+ *   contributes q_k = (uint)(val_k * 255 + 0.5) per channel, the voxel stores the rounded integer mean (sum_k + n / 2) / n in all 8 bits of
+ *   byte k (no count nibble, no 16-sample wrap).  Order independent by construction. */
+int orc_voxelize_slab_mode(const orc_scene_t* sc, int R, int z0, int z1, int accum_mode, uint32_t* base, orc_voxel_stats_t* stats) {
   if (!sc || !base || R <= 0) return -1;
   size_t nvox = (size_t)R * R * R;
+  std::vector<uint32_t> fx_sum;   /* accum_mode 1: four sums + the count per voxel */
+  if (accum_mode == 1) fx_sum.assign(nvox * 5, 0u);
   memset(base, 0, nvox * sizeof(uint32_t)); /* clear_tex_3d, renderer.cpp:320-321 */
   orc_voxel_stats_t st;
   memset(&st, 0, sizeof st);
@@ -607,7 +613,12 @@ int orc_voxelize_slab(const orc_scene_t* sc, int R, int z0, int z1, uint32_t* ba
             if (vx < 0 || vy < 0 || vz < 0 || vx >= R || vy >= R || vz >= R) { st.fragments_oob++; continue; }
             if (vz < z0 || vz >= z1) continue;
             size_t idx = ((size_t)vz * R + vy) * R + vx;
-            base[idx] = rgba8_avg_fold(base[idx], val);
+            if (accum_mode == 1) {
+              for (int k = 0; k < 4; k++) fx_sum[idx * 5 + k] += (uint32_t)(val[k] + 0.5f);
+              fx_sum[idx * 5 + 4]++;
+            } else {
+              base[idx] = rgba8_avg_fold(base[idx], val);
+            }
             st.fragments++;
             emitted++;
             if (stats && per_voxel[idx] < 65535) per_voxel[idx]++;
@@ -617,15 +628,28 @@ int orc_voxelize_slab(const orc_scene_t* sc, int R, int z0, int z1, uint32_t* ba
       if (!emitted) st.tris_no_frag++;
     }
   }
+  if (accum_mode == 1) {
+    for (size_t i = 0; i < nvox; i++) {
+      const uint32_t n = fx_sum[i * 5 + 4];
+      if (!n) continue;
+      uint32_t w = 0;
+      for (int k = 0; k < 4; k++) w |= ((fx_sum[i * 5 + k] + n / 2u) / n) << (8 * k);
+      base[i] = w;
+    }
+  }
   if (stats) {
     for (size_t i = 0; i < nvox; i++) {
-      if (base[i]) st.occupied++;
+      if (accum_mode == 1 ? per_voxel[i] != 0 : base[i] != 0u) st.occupied++;
       if (per_voxel[i] > st.max_per_voxel) st.max_per_voxel = per_voxel[i];
       if (per_voxel[i] >= 16) st.wrapped_voxels++;
     }
     *stats = st;
   }
   return 0;
+}
+
+int orc_voxelize_slab(const orc_scene_t* sc, int R, int z0, int z1, uint32_t* base, orc_voxel_stats_t* stats) {
+  return orc_voxelize_slab_mode(sc, R, z0, z1, 0, base, stats);
 }
 
 int orc_voxelize(const orc_scene_t* sc, int R, uint32_t* base, orc_voxel_stats_t* stats) {

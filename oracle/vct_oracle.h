@@ -93,6 +93,8 @@ void orc_texture_lod(const uint32_t* const* levels, int R, int n_levels, int dir
 int orc_voxelize(const orc_scene_t* scene, int R, uint32_t* base, orc_voxel_stats_t* stats);
 /* same, restricted to voxel z in [z0,z1) (multi-GPU slab semantics); base is still R^3 */
 int orc_voxelize_slab(const orc_scene_t* scene, int R, int z0, int z1, uint32_t* base, orc_voxel_stats_t* stats);
+/* accum_mode 0 = the reference's ordered running average; 1 = the non-reference fixed-point variant (rounded integer mean, order independent) */
+int orc_voxelize_slab_mode(const orc_scene_t* scene, int R, int z0, int z1, int accum_mode, uint32_t* base, orc_voxel_stats_t* stats);
 
 /* pyramid in the reference's layout: 6 textures x n_levels; level l of direction d is
  * out[d*n_levels + l] with (R>>l)^3 texels.  Level 0 of every direction is filled with a

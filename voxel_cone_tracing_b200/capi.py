@@ -21,7 +21,7 @@ EXPORTS = [
     "vct_grid_base_device_ptr", "vct_grid_bytes", "vct_grid_occupancy_words", "vct_grid_download_occupancy", "vct_grid_download_array",
     "vct_target_create", "vct_target_destroy", "vct_target_download_frame", "vct_target_download_frame_async", "vct_target_download_wait",
     "vct_target_download_gbuffer", "vct_target_frame_device_ptr",
-    "vct_voxelize", "vct_voxelize_reserve", "vct_voxelize_stats", "vct_mipmap", "vct_gbuffer", "vct_cone_trace", "vct_cone_trace_count",
+    "vct_voxelize", "vct_voxelize_reserve", "vct_voxelize_stats", "vct_voxelize_set_accum_mode", "vct_mipmap", "vct_gbuffer", "vct_cone_trace", "vct_cone_trace_count",
     "vct_render_frame", "vct_last_frame_timings", "vct_debug_set",
     "vct_peer_export", "vct_peer_connect", "vct_peer_disconnect", "vct_peer_error",
     "vct_tex3d_create", "vct_tex3d_destroy", "vct_tex3d_clear", "vct_tex3d_mip", "vct_tex3d_upload", "vct_tex3d_download",
@@ -60,6 +60,7 @@ def default_params(**kw) -> TraceParams:
 _lib = None
 PEER_HANDLE_BYTES = 320   # sizeof(vct_peer_handle_t)
 DEBUG_MIP_DENSE, DEBUG_CONE_VARIANT, DEBUG_CONE_GRID = 1, 2, 3   # vct_debug_set keys
+ACCUM_ORDERED, ACCUM_FIXED_POINT = 0, 1                          # vct_voxelize_set_accum_mode
 SAMPLER_FP32, SAMPLER_TEX = 0, 1
 DEFAULT_SAMPLER = int(os.environ.get("VCT_SAMPLER", "0"))
 
@@ -106,6 +107,7 @@ def load():
     L.vct_voxelize.argtypes = [vp, vp, vp, i32, i32]
     L.vct_voxelize_reserve.argtypes = [vp, C.c_uint64]
     L.vct_voxelize_stats.argtypes = [vp, C.POINTER(VoxelStats)]
+    L.vct_voxelize_set_accum_mode.argtypes = [vp, C.c_int]
     L.vct_mipmap.argtypes = [vp, vp]
     L.vct_gbuffer.argtypes = [vp, vp, f32p, f32p, vp]
     L.vct_cone_trace.argtypes = [vp, vp, vp, f32p, C.POINTER(TraceParams), vp]
@@ -146,6 +148,10 @@ class Device:
 
     def sync(self):
         check(self.L.vct_device_sync(self.h))
+
+    def set_accum_mode(self, mode: int):
+        """ACCUM_ORDERED (the reference's running average, default) or ACCUM_FIXED_POINT (order-independent integer mean; vct_c.h)"""
+        check(self.L.vct_voxelize_set_accum_mode(self.h, mode))
 
     def debug_set(self, key: int, value: int):
         """measurement / test switches (vct_debug_set): DEBUG_MIP_DENSE, DEBUG_CONE_VARIANT, DEBUG_CONE_GRID"""

@@ -189,7 +189,7 @@ int vct_device_destroy(vct_device_t* d) {
   vct_peer_disconnect(d);
   cudaStreamSynchronize(d->stream);
   cudaFree(d->peer_flags);
-  cudaFree(d->frags); cudaFree(d->fresh);
+  cudaFree(d->frags); cudaFree(d->fresh); cudaFree(d->accum);
   for (auto& r : d->rs) { cudaFree(r.tri_recs); cudaFree(r.item_local); cudaFree(r.item_block); cudaFree(r.big_slot); }
   if (d->stream2) { cudaStreamSynchronize(d->stream2); cudaStreamDestroy(d->stream2); }
   for (cudaEvent_t e : {d->ev_fork, d->ev_join, d->ev_g0, d->ev_g1}) if (e) cudaEventDestroy(e);
@@ -699,6 +699,13 @@ int vct_voxelize_stats(vct_device_t* dev, vct_voxel_stats_t* out) {
   out->max_per_voxel = dev->counters_host[CNT_MAXLIST];
   out->capacity = dev->frag_capacity;
   return check_status(dev);   // VCT_ERR_OVERFLOW (arena grown) if this voxelization dropped fragments
+}
+
+int vct_voxelize_set_accum_mode(vct_device_t* dev, int mode) {
+  VCT_REQUIRE(dev, "device is null");
+  VCT_REQUIRE(mode == VCT_ACCUM_ORDERED || mode == VCT_ACCUM_FIXED_POINT, "accumulation mode must be VCT_ACCUM_ORDERED or VCT_ACCUM_FIXED_POINT");
+  dev->accum_mode = mode;
+  return VCT_OK;
 }
 
 int vct_debug_set(vct_device_t* dev, int key, int value) {

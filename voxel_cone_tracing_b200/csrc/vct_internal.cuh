@@ -181,6 +181,9 @@ struct vct_device {
   vct::FragRec* frags = nullptr;
   uint8_t* fresh = nullptr;          // per arena slot: the fragment was the first of its voxel (= one mark per occupied voxel)
   uint64_t frag_capacity = 0;
+  int accum_mode = 0;                        // VCT_ACCUM_ORDERED (the reference's running average, default) / VCT_ACCUM_FIXED_POINT
+  unsigned long long* accum = nullptr;       // fixed-point mode: two 64-bit accumulators per arena slot (all zero between frames)
+  uint64_t accum_capacity = 0;
   // raster scratch (grown on demand)
   // one set per rasteriser (0 = voxelizer, 1 = G-buffer): the two run concurrently on different streams
   struct RasterScratch {

@@ -75,6 +75,9 @@ struct FragCtx {
   uint32_t frag_capacity;
   uint8_t* fresh;      // per arena slot: this fragment was the first of its voxel
   uint32_t* counters;
+  // VCT_ACCUM_FIXED_POINT (non-reference variant): two 64-bit accumulators per arena slot; the slot of a voxel's FIRST fragment collects
+  // the whole voxel: word 0 = sum R | sum G << 24 | count << 48, word 1 = sum B | sum A << 24.  nullptr = the reference's ordered mode.
+  unsigned long long* accum;
 };
 
 // Interpolated position of a covered pixel and its voxel (voxelize.frag:156-157: truncation, then the image bounds check;
@@ -97,6 +100,19 @@ __device__ __forceinline__ void push_fragment(const FragCtx& c, const VoxTri& v,
   if (idx >= c.frag_capacity) return;
   FragRec r;
   shade_fragment(v, b, c.mats, c.L, c.cube_size, pos, r.val);
+  if (c.accum) {
+    // order-independent integer accumulation: the first fragment to arrive claims the voxel (the grid word holds its slot until the resolve
+    // pass), every fragment adds its rounded colour to that slot's accumulators.  24-bit sums, 16-bit count: exact up to 65535 fragments.
+    const uint32_t prev = atomicCAS(&c.base[voxel], 0u, idx + 1u);
+    const uint32_t owner = prev ? prev - 1u : idx;
+    c.fresh[idx] = prev == 0u ? 1 : 0;
+    if (prev == 0u) c.frags[idx].voxel = voxel;
+    const unsigned long long q0 = (unsigned long long)(uint32_t)(r.val[0] + 0.5f), q1 = (unsigned long long)(uint32_t)(r.val[1] + 0.5f);
+    const unsigned long long q2 = (unsigned long long)(uint32_t)(r.val[2] + 0.5f), q3 = (unsigned long long)(uint32_t)(r.val[3] + 0.5f);
+    atomicAdd(c.accum + 2 * (size_t)owner, q0 | (q1 << 24) | (1ull << 48));
+    atomicAdd(c.accum + 2 * (size_t)owner + 1, q2 | (q3 << 24));
+    return;
+  }
   r.next = atomicExch(&c.base[voxel], idx + 1u);
   r.voxel = voxel;
   r.key = ((unsigned long long)ti << 24) | ((unsigned long long)j << 12) | (unsigned long long)i;
@@ -341,7 +357,7 @@ sparse_clear_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ fra
 __global__ void __launch_bounds__(128)
 vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frags, const uint8_t* __restrict__ fresh,
                    uint32_t* __restrict__ counters, uint32_t frag_capacity, const PeerView pv, uint8_t* __restrict__ tile_touched, int logR,
-                   uint32_t* __restrict__ status) {
+                   uint32_t* __restrict__ status, unsigned long long* __restrict__ accum) {
   // arena too small: fragments were dropped.  Tell the host through the mapped status word (the only time this kernel touches host memory)
   if (blockIdx.x == 0 && threadIdx.x == 0 && counters[CNT_FRAGS] > frag_capacity) {
     *reinterpret_cast<volatile uint32_t*>(status + STATUS_OVERFLOW) = counters[CNT_FRAGS];
@@ -365,10 +381,18 @@ vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frag
     if (!mine) continue;
     n_mine++;
     const uint32_t voxel = frags[f].voxel;
+    uint32_t stored = 0u, n = 0;
+    if (accum) {
+      // fixed-point variant: rounded integer mean of the voxel's fragments; the accumulators are left zero for the next frame
+      const unsigned long long a0 = accum[2 * (size_t)f], a1 = accum[2 * (size_t)f + 1];
+      accum[2 * (size_t)f] = 0ull; accum[2 * (size_t)f + 1] = 0ull;
+      n = (uint32_t)(a0 >> 48);
+      const uint32_t h = n >> 1, s0 = (uint32_t)(a0 & 0xFFFFFFu), s1 = (uint32_t)((a0 >> 24) & 0xFFFFFFu), s2 = (uint32_t)(a1 & 0xFFFFFFu), s3 = (uint32_t)((a1 >> 24) & 0xFFFFFFu);
+      stored = ((s0 + h) / n) | ((s1 + h) / n) << 8 | ((s2 + h) / n) << 16 | ((s3 + h) / n) << 24;
+    } else {
     const uint32_t head = base[voxel];
     unsigned long long keys[kSortMax];
     uint32_t ids[kSortMax];
-    uint32_t n = 0;
     for (uint32_t node = head; node != 0u; node = frags[node - 1u].next) {
       if (n < kSortMax) {
         // insertion sort, ascending key
@@ -379,7 +403,6 @@ vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frag
       }
       n++;
     }
-    uint32_t stored = 0u;
     if (n <= (uint32_t)kSortMax) {
       for (uint32_t i = 0; i < n; i++) stored = avg_fold(stored, frags[ids[i]].val);
     } else {
@@ -397,6 +420,7 @@ vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frag
         last = best;
         first = false;
       }
+    }
     }
     base[voxel] = stored;
     if (tile_touched) tile_touched[tile_of_voxel(voxel, logR)] = 1;   // sparse mip build: this 32x8x8 tile has content
@@ -462,6 +486,16 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
     if (rc) return rc;
   }
   cudaStream_t s = dev->stream;
+  unsigned long long* accum = nullptr;
+  if (dev->accum_mode == VCT_ACCUM_FIXED_POINT) {
+    if (dev->accum_capacity < dev->frag_capacity) {   // (re)allocated zeroed; the resolve pass zeroes what a frame used
+      if (dev->accum) { VCT_CUDA(cudaStreamSynchronize(s)); cudaFree(dev->accum); dev->accum = nullptr; dev->accum_capacity = 0; }
+      VCT_CUDA(cudaMalloc(&dev->accum, dev->frag_capacity * 2 * sizeof(unsigned long long)));
+      VCT_CUDA(cudaMemsetAsync(dev->accum, 0, dev->frag_capacity * 2 * sizeof(unsigned long long), s));
+      dev->accum_capacity = dev->frag_capacity;
+    }
+    accum = dev->accum;
+  }
   // sparse bookkeeping (vct_grid in vct_internal.cuh): the occupied list written below describes level 0 completely only when the
   // level was all zero before; the tile flags stay valid as long as every writer of level 0 marks them
   const bool was_zero = g->base_zero;
@@ -480,13 +514,14 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
     FragCtx ctx;
     ctx.mats = sc->mats; ctx.L = sc->lights; ctx.cube_size = sc->cube_size; ctx.R = g->R; ctx.z0 = z0; ctx.z1 = z1;
     ctx.base = g->base; ctx.frags = dev->frags; ctx.frag_capacity = (uint32_t)dev->frag_capacity; ctx.fresh = dev->fresh; ctx.counters = dev->counters;
+    ctx.accum = accum;
     vox_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, sc->cube_size, g->R, z0, z1, tris,
                                                           dev->rs[0].item_local, dev->rs[0].item_block, ctx, sc->n_tris >= kSmallPathMinTris ? kSmallPixels : 0,
                                                           sc->n_tris >= kSmallPathMinTris ? kMidPixels : 0, dev->counters + CNT_TICKET_VOX, dev->counters + CNT_ITEMS);
     vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->rs[0].item_local, dev->rs[0].item_block, n_blocks, ctx);
   }
   vox_resolve_kernel<<<sms * 8, 128, 0, s>>>(g->base, dev->frags, dev->fresh, dev->counters, (uint32_t)dev->frag_capacity, pv, touched, log2_int(g->R),
-                                             dev->status_dev);
+                                             dev->status_dev, accum);
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;
 }
