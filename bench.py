@@ -213,14 +213,16 @@ class CudaArray:
 class Rig:
     """one config on this rank's GPU: pipeline + the frame function of the chosen exchange"""
 
-    def __init__(self, cfg, args, rank, world, local_rank, torch, dist):
+    def __init__(self, cfg, args, rank, world, local_rank, torch, dist, fp16: bool = False):
         from voxel_cone_tracing_b200 import capi
         self.capi, self.torch, self.dist = capi, torch, dist
         self.cfg, self.args, self.rank, self.world, self.local_rank = cfg, args, rank, world, local_rank
         R, W, H = cfg["R"], cfg["W"], cfg["H"]
         self.sc = build_scene(cfg)
         self.view, self.proj = S.reference_camera(W / H)
-        self.pipe = capi.Pipeline(self.sc, R, W, H, 7, ordinal=local_rank, reserve=max(1 << 20, 8 * self.sc.n_triangles))
+        levels = (R.bit_length() if fp16 else 7)   # fp16 variant: the full chain, log2(R) + 1 levels
+        self.pipe = capi.Pipeline(self.sc, R, W, H, levels, ordinal=local_rank, reserve=max(1 << 20, 8 * self.sc.n_triangles),
+                                  fmt=capi.GRID_RGBA16F if fp16 else capi.GRID_RGBA8)
         self.stream = torch.cuda.ExternalStream(int(self.pipe.dev.L.vct_device_stream(self.pipe.dev.h)), device=torch.device("cuda", local_rank))
         self.prm = capi.default_params(tile_rank=rank, tile_nranks=world, sampler=args.sampler, n_diffuse_cones=cfg.get("cones", 9))
         self.z0, self.z1 = rank * R // world, (rank + 1) * R // world
@@ -429,19 +431,22 @@ def mip_stage(rig: Rig, stage_acc: dict) -> dict:
     return out
 
 
-def run_extra(cfg_id, args, rank, world, local_rank, torch, dist):
+def run_extra(cfg_id, args, rank, world, local_rank, torch, dist, fp16: bool = False):
     """one of the large configs, device-timed at this N (no end-to-end leg, no CPU leg)"""
     cfg = CONFIGS[cfg_id]
-    steps = 10 if cfg_id == 4 else 5
+    steps = 10 if cfg_id == 4 else (3 if fp16 else 5)
     try:
-        rig = Rig(cfg, args, rank, world, local_rank, torch, dist)
+        rig = Rig(cfg, args, rank, world, local_rank, torch, dist, fp16)
         ms = rig.timed(steps, 3)
         st = rig.stage_times(3) if (world == 1 or rig.p2p) else None
         per_rank = None
         if world > 1 and st is not None:
             per_rank = [None] * world
             dist.all_gather_object(per_rank, {k: round(v, 1) for k, v in st.items()})
-        out = {"workload": config_dict(cfg, world, args.sampler, args.exchange, rig.sc.n_triangles)["workload"], "ms_per_frame": ms, "frames_per_s": 1e3 / ms,
+        wl = config_dict(cfg, world, args.sampler, args.exchange, rig.sc.n_triangles)["workload"]
+        if fp16:
+            wl = wl.replace("RGBA8, 7 levels", "RGBA16F grid, full chain of %d levels: BASELINE config 5's storage variant, fp32 software filtering" % cfg["R"].bit_length())
+        out = {"workload": wl, "ms_per_frame": ms, "frames_per_s": 1e3 / ms,
                "steps": steps, "grid": cfg["R"], "frame": [cfg["W"], cfg["H"]], "triangles": rig.sc.n_triangles}
         if world == 1:
             out["stages_us"] = {k: round(v, 1) for k, v in st.items()}
@@ -515,6 +520,8 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
     extra = None
     if not args.no_extra and args.config == 2 and (world == 1 or args.exchange == "p2p"):
         extra = {str(c): run_extra(c, args, rank, world, local_rank, torch, dist) for c in (4, 5)}
+        if world == 1:   # config 5 as BASELINE.json states it: fp16 RGBA grid + full mip chain (single GPU: the exchange is RGBA8 only)
+            extra["5_fp16_full_chain"] = run_extra(5, args, rank, world, local_rank, torch, dist, fp16=True)
 
     if rank == 0:
         out = {"metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),

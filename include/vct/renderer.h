@@ -111,6 +111,9 @@ struct Renderer {
   void* frame_device_ptr();                             // device pointer of the RGBA8 frame
   bool read_voxels(int level, int dir, uint32_t* rgba8); // one level of one directional texture (glGetTexImage)
   void set_sampler(int vct_sampler) { m_sampler = vct_sampler; }  // VCT_SAMPLER_FP32 / VCT_SAMPLER_TEX
+  // storage of the voxel pyramid: VCT_GRID_RGBA8 with 7 levels is the reference (texture_3d.cpp:3-25, renderer.cpp:186); VCT_GRID_RGBA16F and/or
+  // another level count (0 = reference default for RGBA8, the full chain for RGBA16F) is BASELINE config 5's variant.  Recreates the grid.
+  void set_grid_storage(int vct_grid_format, int levels = 0);
   // VCT_ACCUM_ORDERED (the reference's running average, bit-exact, default) / VCT_ACCUM_FIXED_POINT (order-independent integer mean)
   bool set_voxel_accumulation(int vct_accum_mode) { return vct_voxelize_set_accum_mode(m_device.handle(), vct_accum_mode) == VCT_OK; }
   void set_diffuse_cone_count(int n) { m_diffuse_cones = n; }     // 9 = reference, 5 = BASELINE.json variant
@@ -156,6 +159,8 @@ struct Renderer {
   int m_view_voxel_dir = 7;
   float m_view_voxel_lod = 0.0f;
   int m_sampler = VCT_SAMPLER_TEX, m_diffuse_cones = 9, m_rank = 0, m_nranks = 1;
+  int m_grid_format = VCT_GRID_RGBA8, m_grid_levels = 0;
+  static constexpr int VCT_MAX_LEVELS_HOST = 12;
   bool m_staged = false;
   int m_last_rc = 0;
 

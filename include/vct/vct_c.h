@@ -106,6 +106,14 @@ int vct_scene_set_cube_size(vct_scene_t* sc, float cube_size);
  *      create_tex_3d texture_3d.cpp:3-25).  Level 0 is stored once (the reference writes the
  *      same value to all six, voxelize.frag:159-160); levels 1.. hold 6 directions per texel. ---- */
 int vct_grid_create(vct_device_t* dev, int resolution, int levels, vct_grid_t** out);
+/* Storage variant of BASELINE.json config 5 ("fp16 RGBA grid + full mip chain"; NOT the reference's format, which is RGBA8 with 7 levels:
+ * texture_3d.cpp:3-25, renderer.cpp:186).  VCT_GRID_RGBA16F: every texel of every level is four IEEE halves (8 bytes); voxels hold the mean
+ * fragment colour (fixed-point accumulation, see VCT_ACCUM_FIXED_POINT), the mip chain blends in fp32 and rounds to half, the cone tracer
+ * filters in fp32 (software sampler; the texture-unit path and the multi-GPU exchange are RGBA8 only).  Any `levels` up to log2(R)+1. */
+#define VCT_GRID_RGBA8 0
+#define VCT_GRID_RGBA16F 1
+int vct_grid_create_ex(vct_device_t* dev, int resolution, int levels, int format, vct_grid_t** out);
+int vct_grid_download_f16(vct_grid_t* g, int level, int dir, uint64_t* host); /* (R >> level)^3 texels of four halves, R in the low 16 bits */
 int vct_grid_destroy(vct_grid_t* g);
 int vct_grid_clear(vct_grid_t* g);                                        /* clear_tex_3d x6, renderer.cpp:320-321 */
 int vct_grid_upload_base(vct_grid_t* g, const uint32_t* host_rgba8);      /* R^3 texels, [z][y][x] */

@@ -79,6 +79,10 @@ def lib():
         L.orc_voxelize_slab.argtypes = [C.POINTER(SceneT), C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(VoxelStats)]
         L.orc_voxelize_slab_mode.argtypes = [C.POINTER(SceneT), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(VoxelStats)]
         L.orc_mipmap.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.orc_mipmap_fmt.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int]
+        L.orc_trace_cone_fmt.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, f32p, f32p, C.c_float, C.c_float, f32p]
+        L.orc_trace_fmt.argtypes = [C.POINTER(SceneT), f32p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                    C.POINTER(TraceParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(TraceStats)]
         L.orc_gbuffer.argtypes = [C.POINTER(SceneT), f32p, f32p, C.c_int, C.c_int] + [C.c_void_p] * 5
         L.orc_trace.argtypes = [C.POINTER(SceneT), f32p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_void_p, C.c_int, C.c_int,
                                 C.POINTER(TraceParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(TraceStats)]
@@ -126,12 +130,13 @@ class SceneRef:
                         l.ctypes.data if len(l) else None, len(l), float(scene.cube_size))
 
 
-ACCUM_ORDERED, ACCUM_FIXED_POINT = 0, 1
+ACCUM_ORDERED, ACCUM_FIXED_POINT, ACCUM_FP16 = 0, 1, 2   # 2: fixed-point accumulation, RGBA16F voxels (uint64 = four halves)
+FMT_RGBA8, FMT_RGBA16F = 0, 1
 
 
 def voxelize(scene, R: int, z0: int = 0, z1: int | None = None, accum_mode: int = ACCUM_ORDERED):
     sr = SceneRef(scene)
-    base = np.zeros((R, R, R), np.uint32)
+    base = np.zeros((R, R, R), np.uint64 if accum_mode == ACCUM_FP16 else np.uint32)
     st = VoxelStats()
     rc = lib().orc_voxelize_slab_mode(C.byref(sr.c), R, z0, R if z1 is None else z1, accum_mode, base.ctypes.data, C.byref(st))
     assert rc == 0
@@ -141,17 +146,18 @@ def voxelize(scene, R: int, z0: int = 0, z1: int | None = None, accum_mode: int 
 class Pyramid:
     """Reference layout: 6 textures x n_levels (level 0 of all six aliases base)."""
 
-    def __init__(self, base: np.ndarray, n_levels: int = 7):
+    def __init__(self, base: np.ndarray, n_levels: int = 7, fmt: int = FMT_RGBA8):
         R = base.shape[0]
-        self.R, self.n_levels = R, n_levels
-        self.base = np.ascontiguousarray(base, np.uint32)
-        self.levels = [[self.base] + [np.zeros((max(R >> l, 1),) * 3, np.uint32) for l in range(1, n_levels)] for _ in range(6)]
+        self.R, self.n_levels, self.fmt = R, n_levels, fmt
+        dt = np.uint64 if fmt == FMT_RGBA16F else np.uint32
+        self.base = np.ascontiguousarray(base, dt)
+        self.levels = [[self.base] + [np.zeros((max(R >> l, 1),) * 3, dt) for l in range(1, n_levels)] for _ in range(6)]
         self.ptrs = (C.c_void_p * (6 * n_levels))(*[self.levels[d][l].ctypes.data for d in range(6) for l in range(n_levels)])
 
 
-def mipmap(base: np.ndarray, n_levels: int = 7) -> Pyramid:
-    p = Pyramid(base, n_levels)
-    rc = lib().orc_mipmap(p.base.ctypes.data, p.R, n_levels, p.ptrs)
+def mipmap(base: np.ndarray, n_levels: int = 7, fmt: int = FMT_RGBA8) -> Pyramid:
+    p = Pyramid(base, n_levels, fmt)
+    rc = lib().orc_mipmap_fmt(p.base.ctypes.data, p.R, n_levels, p.ptrs, fmt)
     assert rc == 0
     return p
 
@@ -162,7 +168,7 @@ def texture_lod(p: Pyramid, d: int, pos, lod: float):
 
 def trace_cone(p: Pyramid, origin, direction, aperture: float, max_dist: float):
     out = np.zeros(4, np.float32)
-    n = lib().orc_trace_cone(p.ptrs, p.R, p.n_levels, _fp(origin), _fp(direction), aperture, max_dist, out.ctypes.data_as(f32p))
+    n = lib().orc_trace_cone_fmt(p.ptrs, p.R, p.n_levels, p.fmt, _fp(origin), _fp(direction), aperture, max_dist, out.ctypes.data_as(f32p))
     return out, int(n)
 
 
@@ -188,16 +194,16 @@ def trace(scene, view, g: GBuffer, p: Pyramid, params: TraceParams | None = None
     if frame is None:
         frame = np.zeros((g.H, g.W), np.uint32)
     st = TraceStats()
-    rc = lib().orc_trace(C.byref(sr.c), _fp(view), g.W, g.H, g.tri_id.ctypes.data, g.world_pos.ctypes.data, g.normal.ctypes.data,
-                         g.material.ctypes.data, p.ptrs, p.R, p.n_levels, C.byref(params), 0, g.H, tile_stride, tile_phase,
-                         frame.ctypes.data, C.byref(st))
+    rc = lib().orc_trace_fmt(C.byref(sr.c), _fp(view), g.W, g.H, g.tri_id.ctypes.data, g.world_pos.ctypes.data, g.normal.ctypes.data,
+                             g.material.ctypes.data, p.ptrs, p.R, p.n_levels, p.fmt, C.byref(params), 0, g.H, tile_stride, tile_phase,
+                             frame.ctypes.data, C.byref(st))
     assert rc == 0
     return frame, st
 
 
-def render_frame(scene, view, proj, R: int, W: int, H: int, params: TraceParams | None = None, n_levels: int = 7):
-    base, vst = voxelize(scene, R)
-    pyr = mipmap(base, n_levels)
+def render_frame(scene, view, proj, R: int, W: int, H: int, params: TraceParams | None = None, n_levels: int = 7, fmt: int = FMT_RGBA8):
+    base, vst = voxelize(scene, R, accum_mode=ACCUM_FP16 if fmt == FMT_RGBA16F else ACCUM_ORDERED)
+    pyr = mipmap(base, n_levels, fmt)
     g = gbuffer(scene, view, proj, W, H)
     frame, tst = trace(scene, view, g, pyr, params)
     return dict(base=base, pyramid=pyr, gbuffer=g, frame=frame, voxel_stats=vst, trace_stats=tst)

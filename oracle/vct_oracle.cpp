@@ -232,11 +232,25 @@ inline float interp(const float b[3], float a0, float a1, float a2) { return (b[
 
 /* ------------------------------------------------------------------ */
 /* textures (R6, R7) */
+/* Texel storage: fmt 0 = RGBA8 unorm (one uint32 per texel, the reference's format, texture_3d.cpp:3-25);
+ * fmt 1 = RGBA16F (one uint64 per texel: four IEEE halves, R in the low 16 bits) -- the NON-REFERENCE storage variant of BASELINE.json
+ * config 5 ("fp16 RGBA + full mip chain").  The level pointers are then really uint64 arrays. */
 struct Pyramid {
   const uint32_t* const* levels; /* [dir * n_levels + level] */
   int R, n_levels;
+  int fmt = 0;
   inline int size(int l) const { int n = R >> l; return n < 1 ? 1 : n; }
 };
+inline float half_to_float(uint16_t h) { _Float16 v; memcpy(&v, &h, 2); return (float)v; }
+inline uint16_t float_to_half(float f) { _Float16 v = (_Float16)f; uint16_t h; memcpy(&h, &v, 2); return h; } /* round to nearest even */
+inline void unpack_half4(uint64_t c, float out[4]) {
+  for (int k = 0; k < 4; k++) out[k] = half_to_float((uint16_t)(c >> (16 * k)));
+}
+inline uint64_t pack_half4(const float v[4]) {
+  uint64_t r = 0;
+  for (int k = 0; k < 4; k++) r |= (uint64_t)float_to_half(clamp01(v[k])) << (16 * k);
+  return r;
+}
 
 inline void unpack_unorm(uint32_t c, float out[4]) {
   out[0] = (float)(c & 0xFFu) / 255.0f;
@@ -250,7 +264,8 @@ inline uint32_t pack_unorm(const float v[4]) {
   return r;
 }
 
-inline void trilinear(const uint32_t* tex, int N, V3 s, float out[4]) {
+inline void load_texel(const uint32_t* tex, size_t idx, int fmt, float c[4]);
+inline void trilinear(const uint32_t* tex, int N, V3 s, float out[4], int fmt = 0) {
   out[0] = out[1] = out[2] = out[3] = 0.0f;
   float ux = s.x * (float)N - 0.5f, uy = s.y * (float)N - 0.5f, uz = s.z * (float)N - 0.5f;
   if (!(fabsf(ux) < 1.0e9f) || !(fabsf(uy) < 1.0e9f) || !(fabsf(uz) < 1.0e9f)) return; /* NaN / absurd: border */
@@ -271,11 +286,16 @@ inline void trilinear(const uint32_t* tex, int N, V3 s, float out[4]) {
         float wx = dx ? ax : 1.0f - ax;
         float w = (wx * wy) * wz;
         float c[4];
-        unpack_unorm(tex[((size_t)z * N + y) * N + x], c);
+        load_texel(tex, ((size_t)z * N + y) * N + x, fmt, c);
         for (int k = 0; k < 4; k++) out[k] = out[k] + w * c[k];
       }
     }
   }
+}
+
+inline void load_texel(const uint32_t* tex, size_t idx, int fmt, float c[4]) {
+  if (fmt == 1) unpack_half4(reinterpret_cast<const uint64_t*>(tex)[idx], c);
+  else unpack_unorm(tex[idx], c);
 }
 
 inline void texture_lod(const Pyramid& p, int dir, V3 s, float lod, float out[4]) {
@@ -286,8 +306,8 @@ inline void texture_lod(const Pyramid& p, int dir, V3 s, float lod, float out[4]
   int l1 = l0 + 1 < p.n_levels ? l0 + 1 : p.n_levels - 1;
   float f = l - (float)l0;
   float t0[4], t1[4];
-  trilinear(p.levels[dir * p.n_levels + l0], p.size(l0), s, t0);
-  trilinear(p.levels[dir * p.n_levels + l1], p.size(l1), s, t1);
+  trilinear(p.levels[dir * p.n_levels + l0], p.size(l0), s, t0, p.fmt);
+  trilinear(p.levels[dir * p.n_levels + l1], p.size(l1), s, t1, p.fmt);
   for (int k = 0; k < 4; k++) out[k] = (1.0f - f) * t0[k] + f * t1[k];
 }
 
@@ -526,14 +546,18 @@ void orc_camera_front(float pitch_deg, float yaw_deg, float out[3]) {
 
 float orc_specular_aperture(float shininess) { return specular_aperture(shininess); }
 
+int orc_trace_cone_fmt(const uint32_t* const* levels, int R, int n_levels, int fmt, const float origin[3], const float dir[3],
+                       float aperture, float max_dist, float out_rgba[4]) {
+  Pyramid p{levels, R, n_levels, fmt};
+  return trace_cone(p, v3(origin[0], origin[1], origin[2]), v3(dir[0], dir[1], dir[2]), aperture, max_dist, out_rgba);
+}
 int orc_trace_cone(const uint32_t* const* levels, int R, int n_levels, const float origin[3], const float dir[3],
                    float aperture, float max_dist, float out_rgba[4]) {
-  Pyramid p{levels, R, n_levels};
-  return trace_cone(p, v3(origin[0], origin[1], origin[2]), v3(dir[0], dir[1], dir[2]), aperture, max_dist, out_rgba);
+  return orc_trace_cone_fmt(levels, R, n_levels, 0, origin, dir, aperture, max_dist, out_rgba);
 }
 
 void orc_texture_lod(const uint32_t* const* levels, int R, int n_levels, int dir, const float pos[3], float lod, float out[4]) {
-  Pyramid p{levels, R, n_levels};
+  Pyramid p{levels, R, n_levels, 0};
   texture_lod(p, dir, v3(pos[0], pos[1], pos[2]), lod, out);
 }
 
@@ -546,8 +570,8 @@ int orc_voxelize_slab_mode(const orc_scene_t* sc, int R, int z0, int z1, int acc
   if (!sc || !base || R <= 0) return -1;
   size_t nvox = (size_t)R * R * R;
   std::vector<uint32_t> fx_sum;   /* accum_mode 1: four sums + the count per voxel */
-  if (accum_mode == 1) fx_sum.assign(nvox * 5, 0u);
-  memset(base, 0, nvox * sizeof(uint32_t)); /* clear_tex_3d, renderer.cpp:320-321 */
+  if (accum_mode >= 1) fx_sum.assign(nvox * 5, 0u);
+  memset(base, 0, nvox * (accum_mode == 2 ? sizeof(uint64_t) : sizeof(uint32_t))); /* clear_tex_3d, renderer.cpp:320-321 */
   orc_voxel_stats_t st;
   memset(&st, 0, sizeof st);
   std::vector<uint16_t> per_voxel;
@@ -613,11 +637,11 @@ int orc_voxelize_slab_mode(const orc_scene_t* sc, int R, int z0, int z1, int acc
             if (vx < 0 || vy < 0 || vz < 0 || vx >= R || vy >= R || vz >= R) { st.fragments_oob++; continue; }
             if (vz < z0 || vz >= z1) continue;
             size_t idx = ((size_t)vz * R + vy) * R + vx;
-            if (accum_mode == 1) {
+            if (accum_mode >= 1) {
               for (int k = 0; k < 4; k++) fx_sum[idx * 5 + k] += (uint32_t)(val[k] + 0.5f);
               fx_sum[idx * 5 + 4]++;
             } else {
-              base[idx] = rgba8_avg_fold(base[idx], val);
+                base[idx] = rgba8_avg_fold(base[idx], val);
             }
             st.fragments++;
             emitted++;
@@ -636,10 +660,19 @@ int orc_voxelize_slab_mode(const orc_scene_t* sc, int R, int z0, int z1, int acc
       for (int k = 0; k < 4; k++) w |= ((fx_sum[i * 5 + k] + n / 2u) / n) << (8 * k);
       base[i] = w;
     }
+  } else if (accum_mode == 2) { /* RGBA16F grid: the mean colour in [0,1] rounded to half; `base` is really a uint64 array */
+    uint64_t* b64 = reinterpret_cast<uint64_t*>(base);
+    for (size_t i = 0; i < nvox; i++) {
+      const uint32_t n = fx_sum[i * 5 + 4];
+      if (!n) continue;
+      float c[4];
+      for (int k = 0; k < 4; k++) c[k] = (float)fx_sum[i * 5 + k] / ((float)n * 255.0f);
+      b64[i] = pack_half4(c);
+    }
   }
   if (stats) {
     for (size_t i = 0; i < nvox; i++) {
-      if (accum_mode == 1 ? per_voxel[i] != 0 : base[i] != 0u) st.occupied++;
+      if (accum_mode >= 1 ? per_voxel[i] != 0 : base[i] != 0u) st.occupied++;
       if (per_voxel[i] > st.max_per_voxel) st.max_per_voxel = per_voxel[i];
       if (per_voxel[i] >= 16) st.wrapped_voxels++;
     }
@@ -657,11 +690,17 @@ int orc_voxelize(const orc_scene_t* sc, int R, uint32_t* base, orc_voxel_stats_t
 }
 
 /* ---------------- mipmap (M1) ---------------- */
-int orc_mipmap(const uint32_t* base, int R, int n_levels, uint32_t* const* out) {
+int orc_mipmap_fmt(const uint32_t* base, int R, int n_levels, uint32_t* const* out, int fmt);
+int orc_mipmap(const uint32_t* base, int R, int n_levels, uint32_t* const* out) { return orc_mipmap_fmt(base, R, n_levels, out, 0); }
+
+/* fmt 1: every array is uint64 per texel (RGBA16F); the blend runs in fp32 on the exactly converted halves, the result is clamped to
+ * [0,1] like the unorm store of the reference and rounded to half (nearest even) */
+int orc_mipmap_fmt(const uint32_t* base, int R, int n_levels, uint32_t* const* out, int fmt) {
   if (!base || !out || R <= 0 || n_levels < 1) return -1;
   size_t nvox = (size_t)R * R * R;
+  const size_t tb = fmt == 1 ? 8 : 4;
   for (int d = 0; d < 6; d++)
-    if (out[d * n_levels] && out[d * n_levels] != base) memcpy(out[d * n_levels], base, nvox * 4);
+    if (out[d * n_levels] && out[d * n_levels] != base) memcpy(out[d * n_levels], base, nvox * tb);
   /* front/back child pairs per direction, children numbered as mipmap.comp:10-20 */
   static const int off[8][3] = {{1, 1, 1}, {1, 1, 0}, {1, 0, 1}, {1, 0, 0}, {0, 1, 1}, {0, 1, 0}, {0, 0, 1}, {0, 0, 0}};
   static const int pairs[6][4][2] = {
@@ -686,7 +725,7 @@ int orc_mipmap(const uint32_t* base, int R, int n_levels, uint32_t* const* out) 
             float c[8][4];
             for (int i = 0; i < 8; i++) {
               int sx = 2 * x + off[i][0], sy = 2 * y + off[i][1], sz = 2 * z + off[i][2];
-              unpack_unorm(src[((size_t)sz * Ns + sy) * Ns + sx], c[i]);
+              load_texel(src, ((size_t)sz * Ns + sy) * Ns + sx, fmt, c[i]);
             }
             float acc[4];
             for (int k = 0; k < 4; k++) {
@@ -699,7 +738,8 @@ int orc_mipmap(const uint32_t* base, int R, int n_levels, uint32_t* const* out) 
               }
               acc[k] = s / 4.0f;
             }
-            dst[((size_t)z * Nd + y) * Nd + x] = pack_unorm(acc);
+            if (fmt == 1) reinterpret_cast<uint64_t*>(dst)[((size_t)z * Nd + y) * Nd + x] = pack_half4(acc);
+            else dst[((size_t)z * Nd + y) * Nd + x] = pack_unorm(acc);
           }
     }
   }
@@ -829,10 +869,17 @@ int orc_trace(const orc_scene_t* sc, const float view[16], int W, int H, const u
               const float* normal, const uint32_t* material, const uint32_t* const* levels, int R, int n_levels,
               const orc_trace_params_t* prm, int row0, int row1, int tile_stride, int tile_phase, uint32_t* frame,
               orc_trace_stats_t* stats) {
+  return orc_trace_fmt(sc, view, W, H, tri_id, world_pos, normal, material, levels, R, n_levels, 0, prm, row0, row1, tile_stride, tile_phase, frame, stats);
+}
+
+int orc_trace_fmt(const orc_scene_t* sc, const float view[16], int W, int H, const uint32_t* tri_id, const float* world_pos,
+                  const float* normal, const uint32_t* material, const uint32_t* const* levels, int R, int n_levels, int fmt,
+                  const orc_trace_params_t* prm, int row0, int row1, int tile_stride, int tile_phase, uint32_t* frame,
+                  orc_trace_stats_t* stats) {
   if (!sc || !tri_id || !world_pos || !normal || !material || !levels || !prm || !frame) return -1;
   ShadeCtx c;
   c.scene = sc;
-  c.pyr = Pyramid{levels, R, n_levels};
+  c.pyr = Pyramid{levels, R, n_levels, fmt};
   c.prm = prm;
   c.camera_position = v3(view[12], view[13], view[14]); /* glm::column(view, 3), renderer.cpp:279 (sic) */
   if (row0 < 0) row0 = 0;

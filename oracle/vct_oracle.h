@@ -95,6 +95,14 @@ int orc_voxelize(const orc_scene_t* scene, int R, uint32_t* base, orc_voxel_stat
 int orc_voxelize_slab(const orc_scene_t* scene, int R, int z0, int z1, uint32_t* base, orc_voxel_stats_t* stats);
 /* accum_mode 0 = the reference's ordered running average; 1 = the non-reference fixed-point variant (rounded integer mean, order independent) */
 int orc_voxelize_slab_mode(const orc_scene_t* scene, int R, int z0, int z1, int accum_mode, uint32_t* base, orc_voxel_stats_t* stats);
+/* ---- RGBA16F storage variant (BASELINE.json config 5: "fp16 RGBA + full mip chain"; NOT the reference's format): texels are uint64 = four
+ *      halves.  accum_mode 2 of orc_voxelize_slab_mode writes such a grid (mean colour in [0,1], `base` = R^3 uint64); fmt = 1 below. ---- */
+int orc_mipmap_fmt(const uint32_t* base, int R, int n_levels, uint32_t* const* out, int fmt);
+int orc_trace_cone_fmt(const uint32_t* const* levels, int R, int n_levels, int fmt, const float origin[3], const float dir[3], float aperture,
+                       float max_dist, float out_rgba[4]);
+int orc_trace_fmt(const orc_scene_t* scene, const float view[16], int W, int H, const uint32_t* tri_id, const float* world_pos, const float* normal,
+                  const uint32_t* material, const uint32_t* const* levels, int R, int n_levels, int fmt, const orc_trace_params_t* prm, int row0, int row1,
+                  int tile_stride, int tile_phase, uint32_t* frame, orc_trace_stats_t* stats);
 
 /* pyramid in the reference's layout: 6 textures x n_levels; level l of direction d is
  * out[d*n_levels + l] with (R>>l)^3 texels.  Level 0 of every direction is filled with a

@@ -251,6 +251,32 @@ def test_voxelize_fixed_point_accumulation_mode(scene_kind):
     p.close()
 
 
+@pytest.mark.parametrize("R,levels,suzanne", [(64, 7, True), (128, 8, True), (32, 6, False)])
+def test_fp16_grid_full_mip_chain_variant(R, levels, suzanne):
+    """BASELINE config 5's storage variant ("fp16 RGBA grid + full mip chain", NOT the reference's RGBA8 / 7 levels): voxels
+    and all 6 x levels mip volumes as four halves per texel -- bit-exact against the oracle run in the same variant mode (levels =
+    log2(R) + 1 = the full chain down to one texel) -- and the frame within the 2/255 / 45 dB gate."""
+    sc = S.cornell_scene(with_suzanne=suzanne)
+    W, H = 320, 200
+    view, proj = S.reference_camera(W / H)
+    ref = orc.render_frame(sc, view, proj, R, W, H, orc.default_params(), levels, orc.FMT_RGBA16F)
+    p = capi.Pipeline(sc, R, W, H, levels, fmt=capi.GRID_RGBA16F)
+    for _ in range(2):
+        p.render_frame(view, proj, capi.default_params(sampler=capi.SAMPLER_TEX))   # (the variant filters in fp32 whatever the sampler says)
+        base = p.grid.download_f16(0)
+        assert np.array_equal(base, ref["base"]), f"{(base != ref['base']).sum()} fp16 voxels differ"
+        for l in range(1, levels):
+            for d in range(6):
+                got = p.grid.download_f16(l, d)
+                assert np.array_equal(got, ref["pyramid"].levels[d][l]), f"fp16 level {l} dir {d}: {(got != ref['pyramid'].levels[d][l]).sum()} texels differ"
+        _check_frame(p.target.frame(), ref)
+    gst = p.voxel_stats()
+    assert gst.fragments == ref["voxel_stats"].fragments and gst.occupied == ref["voxel_stats"].occupied
+    cnt = p.trace_count(view, capi.default_params())
+    assert abs(cnt.samples - ref["trace_stats"].samples) <= 5e-2 * ref["trace_stats"].samples
+    p.close()
+
+
 def test_voxelize_arena_overflow_is_reported():
     sc = S.cornell_scene()
     p = capi.Pipeline(sc, 128, 64, 64)

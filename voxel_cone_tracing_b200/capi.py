@@ -17,7 +17,7 @@ EXPORTS = [
     "vct_device_create", "vct_device_destroy", "vct_device_sync", "vct_device_stream", "vct_last_error", "vct_version",
     "vct_scene_create", "vct_scene_destroy", "vct_scene_set_geometry", "vct_scene_set_materials", "vct_scene_set_draws",
     "vct_scene_set_lights", "vct_scene_set_cube_size",
-    "vct_grid_create", "vct_grid_destroy", "vct_grid_clear", "vct_grid_upload_base", "vct_grid_download",
+    "vct_grid_create", "vct_grid_create_ex", "vct_grid_download_f16", "vct_grid_destroy", "vct_grid_clear", "vct_grid_upload_base", "vct_grid_download",
     "vct_grid_base_device_ptr", "vct_grid_bytes", "vct_grid_occupancy_words", "vct_grid_download_occupancy", "vct_grid_download_array",
     "vct_target_create", "vct_target_destroy", "vct_target_download_frame", "vct_target_download_frame_async", "vct_target_download_wait",
     "vct_target_download_gbuffer", "vct_target_frame_device_ptr",
@@ -61,6 +61,7 @@ _lib = None
 PEER_HANDLE_BYTES = 320   # sizeof(vct_peer_handle_t)
 DEBUG_MIP_DENSE, DEBUG_CONE_VARIANT, DEBUG_CONE_GRID = 1, 2, 3   # vct_debug_set keys
 ACCUM_ORDERED, ACCUM_FIXED_POINT = 0, 1                          # vct_voxelize_set_accum_mode
+GRID_RGBA8, GRID_RGBA16F = 0, 1                                  # vct_grid_create_ex formats
 SAMPLER_FP32, SAMPLER_TEX = 0, 1
 DEFAULT_SAMPLER = int(os.environ.get("VCT_SAMPLER", "0"))
 
@@ -88,6 +89,8 @@ def load():
     L.vct_scene_set_lights.argtypes = [vp, vp, u32]
     L.vct_scene_set_cube_size.argtypes = [vp, C.c_float]
     L.vct_grid_create.argtypes = [vp, i32, i32, C.POINTER(vp)]
+    L.vct_grid_create_ex.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    L.vct_grid_download_f16.argtypes = [vp, C.c_int, C.c_int, vp]
     L.vct_grid_destroy.argtypes = [vp]
     L.vct_grid_clear.argtypes = [vp]
     L.vct_grid_upload_base.argtypes = [vp, vp]
@@ -163,10 +166,10 @@ class Device:
 
 
 class Grid:
-    def __init__(self, dev: Device, R: int, levels: int = 7):
-        self.dev, self.R, self.levels = dev, R, levels
+    def __init__(self, dev: Device, R: int, levels: int = 7, fmt: int = 0):
+        self.dev, self.R, self.levels, self.fmt = dev, R, levels, fmt
         self.h = C.c_void_p()
-        check(dev.L.vct_grid_create(dev.h, R, levels, C.byref(self.h)))
+        check(dev.L.vct_grid_create_ex(dev.h, R, levels, fmt, C.byref(self.h)))
 
     def clear(self): check(self.dev.L.vct_grid_clear(self.h))
 
@@ -179,6 +182,13 @@ class Grid:
         n = self.R >> level
         out = np.empty((n, n, n), np.uint32)
         check(self.dev.L.vct_grid_download(self.h, level, d, out.ctypes.data))
+        return out
+
+    def download_f16(self, level: int, d: int = 0) -> np.ndarray:
+        """RGBA16F grids: (R >> level)^3 texels as uint64 = four halves (R in the low 16 bits)"""
+        n = self.R >> level
+        out = np.empty((n, n, n), np.uint64)
+        check(self.dev.L.vct_grid_download_f16(self.h, level, d, out.ctypes.data))
         return out
 
     def download_array(self, level: int, d: int) -> np.ndarray:
@@ -279,10 +289,10 @@ class DeviceScene:
 class Pipeline:
     """voxelize -> mip -> G-buffer -> trace, the sequence of Renderer::render() (src/renderer.cpp:392-405)."""
 
-    def __init__(self, sc: S.Scene, R: int, W: int, H: int, levels: int = 7, ordinal: int = 0, reserve: int | None = None):
+    def __init__(self, sc: S.Scene, R: int, W: int, H: int, levels: int = 7, ordinal: int = 0, reserve: int | None = None, fmt: int = 0):
         self.dev = Device(ordinal)
         self.scene = DeviceScene(self.dev, sc)
-        self.grid = Grid(self.dev, R, levels)
+        self.grid = Grid(self.dev, R, levels, fmt)
         self.target = Target(self.dev, W, H)
         if reserve:
             check(self.dev.L.vct_voxelize_reserve(self.dev.h, reserve))

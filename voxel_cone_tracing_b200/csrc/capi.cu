@@ -298,19 +298,39 @@ int vct_scene_set_cube_size(vct_scene_t* s, float cube_size) {
 }
 
 // ------------------------------------------------------------------ grid
-int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) {
+int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) { return vct_grid_create_ex(dev, R, levels, VCT_GRID_RGBA8, out); }
+
+int vct_grid_create_ex(vct_device_t* dev, int R, int levels, int format, vct_grid_t** out) {
   VCT_REQUIRE(dev && out, "null argument");
+  VCT_REQUIRE(format == VCT_GRID_RGBA8 || format == VCT_GRID_RGBA16F, "format must be VCT_GRID_RGBA8 or VCT_GRID_RGBA16F");
+  const bool f16 = format == VCT_GRID_RGBA16F;
   // 1024 = the largest size the 32-bit voxel index (fragment records, tile flags, sparse clear) addresses and the tests cover
   VCT_REQUIRE(R >= 2 && R <= 1024 && (R & (R - 1)) == 0, "resolution must be a power of two in [2, 1024]");
   VCT_REQUIRE(levels >= 1 && levels <= VCT_MAX_LEVELS && (R >> (levels - 1)) >= 1, "levels must satisfy 1 <= levels <= log2(R)+1");
   vct_grid* g = new (std::nothrow) vct_grid();
   if (!g) { set_error("out of host memory"); return VCT_ERR_OOM; }
-  g->dev = dev; g->R = R; g->levels = levels;
+  g->dev = dev; g->R = R; g->levels = levels; g->fmt = format;
   size_t n0 = (size_t)R * R * R;
-  cudaError_t e = cudaMalloc(&g->base, n0 * 4);
+  cudaError_t e = cudaMalloc(&g->base, n0 * (f16 ? 8 : 4));
   g->base_buf[0] = g->base;
-  g->bytes = n0 * 4;
-  if (mip_fused_applies(R, levels)) {
+  g->bytes = n0 * (f16 ? 8 : 4);
+  if (f16 && e == cudaSuccess) {
+    // RGBA16F variant: levels 1.. as linear buffers per direction (no texture array: the tracer filters in fp32), pointer table on the device
+    std::vector<const unsigned long long*> table((size_t)levels * 6, nullptr);
+    for (int d = 0; d < 6; d++) table[d] = reinterpret_cast<const unsigned long long*>(g->base);
+    for (int l = 1; l < levels && e == cudaSuccess; l++) {
+      const size_t n = (size_t)(R >> l) * (R >> l) * (R >> l);
+      for (int d = 0; d < 6 && e == cudaSuccess; d++) {
+        e = cudaMalloc(&g->f16_lvl[l][d], n * 8);
+        if (e == cudaSuccess) e = cudaMemsetAsync(g->f16_lvl[l][d], 0, n * 8, dev->stream);
+        g->bytes += n * 8;
+        table[(size_t)l * 6 + d] = g->f16_lvl[l][d];
+      }
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&g->f16_table, table.size() * sizeof(void*));
+    if (e == cudaSuccess) e = cudaMemcpy(g->f16_table, table.data(), table.size() * sizeof(void*), cudaMemcpyHostToDevice);
+  }
+  if (!f16 && mip_fused_applies(R, levels)) {
     // the streaming mip kernel (csrc/mipmap.cu): one flag pair per 32x8x8 warp-tile, and the small linear copies of the coarse
     // levels that the tail kernel folds
     const size_t n_tiles = n0 / 2048, n_blocks = n0 / 32768, n3 = n0 / 512;
@@ -369,7 +389,7 @@ int vct_grid_create(vct_device_t* dev, int R, int levels, vct_grid_t** out) {
   }
   // levels 1.. additionally live in ONE mipmapped CUDA array (six directions stacked along z, zero pads between them) so that
   // the cone tracer can use the texture units with a single, warp-uniform texture object (GridView)
-  if (levels >= 2 && e == cudaSuccess) {
+  if (levels >= 2 && e == cudaSuccess && !f16) {
     const int L = levels - 1;                                   // array levels
     const int n_coarse = R >> (levels - 1);                     // size of the coarsest level
     const int pitch_coarse = n_coarse + 1;                      // volume + one zero texel
@@ -447,6 +467,8 @@ int vct_grid_destroy(vct_grid_t* g) {
   if (g->dev->peer_grid == g) vct_peer_disconnect(g->dev);
   cudaStreamSynchronize(g->dev->stream);
   cudaFree(g->base_buf[0]); cudaFree(g->base_buf[1]); cudaFree(g->tile_zero); cudaFree(g->tile_touched);
+  for (int l = 0; l < VCT_MAX_LEVELS; l++) for (int d = 0; d < 6; d++) cudaFree(g->f16_lvl[l][d]);
+  cudaFree(g->f16_table);
   cudaFree(g->rec3); cudaFree(g->rec_top); cudaFree(g->occb); cudaFree(g->mip_counters); cudaFree(g->sb_epoch);
   if (g->dev->vox_owner == g) g->dev->vox_owner = nullptr;
   for (int l = 0; l < 4; l++) cudaFree(g->occ[l]);
@@ -465,7 +487,9 @@ int vct_grid_clear(vct_grid_t* g) {
   VCT_REQUIRE(g, "grid is null");
   vct_device* dev = g->dev;
   if (g->base_zero && !g->external) { g->dirty_z0 = g->dirty_z1 = 0; return VCT_OK; }   // nothing has been written since the last clear
-  if (g->sparse_clear_ok && !g->external && dev->vox_owner == g) {
+  if (g->fmt == VCT_GRID_RGBA16F) {   // storage variant: always the dense clear
+    VCT_CUDA(cudaMemsetAsync(g->base, 0, (size_t)g->R * g->R * g->R * 8, dev->stream));
+  } else if (g->sparse_clear_ok && !g->external && dev->vox_owner == g) {
     // the non-zero words are exactly the occupied list of the last voxelization: zero those (and their tile flags)
     int rc = launch_sparse_clear(dev, g);
     if (rc) return rc;
@@ -482,14 +506,27 @@ int vct_grid_clear(vct_grid_t* g) {
 
 int vct_grid_upload_base(vct_grid_t* g, const uint32_t* host) {
   VCT_REQUIRE(g && host, "null argument");
+  VCT_REQUIRE(g->fmt == VCT_GRID_RGBA8, "RGBA8 grids only");
   g->untrack();
   VCT_CUDA(cudaMemcpyAsync(g->base, host, (size_t)g->R * g->R * g->R * 4, cudaMemcpyHostToDevice, g->dev->stream));
   VCT_CUDA(cudaStreamSynchronize(g->dev->stream));
   return VCT_OK;
 }
 
+int vct_grid_download_f16(vct_grid_t* g, int level, int dir, uint64_t* host) {
+  VCT_REQUIRE(g && host, "null argument");
+  VCT_REQUIRE(g->fmt == VCT_GRID_RGBA16F, "not an RGBA16F grid");
+  VCT_REQUIRE(level >= 0 && level < g->levels && dir >= 0 && dir < 6, "bad level / direction");
+  const size_t N = (size_t)(g->R >> level);
+  const void* src = level == 0 ? (const void*)g->base : (const void*)g->f16_lvl[level][dir];
+  VCT_CUDA(cudaMemcpyAsync(host, src, N * N * N * 8, cudaMemcpyDeviceToHost, g->dev->stream));
+  VCT_CUDA(cudaStreamSynchronize(g->dev->stream));
+  return VCT_OK;
+}
+
 int vct_grid_download(vct_grid_t* g, int level, int dir, uint32_t* host) {
   VCT_REQUIRE(g && host, "null argument");
+  VCT_REQUIRE(g->fmt == VCT_GRID_RGBA8, "RGBA8 grids only (vct_grid_download_f16 for the fp16 variant)");
   VCT_REQUIRE(level >= 0 && level < g->levels, "bad level");
   VCT_REQUIRE(dir >= 0 && dir < 6, "bad direction");
   cudaStream_t s = g->dev->stream;
@@ -533,7 +570,7 @@ int vct_grid_download_occupancy(vct_grid_t* g, int level, int dilated, uint32_t*
 }
 
 void* vct_grid_base_device_ptr(vct_grid_t* g) {
-  if (!g) return nullptr;
+  if (!g || g->fmt != VCT_GRID_RGBA8) return nullptr;
   g->external = true;   // the caller may write level 0 (NCCL all-gather of the z-slabs): no sparse bookkeeping from here on
   g->untrack();
   return (void*)g->base;

@@ -25,6 +25,7 @@
 // cone_kernel_fast is the production march.  profiles/r01_ncu_s7.md, r01_cone_experiments_s7.txt: what binds it.
 // FMA contraction is allowed here: the frame is compared against the oracle with a tolerance
 // (max abs 2/255, PSNR >= 45 dB), not bit for bit.
+#include <cuda_fp16.h>
 #include "vct_internal.cuh"
 
 namespace vct {
@@ -176,6 +177,49 @@ __device__ __forceinline__ void fetch_level(const GridView& g, int level, F3 pos
   }
 }
 
+// The same for the RGBA16F storage variant (vct_grid_create_ex): texels are four halves in linear per-direction buffers (level 0: one buffer
+// for all six directions), filtered in fp32.  Byte units like fetch_level: a colour of 1.0 counts 255.
+__device__ __forceinline__ void fetch_level_f16(const GridView& g, int level, F3 pos, F3 adir, int ix, int iy, int iz, float weight, float acc[4]) {
+  const int N = g.R >> level;
+  const float fN = (float)N;
+  const float ux = fmaf(pos.x, fN, -0.5f), uy = fmaf(pos.y, fN, -0.5f), uz = fmaf(pos.z, fN, -0.5f);
+  if (!(ux > -1.0f && ux < fN && uy > -1.0f && uy < fN && uz > -1.0f && uz < fN)) return;
+  const float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
+  const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+  const float ax = ux - fx, ay = uy - fy, az = uz - fz;
+  const float wxs[2] = {1.0f - ax, ax}, wys[2] = {1.0f - ay, ay}, wzs[2] = {1.0f - az, az};
+  const unsigned long long* tx = g.f16[level * 6 + ix];
+  const unsigned long long* ty = g.f16[level * 6 + iy];
+  const unsigned long long* tz = g.f16[level * 6 + iz];
+  const float sx = 255.0f * weight * adir.x, sy = 255.0f * weight * adir.y, sz = 255.0f * weight * adir.z;
+#pragma unroll
+  for (int dz = 0; dz < 2; dz++) {
+    const int z = z0 + dz;
+    if ((unsigned)z >= (unsigned)N) continue;
+#pragma unroll
+    for (int dy = 0; dy < 2; dy++) {
+      const int y = y0 + dy;
+      if ((unsigned)y >= (unsigned)N) continue;
+      const float wyz = wys[dy] * wzs[dz];
+#pragma unroll
+      for (int dx = 0; dx < 2; dx++) {
+        const int x = x0 + dx;
+        if ((unsigned)x >= (unsigned)N) continue;
+        const float w = wxs[dx] * wyz;
+        const size_t idx = ((size_t)z * N + y) * N + x;
+        const unsigned long long a = __ldg(tx + idx), b = level == 0 ? a : __ldg(ty + idx), c = level == 0 ? a : __ldg(tz + idx);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const float va = __half2float(__ushort_as_half((unsigned short)(a >> (16 * k))));
+          const float vb = __half2float(__ushort_as_half((unsigned short)(b >> (16 * k))));
+          const float vc = __half2float(__ushort_as_half((unsigned short)(c >> (16 * k))));
+          acc[k] = fmaf(w, fmaf(sx, va, fmaf(sy, vb, sz * vc)), acc[k]);
+        }
+      }
+    }
+  }
+}
+
 // trace_cone (voxel_cone_tracing.frag:88-119).  Returns the number of loop iterations the reference
 // would execute when COUNT is set (no early exit in that build).
 // the three directional textureLod fetches of sample_voxel through the texture units:
@@ -195,7 +239,7 @@ __device__ __forceinline__ void fetch_tex(const GridView& g, int ix, int iy, int
   acc[3] = fmaf(sx, a.w, fmaf(sy, b.w, fmaf(sz, c.w, acc[3])));
 }
 
-template <bool COUNT, bool TEX>
+template <bool COUNT, bool TEX, bool F16 = false>
 __device__ __forceinline__ uint32_t trace_cone(const GridView& g, F3 origin, F3 dir, float aperture, float max_dist, float out[4]) {
   dir = normalize(dir);
   const int ix = dir.x < 0.0f ? 0 : 1, iy = dir.y < 0.0f ? 2 : 3, iz = dir.z < 0.0f ? 4 : 5;
@@ -232,6 +276,9 @@ __device__ __forceinline__ uint32_t trace_cone(const GridView& g, F3 origin, F3 
       } else if (!(e0 && e1)) {
         fetch_tex(g, ix, iy, iz, sp, adir, lod - 1.0f, 255.0f, s);                 // trilinear + mip-linear in the texture unit
       }
+    } else if (F16) {
+      if (!e0) fetch_level_f16(g, l0, sp, adir, ix, iy, iz, 1.0f - f, s);
+      if (!e1) fetch_level_f16(g, l0 + 1, sp, adir, ix, iy, iz, f, s);
     } else {
       if (!e0) fetch_level(g, l0, sp, adir, ix, iy, iz, 1.0f - f, s);
       if (!e1) fetch_level(g, l0 + 1, sp, adir, ix, iy, iz, f, s);
@@ -507,7 +554,7 @@ tile_list_kernel(const TraceArgs a, uint32_t* __restrict__ tile_list, uint32_t* 
   if (lane < kTilesPerWarp && ((mask >> lane) & 1u)) tile_list[base + __popc(mask & ((1u << lane) - 1u))] = (uint32_t)(first + lane);
 }
 
-template <bool COUNT, bool TEX>
+template <bool COUNT, bool TEX, bool F16 = false>
 __global__ void __launch_bounds__(32 * kConeWarps)
 cone_kernel(const TraceArgs a) {
   const int lane = threadIdx.x & 31;
@@ -533,14 +580,14 @@ cone_kernel(const TraceArgs a) {
         const F3 o1 = normalize(tangent(normal));
         const F3 o2 = normalize(cross(o1, normal));
         const F3 d = diffuse_dir(normal, o1, o2, slot, nd);
-        iters = trace_cone<COUNT, TEX>(a.grid, pos, d, nd == 16 ? kAperture16 : kTan22_5, kMaxDistance, r);
+        iters = trace_cone<COUNT, TEX, F16>(a.grid, pos, d, nd == 16 ? kAperture16 : kTan22_5, kMaxDistance, r);
         kind = 0;
       }
     } else if (slot == nd) {
       if (a.prm.enable_specular) {
         const F3 view_dir = normalize(p.world - cam);
         const F3 sd = normalize(reflect(-view_dir, normal));
-        iters = trace_cone<COUNT, TEX>(a.grid, pos, sd, specular_aperture(m->shininess), kMaxDistance, r);
+        iters = trace_cone<COUNT, TEX, F16>(a.grid, pos, sd, specular_aperture(m->shininess), kMaxDistance, r);
         kind = 2;
       }
     } else if (slot == nd + 1) {
@@ -548,7 +595,7 @@ cone_kernel(const TraceArgs a) {
       if (transmissive && a.prm.enable_specular) {
         const F3 view_dir = normalize(p.world - cam);
         const F3 rd = refract(view_dir, normal, 1.0f / m->ior);
-        iters = trace_cone<COUNT, TEX>(a.grid, pos, rd, specular_aperture(m->shininess), kMaxDistance, r);
+        iters = trace_cone<COUNT, TEX, F16>(a.grid, pos, rd, specular_aperture(m->shininess), kMaxDistance, r);
         kind = 3;
       }
     } else {
@@ -560,7 +607,7 @@ cone_kernel(const TraceArgs a) {
         F3 ld = lp - pos;
         const float d = length(ld);
         ld = f3(ld.x / d, ld.y / d, ld.z / d);
-        iters = trace_cone<COUNT, TEX>(a.grid, pos, ld, 0.1f, d, r);
+        iters = trace_cone<COUNT, TEX, F16>(a.grid, pos, ld, 0.1f, d, r);
         kind = 1;
       }
     }
@@ -863,7 +910,7 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
   const int n_tiles = ((t->W + 7) / 8) * ((t->H + 3) / 4);
   // which march: 3 = production (one-level fetches through the nearest-mip texture object, all diffuse cones of a tile in one warp), 2 = one
   // warp per cone slot, 1 = every fetch blends two levels, 0 = literal loop; vct_debug_set(VCT_DEBUG_CONE_VARIANT) lets tests compare them
-  const bool tex = p->sampler == VCT_SAMPLER_TEX && g->levels >= 2;
+  const bool tex = p->sampler == VCT_SAMPLER_TEX && g->levels >= 2 && g->fmt == VCT_GRID_RGBA8;
   const bool ev = dev->debug_cone_variant >= 0;
   int variant = ev ? dev->debug_cone_variant : 3;
   // grouping makes the diffuse warps nine times longer: with few tiles per GPU (small frames, many ranks) the tail of the launch costs
@@ -888,6 +935,7 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
   a.cone_out = (float4*)t->cone_out;
   cudaStream_t s = dev->stream;
   const bool debug_view = p->view_voxel_dir < 7;
+  VCT_REQUIRE(!(debug_view && g->fmt == VCT_GRID_RGBA16F), "the voxel debug view reads RGBA8 grids only");
   if (!debug_view && phase != 2) {
     { int rc = launch_fill_u32(s, t->tile_list, 1, 0u); if (rc) return rc; }
     tile_list_kernel<<<(n_tiles + 8 * kTilesPerWarp - 1) / (8 * kTilesPerWarp), 256, 0, s>>>(a, t->tile_list + 1, t->tile_list);
@@ -900,7 +948,14 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
     const dim3 grid((n_tiles + kConeWarps - 1) / kConeWarps, a.n_slots);
     const dim3 grid_jobs(grid.x, 3 + sc->lights.n);   // GROUP: the diffuse cones are one job
     VCT_CUDA(cudaEventRecord(dev->ev[6], s));
-    if (count_samples) {
+    if (g->fmt == VCT_GRID_RGBA16F) {   // storage variant: the literal march with fp32 filtering of the half texels
+      if (count_samples) {
+        VCT_CUDA(cudaMemsetAsync(dev->counters + 16, 0, 8 * sizeof(unsigned long long), s));
+        cone_kernel<true, false, true><<<grid, 32 * kConeWarps, 0, s>>>(a);
+      } else {
+        cone_kernel<false, false, true><<<grid, 32 * kConeWarps, 0, s>>>(a);
+      }
+    } else if (count_samples) {
       VCT_CUDA(cudaMemsetAsync(dev->counters + 16, 0, 8 * sizeof(unsigned long long), s));
       cone_kernel<true, false><<<grid, 32 * kConeWarps, 0, s>>>(a);
     } else if (variant == 0) {

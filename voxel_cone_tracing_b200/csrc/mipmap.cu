@@ -21,6 +21,8 @@
 // Arithmetic = oracle rules R5/R6, bit-exact: see mip_arith.cuh (integer dot products, ties replayed in fp32; texels with
 // many ties fall back to the fp32 recipe).  All-zero child groups are skipped (exact: the filter of zeros is zero);
 // mip_generic_kernel / occ_*_kernel cover grids the fused kernel does not (R < 32 or fewer than 6 levels).
+#include <cuda_fp16.h>
+
 #include "mip_arith.cuh"
 #include "vct_internal.cuh"
 
@@ -1144,6 +1146,62 @@ mip_tail_kernel(const TailArgs a) {
   if (warp < a.word_warps3) occ_words_from_bytes(a.occ, a.occb + a.occ.occb_off[3], 3, warp, t & 31);
 }
 
+// ---------------------------------------------------------------------------------------------
+// RGBA16F storage variant (vct_grid_create_ex; BASELINE.json config 5): one level per launch, one thread per (destination texel, direction),
+// the fp32 recipe of mipmap.comp on exactly converted halves, clamp to [0,1] (the unorm store of the reference), round to half.  A plain
+// kernel: the variant is there for coverage and parity, the RGBA8 path above is the one measured against the roofline.
+__device__ __forceinline__ void unpack_half4(unsigned long long c, float (&o)[4]) {
+#pragma unroll
+  for (int k = 0; k < 4; k++) o[k] = __half2float(__ushort_as_half((unsigned short)(c >> (16 * k))));
+}
+__global__ void mip_f16_kernel(const unsigned long long* const* __restrict__ table, int level_src, int Ns, int Nd, unsigned long long* const* __restrict__ dst_table_rw) {
+  const size_t n = (size_t)Nd * Nd * Nd * 6;
+  for (size_t u = (size_t)blockIdx.x * blockDim.x + threadIdx.x; u < n; u += (size_t)gridDim.x * blockDim.x) {
+    const int d = (int)(u % 6);
+    const size_t tex = u / 6;
+    const int x = (int)(tex % Nd), y = (int)((tex / Nd) % Nd), z = (int)(tex / ((size_t)Nd * Nd));
+    const unsigned long long* src = table[level_src * 6 + d];
+    float c[8][4];
+#pragma unroll
+    for (int dz = 0; dz < 2; dz++)
+#pragma unroll
+      for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+        for (int dx = 0; dx < 2; dx++) unpack_half4(src[((size_t)(2 * z + dz) * Ns + (2 * y + dy)) * Ns + (2 * x + dx)], c[child_id(dx, dy, dz)]);
+    const uint32_t word = mip_pair_word(d >> 1);
+    const uint32_t fronts = (d & 1) ? word >> 16 : word & 0xFFFFu, backs = (d & 1) ? word & 0xFFFFu : word >> 16;
+    unsigned long long out = 0ull;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      float sum = 0.f;
+#pragma unroll
+      for (int p = 0; p < 4; p++) {
+        const int f = (int)((fronts >> (4 * p)) & 7u), b = (int)((backs >> (4 * p)) & 7u);
+        // dynamic child index on a register array would go to local memory: select
+        float fk = 0.f, fa = 0.f, bk = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) { if (i == f) { fk = c[i][k]; fa = c[i][3]; } if (i == b) bk = c[i][k]; }
+        const float v = __fadd_rn(fk, __fmul_rn(__fadd_rn(1.0f, -fa), bk));
+        sum = p == 0 ? v : __fadd_rn(sum, v);
+      }
+      const float r = fminf(fmaxf(__fdiv_rn(sum, 4.0f), 0.0f), 1.0f);
+      out |= (unsigned long long)__half_as_ushort(__float2half_rn(r)) << (16 * k);
+    }
+    dst_table_rw[(level_src + 1) * 6 + d][tex] = out;
+  }
+}
+__global__ void __launch_bounds__(256)
+occ_bits_f16_kernel(const unsigned long long* __restrict__ src, uint32_t* __restrict__ occ0, size_t n) {
+  const int lane = threadIdx.x & 31;
+  const size_t n_warps = ((size_t)gridDim.x * blockDim.x) >> 5;
+  for (size_t w = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w * 32 < n; w += n_warps) {
+    const size_t i = w * 32 + lane;
+    const unsigned long long any = i < n ? src[i] : 0ull;
+    const uint32_t bal = __ballot_sync(0xffffffffu, any != 0ull);
+    if (lane == 0) occ0[w] = bal;
+  }
+}
+
 bool mip_fused_applies(int R, int levels) { return R >= 32 && levels >= 6; }
 
 int launch_mipmap(vct_device* dev, vct_grid* g) {
@@ -1154,7 +1212,15 @@ int launch_mipmap(vct_device* dev, vct_grid* g) {
   oa.R = R; oa.levels = g->levels; oa.src0 = g->base; oa.occb = g->occb;
   for (int l = 0; l < VCT_MAX_LEVELS; l++) { oa.occ[l] = g->occ[l]; oa.docc[l] = g->docc[l]; oa.occb_off[l] = g->occb_off[l]; }
 
-  if (mip_fused_applies(R, g->levels)) {
+  if (g->fmt == VCT_GRID_RGBA16F) {
+    for (int l = 0; l + 1 < g->levels; l++) {
+      const int Ns = max(R >> l, 1), Nd = R >> (l + 1);
+      if (Nd < 1) break;
+      const size_t n = (size_t)Nd * Nd * Nd * 6;
+      mip_f16_kernel<<<grid_for(n), 256, 0, s>>>(g->f16_table, l, Ns, Nd, const_cast<unsigned long long* const*>(reinterpret_cast<const unsigned long long* const*>(g->f16_table)));
+    }
+    occ_bits_f16_kernel<<<grid_for((size_t)R * R * R, 256, 148 * 8), 256, 0, s>>>(reinterpret_cast<const unsigned long long*>(g->base), g->occ[0], (size_t)R * R * R);
+  } else if (mip_fused_applies(R, g->levels)) {
     StreamArgs fa;
     memset(&fa, 0, sizeof fa);
     fa.base = g->base; fa.R = R; fa.levels = g->levels; fa.surf = g->surf;
@@ -1209,14 +1275,14 @@ int launch_mipmap(vct_device* dev, vct_grid* g) {
   }
 
   // ---- generic path (small grids / short chains): one launch per level ----
-  for (int l = 0; l + 1 < g->levels; l++) {
+  for (int l = 0; l + 1 < g->levels && g->fmt == VCT_GRID_RGBA8; l++) {
     const int Ns = max(R >> l, 1), Nd = R >> (l + 1);
     if (Nd < 1) break;
     const size_t n = (size_t)Nd * Nd * Nd * 6;
     mip_generic_kernel<<<grid_for(n), 256, 0, s>>>(l == 0 ? g->base : nullptr, l == 0 ? 0 : g->surf.s[l], l == 0 ? 0 : g->surf.pitch[l], g->surf.s[l + 1],
                                                   g->surf.pitch[l + 1], Ns, Nd);
   }
-  occ_bits_kernel<<<grid_for((size_t)R * R * R, 256, 148 * 8), 256, 0, s>>>(oa);
+  if (g->fmt == VCT_GRID_RGBA8) occ_bits_kernel<<<grid_for((size_t)R * R * R, 256, 148 * 8), 256, 0, s>>>(oa);
   int small_first = 1;
   for (; small_first < g->levels && (R >> small_first) >= 64; small_first++) {
     int logN = 0;

@@ -106,6 +106,7 @@ extern "C" {
 
 int vct_peer_export(vct_device_t* dev, vct_grid_t* g, vct_target_t* t, vct_peer_handle_t* out) {
   VCT_REQUIRE(dev && g && t && out, "null argument");
+  VCT_REQUIRE(g->fmt == VCT_GRID_RGBA8, "the multi-GPU exchange handles RGBA8 grids only");
   VCT_CUDA(cudaSetDevice(dev->ordinal));
   const size_t n0 = (size_t)g->R * g->R * g->R * 4;
   if (!g->base_buf[1]) {

@@ -103,6 +103,9 @@ struct GridView {
   const uint32_t* docc_all;
   uint4 occ_tab[VCT_MAX_LEVELS];
   int R, levels;
+  // RGBA16F storage variant (vct_grid_create_ex): f16[level * 6 + dir] = linear (R >> level)^3 texels of four halves (level 0: the same
+  // buffer for every dir = base); nullptr for RGBA8 grids
+  const unsigned long long* const* f16;
 };
 
 // Occupancy bits (built by the mip stage, read by the cone tracer to skip all-zero filter footprints):
@@ -263,6 +266,9 @@ struct vct_scene {
 struct vct_grid {
   vct_device* dev = nullptr;
   int R = 0, levels = 0;
+  int fmt = 0;                          // VCT_GRID_RGBA8 / VCT_GRID_RGBA16F
+  unsigned long long* f16_lvl[VCT_MAX_LEVELS][6] = {};   // RGBA16F: levels 1.. per direction (linear); level 0 = base (8 bytes per voxel)
+  const unsigned long long** f16_table = nullptr;        // the same pointers in device memory: [level * 6 + dir]
   uint32_t* base = nullptr;             // level 0 of the current frame
   uint32_t* base_buf[2] = {};           // base_buf[0] == the allocation; base_buf[1] only in multi-GPU mode (double buffering)
   size_t bytes = 0;
@@ -304,6 +310,7 @@ struct vct_grid {
     for (int i = 0; i < VCT_MAX_LEVELS; i++) { v.docc[i] = docc[i]; v.pitch[i] = surf.pitch[i]; }
     v.tex_lin = tex_lin; v.tex_one = tex_one; v.tex_pt = tex_pt; v.tex_zs = tex_zs;
     v.docc_all = docc_all;
+    v.f16 = f16_table;
     for (int l = 0; l < VCT_MAX_LEVELS; l++) {
       const int N = l < levels ? (R >> l) : 0;
       const float fN = (float)N;

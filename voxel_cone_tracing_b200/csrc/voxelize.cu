@@ -21,6 +21,8 @@
 //                         `fresh` fragments instead of the whole level.
 // Built with -fmad=false: the arithmetic (IEEE add/mul/div/sqrt only, fixed evaluation order) is the
 // same as the oracle's so that voxel occupancy AND colour match bit for bit.
+#include <cuda_fp16.h>
+
 #include "raster.cuh"
 
 namespace vct {
@@ -78,6 +80,7 @@ struct FragCtx {
   // VCT_ACCUM_FIXED_POINT (non-reference variant): two 64-bit accumulators per arena slot; the slot of a voxel's FIRST fragment collects
   // the whole voxel: word 0 = sum R | sum G << 24 | count << 48, word 1 = sum B | sum A << 24.  nullptr = the reference's ordered mode.
   unsigned long long* accum;
+  int vstride;         // 32-bit words per voxel of `base`: 1 (RGBA8) or 2 (RGBA16F: the low word doubles as the claim word until the resolve pass)
 };
 
 // Interpolated position of a covered pixel and its voxel (voxelize.frag:156-157: truncation, then the image bounds check;
@@ -103,7 +106,7 @@ __device__ __forceinline__ void push_fragment(const FragCtx& c, const VoxTri& v,
   if (c.accum) {
     // order-independent integer accumulation: the first fragment to arrive claims the voxel (the grid word holds its slot until the resolve
     // pass), every fragment adds its rounded colour to that slot's accumulators.  24-bit sums, 16-bit count: exact up to 65535 fragments.
-    const uint32_t prev = atomicCAS(&c.base[voxel], 0u, idx + 1u);
+    const uint32_t prev = atomicCAS(&c.base[(size_t)voxel * c.vstride], 0u, idx + 1u);
     const uint32_t owner = prev ? prev - 1u : idx;
     c.fresh[idx] = prev == 0u ? 1 : 0;
     if (prev == 0u) c.frags[idx].voxel = voxel;
@@ -357,7 +360,7 @@ sparse_clear_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ fra
 __global__ void __launch_bounds__(128)
 vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frags, const uint8_t* __restrict__ fresh,
                    uint32_t* __restrict__ counters, uint32_t frag_capacity, const PeerView pv, uint8_t* __restrict__ tile_touched, int logR,
-                   uint32_t* __restrict__ status, unsigned long long* __restrict__ accum) {
+                   uint32_t* __restrict__ status, unsigned long long* __restrict__ accum, int fmt16) {
   // arena too small: fragments were dropped.  Tell the host through the mapped status word (the only time this kernel touches host memory)
   if (blockIdx.x == 0 && threadIdx.x == 0 && counters[CNT_FRAGS] > frag_capacity) {
     *reinterpret_cast<volatile uint32_t*>(status + STATUS_OVERFLOW) = counters[CNT_FRAGS];
@@ -389,6 +392,15 @@ vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frag
       n = (uint32_t)(a0 >> 48);
       const uint32_t h = n >> 1, s0 = (uint32_t)(a0 & 0xFFFFFFu), s1 = (uint32_t)((a0 >> 24) & 0xFFFFFFu), s2 = (uint32_t)(a1 & 0xFFFFFFu), s3 = (uint32_t)((a1 >> 24) & 0xFFFFFFu);
       stored = ((s0 + h) / n) | ((s1 + h) / n) << 8 | ((s2 + h) / n) << 16 | ((s3 + h) / n) << 24;
+      if (fmt16) {
+        // RGBA16F storage variant: the mean colour in [0,1] rounded to half (same expression as the oracle, IEEE division)
+        const float dn = (float)n * 255.0f;
+        const unsigned long long h0 = __half_as_ushort(__float2half_rn((float)s0 / dn)), h1 = __half_as_ushort(__float2half_rn((float)s1 / dn));
+        const unsigned long long h2 = __half_as_ushort(__float2half_rn((float)s2 / dn)), h3 = __half_as_ushort(__float2half_rn((float)s3 / dn));
+        reinterpret_cast<unsigned long long*>(base)[voxel] = h0 | (h1 << 16) | (h2 << 32) | (h3 << 48);
+        max_list = max(max_list, n);
+        continue;
+      }
     } else {
     const uint32_t head = base[voxel];
     unsigned long long keys[kSortMax];
@@ -487,7 +499,7 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
   }
   cudaStream_t s = dev->stream;
   unsigned long long* accum = nullptr;
-  if (dev->accum_mode == VCT_ACCUM_FIXED_POINT) {
+  if (dev->accum_mode == VCT_ACCUM_FIXED_POINT || g->fmt == VCT_GRID_RGBA16F) {   // (an fp16 grid always accumulates in fixed point)
     if (dev->accum_capacity < dev->frag_capacity) {   // (re)allocated zeroed; the resolve pass zeroes what a frame used
       if (dev->accum) { VCT_CUDA(cudaStreamSynchronize(s)); cudaFree(dev->accum); dev->accum = nullptr; dev->accum_capacity = 0; }
       VCT_CUDA(cudaMalloc(&dev->accum, dev->frag_capacity * 2 * sizeof(unsigned long long)));
@@ -515,13 +527,14 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
     ctx.mats = sc->mats; ctx.L = sc->lights; ctx.cube_size = sc->cube_size; ctx.R = g->R; ctx.z0 = z0; ctx.z1 = z1;
     ctx.base = g->base; ctx.frags = dev->frags; ctx.frag_capacity = (uint32_t)dev->frag_capacity; ctx.fresh = dev->fresh; ctx.counters = dev->counters;
     ctx.accum = accum;
+    ctx.vstride = g->fmt == VCT_GRID_RGBA16F ? 2 : 1;
     vox_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, sc->cube_size, g->R, z0, z1, tris,
                                                           dev->rs[0].item_local, dev->rs[0].item_block, ctx, sc->n_tris >= kSmallPathMinTris ? kSmallPixels : 0,
                                                           sc->n_tris >= kSmallPathMinTris ? kMidPixels : 0, dev->counters + CNT_TICKET_VOX, dev->counters + CNT_ITEMS);
     vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->rs[0].item_local, dev->rs[0].item_block, n_blocks, ctx);
   }
   vox_resolve_kernel<<<sms * 8, 128, 0, s>>>(g->base, dev->frags, dev->fresh, dev->counters, (uint32_t)dev->frag_capacity, pv, touched, log2_int(g->R),
-                                             dev->status_dev, accum);
+                                             dev->status_dev, accum, g->fmt == VCT_GRID_RGBA16F ? 1 : 0);
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;
 }

@@ -118,10 +118,17 @@ void Renderer::set_grid_resolution(unsigned int res) {
   m_resolution = res;
   if (!m_device.ok()) return;
   if (m_grid) { vct_grid_destroy(m_grid); m_grid = nullptr; }
-  // always 7 levels in the reference (renderer.cpp:186); glTexStorage3D rejects more than log2(res)+1, so clamp
+  // always 7 levels in the reference (renderer.cpp:186); glTexStorage3D rejects more than log2(res)+1, so clamp.
+  // set_grid_storage() can ask for the full chain (m_grid_levels = 0) and for RGBA16F texels instead (BASELINE config 5's variant).
+  const int want = m_grid_levels > 0 ? m_grid_levels : (m_grid_format == VCT_GRID_RGBA16F ? VCT_MAX_LEVELS_HOST : 7);
   int levels = 1;
-  while (levels < 7 && (res >> levels) >= 1) levels++;
-  check(vct_grid_create(m_device.handle(), (int)res, levels, &m_grid), "vct_grid_create");
+  while (levels < want && (res >> levels) >= 1) levels++;
+  check(vct_grid_create_ex(m_device.handle(), (int)res, levels, m_grid_format, &m_grid), "vct_grid_create_ex");
+}
+
+void Renderer::set_grid_storage(int vct_grid_format, int levels) {
+  m_grid_format = vct_grid_format; m_grid_levels = levels;
+  if (m_resolution) set_grid_resolution((unsigned int)m_resolution);
 }
 
 void Renderer::set_grid_size(float size) { m_cube_size = size; }
