@@ -466,7 +466,7 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    rig = Rig(cfg, args, rank, world, local_rank, torch, dist)
+    rig = Rig(cfg, args, rank, world, local_rank, torch, dist, fp16=args.fp16)
     pipe = rig.pipe
     # ---- timed region: exactly K frames after >= 3 warm-up frames, CUDA events on the launching stream, max over ranks ----
     sampler = ClockSampler(local_rank)
@@ -493,7 +493,7 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
                 print(f"e2e leg failed: {ex}", file=sys.stderr)
 
     roof, stages = None, None
-    if world == 1:
+    if world == 1 and not args.fp16:
         cnt = pipe.trace_count(rig.view, rig.prm)
         roof = cone_roofline(rig, stage_acc["cone_kernel"], (clocks or {}).get("sm_mhz"), cnt)
         stages = {k + "_us": v for k, v in stage_acc.items()}
@@ -507,7 +507,7 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
         stages["shaded_pixels"] = int(cnt.shaded_pixels)
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not args.fp16:
         wl = CpuWorkload(cfg)
         stride = wl.pick_stride(4, 16.0)
         ts = [wl.trace_step(stride, i)[0] for i in range(4)]
@@ -518,7 +518,7 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
     n_tris = rig.sc.n_triangles
     rig.close()
     extra = None
-    if not args.no_extra and args.config == 2 and (world == 1 or args.exchange == "p2p"):
+    if not args.no_extra and args.config == 2 and not args.fp16 and (world == 1 or args.exchange == "p2p"):
         extra = {str(c): run_extra(c, args, rank, world, local_rank, torch, dist) for c in (4, 5)}
         if world == 1:   # config 5 as BASELINE.json states it: fp16 RGBA grid + full mip chain (single GPU: the exchange is RGBA8 only)
             extra["5_fp16_full_chain"] = run_extra(5, args, rank, world, local_rank, torch, dist, fp16=True)
@@ -526,7 +526,7 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
     if rank == 0:
         out = {"metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 RGBA storage)",
-               "data": "synthetic", "config": config_dict(cfg, world, args.sampler, args.exchange, n_tris),
+               "data": "synthetic", "config": dict(config_dict(cfg, world, args.sampler, args.exchange, n_tris), **({"storage": "RGBA16F, full mip chain (variant)"} if args.fp16 else {})),
                "clocks": clocks, "e2e": e2e, "gpu_launches": KERNELS_PER_FRAME * args.steps, "roofline": roof, "cpu_baseline": cpu}
         if stages:
             out["stages"] = stages
@@ -546,6 +546,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--fp16", action="store_true", help="run the chosen config with the RGBA16F grid + full mip chain storage variant (one GPU; not the headline)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the device-timed runs of configs 4 and 5 (extra_configs)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],

@@ -99,6 +99,27 @@ def test_config5_four_million_triangles_1024_8k_16_cones():
     assert info["fragments"] > 20_000_000
 
 
+def test_fp16_full_chain_variant_256_1080p():
+    """BASELINE config 5's storage variant (RGBA16F texels, full mip chain) at config 2's size: 256^3, 9 levels, 1920x1080 -- voxels and all
+    48 mip volumes bit-exact against the oracle in the same variant mode, frame on every 8th 32x32 tile"""
+    sc = S.cornell_scene(with_suzanne=True)
+    R, W, H, levels, stride = 256, 1920, 1080, 9, 8
+    view, proj = S.reference_camera(W / H)
+    exp_base, st = orc.voxelize(sc, R, accum_mode=orc.ACCUM_FP16)
+    pyr = orc.mipmap(exp_base, levels, orc.FMT_RGBA16F)
+    p = capi.Pipeline(sc, R, W, H, levels, fmt=capi.GRID_RGBA16F)
+    p.render_frame(view, proj, capi.default_params())
+    assert np.array_equal(p.grid.download_f16(0), exp_base)
+    for l in range(1, levels):
+        for d in range(6):
+            assert np.array_equal(p.grid.download_f16(l, d), pyr.levels[d][l]), f"fp16 level {l} dir {d}"
+    eg = orc.gbuffer(sc, view, proj, W, H)
+    exp_frame, _ = orc.trace(sc, view, eg, pyr, orc.default_params(), stride, 1)
+    mx, ps = _check_frame_tiles(p.target.frame(), exp_frame, _tile_mask(W, H, stride, 1))
+    print("fp16 variant 256^3 / 9 levels / 1080p: frame max abs", mx, "PSNR", round(ps, 1), "dB; grid bytes", p.grid.nbytes)
+    p.close()
+
+
 def _tiled_random_grid(R, seed=1):
     """R^3 words that differ everywhere but cost one 256^3 draw: a random 256^3 block repeated with a per-block XOR constant"""
     rng = np.random.default_rng(seed)
