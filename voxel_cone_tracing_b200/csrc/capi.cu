@@ -840,8 +840,9 @@ static int render_frame_sharded(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* 
   VCT_CUDA(cudaStreamWaitEvent(dev->stream2, dev->ev_fork, 0));
   dev->stream = dev->stream2;
   VCT_CUDA(cudaEventRecord(dev->ev_g0, dev->stream2));
-  rc = launch_gbuffer(dev, sc, view, proj, t, pv.rank, pv.nranks);
-  if (!rc) rc = launch_cone_trace(dev, sc, g, view, &prm, t, false, &pv, 1);
+  const bool fused_list = prm.view_voxel_dir >= 7;   // the G-buffer resolve builds the live-tile list (the debug view shades every tile: no list)
+  rc = launch_gbuffer(dev, sc, view, proj, t, pv.rank, pv.nranks, fused_list);
+  if (!rc && !fused_list) rc = launch_cone_trace(dev, sc, g, view, &prm, t, false, &pv, 1);
   dev->stream = s;
   if (rc) return rc;
   VCT_CUDA(cudaEventRecord(dev->ev_g1, dev->stream2));
@@ -879,8 +880,9 @@ int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_targ
   VCT_CUDA(cudaStreamWaitEvent(dev->stream2, dev->ev_fork, 0));
   dev->stream = dev->stream2;
   VCT_CUDA(cudaEventRecord(dev->ev_g0, dev->stream2));
-  rc = launch_gbuffer(dev, sc, view, proj, t);
-  if (!rc) rc = launch_cone_trace(dev, sc, g, view, p, t, false, nullptr, 1);   // the live-tile list needs the G-buffer only
+  const bool fused_list = p->view_voxel_dir >= 7;   // the G-buffer resolve builds the live-tile list (the debug view shades every tile: no list)
+  rc = launch_gbuffer(dev, sc, view, proj, t, 0, 1, fused_list);
+  if (!rc && !fused_list) rc = launch_cone_trace(dev, sc, g, view, p, t, false, nullptr, 1);
   dev->stream = s;
   if (rc) return rc;
   VCT_CUDA(cudaEventRecord(dev->ev_g1, dev->stream2));

@@ -336,83 +336,155 @@ __device__ __noinline__ void cam_resolve_clipped(const vct_vertex_t* __restrict_
 // smaller key only if its triangle id is smaller than 0xFFFFFFFF, so mask it explicitly below.
 constexpr unsigned long long kVisClear = ((unsigned long long)0x3F800000u << 32) | 0xFFFFFFFFull;
 
-__global__ void __launch_bounds__(256)
+// what the resolve kernel needs to build the cone tracer's live-tile list on the way (optional: list == nullptr)
+struct TileListOut {
+  uint32_t* list;          // [n] 8x4 tiles (index ty * tiles_x + tx) that hold at least one pixel the cone tracer shades
+  uint32_t* count;         // zeroed by the clear kernel of this pass
+  uint32_t* work_counter;  // the persistent cone kernel's work counter: reset here for the frame
+  float cube_size;
+};
+
+// the piece of the winning triangle that covers pixel (i, j) when the triangle has no record (or the record array overflowed): vertex stage
+// again; out of line in the LEAN instantiation (small scenes: every triangle has a record, the path is dead weight in registers there)
+__device__ __forceinline__ void cam_resolve_recompute(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ dp, uint32_t ti,
+                                                      const float* __restrict__ pvm, int W, int H, int i, int j, float (&b)[3], float (&iw)[3], float (&world)[3][3],
+                                                      float (&nn)[3][3]) {
+  ClipVert in[3];
+  float dn[3];
+  const int n_out = cam_vertex_stage(verts, indices, *dp, ti, pvm, in, dn);
+  if (n_out == 0) {   // registers only
+    CamTri pc;
+    cam_make_piece(in[0], in[1], in[2], W, H, dp->material, pc);
+    raster_sample(pc.rt, i, j, b);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      iw[k] = pc.iw[k];
+#pragma unroll
+      for (int c = 0; c < 3; c++) { world[k][c] = pc.world[k][c]; nn[k][c] = pc.nn[k][c]; }
+    }
+  } else {
+    ResolvedPiece rp;
+    cam_resolve_clipped(verts, indices, dp, ti, pvm, W, H, i, j, &rp);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      b[k] = rp.b[k]; iw[k] = rp.iw[k];
+#pragma unroll
+      for (int c = 0; c < 3; c++) { world[k][c] = rp.world[k][c]; nn[k][c] = rp.nn[k][c]; }
+    }
+  }
+}
+__device__ __noinline__ void cam_resolve_recompute_out_of_line(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ dp,
+                                                               uint32_t ti, const float* __restrict__ pvm, int W, int H, int i, int j, ResolvedPiece* out) {
+  float b[3], iw[3], world[3][3], nn[3][3];
+  cam_resolve_recompute(verts, indices, dp, ti, pvm, W, H, i, j, b, iw, world, nn);
+  for (int k = 0; k < 3; k++) {
+    out->b[k] = b[k]; out->iw[k] = iw[k];
+    for (int c = 0; c < 3; c++) { out->world[k][c] = world[k][c]; out->nn[k][c] = nn[k][c]; }
+  }
+}
+
+// One warp per 8 x 4 pixel tile (the cone tracer's unit), kResolveTiles consecutive tiles per warp: world position and interpolated normal
+// of the winning triangle per pixel, and -- fused here, it was a launch of its own -- the list of tiles with at least one pixel to shade
+// (voxel_cone_tracing.frag:248-251: hit, and inside the grid cube), appended with one atomic per warp.
+constexpr int kResolveTiles = 4;
+template <bool LEAN>
+__global__ void __launch_bounds__(256, LEAN ? 4 : 1)   // LEAN: 64 registers -- the out-of-line recompute path (dead for small scenes) may spill
 cam_resolve_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ draws, uint32_t n_draws, Mat4 pv,
                    const CamTri* __restrict__ recs, const uint32_t* __restrict__ big_slot, const unsigned long long* vis, int W, int H, float* __restrict__ world_pos,
-                   float* __restrict__ normal, uint32_t* __restrict__ material, unsigned long long* vis_out, int tile_rank, int tile_nranks) {
-  const size_t n = (size_t)W * H;
-  for (size_t px = (size_t)blockIdx.x * blockDim.x + threadIdx.x; px < n; px += (size_t)gridDim.x * blockDim.x) {
-    const int i = (int)(px % W), j = (int)(px / W);
-    if (!tile_owned(i, j, W, tile_rank, tile_nranks)) continue;   // pixels of other ranks' tiles are never read by this rank's tracer
-    unsigned long long key = vis[px];
-    uint32_t ti = (uint32_t)(key & 0xFFFFFFFFull);
-    // GL_LESS against the cleared depth 1.0: a fragment exactly at zw == 1.0 fails
-    if ((uint32_t)(key >> 32) >= 0x3F800000u) ti = VCT_NO_TRIANGLE;
-    if (ti == VCT_NO_TRIANGLE) {
-      if (vis_out) vis_out[px] = kVisClear;
-      material[px] = VCT_NO_TRIANGLE;
-      continue;
-    }
-    // the piece of the winning triangle that covers this pixel: from its records, or by running the vertex stage again
-    float b[3], iw[3], world[3][3], nn[3][3];
-    uint32_t mat = 0;
-    bool found = false;
-    const uint32_t bs = __ldg(big_slot + ti);
-    if (bs) {
-      uint32_t slot = (bs & 0x7FFFFFFFu) - 1u;
-      found = raster_sample(recs[slot].rt, i, j, b);
-      if (!found && (bs >> 31)) { slot++; found = raster_sample(recs[slot].rt, i, j, b); }
-      if (found) {
-        const CamTri& v = recs[slot];
+                   float* __restrict__ normal, uint32_t* __restrict__ material, unsigned long long* vis_out, int tile_rank, int tile_nranks, const TileListOut tl) {
+  const int lane = threadIdx.x & 31;
+  if (tl.list && blockIdx.x == 0 && threadIdx.x == 0) *tl.work_counter = 0u;   // the cone kernel of this frame starts at item 0
+  const int tiles_x = (W + 7) / 8, tiles_y = (H + 3) / 4, n_tiles = tiles_x * tiles_y;
+  const int n_groups = (n_tiles + kResolveTiles - 1) / kResolveTiles;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < n_groups; grp += warps) {
+    uint32_t live_mask = 0;
+#pragma unroll 1
+    for (int k = 0; k < kResolveTiles; k++) {
+      const int tile = grp * kResolveTiles + k;
+      if (tile >= n_tiles) break;
+      const int tile_x = tile % tiles_x, tile_y = tile / tiles_x;
+      const int i = tile_x * 8 + (lane & 7), j = tile_y * 4 + (lane >> 3);
+      bool live = false;
+      if (i < W && j < H && tile_owned(i, j, W, tile_rank, tile_nranks)) {   // pixels of other ranks' tiles are never read by this rank's tracer
+        const size_t px = (size_t)j * W + i;
+        const unsigned long long key = vis[px];
+        uint32_t ti = (uint32_t)(key & 0xFFFFFFFFull);
+        // GL_LESS against the cleared depth 1.0: a fragment exactly at zw == 1.0 fails
+        if ((uint32_t)(key >> 32) >= 0x3F800000u) ti = VCT_NO_TRIANGLE;
+        if (ti == VCT_NO_TRIANGLE) {
+          if (vis_out) vis_out[px] = kVisClear;
+          material[px] = VCT_NO_TRIANGLE;
+        } else {
+          // the piece of the winning triangle that covers this pixel: from its records, or by running the vertex stage again
+          float b[3], iw[3], world[3][3], nn[3][3];
+          uint32_t mat = 0;
+          bool found = false;
+          const uint32_t bs = __ldg(big_slot + ti);
+          if (bs) {
+            uint32_t slot = (bs & 0x7FFFFFFFu) - 1u;
+            found = raster_sample(recs[slot].rt, i, j, b);
+            if (!found && (bs >> 31)) { slot++; found = raster_sample(recs[slot].rt, i, j, b); }
+            if (found) {
+              const CamTri& v = recs[slot];
 #pragma unroll
-        for (int k = 0; k < 3; k++) {
-          iw[k] = v.iw[k];
+              for (int q = 0; q < 3; q++) {
+                iw[q] = v.iw[q];
 #pragma unroll
-          for (int c = 0; c < 3; c++) { world[k][c] = v.world[k][c]; nn[k][c] = v.nn[k][c]; }
+                for (int c = 0; c < 3; c++) { world[q][c] = v.world[q][c]; nn[q][c] = v.nn[q][c]; }
+              }
+              mat = v.material;
+            }
+          }
+          if (!found) {   // no record (sub-tile triangle), or the pixel belongs to a piece that was rasterised in line
+            const DrawRec* dp = draws + find_draw(ti, draws, n_draws);
+            if (LEAN) {
+              ResolvedPiece rp;
+              cam_resolve_recompute_out_of_line(verts, indices, dp, ti, pv.m, W, H, i, j, &rp);
+#pragma unroll
+              for (int q = 0; q < 3; q++) {
+                b[q] = rp.b[q]; iw[q] = rp.iw[q];
+#pragma unroll
+                for (int c = 0; c < 3; c++) { world[q][c] = rp.world[q][c]; nn[q][c] = rp.nn[q][c]; }
+              }
+            } else {
+              cam_resolve_recompute(verts, indices, dp, ti, pv.m, W, H, i, j, b, iw, world, nn);
+            }
+            mat = dp->material;
+          }
+          const float q3[3] = {b[0] * iw[0], b[1] * iw[1], b[2] * iw[2]};
+          const float qs = (q3[0] + q3[1]) + q3[2];
+          float wp[3];
+#pragma unroll
+          for (int c = 0; c < 3; c++) {
+            wp[c] = interp3(q3, world[0][c], world[1][c], world[2][c]) / qs;
+            world_pos[px * 3 + c] = wp[c];
+            normal[px * 3 + c] = interp3(q3, nn[0][c], nn[1][c], nn[2][c]) / qs;
+          }
+          material[px] = mat;
+          // the tracer's within_cube test (load_pixel in cone_trace.cu: same expression, same inputs)
+          const float p0 = 0.5f * (wp[0] / tl.cube_size) + 0.5f, p1 = 0.5f * (wp[1] / tl.cube_size) + 0.5f, p2 = 0.5f * (wp[2] / tl.cube_size) + 0.5f;
+          live = fabsf(p0) < 1.0f && fabsf(p1) < 1.0f && fabsf(p2) < 1.0f;
         }
-        mat = v.material;
       }
+      if (__any_sync(0xffffffffu, live)) live_mask |= 1u << k;
     }
-    if (!found) {   // no record (sub-tile triangle), or the pixel belongs to a piece that was rasterised in line
-      const DrawRec* dp = draws + find_draw(ti, draws, n_draws);
-      ClipVert in[3];
-      float dn[3];
-      const int n_out = cam_vertex_stage(verts, indices, *dp, ti, pv.m, in, dn);
-      if (n_out == 0) {   // registers only
-        CamTri pc;
-        cam_make_piece(in[0], in[1], in[2], W, H, dp->material, pc);
-        raster_sample(pc.rt, i, j, b);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          iw[k] = pc.iw[k];
-#pragma unroll
-          for (int c = 0; c < 3; c++) { world[k][c] = pc.world[k][c]; nn[k][c] = pc.nn[k][c]; }
-        }
-      } else {
-        ResolvedPiece rp;
-        cam_resolve_clipped(verts, indices, dp, ti, pv.m, W, H, i, j, &rp);
-#pragma unroll
-        for (int k = 0; k < 3; k++) {
-          b[k] = rp.b[k]; iw[k] = rp.iw[k];
-#pragma unroll
-          for (int c = 0; c < 3; c++) { world[k][c] = rp.world[k][c]; nn[k][c] = rp.nn[k][c]; }
-        }
-      }
-      mat = dp->material;
+    if (tl.list && live_mask) {
+      uint32_t base = 0;
+      if (lane == 0) base = atomicAdd(tl.count, (uint32_t)__popc(live_mask));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (lane < kResolveTiles && ((live_mask >> lane) & 1u)) tl.list[base + __popc(live_mask & ((1u << lane) - 1u))] = (uint32_t)(grp * kResolveTiles + lane);
     }
-    const float q3[3] = {b[0] * iw[0], b[1] * iw[1], b[2] * iw[2]};
-    const float qs = (q3[0] + q3[1]) + q3[2];
-#pragma unroll
-    for (int c = 0; c < 3; c++) {
-      world_pos[px * 3 + c] = interp3(q3, world[0][c], world[1][c], world[2][c]) / qs;
-      normal[px * 3 + c] = interp3(q3, nn[0][c], nn[1][c], nn[2][c]) / qs;
-    }
-    material[px] = mat;
   }
 }
 
 __global__ void fill_u64_kernel(unsigned long long* p, size_t n, unsigned long long v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+// the camera pass's clear: the visibility buffer plus its two counters (record count, live-tile count) in one launch
+__global__ void cam_clear_kernel(unsigned long long* p, size_t n, unsigned long long v, uint32_t* c0, uint32_t* c1) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+  if (blockIdx.x == 0 && threadIdx.x == 0) { if (c0) *c0 = 0u; if (c1) *c1 = 0u; }
 }
 __global__ void fill_u32_kernel(uint32_t* p, size_t n, uint32_t v) {
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
@@ -449,10 +521,17 @@ static void mat4_mul_host(const float* a, const float* b, float* out) {  // colu
     }
 }
 
-int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const float* proj, vct_target_t_* t, int tile_rank, int tile_nranks) {
+int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const float* proj, vct_target_t_* t, int tile_rank, int tile_nranks, bool tile_list) {
   cudaStream_t s = dev->stream;
   const size_t npx = (size_t)t->W * t->H;
-  fill_u64_kernel<<<dev->prop.multiProcessorCount * 8, 256, 0, s>>>(t->vis, npx, kVisClear);
+  const int n_tiles = ((t->W + 7) / 8) * ((t->H + 3) / 4);
+  if (tile_list && !t->tile_list) VCT_CUDA(cudaMalloc(&t->tile_list, ((size_t)n_tiles + 1) * sizeof(uint32_t)));
+  TileListOut tl;
+  memset(&tl, 0, sizeof tl);
+  tl.cube_size = sc->cube_size;
+  if (tile_list) { tl.list = t->tile_list + 1; tl.count = t->tile_list; tl.work_counter = dev->counters + CNT_CONE_WORK; }
+  uint32_t* rec_count = dev->counters + CNT_CAM_RECS;
+  cam_clear_kernel<<<dev->prop.multiProcessorCount * 8, 256, 0, s>>>(t->vis, npx, kVisClear, rec_count, tl.count);
   const int sms = dev->prop.multiProcessorCount;
   if (sc->n_tris) {
     // records only for the pieces that become work items: a compact array (a quarter of the triangles, at least 64 k); a scene
@@ -464,19 +543,24 @@ int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const floa
     mat4_mul_host(proj, view, pv.m);  // projection * view (voxel_cone_tracing.vert:25)
     const uint32_t n_blocks = (sc->n_tris + kSetupThreads - 1) / kSetupThreads;
     CamTri* recs = (CamTri*)dev->rs[1].tri_recs;
-    uint32_t* rec_count = dev->counters + CNT_CAM_RECS;
-    { int rc2 = launch_fill_u32(s, rec_count, 1, 0u); if (rc2) return rc2; }
+    const bool many = sc->n_tris >= kSmallPathMinTris;
     cam_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, pv, t->W, t->H, recs, (uint32_t)rec_capacity, rec_count,
                                                         dev->rs[1].big_slot, dev->rs[1].item_local, dev->rs[1].item_block, t->vis, tile_rank, tile_nranks,
-                                                        sc->n_tris >= kSmallPathMinTris ? kSmallCamPixels : 0, sc->n_tris >= kSmallPathMinTris ? kMidCamPixels : 0,
-                                                        dev->counters + CNT_TICKET_CAM,
+                                                        many ? kSmallCamPixels : 0, many ? kMidCamPixels : 0, dev->counters + CNT_TICKET_CAM,
                                                         dev->counters + CNT_CAM_ITEMS);
     cam_raster_kernel<<<sms * 8, 256, 0, s>>>(recs, dev->rs[1].big_slot, sc->n_tris, dev->rs[1].item_local, dev->rs[1].item_block, n_blocks, t->W, t->vis, dev->counters,
                                               tile_rank, tile_nranks);
-    cam_resolve_kernel<<<sms * 8, 256, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, pv, recs, dev->rs[1].big_slot, t->vis, t->W, t->H, t->world_pos, t->normal,
-                                               t->material, t->vis, tile_rank, tile_nranks);
+    const int groups = (n_tiles + kResolveTiles - 1) / kResolveTiles;
+    const int blocks = min((groups + 7) / 8, sms * 8);
+    if (many)
+      cam_resolve_kernel<false><<<blocks, 256, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, pv, recs, dev->rs[1].big_slot, t->vis, t->W, t->H, t->world_pos,
+                                                       t->normal, t->material, t->vis, tile_rank, tile_nranks, tl);
+    else
+      cam_resolve_kernel<true><<<blocks, 256, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, pv, recs, dev->rs[1].big_slot, t->vis, t->W, t->H, t->world_pos,
+                                                      t->normal, t->material, t->vis, tile_rank, tile_nranks, tl);
   } else {
     launch_fill_u32(s, t->material, npx, VCT_NO_TRIANGLE);
+    if (tile_list) launch_fill_u32(s, dev->counters + CNT_CONE_WORK, 1, 0u);
   }
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;

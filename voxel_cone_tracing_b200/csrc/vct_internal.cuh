@@ -368,7 +368,8 @@ int ensure_pushed_lists(vct_device* dev);
 int check_status(vct_device* dev);   // VCT_ERR_OVERFLOW / VCT_ERR_CUDA if a kernel reported an arena overflow / a peer timeout since the last check
 int launch_mipmap(vct_device* dev, vct_grid* g);
 bool mip_fused_applies(int R, int levels);   // the fused mip kernel (32x8x8 tiles, 32^3 blocks) handles this grid
-int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const float* proj, vct_target_t_* t, int tile_rank = 0, int tile_nranks = 1);
+// tile_list: the resolve kernel also builds the cone tracer's live-tile list (and resets its work counter): launch_cone_trace phase 2 may follow directly
+int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const float* proj, vct_target_t_* t, int tile_rank = 0, int tile_nranks = 1, bool tile_list = false);
 // phase: 0 = tile list + cones + shade; 1 = the live-tile list only (depends on the G-buffer alone: vct_render_frame builds it on the
 // G-buffer stream); 2 = cones + shade with the list of a preceding phase-1 call
 int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* view, const vct_trace_params_t* p, vct_target_t_* t,
