@@ -185,6 +185,8 @@ int vct_last_frame_timings(vct_device_t* dev, float out_ms[8]);
 #define VCT_DEBUG_MIP_DENSE 1
 #define VCT_DEBUG_CONE_VARIANT 2
 #define VCT_DEBUG_CONE_GRID 3
+#define VCT_DEBUG_CONE_RESERVE_SMS 4
+#define VCT_DEBUG_TRACE_LOW_PRIORITY 5
 int vct_debug_set(vct_device_t* dev, int key, int value);
 
 /* ---- multi-GPU (no reference counterpart: the reference is single-GPU).  One process per GPU on one node; the exchange

@@ -10,11 +10,14 @@ R, W, H = 256, 1920, 1080
 sc = S.cornell_scene()
 view, proj = S.reference_camera(W / H)
 prm = capi.default_params(sampler=1)
-pipes = [capi.Pipeline(sc, R, W, H) for _ in range(2)]
-for n_pipes, grid in ((1, 0), (1, 1), (2, 0), (2, 1)):
+pipes = [capi.Pipeline(sc, R, W, H) for _ in range(3)]
+cases = [(1, 0, 0, 0), (2, 0, 0, 0), (1, 0, 0, 1)] + [(2, 0, k, 1) for k in (0, 2, 4, 6, 8, 10, 12, 16, 24)] + [(3, 0, 8, 1), (2, 1, 0, 1)]
+for n_pipes, grid, reserve, low in cases:
     use = pipes[:n_pipes]
     for p in use:
         p.dev.debug_set(capi.DEBUG_CONE_GRID, grid)
+        p.dev.debug_set(capi.DEBUG_CONE_RESERVE_SMS, reserve)
+        p.dev.debug_set(capi.DEBUG_TRACE_LOW_PRIORITY, low)
     for _ in range(4):
         for p in use: p.render_frame(view, proj, prm)
     for p in use: p.sync()
@@ -26,6 +29,6 @@ for n_pipes, grid in ((1, 0), (1, 1), (2, 0), (2, 1)):
         p.render_frame(view, proj, prm)
     for p in use: p.sync()
     dt = time.perf_counter() - t0
-    print(f"{n_pipes} frame(s) in flight, cone_grid={grid}: {1e3 * dt / N:.3f} ms/frame ({N / dt:.0f} frames/s)", flush=True)
+    print(f"{n_pipes} frame(s) in flight, cone_grid={grid}, reserved SMs={reserve}, trace on low-priority stream={low}: {1e3 * dt / N:.3f} ms/frame ({N / dt:.0f} frames/s)", flush=True)
     print("   last frame of pipeline 0 (us):", {k: round(v * 1e3, 1) for k, v in use[0].timings().items()}, flush=True)
 for p in pipes: p.close()

@@ -174,7 +174,11 @@ int vct_device_create(int ordinal, vct_device_t** out) {
   for (int i = 0; i < STATUS_WORDS; i++) d->status_host[i] = 0u;
   VCT_CUDA(cudaHostGetDevicePointer((void**)&d->status_dev, (void*)d->status_host, 0));
   for (int i = 0; i < 8; i++) VCT_CUDA(cudaEventCreate(&d->ev[i]));
-  VCT_CUDA(cudaStreamCreateWithPriority(&d->stream2, cudaStreamNonBlocking, prio_lo));
+  // numerically lower = more urgent: [prio_hi, prio_lo].  The G-buffer stream sits between the critical path and the trace stream
+  VCT_CUDA(cudaStreamCreateWithPriority(&d->stream2, cudaStreamNonBlocking, prio_hi < prio_lo ? prio_hi + 1 : prio_lo));
+  VCT_CUDA(cudaStreamCreateWithPriority(&d->stream3, cudaStreamNonBlocking, prio_lo));
+  VCT_CUDA(cudaEventCreateWithFlags(&d->ev_front, cudaEventDisableTiming));
+  VCT_CUDA(cudaEventCreateWithFlags(&d->ev_trace, cudaEventDisableTiming));
   VCT_CUDA(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
   VCT_CUDA(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
   VCT_CUDA(cudaEventCreate(&d->ev_g0));
@@ -192,7 +196,8 @@ int vct_device_destroy(vct_device_t* d) {
   cudaFree(d->frags); cudaFree(d->fresh); cudaFree(d->accum);
   for (auto& r : d->rs) { cudaFree(r.tri_recs); cudaFree(r.item_local); cudaFree(r.item_block); cudaFree(r.big_slot); }
   if (d->stream2) { cudaStreamSynchronize(d->stream2); cudaStreamDestroy(d->stream2); }
-  for (cudaEvent_t e : {d->ev_fork, d->ev_join, d->ev_g0, d->ev_g1}) if (e) cudaEventDestroy(e);
+  if (d->stream3) { cudaStreamSynchronize(d->stream3); cudaStreamDestroy(d->stream3); }
+  for (cudaEvent_t e : {d->ev_fork, d->ev_join, d->ev_g0, d->ev_g1, d->ev_front, d->ev_trace}) if (e) cudaEventDestroy(e);
   cudaFree(d->counters); cudaFreeHost(d->counters_host); cudaFreeHost((void*)d->status_host);
   for (int i = 0; i < 8; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
   cudaStreamDestroy(d->stream);
@@ -751,6 +756,11 @@ int vct_debug_set(vct_device_t* dev, int key, int value) {
     case VCT_DEBUG_MIP_DENSE: dev->debug_mip_dense = value != 0; return VCT_OK;
     case VCT_DEBUG_CONE_VARIANT: VCT_REQUIRE(value >= -1 && value <= 3, "cone variant must be -1..3"); dev->debug_cone_variant = value; return VCT_OK;
     case VCT_DEBUG_CONE_GRID: dev->debug_cone_grid = value != 0; return VCT_OK;
+    case VCT_DEBUG_TRACE_LOW_PRIORITY: dev->trace_low_priority = value != 0; return VCT_OK;
+    case VCT_DEBUG_CONE_RESERVE_SMS:
+      VCT_REQUIRE(value >= 0 && value < dev->prop.multiProcessorCount, "reserved SM count out of range");
+      dev->cone_reserved_sms = value;
+      return VCT_OK;
   }
   set_error("vct_debug_set: unknown key %d", key);
   return VCT_ERR_INVALID;
@@ -895,7 +905,19 @@ int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_targ
     VCT_CUDA(cudaEventRecord(t->copy_gate, s));
     if ((rc = start_pending_readback(t, t->copy_gate))) return rc;
   }
-  if ((rc = launch_cone_trace(dev, sc, g, view, p, t, false, nullptr, 2))) return rc;
+  if (dev->trace_low_priority) {   // frames in flight: cones + shade on the low-priority stream, behind another pipeline's front half
+    VCT_CUDA(cudaEventRecord(dev->ev_front, s));
+    VCT_CUDA(cudaStreamWaitEvent(dev->stream3, dev->ev_front, 0));
+    dev->stream = dev->stream3;
+  }
+  rc = launch_cone_trace(dev, sc, g, view, p, t, false, nullptr, 2);
+  if (dev->trace_low_priority) {
+    dev->stream = s;
+    if (rc) return rc;
+    VCT_CUDA(cudaEventRecord(dev->ev_trace, dev->stream3));
+    VCT_CUDA(cudaStreamWaitEvent(s, dev->ev_trace, 0));
+  }
+  if (rc) return rc;
   VCT_CUDA(cudaEventRecord(dev->ev[5], s));
   dev->have_timings = true;
   dev->gbuffer_overlapped = true;

@@ -71,6 +71,7 @@ struct TraceArgs {
   int n_diffuse, n_slots;
   int n_jobs;                  // work items per live tile of cone_kernel_fast
   uint32_t* work_counter;      // next (job, tile) item of the persistent cone kernel; zeroed by tile_list_kernel
+  uint32_t first_reserved_sm;  // persistent cone kernel: CTAs placed on an SM with %smid >= this retire at once (SMs left to another frame's front half)
   int grouped;                 // cone_out layout: 0 = [slot][pixel]; 1 = [job][pixel] with job 0 = SUM of the diffuse cones, 1 specular, 2 refraction, 3 + i shadow of light i
   const uint32_t* tile_list;   // live 8x4 tiles (tile_y * tiles_x + tile_x), built by tile_list_kernel
   uint32_t* tile_count;
@@ -731,6 +732,11 @@ __device__ __forceinline__ void cone_work_item(const TraceArgs& a, uint32_t t, i
 template <bool TEX, bool SPLIT, int MIN_CTAS, bool GROUP>
 __global__ void __launch_bounds__(32 * kConeWarps, MIN_CTAS)
 cone_kernel_fast(const TraceArgs a) {
+  {
+    uint32_t smid;
+    asm("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (smid >= a.first_reserved_sm) return;
+  }
   const int lane = threadIdx.x & 31;
   const uint32_t n_live = *a.tile_count;
   const uint32_t total = n_live * (uint32_t)a.n_jobs;
@@ -964,6 +970,7 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
     } else {
       const bool persist = !dev->debug_cone_grid;
       const int sms = dev->prop.multiProcessorCount;
+      a.first_reserved_sm = (uint32_t)(sms - dev->cone_reserved_sms);
       a.n_jobs = a.grouped ? (int)grid_jobs.y : a.n_slots;
       // launch K<TEX, SPLIT, MIN_CTAS, GROUP>: persistent (MIN_CTAS CTAs per SM) or one warp per (tile, job) of the whole frame
 #define VCT_LAUNCH_CONE(TEXV, SPLITV, MINC, GROUPV)                                                                   \

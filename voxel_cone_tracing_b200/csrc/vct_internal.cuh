@@ -198,6 +198,9 @@ struct vct_device {
   } rs[2];
   // second stream: the G-buffer pass of a frame does not depend on the voxel grid and runs beside clear + voxelize + mip
   cudaStream_t stream2 = nullptr;
+  cudaStream_t stream3 = nullptr;    // lowest priority: the trace of a pipelined frame (trace_low_priority)
+  cudaEvent_t ev_front = nullptr, ev_trace = nullptr;
+  bool trace_low_priority = false;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_g0 = nullptr, ev_g1 = nullptr;
   uint32_t* counters = nullptr;      // device counters, see enum below
   uint32_t* counters_host = nullptr; // pinned mirror
@@ -213,6 +216,7 @@ struct vct_device {
   // measurement / test switches (vct_debug_set); never read from the environment
   bool debug_mip_dense = false;      // every mip build reads and writes every tile
   int debug_cone_variant = -1;       // -1 = automatic; 0 literal loop, 1 two-level fetches, 2 one warp per cone slot, 3 grouped diffuse cones
+  int cone_reserved_sms = 0;         // SMs the persistent cone kernel leaves free (frames in flight: the next frame's front half runs there)
   bool debug_cone_grid = false;      // cone kernel on a host-sized grid instead of the persistent work queue
   bool mip_attr_set = false;
   // multi-GPU connection (vct_peer_connect)
