@@ -11,7 +11,7 @@ sc = S.cornell_scene()
 view, proj = S.reference_camera(W / H)
 prm = capi.default_params(sampler=1)
 pipes = [capi.Pipeline(sc, R, W, H) for _ in range(3)]
-cases = [(1, 0, 0, 0), (2, 0, 0, 0), (1, 0, 0, 1)] + [(2, 0, k, 1) for k in (0, 2, 4, 6, 8, 10, 12, 16, 24)] + [(3, 0, 8, 1), (2, 1, 0, 1)]
+cases = [(1, 0, 0, 0), (2, 0, 0, 0), (1, 0, 0, 1)] + [(2, 0, k, 1) for k in (0, 2, 4, 6, 8, 10, 12, 16, 24)] + [(3, 0, 8, 1), (3, 0, 4, 1)]
 for n_pipes, grid, reserve, low in cases:
     use = pipes[:n_pipes]
     for p in use:

@@ -176,7 +176,11 @@ int vct_device_create(int ordinal, vct_device_t** out) {
   for (int i = 0; i < 8; i++) VCT_CUDA(cudaEventCreate(&d->ev[i]));
   // numerically lower = more urgent: [prio_hi, prio_lo].  The G-buffer stream sits between the critical path and the trace stream
   VCT_CUDA(cudaStreamCreateWithPriority(&d->stream2, cudaStreamNonBlocking, prio_hi < prio_lo ? prio_hi + 1 : prio_lo));
-  VCT_CUDA(cudaStreamCreateWithPriority(&d->stream3, cudaStreamNonBlocking, prio_lo));
+  // one trace stream per process and device ordinal: the traces of all pipelines on a GPU run one after the other (a persistent
+  // cone kernel launched beside another one would find only the reserved SMs free and retire without doing its work)
+  static cudaStream_t g_trace_stream[64] = {};
+  if (!g_trace_stream[ordinal & 63]) VCT_CUDA(cudaStreamCreateWithPriority(&g_trace_stream[ordinal & 63], cudaStreamNonBlocking, prio_lo));
+  d->stream3 = g_trace_stream[ordinal & 63];
   VCT_CUDA(cudaEventCreateWithFlags(&d->ev_front, cudaEventDisableTiming));
   VCT_CUDA(cudaEventCreateWithFlags(&d->ev_trace, cudaEventDisableTiming));
   VCT_CUDA(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
@@ -196,7 +200,7 @@ int vct_device_destroy(vct_device_t* d) {
   cudaFree(d->frags); cudaFree(d->fresh); cudaFree(d->accum);
   for (auto& r : d->rs) { cudaFree(r.tri_recs); cudaFree(r.item_local); cudaFree(r.item_block); cudaFree(r.big_slot); }
   if (d->stream2) { cudaStreamSynchronize(d->stream2); cudaStreamDestroy(d->stream2); }
-  if (d->stream3) { cudaStreamSynchronize(d->stream3); cudaStreamDestroy(d->stream3); }
+  if (d->stream3) cudaStreamSynchronize(d->stream3);   // shared by the device objects of this GPU: never destroyed
   for (cudaEvent_t e : {d->ev_fork, d->ev_join, d->ev_g0, d->ev_g1, d->ev_front, d->ev_trace}) if (e) cudaEventDestroy(e);
   cudaFree(d->counters); cudaFreeHost(d->counters_host); cudaFreeHost((void*)d->status_host);
   for (int i = 0; i < 8; i++) if (d->ev[i]) cudaEventDestroy(d->ev[i]);
