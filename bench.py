@@ -61,7 +61,7 @@ def build_scene(cfg, frame: int = 0):
     return S.synthetic_scene(cfg["tris"], cfg["seed"])
 
 
-def config_dict(cfg, world: int, sampler: int, exchange: str, n_tris: int) -> dict:
+def config_dict(cfg, world: int, sampler: int, exchange: str, n_tris: int, fif: int = 1) -> dict:
     """identical for both arms (the driver compares them)"""
     R, W, H = cfg["R"], cfg["W"], cfg["H"]
     par = f"z-slab voxelize + screen-tile trace x{world}"
@@ -72,6 +72,7 @@ def config_dict(cfg, world: int, sampler: int, exchange: str, n_tris: int) -> di
     return {"workload": cfg["name"] + ", revoxelize+mip+gbuffer+trace per frame, %d diffuse + 1 specular + 1 shadow cone" % cfg.get("cones", 9),
             "sampler": "texture units (levels >= 1), software level 0" if sampler == 1 else "software fp32 trilinear",
             "grid": R, "frame": [W, H], "triangles": n_tris, "parallelism": par,
+            "frames_in_flight": fif if (world == 1 or exchange == "p2p") else 1,
             "l2": "no explicit flush: pyramid + G-buffer + frame working set (%.0f MB) exceeds the 126 MB L2 and is rewritten every frame" % ws}
 
 
@@ -195,7 +196,7 @@ def run_reference(args, cfg, rank: int, world: int):
         "impl": "reference", "metric": "frames_per_sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "frame_ms": frame_ms, "extrapolated": stride != 1, "tile_stride": stride,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 RGBA storage)", "data": "synthetic",
-        "config": config_dict(cfg, world, args.sampler, args.exchange, wl.sc.n_triangles),
+        "config": config_dict(cfg, world, args.sampler, args.exchange, wl.sc.n_triangles, args.frames_in_flight),
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": wl.cores, "kind": "port", "sample": wl.sample_text(stride),
                          "voxelize_s": wl.t_vox, "mip_s": wl.t_mip, "gbuffer_s": wl.t_gbuf},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -221,38 +222,55 @@ class Rig:
         self.sc = build_scene(cfg)
         self.view, self.proj = S.reference_camera(W / H)
         levels = (R.bit_length() if fp16 else 7)   # fp16 variant: the full chain, log2(R) + 1 levels
-        self.pipe = capi.Pipeline(self.sc, R, W, H, levels, ordinal=local_rank, reserve=max(1 << 20, 8 * self.sc.n_triangles),
-                                  fmt=capi.GRID_RGBA16F if fp16 else capi.GRID_RGBA8)
-        self.stream = torch.cuda.ExternalStream(int(self.pipe.dev.L.vct_device_stream(self.pipe.dev.h)), device=torch.device("cuda", local_rank))
         self.prm = capi.default_params(tile_rank=rank, tile_nranks=world, sampler=args.sampler, n_diffuse_cones=cfg.get("cones", 9))
         self.z0, self.z1 = rank * R // world, (rank + 1) * R // world
         self.p2p = world > 1 and args.exchange == "p2p"
+        # Frames in flight: F independent pipelines (device object = stream set + arenas, grid, target) render alternate frames.  The
+        # front half of frame i+1 (clear, voxelize, exchange, mip, G-buffer: chains of small latency-bound kernels) then runs beside the
+        # trace of frame i; the traces of all pipelines are serialised on one low-priority stream per GPU (VCT_DEBUG_TRACE_LOW_PRIORITY).
+        self.F = args.frames_in_flight if (world == 1 or self.p2p) else 1
+        self.pipes, self.streams = [], []
+        for k in range(self.F):
+            pipe = capi.Pipeline(self.sc, R, W, H, levels, ordinal=local_rank, reserve=max(1 << 20, 8 * self.sc.n_triangles),
+                                 fmt=capi.GRID_RGBA16F if fp16 else capi.GRID_RGBA8)
+            if self.F > 1 and args.trace_stream == "shared":
+                pipe.dev.debug_set(capi.DEBUG_TRACE_LOW_PRIORITY, 1)
+            self.pipes.append(pipe)
+            self.streams.append(torch.cuda.ExternalStream(int(pipe.dev.L.vct_device_stream(pipe.dev.h)), device=torch.device("cuda", local_rank)))
+            # size the fragment arena for this rank's slab before anything is timed (the library grows it on overflow and asks for a re-run)
+            for _ in range(4):
+                pipe.clear(); pipe.voxelize(self.z0, self.z1)
+                try:
+                    pipe.voxel_stats()
+                    break
+                except capi.VctError as e:
+                    if "overflow" not in str(e):
+                        raise
+            pipe.clear()
+        self.pipe, self.stream = self.pipes[0], self.streams[0]
+        self.n_frames = 0
         pipe = self.pipe
-        # size the fragment arena for this rank's slab before anything is timed (the library grows it on overflow and asks for a re-run)
-        for _ in range(4):
-            pipe.clear(); pipe.voxelize(self.z0, self.z1)
-            try:
-                pipe.voxel_stats()
-                break
-            except capi.VctError as e:
-                if "overflow" not in str(e):
-                    raise
-        pipe.clear()
         self.base_t = self.frame_t = None
         if world > 1 and not self.p2p:
             self.base_t = torch.as_tensor(CudaArray(pipe.grid.base_ptr, (R * R * R,), "<i4"), device=torch.device("cuda", local_rank))
             self.frame_t = torch.as_tensor(CudaArray(pipe.target.frame_ptr, (W * H,), "<i4"), device=torch.device("cuda", local_rank))
         if self.p2p:
-            # NVLink peer-memory exchange fused into the resolve / shade kernels (csrc/peer.cu): handles travel once, here
-            handles = [None] * world
-            dist.all_gather_object(handles, pipe.peer_export())
-            pipe.peer_connect(rank, world, handles, frame_root=0)
+            # NVLink peer-memory exchange fused into the resolve / shade kernels (csrc/peer.cu): handles travel once, here (one connection per pipeline)
+            for pipe in self.pipes:
+                handles = [None] * world
+                dist.all_gather_object(handles, pipe.peer_export())
+                pipe.peer_connect(rank, world, handles, frame_root=0)
             dist.barrier()
+
+    def next_pipe(self):
+        pipe = self.pipes[self.n_frames % self.F]
+        self.n_frames += 1
+        return pipe
 
     def frame(self):
         pipe, dist, torch = self.pipe, self.dist, self.torch
         if self.world == 1 or self.p2p:
-            pipe.render_frame(self.view, self.proj, self.prm)
+            self.next_pipe().render_frame(self.view, self.proj, self.prm)
             return
         R = self.cfg["R"]
         per_rank = R * R * R // self.world
@@ -269,7 +287,8 @@ class Rig:
     def barrier(self):
         if self.world > 1:
             self.dist.barrier()
-        self.pipe.sync()
+        for pipe in self.pipes:
+            pipe.sync()
         self.torch.cuda.synchronize()
 
     def timed(self, steps: int, warmup: int) -> float:
@@ -283,6 +302,10 @@ class Rig:
         e0.record(self.stream)
         for _ in range(steps):
             self.frame()
+        for st in self.streams[1:]:   # the clock stops when the last frame of EVERY pipeline is done
+            ev = torch.cuda.Event()
+            ev.record(st)
+            self.stream.wait_event(ev)
         e1.record(self.stream)
         self.barrier()
         ms = e0.elapsed_time(e1)
@@ -295,7 +318,7 @@ class Rig:
     def stage_times(self, n: int) -> dict:
         """per-stage device times of this rank in us (CUDA events inside vct_render_frame), averaged over n frames"""
         acc = {}
-        for _ in range(n):
+        for _ in range(n):   # one pipeline, one frame at a time: the stages of a frame on an otherwise idle GPU
             self.pipe.render_frame(self.view, self.proj, self.prm)
             for k, v in self.pipe.timings().items():
                 acc[k] = acc.get(k, 0.0) + v * 1e3 / n
@@ -303,11 +326,14 @@ class Rig:
 
     def close(self):
         if self.p2p:
-            self.pipe.peer_check()        # raises if a flag wait ever timed out
+            for pipe in self.pipes:
+                pipe.peer_check()         # raises if a flag wait ever timed out
             self.barrier()                # nobody unmaps while a peer may still be storing into it
-            self.pipe.peer_disconnect()
+            for pipe in self.pipes:
+                pipe.peer_disconnect()
             self.barrier()
-        self.pipe.close()
+        for pipe in self.pipes:
+            pipe.close()
 
 
 def h2d_bytes(sc) -> int:
@@ -317,27 +343,31 @@ def h2d_bytes(sc) -> int:
 def e2e_loop(rig: Rig, steps: int):
     """the frame through the public C ABI with HOST buffers: every step uploads the scene (geometry, materials, draw list, lights)
     from host memory and reads the finished frame back into pinned host memory; wall clock, max over ranks"""
-    torch, pipe, sc, rank, world = rig.torch, rig.pipe, rig.sc, rig.rank, rig.world
+    torch, sc, rank, world = rig.torch, rig.sc, rig.rank, rig.world
     W, H = rig.cfg["W"], rig.cfg["H"]
-    host_frames = [torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(2)] if rank == 0 else None
-    for i in range(2):
+    F = rig.F
+    host_frames = [torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(2 * F)] if rank == 0 else None
+    for i in range(2 * F):
+        pipe = rig.next_pipe()
         pipe.scene.upload(sc); pipe.render_frame(rig.view, rig.proj, rig.prm)
         if rank == 0:
             pipe.target.wait(pipe.target.frame_async(host_frames[i]))
     rig.barrier()
     t0 = time.perf_counter()
-    prev = None
+    pending = []                                             # (pipeline, ticket) of the read-backs in flight, oldest first
     for i in range(steps):
+        pipe = rig.next_pipe()
         pipe.scene.upload(sc)                                # H2D: geometry, materials, draw list (pinned staging ring, async)
         pipe.render_frame(rig.view, rig.proj, rig.prm)
         if rank == 0:
-            tk = pipe.target.frame_async(host_frames[i & 1])  # D2H of this frame, asynchronous: overlaps the next frame
-            if prev is not None:
-                pipe.target.wait(prev)                        # frame i-1 is in host memory
-            prev = tk
-    if rank == 0 and prev is not None:
-        pipe.target.wait(prev)
-    pipe.sync()
+            pending.append((pipe, pipe.target.frame_async(host_frames[i % (2 * F)])))   # D2H of this frame, asynchronous: overlaps the next frame(s)
+            if len(pending) > F:
+                q, tk = pending.pop(0)
+                q.target.wait(tk)                             # frame i-F is in host memory
+    for q, tk in pending:
+        q.target.wait(tk)
+    for pipe in rig.pipes:
+        pipe.sync()
     dt = time.perf_counter() - t0
     if world > 1:
         tt = torch.tensor([dt], device=f"cuda:{rig.local_rank}")
@@ -348,8 +378,9 @@ def e2e_loop(rig: Rig, steps: int):
            "note": ("every rank uploads the scene from host memory and renders its share every step, the root reads the merged frame back to pinned host "
                     "memory" if world > 1 else "scene uploaded from host memory and the finished frame read back to pinned host memory EVERY step through the C ABI")
                    + "; the read-back of frame i overlaps the rendering of frame i+1 (vct_target_download_frame_async); wall clock"}
-    if world == 1:   # the same loop fully serialised (blocking read-back each step), for reference
+    if world == 1:   # the same loop fully serialised (one pipeline, blocking read-back each step), for reference
         n = min(steps, 50)
+        pipe = rig.pipe
         pipe.sync()
         t0 = time.perf_counter()
         for i in range(n):
@@ -443,7 +474,7 @@ def run_extra(cfg_id, args, rank, world, local_rank, torch, dist, fp16: bool = F
         if world > 1 and st is not None:
             per_rank = [None] * world
             dist.all_gather_object(per_rank, {k: round(v, 1) for k, v in st.items()})
-        wl = config_dict(cfg, world, args.sampler, args.exchange, rig.sc.n_triangles)["workload"]
+        wl = config_dict(cfg, world, args.sampler, args.exchange, rig.sc.n_triangles, args.frames_in_flight)["workload"]
         if fp16:
             wl = wl.replace("RGBA8, 7 levels", "RGBA16F grid, full chain of %d levels: BASELINE config 5's storage variant, fp32 software filtering" % cfg["R"].bit_length())
         out = {"workload": wl, "ms_per_frame": ms, "frames_per_s": 1e3 / ms,
@@ -526,7 +557,7 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
     if rank == 0:
         out = {"metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 RGBA storage)",
-               "data": "synthetic", "config": dict(config_dict(cfg, world, args.sampler, args.exchange, n_tris), **({"storage": "RGBA16F, full mip chain (variant)"} if args.fp16 else {})),
+               "data": "synthetic", "config": dict(config_dict(cfg, world, args.sampler, args.exchange, n_tris, args.frames_in_flight), **({"storage": "RGBA16F, full mip chain (variant)"} if args.fp16 else {})),
                "clocks": clocks, "e2e": e2e, "gpu_launches": KERNELS_PER_FRAME * args.steps, "roofline": roof, "cpu_baseline": cpu}
         if stages:
             out["stages"] = stages
@@ -547,6 +578,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--fp16", action="store_true", help="run the chosen config with the RGBA16F grid + full mip chain storage variant (one GPU; not the headline)")
+    ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2, 3],
+                    help="independent pipelines rendering alternate frames (the front half of frame i+1 runs beside the trace of frame i); 1 = the plain loop")
+    ap.add_argument("--trace-stream", default="shared", choices=["shared", "own"],
+                    help="frames in flight: cones + shade of all pipelines on one low-priority stream per GPU (default) or on each pipeline's own stream")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the device-timed runs of configs 4 and 5 (extra_configs)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],

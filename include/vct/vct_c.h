@@ -64,7 +64,7 @@ typedef struct {
   float view_voxel_lod;
   int32_t n_diffuse_cones; /* 9 = reference (voxel_cone_tracing.frag:153-165); 5 = normal + 4 side cones (BASELINE.json config 1);
                             * 16 = normal + 5 at 30 deg + 10 at 60 deg, aperture 2 tan 15 deg (config 5); non-reference variants */
-  int32_t tile_rank, tile_nranks; /* this call shades 32x32 screen tiles t with t % tile_nranks == tile_rank */
+  int32_t tile_rank, tile_nranks; /* this call shades the 32x32 screen tiles (tx, ty) with (tx + k ty) % tile_nranks == tile_rank, k = 3 (5 or 7 when 3 / 15 divides tile_nranks) */
   int32_t sampler; /* VCT_SAMPLER_*: how textureLod is evaluated */
 } vct_trace_params_t;
 
@@ -187,6 +187,7 @@ int vct_last_frame_timings(vct_device_t* dev, float out_ms[8]);
 #define VCT_DEBUG_CONE_GRID 3
 #define VCT_DEBUG_CONE_RESERVE_SMS 4
 #define VCT_DEBUG_TRACE_LOW_PRIORITY 5
+#define VCT_DEBUG_PEER_REPLICATE 6
 int vct_debug_set(vct_device_t* dev, int key, int value);
 
 /* ---- multi-GPU (no reference counterpart: the reference is single-GPU).  One process per GPU on one node; the exchange

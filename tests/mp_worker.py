@@ -61,13 +61,23 @@ def main():
         rb = torch.from_numpy(np.stack(ref_bases).astype(np.int64)) if rank == 0 else torch.zeros((n_frames, R, R, R), dtype=torch.int64)
         dist.broadcast(rb, 0)                   # every rank checks its gathered grid against the single-GPU grid, every frame
         ref_bases = rb.numpy().astype(np.uint32)
-        pipe = capi.Pipeline(sc, R, W, H, ordinal=ordinal)
-        handles = [None] * world
-        dist.all_gather_object(handles, pipe.peer_export())
-        pipe.peer_connect(rank, world, handles, frame_root=0)
+        # VCT_TEST_REPLICATE: 0 = z-slab voxelization + sparse voxel push, 1 = every rank voxelizes the whole scene (small-scene mode);
+        # VCT_TEST_FIF: pipelines rendering alternate frames (frames in flight; their traces share one low-priority stream per GPU)
+        replicate, fif = int(os.environ.get("VCT_TEST_REPLICATE", "0")), int(os.environ.get("VCT_TEST_FIF", "1"))
+        pipes = []
+        for _ in range(fif):
+            pipe = capi.Pipeline(sc, R, W, H, ordinal=ordinal)
+            pipe.dev.debug_set(capi.DEBUG_PEER_REPLICATE, replicate)
+            if fif > 1:
+                pipe.dev.debug_set(capi.DEBUG_TRACE_LOW_PRIORITY, 1)
+            handles = [None] * world
+            dist.all_gather_object(handles, pipe.peer_export())
+            pipe.peer_connect(rank, world, handles, frame_root=0)
+            pipes.append(pipe)
         dist.barrier()
         ok = True
         for k in range(n_frames):
+            pipe = pipes[k % fif]
             pipe.scene.upload(scenes[k])
             pipe.render_frame(view, proj, prm)
             pipe.sync()
@@ -77,12 +87,14 @@ def main():
             ok &= bool(np.array_equal(pipe.grid.download(0), ref_bases[k]))
             dist.barrier()
         # the same frames again WITHOUT host synchronisation in between: ranks run ahead of each other as far as the flags allow
-        for k in range(n_frames + 1):
+        for k in range(2 * n_frames + 1):
+            pipe = pipes[k % fif]
             pipe.scene.upload(scenes[k % n_frames])
             pipe.render_frame(view, proj, prm)
-        pipe.sync()
+        for q in pipes:
+            q.sync()
         dist.barrier()
-        ref_base = ref_bases[0]                 # the last frame rendered was scene 0
+        ref_base = ref_bases[0]                 # the last frame rendered was scene 0, on `pipe`
         if rank == 0:
             ok &= bool(np.array_equal(pipe.target.frame(), ref_frames[0]))
             ref_l2 = None
@@ -92,11 +104,14 @@ def main():
         ok &= bool(torch.equal(bt, b0))         # every rank ends up with the same full grid
         if rank == 0:
             ok &= bool(np.array_equal(base, ref_base))
-        pipe.peer_check()
+        for q in pipes:
+            q.peer_check()
         dist.barrier()
-        pipe.peer_disconnect()
+        for q in pipes:
+            q.peer_disconnect()
         dist.barrier()
-        pipe.close()
+        for q in pipes:
+            q.close()
         result["ok"] = ok
         result["gpus"] = ngpu
     flags = [None] * world

@@ -18,7 +18,7 @@ def test_reference_arm_prints_the_contract_line():
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["value"] == line["value"]
     assert line["cpu_baseline"]["cores"] == (os.cpu_count() or 1)
     assert line["e2e"] == {"value": line["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert set(line["config"]) == {"workload", "sampler", "grid", "frame", "triangles", "parallelism", "l2"}
+    assert set(line["config"]) == {"workload", "sampler", "grid", "frame", "triangles", "parallelism", "frames_in_flight", "l2"}
     assert line["gpu_launches"] == 0
 
 

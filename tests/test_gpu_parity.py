@@ -552,13 +552,48 @@ def test_tile_split_equals_full_frame():
         p.trace(view, capi.default_params(tile_rank=r, tile_nranks=3))
         parts.append(p.target.frame().copy())
     ty, tx = np.meshgrid(np.arange(H) // 32, np.arange(W) // 32, indexing="ij")
-    owner = (ty * ((W + 31) // 32) + tx) % 3
+    owner = capi.screen_tile_owner(tx, ty, 3)
     merged = np.zeros_like(full)
     for r in range(3):
         # a rank only writes its own tiles; the rest of its buffer still holds the previous content
         merged[owner == r] = parts[r][owner == r]
     assert np.array_equal(merged, full)
     p.close()
+
+
+def test_frames_in_flight_equal_the_plain_loop():
+    """two pipelines (device objects) rendering alternate frames of a moving object, their traces serialised on the shared low-priority
+    stream (VCT_DEBUG_TRACE_LOW_PRIORITY), no host synchronisation in between: every frame equals the one-pipeline render"""
+    R, W, H, n = 64, 320, 200, 7
+    view, proj = S.reference_camera(W / H)
+    scenes = [S.cornell_scene(with_suzanne=True, theta=0.2 + 0.35 * k) for k in range(n)]
+    one = capi.Pipeline(scenes[0], R, W, H)
+    want = []
+    for sc in scenes:
+        one.scene.upload(sc); one.render_frame(view, proj)
+        want.append((one.target.frame().copy(), one.grid.download(0), one.grid.download(2, 4)))
+    one.close()
+    pipes = [capi.Pipeline(scenes[0], R, W, H) for _ in range(2)]
+    for p in pipes:
+        p.dev.debug_set(capi.DEBUG_TRACE_LOW_PRIORITY, 1)
+    host = [np.zeros((H, W), np.uint32) for _ in range(n)]
+    tickets = []
+    for k, sc in enumerate(scenes):
+        p = pipes[k & 1]
+        p.scene.upload(sc); p.render_frame(view, proj)
+        tickets.append((p, p.target.frame_async(host[k])))
+        if k >= 2:
+            q, tk = tickets[k - 2]
+            q.target.wait(tk)
+    for q, tk in tickets[-2:]:
+        q.target.wait(tk)
+    for k in range(n):
+        assert np.array_equal(host[k], want[k][0]), f"frame {k}"
+    for k in (n - 2, n - 1):   # the grids the two pipelines end with
+        p = pipes[k & 1]
+        assert np.array_equal(p.grid.download(0), want[k][1]) and np.array_equal(p.grid.download(2, 4), want[k][2])
+    for p in pipes:
+        p.close()
 
 
 def test_render_is_deterministic():

@@ -39,7 +39,9 @@ def test_sharding_logic_on_cpu_gloo(tmp_path, world):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("sampler", [0, 1])
-def test_peer_exchange_two_ranks_bit_identical(tmp_path, sampler):
-    res = _launch("gpu", 2, tmp_path, 600, {"VCT_TEST_SAMPLER": str(sampler)})
+@pytest.mark.parametrize("sampler,replicate,fif", [(0, 0, 1), (1, 0, 1), (1, 1, 1), (1, 0, 2), (1, 1, 2)])
+def test_peer_exchange_two_ranks_bit_identical(tmp_path, sampler, replicate, fif):
+    """sampler: software / texture-unit cone sampler; replicate: z-slab voxelization + voxel push (0) or small-scene mode, every rank voxelizes
+    everything (1); fif: pipelines rendering alternate frames (frames in flight)"""
+    res = _launch("gpu", 2, tmp_path, 600, {"VCT_TEST_SAMPLER": str(sampler), "VCT_TEST_REPLICATE": str(replicate), "VCT_TEST_FIF": str(fif)})
     assert res["ok"], res

@@ -59,7 +59,7 @@ def default_params(**kw) -> TraceParams:
 
 _lib = None
 PEER_HANDLE_BYTES = 320   # sizeof(vct_peer_handle_t)
-DEBUG_MIP_DENSE, DEBUG_CONE_VARIANT, DEBUG_CONE_GRID, DEBUG_CONE_RESERVE_SMS, DEBUG_TRACE_LOW_PRIORITY = 1, 2, 3, 4, 5   # vct_debug_set keys
+DEBUG_MIP_DENSE, DEBUG_CONE_VARIANT, DEBUG_CONE_GRID, DEBUG_CONE_RESERVE_SMS, DEBUG_TRACE_LOW_PRIORITY, DEBUG_PEER_REPLICATE = 1, 2, 3, 4, 5, 6   # vct_debug_set keys
 ACCUM_ORDERED, ACCUM_FIXED_POINT = 0, 1                          # vct_voxelize_set_accum_mode
 GRID_RGBA8, GRID_RGBA16F = 0, 1                                  # vct_grid_create_ex formats
 SAMPLER_FP32, SAMPLER_TEX = 0, 1
@@ -284,6 +284,12 @@ class DeviceScene:
     def close(self):
         if self.h:
             self.dev.L.vct_scene_destroy(self.h); self.h = C.c_void_p()
+
+
+def screen_tile_owner(tx, ty, nranks: int):
+    """rank that shades the 32x32 screen tile (tx, ty) of a frame split over `nranks` (screen_tile_owner in csrc/vct_internal.cuh); numpy arrays welcome"""
+    k = 3 if nranks % 3 else (5 if nranks % 5 else 7)
+    return (tx + k * ty) % nranks
 
 
 class Pipeline:

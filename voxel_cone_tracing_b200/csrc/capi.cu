@@ -760,6 +760,11 @@ int vct_debug_set(vct_device_t* dev, int key, int value) {
     case VCT_DEBUG_MIP_DENSE: dev->debug_mip_dense = value != 0; return VCT_OK;
     case VCT_DEBUG_CONE_VARIANT: VCT_REQUIRE(value >= -1 && value <= 3, "cone variant must be -1..3"); dev->debug_cone_variant = value; return VCT_OK;
     case VCT_DEBUG_CONE_GRID: dev->debug_cone_grid = value != 0; return VCT_OK;
+    case VCT_DEBUG_PEER_REPLICATE:
+      VCT_REQUIRE(value >= -1 && value <= 1, "peer replicate must be -1 (automatic), 0 or 1");
+      VCT_REQUIRE(dev->peers.nranks <= 1, "set before vct_peer_connect");
+      dev->peer_replicate_force = value;
+      return VCT_OK;
     case VCT_DEBUG_TRACE_LOW_PRIORITY: dev->trace_low_priority = value != 0; return VCT_OK;
     case VCT_DEBUG_CONE_RESERVE_SMS:
       VCT_REQUIRE(value >= 0 && value < dev->prop.multiProcessorCount, "reserved SM count out of range");
@@ -810,6 +815,34 @@ int vct_cone_trace_count(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, cons
 //    flag was seen (frame e-1 of this rank), and last read by this rank's own trace of frame e-1 (stream order).
 //  * a peer's frame buffer receives tiles of frame e only after that peer published PUSHED(e), i.e. after everything it
 //    had enqueued for frame e-1 (including a frame download) in stream order.
+// the trace of one rank's screen tiles (+ their push to the root) and, on the root, the wait for everybody's tiles
+static int sharded_trace(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_target_t* t, const float view[16], const vct_trace_params_t* prm,
+                         const PeerView& pv, uint32_t epoch) {
+  cudaStream_t s = dev->stream;
+  int rc;
+  if (dev->trace_low_priority) {   // frames in flight: see vct_render_frame
+    VCT_CUDA(cudaEventRecord(dev->ev_front, s));
+    VCT_CUDA(cudaStreamWaitEvent(dev->stream3, dev->ev_front, 0));
+    dev->stream = dev->stream3;
+  }
+  rc = launch_cone_trace(dev, sc, g, view, prm, t, false, &pv, 2);                           // + push of the tiles to the root
+  if (dev->trace_low_priority) {
+    dev->stream = s;
+    if (rc) return rc;
+    VCT_CUDA(cudaEventRecord(dev->ev_trace, dev->stream3));
+    VCT_CUDA(cudaStreamWaitEvent(s, dev->ev_trace, 0));
+  }
+  if (rc) return rc;
+  // the root's wait for the other ranks' tiles sits on this pipeline's own stream: it holds back what follows on this device object
+  // (a download, its next frame), not the shared trace stream
+  if (pv.frame_root < 0 || pv.frame_root == pv.rank)
+    if ((rc = launch_peer_wait(dev, PEER_FLAG_FRAME, epoch))) return rc;                    // every tile has arrived
+  VCT_CUDA(cudaEventRecord(dev->ev[5], s));
+  dev->have_timings = true;
+  dev->gbuffer_overlapped = true;
+  return VCT_OK;
+}
+
 static int render_frame_sharded(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_target_t* t, const float view[16], const float proj[16],
                                 const vct_trace_params_t* p) {
   cudaStream_t s = dev->stream;
@@ -818,6 +851,49 @@ static int render_frame_sharded(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* 
   PeerView pv = dev->peers;
   pv.epoch = epoch;
   for (int r = 0; r < pv.nranks; r++) { pv.base[r] = dev->peer_base_all[b][r]; pv.touched[r] = dev->peer_touched_all[b][r]; }
+  // A small scene (the reference's Cornell box: 1 k triangles) voxelizes in ~70 us of launch and dependency latency whatever the slab:
+  // sharding it saves nothing and adds the peers' flag waits to every rank's front half.  Every rank then voxelizes the whole scene into
+  // its own grid (no voxel exchange, the single-GPU sparse clear / sparse mip bookkeeping), and only the screen tiles are split.
+  // Decided once per connection from the scene of its first frame (the same on every rank).
+  if (dev->peer_replicate < 0) {
+    dev->peer_replicate = dev->peer_replicate_force >= 0 ? dev->peer_replicate_force : (sc->n_tris <= 16384u ? 1 : 0);
+    if (dev->peer_replicate == 1) {   // nobody stores into this grid: back to the tracked single-GPU state (the first clear is dense)
+      g->base = g->base_buf[0];
+      g->external = false;
+      g->peer_touched = nullptr;
+      g->untrack();
+    }
+  }
+  if (dev->peer_replicate == 1) {
+    cudaStream_t s = dev->stream;
+    vct_trace_params_t prm = *p;
+    prm.tile_rank = pv.rank; prm.tile_nranks = pv.nranks;
+    int rc;
+    VCT_CUDA(cudaEventRecord(dev->ev[0], s));
+    VCT_CUDA(cudaEventRecord(dev->ev_fork, s));
+    // PUSHED(e) of rank r now only says "r has finished everything it had queued before frame e": its frame buffer may receive tiles of e
+    if ((rc = launch_peer_signal(dev, pv, PEER_FLAG_PUSHED))) return rc;
+    if ((rc = vct_grid_clear(g))) return rc;
+    VCT_CUDA(cudaEventRecord(dev->ev[1], s));
+    if ((rc = launch_voxelize(dev, sc, g, 0, g->R))) return rc;
+    VCT_CUDA(cudaEventRecord(dev->ev[2], s));
+    VCT_CUDA(cudaStreamWaitEvent(dev->stream2, dev->ev_fork, 0));
+    dev->stream = dev->stream2;
+    VCT_CUDA(cudaEventRecord(dev->ev_g0, dev->stream2));
+    const bool fused_list = prm.view_voxel_dir >= 7;
+    rc = launch_gbuffer(dev, sc, view, proj, t, pv.rank, pv.nranks, fused_list);
+    if (!rc && !fused_list) rc = launch_cone_trace(dev, sc, g, view, &prm, t, false, &pv, 1);
+    dev->stream = s;
+    if (rc) return rc;
+    VCT_CUDA(cudaEventRecord(dev->ev_g1, dev->stream2));
+    VCT_CUDA(cudaEventRecord(dev->ev_join, dev->stream2));
+    if ((rc = launch_mipmap(dev, g))) return rc;
+    VCT_CUDA(cudaEventRecord(dev->ev[3], s));
+    VCT_CUDA(cudaStreamWaitEvent(s, dev->ev_join, 0));
+    if ((rc = launch_peer_wait(dev, PEER_FLAG_PUSHED, epoch))) return rc;   // the destination frame(s) are free (long since: the flags went out at the head of the frame)
+    VCT_CUDA(cudaEventRecord(dev->ev[4], s));
+    return sharded_trace(dev, sc, g, t, view, &prm, pv, epoch);
+  }
   g->base = g->base_buf[b];
   // every rank exported tile flags (same grid size everywhere: all or none); a mip tile is 8 slices deep and must belong to ONE slab
   // Decided once per connection, from the scene of its first frame (the same on every rank): the un-push stores nranks words + flags per
@@ -866,13 +942,7 @@ static int render_frame_sharded(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* 
   VCT_CUDA(cudaEventRecord(dev->ev[3], s));
   VCT_CUDA(cudaStreamWaitEvent(s, dev->ev_join, 0));
   VCT_CUDA(cudaEventRecord(dev->ev[4], s));
-  if ((rc = launch_cone_trace(dev, sc, g, view, &prm, t, false, &pv, 2))) return rc;         // + push of the tiles to the root
-  if (pv.frame_root < 0 || pv.frame_root == pv.rank)
-    if ((rc = launch_peer_wait(dev, PEER_FLAG_FRAME, epoch))) return rc;                    // every tile has arrived
-  VCT_CUDA(cudaEventRecord(dev->ev[5], s));
-  dev->have_timings = true;
-  dev->gbuffer_overlapped = true;
-  return VCT_OK;
+  return sharded_trace(dev, sc, g, t, view, &prm, pv, epoch);
 }
 
 int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_target_t* t, const float view[16], const float proj[16],

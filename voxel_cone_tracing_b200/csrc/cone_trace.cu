@@ -517,10 +517,9 @@ __device__ __forceinline__ Pixel load_pixel(const TraceArgs& a, int px, int py) 
 }
 
 __device__ __forceinline__ bool tile_is_mine(const TraceArgs& a, int tile_x, int tile_y) {
-  // multi-GPU split: 32x32 screen tiles are dealt round-robin to ranks
+  // multi-GPU split: 32x32 screen tiles are dealt to the ranks on a diagonal lattice (screen_tile_owner)
   if (a.prm.tile_nranks <= 1) return true;
-  const int t32 = (tile_y / 8) * ((a.W + 31) / 32) + (tile_x / 4);
-  return t32 % a.prm.tile_nranks == a.prm.tile_rank;
+  return screen_tile_owner(tile_x / 4, tile_y / 8, a.prm.tile_nranks) == a.prm.tile_rank;
 }
 
 // Compacts the 8x4 tiles that contain at least one shaded pixel.  One warp takes kTilesPerWarp consecutive tiles: the G-buffer
@@ -863,16 +862,18 @@ shade_kernel(const TraceArgs a) {
   if (mine) shade_pixel(a, tile_x, tile_y, lane);
 }
 
-// multi-GPU: one CTA per 32x32 screen tile of this rank copies the finished pixels into the frame of the root rank
-// (or of every rank) over NVLink with 16-byte stores (a tile row = 128 contiguous bytes); the last CTA then publishes
-// this rank's "tiles done" flag to the destination(s).
+// multi-GPU: the CTAs stride over this rank's 32x32 screen tiles and copy the finished pixels into the frame of the root rank
+// (or of every rank) over NVLink with 16-byte stores (a tile row = 128 contiguous bytes); each CTA fences once, the last one publishes
+// this rank's "tiles done" flag to the destination(s).  (Fusing the copy into shade_kernel was measured twice this round -- pixels pushed
+// as they are shaded, and per 32x8 strip -- and lost: a system-scope fence per shading CTA costs more than this second pass, N = 2:
+// shade + push 59 us here, 74 / 105 us fused.)
 __global__ void __launch_bounds__(256)
 frame_push_kernel(const TraceArgs a) {
   const int tiles_x = (a.W + 31) >> 5, tiles_y = (a.H + 31) >> 5;
-  const int n_mine = (tiles_x * tiles_y - a.pv.rank + a.pv.nranks - 1) / a.pv.nranks;
-  for (int k = blockIdx.x; k < n_mine; k += gridDim.x) {
-    const int tile = a.pv.rank + k * a.pv.nranks;
-    const int x0 = (tile % tiles_x) * 32, y0 = (tile / tiles_x) * 32;
+  for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+    const int tx = tile % tiles_x, ty = tile / tiles_x;
+    if (screen_tile_owner(tx, ty, a.pv.nranks) != a.pv.rank) continue;
+    const int x0 = tx * 32, y0 = ty * 32;
     for (int u = threadIdx.x; u < 32 * 8; u += blockDim.x) {   // 32 rows x 8 uint4
       const int x = x0 + 4 * (u & 7), y = y0 + (u >> 3);
       if (y >= a.H || x >= a.W) continue;
@@ -992,7 +993,7 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
   shade_kernel<<<(n_tiles + 7) / 8, 256, 0, s>>>(a);
   if (a.pv.nranks > 1) {
     const int n32 = ((t->W + 31) / 32) * ((t->H + 31) / 32);
-    frame_push_kernel<<<min(n32 / a.pv.nranks + 1, dev->prop.multiProcessorCount * 4), 256, 0, s>>>(a);
+    frame_push_kernel<<<min(n32, dev->prop.multiProcessorCount * 4), 256, 0, s>>>(a);
   }
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;

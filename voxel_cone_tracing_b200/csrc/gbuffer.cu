@@ -122,7 +122,7 @@ __device__ __noinline__ int cam_clip_pieces(const vct_vertex_t* __restrict__ ver
 }
 
 __device__ __forceinline__ bool tile_owned(int i, int j, int W, int tile_rank, int tile_nranks) {
-  return tile_nranks <= 1 || ((j >> 5) * ((W + 31) >> 5) + (i >> 5)) % tile_nranks == tile_rank;
+  return tile_nranks <= 1 || screen_tile_owner(i >> 5, j >> 5, tile_nranks) == tile_rank;
 }
 
 // depth test of every covered pixel of a piece, one lane per piece (the sub-tile triangles of a large scene)

@@ -91,6 +91,15 @@ int ensure_pushed_lists(vct_device* dev) {
   return VCT_OK;
 }
 
+// a flag of its own launch: "everything this device object had queued before has completed" (replicated voxelization has no
+// pushing kernel to carry the PUSHED flag)
+__global__ void peer_signal_kernel(const PeerView pv, int kind) { peer_signal_last_block(pv, kind, -1); }
+int launch_peer_signal(vct_device* dev, const PeerView& pv, int kind) {
+  peer_signal_kernel<<<1, 32, 0, dev->stream>>>(pv, kind);
+  VCT_CUDA(cudaGetLastError());
+  return VCT_OK;
+}
+
 int launch_peer_wait(vct_device* dev, int kind, uint32_t epoch) {
   const long long timeout = (long long)dev->prop.clockRate * 1000ll * 5ll;   // ~5 s of SM clock (clockRate is in kHz)
   peer_wait_kernel<<<1, 32, 0, dev->stream>>>(dev->peer_flags, kind, dev->peers.nranks, epoch, dev->peer_flags + kFlagWords - 1, dev->status_dev, timeout);
@@ -152,6 +161,7 @@ int vct_peer_disconnect(vct_device_t* dev) {
   dev->peer_grid = nullptr; dev->peer_target = nullptr;
   dev->peer_epoch = 0;
   dev->peer_sparse_mode = -1;
+  dev->peer_replicate = -1;
   return VCT_OK;
 }
 

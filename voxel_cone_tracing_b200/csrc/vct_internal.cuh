@@ -161,6 +161,14 @@ __device__ __forceinline__ void peer_signal_last_block(const PeerView& pv, int k
   }
 }
 
+// Multi-GPU split of the frame: which rank owns the 32x32 screen tile (tx, ty).  A diagonal lattice -- (tx + k ty) mod n with k coprime to n --
+// spreads every rank's tiles evenly in both directions; plain round-robin over the row-major tile index gives (tx + 60 ty) mod 8 =
+// (tx + 4 ty) mod 8 at 1920 pixels: two column phases only, which line up with the walls of the scene (cone kernel 117..128 us per rank at N = 8).
+__host__ __device__ __forceinline__ int screen_tile_owner(int tx, int ty, int nranks) {
+  const int k = nranks % 3 ? 3 : (nranks % 5 ? 5 : 7);
+  return (tx + k * ty) % nranks;
+}
+
 // surface handles of the stacked mipmapped array: s[grid level], level >= 1; direction d starts at z = d * pitch[level]
 struct SurfSet {
   cudaSurfaceObject_t s[VCT_MAX_LEVELS];
@@ -233,6 +241,8 @@ struct vct_device {
   int peer_sparse_mode = -1;                        // -1 undecided, 0 dense clear + dense mip under peers, 1 sparse (decided at the first frame of a connection)
   vct_grid* peer_grid = nullptr;
   vct_target_t_* peer_target = nullptr;
+  int peer_replicate = -1;             // -1 undecided, 1 = small scene: every rank voxelizes all of it (no voxel exchange), 0 = z-slabs + push
+  int peer_replicate_force = -1;       // VCT_DEBUG_PEER_REPLICATE: -1 automatic, 0 never, 1 always
   uint32_t peer_epoch = 0;             // frames rendered since vct_peer_connect
   bool peer_export_fresh = false;      // vct_peer_export ran (flag block zeroed) and no connect has consumed it yet
 };
@@ -367,6 +377,7 @@ int launch_copy_u32(cudaStream_t s, uint32_t* dst, const uint32_t* src, size_t n
 int ensure_tri_scratch(vct_device* dev, int which /* 0 voxelizer, 1 G-buffer */, size_t n_tris, size_t rec_bytes_total);
 int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1, const PeerView* push = nullptr);
 int launch_peer_wait(vct_device* dev, int kind, uint32_t epoch);
+int launch_peer_signal(vct_device* dev, const PeerView& pv, int kind);      // publish pv.epoch under `kind` to every rank (a launch of its own)
 int launch_peer_unpush(vct_device* dev, const PeerView& pv, int logR);   // zero the voxels this rank pushed into this frame's buffer two frames ago
 int ensure_pushed_lists(vct_device* dev);
 int check_status(vct_device* dev);   // VCT_ERR_OVERFLOW / VCT_ERR_CUDA if a kernel reported an arena overflow / a peer timeout since the last check
