@@ -72,8 +72,17 @@ def config_dict(cfg, world: int, sampler: int, exchange: str, n_tris: int, fif: 
     return {"workload": cfg["name"] + ", revoxelize+mip+gbuffer+trace per frame, %d diffuse + 1 specular + 1 shadow cone" % cfg.get("cones", 9),
             "sampler": "texture units (levels >= 1), software level 0" if sampler == 1 else "software fp32 trilinear",
             "grid": R, "frame": [W, H], "triangles": n_tris, "parallelism": par,
-            "frames_in_flight": fif if (world == 1 or exchange == "p2p") else 1,
+            "frames_in_flight": fif,
             "l2": "no explicit flush: pyramid + G-buffer + frame working set (%.0f MB) exceeds the 126 MB L2 and is rewritten every frame" % ws}
+
+
+def frames_in_flight(args, n_tris: int, world: int, exchange: str) -> int:
+    """--frames-in-flight 0 (default) = automatic: two pipelines for scenes whose front half (clear, voxelize, mip, G-buffer) is latency-bound
+    launch chains (<= 64 k triangles: the reference's scenes), one for the large synthetic scenes, where that half is real whole-GPU work
+    and a second frame beside the cone kernel only adds contention (config 5 on one GPU: 91.1 ms with one, 95.7 ms with two)"""
+    if world > 1 and exchange != "p2p":
+        return 1
+    return args.frames_in_flight or (2 if n_tris <= 65536 else 1)
 
 
 def measured_peaks():
@@ -196,7 +205,7 @@ def run_reference(args, cfg, rank: int, world: int):
         "impl": "reference", "metric": "frames_per_sec", "value": v, "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms, "frame_ms": frame_ms, "extrapolated": stride != 1, "tile_stride": stride,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 RGBA storage)", "data": "synthetic",
-        "config": config_dict(cfg, world, args.sampler, args.exchange, wl.sc.n_triangles, args.frames_in_flight),
+        "config": config_dict(cfg, world, args.sampler, args.exchange, wl.sc.n_triangles, frames_in_flight(args, wl.sc.n_triangles, world, args.exchange)),
         "cpu_baseline": {"value": v, "unit": "frames/s", "cores": wl.cores, "kind": "port", "sample": wl.sample_text(stride),
                          "voxelize_s": wl.t_vox, "mip_s": wl.t_mip, "gbuffer_s": wl.t_gbuf},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -228,13 +237,17 @@ class Rig:
         # Frames in flight: F independent pipelines (device object = stream set + arenas, grid, target) render alternate frames.  The
         # front half of frame i+1 (clear, voxelize, exchange, mip, G-buffer: chains of small latency-bound kernels) then runs beside the
         # trace of frame i; the traces of all pipelines are serialised on one low-priority stream per GPU (VCT_DEBUG_TRACE_LOW_PRIORITY).
-        self.F = args.frames_in_flight if (world == 1 or self.p2p) else 1
+        self.F = frames_in_flight(args, self.sc.n_triangles, world, args.exchange)
         self.pipes, self.streams = [], []
         for k in range(self.F):
             pipe = capi.Pipeline(self.sc, R, W, H, levels, ordinal=local_rank, reserve=max(1 << 20, 8 * self.sc.n_triangles),
                                  fmt=capi.GRID_RGBA16F if fp16 else capi.GRID_RGBA8)
             if self.F > 1 and args.trace_stream == "shared":
                 pipe.dev.debug_set(capi.DEBUG_TRACE_LOW_PRIORITY, 1)
+            if args.cone_grid:
+                pipe.dev.debug_set(capi.DEBUG_CONE_GRID, 1)
+            if args.reserve_sms:
+                pipe.dev.debug_set(capi.DEBUG_CONE_RESERVE_SMS, args.reserve_sms)
             self.pipes.append(pipe)
             self.streams.append(torch.cuda.ExternalStream(int(pipe.dev.L.vct_device_stream(pipe.dev.h)), device=torch.device("cuda", local_rank)))
             # size the fragment arena for this rank's slab before anything is timed (the library grows it on overflow and asks for a re-run)
@@ -346,7 +359,10 @@ def e2e_loop(rig: Rig, steps: int):
     torch, sc, rank, world = rig.torch, rig.sc, rig.rank, rig.world
     W, H = rig.cfg["W"], rig.cfg["H"]
     F = rig.F
-    host_frames = [torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(2 * F)] if rank == 0 else None
+    # ring of 3F pinned frames: the copy of frame i out of its pipeline's snapshot is started by that pipeline's NEXT frame (i + F, see
+    # vct_target_download_frame_async), so the host collects frame i - 2F while frame i is being enqueued and never waits on work it has only just queued
+    NB = 3 * F
+    host_frames = [torch.empty((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32) for _ in range(NB)] if rank == 0 else None
     for i in range(2 * F):
         pipe = rig.next_pipe()
         pipe.scene.upload(sc); pipe.render_frame(rig.view, rig.proj, rig.prm)
@@ -360,10 +376,10 @@ def e2e_loop(rig: Rig, steps: int):
         pipe.scene.upload(sc)                                # H2D: geometry, materials, draw list (pinned staging ring, async)
         pipe.render_frame(rig.view, rig.proj, rig.prm)
         if rank == 0:
-            pending.append((pipe, pipe.target.frame_async(host_frames[i % (2 * F)])))   # D2H of this frame, asynchronous: overlaps the next frame(s)
-            if len(pending) > F:
+            if len(pending) >= 2 * F:
                 q, tk = pending.pop(0)
-                q.target.wait(tk)                             # frame i-F is in host memory
+                q.target.wait(tk)                             # frame i-2F is in host memory (its buffer is reused by frame i+F)
+            pending.append((pipe, pipe.target.frame_async(host_frames[i % NB])))   # D2H of this frame, asynchronous: overlaps the next frames
     for q, tk in pending:
         q.target.wait(tk)
     for pipe in rig.pipes:
@@ -474,7 +490,7 @@ def run_extra(cfg_id, args, rank, world, local_rank, torch, dist, fp16: bool = F
         if world > 1 and st is not None:
             per_rank = [None] * world
             dist.all_gather_object(per_rank, {k: round(v, 1) for k, v in st.items()})
-        wl = config_dict(cfg, world, args.sampler, args.exchange, rig.sc.n_triangles, args.frames_in_flight)["workload"]
+        wl = config_dict(cfg, world, args.sampler, args.exchange, rig.sc.n_triangles, rig.F)["workload"]
         if fp16:
             wl = wl.replace("RGBA8, 7 levels", "RGBA16F grid, full chain of %d levels: BASELINE config 5's storage variant, fp32 software filtering" % cfg["R"].bit_length())
         out = {"workload": wl, "ms_per_frame": ms, "frames_per_s": 1e3 / ms,
@@ -546,7 +562,7 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
         cpu = {"value": 1.0 / fs, "unit": "frames/s", "cores": wl.cores, "kind": "port", "sample": wl.sample_text(stride) + " (4 steps)",
                "frame_s": fs, "voxelize_s": wl.t_vox, "mip_s": wl.t_mip, "gbuffer_s": wl.t_gbuf}
 
-    n_tris = rig.sc.n_triangles
+    n_tris, n_fif = rig.sc.n_triangles, rig.F
     rig.close()
     extra = None
     if not args.no_extra and args.config == 2 and not args.fp16 and (world == 1 or args.exchange == "p2p"):
@@ -557,7 +573,7 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
     if rank == 0:
         out = {"metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 RGBA storage)",
-               "data": "synthetic", "config": dict(config_dict(cfg, world, args.sampler, args.exchange, n_tris, args.frames_in_flight), **({"storage": "RGBA16F, full mip chain (variant)"} if args.fp16 else {})),
+               "data": "synthetic", "config": dict(config_dict(cfg, world, args.sampler, args.exchange, n_tris, n_fif), **({"storage": "RGBA16F, full mip chain (variant)"} if args.fp16 else {})),
                "clocks": clocks, "e2e": e2e, "gpu_launches": KERNELS_PER_FRAME * args.steps, "roofline": roof, "cpu_baseline": cpu}
         if stages:
             out["stages"] = stages
@@ -578,10 +594,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
     ap.add_argument("--fp16", action="store_true", help="run the chosen config with the RGBA16F grid + full mip chain storage variant (one GPU; not the headline)")
-    ap.add_argument("--frames-in-flight", type=int, default=2, choices=[1, 2, 3],
-                    help="independent pipelines rendering alternate frames (the front half of frame i+1 runs beside the trace of frame i); 1 = the plain loop")
+    ap.add_argument("--frames-in-flight", type=int, default=0, choices=[0, 1, 2, 3],
+                    help="independent pipelines rendering alternate frames (the front half of frame i+1 runs beside the trace of frame i); 1 = the plain loop, 0 = automatic (2 for scenes of <= 64 k triangles)")
     ap.add_argument("--trace-stream", default="shared", choices=["shared", "own"],
                     help="frames in flight: cones + shade of all pipelines on one low-priority stream per GPU (default) or on each pipeline's own stream")
+    ap.add_argument("--cone-grid", action="store_true", help="experiment: cone kernel on a host-sized grid instead of the persistent work queue")
+    ap.add_argument("--reserve-sms", type=int, default=0, help="experiment: SMs the persistent cone kernel leaves to the other pipeline's front half")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the device-timed runs of configs 4 and 5 (extra_configs)")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],

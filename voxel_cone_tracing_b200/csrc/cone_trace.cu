@@ -71,6 +71,7 @@ struct TraceArgs {
   int n_diffuse, n_slots;
   int n_jobs;                  // work items per live tile of cone_kernel_fast
   uint32_t* work_counter;      // next (job, tile) item of the persistent cone kernel; zeroed by tile_list_kernel
+  int tile_k;                  // multi-GPU split of the frame: lattice step of screen_tile_owner for prm.tile_nranks
   uint32_t first_reserved_sm;  // persistent cone kernel: CTAs placed on an SM with %smid >= this retire at once (SMs left to another frame's front half)
   int grouped;                 // cone_out layout: 0 = [slot][pixel]; 1 = [job][pixel] with job 0 = SUM of the diffuse cones, 1 specular, 2 refraction, 3 + i shadow of light i
   const uint32_t* tile_list;   // live 8x4 tiles (tile_y * tiles_x + tile_x), built by tile_list_kernel
@@ -519,7 +520,7 @@ __device__ __forceinline__ Pixel load_pixel(const TraceArgs& a, int px, int py) 
 __device__ __forceinline__ bool tile_is_mine(const TraceArgs& a, int tile_x, int tile_y) {
   // multi-GPU split: 32x32 screen tiles are dealt to the ranks on a diagonal lattice (screen_tile_owner)
   if (a.prm.tile_nranks <= 1) return true;
-  return screen_tile_owner(tile_x / 4, tile_y / 8, a.prm.tile_nranks) == a.prm.tile_rank;
+  return screen_tile_owner(tile_x / 4, tile_y / 8, a.prm.tile_nranks, a.tile_k) == a.prm.tile_rank;
 }
 
 // Compacts the 8x4 tiles that contain at least one shaded pixel.  One warp takes kTilesPerWarp consecutive tiles: the G-buffer
@@ -872,7 +873,7 @@ frame_push_kernel(const TraceArgs a) {
   const int tiles_x = (a.W + 31) >> 5, tiles_y = (a.H + 31) >> 5;
   for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
     const int tx = tile % tiles_x, ty = tile / tiles_x;
-    if (screen_tile_owner(tx, ty, a.pv.nranks) != a.pv.rank) continue;
+    if (screen_tile_owner(tx, ty, a.pv.nranks, a.tile_k) != a.pv.rank) continue;
     const int x0 = tx * 32, y0 = ty * 32;
     for (int u = threadIdx.x; u < 32 * 8; u += blockDim.x) {   // 32 rows x 8 uint4
       const int x = x0 + 4 * (u & 7), y = y0 + (u >> 3);
@@ -907,6 +908,7 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
   a.cam_pos[0] = view[12]; a.cam_pos[1] = view[13]; a.cam_pos[2] = view[14];
   a.prm = *p;
   if (a.prm.tile_nranks < 1) { a.prm.tile_nranks = 1; a.prm.tile_rank = 0; }
+  a.tile_k = screen_tile_k(a.prm.tile_nranks);
   a.counts = (unsigned long long*)(dev->counters + 16);
   a.n_diffuse = p->n_diffuse_cones == 5 ? 5 : (p->n_diffuse_cones == 16 ? 16 : 9);
   a.n_slots = a.n_diffuse + 2 + sc->lights.n;

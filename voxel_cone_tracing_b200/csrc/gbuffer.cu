@@ -121,8 +121,15 @@ __device__ __noinline__ int cam_clip_pieces(const vct_vertex_t* __restrict__ ver
   return n_pieces;
 }
 
+// tile_rank carries the lattice step in its high half (launch_gbuffer): rank | screen_tile_k(nranks) << 16.  The multi-GPU test is a
+// call, not inline: written inline, the compiler evaluates the modulo speculatively inside the rasterisers' pixel loops also when
+// tile_nranks == 1 (measured: cam_setup_kernel of the 1 M-triangle scene on one GPU 665 -> 1040 us).
+__device__ __noinline__ bool tile_owned_split(int i, int j, int tile_rank, int tile_nranks) {
+  return screen_tile_owner(i >> 5, j >> 5, tile_nranks, tile_rank >> 16) == (tile_rank & 0xFFFF);
+}
 __device__ __forceinline__ bool tile_owned(int i, int j, int W, int tile_rank, int tile_nranks) {
-  return tile_nranks <= 1 || screen_tile_owner(i >> 5, j >> 5, tile_nranks) == tile_rank;
+  if (tile_nranks <= 1) return true;
+  return tile_owned_split(i, j, tile_rank, tile_nranks);
 }
 
 // depth test of every covered pixel of a piece, one lane per piece (the sub-tile triangles of a large scene)
@@ -523,6 +530,8 @@ static void mat4_mul_host(const float* a, const float* b, float* out) {  // colu
 
 int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const float* proj, vct_target_t_* t, int tile_rank, int tile_nranks, bool tile_list) {
   cudaStream_t s = dev->stream;
+  if (tile_nranks < 1) { tile_nranks = 1; tile_rank = 0; }
+  tile_rank |= screen_tile_k(tile_nranks) << 16;   // the kernels' tile_owned() unpacks it
   const size_t npx = (size_t)t->W * t->H;
   const int n_tiles = ((t->W + 7) / 8) * ((t->H + 3) / 4);
   if (tile_list && !t->tile_list) VCT_CUDA(cudaMalloc(&t->tile_list, ((size_t)n_tiles + 1) * sizeof(uint32_t)));

@@ -164,10 +164,9 @@ __device__ __forceinline__ void peer_signal_last_block(const PeerView& pv, int k
 // Multi-GPU split of the frame: which rank owns the 32x32 screen tile (tx, ty).  A diagonal lattice -- (tx + k ty) mod n with k coprime to n --
 // spreads every rank's tiles evenly in both directions; plain round-robin over the row-major tile index gives (tx + 60 ty) mod 8 =
 // (tx + 4 ty) mod 8 at 1920 pixels: two column phases only, which line up with the walls of the scene (cone kernel 117..128 us per rank at N = 8).
-__host__ __device__ __forceinline__ int screen_tile_owner(int tx, int ty, int nranks) {
-  const int k = nranks % 3 ? 3 : (nranks % 5 ? 5 : 7);
-  return (tx + k * ty) % nranks;
-}
+// k is computed once per launch on the host (screen_tile_k) and travels with the kernel arguments: one modulo per test on the device.
+__host__ __device__ __forceinline__ int screen_tile_k(int nranks) { return nranks % 3 ? 3 : (nranks % 5 ? 5 : 7); }
+__host__ __device__ __forceinline__ int screen_tile_owner(int tx, int ty, int nranks, int k) { return (tx + k * ty) % nranks; }
 
 // surface handles of the stacked mipmapped array: s[grid level], level >= 1; direction d starts at z = d * pitch[level]
 struct SurfSet {

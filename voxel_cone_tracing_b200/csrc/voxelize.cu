@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kSetupThreads)
 vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ draws,
                  uint32_t n_draws, uint32_t n_tris, float cube_size, int R, int z0, int z1, VoxTri* __restrict__ out, uint32_t* __restrict__ item_local,
                  uint32_t* __restrict__ item_block, const FragCtx ctx, int small_limit, int mid_limit, uint32_t* scan_ticket, uint32_t* scan_total) {
-  __shared__ VoxTri stage[kSetupThreads / 32];   // the triangle the warp is rasterising together
+  __shared__ VoxTri stage[kSetupThreads];   // the mid-sized triangles of the block, one slot per lane: the warp rasterises them together
   uint32_t t = blockIdx.x * kSetupThreads + threadIdx.x;
   uint32_t count = 0;
   VoxTri v;
@@ -246,27 +246,54 @@ vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
     const int i = v.rt.imin + p % bw, j = v.rt.jmin + p / bw;
     if (edge_block_sample(eb0, p % bw, p / bw, b) && fragment_voxel(ctx, v, b, pos, voxel)) push_fragment(ctx, v, t, i, j, b, pos, voxel, slot++);
   }
-  // ---- mid-sized triangles: the whole warp on one triangle at a time ----
+  // ---- mid-sized triangles: the whole warp on one triangle at a time, in TWO passes over the warp's mid triangles: count the fragments,
+  // reserve their arena slots with ONE atomic, write them.  (One reservation per 8 x 4-pixel step -- four or five per triangle -- made the
+  // warp wait for an L2 atomic round trip every few dozen instructions: the set-up kernel of the 4 M-triangle scene spent its time there.)
   const bool mid = count > 0 && !small && bw * bh <= mid_limit;
-  for (uint32_t m = __ballot_sync(0xffffffffu, mid); m; m &= m - 1u) {
-    const int src = __ffs((int)m) - 1;
-    VoxTri& sv = stage[threadIdx.x >> 5];
+  const uint32_t mid_mask = __ballot_sync(0xffffffffu, mid);
+  if (mid_mask) {
+    VoxTri* wst = stage + (threadIdx.x & ~31);   // this warp's 32 slots
+    if (mid) wst[lane] = v;
     __syncwarp();
-    if (lane == src) sv = v;
-    __syncwarp();
-    const uint32_t ti = __shfl_sync(0xffffffffu, t, src);
-    const RasterTri& rt = sv.rt;
     const int lx = lane & 7, ly = lane >> 3;
-    EdgeBlock eb;
-    edge_block_setup(rt, rt.imin, rt.jmin, eb);
-    for (int j0 = rt.jmin; j0 <= rt.jmax; j0 += 4)
-      for (int i0 = rt.imin; i0 <= rt.imax; i0 += 8) {   // uniform trip counts: every lane reaches emit_fragments (warp-wide ballots)
-        int pi[1] = {i0 + lx}, pj[1] = {j0 + ly};
-        float pb[1][3];
-        bool covered[1];
-        covered[0] = pi[0] <= rt.imax && pj[0] <= rt.jmax && edge_block_sample(eb, pi[0] - rt.imin, pj[0] - rt.jmin, pb[0]);
-        emit_fragments<1>(ctx, sv, ti, pi, pj, pb, covered, lane);
+    uint32_t total = 0;
+    for (uint32_t m = mid_mask; m; m &= m - 1u) {
+      const VoxTri& sv = wst[__ffs((int)m) - 1];
+      const RasterTri& rt = sv.rt;
+      EdgeBlock eb;
+      edge_block_setup(rt, rt.imin, rt.jmin, eb);
+      for (int j0 = rt.jmin; j0 <= rt.jmax; j0 += 4)
+        for (int i0 = rt.imin; i0 <= rt.imax; i0 += 8) {   // uniform trip counts (warp-wide ballots)
+          const int pi = i0 + lx, pj = j0 + ly;
+          float pb[3];
+          F3 pos; uint32_t voxel;
+          const bool covered = pi <= rt.imax && pj <= rt.jmax && edge_block_sample(eb, pi - rt.imin, pj - rt.jmin, pb) && fragment_voxel(ctx, sv, pb, pos, voxel);
+          total += (uint32_t)__popc(__ballot_sync(0xffffffffu, covered));
+        }
+    }
+    if (total) {
+      uint32_t basei = 0;
+      if (lane == 0) basei = atomicAdd(&ctx.counters[CNT_FRAGS], total);
+      basei = __shfl_sync(0xffffffffu, basei, 0);
+      for (uint32_t m = mid_mask; m; m &= m - 1u) {
+        const int src = __ffs((int)m) - 1;
+        const VoxTri& sv = wst[src];
+        const uint32_t ti = __shfl_sync(0xffffffffu, t, src);
+        const RasterTri& rt = sv.rt;
+        EdgeBlock eb;
+        edge_block_setup(rt, rt.imin, rt.jmin, eb);
+        for (int j0 = rt.jmin; j0 <= rt.jmax; j0 += 4)
+          for (int i0 = rt.imin; i0 <= rt.imax; i0 += 8) {
+            const int pi = i0 + lx, pj = j0 + ly;
+            float pb[3];
+            F3 pos; uint32_t voxel;
+            const bool covered = pi <= rt.imax && pj <= rt.jmax && edge_block_sample(eb, pi - rt.imin, pj - rt.jmin, pb) && fragment_voxel(ctx, sv, pb, pos, voxel);
+            const uint32_t cm = __ballot_sync(0xffffffffu, covered);
+            if (covered) push_fragment(ctx, sv, ti, pi, pj, pb, pos, voxel, basei + (uint32_t)__popc(cm & ((1u << lane) - 1u)));
+            basei += (uint32_t)__popc(cm);
+          }
       }
+    }
   }
   if (small || mid) count = 0;
   else if (t < n_tris) out[t] = v;   // only triangles that become work items are read again
