@@ -65,9 +65,12 @@ def config_dict(cfg, world: int, sampler: int, exchange: str, n_tris: int, fif: 
     """identical for both arms (the driver compares them)"""
     R, W, H = cfg["R"], cfg["W"], cfg["H"]
     par = f"z-slab voxelize + screen-tile trace x{world}"
-    if world > 1:
-        par += (", sparse NVLink peer-store exchange fused into the resolve/shade kernels (CUDA IPC, no collective)" if exchange == "p2p"
-                else ", NCCL all-gather of the base level + all-reduce of the frame")
+    if world > 1 and exchange == "p2p":
+        par = ((f"every rank voxelizes the whole scene (<= 16 k triangles: no voxel exchange) + screen-tile trace x{world}" if n_tris <= 16384 else
+                f"z-slab voxelize with sparse voxel push over NVLink peer memory fused into the resolve kernel + screen-tile trace x{world}")
+               + ", finished tiles stored into the root's frame over NVLink (CUDA IPC, epoch flags, no collective)")
+    elif world > 1:
+        par += ", NCCL all-gather of the base level + all-reduce of the frame"
     ws = (7.43 * R ** 3 + W * H * 40) / 1e6
     return {"workload": cfg["name"] + ", revoxelize+mip+gbuffer+trace per frame, %d diffuse + 1 specular + 1 shadow cone" % cfg.get("cones", 9),
             "sampler": "texture units (levels >= 1), software level 0" if sampler == 1 else "software fp32 trilinear",
@@ -244,6 +247,8 @@ class Rig:
                                  fmt=capi.GRID_RGBA16F if fp16 else capi.GRID_RGBA8)
             if self.F > 1 and args.trace_stream == "shared":
                 pipe.dev.debug_set(capi.DEBUG_TRACE_LOW_PRIORITY, 1)
+            if args.replicate >= 0:
+                pipe.dev.debug_set(capi.DEBUG_PEER_REPLICATE, args.replicate)
             if args.cone_grid:
                 pipe.dev.debug_set(capi.DEBUG_CONE_GRID, 1)
             if args.reserve_sms:
@@ -598,6 +603,8 @@ def main():
                     help="independent pipelines rendering alternate frames (the front half of frame i+1 runs beside the trace of frame i); 1 = the plain loop, 0 = automatic (2 for scenes of <= 64 k triangles)")
     ap.add_argument("--trace-stream", default="shared", choices=["shared", "own"],
                     help="frames in flight: cones + shade of all pipelines on one low-priority stream per GPU (default) or on each pipeline's own stream")
+    ap.add_argument("--replicate", type=int, default=-1, choices=[-1, 0, 1],
+                    help="multi-GPU voxelization: 1 = every rank voxelizes the whole scene, 0 = z-slabs + voxel push, -1 = by scene size (library default)")
     ap.add_argument("--cone-grid", action="store_true", help="experiment: cone kernel on a host-sized grid instead of the persistent work queue")
     ap.add_argument("--reserve-sms", type=int, default=0, help="experiment: SMs the persistent cone kernel leaves to the other pipeline's front half")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

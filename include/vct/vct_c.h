@@ -176,6 +176,10 @@ int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_targ
  * beside [0]-[2], this is what is left of it after the mip build) [4] trace (tile list + cones + shade) [5] total
  * [6] cone kernel alone [7] the G-buffer pass itself on its own stream (0 when it ran in line); synchronises */
 int vct_last_frame_timings(vct_device_t* dev, float out_ms[8]);
+/* measurement: the event times of dev's last frame relative to the START of ref's last frame (two device objects of one process: frames
+ * in flight), ms: [0] frame start [1] clear done [2] voxelize done [3] mip done [4] front half done (G-buffer joined) [5] frame done
+ * [6] cone kernel start [7] cone kernel end; -1 where an event was not recorded.  Synchronises. */
+int vct_debug_frame_events(vct_device_t* dev, vct_device_t* ref, float out_ms[8]);
 
 /* measurement / test switches (replace the environment variables of round 1; nothing on the launch path reads the environment):
  *   VCT_DEBUG_MIP_DENSE    1 = every vct_mipmap reads and writes every tile (the dense build a first frame or an upload pays)

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libvct_cuda.so")
 
 EXPORTS = [
-    "vct_device_create", "vct_device_destroy", "vct_device_sync", "vct_device_stream", "vct_last_error", "vct_version",
+    "vct_debug_frame_events", "vct_device_create", "vct_device_destroy", "vct_device_sync", "vct_device_stream", "vct_last_error", "vct_version",
     "vct_scene_create", "vct_scene_destroy", "vct_scene_set_geometry", "vct_scene_set_materials", "vct_scene_set_draws",
     "vct_scene_set_lights", "vct_scene_set_cube_size",
     "vct_grid_create", "vct_grid_create_ex", "vct_grid_download_f16", "vct_grid_destroy", "vct_grid_clear", "vct_grid_upload_base", "vct_grid_download",
@@ -80,6 +80,7 @@ def load():
     L.vct_device_create.argtypes = [i32, C.POINTER(vp)]
     L.vct_device_destroy.argtypes = [vp]
     L.vct_device_sync.argtypes = [vp]
+    L.vct_debug_frame_events.argtypes = [vp, vp, C.POINTER(C.c_float)]
     L.vct_device_stream.argtypes = [vp]; L.vct_device_stream.restype = vp
     L.vct_scene_create.argtypes = [vp, C.POINTER(vp)]
     L.vct_scene_destroy.argtypes = [vp]

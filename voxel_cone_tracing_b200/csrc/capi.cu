@@ -871,8 +871,6 @@ static int render_frame_sharded(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* 
     int rc;
     VCT_CUDA(cudaEventRecord(dev->ev[0], s));
     VCT_CUDA(cudaEventRecord(dev->ev_fork, s));
-    // PUSHED(e) of rank r now only says "r has finished everything it had queued before frame e": its frame buffer may receive tiles of e
-    if ((rc = launch_peer_signal(dev, pv, PEER_FLAG_PUSHED))) return rc;
     if ((rc = vct_grid_clear(g))) return rc;
     VCT_CUDA(cudaEventRecord(dev->ev[1], s));
     if ((rc = launch_voxelize(dev, sc, g, 0, g->R))) return rc;
@@ -881,7 +879,10 @@ static int render_frame_sharded(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* 
     dev->stream = dev->stream2;
     VCT_CUDA(cudaEventRecord(dev->ev_g0, dev->stream2));
     const bool fused_list = prm.view_voxel_dir >= 7;
-    rc = launch_gbuffer(dev, sc, view, proj, t, pv.rank, pv.nranks, fused_list);
+    // PUSHED(e) of rank r now only says "r has finished everything it had queued before frame e" (the fork event): its frame buffer may
+    // receive tiles of e.  Sent from the second stream: a system fence + N remote stores that the critical path need not wait for.
+    rc = launch_peer_signal(dev, pv, PEER_FLAG_PUSHED);
+    if (!rc) rc = launch_gbuffer(dev, sc, view, proj, t, pv.rank, pv.nranks, fused_list);
     if (!rc && !fused_list) rc = launch_cone_trace(dev, sc, g, view, &prm, t, false, &pv, 1);
     dev->stream = s;
     if (rc) return rc;
@@ -995,6 +996,18 @@ int vct_render_frame(vct_device_t* dev, vct_scene_t* sc, vct_grid_t* g, vct_targ
   VCT_CUDA(cudaEventRecord(dev->ev[5], s));
   dev->have_timings = true;
   dev->gbuffer_overlapped = true;
+  return VCT_OK;
+}
+
+int vct_debug_frame_events(vct_device_t* dev, vct_device_t* ref, float out_ms[8]) {
+  VCT_REQUIRE(dev && ref && out_ms, "null argument");
+  VCT_REQUIRE(dev->have_timings && ref->have_timings, "no frame has been rendered");
+  VCT_CUDA(cudaEventSynchronize(dev->ev[5]));
+  VCT_CUDA(cudaEventSynchronize(ref->ev[5]));
+  for (int i = 0; i < 8; i++) {
+    out_ms[i] = 0.0f;
+    if (cudaEventElapsedTime(&out_ms[i], ref->ev[0], dev->ev[i]) != cudaSuccess) { out_ms[i] = -1.0f; cudaGetLastError(); }
+  }
   return VCT_OK;
 }
 
