@@ -249,6 +249,8 @@ class Rig:
                 pipe.dev.debug_set(capi.DEBUG_TRACE_LOW_PRIORITY, 1)
             if args.replicate >= 0:
                 pipe.dev.debug_set(capi.DEBUG_PEER_REPLICATE, args.replicate)
+            if args.cone_ctas:
+                pipe.dev.debug_set(capi.DEBUG_CONE_CTAS_PER_SM, args.cone_ctas)
             if args.cone_grid:
                 pipe.dev.debug_set(capi.DEBUG_CONE_GRID, 1)
             if args.reserve_sms:
@@ -605,6 +607,7 @@ def main():
                     help="frames in flight: cones + shade of all pipelines on one low-priority stream per GPU (default) or on each pipeline's own stream")
     ap.add_argument("--replicate", type=int, default=-1, choices=[-1, 0, 1],
                     help="multi-GPU voxelization: 1 = every rank voxelizes the whole scene, 0 = z-slabs + voxel push, -1 = by scene size (library default)")
+    ap.add_argument("--cone-ctas", type=int, default=0, help="experiment: CTAs per SM of the persistent cone kernel (default: all that fit, 10)")
     ap.add_argument("--cone-grid", action="store_true", help="experiment: cone kernel on a host-sized grid instead of the persistent work queue")
     ap.add_argument("--reserve-sms", type=int, default=0, help="experiment: SMs the persistent cone kernel leaves to the other pipeline's front half")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

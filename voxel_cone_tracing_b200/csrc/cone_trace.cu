@@ -978,7 +978,7 @@ int launch_cone_trace(vct_device* dev, vct_scene* sc, vct_grid* g, const float* 
       // launch K<TEX, SPLIT, MIN_CTAS, GROUP>: persistent (MIN_CTAS CTAs per SM) or one warp per (tile, job) of the whole frame
 #define VCT_LAUNCH_CONE(TEXV, SPLITV, MINC, GROUPV)                                                                   \
   do {                                                                                                                \
-    if (persist) cone_kernel_fast<TEXV, SPLITV, MINC, GROUPV><<<sms * MINC, 32 * kConeWarps, 0, s>>>(a);              \
+    if (persist) cone_kernel_fast<TEXV, SPLITV, MINC, GROUPV><<<sms * (dev->cone_ctas_per_sm > 0 && dev->cone_ctas_per_sm < MINC ? dev->cone_ctas_per_sm : MINC), 32 * kConeWarps, 0, s>>>(a); \
     else cone_kernel_grid<TEXV, SPLITV, MINC, GROUPV><<<GROUPV ? grid_jobs : grid, 32 * kConeWarps, 0, s>>>(a);       \
   } while (0)
       if (variant == 1) {

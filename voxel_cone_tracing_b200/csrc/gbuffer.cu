@@ -131,15 +131,22 @@ __device__ __forceinline__ bool tile_owned(int i, int j, int W, int tile_rank, i
   if (tile_nranks <= 1) return true;
   return tile_owned_split(i, j, tile_rank, tile_nranks);
 }
+// the set-up kernel is compiled twice (SPLIT = the frame is shared between ranks): its one-GPU build carries no ownership code at all
+template <bool SPLIT>
+__device__ __forceinline__ bool tile_owned_t(int i, int j, int tile_rank, int tile_nranks) {
+  if (!SPLIT) return true;
+  return screen_tile_owner(i >> 5, j >> 5, tile_nranks, tile_rank >> 16) == (tile_rank & 0xFFFF);
+}
 
 // depth test of every covered pixel of a piece, one lane per piece (the sub-tile triangles of a large scene)
+template <bool SPLIT>
 __device__ __forceinline__ void raster_piece_inline(const CamTri& v, uint32_t t, int W, unsigned long long* __restrict__ vis, int tile_rank, int tile_nranks) {
   const int bw = v.rt.imax - v.rt.imin + 1, bh = v.rt.jmax - v.rt.jmin + 1;
   EdgeBlock eb;   // edge functions once at the box origin; a pixel then costs two 32 x 32 -> 64 multiply-adds per edge (same integers as raster_sample)
   edge_block_setup(v.rt, v.rt.imin, v.rt.jmin, eb);
   for (int j = v.rt.jmin; j < v.rt.jmin + bh; j++)
     for (int i = v.rt.imin; i < v.rt.imin + bw; i++) {
-      if (!tile_owned(i, j, W, tile_rank, tile_nranks)) continue;   // multi-GPU: not this rank's screen tile
+      if (!tile_owned_t<SPLIT>(i, j, tile_rank, tile_nranks)) continue;   // multi-GPU: not this rank's screen tile
       float b[3];
       if (edge_block_sample(eb, i - v.rt.imin, j - v.rt.jmin, b)) {
         const float zw = interp3(b, v.zw[0], v.zw[1], v.zw[2]);
@@ -150,6 +157,7 @@ __device__ __forceinline__ void raster_piece_inline(const CamTri& v, uint32_t t,
 
 // depth test of every covered pixel of ONE piece by all 32 lanes: the owner lane's set-up travels by shuffles, the lanes sweep the
 // bounding box in 8 x 4 pixel steps.  Called by the whole warp (src = owner lane); same arithmetic as raster_piece_inline.
+template <bool SPLIT>
 __device__ __forceinline__ void raster_piece_warp(const CamTri& mine, uint32_t my_tri, int src, int lane, int W, unsigned long long* __restrict__ vis,
                                                   int tile_rank, int tile_nranks) {
   RasterTri rt;
@@ -165,10 +173,11 @@ __device__ __forceinline__ void raster_piece_warp(const CamTri& mine, uint32_t m
   const int lx = lane & 7, ly = lane >> 3;
   EdgeBlock eb;
   edge_block_setup(rt, rt.imin, rt.jmin, eb);
-  // steps aligned to the 8 x 4 grid: a step lies inside one 32 x 32 screen tile, so "is it this rank's tile" is one test per step
-  for (int j0 = rt.jmin & ~3; j0 <= rt.jmax; j0 += 4)
-    for (int i0 = rt.imin & ~7; i0 <= rt.imax; i0 += 8) {
-      if (!tile_owned(i0, j0, W, tile_rank, tile_nranks)) continue;   // multi-GPU: another rank shades (and rasterises) this tile
+  // multi-GPU: steps aligned to the 8 x 4 grid -- a step then lies inside one 32 x 32 screen tile and "is it this rank's tile" is one test
+  // per step.  One GPU: steps start at the corner of the bounding box (a 10 x 10-pixel box is 2 x 3 steps, not up to 3 x 4).
+  for (int j0 = SPLIT ? rt.jmin & ~3 : rt.jmin; j0 <= rt.jmax; j0 += 4)
+    for (int i0 = SPLIT ? rt.imin & ~7 : rt.imin; i0 <= rt.imax; i0 += 8) {
+      if (!tile_owned_t<SPLIT>(i0, j0, tile_rank, tile_nranks)) continue;   // another rank shades (and rasterises) this tile
       const int i = i0 + lx, j = j0 + ly;
       if (i < rt.imin || i > rt.imax || j < rt.jmin || j > rt.jmax) continue;
       float b[3];
@@ -180,18 +189,20 @@ __device__ __forceinline__ void raster_piece_warp(const CamTri& mine, uint32_t m
 }
 
 // does the pixel box [i0,i1] x [j0,j1] touch a 32 x 32 screen tile of this rank?  (boxes of up to 3 x 3 tiles are tested exactly, larger ones kept)
+template <bool SPLIT>
 __device__ __forceinline__ bool box_touches_owned_tile(int i0, int i1, int j0, int j1, int W, int tile_rank, int tile_nranks) {
-  if (tile_nranks <= 1) return true;
+  if (!SPLIT) return true;
   const int tx0 = i0 >> 5, tx1 = i1 >> 5, ty0 = j0 >> 5, ty1 = j1 >> 5;
   if (tx1 - tx0 > 2 || ty1 - ty0 > 2) return true;
   for (int ty = ty0; ty <= ty1; ty++)
     for (int tx = tx0; tx <= tx1; tx++)
-      if (tile_owned(tx << 5, ty << 5, W, tile_rank, tile_nranks)) return true;
+      if (tile_owned_t<SPLIT>(tx << 5, ty << 5, tile_rank, tile_nranks)) return true;
   return false;
 }
 
 // A triangle that crosses the near plane, start to finish (called by its own lane only): clip, cull, then every piece either gets a record
 // + work items (returned count) or is depth-tested in line.  Sets big_slot[t].
+template <bool SPLIT>
 __device__ __noinline__ uint32_t cam_setup_clipped(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ d, uint32_t t,
                                                    const float* __restrict__ pvm, int W, int H, CamTri* __restrict__ recs, uint32_t rec_capacity,
                                                    uint32_t* __restrict__ rec_count, uint32_t* __restrict__ big_slot, unsigned long long* __restrict__ vis,
@@ -202,7 +213,7 @@ __device__ __noinline__ uint32_t cam_setup_clipped(const vct_vertex_t* __restric
   int n_big = 0;
   for (int q = 0; q < n; q++) {
     const RasterTri& rt = pc[q].rt;
-    if (!box_touches_owned_tile(rt.imin, rt.imax, rt.jmin, rt.jmax, W, tile_rank, tile_nranks)) { pc[q].rt.sign = 0; continue; }
+    if (!box_touches_owned_tile<SPLIT>(rt.imin, rt.imax, rt.jmin, rt.jmax, W, tile_rank, tile_nranks)) { pc[q].rt.sign = 0; continue; }
     big[q] = (rt.imax - rt.imin + 1) * (rt.jmax - rt.jmin + 1) > record_limit;
     n_big += big[q] ? 1 : 0;
   }
@@ -219,7 +230,7 @@ __device__ __noinline__ uint32_t cam_setup_clipped(const vct_vertex_t* __restric
       count += pc[q].pad;
       recs[slot++] = pc[q];
     } else {
-      raster_piece_inline(pc[q], t, W, vis, tile_rank, tile_nranks);
+      raster_piece_inline<SPLIT>(pc[q], t, W, vis, tile_rank, tile_nranks);
     }
   }
   return count;
@@ -227,6 +238,7 @@ __device__ __noinline__ uint32_t cam_setup_clipped(const vct_vertex_t* __restric
 
 // big_slot[t]: 0 = the triangle has no records (culled, or rasterised in line: the resolve kernel re-runs the vertex stage);
 // else 1 + index of its first record in `recs` | (number of records - 1) << 31.  recs[slot].pad = work items of that record.
+template <bool SPLIT>
 __global__ void __launch_bounds__(kSetupThreads)
 cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restrict__ indices, const DrawRec* __restrict__ draws,
                  uint32_t n_draws, uint32_t n_tris, Mat4 pv, int W, int H, CamTri* __restrict__ recs, uint32_t rec_capacity, uint32_t* __restrict__ rec_count,
@@ -249,7 +261,7 @@ cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
       // multi-GPU: a piece whose bounding box touches none of this rank's screen tiles is somebody else's work (a sub-tile triangle of a
       // 4 M-triangle scene touches one or two tiles: seven eighths of them end here on each of eight ranks)
       const bool have = cam_make_piece(in[0], in[1], in[2], W, H, dp->material, pc) &&
-                        box_touches_owned_tile(pc.rt.imin, pc.rt.imax, pc.rt.jmin, pc.rt.jmax, W, tile_rank, tile_nranks);
+                        box_touches_owned_tile<SPLIT>(pc.rt.imin, pc.rt.imax, pc.rt.jmin, pc.rt.jmax, W, tile_rank, tile_nranks);
       uint32_t bs = 0u;
       if (have) {
         const int area = (pc.rt.imax - pc.rt.imin + 1) * (pc.rt.jmax - pc.rt.jmin + 1);
@@ -266,18 +278,18 @@ cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
             mid = true;
           }
         } else if (!mid) {
-          raster_piece_inline(pc, t, W, vis, tile_rank, tile_nranks);
+          raster_piece_inline<SPLIT>(pc, t, W, vis, tile_rank, tile_nranks);
         }
       }
       big_slot[t] = bs;
     } else if (n_out < 3) {
-      count = cam_setup_clipped(verts, indices, dp, t, pv.m, W, H, recs, rec_capacity, rec_count, big_slot, vis, tile_rank, tile_nranks, mid_limit);
+      count = cam_setup_clipped<SPLIT>(verts, indices, dp, t, pv.m, W, H, recs, rec_capacity, rec_count, big_slot, vis, tile_rank, tile_nranks, mid_limit);
     } else {
       big_slot[t] = 0u;
     }
   }
   // the mid-sized pieces of the warp's 32 triangles, one after the other, all lanes on each
-  for (uint32_t m = __ballot_sync(0xffffffffu, mid); m; m &= m - 1u) raster_piece_warp(pc, t, __ffs((int)m) - 1, lane, W, vis, tile_rank, tile_nranks);
+  for (uint32_t m = __ballot_sync(0xffffffffu, mid); m; m &= m - 1u) raster_piece_warp<SPLIT>(pc, t, __ffs((int)m) - 1, lane, W, vis, tile_rank, tile_nranks);
   block_scan_items(count, t, n_tris, item_local, item_block, scan_ticket, scan_total);
 }
 
@@ -553,7 +565,13 @@ int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const floa
     const uint32_t n_blocks = (sc->n_tris + kSetupThreads - 1) / kSetupThreads;
     CamTri* recs = (CamTri*)dev->rs[1].tri_recs;
     const bool many = sc->n_tris >= kSmallPathMinTris;
-    cam_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, pv, t->W, t->H, recs, (uint32_t)rec_capacity, rec_count,
+    if (tile_nranks > 1)
+      cam_setup_kernel<true><<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, pv, t->W, t->H, recs, (uint32_t)rec_capacity, rec_count,
+                                                        dev->rs[1].big_slot, dev->rs[1].item_local, dev->rs[1].item_block, t->vis, tile_rank, tile_nranks,
+                                                        many ? kSmallCamPixels : 0, many ? kMidCamPixels : 0, dev->counters + CNT_TICKET_CAM,
+                                                        dev->counters + CNT_CAM_ITEMS);
+    else
+      cam_setup_kernel<false><<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, pv, t->W, t->H, recs, (uint32_t)rec_capacity, rec_count,
                                                         dev->rs[1].big_slot, dev->rs[1].item_local, dev->rs[1].item_block, t->vis, tile_rank, tile_nranks,
                                                         many ? kSmallCamPixels : 0, many ? kMidCamPixels : 0, dev->counters + CNT_TICKET_CAM,
                                                         dev->counters + CNT_CAM_ITEMS);
