@@ -383,52 +383,29 @@ sparse_clear_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ fra
   }
 }
 
-// One thread per arena slot; the thread of a voxel's FIRST fragment (`fresh`) resolves the voxel.
-__global__ void __launch_bounds__(128)
-vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frags, const uint8_t* __restrict__ fresh,
-                   uint32_t* __restrict__ counters, uint32_t frag_capacity, const PeerView pv, uint8_t* __restrict__ tile_touched, int logR,
-                   uint32_t* __restrict__ status, unsigned long long* __restrict__ accum, int fmt16) {
-  // arena too small: fragments were dropped.  Tell the host through the mapped status word (the only time this kernel touches host memory)
-  if (blockIdx.x == 0 && threadIdx.x == 0 && counters[CNT_FRAGS] > frag_capacity) {
-    *reinterpret_cast<volatile uint32_t*>(status + STATUS_OVERFLOW) = counters[CNT_FRAGS];
-    __threadfence_system();
-  }
-  const uint32_t n_frags = min(counters[CNT_FRAGS], frag_capacity);
-  uint32_t n_mine = 0, max_list = 0;
-  const int lane = threadIdx.x & 31;
-  // warp-uniform trip count: the list of pushed voxels (multi-GPU) is appended with one atomic per warp and round
-  for (uint32_t f0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; f0 < n_frags; f0 += gridDim.x * blockDim.x) {
-    const uint32_t f = f0 + lane;
-    const bool mine = f < n_frags && fresh[f];
-    uint32_t list_pos = 0;
-    if (pv.pushed) {
-      const uint32_t mm = __ballot_sync(0xffffffffu, mine);
-      if (mm) {
-        if (lane == 0) list_pos = atomicAdd(pv.pushed_n, (uint32_t)__popc(mm));
-        list_pos = __shfl_sync(0xffffffffu, list_pos, 0) + (uint32_t)__popc(mm & ((1u << lane) - 1u));
-      }
+// Resolves the voxel whose first fragment sits in arena slot f: sorts the voxel's fragment list by the canonical key and folds it with the
+// reference's running average (or reads the fixed-point accumulators), stores the word, marks the mip tile, multi-GPU: stores into the
+// peers.  Returns the number of fragments of the voxel.
+__device__ __forceinline__ uint32_t resolve_voxel(uint32_t f, uint32_t list_pos, uint32_t* __restrict__ base, const FragRec* __restrict__ frags, const PeerView& pv,
+                                                  uint8_t* __restrict__ tile_touched, int logR, unsigned long long* __restrict__ accum, int fmt16) {
+  const uint32_t voxel = frags[f].voxel;
+  uint32_t stored = 0u, n = 0;
+  if (accum) {
+    // fixed-point variant: rounded integer mean of the voxel's fragments; the accumulators are left zero for the next frame
+    const unsigned long long a0 = accum[2 * (size_t)f], a1 = accum[2 * (size_t)f + 1];
+    accum[2 * (size_t)f] = 0ull; accum[2 * (size_t)f + 1] = 0ull;
+    n = (uint32_t)(a0 >> 48);
+    const uint32_t h = n >> 1, s0 = (uint32_t)(a0 & 0xFFFFFFu), s1 = (uint32_t)((a0 >> 24) & 0xFFFFFFu), s2 = (uint32_t)(a1 & 0xFFFFFFu), s3 = (uint32_t)((a1 >> 24) & 0xFFFFFFu);
+    stored = ((s0 + h) / n) | ((s1 + h) / n) << 8 | ((s2 + h) / n) << 16 | ((s3 + h) / n) << 24;
+    if (fmt16) {
+      // RGBA16F storage variant: the mean colour in [0,1] rounded to half (same expression as the oracle, IEEE division)
+      const float dn = (float)n * 255.0f;
+      const unsigned long long h0 = __half_as_ushort(__float2half_rn((float)s0 / dn)), h1 = __half_as_ushort(__float2half_rn((float)s1 / dn));
+      const unsigned long long h2 = __half_as_ushort(__float2half_rn((float)s2 / dn)), h3 = __half_as_ushort(__float2half_rn((float)s3 / dn));
+      reinterpret_cast<unsigned long long*>(base)[voxel] = h0 | (h1 << 16) | (h2 << 32) | (h3 << 48);
+      return n;
     }
-    if (!mine) continue;
-    n_mine++;
-    const uint32_t voxel = frags[f].voxel;
-    uint32_t stored = 0u, n = 0;
-    if (accum) {
-      // fixed-point variant: rounded integer mean of the voxel's fragments; the accumulators are left zero for the next frame
-      const unsigned long long a0 = accum[2 * (size_t)f], a1 = accum[2 * (size_t)f + 1];
-      accum[2 * (size_t)f] = 0ull; accum[2 * (size_t)f + 1] = 0ull;
-      n = (uint32_t)(a0 >> 48);
-      const uint32_t h = n >> 1, s0 = (uint32_t)(a0 & 0xFFFFFFu), s1 = (uint32_t)((a0 >> 24) & 0xFFFFFFu), s2 = (uint32_t)(a1 & 0xFFFFFFu), s3 = (uint32_t)((a1 >> 24) & 0xFFFFFFu);
-      stored = ((s0 + h) / n) | ((s1 + h) / n) << 8 | ((s2 + h) / n) << 16 | ((s3 + h) / n) << 24;
-      if (fmt16) {
-        // RGBA16F storage variant: the mean colour in [0,1] rounded to half (same expression as the oracle, IEEE division)
-        const float dn = (float)n * 255.0f;
-        const unsigned long long h0 = __half_as_ushort(__float2half_rn((float)s0 / dn)), h1 = __half_as_ushort(__float2half_rn((float)s1 / dn));
-        const unsigned long long h2 = __half_as_ushort(__float2half_rn((float)s2 / dn)), h3 = __half_as_ushort(__float2half_rn((float)s3 / dn));
-        reinterpret_cast<unsigned long long*>(base)[voxel] = h0 | (h1 << 16) | (h2 << 32) | (h3 << 48);
-        max_list = max(max_list, n);
-        continue;
-      }
-    } else {
+  } else {
     const uint32_t head = base[voxel];
     unsigned long long keys[kSortMax];
     uint32_t ids[kSortMax];
@@ -460,18 +437,66 @@ vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frag
         first = false;
       }
     }
+  }
+  base[voxel] = stored;
+  const uint32_t tile = tile_of_voxel(voxel, logR);
+  if (tile_touched) tile_touched[tile] = 1;   // sparse mip build: this 32x8x8 tile has content
+  // multi-GPU: the slab owner writes the resolved voxel straight into every peer's grid over NVLink (sparse
+  // exchange: only occupied voxels travel; replaces the dense all-gather of the base level)
+  for (int p = 0; p < pv.nranks; p++) {
+    if (p != pv.rank) pv.base[p][voxel] = stored;
+    if (pv.touched[p]) pv.touched[p][tile] = 1;   // keeps every rank's mip build sparse (own rank included)
+  }
+  if (pv.pushed && list_pos < pv.pushed_capacity) pv.pushed[list_pos] = voxel;
+  return n;
+}
+
+// The warp scans arena slots, 32 at a time, and queues the slots of voxels' FIRST fragments (`fresh`); whenever 32 are queued every
+// lane resolves one voxel.  (One thread per slot, the fresh ones resolving in place, left a third of the lanes -- one voxel per 3.2
+// fragments in the large scenes -- chasing list links while the others idled: the kernel is bound by the latency of those dependent
+// loads, and the loads in flight per warp are what it has to offer against it.)
+__global__ void __launch_bounds__(128)
+vox_resolve_kernel(uint32_t* __restrict__ base, const FragRec* __restrict__ frags, const uint8_t* __restrict__ fresh,
+                   uint32_t* __restrict__ counters, uint32_t frag_capacity, const PeerView pv, uint8_t* __restrict__ tile_touched, int logR,
+                   uint32_t* __restrict__ status, unsigned long long* __restrict__ accum, int fmt16) {
+  __shared__ uint2 queue_s[4][64];   // per warp: (arena slot, position in the pushed list) of the voxels waiting to be resolved
+  // arena too small: fragments were dropped.  Tell the host through the mapped status word (the only time this kernel touches host memory)
+  if (blockIdx.x == 0 && threadIdx.x == 0 && counters[CNT_FRAGS] > frag_capacity) {
+    *reinterpret_cast<volatile uint32_t*>(status + STATUS_OVERFLOW) = counters[CNT_FRAGS];
+    __threadfence_system();
+  }
+  const uint32_t n_frags = min(counters[CNT_FRAGS], frag_capacity);
+  uint32_t n_mine = 0, max_list = 0;
+  const int lane = threadIdx.x & 31;
+  uint2* queue = queue_s[threadIdx.x >> 5];
+  int qn = 0;
+  for (uint32_t f0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; f0 < n_frags; f0 += gridDim.x * blockDim.x) {
+    const uint32_t f = f0 + lane;
+    const bool mine = f < n_frags && fresh[f];
+    const uint32_t mm = __ballot_sync(0xffffffffu, mine);
+    if (mm) {
+      const uint32_t before = (uint32_t)__popc(mm & ((1u << lane) - 1u));
+      uint32_t list_pos = 0;
+      if (pv.pushed) {   // multi-GPU: the list of pushed voxels is appended with one atomic per warp and round
+        if (lane == 0) list_pos = atomicAdd(pv.pushed_n, (uint32_t)__popc(mm));
+        list_pos = __shfl_sync(0xffffffffu, list_pos, 0) + before;
+      }
+      if (mine) queue[qn + (int)before] = make_uint2(f, list_pos);
+      qn += __popc(mm);
+      __syncwarp();
     }
-    base[voxel] = stored;
-    if (tile_touched) tile_touched[tile_of_voxel(voxel, logR)] = 1;   // sparse mip build: this 32x8x8 tile has content
-    // multi-GPU: the slab owner writes the resolved voxel straight into every peer's grid over NVLink (sparse
-    // exchange: only occupied voxels travel; replaces the dense all-gather of the base level)
-    const uint32_t tile = tile_of_voxel(voxel, logR);
-    for (int p = 0; p < pv.nranks; p++) {
-      if (p != pv.rank) pv.base[p][voxel] = stored;
-      if (pv.touched[p]) pv.touched[p][tile] = 1;   // keeps every rank's mip build sparse (own rank included)
+    if (qn >= 32) {
+      qn -= 32;
+      const uint2 e = queue[qn + lane];
+      __syncwarp();   // the entries are in registers before the next round appends over them
+      max_list = max(max_list, resolve_voxel(e.x, e.y, base, frags, pv, tile_touched, logR, accum, fmt16));
+      n_mine++;
     }
-    if (pv.pushed && list_pos < pv.pushed_capacity) pv.pushed[list_pos] = voxel;
-    max_list = max(max_list, n);
+  }
+  if (lane < qn) {
+    const uint2 e = queue[lane];
+    max_list = max(max_list, resolve_voxel(e.x, e.y, base, frags, pv, tile_touched, logR, accum, fmt16));
+    n_mine++;
   }
   // statistics (vct_voxelize_stats): occupied voxels and the longest list, one atomic each per warp
   n_mine = __reduce_add_sync(0xffffffffu, n_mine);
@@ -560,7 +585,7 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
                                                           sc->n_tris >= kSmallPathMinTris ? kMidPixels : 0, dev->counters + CNT_TICKET_VOX, dev->counters + CNT_ITEMS);
     vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->rs[0].item_local, dev->rs[0].item_block, n_blocks, ctx);
   }
-  vox_resolve_kernel<<<sms * 8, 128, 0, s>>>(g->base, dev->frags, dev->fresh, dev->counters, (uint32_t)dev->frag_capacity, pv, touched, log2_int(g->R),
+  vox_resolve_kernel<<<sms * 16, 128, 0, s>>>(g->base, dev->frags, dev->fresh, dev->counters, (uint32_t)dev->frag_capacity, pv, touched, log2_int(g->R),
                                              dev->status_dev, accum, g->fmt == VCT_GRID_RGBA16F ? 1 : 0);
   VCT_CUDA(cudaGetLastError());
   return VCT_OK;
