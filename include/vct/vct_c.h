@@ -193,6 +193,7 @@ int vct_debug_frame_events(vct_device_t* dev, vct_device_t* ref, float out_ms[8]
 #define VCT_DEBUG_TRACE_LOW_PRIORITY 5
 #define VCT_DEBUG_PEER_REPLICATE 6
 #define VCT_DEBUG_CONE_CTAS_PER_SM 7
+#define VCT_DEBUG_SMALL_LIMIT 8
 int vct_debug_set(vct_device_t* dev, int key, int value);
 
 /* ---- multi-GPU (no reference counterpart: the reference is single-GPU).  One process per GPU on one node; the exchange

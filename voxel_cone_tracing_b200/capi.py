@@ -59,7 +59,7 @@ def default_params(**kw) -> TraceParams:
 
 _lib = None
 PEER_HANDLE_BYTES = 320   # sizeof(vct_peer_handle_t)
-DEBUG_MIP_DENSE, DEBUG_CONE_VARIANT, DEBUG_CONE_GRID, DEBUG_CONE_RESERVE_SMS, DEBUG_TRACE_LOW_PRIORITY, DEBUG_PEER_REPLICATE, DEBUG_CONE_CTAS_PER_SM = 1, 2, 3, 4, 5, 6, 7   # vct_debug_set keys
+DEBUG_MIP_DENSE, DEBUG_CONE_VARIANT, DEBUG_CONE_GRID, DEBUG_CONE_RESERVE_SMS, DEBUG_TRACE_LOW_PRIORITY, DEBUG_PEER_REPLICATE, DEBUG_CONE_CTAS_PER_SM, DEBUG_SMALL_LIMIT = 1, 2, 3, 4, 5, 6, 7, 8   # vct_debug_set keys
 ACCUM_ORDERED, ACCUM_FIXED_POINT = 0, 1                          # vct_voxelize_set_accum_mode
 GRID_RGBA8, GRID_RGBA16F = 0, 1                                  # vct_grid_create_ex formats
 SAMPLER_FP32, SAMPLER_TEX = 0, 1

@@ -761,6 +761,7 @@ int vct_debug_set(vct_device_t* dev, int key, int value) {
     case VCT_DEBUG_CONE_VARIANT: VCT_REQUIRE(value >= -1 && value <= 3, "cone variant must be -1..3"); dev->debug_cone_variant = value; return VCT_OK;
     case VCT_DEBUG_CONE_GRID: dev->debug_cone_grid = value != 0; return VCT_OK;
     case VCT_DEBUG_CONE_CTAS_PER_SM: VCT_REQUIRE(value >= 0 && value <= 16, "CTAs per SM out of range"); dev->cone_ctas_per_sm = value; return VCT_OK;
+    case VCT_DEBUG_SMALL_LIMIT: VCT_REQUIRE(value >= -1 && value <= 1024, "small-triangle limit out of range"); dev->debug_small_limit = value; return VCT_OK;
     case VCT_DEBUG_PEER_REPLICATE:
       VCT_REQUIRE(value >= -1 && value <= 1, "peer replicate must be -1 (automatic), 0 or 1");
       VCT_REQUIRE(dev->peers.nranks <= 1, "set before vct_peer_connect");

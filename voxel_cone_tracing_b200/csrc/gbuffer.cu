@@ -21,7 +21,7 @@
 namespace vct {
 
 struct Mat4 { float m[16]; };
-constexpr int kSmallCamPixels = 36;
+constexpr int kSmallCamPixels = 100;   // swept together with the voxelizer's limit (tools/small_limit_sweep.py)
 // Pieces with up to this many pixel centres in their bounding box (and more than kSmallCamPixels) are rasterised by the whole warp
 // inside the set-up kernel, one piece after the other, 8 x 4 pixels per step: no record, no work item, no prefix search.  At 8K with
 // 4 M triangles nearly every triangle is of this size (a few dozen to a few hundred pixels); round 1 gave each of them a record + items
@@ -568,12 +568,12 @@ int launch_gbuffer(vct_device* dev, vct_scene* sc, const float* view, const floa
     if (tile_nranks > 1)
       cam_setup_kernel<true><<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, pv, t->W, t->H, recs, (uint32_t)rec_capacity, rec_count,
                                                         dev->rs[1].big_slot, dev->rs[1].item_local, dev->rs[1].item_block, t->vis, tile_rank, tile_nranks,
-                                                        many ? kSmallCamPixels : 0, many ? kMidCamPixels : 0, dev->counters + CNT_TICKET_CAM,
+                                                        many ? (dev->debug_small_limit >= 0 ? dev->debug_small_limit : kSmallCamPixels) : 0, many ? kMidCamPixels : 0, dev->counters + CNT_TICKET_CAM,
                                                         dev->counters + CNT_CAM_ITEMS);
     else
       cam_setup_kernel<false><<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, pv, t->W, t->H, recs, (uint32_t)rec_capacity, rec_count,
                                                         dev->rs[1].big_slot, dev->rs[1].item_local, dev->rs[1].item_block, t->vis, tile_rank, tile_nranks,
-                                                        many ? kSmallCamPixels : 0, many ? kMidCamPixels : 0, dev->counters + CNT_TICKET_CAM,
+                                                        many ? (dev->debug_small_limit >= 0 ? dev->debug_small_limit : kSmallCamPixels) : 0, many ? kMidCamPixels : 0, dev->counters + CNT_TICKET_CAM,
                                                         dev->counters + CNT_CAM_ITEMS);
     cam_raster_kernel<<<sms * 8, 256, 0, s>>>(recs, dev->rs[1].big_slot, sc->n_tris, dev->rs[1].item_local, dev->rs[1].item_block, n_blocks, t->W, t->vis, dev->counters,
                                               tile_rank, tile_nranks);

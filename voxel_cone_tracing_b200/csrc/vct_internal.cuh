@@ -223,6 +223,7 @@ struct vct_device {
   // measurement / test switches (vct_debug_set); never read from the environment
   bool debug_mip_dense = false;      // every mip build reads and writes every tile
   int debug_cone_variant = -1;       // -1 = automatic; 0 literal loop, 1 two-level fetches, 2 one warp per cone slot, 3 grouped diffuse cones
+  int debug_small_limit = -1;        // >= 0: bounding-box size (pixels) up to which the set-up kernels rasterise a triangle by its own lane (default: kSmallPixels / kSmallCamPixels)
   int cone_ctas_per_sm = 0;          // > 0: the persistent cone kernel launches this many CTAs per SM instead of all that fit (frames in flight: room for the other frame's kernels)
   int cone_reserved_sms = 0;         // SMs the persistent cone kernel leaves free (frames in flight: the next frame's front half runs there)
   bool debug_cone_grid = false;      // cone kernel on a host-sized grid instead of the persistent work queue

@@ -9,7 +9,7 @@
 //   3. vox_raster_kernel  one warp per macro tile (8x8 .. 64x64 pixels, per triangle) (8x8 blocks culled by the edge functions): coverage, fragment shading (voxelize.frag:122-157),
 //                         append of a 32-byte fragment record to a per-voxel linked list whose head
 //                         lives in the grid word itself (atomicExch); the fragment that finds the voxel
-//                         empty marks its arena slot (`fresh`).  Triangles of <= 36 pixels are rasterised
+//                         empty marks its arena slot (`fresh`).  Triangles of <= 100 pixels are rasterised
 //                         inside 1. (count pass, one arena atomic per warp, write pass).
 //   4. vox_resolve_kernel one thread per arena slot, the `fresh` ones resolve their voxel: sorts the voxel's fragments by the canonical
 //                         order key (draw, triangle, row, column) and folds them with the reference's
@@ -152,7 +152,7 @@ __device__ __forceinline__ void emit_fragments(const FragCtx& c, const VoxTri& v
 // triangles whose bounding box holds at most this many pixel centres are rasterised inside the setup kernel (one lane
 // per triangle, the warp walks the boxes in lock-step) instead of becoming 8x8 work items: a scene of millions of
 // sub-voxel triangles would otherwise spend a whole warp on one or two fragments
-constexpr int kSmallPixels = 36;
+constexpr int kSmallPixels = 100;   // swept on the 1 M / 4 M-triangle scenes (tools/small_limit_sweep.py): 36 -> 100 takes 9 % off the voxelization at 1024^3, flat beyond
 // ... and those with up to this many (a few 8x8 blocks) by the whole warp inside the setup kernel, one triangle after the other, 8 x 4
 // pixels per step: no VoxTri record, no work items, no prefix searches.  In the 1 M / 4 M-triangle scenes nearly every triangle is of
 // this size; as 8x8 work items they were 9.4 of the 16 ms of the voxelization at 1024^3.
@@ -223,10 +223,11 @@ vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
   uint32_t mine = 0;
   EdgeBlock eb0;   // edge functions at the box origin (same integers as raster_sample, two multiply-adds per edge and pixel)
   edge_block_setup(v.rt, v.rt.imin, v.rt.jmin, eb0);
-  for (int p = 0; p < npx; p++) {
+  for (int p = 0, ox = 0, oy = 0; p < npx; p++) {   // one flat loop (lanes differ in box shape, not only in size); the column / row counters replace p % bw, p / bw
     float b[3];
     F3 pos; uint32_t voxel;
-    if (edge_block_sample(eb0, p % bw, p / bw, b) && fragment_voxel(ctx, v, b, pos, voxel)) mine++;
+    if (edge_block_sample(eb0, ox, oy, b) && fragment_voxel(ctx, v, b, pos, voxel)) mine++;
+    if (++ox == bw) { ox = 0; oy++; }
   }
   uint32_t incl = mine;
 #pragma unroll
@@ -240,11 +241,11 @@ vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
     if (lane == 0) slot = atomicAdd(&ctx.counters[CNT_FRAGS], warp_total);
     slot = __shfl_sync(0xffffffffu, slot, 0) + (incl - mine);
   }
-  for (int p = 0; p < npx; p++) {
+  for (int p = 0, ox = 0, oy = 0; p < npx; p++) {
     float b[3];
     F3 pos; uint32_t voxel;
-    const int i = v.rt.imin + p % bw, j = v.rt.jmin + p / bw;
-    if (edge_block_sample(eb0, p % bw, p / bw, b) && fragment_voxel(ctx, v, b, pos, voxel)) push_fragment(ctx, v, t, i, j, b, pos, voxel, slot++);
+    if (edge_block_sample(eb0, ox, oy, b) && fragment_voxel(ctx, v, b, pos, voxel)) push_fragment(ctx, v, t, v.rt.imin + ox, v.rt.jmin + oy, b, pos, voxel, slot++);
+    if (++ox == bw) { ox = 0; oy++; }
   }
   // ---- mid-sized triangles: the whole warp on one triangle at a time, in TWO passes over the warp's mid triangles: count the fragments,
   // reserve their arena slots with ONE atomic, write them.  (One reservation per 8 x 4-pixel step -- four or five per triangle -- made the
@@ -581,7 +582,7 @@ int launch_voxelize(vct_device* dev, vct_scene* sc, vct_grid* g, int z0, int z1,
     ctx.accum = accum;
     ctx.vstride = g->fmt == VCT_GRID_RGBA16F ? 2 : 1;
     vox_setup_kernel<<<n_blocks, kSetupThreads, 0, s>>>(sc->verts, sc->indices, sc->draws, sc->n_draws, sc->n_tris, sc->cube_size, g->R, z0, z1, tris,
-                                                          dev->rs[0].item_local, dev->rs[0].item_block, ctx, sc->n_tris >= kSmallPathMinTris ? kSmallPixels : 0,
+                                                          dev->rs[0].item_local, dev->rs[0].item_block, ctx, sc->n_tris >= kSmallPathMinTris ? (dev->debug_small_limit >= 0 ? dev->debug_small_limit : kSmallPixels) : 0,
                                                           sc->n_tris >= kSmallPathMinTris ? kMidPixels : 0, dev->counters + CNT_TICKET_VOX, dev->counters + CNT_ITEMS);
     vox_raster_kernel<<<sms * 8, 256, 0, s>>>(tris, sc->n_tris, dev->rs[0].item_local, dev->rs[0].item_block, n_blocks, ctx);
   }
