@@ -226,6 +226,7 @@ __device__ __noinline__ uint32_t cam_setup_clipped(const vct_vertex_t* __restric
   for (int q = 0; q < n; q++) {
     if (pc[q].rt.sign == 0) continue;
     if (big[q]) {
+      if (record_limit > 0) raster_choose_macro(pc[q].rt, kMaxItemsManyTris);
       pc[q].pad = raster_item_count(pc[q].rt);
       count += pc[q].pad;
       recs[slot++] = pc[q];
@@ -270,6 +271,7 @@ cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
         if (big) {
           const uint32_t slot = atomicAdd(rec_count, 1u);
           if (slot < rec_capacity) {
+            if (mid_limit > 0) raster_choose_macro(pc.rt, kMaxItemsManyTris);
             pc.pad = raster_item_count(pc.rt);
             count = pc.pad;
             recs[slot] = pc;

@@ -62,6 +62,17 @@ __device__ __forceinline__ bool raster_setup(const float xw[3], const float yw[3
   return true;
 }
 
+// Scenes of many triangles (the set-up kernels' in-line paths are on: mid_limit > 0) want FEW, large work items per triangle: an item costs
+// two binary searches, a 160-byte record load and the block culling before its first pixel, and the 4 M-triangle scene at 8K turned its
+// triangles of 70..200 pixels across into 977 k items of 8 x 8 pixels (cam_raster_kernel 2.4 ms, 1.5 G warp instructions).  Small scenes
+// keep up to kMaxItemsPerTri small items per triangle: their few triangles need the parallelism.
+constexpr uint32_t kMaxItemsManyTris = 16;
+__device__ __forceinline__ void raster_choose_macro(RasterTri& t, uint32_t max_items) {
+  int ms = kMacroShiftMin;
+  while (ms < kMacroShiftMax && (uint32_t)((t.imax >> ms) - (t.imin >> ms) + 1) * (uint32_t)((t.jmax >> ms) - (t.jmin >> ms) + 1) > max_items) ms++;
+  t.mshift = ms;
+}
+
 __device__ __forceinline__ uint32_t raster_item_count(const RasterTri& t) {
   if (t.sign == 0) return 0u;
   const int ms = t.mshift;

@@ -297,7 +297,10 @@ vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
     }
   }
   if (small || mid) count = 0;
-  else if (t < n_tris) out[t] = v;   // only triangles that become work items are read again
+  else if (t < n_tris) {
+    if (mid_limit > 0 && count) { raster_choose_macro(v.rt, kMaxItemsManyTris); count = raster_item_count(v.rt); }
+    out[t] = v;   // only triangles that become work items are read again
+  }
   block_scan_items(count, t, n_tris, item_local, item_block, scan_ticket, scan_total);
 }
 
