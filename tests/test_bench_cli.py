@@ -27,3 +27,38 @@ def test_reference_arm_non_root_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--config", "1", "--steps", "1", "--warmup", "0"],
                        capture_output=True, text=True, timeout=120, env=env, cwd=ROOT)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_frames_in_flight_rule_and_config_keys():
+    """--frames-in-flight 0 = automatic: two pipelines for the reference's scenes, one for the large synthetic ones; NCCL exchange: always one"""
+    import argparse
+    sys.path.insert(0, ROOT)
+    import bench
+    a = argparse.Namespace(frames_in_flight=0)
+    assert bench.frames_in_flight(a, 1112, 1, "p2p") == 2 and bench.frames_in_flight(a, 1112, 8, "p2p") == 2
+    assert bench.frames_in_flight(a, 998412, 1, "p2p") == 1 and bench.frames_in_flight(a, 1112, 2, "nccl") == 1
+    a.frames_in_flight = 3
+    assert bench.frames_in_flight(a, 998412, 4, "p2p") == 3
+    c1 = bench.config_dict(bench.CONFIGS[2], 1, 1, "p2p", 1112, 2)
+    c8 = bench.config_dict(bench.CONFIGS[2], 8, 1, "p2p", 1112, 2)
+    assert set(c1) == set(c8) and "every rank voxelizes the whole scene" in c8["parallelism"]
+    assert "z-slab" in bench.config_dict(bench.CONFIGS[4], 8, 1, "p2p", 998412, 1)["parallelism"]
+
+
+def test_screen_tile_lattice_is_a_balanced_partition():
+    """capi.screen_tile_owner (= screen_tile_owner in csrc/vct_internal.cuh): every 32x32 tile has exactly one owner, the ranks' shares of a
+    frame are balanced, and neighbours in a row AND in a column belong to different ranks"""
+    import numpy as np
+    sys.path.insert(0, ROOT)
+    from voxel_cone_tracing_b200 import capi
+    for W, H in ((1920, 1080), (7680, 4320), (320, 200)):
+        ty, tx = np.meshgrid(np.arange((H + 31) // 32), np.arange((W + 31) // 32), indexing="ij")
+        for n in (1, 2, 3, 4, 5, 6, 8, 15):
+            own = capi.screen_tile_owner(tx, ty, n)
+            assert own.min() >= 0 and own.max() < n
+            counts = np.bincount(own.ravel(), minlength=n)
+            assert counts.sum() == own.size
+            if own.size >= 64 * n:
+                assert counts.max() - counts.min() <= 0.05 * own.size / n + 2
+            if n >= 2:
+                assert (own[:, 1:] != own[:, :-1]).all() and (own[1:, :] != own[:-1, :]).all()
