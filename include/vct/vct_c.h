@@ -181,11 +181,22 @@ int vct_last_frame_timings(vct_device_t* dev, float out_ms[8]);
  * [6] cone kernel start [7] cone kernel end; -1 where an event was not recorded.  Synchronises. */
 int vct_debug_frame_events(vct_device_t* dev, vct_device_t* ref, float out_ms[8]);
 
-/* measurement / test switches (replace the environment variables of round 1; nothing on the launch path reads the environment):
- *   VCT_DEBUG_MIP_DENSE    1 = every vct_mipmap reads and writes every tile (the dense build a first frame or an upload pays)
- *   VCT_DEBUG_CONE_VARIANT -1 = automatic, 0 = literal shader loop, 1 = every fetch blends two levels, 2 = one warp per cone slot,
- *                          3 = all diffuse cones of a tile in one warp
- *   VCT_DEBUG_CONE_GRID    1 = cone kernel on a grid sized by the host instead of the persistent work queue */
+/* measurement / test / tuning switches (replace the environment variables of round 1; nothing on the launch path reads the environment):
+ *   VCT_DEBUG_MIP_DENSE          1 = every vct_mipmap reads and writes every tile (the dense build a first frame or an upload pays)
+ *   VCT_DEBUG_CONE_VARIANT       -1 = automatic, 0 = literal shader loop, 1 = every fetch blends two levels, 2 = one warp per cone slot,
+ *                                3 = all diffuse cones of a tile in one warp
+ *   VCT_DEBUG_CONE_GRID          1 = cone kernel on a grid sized by the host instead of the persistent work queue
+ *   VCT_DEBUG_CONE_RESERVE_SMS   k = CTAs of the persistent cone kernel that land on the last k SMs retire at once (experiment: SMs left to
+ *                                another frame's front half; profiles/r02_frames_in_flight.txt)
+ *   VCT_DEBUG_TRACE_LOW_PRIORITY 1 = FRAMES IN FLIGHT: cones + shade of this device object run on the one lowest-priority stream that all
+ *                                device objects of the GPU share.  Two device objects (each with its scene / grid / target) rendering
+ *                                alternate frames then overlap the front half of frame i+1 with the trace of frame i; results are
+ *                                identical to the plain loop
+ *   VCT_DEBUG_PEER_REPLICATE     multi-GPU voxelization, set before vct_peer_connect: 1 = every rank voxelizes the whole scene (no voxel
+ *                                exchange), 0 = z-slabs + sparse voxel push, -1 = by scene size (<= 16 k triangles: replicate)
+ *   VCT_DEBUG_CONE_CTAS_PER_SM   n = CTAs per SM of the persistent cone kernel (experiment; 0 = all that fit)
+ *   VCT_DEBUG_SMALL_LIMIT        p = bounding-box size in pixels up to which the set-up kernels rasterise a triangle by its own lane
+ *                                (-1 = built-in 100; tools/small_limit_sweep.py) */
 #define VCT_DEBUG_MIP_DENSE 1
 #define VCT_DEBUG_CONE_VARIANT 2
 #define VCT_DEBUG_CONE_GRID 3
@@ -200,11 +211,15 @@ int vct_debug_set(vct_device_t* dev, int key, int value);
  *      runs over NVLink peer memory (CUDA IPC), fused into the producing kernels -- see csrc/peer.cu.  Protocol:
  *        every rank:  vct_peer_export(...)  ->  exchange the handles (any transport: torch.distributed, MPI, a file)
  *                     vct_peer_connect(..., all_handles, frame_root)  ->  process barrier  ->  vct_render_frame per frame
- *      After the connect, vct_render_frame on that grid/target renders this rank's share: voxelizes its z-slab
- *      [rank*R/n, (rank+1)*R/n) (integer division) and stores the resolved voxels into every peer's grid, builds the mip chain locally once
- *      all slabs have arrived, traces the 32x32 screen tiles with tile % n == rank and stores the finished pixels into the
+ *      After the connect, vct_render_frame on that grid/target renders this rank's share.  Scenes of more than 16 k triangles: it voxelizes
+ *      its z-slab [rank*R/n, (rank+1)*R/n) (integer division), stores the resolved voxels into every peer's grid and builds the mip chain
+ *      locally once all slabs have arrived.  Smaller scenes (voxelization is launch latency, not work): every rank voxelizes the whole scene
+ *      into its own grid and no voxel crosses NVLink (VCT_DEBUG_PEER_REPLICATE forces either mode; decided at the first frame of a
+ *      connection, from a scene that must be the same on every rank).  Either way the rank rasterises the G-buffer of and traces the
+ *      32x32 screen tiles (tx, ty) with (tx + k ty) % n == rank (vct_trace_params_t.tile_rank) and stores the finished pixels into the
  *      frame of rank `frame_root` (-1: of every rank).  All ranks must call vct_render_frame the same number of times.
- *      The grid and the frame are bit-identical to the single-GPU result. ---- */
+ *      The grid and the frame are bit-identical to the single-GPU result.  A peer that never signals (dead, out of step) makes the
+ *      next call on the device return VCT_ERR_CUDA after ~5 s. ---- */
 typedef struct { unsigned char bytes[320]; } vct_peer_handle_t;
 int vct_peer_export(vct_device_t* dev, vct_grid_t* g, vct_target_t* t, vct_peer_handle_t* out);
 int vct_peer_connect(vct_device_t* dev, vct_grid_t* g, vct_target_t* t, int rank, int nranks, const vct_peer_handle_t* all_ranks, int frame_root);

@@ -15,7 +15,7 @@
 //   VCT_SAMPLER_TEX    levels >= 1 through the texture units from ONE mipmapped array that stacks the six directional
 //                      volumes along z (GridView in vct_internal.cuh), level 0 in software (shared by the three
 //                      directions).  The benchmarked path; frame within 2/255, PSNR > 64 dB of the oracle.
-//   VCT_SAMPLER_FP32   software trilinear + mip-linear with fp32 weights from the 24-byte records (rule R7 of the
+//   VCT_SAMPLER_FP32   software trilinear + mip-linear with fp32 weights from point-sampled texels of the array (rule R7 of the
 //                      oracle exactly): trilinear in floor(lod) and floor(lod)+1, CLAMP_TO_BORDER with a zero border.
 // Result-preserving savings over the literal shader (every skipped term is exactly zero in the reference): level 0 is
 // fetched once for the three directions (all six level-0 textures are identical), a level whose filter footprint is empty
