@@ -252,7 +252,7 @@ cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
   pc.rt.sign = 0; pc.rt.imin = 0; pc.rt.imax = -1; pc.rt.jmin = 0; pc.rt.jmax = -1; pc.rt.area = 0; pc.rt.mshift = kMacroShiftMin;
 #pragma unroll
   for (int k = 0; k < 3; k++) { pc.rt.X[k] = pc.rt.Y[k] = 0; pc.zw[k] = 0.0f; }
-  bool mid = false;
+  bool mid = false, small = false;
   if (t < n_tris) {
     const DrawRec* dp = draws + find_draw(t, draws, n_draws);
     ClipVert in[3];
@@ -280,7 +280,7 @@ cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
             mid = true;
           }
         } else if (!mid) {
-          raster_piece_inline<SPLIT>(pc, t, W, vis, tile_rank, tile_nranks);
+          small = true;
         }
       }
       big_slot[t] = bs;
@@ -290,9 +290,12 @@ cam_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
       big_slot[t] = 0u;
     }
   }
+  // The block's item scan comes BEFORE the in-line rasterisation: its barriers are then reached by warps that have all done the same
+  // (uniform) set-up work, and the divergent pixel loops below end without anybody waiting for the block's slowest warp.
+  block_scan_items(count, t, n_tris, item_local, item_block, scan_ticket, scan_total);
+  if (small) raster_piece_inline<SPLIT>(pc, t, W, vis, tile_rank, tile_nranks);
   // the mid-sized pieces of the warp's 32 triangles, one after the other, all lanes on each
   for (uint32_t m = __ballot_sync(0xffffffffu, mid); m; m &= m - 1u) raster_piece_warp<SPLIT>(pc, t, __ffs((int)m) - 1, lane, W, vis, tile_rank, tile_nranks);
-  block_scan_items(count, t, n_tris, item_local, item_block, scan_ticket, scan_total);
 }
 
 __global__ void __launch_bounds__(256)

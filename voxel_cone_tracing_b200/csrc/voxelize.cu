@@ -216,6 +216,18 @@ vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
   const int bw = v.rt.imax - v.rt.imin + 1, bh = v.rt.jmax - v.rt.jmin + 1;
   const bool small = count > 0 && bw * bh <= small_limit;
   const int npx = small ? bw * bh : 0;
+  const bool mid = count > 0 && !small && bw * bh <= mid_limit;
+  // The block's item scan comes BEFORE the in-line rasterisation: its barriers are then reached by warps that have all done the same
+  // (uniform) set-up work, and the divergent pixel loops below end without anybody waiting for the block's slowest warp.
+  {
+    uint32_t items = count;
+    if (small || mid) items = 0;
+    else if (t < n_tris) {
+      if (mid_limit > 0 && count) { raster_choose_macro(v.rt, kMaxItemsManyTris); items = raster_item_count(v.rt); }
+      out[t] = v;   // only triangles that become work items are read again
+    }
+    block_scan_items(items, t, n_tris, item_local, item_block, scan_ticket, scan_total);
+  }
   // pass 1: every lane counts the fragments of its own triangle; pass 2: it writes them at consecutive slots of the warp's
   // reservation -- ONE arena atomic per warp of 32 triangles (one per pixel step of the lock-stepped walk before: 9 M same-address
   // atomics per frame on the 4 M-triangle scene)
@@ -250,7 +262,6 @@ vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
   // ---- mid-sized triangles: the whole warp on one triangle at a time, in TWO passes over the warp's mid triangles: count the fragments,
   // reserve their arena slots with ONE atomic, write them.  (One reservation per 8 x 4-pixel step -- four or five per triangle -- made the
   // warp wait for an L2 atomic round trip every few dozen instructions: the set-up kernel of the 4 M-triangle scene spent its time there.)
-  const bool mid = count > 0 && !small && bw * bh <= mid_limit;
   const uint32_t mid_mask = __ballot_sync(0xffffffffu, mid);
   if (mid_mask) {
     VoxTri* wst = stage + (threadIdx.x & ~31);   // this warp's 32 slots
@@ -296,12 +307,6 @@ vox_setup_kernel(const vct_vertex_t* __restrict__ verts, const uint32_t* __restr
       }
     }
   }
-  if (small || mid) count = 0;
-  else if (t < n_tris) {
-    if (mid_limit > 0 && count) { raster_choose_macro(v.rt, kMaxItemsManyTris); count = raster_item_count(v.rt); }
-    out[t] = v;   // only triangles that become work items are read again
-  }
-  block_scan_items(count, t, n_tris, item_local, item_block, scan_ticket, scan_total);
 }
 
 __global__ void __launch_bounds__(256)
