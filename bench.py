@@ -45,10 +45,12 @@ CONFIGS = {
     5: dict(name="synthetic 4M triangles 1024^3 7680x4320 (RGBA8, 7 levels; 16 diffuse cones: BASELINE config 5's cone variant)", R=1024, W=7680, H=4320,
             scene="synthetic", tris=4_000_000, seed=0x5EED0002, cones=16),
 }
-# kernels per frame (one GPU): clear 1 (sparse: the previous frame's occupied voxels) + voxelize 4 (counter reset, setup+scan, raster, resolve)
-# + mip 2 (fused levels 1-3; tail = levels 4.. + occupancy dilation) + G-buffer 5 (clear, record counter reset, setup+scan, raster, resolve)
-# + trace 4 (list reset, tile list, cones, shade); checked against the ncu launch list (profiles/r02_launch_summary_c2.txt)
-KERNELS_PER_FRAME = 16
+# kernels per frame (one GPU), checked against the ncu launch list (profiles/r02_launches_c2.csv): clear 1 (sparse: the previous frame's occupied
+# voxels) + voxelize 4 (counter reset, setup+scan, raster, resolve) + mip 2 (levels 1-3 streaming; tail = levels 4.. + occupancy dilation)
+# + G-buffer 4 (clear + counter resets, setup+scan, raster, resolve + live-tile list) + trace 2 (cones, shade).
+# N > 1 adds the flag kernels and the tile push: signal, wait for the destination frame, frame push (+ the root's wait for everybody's tiles)
+KERNELS_PER_FRAME = 13
+KERNELS_PER_FRAME_MULTI = 16
 # ncu --set full counters of the dominant kernel on the headline workload, extracted by tools/ncu_to_json.py from a capture of THIS tree
 CONE_PROFILE = os.path.join(ROOT, "profiles", "r02_cone_kernel_ncu.json")
 
@@ -581,7 +583,7 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
         out = {"metric": "frames_per_sec", "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 RGBA storage)",
                "data": "synthetic", "config": dict(config_dict(cfg, world, args.sampler, args.exchange, n_tris, n_fif), **({"storage": "RGBA16F, full mip chain (variant)"} if args.fp16 else {})),
-               "clocks": clocks, "e2e": e2e, "gpu_launches": KERNELS_PER_FRAME * args.steps, "roofline": roof, "cpu_baseline": cpu}
+               "clocks": clocks, "e2e": e2e, "gpu_launches": (KERNELS_PER_FRAME if world == 1 else KERNELS_PER_FRAME_MULTI) * args.steps, "roofline": roof, "cpu_baseline": cpu}
         if stages:
             out["stages"] = stages
         if rank_stages:
