@@ -1,0 +1,357 @@
+/*
+ * harness.cpp -- runs THE REFERENCE'S OWN GLSL (shader/voxelize.{vert,geom,frag}, mipmap.comp, voxel_cone_tracing.{vert,frag})
+ * on the CPU.  TEST INFRASTRUCTURE ONLY: the second, reference-sourced checker beside the restated oracle (vct_oracle.cpp).
+ *
+ * How: oracle/glsl_ref/glsl2cpp.py rewrites the shader text, read from /root/reference where it lies, into C++ member
+ * declarations (purely syntactic, see its header; output under oracle/_ref/gen/, never committed); each shader becomes the
+ * body of a struct below; vectors, matrices, swizzles and built-ins are the reference's vendored GLM 0.9.9
+ * (thirdparty/glm) plus glsl_env.h.  This file is the "driver + fixed-function GPU" around them:
+ *   * the uniform / vertex-array set-up and draw loop of src/renderer.cpp:241-256 (draw_models), :283-314 (filter),
+ *     :316-353 (voxelize), :355-390 (visualize), :258-281 (lights, camera);
+ *   * rasterisation, interpolation, clipping, depth test, texel conversion and textureLod from vct_fixed_function.h --
+ *     the SAME written rules R1-R4, R6-R8 the oracle uses, so the two programs differ only in the programmable stages.
+ * Fragments are executed sequentially in the canonical order R4, so the imageAtomicCompSwap loop of voxelize.frag:95-120
+ * runs exactly as written (first swap fails against a non-empty voxel, one averaging step, second swap succeeds).
+ *
+ * Compiled twice into one library (oracle/Makefile): GLREF_RULES=1 -> glref_rules_* entry points (built-ins follow the
+ * oracle's rules R5 / R9: results must equal the oracle's BIT FOR BIT), GLREF_RULES=0 -> glref_glm_* (GLM's own built-ins:
+ * shows how far implementation-defined precision moves the result).
+ */
+#include <stdint.h>
+#include <string.h>
+#include <limits>
+#include <vector>
+
+#define GLM_FORCE_SWIZZLE
+#include <glm/glm.hpp>
+#include <glm/gtc/matrix_access.hpp>
+
+#include "../vct_fixed_function.h"
+#include "../vct_oracle.h"   /* POD scene types only */
+
+#if GLREF_RULES
+#define GLREF_NS glref_rules
+#define GLREF_FN(name) glref_rules_##name
+#else
+#define GLREF_NS glref_glm
+#define GLREF_FN(name) glref_glm_##name
+#endif
+
+#include "glsl_env.h"
+
+namespace GLREF_NS {
+
+/* ---- the six shaders: generated member declarations wrapped in one struct each ---- */
+struct voxelize_vert {
+  vec4 gl_Position;
+#include "gen/voxelize_vert.inc"
+};
+struct voxelize_geom {
+  vec4 gl_Position;
+  virtual void EmitVertex() = 0;
+  void EndPrimitive() {}
+  virtual ~voxelize_geom() {}
+#include "gen/voxelize_geom.inc"
+};
+struct voxelize_frag {
+#include "gen/voxelize_frag.inc"
+};
+struct mipmap_comp {
+  uvec3 gl_GlobalInvocationID;
+#include "gen/mipmap_comp.inc"
+};
+struct cone_vert {
+  vec4 gl_Position;
+#include "gen/voxel_cone_tracing_vert.inc"
+};
+struct cone_frag {
+#include "gen/voxel_cone_tracing_frag.inc"
+};
+
+struct GeomRun : voxelize_geom {
+  struct Out { vec4 pos; GS_OUT v; };
+  std::vector<Out> emitted;
+  void EmitVertex() override { emitted.push_back(Out{gl_Position, gs_out}); }
+};
+
+inline mat4 load_mat4(const float* m) {
+  mat4 r;
+  for (int c = 0; c < 4; c++)
+    for (int k = 0; k < 4; k++) r[c][k] = m[c * 4 + k];
+  return r;
+}
+inline vec3 load3(const float* p) { return vec3(p[0], p[1], p[2]); }
+
+/* material UBO (src/renderer.h:94-120) */
+template <class S>
+void bind_material(S& s, const orc_material_t& m) {
+  s.ambient = load3(m.ambient); s.diffuse = load3(m.diffuse); s.specular = load3(m.specular);
+  s.transmittance = load3(m.transmittance); s.emission = load3(m.emission);
+  s.shininess = m.shininess; s.ior = m.ior; s.dissolve = m.dissolve; s.illum = m.illum;
+  s.roughness = m.roughness; s.metallic = m.metallic; s.sheen = m.sheen; s.clearcoat_thickness = m.clearcoat_thickness;
+  s.clearcoat_roughness = m.clearcoat_roughness; s.anisotropy = m.anisotropy; s.anisotropy_rotation = m.anisotropy_rotation;
+}
+/* upload_lights, src/renderer.cpp:258-273: every queued light is uploaded, the shader clamps the count */
+template <class S>
+void upload_lights(S& s, const orc_scene_t* sc) {
+  for (uint32_t i = 0; i < sc->n_lights && i < s.point_lights.size(); i++) {
+    s.point_lights[i].position = load3(sc->lights[i].position);
+    s.point_lights[i].color = load3(sc->lights[i].color);
+    s.point_lights[i].intensity = sc->lights[i].intensity;
+  }
+  s.point_light_count = (int)sc->n_lights;
+}
+
+/* ---- Renderer::voxelize(), src/renderer.cpp:316-353, without the filter() call ---- */
+int run_voxelize(const orc_scene_t* sc, int R, uint32_t* const tex[6], uint64_t* n_fragments) {
+  using namespace vct_ff;
+  const size_t nvox = (size_t)R * R * R;
+  for (int i = 0; i < 6; i++) memset(tex[i], 0, nvox * sizeof(uint32_t));   /* clear_tex_3d :320-321 */
+  voxelize_vert vs;
+  GeomRun gs;
+  voxelize_frag fs;
+  vs.cube_size = sc->cube_size;      /* :326 */
+  fs.cube_size = sc->cube_size;
+  /* the camera UBO is bound (:333) but gl_Position of the vertex stage is replaced by the geometry stage */
+  vs.projection = mat4(1.0f); vs.view = mat4(1.0f);
+  for (int i = 0; i < 6; i++) { fs.tex3D[i].texels = tex[i]; fs.tex3D[i].N = R; }   /* :330-331 */
+  upload_lights(fs, sc);
+  const int W = 2 * R;               /* :339-340 */
+  uint64_t frags = 0;
+  for (uint32_t d = 0; d < sc->n_draws; d++) {       /* draw_models :241-256 */
+    const orc_draw_t& dr = sc->draws[d];
+    vs.model = load_mat4(dr.model);
+    bind_material(fs, sc->mats[dr.material]);
+    for (uint32_t t = 0; t + 3 <= dr.index_count; t += 3) {
+      for (int k = 0; k < 3; k++) {
+        const orc_vertex_t& v = sc->verts[dr.vertex_base + sc->indices[dr.first_index + t + k]];
+        vs.position = load3(v.pos); vs.normal = load3(v.norm); vs.uv = vec2(v.uv[0], v.uv[1]);
+        vs._init_globals();
+        vs.main();
+        gs.vs_out[k].world_position = vs.vs_out.world_position;
+        gs.vs_out[k].normal = vs.vs_out.normal;
+        gs.vs_out[k].uv = vs.vs_out.uv;
+      }
+      gs.emitted.clear();
+      gs._init_globals();
+      gs.main();
+      if (gs.emitted.size() != 3) return -2;
+      /* fixed function: divide by w (= 1), viewport R1, rasterise R2, interpolate R3 (w = 1: affine) */
+      float xw[3], yw[3];
+      for (int k = 0; k < 3; k++) {
+        const vec4 p = gs.emitted[k].pos;
+        xw[k] = viewport(p.x / p.w, W);
+        yw[k] = viewport(p.y / p.w, W);
+      }
+      RasterTri rt = raster_setup(xw, yw, W, W);
+      if (!rt.valid) continue;
+      const GeomRun::Out* e = gs.emitted.data();
+      for (int j = rt.jmin; j <= rt.jmax; j++)
+        for (int i = rt.imin; i <= rt.imax; i++) {
+          float b[3];
+          if (!raster_sample(rt, i, j, b)) continue;
+          for (int c = 0; c < 4; c++) fs.gs_out.world_position[c] = interp(b, e[0].v.world_position[c], e[1].v.world_position[c], e[2].v.world_position[c]);
+          for (int c = 0; c < 3; c++) fs.gs_out.normal[c] = interp(b, e[0].v.normal[c], e[1].v.normal[c], e[2].v.normal[c]);
+          for (int c = 0; c < 2; c++) fs.gs_out.uv[c] = interp(b, e[0].v.uv[c], e[1].v.uv[c], e[2].v.uv[c]);
+          fs._init_globals();
+          fs.main();
+          frags++;
+        }
+    }
+  }
+  if (n_fragments) *n_fragments = frags;
+  return 0;
+}
+
+/* ---- Renderer::filter(), src/renderer.cpp:283-314 ---- */
+int run_mipmap(uint32_t* const* levels, int R, int n_levels) {
+  mipmap_comp proto;
+  for (int d = 0; d < 6; d++) {
+    proto.src_tex3D[d].levels = levels + (size_t)d * n_levels;
+    proto.src_tex3D[d].R = R;
+    proto.src_tex3D[d].n_levels = n_levels;
+  }
+  int current_dim = R, mip = 0;
+  while (current_dim >= 1) {
+    /* levels past the texture's storage cannot be bound: the reference's remaining dispatches have no effect */
+    if (mip + 1 >= n_levels || (R >> (mip + 1)) < 1) break;
+    proto.resolution = current_dim;
+    proto.mip = mip;
+    const int Nd = R >> (mip + 1);
+    for (int d = 0; d < 6; d++) { proto.dest_tex3D[d].texels = levels[(size_t)d * n_levels + mip + 1]; proto.dest_tex3D[d].N = Nd; }
+    /* glDispatchCompute(ceil(dim / 8))^3 groups of 8^3: invocations with an id >= resolution return at once (mipmap.comp:47-50);
+     * those in [Nd, resolution) would fetch and store outside the images, which GL discards -- they are not run here */
+#pragma omp parallel for schedule(static)
+    for (int z = 0; z < Nd; z++) {
+      mipmap_comp cs = proto;
+      for (int y = 0; y < Nd; y++)
+        for (int x = 0; x < Nd; x++) {
+          cs.gl_GlobalInvocationID = uvec3(x, y, z);
+          cs._init_globals();
+          cs.main();
+        }
+    }
+    mip++;
+    current_dim /= 2;
+  }
+  return 0;
+}
+
+/* ---- vertex stage of Renderer::visualize() + the fixed-function camera pass ---- */
+int run_gbuffer(const orc_scene_t* sc, const float view[16], const float proj[16], int W, int H, uint32_t* tri_id, float* depth,
+                float* world_pos, float* normal, uint32_t* material) {
+  using namespace vct_ff;
+  cone_vert vs;
+  vs.projection = load_mat4(proj);
+  vs.view = load_mat4(view);
+  CameraPass pass(W, H);
+  uint32_t seq = 0;
+  for (uint32_t d = 0; d < sc->n_draws; d++) {
+    const orc_draw_t& dr = sc->draws[d];
+    vs.model = load_mat4(dr.model);
+    for (uint32_t t = 0; t + 3 <= dr.index_count; t += 3, seq++) {
+      FFVertex in[3];
+      for (int k = 0; k < 3; k++) {
+        const orc_vertex_t& v = sc->verts[dr.vertex_base + sc->indices[dr.first_index + t + k]];
+        vs.position = load3(v.pos); vs.normal = load3(v.norm); vs.uv = vec2(v.uv[0], v.uv[1]);
+        vs._init_globals();
+        vs.main();
+        in[k].clip = V4{vs.gl_Position.x, vs.gl_Position.y, vs.gl_Position.z, vs.gl_Position.w};
+        in[k].world = v3(vs.vs_out.world_position.x, vs.vs_out.world_position.y, vs.vs_out.world_position.z);
+        in[k].nrm = v3(vs.vs_out.normal.x, vs.vs_out.normal.y, vs.vs_out.normal.z);
+      }
+      pass.add_triangle(in, dr.material, seq);
+    }
+  }
+  pass.resolve(tri_id, depth, world_pos, normal, material);
+  return 0;
+}
+
+/* ---- fragment stage of Renderer::visualize(), src/renderer.cpp:355-390, on a resolved G-buffer ---- */
+void setup_cone_frag(cone_frag& fs, const orc_scene_t* sc, const float view[16], const uint32_t* const* levels, int R, int n_levels,
+                     const orc_trace_params_t* prm) {
+  fs.cube_size = sc->cube_size;   /* :365-366 */
+  fs.cube_res = R;
+  fs.enable_diffuse = prm->enable_diffuse != 0; fs.enable_specular = prm->enable_specular != 0;   /* :368-371 */
+  fs.enable_shadow = prm->enable_shadow != 0; fs.enable_direct = prm->enable_direct != 0;
+  fs.view_voxel_dir = prm->view_voxel_dir; fs.view_voxel_lod = prm->view_voxel_lod;               /* :373-374 */
+  for (int d = 0; d < 6; d++) { fs.tex3D[d].levels = levels + (size_t)d * n_levels; fs.tex3D[d].R = R; fs.tex3D[d].n_levels = n_levels; }
+  /* upload_camera :279-280: glm::column(view, 3) (sic) */
+  const mat4 v = load_mat4(view);
+  fs.camera_position = vec3(glm::column(v, 3));
+  upload_lights(fs, sc);
+}
+
+int run_shade(const orc_scene_t* sc, const float view[16], int W, int H, const uint32_t* tri_id, const float* world_pos, const float* normal,
+              const uint32_t* material, const uint32_t* const* levels, int R, int n_levels, const orc_trace_params_t* prm, int tile_stride,
+              int tile_phase, uint32_t* frame) {
+  using namespace vct_ff;
+  cone_frag proto;
+  setup_cone_frag(proto, sc, view, levels, R, n_levels, prm);
+  if (tile_stride < 1) tile_stride = 1;
+  const int tiles_x = (W + 31) / 32;
+  const float unwritten = std::numeric_limits<float>::quiet_NaN();
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int j = 0; j < H; j++) {
+    cone_frag fs = proto;
+    for (int i = 0; i < W; i++) {
+      const int tile = (j / 32) * tiles_x + (i / 32);
+      if (tile % tile_stride != tile_phase) continue;
+      const size_t px = (size_t)j * W + i;
+      if (tri_id[px] == 0xFFFFFFFFu) { frame[px] = kClearColour; continue; }
+      bind_material(fs, sc->mats[material[px]]);
+      fs.vs_out.world_position = vec4(world_pos[px * 3], world_pos[px * 3 + 1], world_pos[px * 3 + 2], 1.0f);
+      fs.vs_out.normal = vec3(normal[px * 3], normal[px * 3 + 1], normal[px * 3 + 2]);
+      fs.final_color = vec4(unwritten);
+      fs._init_globals();
+      fs.main();
+      if (fs.final_color.x != fs.final_color.x && fs.final_color.w != fs.final_color.w) { frame[px] = kClearColour; continue; } /* returned before writing */
+      float rgba[4] = {fs.final_color.x, fs.final_color.y, fs.final_color.z, fs.final_color.w};
+      /* blend SRC_ALPHA / ONE_MINUS_SRC_ALPHA over the clear colour (:387-388); alpha = 1 for shaded pixels */
+      if (prm->view_voxel_dir < 7) {
+        const float bg[4] = {0.15f, 0.25f, 0.25f, 1.0f};
+        const float a = rgba[3];
+        for (int k = 0; k < 4; k++) rgba[k] = rgba[k] * a + bg[k] * (1.0f - a);
+      }
+      frame[px] = pack_unorm(rgba);
+    }
+  }
+  return 0;
+}
+
+}  // namespace GLREF_NS
+
+/* ================================================================== */
+extern "C" {
+
+/* tex[0..5]: the six level-0 images (R^3 uint32 each), cleared by the callee like clear_tex_3d */
+int GLREF_FN(voxelize)(const orc_scene_t* sc, int R, uint32_t* const* tex, uint64_t* n_fragments) {
+  if (!sc || !tex || R <= 0) return -1;
+  return GLREF_NS::run_voxelize(sc, R, tex, n_fragments);
+}
+
+/* levels[d * n_levels + l]: level 0 of every direction filled by the caller */
+int GLREF_FN(mipmap)(uint32_t* const* levels, int R, int n_levels) {
+  if (!levels || R <= 0 || n_levels < 1) return -1;
+  return GLREF_NS::run_mipmap(levels, R, n_levels);
+}
+
+int GLREF_FN(gbuffer)(const orc_scene_t* sc, const float view[16], const float proj[16], int W, int H, uint32_t* tri_id, float* depth,
+                      float* world_pos, float* normal, uint32_t* material) {
+  if (!sc || !tri_id || !depth) return -1;
+  return GLREF_NS::run_gbuffer(sc, view, proj, W, H, tri_id, depth, world_pos, normal, material);
+}
+
+int GLREF_FN(shade)(const orc_scene_t* sc, const float view[16], int W, int H, const uint32_t* tri_id, const float* world_pos,
+                    const float* normal, const uint32_t* material, const uint32_t* const* levels, int R, int n_levels,
+                    const orc_trace_params_t* prm, int tile_stride, int tile_phase, uint32_t* frame) {
+  if (!sc || !tri_id || !world_pos || !normal || !material || !levels || !prm || !frame) return -1;
+  return GLREF_NS::run_shade(sc, view, W, H, tri_id, world_pos, normal, material, levels, R, n_levels, prm, tile_stride, tile_phase, frame);
+}
+
+/* trace_cone() of voxel_cone_tracing.frag:88-119 on its own (float results, no 8-bit rounding in between) */
+int GLREF_FN(trace_cone)(const uint32_t* const* levels, int R, int n_levels, const float origin[3], const float dir[3], float aperture,
+                         float max_dist, float out_rgba[4]) {
+  using namespace GLREF_NS;
+  cone_frag fs;
+  for (int d = 0; d < 6; d++) { fs.tex3D[d].levels = levels + (size_t)d * n_levels; fs.tex3D[d].R = R; fs.tex3D[d].n_levels = n_levels; }
+  fs.cube_res = R;
+  fs.cube_size = 1.0f;
+  fs.shininess = 1.0f;
+  fs._init_globals();
+  const vec4 r = fs.trace_cone(load3(origin), load3(dir), aperture, max_dist);
+  out_rgba[0] = r.x; out_rgba[1] = r.y; out_rgba[2] = r.z; out_rgba[3] = r.w;
+  return 0;
+}
+
+/* imageAtomicRGBA8Avg of voxelize.frag:95-120 applied to one texel that holds `stored` */
+uint32_t GLREF_FN(rgba8_avg)(uint32_t stored, const float val01[4]) {
+  using namespace GLREF_NS;
+  voxelize_frag fs;
+  uint32_t texel = stored;
+  uimage3D img; img.texels = &texel; img.N = 1;
+  fs.imageAtomicRGBA8Avg(img, ivec3(0), vec4(val01[0], val01[1], val01[2], val01[3]));
+  return texel;
+}
+
+/* axis selection of voxelize.geom:25-55: 0 = (x,y), 1 = (y,z), 2 = (x,z) projection, recognised from the emitted positions */
+int GLREF_FN(select_axis)(const float wp0[3], const float wp1[3], const float wp2[3]) {
+  using namespace GLREF_NS;
+  GeomRun gs;
+  const float* w[3] = {wp0, wp1, wp2};
+  for (int k = 0; k < 3; k++) { gs.vs_out[k].world_position = vec4(load3(w[k]), 1.0f); gs.vs_out[k].normal = vec3(0.0f); gs.vs_out[k].uv = vec2(0.0f); }
+  gs._init_globals();
+  gs.main();
+  if (gs.emitted.size() != 3) return -1;
+  /* which pair of coordinates was copied into gl_Position.xy for all three vertices? */
+  const int pairs[3][2] = {{0, 1}, {1, 2}, {0, 2}};
+  int found = -1, n_found = 0;
+  for (int a = 0; a < 3; a++) {
+    bool ok = true;
+    for (int k = 0; k < 3; k++) ok = ok && gs.emitted[k].pos.x == w[k][pairs[a][0]] && gs.emitted[k].pos.y == w[k][pairs[a][1]];
+    if (ok) { found = a; n_found++; }
+  }
+  return n_found == 1 ? found : -2;   /* -2: ambiguous input (choose vertices with distinct coordinates) */
+}
+
+}  /* extern "C" */

@@ -43,6 +43,7 @@
  *      as cofactor(upper 3x3) / det in double precision, rounded to float.
  */
 #include "vct_oracle.h"
+#include "vct_fixed_function.h"
 
 #include <math.h>
 #include <stdlib.h>
@@ -54,17 +55,8 @@
 #endif
 
 namespace {
+using namespace vct_ff;
 
-struct V3 { float x, y, z; };
-struct V4 { float x, y, z, w; };
-
-inline V3 v3(float x, float y, float z) { return V3{x, y, z}; }
-inline V3 add(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
-inline V3 sub(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
-inline V3 mul(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
-inline V3 mulv(V3 a, V3 b) { return v3(a.x * b.x, a.y * b.y, a.z * b.z); }
-inline V3 divs(V3 a, float s) { return v3(a.x / s, a.y / s, a.z / s); }
-inline V3 neg(V3 a) { return v3(-a.x, -a.y, -a.z); }
 inline float dot(V3 a, V3 b) { return (a.x * b.x + a.y * b.y) + a.z * b.z; }
 inline V3 cross(V3 a, V3 b) {
   return v3(a.y * b.z - b.y * a.z, a.z * b.x - b.z * a.x, a.x * b.y - b.x * a.y);
@@ -72,7 +64,6 @@ inline V3 cross(V3 a, V3 b) {
 inline float length(V3 a) { return sqrtf(dot(a, a)); }
 inline V3 normalize(V3 a) { return divs(a, length(a)); }                 /* R5 */
 inline V3 mix(V3 a, V3 b, float t) { return add(mul(a, 1.0f - t), mul(b, t)); }
-inline float clamp01(float v) { return fminf(fmaxf(v, 0.0f), 1.0f); }
 inline V3 scale_and_bias(V3 p) { return v3(0.5f * p.x + 0.5f, 0.5f * p.y + 0.5f, 0.5f * p.z + 0.5f); }
 inline V3 reflect(V3 I, V3 N) { return sub(I, mul(N, 2.0f * dot(N, I))); }
 inline V3 refract(V3 I, V3 N, float eta) {
@@ -166,150 +157,6 @@ inline int select_axis(V3 w0, V3 w1, V3 w2) {
   return 2;
 }
 
-/* ------------------------------------------------------------------ */
-/* R2/R3 rasteriser */
-struct RasterTri {
-  int64_t X[3], Y[3];
-  int64_t area;  /* > 0 after orientation fix */
-  int sign;
-  int imin, imax, jmin, jmax;
-  bool valid;
-};
-
-inline int64_t floor_div(int64_t a, int64_t b) { int64_t q = a / b, r = a % b; return (r != 0 && ((r < 0) != (b < 0))) ? q - 1 : q; }
-inline int64_t ceil_div(int64_t a, int64_t b) { return -floor_div(-a, b); }
-
-inline RasterTri raster_setup(const float xw[3], const float yw[3], int W, int H) {
-  RasterTri t;
-  t.valid = false;
-  for (int k = 0; k < 3; k++) {
-    if (!(fabsf(xw[k]) <= 2097152.0f) || !(fabsf(yw[k]) <= 2097152.0f)) return t; /* guard band, also NaN */
-    t.X[k] = (int64_t)rintf(xw[k] * 256.0f);
-    t.Y[k] = (int64_t)rintf(yw[k] * 256.0f);
-  }
-  int64_t a = (t.X[1] - t.X[0]) * (t.Y[2] - t.Y[0]) - (t.Y[1] - t.Y[0]) * (t.X[2] - t.X[0]);
-  if (a == 0) return t;
-  t.sign = a > 0 ? 1 : -1;
-  t.area = a > 0 ? a : -a;
-  int64_t minx = std::min(t.X[0], std::min(t.X[1], t.X[2])), maxx = std::max(t.X[0], std::max(t.X[1], t.X[2]));
-  int64_t miny = std::min(t.Y[0], std::min(t.Y[1], t.Y[2])), maxy = std::max(t.Y[0], std::max(t.Y[1], t.Y[2]));
-  int64_t i0 = ceil_div(minx - 128, 256), i1 = floor_div(maxx - 128, 256);
-  int64_t j0 = ceil_div(miny - 128, 256), j1 = floor_div(maxy - 128, 256);
-  if (i0 < 0) i0 = 0;
-  if (j0 < 0) j0 = 0;
-  if (i1 > W - 1) i1 = W - 1;
-  if (j1 > H - 1) j1 = H - 1;
-  if (i0 > i1 || j0 > j1) return t;
-  t.imin = (int)i0; t.imax = (int)i1; t.jmin = (int)j0; t.jmax = (int)j1;
-  t.valid = true;
-  return t;
-}
-
-/* coverage + barycentrics of pixel (i,j); returns false if not covered */
-inline bool raster_sample(const RasterTri& t, int i, int j, float b[3]) {
-  int64_t px = (int64_t)i * 256 + 128, py = (int64_t)j * 256 + 128;
-  int64_t E[3];
-  for (int k = 0; k < 3; k++) {
-    int a = (k + 1) % 3, c = (k + 2) % 3;
-    int64_t dx = t.X[c] - t.X[a], dy = t.Y[c] - t.Y[a];
-    int64_t e = dx * (py - t.Y[a]) - dy * (px - t.X[a]);
-    if (t.sign < 0) { e = -e; dx = -dx; dy = -dy; }
-    if (e < 0) return false;
-    if (e == 0) {
-      bool topleft = (dy < 0) || (dy == 0 && dx < 0);
-      if (!topleft) return false;
-    }
-    E[k] = e;
-  }
-  float fa = (float)t.area;
-  b[0] = (float)E[0] / fa;
-  b[1] = (float)E[1] / fa;
-  b[2] = (float)E[2] / fa;
-  return true;
-}
-
-inline float interp(const float b[3], float a0, float a1, float a2) { return (b[0] * a0 + b[1] * a1) + b[2] * a2; }
-
-/* ------------------------------------------------------------------ */
-/* textures (R6, R7) */
-/* Texel storage: fmt 0 = RGBA8 unorm (one uint32 per texel, the reference's format, texture_3d.cpp:3-25);
- * fmt 1 = RGBA16F (one uint64 per texel: four IEEE halves, R in the low 16 bits) -- the NON-REFERENCE storage variant of BASELINE.json
- * config 5 ("fp16 RGBA + full mip chain").  The level pointers are then really uint64 arrays. */
-struct Pyramid {
-  const uint32_t* const* levels; /* [dir * n_levels + level] */
-  int R, n_levels;
-  int fmt = 0;
-  inline int size(int l) const { int n = R >> l; return n < 1 ? 1 : n; }
-};
-inline float half_to_float(uint16_t h) { _Float16 v; memcpy(&v, &h, 2); return (float)v; }
-inline uint16_t float_to_half(float f) { _Float16 v = (_Float16)f; uint16_t h; memcpy(&h, &v, 2); return h; } /* round to nearest even */
-inline void unpack_half4(uint64_t c, float out[4]) {
-  for (int k = 0; k < 4; k++) out[k] = half_to_float((uint16_t)(c >> (16 * k)));
-}
-inline uint64_t pack_half4(const float v[4]) {
-  uint64_t r = 0;
-  for (int k = 0; k < 4; k++) r |= (uint64_t)float_to_half(clamp01(v[k])) << (16 * k);
-  return r;
-}
-
-inline void unpack_unorm(uint32_t c, float out[4]) {
-  out[0] = (float)(c & 0xFFu) / 255.0f;
-  out[1] = (float)((c >> 8) & 0xFFu) / 255.0f;
-  out[2] = (float)((c >> 16) & 0xFFu) / 255.0f;
-  out[3] = (float)((c >> 24) & 0xFFu) / 255.0f;
-}
-inline uint32_t pack_unorm(const float v[4]) {
-  uint32_t r = 0;
-  for (int k = 0; k < 4; k++) r |= ((uint32_t)rintf(clamp01(v[k]) * 255.0f)) << (8 * k);
-  return r;
-}
-
-inline void load_texel(const uint32_t* tex, size_t idx, int fmt, float c[4]);
-inline void trilinear(const uint32_t* tex, int N, V3 s, float out[4], int fmt = 0) {
-  out[0] = out[1] = out[2] = out[3] = 0.0f;
-  float ux = s.x * (float)N - 0.5f, uy = s.y * (float)N - 0.5f, uz = s.z * (float)N - 0.5f;
-  if (!(fabsf(ux) < 1.0e9f) || !(fabsf(uy) < 1.0e9f) || !(fabsf(uz) < 1.0e9f)) return; /* NaN / absurd: border */
-  float fx = floorf(ux), fy = floorf(uy), fz = floorf(uz);
-  int ix = (int)fx, iy = (int)fy, iz = (int)fz;
-  float ax = ux - fx, ay = uy - fy, az = uz - fz;
-  for (int dz = 0; dz < 2; dz++) {
-    int z = iz + dz;
-    if (z < 0 || z >= N) continue;
-    float wz = dz ? az : 1.0f - az;
-    for (int dy = 0; dy < 2; dy++) {
-      int y = iy + dy;
-      if (y < 0 || y >= N) continue;
-      float wy = dy ? ay : 1.0f - ay;
-      for (int dx = 0; dx < 2; dx++) {
-        int x = ix + dx;
-        if (x < 0 || x >= N) continue;
-        float wx = dx ? ax : 1.0f - ax;
-        float w = (wx * wy) * wz;
-        float c[4];
-        load_texel(tex, ((size_t)z * N + y) * N + x, fmt, c);
-        for (int k = 0; k < 4; k++) out[k] = out[k] + w * c[k];
-      }
-    }
-  }
-}
-
-inline void load_texel(const uint32_t* tex, size_t idx, int fmt, float c[4]) {
-  if (fmt == 1) unpack_half4(reinterpret_cast<const uint64_t*>(tex)[idx], c);
-  else unpack_unorm(tex[idx], c);
-}
-
-inline void texture_lod(const Pyramid& p, int dir, V3 s, float lod, float out[4]) {
-  float maxl = (float)(p.n_levels - 1);
-  float l = fminf(fmaxf(lod, 0.0f), maxl);
-  if (!(l == l)) l = 0.0f;
-  int l0 = (int)floorf(l);
-  int l1 = l0 + 1 < p.n_levels ? l0 + 1 : p.n_levels - 1;
-  float f = l - (float)l0;
-  float t0[4], t1[4];
-  trilinear(p.levels[dir * p.n_levels + l0], p.size(l0), s, t0, p.fmt);
-  trilinear(p.levels[dir * p.n_levels + l1], p.size(l1), s, t1, p.fmt);
-  for (int k = 0; k < 4; k++) out[k] = (1.0f - f) * t0[k] + f * t1[k];
-}
 
 /* C2: voxel_cone_tracing.frag:71-86 */
 inline void sample_voxel(const Pyramid& p, V3 pos, V3 dir, float lod, float out[4]) {
@@ -599,8 +446,8 @@ int orc_voxelize_slab_mode(const orc_scene_t* sc, int R, int z0, int z1, int acc
       for (int k = 0; k < 3; k++) {
         float a = axis == 1 ? wp[k].y : wp[k].x;
         float b = axis == 0 ? wp[k].y : wp[k].z;
-        xw[k] = (a + 1.0f) * ((float)W * 0.5f); /* R1 */
-        yw[k] = (b + 1.0f) * ((float)W * 0.5f);
+        xw[k] = viewport(a, W); /* R1 */
+        yw[k] = viewport(b, W);
       }
       RasterTri rt = raster_setup(xw, yw, W, W);
       uint64_t emitted = 0;
@@ -750,117 +597,27 @@ int orc_mipmap_fmt(const uint32_t* base, int R, int n_levels, uint32_t* const* o
 int orc_gbuffer(const orc_scene_t* sc, const float view[16], const float proj[16], int W, int H, uint32_t* tri_id,
                 float* depth, float* world_pos, float* normal, uint32_t* material) {
   if (!sc || !tri_id || !depth) return -1;
-  size_t npx = (size_t)W * H;
-  for (size_t i = 0; i < npx; i++) { tri_id[i] = 0xFFFFFFFFu; depth[i] = 1.0f; } /* glClear depth = 1 */
   float pv[16];
   mat4_mul(proj, view, pv); /* projection * view, voxel_cone_tracing.vert:25 */
-
-  struct TriRec { RasterTri rt; V3 world[3], nrm[3]; float iw[3], zw[3]; uint32_t material; uint32_t seq; };
-  struct ClipVert { V4 clip; V3 world, nrm; };
-  std::vector<TriRec> tris;
+  CameraPass pass(W, H);   /* clipping, rasterisation, depth test, interpolation: vct_fixed_function.h */
   uint32_t seq = 0;
   for (uint32_t d = 0; d < sc->n_draws; d++) {
     const orc_draw_t& dr = sc->draws[d];
     float nm[9];
     normal_matrix(dr.model, nm);
     for (uint32_t t = 0; t + 3 <= dr.index_count; t += 3, seq++) {
-      ClipVert in[3];
-      float dn[3]; /* signed distance to the near plane in clip space: z_c + w_c >= 0 is inside (-w <= z) */
-      int n_out = 0;
+      FFVertex in[3];
       for (int k = 0; k < 3; k++) {
         const orc_vertex_t& v = sc->verts[dr.vertex_base + sc->indices[dr.first_index + t + k]];
         V4 w = mat4_mul_point(dr.model, v3(v.pos[0], v.pos[1], v.pos[2])); /* :24 */
         in[k].world = v3(w.x, w.y, w.z);
         in[k].nrm = normalize(mat3_mul(nm, v3(v.norm[0], v.norm[1], v.norm[2]))); /* :26 */
         in[k].clip = mat4_mul_v4(pv, w);
-        dn[k] = in[k].clip.z + in[k].clip.w;
-        if (!(dn[k] >= 0.0f)) n_out++;   /* also NaN */
       }
-      if (n_out == 3) continue;
-      /* R2c: near-plane clipping (GL clips primitives against -w <= z, OpenGL 4.5 13.7; src/renderer.cpp:384-388 enables nothing that
-       * would change it).  Sutherland-Hodgman on the one plane; a new vertex is always computed FROM THE INSIDE vertex of its edge
-       * (t = d_in / (d_in - d_out), P = in + t * (out - in), fp32, no FMA) so that two triangles sharing the edge get the same point.
-       * The 3- or 4-vertex polygon is drawn as the fan (p0,p1,p2), (p0,p2,p3); every piece keeps the triangle's sequence number. */
-      ClipVert poly[4];
-      int np = 0;
-      if (n_out == 0) {
-        poly[0] = in[0]; poly[1] = in[1]; poly[2] = in[2]; np = 3;
-      } else {
-        for (int k = 0; k < 3; k++) {
-          const int k1 = (k + 1) % 3;
-          const bool in_a = dn[k] >= 0.0f, in_b = dn[k1] >= 0.0f;
-          if (in_a) poly[np++] = in[k];
-          if (in_a != in_b) {
-            const ClipVert& vi = in_a ? in[k] : in[k1];
-            const ClipVert& vo = in_a ? in[k1] : in[k];
-            const float di = in_a ? dn[k] : dn[k1], dout = in_a ? dn[k1] : dn[k];
-            const float tt = di / (di - dout);
-            ClipVert c;
-            c.clip.x = vi.clip.x + tt * (vo.clip.x - vi.clip.x); c.clip.y = vi.clip.y + tt * (vo.clip.y - vi.clip.y);
-            c.clip.z = vi.clip.z + tt * (vo.clip.z - vi.clip.z); c.clip.w = vi.clip.w + tt * (vo.clip.w - vi.clip.w);
-            c.world = add(vi.world, mul(sub(vo.world, vi.world), tt));
-            c.nrm = add(vi.nrm, mul(sub(vo.nrm, vi.nrm), tt));
-            poly[np++] = c;
-          }
-        }
-      }
-      for (int piece = 0; piece + 3 <= np; piece++) {
-        const ClipVert* pvt[3] = {&poly[0], &poly[piece + 1], &poly[piece + 2]};
-        TriRec r;
-        r.seq = seq;
-        r.material = dr.material;
-        float xw[3], yw[3];
-        bool ok = true;
-        for (int k = 0; k < 3; k++) {
-          const V4 clip = pvt[k]->clip;
-          r.world[k] = pvt[k]->world;
-          r.nrm[k] = pvt[k]->nrm;
-          if (!(clip.w > 0.0f)) { ok = false; break; } /* R2: cannot happen behind a near plane with near > 0; guards general matrices */
-          float iw = 1.0f / clip.w;
-          r.iw[k] = iw;
-          float xn = clip.x * iw, yn = clip.y * iw, zn = clip.z * iw;
-          xw[k] = (xn + 1.0f) * ((float)W * 0.5f);
-          yw[k] = (yn + 1.0f) * ((float)H * 0.5f);
-          r.zw[k] = (zn + 1.0f) * 0.5f;
-        }
-        if (!ok) continue;
-        r.rt = raster_setup(xw, yw, W, H);
-        if (!r.rt.valid) continue;
-        tris.push_back(r);
-      }
+      pass.add_triangle(in, dr.material, seq);
     }
   }
-  /* row bands in parallel; inside a band triangles are visited in draw order => GL_LESS, first wins ties */
-#pragma omp parallel for schedule(dynamic, 8)
-  for (int j = 0; j < H; j++) {
-    for (size_t ti = 0; ti < tris.size(); ti++) {
-      const TriRec& r = tris[ti];
-      if (j < r.rt.jmin || j > r.rt.jmax) continue;
-      for (int i = r.rt.imin; i <= r.rt.imax; i++) {
-        float b[3];
-        if (!raster_sample(r.rt, i, j, b)) continue;
-        float zw = interp(b, r.zw[0], r.zw[1], r.zw[2]);
-        if (!(zw >= 0.0f && zw <= 1.0f)) continue;
-        size_t px = (size_t)j * W + i;
-        if (!(zw < depth[px])) continue;
-        depth[px] = zw;
-        tri_id[px] = r.seq;
-        float q[3] = {b[0] * r.iw[0], b[1] * r.iw[1], b[2] * r.iw[2]};
-        float qs = (q[0] + q[1]) + q[2];
-        if (world_pos) {
-          world_pos[px * 3 + 0] = interp(q, r.world[0].x, r.world[1].x, r.world[2].x) / qs;
-          world_pos[px * 3 + 1] = interp(q, r.world[0].y, r.world[1].y, r.world[2].y) / qs;
-          world_pos[px * 3 + 2] = interp(q, r.world[0].z, r.world[1].z, r.world[2].z) / qs;
-        }
-        if (normal) {
-          normal[px * 3 + 0] = interp(q, r.nrm[0].x, r.nrm[1].x, r.nrm[2].x) / qs;
-          normal[px * 3 + 1] = interp(q, r.nrm[0].y, r.nrm[1].y, r.nrm[2].y) / qs;
-          normal[px * 3 + 2] = interp(q, r.nrm[0].z, r.nrm[1].z, r.nrm[2].z) / qs;
-        }
-        if (material) material[px] = r.material;
-      }
-    }
-  }
+  pass.resolve(tri_id, depth, world_pos, normal, material);
   return 0;
 }
 
