@@ -1,7 +1,8 @@
 """ctypes binding of the CPU oracle (oracle/libvct_oracle.so).
 
 TEST INFRASTRUCTURE ONLY: the product (voxel_cone_tracing_b200) never imports this module.
-PARITY UNPINNED -- see oracle/vct_oracle.h.
+PARITY: shader arithmetic pinned to the reference's own GLSL run on the CPU (oracle/glsl_ref.py), fixed-function GL rules unpinned
+-- see oracle/vct_oracle.h.
 """
 from __future__ import annotations
 

@@ -1,10 +1,11 @@
 /*
  * vct_oracle.cpp -- CPU ORACLE: a plain C++ restatement of the reference's GLSL hot path.
  *
- * TEST INFRASTRUCTURE ONLY (see vct_oracle.h).  PARITY UNPINNED: no OpenGL 4.5
- * implementation exists in this image and the reference ships no tests / golden vectors;
- * the known-answer tests in tests/test_oracle_kat.py (derived by hand from the shader text,
- * SURVEY.md 8c) are the only pins.
+ * TEST INFRASTRUCTURE ONLY (see vct_oracle.h).  PARITY: the shader arithmetic below is pinned, bit for bit, to the reference's
+ * own GLSL text executed on the CPU (oracle/glsl_ref/, tests/test_glsl_ref.py); the fixed-function GL behaviour (rules R1-R4,
+ * R6-R8, in vct_fixed_function.h) and the precision rules R5 / R9 are UNPINNED -- no OpenGL 4.5 implementation exists in this
+ * image and the reference ships no tests / golden vectors.  Known-answer tests: tests/test_oracle_kat.py (derived by hand from
+ * the shader text).
  *
  * What is restated (paths relative to /root/reference):
  *   shader/voxelize.vert:24-30, voxelize.geom:25-55, voxelize.frag:46-161

@@ -4,13 +4,16 @@
  * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product.  Only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it.
  *
- * PARITY UNPINNED: the reference (latencyhiding/voxel_cone_tracing) has no tests, golden
- * vectors or fixtures for this path, and its arithmetic is GLSL that needs an OpenGL 4.5
- * driver, which does not exist in this image (no libGL/EGL/OSMesa, no llvmpipe with
- * compute/image-atomics).  This oracle is therefore a restatement of the shader text plus
- * a written-down choice for every implementation-defined GL behaviour (see vct_oracle.cpp
- * header).  It is pinned only by known-answer tests derived by hand from the shader text
- * (tests/test_oracle_kat.py) and by the tinyobjloader cross-check of the scene inputs.
+ * PARITY: the PROGRAMMABLE stages are pinned to the reference itself -- its six GLSL shaders, read from /root/reference where
+ * they lie, are rewritten syntactically, compiled against the reference's vendored GLM and executed on the CPU
+ * (oracle/glsl_ref/ -> oracle/_ref/libvct_glsl_ref.so); voxel grid, all mip volumes, G-buffer attributes and the frame of this
+ * oracle equal that program's BIT FOR BIT (tests/test_glsl_ref.py; vectors it produced: tests/golden/glsl_ref_vectors.json,
+ * tests/test_glsl_ref_golden.py).  The FIXED-FUNCTION stages stay UNPINNED: the reference (latencyhiding/voxel_cone_tracing) has
+ * no tests, golden vectors or fixtures for this path and no OpenGL 4.5 driver exists in this image (no libGL/EGL/OSMesa, no
+ * llvmpipe with compute/image-atomics), so rasterisation, fragment order, texture filtering and the precision of built-ins
+ * follow written rules (R1-R9 in vct_oracle.cpp, shared with the GLSL harness through vct_fixed_function.h) that no GL
+ * implementation has validated.  Beside that: known-answer tests derived by hand from the shader text
+ * (tests/test_oracle_kat.py) and the tinyobjloader cross-check of the scene inputs.
  */
 #ifndef VCT_ORACLE_H
 #define VCT_ORACLE_H

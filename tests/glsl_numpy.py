@@ -2,8 +2,8 @@
 (shader/voxelize.vert:24-30, voxelize.geom:25-55, voxelize.frag:66-161, mipmap.comp:10-100, voxel_cone_tracing.frag:71-119)
 and the GL rules of SURVEY.md appendix A, NOT from oracle/vct_oracle.cpp.  Test infrastructure only.
 
-Purpose: the C++ oracle is the parity anchor of the CUDA path, and nothing in this image can run the reference's GLSL
-(parity unpinned).  A transcription slip in the oracle would be copied faithfully by the kernels and
+Purpose: the C++ oracle is the parity anchor of the CUDA path, and no GL driver in this image can run the reference's GLSL
+(this module predates oracle/glsl_ref/, which compiles the shader text itself for the CPU).  A transcription slip in the oracle would be copied faithfully by the kernels and
 every "CUDA == oracle" test would still pass.  This module narrows that gap: a different author-pass, a different language,
 array-at-a-time instead of fragment-at-a-time, compared against the oracle on the reference scene by
 tests/test_second_restatement.py.  It shares only the written-down rules (1/256-pixel snapping, top-left fill rule,

@@ -1,7 +1,8 @@
 """GPU parity tests: every stage of the CUDA path (through the C ABI) against the CPU oracle on
 the same inputs.  Bars (BASELINE.json north_star): voxel occupancy bit-exact, voxel colour <= 1 LSB
 (we require bit-exact: the kernels share the oracle's arithmetic rules), frame max-abs <= 2/255 and
-PSNR >= 45 dB.  Oracle = CPU restatement; llvmpipe is unavailable in this image (parity unpinned)."""
+PSNR >= 45 dB.  Oracle = CPU restatement, itself equal bit for bit to the reference's own GLSL run on the CPU (tests/test_glsl_ref.py); the
+fixed-function GL rules stay unpinned: llvmpipe is unavailable in this image."""
 import numpy as np
 import pytest
 
@@ -378,6 +379,32 @@ def test_frame_config1_cornell_128_512(sampler):
     for k in ("samples_diffuse", "samples_shadow", "samples_specular", "samples_refraction"):
         a, b = getattr(cnt, k), getattr(ts, k)
         assert abs(a - b) <= 5e-2 * max(b, 1), (k, a, b)   # alpha == 1.0 rounding may flip a loop exit by one (invisible) sample
+
+
+@pytest.mark.parametrize("suzanne,R,W,H", [(False, 128, 512, 512), (True, 128, 400, 300)])
+def test_cuda_vs_reference_glsl(suzanne, R, W, H):
+    """The CUDA path against THE REFERENCE'S OWN GLSL executed on the CPU (oracle/_ref/libvct_glsl_ref.so: shader/*.vert|geom|frag|comp
+    translated syntactically and compiled against the reference's GLM, see oracle/glsl_ref/harness.cpp; built in the dev container,
+    ships prebuilt).  BASELINE config 1 and the Suzanne scene (refraction): voxel grid, every mip volume and the G-buffer bit for
+    bit, the frame inside the 2/255 / 45 dB gate for both samplers."""
+    from oracle import glsl_ref as G
+    if not G.available():
+        pytest.skip("oracle/_ref/libvct_glsl_ref.so not shipped")
+    sc = S.cornell_scene(with_suzanne=suzanne)
+    view, proj = S.reference_camera(W / H)
+    ref = G.render_frame(sc, view, proj, R, W, H, mode="rules")
+    p = capi.Pipeline(sc, R, W, H, 7)
+    for sampler in SAMPLERS:
+        p.render_frame(view, proj, capi.default_params(sampler=sampler))
+        _check_frame(p.target.frame(), ref)
+    got = p.grid.download(0)
+    assert np.array_equal(got, ref["base"]), f"{(got != ref['base']).sum()} voxels differ from the reference's voxelize.frag"
+    assert_pyramid_equal(p.grid, ref["pyramid"])
+    gb = p.target.gbuffer()
+    hit = ref["gbuffer"].tri_id != 0xFFFFFFFF
+    assert np.array_equal(gb["tri_id"], ref["gbuffer"].tri_id)
+    assert np.array_equal(gb["world_pos"][hit], ref["gbuffer"].world_pos[hit]) and np.array_equal(gb["normal"][hit], ref["gbuffer"].normal[hit])
+    p.close()
 
 
 @pytest.mark.parametrize("sampler", SAMPLERS)

@@ -1,7 +1,8 @@
 """Known-answer tests pinning the CPU oracle.  The vectors were derived by hand
 from the shader text (shader/voxelize.frag:66-120, voxelize.geom:25-55, mipmap.comp:40-98,
 voxel_cone_tracing.frag:88-119, src/camera.h, glm::perspective); the reference itself ships no
-tests or golden data, so these are the oracle's only pins ("parity unpinned")."""
+tests or golden data.  (Since round 2 the oracle is also held, bit for bit, against the reference's GLSL text itself
+compiled for the CPU: tests/test_glsl_ref.py.)"""
 import math
 
 import numpy as np

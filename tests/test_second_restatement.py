@@ -1,5 +1,6 @@
 """The C++ oracle against a second, independently written numpy restatement of the reference's GLSL (tests/glsl_numpy.py) on
-the reference scene -- narrows "parity unpinned" (nothing in this image can execute the shaders themselves): a slip in one
+the reference scene (kept beside tests/test_glsl_ref.py, which runs the shader text itself: this one shares no fixed-function code
+with the oracle): a slip in one
 of the two restatements of voxelize.frag:95-161 (V4/V5), mipmap.comp:45-100 (M1) or voxel_cone_tracing.frag:80-119 (C2/C3)
 shows up as a difference here.  CPU only."""
 import numpy as np
