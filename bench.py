@@ -14,8 +14,9 @@ Besides the headline config the line carries `extra_configs`: BASELINE.json's co
 512^3, 3840x2160) and 5 (4 M triangles, 1024^3, 7680x4320, 16 cones) device-timed at the same N, so that
 the driver's 1/2/4/8 runs hold the scaling curves north_star asks for.
 
-`--impl reference` times the CPU oracle (the reference's GLSL needs an OpenGL 4.5 driver that does not
-exist in this image -- see DESIGN.md) on the host cores on a bounded sample of the same workload.
+`--impl reference` times the reference's own GLSL compiled for the CPU (oracle/_ref/libvct_glsl_ref.so, kind "reference"; no
+OpenGL 4.5 driver exists in this image -- see DESIGN.md) or, where that library is absent or cannot render the workload, the CPU
+oracle (kind "port"), on all host cores, on a bounded sample of the same workload.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -145,23 +146,42 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------- CPU oracle legs
 class CpuWorkload:
-    """The same frame on the host cores with the oracle.  voxelize + mip + G-buffer are run (and timed) in
-    full once; a "step" then traces every `stride`-th 32x32 screen tile (a different phase each step).  With
-    stride 1 a step IS the full trace; with stride > 1 the frame time is t_voxelize + t_mip + t_gbuffer +
-    stride * t_trace_step and the line says that it is extrapolated."""
+    """The same frame on the host cores.  Two back ends:
+    * kind "reference": THE REFERENCE'S OWN GLSL executed on the CPU (oracle/_ref/libvct_glsl_ref.so -- its six shaders rewritten
+      syntactically and compiled against its vendored GLM, build "glm" = GLM's own built-ins; OpenMP over rows / slices), used when
+      the library is there and the workload is one the reference can render (RGBA8, 9 diffuse cones);
+    * kind "port": the restated oracle (C++/OpenMP) otherwise.
+    voxelize + mip + G-buffer are run (and timed) in full once; a "step" then traces every `stride`-th 32x32 screen tile (a
+    different phase each step).  With stride 1 a step IS the full trace; with stride > 1 the frame time is t_voxelize + t_mip +
+    t_gbuffer + stride * t_trace_step and the line says that it is extrapolated."""
 
     def __init__(self, cfg):
         from oracle import orc
         self.orc, self.cfg = orc, cfg
+        self.ref = None
+        if cfg.get("cones", 9) == 9:
+            try:
+                from oracle import glsl_ref
+                if glsl_ref.available():
+                    glsl_ref.lib()
+                    self.ref = glsl_ref
+            except (OSError, subprocess.CalledProcessError):
+                self.ref = None
+        self.kind = "reference" if self.ref else "port"
         # torchrun exports OMP_NUM_THREADS=1 to every rank: the baseline uses all the cores whoever launched it
         orc.set_num_threads(os.cpu_count() or 1)
         self.sc = build_scene(cfg)
         R, W, H = cfg["R"], cfg["W"], cfg["H"]
         self.view, self.proj = S.reference_camera(W / H)
         orc.mipmap(np.zeros((8, 8, 8), np.uint32), 4)   # spin up the OpenMP pool outside the timed part
-        t0 = time.perf_counter(); base, _ = orc.voxelize(self.sc, R)
-        t1 = time.perf_counter(); self.pyr = orc.mipmap(base, 7)
-        t2 = time.perf_counter(); self.g = orc.gbuffer(self.sc, self.view, self.proj, W, H)
+        if self.ref:
+            t0 = time.perf_counter(); tex, _ = self.ref.voxelize(self.sc, R, "glm")
+            t1 = time.perf_counter(); self.pyr = self.ref.mipmap(tex[0], 7, "glm")
+            t2 = time.perf_counter(); self.g = self.ref.gbuffer(self.sc, self.view, self.proj, W, H, "glm")
+        else:
+            t0 = time.perf_counter(); base, _ = orc.voxelize(self.sc, R)
+            t1 = time.perf_counter(); self.pyr = orc.mipmap(base, 7)
+            t2 = time.perf_counter(); self.g = orc.gbuffer(self.sc, self.view, self.proj, W, H)
         t3 = time.perf_counter()
         self.t_vox, self.t_mip, self.t_gbuf = t1 - t0, t2 - t1, t3 - t2
         self.cores = orc.num_threads()
@@ -169,7 +189,11 @@ class CpuWorkload:
         self.n_tiles = ((W + 31) // 32) * ((H + 31) // 32)
 
     def trace_step(self, stride: int, phase: int):
+        """-> (seconds, samples taken or None: the reference's shader does not count them)"""
         t0 = time.perf_counter()
+        if self.ref:
+            self.ref.shade(self.sc, self.view, self.g, self.pyr, None, stride, phase % stride, "glm")
+            return time.perf_counter() - t0, None
         _, st = self.orc.trace(self.sc, self.view, self.g, self.pyr, self.orc.default_params(n_diffuse_cones=self.cfg.get("cones", 9)), stride, phase % stride, self.frame)
         dt = time.perf_counter() - t0
         return dt, int(st.samples)
@@ -190,7 +214,9 @@ class CpuWorkload:
     def sample_text(self, stride: int) -> str:
         how = ("each step cone-traces the whole frame" if stride == 1 else
                f"each step cone-traces every {stride}th 32x32 tile; the frame time is EXTRAPOLATED: voxelize + mip + G-buffer + {stride} x the step's trace time")
-        return (f"oracle = CPU restatement of the GLSL (C++/OpenMP, {self.cores} threads; Mesa llvmpipe is unavailable in this image): "
+        what = ("the reference's own GLSL (shader/*.vert|geom|frag|comp rewritten syntactically, compiled against its vendored GLM, oracle/_ref/libvct_glsl_ref.so) "
+                "executed on the CPU behind the oracle's fixed-function rules" if self.ref else "oracle = CPU restatement of the GLSL")
+        return (f"{what} (C++/OpenMP, {self.cores} threads; Mesa llvmpipe is unavailable in this image): "
                 f"voxelize+mip+G-buffer of '{self.cfg['name']}' in full (timed once), {how}")
 
 
@@ -211,7 +237,7 @@ def run_reference(args, cfg, rank: int, world: int):
         "ms_per_step": step_ms, "frame_ms": frame_ms, "extrapolated": stride != 1, "tile_stride": stride,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 (u8 RGBA storage)", "data": "synthetic",
         "config": config_dict(cfg, world, args.sampler, args.exchange, wl.sc.n_triangles, frames_in_flight(args, wl.sc.n_triangles, world, args.exchange)),
-        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": wl.cores, "kind": "port", "sample": wl.sample_text(stride),
+        "cpu_baseline": {"value": v, "unit": "frames/s", "cores": wl.cores, "kind": wl.kind, "sample": wl.sample_text(stride),
                          "voxelize_s": wl.t_vox, "mip_s": wl.t_mip, "gbuffer_s": wl.t_gbuf},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
@@ -568,7 +594,7 @@ def run_ours(args, cfg, rank: int, world: int, local_rank: int):
         stride = wl.pick_stride(4, 16.0)
         ts = [wl.trace_step(stride, i)[0] for i in range(4)]
         fs = sum(wl.frame_seconds(t, stride) for t in ts) / len(ts)
-        cpu = {"value": 1.0 / fs, "unit": "frames/s", "cores": wl.cores, "kind": "port", "sample": wl.sample_text(stride) + " (4 steps)",
+        cpu = {"value": 1.0 / fs, "unit": "frames/s", "cores": wl.cores, "kind": wl.kind, "sample": wl.sample_text(stride) + " (4 steps)",
                "frame_s": fs, "voxelize_s": wl.t_vox, "mip_s": wl.t_mip, "gbuffer_s": wl.t_gbuf}
 
     n_tris, n_fif = rig.sc.n_triangles, rig.F

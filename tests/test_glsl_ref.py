@@ -191,6 +191,19 @@ def test_frame_config1_bit_exact():
     assert (glm["frame"] != ref["frame"]).mean() < 0.02
 
 
+def test_frame_config2_full_size_bit_exact():
+    """BASELINE config 2, the benchmark workload, at full size (256^3, 1920x1080): all four stages from the reference's GLSL"""
+    sc = S.cornell_scene()
+    view, proj = S.reference_camera(1920 / 1080)
+    ref = orc.render_frame(sc, view, proj, 256, 1920, 1080)
+    got = G.render_frame(sc, view, proj, 256, 1920, 1080, mode="rules")
+    assert np.array_equal(got["base"], ref["base"])
+    assert all(np.array_equal(got["pyramid"].levels[d][l], ref["pyramid"].levels[d][l]) for d in range(6) for l in range(1, 7))
+    assert np.array_equal(got["gbuffer"].tri_id, ref["gbuffer"].tri_id) and np.array_equal(got["gbuffer"].depth, ref["gbuffer"].depth)
+    assert np.array_equal(got["frame"], ref["frame"]), f"{(got['frame'] != ref['frame']).sum()} pixels differ"
+    assert ref["trace_stats"].shaded_pixels > 700_000
+
+
 @pytest.mark.parametrize("kw", [dict(), dict(enable_shadow=0), dict(enable_diffuse=0, enable_specular=0), dict(enable_direct=0),
                                 dict(view_voxel_dir=1, view_voxel_lod=1.5), dict(view_voxel_dir=4, view_voxel_lod=0.0), dict(view_voxel_dir=3, view_voxel_lod=3.25)])
 @pytest.mark.parametrize("camera", [CAMERAS[0], CAMERAS[2]])
