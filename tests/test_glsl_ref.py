@@ -217,3 +217,39 @@ def test_frame_variants_bit_exact(kw, camera):
     frame = G.shade(sc, view, ref["gbuffer"], ref["pyramid"], orc.default_params(**kw), mode="rules")
     assert np.array_equal(frame, ref["frame"]), f"{(frame != ref['frame']).sum()} pixels differ, max {byte_diff(frame, ref['frame']).max()}"
     assert (ref["frame"] != 0xFF404026).mean() > 0.3
+
+
+# --------------------------------------------------------------------------- BASELINE configs 3 and 4 at full size
+@pytest.mark.parametrize("frame_no", [0, 21])
+def test_config3_full_size(frame_no):
+    """BASELINE config 3 (Cornell box + rotating Suzanne, 512^3, 2560x1440): voxel grid (all six textures), the 36 mip volumes and the
+    G-buffer in full, the frame on every 8th 32x32 tile"""
+    import bench
+    cfg = bench.CONFIGS[3]
+    sc = bench.build_scene(cfg, frame_no)
+    R, W, H = cfg["R"], cfg["W"], cfg["H"]
+    base, st = orc.voxelize(sc, R)
+    tex, n = G.voxelize(sc, R, "rules")
+    assert n == st.fragments + st.fragments_oob
+    assert all(np.array_equal(tex[i], base) for i in range(6))
+    del tex
+    po, pg = orc.mipmap(base, 7), G.mipmap(base, 7, "rules")
+    assert all(np.array_equal(pg.levels[d][l], po.levels[d][l]) for d in range(6) for l in range(1, 7))
+    view, proj = S.reference_camera(W / H)
+    go, gg = orc.gbuffer(sc, view, proj, W, H), G.gbuffer(sc, view, proj, W, H, "rules")
+    assert np.array_equal(go.tri_id, gg.tri_id) and np.array_equal(go.depth, gg.depth)
+    assert np.array_equal(go.world_pos.view(np.uint32), gg.world_pos.view(np.uint32)) and np.array_equal(go.normal.view(np.uint32), gg.normal.view(np.uint32))
+    fo, _ = orc.trace(sc, view, go, po, None, 8, frame_no % 8)
+    fg = G.shade(sc, view, go, po, None, 8, frame_no % 8, "rules")
+    assert np.array_equal(fo, fg) and (fo != 0).sum() > 400_000
+
+
+def test_config4_voxel_grid_full_size():
+    """BASELINE config 4 (1 M synthetic triangles, 512^3): 8.8 M fragments through voxelize.frag's compare-and-swap loop"""
+    import bench
+    cfg = bench.CONFIGS[4]
+    sc = bench.build_scene(cfg)
+    base, st = orc.voxelize(sc, cfg["R"])
+    tex, n = G.voxelize(sc, cfg["R"], "rules")
+    assert n == st.fragments + st.fragments_oob and st.fragments > 8_000_000
+    assert np.array_equal(tex[0], base) and np.array_equal(tex[5], base)

@@ -162,3 +162,28 @@ def test_mip_sparse_and_opaque_grid_512():
     _check_pyramid(g, base)
     g.close()
     dev.close()
+
+
+def test_config2_cuda_vs_reference_glsl_full_size():
+    """BASELINE config 2 -- the benchmark workload, 256^3 / 1920x1080 -- against THE REFERENCE'S OWN GLSL executed on the CPU
+    (oracle/_ref/libvct_glsl_ref.so, built in the dev container from /root/reference where it lies, shipped prebuilt): voxel grid,
+    the 36 mip volumes and the G-buffer bit for bit, the whole frame inside the 2/255 / 45 dB gate."""
+    from oracle import glsl_ref as G
+    if not G.available():
+        pytest.skip("oracle/_ref/libvct_glsl_ref.so not shipped")
+    sc = S.cornell_scene()
+    R, W, H = 256, 1920, 1080
+    view, proj = S.reference_camera(W / H)
+    ref = G.render_frame(sc, view, proj, R, W, H, mode="rules")
+    p = capi.Pipeline(sc, R, W, H, 7)
+    p.render_frame(view, proj, capi.default_params(sampler=capi.SAMPLER_TEX))
+    assert np.array_equal(p.grid.download(0), ref["base"])
+    for l in range(1, 7):
+        for d in range(6):
+            assert np.array_equal(p.grid.download(l, d), ref["pyramid"].levels[d][l]), (l, d)
+    gb = p.target.gbuffer()
+    hit = ref["gbuffer"].tri_id != 0xFFFFFFFF
+    assert np.array_equal(gb["tri_id"], ref["gbuffer"].tri_id)
+    assert np.array_equal(gb["world_pos"][hit], ref["gbuffer"].world_pos[hit]) and np.array_equal(gb["normal"][hit], ref["gbuffer"].normal[hit])
+    _check_frame_tiles(p.target.frame(), ref["frame"], np.ones((H, W), bool))
+    p.close()
