@@ -36,6 +36,7 @@ def lib():
         for m in MODES:
             f = lambda n: getattr(L, "glref_%s_%s" % (m, n))  # noqa: E731
             f("voxelize").argtypes = [C.POINTER(orc.SceneT), C.c_int, C.c_void_p, C.POINTER(C.c_uint64)]
+            f("voxelize_variant").argtypes = [C.POINTER(orc.SceneT), C.c_int, C.c_void_p, C.POINTER(C.c_uint64), C.c_int, C.c_int, C.c_uint32]
             f("mipmap").argtypes = [C.c_void_p, C.c_int, C.c_int]
             f("gbuffer").argtypes = [C.POINTER(orc.SceneT), orc.f32p, orc.f32p, C.c_int, C.c_int] + [C.c_void_p] * 5
             f("shade").argtypes = [C.POINTER(orc.SceneT), orc.f32p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [
@@ -62,6 +63,22 @@ def voxelize(scene, R: int, mode: str = "rules"):
     rc = _fn(mode, "voxelize")(C.byref(sr.c), R, ptrs, C.byref(n))
     assert rc == 0, rc
     return tex, int(n.value)
+
+
+ORDER_RULE, ORDER_REVERSED_IN_TRIANGLE, ORDER_REVERSED_TRIANGLES, ORDER_RANDOM = 0, 1, 2, 3
+BARY_SNAPPED, BARY_UNSNAPPED = 0, 1
+
+
+def voxelize_variant(scene, R: int, order: int = ORDER_RULE, bary: int = BARY_SNAPPED, seed: int = 0, mode: str = "rules") -> np.ndarray:
+    """SENSITIVITY STUDIES ONLY (tools/fixed_function_sensitivity.py): the voxel grid under another valid fragment order (GL guarantees none)
+    or with barycentrics from the unsnapped vertex positions; -> texture 0"""
+    sr = orc.SceneRef(scene)
+    tex = np.zeros((6, R, R, R), np.uint32)
+    ptrs = (C.c_void_p * 6)(*[tex[i].ctypes.data for i in range(6)])
+    n = C.c_uint64(0)
+    rc = _fn(mode, "voxelize_variant")(C.byref(sr.c), R, ptrs, C.byref(n), order, bary, seed)
+    assert rc == 0, rc
+    return tex[0]
 
 
 def mipmap(base: np.ndarray, n_levels: int = 7, mode: str = "rules") -> orc.Pyramid:

@@ -19,6 +19,7 @@
  */
 #include <stdint.h>
 #include <string.h>
+#include <algorithm>
 #include <limits>
 #include <vector>
 
@@ -102,8 +103,39 @@ void upload_lights(S& s, const orc_scene_t* sc) {
   s.point_light_count = (int)sc->n_lights;
 }
 
-/* ---- Renderer::voxelize(), src/renderer.cpp:316-353, without the filter() call ---- */
-int run_voxelize(const orc_scene_t* sc, int R, uint32_t* const tex[6], uint64_t* n_fragments) {
+/* ---- Renderer::voxelize(), src/renderer.cpp:316-353, without the filter() call ----
+ * order / bary: SENSITIVITY STUDY switches (tools/fixed_function_sensitivity.py), both 0 for every parity check:
+ *   order 0 = rule R4 (draw order, index-buffer order, pixel row ascending, column ascending) -- fragments executed as they are generated;
+ *         1 = rows and columns descending inside every triangle; 2 = triangles in reverse order; 3 = all fragments of the frame in a
+ *         seeded random order (GL guarantees no order between the fragments of a draw call: each is one valid execution);
+ *   bary  0 = rule R3 (barycentrics from the snapped vertex positions); 1 = from the unsnapped float positions (SURVEY appendix A's
+ *         first draft), coverage unchanged. */
+struct VoxTriJob { GeomRun::Out e[3]; vct_ff::RasterTri rt; float xw[3], yw[3]; uint32_t material; };
+struct VoxFragJob { uint32_t tri; int i, j; };
+
+inline void run_voxel_fragment(voxelize_frag& fs, const VoxTriJob& tj, int i, int j, int bary) {
+  using namespace vct_ff;
+  float b[3];
+  if (!raster_sample(tj.rt, i, j, b)) return;
+  if (bary == 1) {
+    const float px = (float)i + 0.5f, py = (float)j + 0.5f;
+    float e[3];
+    for (int k = 0; k < 3; k++) {
+      const int a = (k + 1) % 3, c = (k + 2) % 3;
+      e[k] = (tj.xw[c] - tj.xw[a]) * (py - tj.yw[a]) - (tj.yw[c] - tj.yw[a]) * (px - tj.xw[a]);
+    }
+    const float sum = (e[0] + e[1]) + e[2];
+    for (int k = 0; k < 3; k++) b[k] = e[k] / sum;
+  }
+  const GeomRun::Out* e = tj.e;
+  for (int c = 0; c < 4; c++) fs.gs_out.world_position[c] = interp(b, e[0].v.world_position[c], e[1].v.world_position[c], e[2].v.world_position[c]);
+  for (int c = 0; c < 3; c++) fs.gs_out.normal[c] = interp(b, e[0].v.normal[c], e[1].v.normal[c], e[2].v.normal[c]);
+  for (int c = 0; c < 2; c++) fs.gs_out.uv[c] = interp(b, e[0].v.uv[c], e[1].v.uv[c], e[2].v.uv[c]);
+  fs._init_globals();
+  fs.main();
+}
+
+int run_voxelize(const orc_scene_t* sc, int R, uint32_t* const tex[6], uint64_t* n_fragments, int order, int bary, uint32_t seed) {
   using namespace vct_ff;
   const size_t nvox = (size_t)R * R * R;
   for (int i = 0; i < 6; i++) memset(tex[i], 0, nvox * sizeof(uint32_t));   /* clear_tex_3d :320-321 */
@@ -118,6 +150,8 @@ int run_voxelize(const orc_scene_t* sc, int R, uint32_t* const tex[6], uint64_t*
   upload_lights(fs, sc);
   const int W = 2 * R;               /* :339-340 */
   uint64_t frags = 0;
+  std::vector<VoxTriJob> tri_jobs;   /* order != 0 only */
+  std::vector<VoxFragJob> frag_jobs;
   for (uint32_t d = 0; d < sc->n_draws; d++) {       /* draw_models :241-256 */
     const orc_draw_t& dr = sc->draws[d];
     vs.model = load_mat4(dr.model);
@@ -137,26 +171,61 @@ int run_voxelize(const orc_scene_t* sc, int R, uint32_t* const tex[6], uint64_t*
       gs.main();
       if (gs.emitted.size() != 3) return -2;
       /* fixed function: divide by w (= 1), viewport R1, rasterise R2, interpolate R3 (w = 1: affine) */
-      float xw[3], yw[3];
+      VoxTriJob tj;
       for (int k = 0; k < 3; k++) {
+        tj.e[k] = gs.emitted[k];
         const vec4 p = gs.emitted[k].pos;
-        xw[k] = viewport(p.x / p.w, W);
-        yw[k] = viewport(p.y / p.w, W);
+        tj.xw[k] = viewport(p.x / p.w, W);
+        tj.yw[k] = viewport(p.y / p.w, W);
       }
-      RasterTri rt = raster_setup(xw, yw, W, W);
-      if (!rt.valid) continue;
-      const GeomRun::Out* e = gs.emitted.data();
-      for (int j = rt.jmin; j <= rt.jmax; j++)
-        for (int i = rt.imin; i <= rt.imax; i++) {
+      tj.material = dr.material;
+      tj.rt = raster_setup(tj.xw, tj.yw, W, W);
+      if (!tj.rt.valid) continue;
+      for (int j = tj.rt.jmin; j <= tj.rt.jmax; j++)
+        for (int i = tj.rt.imin; i <= tj.rt.imax; i++) {
           float b[3];
-          if (!raster_sample(rt, i, j, b)) continue;
-          for (int c = 0; c < 4; c++) fs.gs_out.world_position[c] = interp(b, e[0].v.world_position[c], e[1].v.world_position[c], e[2].v.world_position[c]);
-          for (int c = 0; c < 3; c++) fs.gs_out.normal[c] = interp(b, e[0].v.normal[c], e[1].v.normal[c], e[2].v.normal[c]);
-          for (int c = 0; c < 2; c++) fs.gs_out.uv[c] = interp(b, e[0].v.uv[c], e[1].v.uv[c], e[2].v.uv[c]);
-          fs._init_globals();
-          fs.main();
+          if (!raster_sample(tj.rt, i, j, b)) continue;
           frags++;
+          if (order == 0) run_voxel_fragment(fs, tj, i, j, bary);
+          else frag_jobs.push_back(VoxFragJob{(uint32_t)tri_jobs.size(), i, j});
         }
+      if (order != 0) tri_jobs.push_back(tj);
+    }
+  }
+  if (order != 0) {
+    const size_t n = frag_jobs.size();
+    if (order == 1) {          /* inside every triangle: last fragment first */
+      size_t a = 0;
+      while (a < n) {
+        size_t b = a;
+        while (b < n && frag_jobs[b].tri == frag_jobs[a].tri) b++;
+        std::reverse(frag_jobs.begin() + a, frag_jobs.begin() + b);
+        a = b;
+      }
+    } else if (order == 2) {   /* last triangle first, fragments of a triangle in rule order */
+      std::vector<VoxFragJob> r;
+      r.reserve(n);
+      size_t b = n;
+      while (b > 0) {
+        size_t a = b - 1;
+        while (a > 0 && frag_jobs[a - 1].tri == frag_jobs[b - 1].tri) a--;
+        r.insert(r.end(), frag_jobs.begin() + a, frag_jobs.begin() + b);
+        b = a;
+      }
+      frag_jobs.swap(r);
+    } else {                    /* Fisher-Yates with a 64-bit LCG */
+      uint64_t st = 0x9E3779B97F4A7C15ull ^ seed;
+      for (size_t k = n; k > 1; k--) {
+        st = st * 6364136223846793005ull + 1442695040888963407ull;
+        const size_t r = (size_t)((st >> 33) % k);
+        std::swap(frag_jobs[k - 1], frag_jobs[r]);
+      }
+    }
+    uint32_t bound = 0xFFFFFFFFu;
+    for (const VoxFragJob& fj : frag_jobs) {
+      const VoxTriJob& tj = tri_jobs[fj.tri];
+      if (tj.material != bound) { bind_material(fs, sc->mats[tj.material]); bound = tj.material; }
+      run_voxel_fragment(fs, tj, fj.i, fj.j, bary);
     }
   }
   if (n_fragments) *n_fragments = frags;
@@ -287,7 +356,13 @@ extern "C" {
 /* tex[0..5]: the six level-0 images (R^3 uint32 each), cleared by the callee like clear_tex_3d */
 int GLREF_FN(voxelize)(const orc_scene_t* sc, int R, uint32_t* const* tex, uint64_t* n_fragments) {
   if (!sc || !tex || R <= 0) return -1;
-  return GLREF_NS::run_voxelize(sc, R, tex, n_fragments);
+  return GLREF_NS::run_voxelize(sc, R, tex, n_fragments, 0, 0, 0u);
+}
+
+/* sensitivity studies only: another fragment order / barycentric rule (see run_voxelize) */
+int GLREF_FN(voxelize_variant)(const orc_scene_t* sc, int R, uint32_t* const* tex, uint64_t* n_fragments, int order, int bary, uint32_t seed) {
+  if (!sc || !tex || R <= 0 || order < 0 || order > 3 || bary < 0 || bary > 1) return -1;
+  return GLREF_NS::run_voxelize(sc, R, tex, n_fragments, order, bary, seed);
 }
 
 /* levels[d * n_levels + l]: level 0 of every direction filled by the caller */
