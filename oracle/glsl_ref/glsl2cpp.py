@@ -2,7 +2,7 @@
 """glsl2cpp.py -- turns the REFERENCE'S OWN shader text into C++ that compiles against the reference's vendored GLM.
 
 TEST INFRASTRUCTURE ONLY (oracle/).  Nothing is copied into the repository: the shaders are read from where they lie
-(/root/reference/shader/*.vert|geom|frag|comp) at build time and the generated text goes to oracle/_ref/gen/ (git-ignored).
+(/root/reference/shader/*.vert|geom|frag|comp) at build time; the generated text lives in oracle/_ref/gen/ (git-ignored) only while the library is being compiled.
 
 The translation is purely syntactic -- no expression, constant or statement of a shader body is touched:
   * `#version`, `layout(...)` qualifiers and the `uniform` / `in` / `out` storage qualifiers are dropped, so every global

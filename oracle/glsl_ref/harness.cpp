@@ -3,7 +3,7 @@
  * on the CPU.  TEST INFRASTRUCTURE ONLY: the second, reference-sourced checker beside the restated oracle (vct_oracle.cpp).
  *
  * How: oracle/glsl_ref/glsl2cpp.py rewrites the shader text, read from /root/reference where it lies, into C++ member
- * declarations (purely syntactic, see its header; output under oracle/_ref/gen/, never committed); each shader becomes the
+ * declarations (purely syntactic, see its header; output under oracle/_ref/gen/ during the build only, never committed); each shader becomes the
  * body of a struct below; vectors, matrices, swizzles and built-ins are the reference's vendored GLM 0.9.9
  * (thirdparty/glm) plus glsl_env.h.  This file is the "driver + fixed-function GPU" around them:
  *   * the uniform / vertex-array set-up and draw loop of src/renderer.cpp:241-256 (draw_models), :283-314 (filter),
