@@ -18,6 +18,7 @@
  */
 #include <array>
 #include <cmath>
+#include <vector>
 
 namespace GLREF_NS {
 
@@ -102,7 +103,29 @@ struct sampler3D {
   const uint32_t* const* levels = nullptr;   /* [n_levels] */
   int R = 0, n_levels = 0;
 };
+/* PERFORMANCE-MODEL hook (glref_*_tex_model, tools/tex_lane_model.py): when a recorder is installed every textureLod call
+ * appends which levels the fetch blends and whether their 2x2x2 footprints hold only zero texels.  Never set during parity checks. */
+struct TexRecord { float lod; bool empty_l0, empty_l1; };
+inline std::vector<TexRecord>*& tex_recorder() { static thread_local std::vector<TexRecord>* r = nullptr; return r; }
+inline bool footprint_is_zero(const uint32_t* tex, int N, vec3 const& p) {
+  const float ux = p.x * (float)N - 0.5f, uy = p.y * (float)N - 0.5f, uz = p.z * (float)N - 0.5f;
+  if (!(fabsf(ux) < 1.0e9f) || !(fabsf(uy) < 1.0e9f) || !(fabsf(uz) < 1.0e9f)) return true;
+  const int ix = (int)floorf(ux), iy = (int)floorf(uy), iz = (int)floorf(uz);
+  for (int dz = 0; dz < 2; dz++)
+    for (int dy = 0; dy < 2; dy++)
+      for (int dx = 0; dx < 2; dx++) {
+        const int x = ix + dx, y = iy + dy, z = iz + dz;
+        if (x < 0 || y < 0 || z < 0 || x >= N || y >= N || z >= N) continue;
+        if (tex[((size_t)z * N + y) * N + x]) return false;
+      }
+  return true;
+}
 inline vec4 textureLod(sampler3D const& s, vec3 const& p, float lod) {   /* R7 */
+  if (tex_recorder()) {
+    const float l = fminf(fmaxf(lod, 0.0f), (float)(s.n_levels - 1));
+    const int l0 = (int)floorf(l), l1 = l0 + 1 < s.n_levels ? l0 + 1 : s.n_levels - 1;
+    tex_recorder()->push_back(TexRecord{l, footprint_is_zero(s.levels[l0], s.R >> l0, p), footprint_is_zero(s.levels[l1], s.R >> l1, p)});
+  }
   vct_ff::Pyramid pyr{s.levels, s.R, s.n_levels, 0};
   float out[4];
   vct_ff::texture_lod(pyr, 0, vct_ff::v3(p.x, p.y, p.z), lod, out);

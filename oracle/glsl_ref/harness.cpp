@@ -348,6 +348,133 @@ int run_shade(const orc_scene_t* sc, const float view[16], int W, int H, const u
   return 0;
 }
 
+#if GLREF_RULES
+/* ---- PERFORMANCE MODEL of the texture-unit work of the product's cone kernel (tools/tex_lane_model.py; not a parity check) ----
+ * Every cone the reference's fragment shader would trace for the pixels of one 2x2 pixel block (= one TEX quad of cone_kernel_fast)
+ * is marched with the shader's own trace_cone; a recorder in textureLod classifies every sample the way the kernel does
+ * (csrc/cone_trace.cu trace_cone_fast): 0 = no texture fetch (footprint empty, or level 0 alone, which the kernel filters in
+ * software), 1 = one level through the texture unit, 2 = two levels.  The TEX pipe works on whole quads, so a fetch costs the same
+ * whether one or four lanes of a quad need it; the model adds up quad-level fetch units (one level of one direction of one quad) for
+ *   [0] ideal: every lane's own need / 4 (perfectly packed quads)
+ *   [1] the kernel as it is: a one-level and a two-level instruction are issued separately when the lanes of a quad disagree
+ *   [2] quad-uniform decision: if any lane of the quad needs two levels all its fetching lanes take the two-level instruction
+ *   [3] lane-autonomous march: every lane skips its own empty samples; the quad pays max-over-lanes per fetching round (+ rule [2])
+ *   [4] samples (lane steps), [5] samples that fetch, [6] warp-level... (unused)
+ * Units are multiplied by the number of directions with a non-zero weight (3 almost always). */
+struct ConeSeq { std::vector<uint8_t> cls; };
+
+inline void classify(const std::vector<TexRecord>& rec, int n_levels, ConeSeq& out) {
+  out.cls.clear();
+  for (size_t i = 0; i + 3 <= rec.size(); i += 3) {
+    const float lod = rec[i].lod;
+    const bool e0 = rec[i].empty_l0 && rec[i + 1].empty_l0 && rec[i + 2].empty_l0;
+    const bool e1 = rec[i].empty_l1 && rec[i + 1].empty_l1 && rec[i + 2].empty_l1;
+    uint8_t c;
+    if (lod < 1.0f) c = (lod > 0.0f && !e1) ? 1 : 0;          /* level 1 through the texture unit, level 0 in software */
+    else {
+      const bool two = lod > floorf(lod);
+      if (two) c = e1 ? 0 : (e0 ? 1 : 2);                       /* coarser level empty => finer empty too */
+      else c = e0 ? 0 : 1;
+    }
+    out.cls.push_back(c);
+  }
+  (void)n_levels;
+}
+
+int run_tex_model(const orc_scene_t* sc, const float view[16], int W, int H, const uint32_t* tri_id, const float* world_pos, const float* normal,
+                  const uint32_t* material, const uint32_t* const* levels, int R, int n_levels, const orc_trace_params_t* prm, int tile_stride,
+                  int tile_phase, double out[8]) {
+  cone_frag proto;
+  setup_cone_frag(proto, sc, view, levels, R, n_levels, prm);
+  if (tile_stride < 1) tile_stride = 1;
+  const int tiles_x = (W + 31) / 32;
+  double t_ideal = 0, t_cur = 0, t_quad = 0, t_auto = 0, t_samples = 0, t_fetching = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : t_ideal, t_cur, t_quad, t_auto, t_samples, t_fetching)
+  for (int qy = 0; qy < H / 2; qy++) {
+    cone_frag fs = proto;
+    std::vector<TexRecord> rec;
+    std::vector<ConeSeq> seq[4];
+    for (int qx = 0; qx < W / 2; qx++) {
+      const int tile = ((2 * qy) / 32) * tiles_x + ((2 * qx) / 32);
+      if (tile % tile_stride != tile_phase) continue;
+      size_t n_jobs = 0;
+      for (int l = 0; l < 4; l++) {
+        seq[l].clear();
+        const int x = 2 * qx + (l & 1), y = 2 * qy + (l >> 1);
+        const size_t px = (size_t)y * W + x;
+        if (tri_id[px] == 0xFFFFFFFFu) continue;
+        bind_material(fs, sc->mats[material[px]]);
+        fs.vs_out.world_position = vec4(world_pos[px * 3], world_pos[px * 3 + 1], world_pos[px * 3 + 2], 1.0f);
+        fs.vs_out.normal = vec3(normal[px * 3], normal[px * 3 + 1], normal[px * 3 + 2]);
+        fs._init_globals();
+        const vec3 pos = fs.scale_and_bias(vec3(fs.vs_out.world_position.x, fs.vs_out.world_position.y, fs.vs_out.world_position.z) / fs.cube_size);
+        if (!fs.within_cube(pos, 0)) continue;
+        const vec3 n = fs.vs_out.normal;
+        const vec3 view_dir = normalize(vec3(fs.vs_out.world_position.x, fs.vs_out.world_position.y, fs.vs_out.world_position.z) - fs.camera_position);
+        /* the cones of main(): voxel_cone_tracing.frag:140-168 (diffuse), :175-218 (shadow), :229-241 (specular, refraction) */
+        struct Cone { vec3 dir; float ap, md; };
+        std::vector<Cone> cones;
+        const float TAN = 0.55785173935f, MAXD = 1.73205080757f;
+        if (fs.enable_diffuse) {
+          const vec3 o1 = normalize(fs.tangent(n)), o2 = normalize(cross(o1, n));
+          const vec3 c1 = 0.5f * (o1 + o2), c2 = 0.5f * (o1 - o2);
+          const vec3 d[9] = {n, mix(n, o1, 0.5f), mix(n, -o1, 0.5f), mix(n, o2, 0.5f), mix(n, -o2, 0.5f), mix(n, c1, 0.5f), mix(n, -c1, 0.5f), mix(n, c2, 0.5f), mix(n, -c2, 0.5f)};
+          for (int i = 0; i < 9; i++) cones.push_back(Cone{d[i], TAN, MAXD});
+        }
+        if (fs.enable_direct && fs.enable_shadow)
+          for (int i = 0; i < fs.point_light_count && i < 10; i++) {
+            const vec3 lp = fs.scale_and_bias(fs.point_lights[i].position / fs.cube_size);
+            vec3 ld = lp - pos;
+            const float d = length(ld);
+            cones.push_back(Cone{normalize(ld), 0.1f, d});
+          }
+        if (fs.enable_specular) {
+          cones.push_back(Cone{normalize(reflect(-view_dir, n)), fs.specular_aperture, MAXD});
+          if (fs.illum == 4 || fs.illum == 6 || fs.illum == 7 || fs.illum == 9) cones.push_back(Cone{refract(view_dir, n, 1.0f / fs.ior), fs.specular_aperture, MAXD});
+        }
+        seq[l].resize(cones.size());
+        for (size_t c = 0; c < cones.size(); c++) {
+          rec.clear();
+          tex_recorder() = &rec;
+          (void)fs.trace_cone(pos, cones[c].dir, cones[c].ap, cones[c].md);
+          tex_recorder() = nullptr;
+          classify(rec, n_levels, seq[l][c]);
+        }
+        n_jobs = std::max(n_jobs, cones.size());
+      }
+      for (size_t j = 0; j < n_jobs; j++) {
+        const std::vector<uint8_t>* s[4];
+        static const std::vector<uint8_t> none;
+        size_t steps = 0;
+        for (int l = 0; l < 4; l++) { s[l] = j < seq[l].size() ? &seq[l][j].cls : &none; steps = std::max(steps, s[l]->size()); }
+        std::vector<uint8_t> packed[4];
+        for (size_t k = 0; k < steps; k++) {
+          int any1 = 0, any2 = 0;
+          for (int l = 0; l < 4; l++) {
+            if (k >= s[l]->size()) continue;
+            const uint8_t c = (*s[l])[k];
+            t_samples += 1; t_ideal += c / 4.0;
+            if (c) { t_fetching += 1; packed[l].push_back(c); }
+            any1 |= c == 1; any2 |= c == 2;
+          }
+          t_cur += any1 * 1 + any2 * 2;
+          t_quad += any2 ? 2 : any1;
+        }
+        size_t rounds = 0;
+        for (int l = 0; l < 4; l++) rounds = std::max(rounds, packed[l].size());
+        for (size_t k = 0; k < rounds; k++) {
+          int m = 0;
+          for (int l = 0; l < 4; l++) if (k < packed[l].size()) m = std::max<int>(m, packed[l][k]);
+          t_auto += m;
+        }
+      }
+    }
+  }
+  out[0] = 3 * t_ideal; out[1] = 3 * t_cur; out[2] = 3 * t_quad; out[3] = 3 * t_auto; out[4] = t_samples; out[5] = t_fetching; out[6] = out[7] = 0;
+  return 0;
+}
+#endif
+
 }  // namespace GLREF_NS
 
 /* ================================================================== */
@@ -383,6 +510,16 @@ int GLREF_FN(shade)(const orc_scene_t* sc, const float view[16], int W, int H, c
   if (!sc || !tri_id || !world_pos || !normal || !material || !levels || !prm || !frame) return -1;
   return GLREF_NS::run_shade(sc, view, W, H, tri_id, world_pos, normal, material, levels, R, n_levels, prm, tile_stride, tile_phase, frame);
 }
+
+#if GLREF_RULES
+/* performance model of the cone kernel's texture-unit work (see run_tex_model); out[0..5] */
+int glref_rules_tex_model(const orc_scene_t* sc, const float view[16], int W, int H, const uint32_t* tri_id, const float* world_pos,
+                          const float* normal, const uint32_t* material, const uint32_t* const* levels, int R, int n_levels,
+                          const orc_trace_params_t* prm, int tile_stride, int tile_phase, double* out) {
+  if (!sc || !tri_id || !world_pos || !normal || !material || !levels || !prm || !out) return -1;
+  return GLREF_NS::run_tex_model(sc, view, W, H, tri_id, world_pos, normal, material, levels, R, n_levels, prm, tile_stride, tile_phase, out);
+}
+#endif
 
 /* trace_cone() of voxel_cone_tracing.frag:88-119 on its own (float results, no 8-bit rounding in between) */
 int GLREF_FN(trace_cone)(const uint32_t* const* levels, int R, int n_levels, const float origin[3], const float dir[3], float aperture,
