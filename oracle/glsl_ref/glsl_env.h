@@ -33,12 +33,21 @@ using glm::abs; using glm::cross; using glm::transpose; using glm::log2; using g
 using glm::min; using glm::max; using glm::clamp; using glm::dot; using glm::length;
 
 /* ---- (1) implicit conversions ---- */
-inline float max(float a, float b) { return glm::max(a, b); }      /* max(x, 0) */
+/* max(x, 0), clamp(emission, 0, 1), clamp(vec4, 0, 1).  GLSL leaves min / max / clamp of a NaN undefined (a vertex normal of length
+ * zero makes normalize() produce one): the rules build returns the non-NaN operand, as IEEE minNum / maxNum, NVIDIA's FMNMX, CUDA's
+ * fminf / fmaxf and the oracle do; the glm build keeps GLM's `(a < b) ? b : a`, which passes the NaN on. */
+#if GLREF_RULES
+inline float max(float a, float b) { return fmaxf(a, b); }
+inline float min(float a, float b) { return fminf(a, b); }
+inline float clamp(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+#else
+inline float max(float a, float b) { return glm::max(a, b); }
 inline float min(float a, float b) { return glm::min(a, b); }
-inline int min(int a, int b) { return glm::min(a, b); }
 inline float clamp(float v, float lo, float hi) { return glm::clamp(v, lo, hi); }
-inline vec3 clamp(vec3 const& v, float lo, float hi) { return glm::clamp(v, lo, hi); }   /* clamp(emission, 0, 1) */
-inline vec4 clamp(vec4 const& v, float lo, float hi) { return glm::clamp(v, lo, hi); }
+#endif
+inline int min(int a, int b) { return glm::min(a, b); }
+inline vec3 clamp(vec3 const& v, float lo, float hi) { return vec3(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi)); }
+inline vec4 clamp(vec4 const& v, float lo, float hi) { return vec4(clamp(v.x, lo, hi), clamp(v.y, lo, hi), clamp(v.z, lo, hi), clamp(v.w, lo, hi)); }
 inline vec4 operator/(vec4 const& v, float s) { return vec4(v.x / s, v.y / s, v.z / s, v.w / s); }   /* (a + b + c + d) / 4, rval / 2 */
 inline vec4 operator*(vec4 const& v, float s) { return vec4(v.x * s, v.y * s, v.z * s, v.w * s); }   /* rval * n (uint) */
 inline vec3 operator*(ivec3 const& a, vec3 const& b) { return vec3(a) * b; }                          /* dim * scale_and_bias(pos) */

@@ -33,7 +33,9 @@
  *   R4 fragment order for the order-dependent running average: draw order, triangle order in
  *      the index buffer, pixel row ascending, pixel column ascending (GL gives no guarantee).
  *   R5 float->int: truncation; GLSL round(): ties-to-even (rintf); normalize(v) = v / sqrt(dot);
- *      no fused multiply-add anywhere (build with -ffp-contract=off); left-to-right evaluation.
+ *      no fused multiply-add anywhere (build with -ffp-contract=off); left-to-right evaluation; min / max / clamp of a NaN
+ *      (GLSL: undefined; a zero-length vertex normal produces one) return the non-NaN operand (fminf / fmaxf = IEEE minNum /
+ *      maxNum = NVIDIA's FMNMX), so such a fragment stores colour 0.
  *   R6 unorm8 -> float: c / 255.0f; float -> unorm8: rintf(clamp(v,0,1) * 255.0f).
  *   R7 textureLod: lod clamped to [0, levels-1]; l0 = floor, l1 = min(l0+1, levels-1);
  *      per level u = s*N - 0.5, i0 = floor(u), fp32 trilinear weights, texels outside

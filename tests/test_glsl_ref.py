@@ -271,3 +271,34 @@ def test_fragment_order_is_the_only_freedom_that_matters():
         assert (b != base).sum() > 0.02 * (base != 0).sum()
     a, b = G.voxelize_variant(sc, R, order=G.ORDER_RANDOM, seed=7), G.voxelize_variant(sc, R, order=G.ORDER_RANDOM, seed=7)
     assert np.array_equal(a, b)
+
+
+# --------------------------------------------------------------------------- edge cases
+from edge_scenes import EDGE_KINDS, edge_scene  # noqa: E402
+
+
+@pytest.mark.parametrize("kind", EDGE_KINDS)
+def test_edge_cases_bit_exact(kind):
+    sc = edge_scene(kind)
+    R, W, H = 32, 96, 64
+    view, proj = S.reference_camera(W / H, eye=(0.1, 0.2, 1.6))
+    ref = orc.render_frame(sc, view, proj, R, W, H, n_levels=6)
+    got = G.render_frame(sc, view, proj, R, W, H, n_levels=6, mode="rules")
+    st = ref["voxel_stats"]
+    assert got["fragments"] == st.fragments + st.fragments_oob
+    assert np.array_equal(got["base"], ref["base"])
+    assert all(np.array_equal(got["pyramid"].levels[d][l], ref["pyramid"].levels[d][l]) for d in range(6) for l in range(1, 6))
+    assert np.array_equal(got["gbuffer"].tri_id, ref["gbuffer"].tri_id)
+    assert np.array_equal(got["frame"], ref["frame"])
+    if kind == "stack":
+        assert st.wrapped_voxels > 0 and st.max_per_voxel >= 80
+    if kind == "outside":
+        assert st.fragments_oob > 0
+    if kind == "empty":
+        assert st.fragments == 0 and (ref["frame"] == 0xFF404026).all()
+    if kind == "tir":      # some pixels of the tilted pane are totally reflecting (black: NaN), others refract
+        pane = ref["gbuffer"].tri_id < 2
+        black = (ref["frame"] & 0xFFFFFF) == 0
+        assert 0.05 < black[pane].mean() < 0.95
+    if kind == "lights":
+        assert len(sc.lights) == 12 and (ref["frame"] != 0xFF404026).mean() > 0.1

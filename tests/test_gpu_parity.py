@@ -658,3 +658,28 @@ def test_tex3d_clear_and_box_mip(dev):
     assert np.array_equal(l1.view(np.uint8).reshape(2, 4, 8, 4), exp.astype(np.uint8))
     assert dev.L.vct_tex3d_create(dev.h, 16, 8, 4, 9, ctypes.byref(ctypes.c_void_p())) == -1   # too many levels (glTexStorage3D rule)
     capi.check(dev.L.vct_tex3d_destroy(h))
+
+
+# --------------------------------------------------------------------------- corners of the path
+from edge_scenes import EDGE_KINDS, edge_scene  # noqa: E402
+
+
+@pytest.mark.parametrize("kind", EDGE_KINDS)
+def test_edge_case_scenes(kind):
+    """the 16-sample count wrap, geometry outside the cube, degenerate triangles and NaN normals, twelve lights (the shader clamps to ten)
+    on a tilted transmissive quad, a scene that produces nothing: the same scenes tests/test_glsl_ref.py runs through the reference's
+    own GLSL.  Voxels, mip volumes and visibility bit for bit, the frame inside the gate."""
+    sc = edge_scene(kind)
+    R, W, H = 32, 96, 64
+    view, proj = S.reference_camera(W / H, eye=(0.1, 0.2, 1.6))
+    ref = orc.render_frame(sc, view, proj, R, W, H, n_levels=6)
+    p = capi.Pipeline(sc, R, W, H, 6)
+    for sampler in SAMPLERS:
+        p.render_frame(view, proj, capi.default_params(sampler=sampler))
+        _check_frame(p.target.frame(), ref)
+    assert np.array_equal(p.grid.download(0), ref["base"])
+    assert_pyramid_equal(p.grid, ref["pyramid"])
+    assert np.array_equal(p.target.gbuffer()["tri_id"], ref["gbuffer"].tri_id)
+    gst, st = p.voxel_stats(), ref["voxel_stats"]
+    assert (gst.fragments, gst.occupied, gst.max_per_voxel) == (st.fragments, st.occupied, st.max_per_voxel)
+    p.close()

@@ -19,7 +19,6 @@ sys.path.insert(0, ROOT)
 import numpy as np  # noqa: E402
 
 from oracle import glsl_ref as G  # noqa: E402
-from oracle import orc  # noqa: E402
 from voxel_cone_tracing_b200 import scene as S  # noqa: E402
 
 OUT = os.path.join(ROOT, "tests", "golden", "glsl_ref_vectors.json")

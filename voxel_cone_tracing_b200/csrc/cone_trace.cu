@@ -252,6 +252,15 @@ __device__ __forceinline__ uint32_t trace_cone(const GridView& g, F3 origin, F3 
   const float margin = 0.5f / (float)(g.R >> (g.levels - 1));  // half a texel of the coarsest level
   float acc[4] = {0.f, 0.f, 0.f, 0.f};  // byte units
   float dist = 3.0f * voxel_size;
+  if (!(dir.x == dir.x && dir.y == dir.y && dir.z == dir.z)) {
+    // A direction that is not a number (normalize() of a zero vector: refract() under total reflection, a vertex normal of length zero).
+    // In the reference every weight |d| * textureLod(..) of the first sample is NaN, the accumulator turns NaN and `alpha < 1` ends the
+    // loop (voxel_cone_tracing.frag:98-116): the cone returns NaN whenever its loop runs at all, and the pixel ends up black.
+    const bool runs = dist < max_dist;
+#pragma unroll
+    for (int c = 0; c < 4; c++) out[c] = runs ? __int_as_float(0x7FC00000) : 0.0f;
+    return runs ? 1u : 0u;
+  }
   float diam = dist * aperture;
   F3 sp = f3(fmaf(dir.x, dist, origin.x), fmaf(dir.y, dist, origin.y), fmaf(dir.z, dist, origin.z));
   uint32_t iters = 0;
@@ -372,7 +381,7 @@ __device__ __forceinline__ void trace_cone_fast(const GridView& g, bool alive, F
       else t_exit = (o[k] <= -margin || o[k] >= 1.0f + margin) ? 0.0f : max_dist;
       end = fminf(end, t_exit + voxel_size);   // + one voxel: rounding slack, the extra samples are exactly zero
     }
-    if (!(d[0] == d[0] && d[1] == d[1] && d[2] == d[2]) || !alive) end = 0.0f;   // NaN direction (refract() of total reflection): every sample is zero
+    if (!(d[0] == d[0] && d[1] == d[1] && d[2] == d[2]) || !alive) end = 0.0f;   // NaN direction: no march, the result is set behind the loop
   }
   float acc[4] = {0.f, 0.f, 0.f, 0.f};  // byte units
   const F3 zo = f3((float)ix * (1.0f / 6.0f), (float)iy * (1.0f / 6.0f), (float)iz * (1.0f / 6.0f));   // where the cone's three directions start in the stacked array
@@ -420,6 +429,13 @@ __device__ __forceinline__ void trace_cone_fast(const GridView& g, bool alive, F
     for (int c = 0; c < 4; c++) acc[c] = fmaf(k, s[c], acc[c]);
     dist = dist + fmaxf(diam * 0.5f, voxel_size);
     diam = dist * aperture;
+  }
+  // A direction that is not a number (normalize() of a zero vector: refract() under total reflection, a vertex normal of length zero).
+  // In the reference every weight |d| * textureLod(..) of the first sample is NaN, the accumulator turns NaN and `alpha < 1` ends the
+  // loop (voxel_cone_tracing.frag:98-116): the cone returns NaN whenever its loop runs at all, and the pixel ends up black.
+  if (alive && !(dir.x == dir.x && dir.y == dir.y && dir.z == dir.z) && 3.0f * voxel_size < max_dist) {
+#pragma unroll
+    for (int c = 0; c < 4; c++) acc[c] = __int_as_float(0x7FC00000);
   }
 #pragma unroll
   for (int c = 0; c < 4; c++) out[c] = acc[c] * (1.0f / 255.0f);
