@@ -5,7 +5,7 @@ import numpy as np
 
 from voxel_cone_tracing_b200 import scene as S
 
-EDGE_KINDS = ["stack", "outside", "degenerate", "lights", "tir", "empty"]
+EDGE_KINDS = ["stack", "outside", "degenerate", "lights", "tir", "mirror", "nolight", "empty"]
 
 
 def _quad_mesh(z, half=0.2, copies=1):
@@ -41,6 +41,20 @@ def edge_scene(kind):
         b.add_mesh(_quad_mesh(0.0, half=0.7), S.mat_trs((0.0, 0.0, 0.0), 0.75, 1.0), material_override=b.add_material(m))
         b.add_mesh(_quad_mesh(-0.6, half=0.9), material_override=0)
         b.add_light((0.3, 0.4, 0.8))
+    elif kind == "mirror":         # general model matrices: mirrored (negative determinant), non-uniformly scaled, sheared and rotated about x
+        import os
+        mesh = S.load_vctmesh(os.path.join(S.ASSET_DIR, "suzanne.vctmesh"))
+        mid = b.add_material(m)
+        c, s_ = np.cos(0.5), np.sin(0.5)
+        rot_x = np.array([[1, 0, 0, 0], [0, c, -s_, 0], [0, s_, c, 0], [0, 0, 0, 1]], np.float64)
+        shear = np.array([[-0.45, 0.12, 0, 0.2], [0, 0.3, 0.05, -0.1], [0.07, 0, 0.5, 0.05], [0, 0, 0, 1]], np.float64)   # det < 0
+        model = (rot_x @ shear).astype(np.float32).T.reshape(16).copy()          # column-major like glm::mat4
+        b.add_mesh(mesh, model, material_override=mid)
+        m2 = S.default_material(); m2["diffuse"][:3] = (0.8, 0.7, 0.2); m2["specular"][:3] = (0.6, 0.6, 0.6); m2["shininess"] = 0.0
+        b.add_mesh(_quad_mesh(-0.5, half=0.8), S.mat_trs((0.0, 0.0, 0.0), -0.3, 1.1), material_override=b.add_material(m2))
+        b.add_light((0.4, 0.5, 0.9), (1.0, 0.9, 0.8), 1.5)
+    elif kind == "nolight":        # point_light_count = 0: no shadow cones, direct term = emission
+        b.add_mesh(_quad_mesh(0.0, half=0.5), S.mat_trs((0.0, 0.0, 0.0), 0.4, 1.0), material_override=b.add_material(m))
     elif kind == "empty":          # nothing inside the cube, nothing in front of the camera
         b.add_mesh(_quad_mesh(5.0, half=0.3), material_override=b.add_material(m))
         b.add_light((0.0, 0.0, 0.8))
