@@ -63,3 +63,52 @@ def edge_scene(kind):
 
 def mat_trs_tilt():
     return S.mat_trs((0.05, -0.1, 0.0), 0.6, 0.9)
+
+
+# --------------------------------------------------------------------------- seeded random scenes
+def fuzz_case(seed: int):
+    """A random small workload: triangle soups under random affine model matrices (some mirrored), random materials (opaque and
+    transmissive, ior below and above 1, shininess 0 .. 1000, emission above 1), vertices partly outside the cube, a few zero normals,
+    0 .. 12 lights inside and outside the cube, a random camera (often inside the geometry) and random phase toggles.
+    -> (scene, R, levels, W, H, camera kwargs, trace-parameter kwargs)"""
+    rng = np.random.default_rng(1000 + seed)
+    cube = float(rng.choice([0.75, 1.0, 2.0, 3.0]))
+    b = S.SceneBuilder(cube)
+    n_mats = int(rng.integers(1, 4))
+    for _ in range(n_mats):
+        m = S.default_material()
+        m["diffuse"][:3] = rng.random(3); m["specular"][:3] = rng.random(3) * rng.choice([0.0, 1.0]); m["transmittance"][:3] = rng.random(3)
+        m["emission"] = rng.random(3) * rng.choice([0.0, 0.3, 1.5])
+        m["shininess"] = float(rng.choice([0.0, 1.0, 10.0, 96.0, 1000.0])); m["ior"] = float(rng.choice([0.6, 1.0, 1.45, 5.0]))
+        m["dissolve"] = float(rng.choice([0.0, 0.05, 0.1, 0.5, 1.0])); m["illum"] = int(rng.choice([0, 2, 2, 4, 6, 7, 9]))
+        b.add_material(m)
+    for _ in range(int(rng.integers(1, 4))):
+        n_tri = int(rng.integers(8, 160))
+        centre = (rng.random((n_tri, 1, 3)) * 2.4 - 1.2) * cube
+        size = rng.choice([0.05, 0.2, 0.6], (n_tri, 1, 1)) * cube
+        pos = (centre + (rng.random((n_tri, 3, 3)) - 0.5) * size).reshape(-1, 3)
+        v = np.zeros(3 * n_tri, S.VERTEX)
+        v["pos"] = pos
+        nrm = rng.standard_normal((3 * n_tri, 3))
+        nrm[rng.random(3 * n_tri) < 0.02] = 0.0                      # a few normals of length zero (NaN after normalize)
+        v["norm"] = nrm
+        v["uv"] = rng.random((3 * n_tri, 2))
+        a = rng.standard_normal((3, 3)) * 0.35 + np.eye(3) * rng.choice([-1.0, 1.0]) * 0.8
+        model = np.eye(4); model[:3, :3] = a; model[:3, 3] = (rng.random(3) - 0.5) * 0.3 * cube
+        b.add_mesh(S.Mesh(v, np.arange(3 * n_tri, dtype="<u4"), [(0, 3 * n_tri, -1)], np.zeros(0, S.MATERIAL)),
+                   model.astype(np.float32).T.reshape(16).copy(), material_override=int(rng.integers(0, n_mats)))
+    for _ in range(int(rng.choice([0, 1, 1, 2, 3, 12]))):
+        b.add_light((rng.random(3) * 2.6 - 1.3) * cube, rng.random(3), float(rng.choice([0.5, 1.0, 2.0])))
+    R = int(rng.choice([32, 64]))
+    eye = (rng.random(3) * 2.0 - 1.0) * cube * 1.2
+    d = -eye / max(float(np.linalg.norm(eye)), 1e-3)                  # towards the middle of the cube, +- 20 degrees
+    cam = dict(eye=tuple(eye.tolist()), pitch=float(np.degrees(np.arcsin(np.clip(d[1], -1, 1))) + rng.uniform(-20, 20)),
+               yaw=float(np.degrees(np.arctan2(d[2], d[0])) + rng.uniform(-20, 20)))
+    prm = dict(enable_direct=int(rng.random() < 0.85), enable_diffuse=int(rng.random() < 0.85), enable_specular=int(rng.random() < 0.85),
+               enable_shadow=int(rng.random() < 0.8))
+    if rng.random() < 0.15:
+        prm.update(view_voxel_dir=int(rng.integers(0, 6)), view_voxel_lod=float(rng.choice([0.0, 0.5, 2.25, 9.0])))
+    return b.build(), R, (6 if R == 32 else 7), int(rng.choice([64, 96, 131])), int(rng.choice([48, 64, 77])), cam, prm
+
+
+FUZZ_SEEDS = list(range(24))

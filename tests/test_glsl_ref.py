@@ -302,3 +302,20 @@ def test_edge_cases_bit_exact(kind):
         assert 0.05 < black[pane].mean() < 0.95
     if kind == "lights":
         assert len(sc.lights) == 12 and (ref["frame"] != 0xFF404026).mean() > 0.1
+
+
+from edge_scenes import FUZZ_SEEDS, fuzz_case  # noqa: E402
+
+
+@pytest.mark.parametrize("seed", FUZZ_SEEDS)
+def test_random_scenes_bit_exact(seed):
+    """seeded random workloads (tests/edge_scenes.py::fuzz_case): oracle == the reference's GLSL in every output"""
+    sc, R, levels, W, H, cam, kw = fuzz_case(seed)
+    view, proj = S.reference_camera(W / H, **cam)
+    ref = orc.render_frame(sc, view, proj, R, W, H, orc.default_params(**kw), levels)
+    got = G.render_frame(sc, view, proj, R, W, H, orc.default_params(**kw), levels, mode="rules")
+    assert got["fragments"] == ref["voxel_stats"].fragments + ref["voxel_stats"].fragments_oob
+    assert np.array_equal(got["base"], ref["base"])
+    assert all(np.array_equal(got["pyramid"].levels[d][l], ref["pyramid"].levels[d][l]) for d in range(6) for l in range(1, levels))
+    assert np.array_equal(got["gbuffer"].tri_id, ref["gbuffer"].tri_id) and np.array_equal(got["gbuffer"].depth, ref["gbuffer"].depth)
+    assert np.array_equal(got["frame"], ref["frame"]), f"{(got['frame'] != ref['frame']).sum()} pixels differ"
