@@ -716,3 +716,19 @@ def test_random_scenes(seed):
     tex = p.target.frame()
     assert psnr(tex, ref["frame"]) >= 40.0 and (np.abs(tex.view(np.uint8).astype(np.int32) - ref["frame"].view(np.uint8).astype(np.int32)) > 2).mean() < 0.01
     p.close()
+
+
+@pytest.mark.parametrize("kind", ["degenerate", "tir", "lights"])
+def test_edge_case_scenes_large_frame(kind):
+    """the same corner cases at 1920x1080: frames of >= 32 k live tiles take the grouped path of the cone kernel (all diffuse cones of a
+    tile in one warp, their sum stored), where a NaN cone has to survive the summation"""
+    sc = edge_scene(kind)
+    R, W, H = 32, 1920, 1080
+    view, proj = S.reference_camera(W / H, eye=(0.05, 0.1, 0.9))
+    ref = orc.render_frame(sc, view, proj, R, W, H, n_levels=6)
+    assert ref["trace_stats"].shaded_pixels > 300_000
+    p = capi.Pipeline(sc, R, W, H, 6)
+    for sampler in SAMPLERS:
+        p.render_frame(view, proj, capi.default_params(sampler=sampler))
+        _check_frame(p.target.frame(), ref)
+    p.close()
