@@ -66,7 +66,7 @@ def mat_trs_tilt():
 
 
 # --------------------------------------------------------------------------- seeded random scenes
-def fuzz_case(seed: int):
+def fuzz_case(seed: int, big: bool = False):
     """A random small workload: triangle soups under random affine model matrices (some mirrored), random materials (opaque and
     transmissive, ior below and above 1, shininess 0 .. 1000, emission above 1), vertices partly outside the cube, a few zero normals,
     0 .. 12 lights inside and outside the cube, a random camera (often inside the geometry) and random phase toggles.
@@ -85,7 +85,7 @@ def fuzz_case(seed: int):
     for _ in range(int(rng.integers(1, 4))):
         n_tri = int(rng.integers(8, 160))
         centre = (rng.random((n_tri, 1, 3)) * 2.4 - 1.2) * cube
-        size = rng.choice([0.05, 0.2, 0.6], (n_tri, 1, 1)) * cube
+        size = rng.choice([0.6, 1.5, 2.5] if big else [0.05, 0.2, 0.6], (n_tri, 1, 1)) * cube   # big: dozens of fragments per voxel (count wrap)
         pos = (centre + (rng.random((n_tri, 3, 3)) - 0.5) * size).reshape(-1, 3)
         v = np.zeros(3 * n_tri, S.VERTEX)
         v["pos"] = pos
