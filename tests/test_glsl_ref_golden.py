@@ -86,3 +86,57 @@ def test_cones_and_frames(gold):
         if sha(frame) != fr["frame_sha256"]:   # (libm: powf / log2f / tanf) -- then within one 8-bit step, nearly everywhere equal
             d = np.abs(frame.view(np.uint8).astype(np.int32) - exp.view(np.uint8).astype(np.int32))
             assert d.max() <= 1 and (frame != exp).mean() < 0.01
+
+
+def test_translator_on_a_synthetic_shader():
+    """oracle/glsl_ref/glsl2cpp.py on a hand-written snippet (no reference tree needed): qualifiers and blocks become plain members,
+    arrays become glsl_array, literals get their suffix, non-constant global initialisers move into _init_globals(), defines are
+    undefined again -- and statements inside functions stay as they are"""
+    import importlib.util
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "glsl_ref", "glsl2cpp.py")
+    spec = importlib.util.spec_from_file_location("glsl2cpp", path)
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    src = """#version 450 core
+layout (local_size_x = 8) in;
+layout (std140, binding = 1) uniform material
+{
+  vec3 diffuse;
+  float shininess;
+};
+in VS_OUT
+{
+  vec4 world_position;
+} vs_out[];
+uniform layout (binding = 2, r32ui) uimage3D tex3D[6];
+uniform int cube_res;
+out vec4 final_color;
+float voxel_size = 1.0 / cube_res;
+#define HALF 0.5
+const ivec3 offs[] = ivec3[2]
+(
+  ivec3(1, 0, 0),
+  ivec3(0, 1, 0)
+);
+vec4[2] both(vec4 v)
+{
+  vec4 r[2];
+  r[0] = v * 0.25 + vec4(HALF);
+  r[1] = v / 2;
+  return r;
+}
+void main()
+{
+  final_color = both(vs_out[0].world_position)[1] * voxel_size;
+}
+"""
+    out = mod.translate(src, "synthetic.frag")
+    flat = " ".join(out.split())
+    assert "#version" not in out and "layout" not in out and "uniform" not in out
+    assert "vec3 diffuse;" in flat and "float shininess;" in flat and "material" not in flat          # block flattened
+    assert "struct VS_OUT { vec4 world_position; } vs_out[3];" in flat                                 # interface block, one triangle
+    assert "glsl_array<uimage3D, 6> tex3D;" in flat and "int cube_res;" in flat and "vec4 final_color;" in flat
+    assert "float voxel_size;" in flat and "void _init_globals() { voxel_size = 1.0f / cube_res; }" in flat
+    assert "const glsl_array<ivec3, 2> offs = glsl_array<ivec3, 2>{{ ivec3(1, 0, 0), ivec3(0, 1, 0) }};" in flat
+    assert "glsl_array<vec4, 2> both(vec4 v)" in flat and "glsl_array<vec4, 2> r;" in flat
+    assert "r[0] = v * 0.25f + vec4(HALF);" in flat and "r[1] = v / 2;" in flat                       # statements untouched but for the suffix
+    assert "#define HALF 0.5f" in out and out.rstrip().endswith("#undef HALF")
