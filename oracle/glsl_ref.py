@@ -45,6 +45,8 @@ def lib():
             f("rgba8_avg").restype = C.c_uint32
             f("rgba8_avg").argtypes = [C.c_uint32, orc.f32p]
             f("select_axis").argtypes = [orc.f32p, orc.f32p, orc.f32p]
+        L.glref_camera.argtypes = [orc.f32p, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, orc.f32p, orc.f32p]
+        L.glref_model_trs.argtypes = [orc.f32p, C.c_float, C.c_float, orc.f32p]
         _LIB = L
     return _LIB
 
@@ -132,3 +134,19 @@ def render_frame(scene, view, proj, R: int, W: int, H: int, params=None, n_level
     g = gbuffer(scene, view, proj, W, H, mode)
     frame = shade(scene, view, g, pyr, params, mode=mode)
     return dict(base=tex[0], pyramid=pyr, gbuffer=g, frame=frame, fragments=n_frag)
+
+
+def camera(eye, pitch_deg: float, yaw_deg: float, lens_angle: float, aspect: float, z_near: float, z_far: float):
+    """the reference's own Camera struct (src/camera.h, compiled where it lies): -> (view, projection), column-major"""
+    view, proj = np.zeros(16, np.float32), np.zeros(16, np.float32)
+    rc = lib().glref_camera(orc._fp(eye), pitch_deg, yaw_deg, lens_angle, aspect, z_near, z_far, view.ctypes.data_as(orc.f32p), proj.ctypes.data_as(orc.f32p))
+    assert rc == 0
+    return view, proj
+
+
+def model_trs(t, rot_y: float, scale: float) -> np.ndarray:
+    """glm::translate / rotate / scale as src/main.cpp:369-372 applies them (identity start), column-major"""
+    out = np.zeros(16, np.float32)
+    rc = lib().glref_model_trs(orc._fp(t), rot_y, scale, out.ctypes.data_as(orc.f32p))
+    assert rc == 0
+    return out

@@ -521,6 +521,34 @@ int glref_rules_tex_model(const orc_scene_t* sc, const float view[16], int W, in
 }
 #endif
 
+#if !GLREF_RULES
+/* ---- the reference's HOST-SIDE matrix code, to pin the product's camera / model-matrix helpers (scene.py, include/vct/math.h) ----
+ * Camera is the reference's own struct, compiled from src/camera.h where it lies (GLM only); the model matrix follows
+ * src/main.cpp:369-372 with the identity start the author intended (glm 0.9.9 leaves `glm::mat4 m;` uninitialised). */
+}  /* extern "C" */
+#include <glm/gtc/matrix_transform.hpp>
+#include "camera.h"
+extern "C" {
+int glref_camera(const float eye[3], float pitch_deg, float yaw_deg, float lens_angle, float aspect, float z_near, float z_far, float view[16],
+                 float proj[16]) {
+  Camera cam(glm::vec3(eye[0], eye[1], eye[2]), pitch_deg, yaw_deg);       /* main.cpp:107 */
+  cam.set_perspective(lens_angle, aspect, z_near, z_far);                     /* main.cpp:108: 45.0f, taken as radians by glm 0.9.9 */
+  const glm::mat4 v = cam.get_lookat(), p = cam.get_projection();             /* main.cpp:109 */
+  for (int c = 0; c < 4; c++)
+    for (int r = 0; r < 4; r++) { view[c * 4 + r] = v[c][r]; proj[c * 4 + r] = p[c][r]; }
+  return 0;
+}
+int glref_model_trs(const float t[3], float rot_y, float scale, float out[16]) {
+  glm::mat4 m(1.0f);
+  m = glm::translate(m, glm::vec3(t[0], t[1], t[2]));                         /* main.cpp:370 */
+  m = glm::rotate(m, rot_y, glm::vec3(0, 1, 0));                              /* main.cpp:371 */
+  m = glm::scale(m, glm::vec3(scale, scale, scale));                          /* main.cpp:372 */
+  for (int c = 0; c < 4; c++)
+    for (int r = 0; r < 4; r++) out[c * 4 + r] = m[c][r];
+  return 0;
+}
+#endif
+
 /* trace_cone() of voxel_cone_tracing.frag:88-119 on its own (float results, no 8-bit rounding in between) */
 int GLREF_FN(trace_cone)(const uint32_t* const* levels, int R, int n_levels, const float origin[3], const float dir[3], float aperture,
                          float max_dist, float out_rgba[4]) {

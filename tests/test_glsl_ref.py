@@ -321,3 +321,22 @@ def test_random_scenes_bit_exact(seed, big):
     assert all(np.array_equal(got["pyramid"].levels[d][l], ref["pyramid"].levels[d][l]) for d in range(6) for l in range(1, levels))
     assert np.array_equal(got["gbuffer"].tri_id, ref["gbuffer"].tri_id) and np.array_equal(got["gbuffer"].depth, ref["gbuffer"].depth)
     assert np.array_equal(got["frame"], ref["frame"]), f"{(got['frame'] != ref['frame']).sum()} pixels differ"
+
+
+# --------------------------------------------------------------------------- host-side matrices
+def test_camera_and_model_matrices_match_the_reference_host_code():
+    """the camera the benchmark uses (scene.reference_camera, restated in the oracle and in include/vct/math.h) against the reference's own
+    Camera struct (src/camera.h compiled where it lies: calc_front, glm::lookAt, glm::perspective with 45.0f taken as RADIANS) and the
+    Suzanne model matrix against glm::translate / rotate / scale as src/main.cpp:369-372 applies them"""
+    for aspect in (1.0, 1920 / 1080, 2560 / 1440):
+        v, p = S.reference_camera(aspect)
+        gv, gp = G.camera((0.0, 0.9, 3.0), 0.0, -90.0, 45.0, aspect, 0.1, 100.0)      # main.cpp:107-108
+        assert np.array_equal(v.view(np.uint32), gv.view(np.uint32)) and np.array_equal(p.view(np.uint32), gp.view(np.uint32))
+        assert np.array_equal(orc.perspective(45.0, aspect, 0.1, 100.0).view(np.uint32), gp.view(np.uint32))
+        assert abs(p[5] - 1.0 / np.tan(22.5)) < 1e-6                      # tan(22.5 rad) = 0.5579: an effective vertical field of view of 58.3 degrees
+    for cam in CAMERAS[1:]:
+        v, p = S.reference_camera(1.5, **cam)
+        gv, gp = G.camera(cam["eye"], cam["pitch"], cam["yaw"], 45.0, 1.5, 0.1, 100.0)
+        assert np.allclose(v, gv, rtol=0, atol=5e-7) and np.array_equal(p.view(np.uint32), gp.view(np.uint32))   # (libm vs numpy cos / sin: one ulp)
+    for theta in (0.0, 0.05, 0.3, 1.05, 2.9, -0.7):
+        assert np.allclose(S.mat_trs((0.0, 1.1, -0.5), theta, 0.3), G.model_trs((0.0, 1.1, -0.5), theta, 0.3), rtol=0, atol=1e-7)
