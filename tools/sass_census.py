@@ -79,7 +79,7 @@ def main():
     print("voxelizer's list push / counters, the G-buffer's 64-bit `atomicMin`, the work queues.  No tensor-core or TMA instruction is")
     print("expected on this path (nothing is a contraction; the mip ring moved from TMA to per-warp cp.async in round 2).")
     print("Template arguments: `cone_kernel_fast|grid<TEX sampler, SPLIT (one- / two-level fetches split), MIN_CTAS per SM, GROUP (all diffuse")
-    print("cones of a tile in one warp)>` -- `<1, 1, 10, 0>` is the kernel of the benchmarked config 2, `<1, 1, 10, 1>` the one of the 4K / 8K frames;")
+    print("cones of a tile in one warp)>` -- `<1, 1, 10, 1>` is the kernel of the benchmarked config 2 and of the 4K / 8K frames, `<1, 1, 10, 0>` the one of frames with fewer than 32768 tiles per rank (config 1, N >= 4);")
     print("`cone_kernel<COUNT, TEX, F16>` = the literal march (sample counters, RGBA16F variant); `cam_setup_kernel<SPLIT>` / `cam_resolve_kernel<LEAN>`:")
     print("frame shared between ranks / register-capped resolve.\n")
     hdr = ["kernel", "regs", "stack B", "smem B", "SASS"] + [c for c, _ in CLASSES]
