@@ -75,121 +75,294 @@ def default_material() -> np.ndarray:
     return m
 
 
+# --- tinyobjloader v1.1.0's token grammar (thirdparty/tinyobjloader/tiny_obj_loader.h), restated -------------------------------
+# The reference's models are whatever that loader makes of the file (src/renderer.cpp:417), including what it makes of
+# malformed numbers and of statements in unusual order; tests/test_obj_reader_fuzz.py holds this reader and the C++ one
+# (host/obj_loader.cpp) against the loader itself on random files.
+_POW_LUT = (1.0, 0.1, 0.01, 0.001, 0.0001, 0.00001, 0.000001, 0.0000001)
+
+
+def _isdigit(c: str) -> bool:
+    return "0" <= c <= "9"
+
+
+def _try_parse_double(s: str):
+    """tryParseDouble (tiny_obj_loader.h:498-605): [sign] digits ['.' digits] [(e|E) [sign] digits], greedy, value of
+    the conforming prefix; None where the loader reports failure (no leading digit, empty exponent).  The arithmetic is
+    the loader's own (decimal digits added through a table of powers, 10^e as ldexp(m * 5^e, e)), not strtod's."""
+    n = len(s)
+    if n == 0:
+        return None
+    i, sign = 0, 1.0
+    if s[0] in "+-":
+        sign = -1.0 if s[0] == "-" else 1.0
+        i = 1
+    elif not _isdigit(s[0]):
+        return None
+    mant, read = 0.0, 0
+    while i < n and _isdigit(s[i]):
+        mant = mant * 10.0 + (ord(s[i]) - 48)
+        i += 1
+        read += 1
+    if read == 0:
+        return None
+    exponent = 0
+    if i < n and s[i] == ".":
+        i += 1
+        read = 1
+        while i < n and _isdigit(s[i]):
+            mant += (ord(s[i]) - 48) * (_POW_LUT[read] if read < 8 else math.pow(10.0, -read))
+            read += 1
+            i += 1
+    if i < n and s[i] in "eE":
+        i += 1
+        esign = 1
+        if i < n and s[i] in "+-":
+            esign = -1 if s[i] == "-" else 1
+            i += 1
+        elif not (i < n and _isdigit(s[i])):
+            return None
+        read = 0
+        while i < n and _isdigit(s[i]):
+            exponent = exponent * 10 + (ord(s[i]) - 48)
+            i += 1
+            read += 1
+        exponent *= esign
+        if read == 0:
+            return None
+    if exponent:
+        try:
+            mant = math.ldexp(mant * math.pow(5.0, exponent), exponent)
+        except OverflowError:
+            mant = math.inf
+    return sign * mant
+
+
+def _skip_ws(line: str, pos: int) -> int:
+    while pos < len(line) and line[pos] in " \t":
+        pos += 1
+    return pos
+
+
+def _parse_real(line: str, pos: int, default: float = 0.0):
+    """parseReal (:612-621): next blank-separated token as a float (double rounded once), `default` where it does not parse."""
+    pos = _skip_ws(line, pos)
+    end = pos
+    while end < len(line) and line[end] not in " \t\r":
+        end += 1
+    val = _try_parse_double(line[pos:end])
+    with np.errstate(over="ignore"):
+        return np.float32(default if val is None else val), end
+
+
+def _reals(line: str, pos: int, n: int):
+    out = []
+    for _ in range(n):
+        v, pos = _parse_real(line, pos)
+        out.append(v)
+    return tuple(out)
+
+
+def _atoi(line: str, pos: int) -> int:
+    n = len(line)
+    while pos < n and line[pos] in " \t\n\v\f\r":
+        pos += 1
+    sign = 1
+    if pos < n and line[pos] in "+-":
+        sign = -1 if line[pos] == "-" else 1
+        pos += 1
+    v = 0
+    while pos < n and _isdigit(line[pos]):
+        v = v * 10 + (ord(line[pos]) - 48)
+        pos += 1
+    return sign * v
+
+
+def _split_lines(blob: bytes):
+    """safeGetline: \n, \r\n and a lone \r all end a line."""
+    return blob.decode("latin-1").replace("\r\n", "\n").replace("\r", "\n").split("\n")
+
+
+def _is_stmt(tok: str, key: str) -> bool:
+    return tok.startswith(key) and len(tok) > len(key) and tok[len(key)] in " \t"
+
+
 def parse_mtl(path: str):
-    """MTL subset used by the reference's create_material (src/renderer.cpp:49-81)."""
+    """LoadMtl (tiny_obj_loader.h:1049-1431) for the constants create_material forwards (src/renderer.cpp:49-81):
+    (materials, names).  A material's name is the rest of its `newmtl` line; statements in front of the first `newmtl`
+    belong to a nameless material that is dropped, a file without any `newmtl` yields that one nameless material."""
     mats, names = [], []
-    cur = None
+    cur, name = default_material(), ""
     has_d = False
-    with open(path, "r", errors="replace") as f:
-        for raw in f:
-            line = raw.split("#", 1)[0].strip()
-            if not line:
-                continue
-            tok = line.split()
-            key, args = tok[0], tok[1:]
-            if key == "newmtl":
-                if cur is not None:
-                    mats.append(cur)
-                cur = default_material()
-                names.append(args[0] if args else "")
-                has_d = False
-                continue
-            if cur is None:
-                continue
-            f3 = lambda: [float(a) for a in (args + ["0", "0", "0"])[:3]]
-            if key == "Ka": cur["ambient"][:3] = f3()
-            elif key == "Kd": cur["diffuse"][:3] = f3()
-            elif key == "Ks": cur["specular"][:3] = f3()
-            elif key in ("Kt", "Tf"): cur["transmittance"][:3] = f3()
-            elif key == "Ke": cur["emission"][:3] = f3()
-            elif key == "Ni": cur["ior"] = float(args[0])
-            elif key == "Ns": cur["shininess"] = float(args[0])
-            elif key == "illum": cur["illum"] = int(float(args[0]))
-            elif key == "d":
-                cur["dissolve"] = float(args[0]); has_d = True
-            elif key == "Tr":
-                if not has_d:                      # `d` wins over `Tr` (tiny_obj_loader.h:1203-1222)
-                    cur["dissolve"] = 1.0 - float(args[0])
-            elif key == "Pr": cur["roughness"] = float(args[0])
-            elif key == "Pm": cur["metallic"] = float(args[0])
-            elif key == "Ps": cur["sheen"] = float(args[0])
-            elif key == "Pc": cur["clearcoat_thickness"] = float(args[0])
-            elif key == "Pcr": cur["clearcoat_roughness"] = float(args[0])
-            elif key == "aniso": cur["anisotropy"] = float(args[0])
-            elif key == "anisor": cur["anisotropy_rotation"] = float(args[0])
-    if cur is not None:
-        mats.append(cur)
-    arr = np.array(mats, MATERIAL) if mats else np.zeros(0, MATERIAL)
-    return arr, names
+    with open(path, "rb") as f:
+        lines = _split_lines(f.read())
+    for raw in lines:
+        tok = raw.rstrip(" \t").lstrip(" \t")
+        if not tok or tok[0] == "#":
+            continue
+        if _is_stmt(tok, "newmtl"):
+            if name:
+                mats.append(cur); names.append(name)
+            cur, name, has_d = default_material(), tok[7:], False
+            continue
+        three = None
+        for key, fld in (("Ka", "ambient"), ("Kd", "diffuse"), ("Ks", "specular"), ("Kt", "transmittance"), ("Tf", "transmittance"), ("Ke", "emission")):
+            if _is_stmt(tok, key):
+                three = fld
+                break
+        if three:
+            cur[three][:3] = _reals(tok, 2, 3)
+            continue
+        one = None
+        for key, fld in (("Ni", "ior"), ("Ns", "shininess"), ("Pr", "roughness"), ("Pm", "metallic"), ("Ps", "sheen"), ("Pc", "clearcoat_thickness"),
+                         ("Pcr", "clearcoat_roughness"), ("aniso", "anisotropy"), ("anisor", "anisotropy_rotation")):
+            if _is_stmt(tok, key):
+                one = (fld, len(key))
+                break
+        if one:
+            cur[one[0]] = _parse_real(tok, one[1])[0]
+        elif _is_stmt(tok, "illum"):
+            cur["illum"] = _atoi(tok, 6)                         # parseInt = atoi
+        elif _is_stmt(tok, "d"):
+            cur["dissolve"] = _parse_real(tok, 1)[0]
+            has_d = True
+        elif _is_stmt(tok, "Tr"):
+            if not has_d:                          # `d` wins over `Tr` (:1203-1222); the subtraction is in float
+                cur["dissolve"] = np.float32(1.0) - _parse_real(tok, 2)[0]
+    mats.append(cur); names.append(name)           # the last material is flushed whatever its name (:1426-1428)
+    return np.array(mats, MATERIAL), names
+
+
+class ObjError(ValueError):
+    """tinyobj::LoadObj returned false (Renderer::load_model prints "Error loading file" and returns INVALID_ID)."""
 
 
 def load_obj(path: str) -> Mesh:
-    """OBJ -> deduplicated vertex/index buffers + per-material ranges, following
-    Renderer::load_model (src/renderer.cpp:407-603): faces fan-triangulated, one vertex per
-    distinct (pos, normal, uv) triple in first-use order, a new range whenever the material
-    changes inside a shape or a new group/object starts."""
+    """OBJ -> deduplicated vertex/index buffers + per-material ranges.
+
+    Parsing restates tinyobj::LoadObj with triangulate = true (tiny_obj_loader.h:1525-1790) as a state machine of its own:
+    faces collect in a pending group; `usemtl` with a different material moves the group into the current shape (tagged
+    with the material that was current), `g` and `o` do the same and then close the shape -- `g` keeps it if it has
+    triangles, `o` keeps it only if the pending group was not empty (so `usemtl` directly in front of an `o` loses the
+    shape: the loader's behaviour, reproduced) -- and the end of the file keeps whatever is left.  Polygons become fans.
+    Flattening follows Renderer::load_model (src/renderer.cpp:407-557): one vertex per distinct (pos, normal, uv) triple
+    in first-use order, one range per shape and per run of one material inside it (material -1 = none)."""
     pos, nrm, tex = [], [], []
-    mats = np.zeros(0, MATERIAL)
-    names: list = []
-    cur_mat = -1
-    verts, index, uniq = [], [], {}
-    ranges = []
-    start = 0
-    range_mat = None
-    base = os.path.dirname(path)
+    mats_list, names = [], []
+    mat_map = {}
+    material = -1
+    group, shape, shapes = [], [], []
+    base = path[: max(path.rfind("/"), path.rfind("\\")) + 1]     # renderer.cpp:413-414
 
-    def close_range():
-        nonlocal start, range_mat
+    def export() -> bool:
+        if not group:
+            return False
+        for face in group:
+            for k in range(2, len(face)):
+                shape.append((face[0], face[k - 1], face[k], material))
+        return True
+
+    with open(path, "rb") as f:
+        lines = _split_lines(f.read())
+    for raw in lines:
+        tok = raw.lstrip(" \t")
+        if not tok or tok[0] == "#":
+            continue
+        if _is_stmt(tok, "v"):
+            pos.append(_reals(tok, 2, 3))
+        elif _is_stmt(tok, "vn"):
+            nrm.append(_reals(tok, 3, 3))
+        elif _is_stmt(tok, "vt"):
+            tex.append(_reals(tok, 3, 2))
+        elif _is_stmt(tok, "f"):
+            p, n, face = _skip_ws(tok, 2), len(tok), []
+
+            def fix(idx: int, count: int):
+                if idx == 0:
+                    raise ObjError(f"{path}: zero index in `f` line")
+                return idx - 1 if idx > 0 else count + idx
+
+            def skip_index(q: int) -> int:
+                while q < n and tok[q] not in "/ \t\r":
+                    q += 1
+                return q
+
+            while p < n:                                           # parseTriple (:745-799): i, i/j, i//k, i/j/k
+                vi, ti, ni = fix(_atoi(tok, p), len(pos)), None, None
+                p = skip_index(p)
+                if p < n and tok[p] == "/":
+                    p += 1
+                    if p < n and tok[p] == "/":
+                        p += 1
+                        ni = fix(_atoi(tok, p), len(nrm))
+                        p = skip_index(p)
+                    else:
+                        ti = fix(_atoi(tok, p), len(tex))
+                        p = skip_index(p)
+                        if p < n and tok[p] == "/":
+                            p += 1
+                            ni = fix(_atoi(tok, p), len(nrm))
+                            p = skip_index(p)
+                # a relative normal / texcoord index that points in front of the array counts as "none" (load_model tests >= 0,
+                # renderer.cpp:489,499); anything else out of range is undefined behaviour in the reference: refused here
+                ti = None if ti is not None and ti < 0 else ti
+                ni = None if ni is not None and ni < 0 else ni
+                if not (0 <= vi < len(pos)) or (ti is not None and ti >= len(tex)) or (ni is not None and ni >= len(nrm)):
+                    raise ObjError(f"{path}: `f` line refers to an element that does not exist")
+                face.append((vi, ti, ni))
+                p = _skip_ws(tok, p)
+            group.append(face)
+        elif _is_stmt(tok, "usemtl"):
+            new = mat_map.get(tok[7:], -1)
+            if new != material:
+                export()
+                group = []
+                material = new
+        elif _is_stmt(tok, "mtllib"):
+            for name in tok[7:].split(" "):
+                try:
+                    m, nm = parse_mtl(base + name)
+                except OSError:
+                    continue                                       # "WARN: Material file not found", the load goes on
+                for mm, nn in zip(m, nm):
+                    mat_map.setdefault(nn, len(mats_list))
+                    mats_list.append(mm); names.append(nn)
+                break
+        elif _is_stmt(tok, "g"):
+            export()
+            if shape:
+                shapes.append(shape)
+            shape, group = [], []
+        elif _is_stmt(tok, "o"):
+            if export():
+                shapes.append(shape)
+            shape, group = [], []
+    if export() or shape:
+        shapes.append(shape)
+
+    verts, index, uniq, ranges = [], [], {}, []
+    zero2, zero3 = (np.float32(0),) * 2, (np.float32(0),) * 3
+    for sh in shapes:
+        start, run_mat = len(index), None
+        for (c0, c1, c2, m) in sh:
+            if run_mat is not None and m != run_mat:
+                ranges.append((start, len(index) - start, run_mat))
+                start = len(index)
+            run_mat = m
+            for (vi, ti, ni) in (c0, c1, c2):
+                keyv = (pos[vi], nrm[ni] if ni is not None else zero3, tex[ti] if ti is not None else zero2)
+                j = uniq.get(keyv)                                 # -0.0 == 0.0 here as in vert_data_t::operator== (renderer.cpp:31-34); first-seen bits kept
+                if j is None:
+                    j = len(verts); uniq[keyv] = j; verts.append(keyv)
+                index.append(j)
         if len(index) > start:
-            ranges.append((start, len(index) - start, range_mat if range_mat is not None else -1))
-        start = len(index)
-        range_mat = None
-
-    with open(path, "r", errors="replace") as f:
-        for raw in f:
-            line = raw.split("#", 1)[0].strip()
-            if not line:
-                continue
-            tok = line.split()
-            key, args = tok[0], tok[1:]
-            if key == "v": pos.append(tuple(np.float32(a) for a in args[:3]))
-            elif key == "vn": nrm.append(tuple(np.float32(a) for a in args[:3]))
-            elif key == "vt": tex.append(tuple(np.float32(a) for a in (args + ["0"])[:2]))
-            elif key == "mtllib":
-                mats, names = parse_mtl(os.path.join(base, args[0]))
-            elif key == "usemtl":
-                cur_mat = names.index(args[0]) if args and args[0] in names else -1
-            elif key in ("g", "o"):
-                close_range()
-            elif key == "f":
-                corners = []
-                for a in args:
-                    parts = (a.split("/") + ["", ""])[:3]
-                    vi = int(parts[0]); vi = vi - 1 if vi > 0 else len(pos) + vi
-                    ti = None
-                    if parts[1]:
-                        ti = int(parts[1]); ti = ti - 1 if ti > 0 else len(tex) + ti
-                    ni = None
-                    if parts[2]:
-                        ni = int(parts[2]); ni = ni - 1 if ni > 0 else len(nrm) + ni
-                    corners.append((vi, ti, ni))
-                if range_mat is not None and range_mat != cur_mat:
-                    close_range()
-                range_mat = cur_mat
-                for k in range(1, len(corners) - 1):
-                    for c in (corners[0], corners[k], corners[k + 1]):
-                        p = pos[c[0]]
-                        t = tex[c[1]] if c[1] is not None else (np.float32(0), np.float32(0))
-                        n = nrm[c[2]] if c[2] is not None else (np.float32(0),) * 3
-                        keyv = (p, n, t)
-                        j = uniq.get(keyv)
-                        if j is None:
-                            j = len(verts); uniq[keyv] = j; verts.append(keyv)
-                        index.append(j)
-    close_range()
+            ranges.append((start, len(index) - start, run_mat))
+    if not index:
+        raise ObjError(f"{path}: no triangles")
     varr = np.zeros(len(verts), VERTEX)
     for i, (p, n, t) in enumerate(verts):
         varr[i]["pos"] = p; varr[i]["norm"] = n; varr[i]["uv"] = t
+    mats = np.array(mats_list, MATERIAL) if mats_list else np.zeros(0, MATERIAL)
     return Mesh(varr, np.array(index, "<u4"), ranges, mats, names)
 
 
