@@ -1,0 +1,101 @@
+"""The reference's visualisation pass on a real OpenGL implementation (TEST INFRASTRUCTURE ONLY).
+
+oracle/_ref/gl/vct_gl_ref (oracle/gl_ref/gl_harness.c) compiles the reference's UNMODIFIED shader/voxel_cone_tracing.vert|frag
+with Mesa 18.1 llvmpipe -- the software GL that ships inside Nsight Compute, loaded behind a stand-in libX11 -- and replays
+Renderer::visualize (src/renderer.cpp:355-390) with the GL state of the reference.  llvmpipe 18.1 cannot run the voxelization
+and mip passes (no image load/store, no compute), so the six voxel textures are filled with a given grid + mip chain.
+
+What this pins: the fixed-function half the CPU restatements only write down as rules -- where a triangle's fragments fall,
+clipping, perspective-correct interpolation, the depth test, textureLod's filtering, blending and the unorm conversion -- plus
+the fragment shader as a GL compiler executes it, for the visualisation pass.  PARITY of the voxelization pass's raster /
+fragment order stays unpinned.
+
+    frame_u8, frame_f32 = gl_ref.visualize(scene, view, proj, pyramid, W, H, params)
+"""
+from __future__ import annotations
+
+import os
+import struct
+import subprocess
+import tempfile
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+BINARY = os.path.join(_HERE, "_ref", "gl", "vct_gl_ref")
+MESA_LIBGL = os.environ.get("VCT_MESA_LIBGL", "/opt/nvidia/nsight-compute/2025.2.1/host/linux-desktop-glibc_2_11_3-x64/Mesa/libGL.so.1")
+SHADER_DIR = os.environ.get("VCT_REFERENCE_SHADERS", "/root/reference/shader")
+
+
+# Mesa 18.1's llvmpipe advertises GL 3.3: indexing a sampler array with a value that is not a constant is undefined there, and this
+# build samples tex3D[0] whatever the index (measured: the voxel debug view shows texture 0 for every view_voxel_dir).  The
+# reference's fragment shader does it three times (voxel_cone_tracing.frag:83-85,255), so for THIS driver the text gets one
+# syntactic change: `textureLod(tex3D[i], p, lod)` becomes a call of a six-way select over constant indices.  Nothing else is touched.
+_SELECT = """
+vec4 vct_tex3D_select(int i, vec3 p, float lod)
+{
+  if (i == 0) return textureLod(tex3D[0], p, lod);
+  if (i == 1) return textureLod(tex3D[1], p, lod);
+  if (i == 2) return textureLod(tex3D[2], p, lod);
+  if (i == 3) return textureLod(tex3D[3], p, lod);
+  if (i == 4) return textureLod(tex3D[4], p, lod);
+  return textureLod(tex3D[5], p, lod);
+}
+"""
+
+
+def shader_dir_for_driver(tmp: str, expand_sampler_index: bool = True) -> str:
+    """Copies the two shaders into `tmp`, the fragment shader with its dynamic sampler indices expanded (see above)."""
+    import re
+    for name in ("voxel_cone_tracing.vert", "voxel_cone_tracing.frag"):
+        text = open(os.path.join(SHADER_DIR, name)).read()
+        if name.endswith(".frag") and expand_sampler_index:
+            decl = "uniform sampler3D tex3D[6];"
+            assert text.count(decl) == 1
+            text, n = re.subn(r"textureLod\(tex3D\[([^\]]+)\]\s*,", r"vct_tex3D_select(int(\1),", text)
+            assert n == 4, n
+            text = text.replace(decl, decl + "\n" + _SELECT)
+        with open(os.path.join(tmp, name), "w") as f:
+            f.write(text)
+    return tmp
+
+
+def available() -> bool:
+    return os.path.exists(BINARY) and os.path.exists(MESA_LIBGL) and os.path.exists(os.path.join(SHADER_DIR, "voxel_cone_tracing.frag"))
+
+
+def visualize(scene, view, proj, pyramid, W: int, H: int, params=None, threads: int | None = None, expand_sampler_index: bool = True):
+    """(RGBA8 frame as uint32[H, W], RGBA32F frame as float32[H, W, 4]); row 0 = bottom, like glReadPixels and the library's frame."""
+    from . import orc
+    params = params or orc.default_params()
+    R, levels = pyramid.R, pyramid.n_levels
+    with tempfile.TemporaryDirectory() as d:
+        job, out = os.path.join(d, "job.bin"), os.path.join(d, "out.bin")
+        with open(job, "wb") as f:
+            f.write(b"VCTGLJOB")
+            f.write(struct.pack("<9I", W, H, R, levels, len(scene.verts), len(scene.indices), len(scene.draws), len(scene.materials), len(scene.lights)))
+            f.write(struct.pack("<5i", params.enable_direct, params.enable_diffuse, params.enable_specular, params.enable_shadow, params.view_voxel_dir))
+            f.write(struct.pack("<2f", params.view_voxel_lod, scene.cube_size))
+            f.write(np.asarray(view, "<f4").reshape(16).tobytes())
+            f.write(np.asarray(proj, "<f4").reshape(16).tobytes())
+            f.write(np.ascontiguousarray(scene.lights).tobytes())
+            f.write(np.ascontiguousarray(scene.materials).tobytes())
+            f.write(np.ascontiguousarray(scene.draws).tobytes())
+            f.write(np.ascontiguousarray(scene.verts).tobytes())
+            f.write(np.ascontiguousarray(scene.indices, "<u4").tobytes())
+            f.write(np.ascontiguousarray(pyramid.base, "<u4").tobytes())
+            for dirn in range(6):
+                for l in range(1, levels):
+                    f.write(np.ascontiguousarray(pyramid.levels[dirn][l], "<u4").tobytes())
+        env = dict(os.environ, VCT_MESA_LIBGL=MESA_LIBGL)
+        if threads is not None:
+            env["LP_NUM_THREADS"] = str(threads)
+        r = subprocess.run([BINARY, shader_dir_for_driver(d, expand_sampler_index), job, out], capture_output=True, text=True, env=env)
+        if r.returncode:
+            raise RuntimeError(f"vct_gl_ref failed ({r.returncode}): {r.stderr[-2000:]}")
+        blob = open(out, "rb").read()
+    n = W * H
+    u8 = np.frombuffer(blob, "<u4", n, 0).reshape(H, W).copy()
+    f32 = np.frombuffer(blob, "<f4", n * 4, n * 4).reshape(H, W, 4).copy()
+    visualize.last_log = r.stderr
+    return u8, f32

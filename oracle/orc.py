@@ -88,6 +88,7 @@ def lib():
         L.orc_trace.argtypes = [C.POINTER(SceneT), f32p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_void_p, C.c_int, C.c_int,
                                 C.POINTER(TraceParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(TraceStats)]
         L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_debug_set_lod_filter.argtypes = [C.c_int]
         _LIB = L
     return _LIB
 
@@ -217,3 +218,8 @@ def num_threads() -> int:
 def set_num_threads(n: int) -> None:
     """OpenMP threads of the oracle (torchrun exports OMP_NUM_THREADS=1 to its ranks: bench.py's CPU legs ask for all the cores)"""
     lib().orc_set_num_threads(int(n))
+
+
+def debug_set_lod_filter(mode: int) -> None:
+    """TEST SWITCH: 0 = rule R7, 1 = Mesa llvmpipe's brilinear mip filter (tests/test_gl_llvmpipe.py restores 0)."""
+    lib().orc_debug_set_lod_filter(int(mode))

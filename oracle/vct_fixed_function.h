@@ -164,6 +164,14 @@ inline void load_texel(const uint32_t* tex, size_t idx, int fmt, float c[4]) {
   else unpack_unorm(tex[idx], c);
 }
 
+/* TEST SWITCH (tests/test_gl_llvmpipe.py only; 0 everywhere else): 1 = the mip filter of Mesa llvmpipe, the one OpenGL implementation this
+ * image has.  llvmpipe does not blend two levels linearly in the LOD fraction as the GL specification writes it (rule R7) but "brilinearly"
+ * (gallivm lp_bld_sample.c, lp_build_brilinear_lod with BRILINEAR_FACTOR 2): lod + 0.25 is split into level and fraction phi, the weight of
+ * the coarser level is 2 phi - 1, and a weight <= 0 means the finer level alone -- i.e. one level for fractions below 0.25 and above 0.75, a
+ * ramp of twice the slope between.  With the switch on, the oracle can be compared with the reference's shaders RUNNING on llvmpipe without
+ * the driver's shortcut drowning everything else. */
+inline int& lod_filter_mode() { static int mode = 0; return mode; }
+
 inline void texture_lod(const Pyramid& p, int dir, V3 s, float lod, float out[4]) {
   float maxl = (float)(p.n_levels - 1);
   float l = fminf(fmaxf(lod, 0.0f), maxl);
@@ -171,6 +179,14 @@ inline void texture_lod(const Pyramid& p, int dir, V3 s, float lod, float out[4]
   int l0 = (int)floorf(l);
   int l1 = l0 + 1 < p.n_levels ? l0 + 1 : p.n_levels - 1;
   float f = l - (float)l0;
+  if (lod_filter_mode() == 1) {
+    float lb = l + 0.25f;
+    l0 = (int)floorf(lb);
+    f = (lb - (float)l0) * 2.0f + -1.0f;
+    if (l0 >= p.n_levels - 1) { l0 = p.n_levels - 1; f = 0.0f; }
+    if (f <= 0.0f) f = 0.0f;
+    l1 = l0 + 1 < p.n_levels ? l0 + 1 : p.n_levels - 1;
+  }
   float t0[4], t1[4];
   trilinear(p.levels[dir * p.n_levels + l0], p.size(l0), s, t0, p.fmt);
   trilinear(p.levels[dir * p.n_levels + l1], p.size(l1), s, t1, p.fmt);

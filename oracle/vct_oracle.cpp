@@ -685,6 +685,7 @@ int orc_num_threads(void) {
   return 1;
 #endif
 }
+void orc_debug_set_lod_filter(int mode) { vct_ff::lod_filter_mode() = mode; }
 void orc_set_num_threads(int n) {
 #ifdef _OPENMP
   if (n > 0) omp_set_num_threads(n);

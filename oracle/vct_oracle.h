@@ -126,6 +126,9 @@ int orc_trace(const orc_scene_t* scene, const float view[16], int W, int H,
 
 int orc_num_threads(void);
 void orc_set_num_threads(int n);
+/* TEST SWITCH: 0 = rule R7 (default), 1 = Mesa llvmpipe's brilinear mip filter (vct_fixed_function.h lod_filter_mode); used only by
+ * tests/test_gl_llvmpipe.py to compare the oracle with the reference's shaders running on that driver. */
+void orc_debug_set_lod_filter(int mode);
 
 #ifdef __cplusplus
 }
