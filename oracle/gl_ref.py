@@ -60,6 +60,62 @@ def shader_dir_for_driver(tmp: str, expand_sampler_index: bool = True) -> str:
     return tmp
 
 
+def voxelize_shader_dir_for_driver(tmp: str) -> str:
+    """voxelize.vert and voxelize.geom unmodified; voxelize.frag with its image store turned into colour outputs.  llvmpipe 18.1 has no
+    image load/store (GL 4.2), so the fragment shader cannot run as written; what it computes up to the store -- the voxel coordinate and
+    the colour handed to imageAtomicRGBA8Avg (voxelize.frag:122-161) -- is kept character for character and written to two render targets
+    instead.  The compare-and-swap loop itself (voxelize.frag:95-120) is pinned elsewhere (oracle/glsl_ref: the reference's text compiled
+    for the CPU)."""
+    for name in ("voxelize.vert", "voxelize.geom"):
+        with open(os.path.join(tmp, name), "w") as f:
+            f.write(open(os.path.join(SHADER_DIR, name)).read())
+    text = open(os.path.join(SHADER_DIR, "voxelize.frag")).read()
+
+    def once(old, new):
+        nonlocal text
+        assert text.count(old) == 1, old
+        text = text.replace(old, new)
+
+    once("uniform layout (binding = 2, r32ui) uimage3D tex3D[6];",
+         "uniform int vct_grid_res;\nlayout (location = 0) out vec4 vct_voxel;\nlayout (location = 1) out vec4 vct_color;")
+    a, b = text.index("void imageAtomicRGBA8Avg("), text.index("void main()")
+    text = text[:a] + text[b:]                                                    # the CAS loop needs image atomics
+    once("ivec3 dim = imageSize(tex3D[0]);", "ivec3 dim = ivec3(vct_grid_res);")
+    once("  for (int i = 0; i < 6; i++)\n    imageAtomicRGBA8Avg(tex3D[i], voxel_pos, final_color);",
+         "  vct_voxel = vec4(voxel_pos, 1.0);\n  vct_color = final_color;")
+    with open(os.path.join(tmp, "voxelize.frag"), "w") as f:
+        f.write(text)
+    return tmp
+
+
+def voxelize_fragments(scene, R: int):
+    """The fragments of Renderer::voxelize on llvmpipe, in draw / triangle / row / column order:
+    (triangle sequence u32[n], pixel xy u32[n, 2], voxel coordinate f32[n, 3], colour f32[n, 4])."""
+    with tempfile.TemporaryDirectory() as d:
+        job, out = os.path.join(d, "job.bin"), os.path.join(d, "out.bin")
+        with open(job, "wb") as f:
+            f.write(b"VCTGLJOB")
+            f.write(struct.pack("<9I", 2 * R, 2 * R, R, 0, len(scene.verts), len(scene.indices), len(scene.draws), len(scene.materials), len(scene.lights)))
+            f.write(struct.pack("<5i", 1, 1, 1, 1, 7))
+            f.write(struct.pack("<2f", 0.0, scene.cube_size))
+            f.write(np.eye(4, dtype="<f4").tobytes())
+            f.write(np.eye(4, dtype="<f4").tobytes())
+            f.write(np.ascontiguousarray(scene.lights).tobytes())
+            f.write(np.ascontiguousarray(scene.materials).tobytes())
+            f.write(np.ascontiguousarray(scene.draws).tobytes())
+            f.write(np.ascontiguousarray(scene.verts).tobytes())
+            f.write(np.ascontiguousarray(scene.indices, "<u4").tobytes())
+        r = subprocess.run([BINARY, voxelize_shader_dir_for_driver(d), job, out], capture_output=True, text=True,
+                           env=dict(os.environ, VCT_MESA_LIBGL=MESA_LIBGL))
+        if r.returncode:
+            raise RuntimeError(f"vct_gl_ref failed ({r.returncode}): {r.stderr[-2000:]}")
+        blob = open(out, "rb").read()
+    voxelize_fragments.last_log = r.stderr
+    n = struct.unpack_from("<I", blob, 0)[0]
+    rec = np.frombuffer(blob, "<u4", n * 10, 4).reshape(n, 10)
+    return rec[:, 0].copy(), rec[:, 1:3].copy(), rec[:, 3:6].copy().view("<f4"), rec[:, 6:10].copy().view("<f4")
+
+
 def available() -> bool:
     return os.path.exists(BINARY) and os.path.exists(MESA_LIBGL) and os.path.exists(os.path.join(SHADER_DIR, "voxel_cone_tracing.frag"))
 

@@ -52,6 +52,7 @@ typedef ptrdiff_t GLsizeiptr, GLintptr;
   X(void, Disable, (GLenum)) X(void, Clear, (GLbitfield)) X(void, ClearColor, (GLfloat, GLfloat, GLfloat, GLfloat))                             \
   X(void, BlendFunc, (GLenum, GLenum)) X(void, DrawElementsBaseVertex, (GLenum, GLsizei, GLenum, const void*, GLint))                           \
   X(void, ReadPixels, (GLint, GLint, GLsizei, GLsizei, GLenum, GLenum, void*)) X(void, PixelStorei, (GLenum, GLint)) X(GLenum, GetError, (void)) \
+  X(void, DrawBuffers, (GLsizei, const GLenum*)) X(void, ReadBuffer, (GLenum)) X(void, ColorMask, (unsigned char, unsigned char, unsigned char, unsigned char)) \
   X(void, Finish, (void)) X(const unsigned char*, GetString, (GLenum)) X(void, ClampColor, (GLenum, GLenum))
 
 #define X(ret, name, args) static ret(*gl##name) args;
@@ -95,6 +96,90 @@ struct Job {
   int32_t direct, diffuse, specular, shadow, view_voxel_dir;
   float view_voxel_lod, cube_size, view[16], proj[16];
 };
+
+// ---- Renderer::voxelize (renderer.cpp:316-353) as far as this driver can run it: the reference's voxelize.vert and voxelize.geom
+// unmodified, and its voxelize.frag with the image store replaced by two colour outputs (oracle/gl_ref.py does that to the text: llvmpipe
+// 18.1 has no image load/store) -- voxel coordinate and colour of every fragment, i.e. the arguments of imageAtomicRGBA8Avg.  GL state as
+// the reference sets it: viewport 2R x 2R, no depth test, no culling, no blending.  One draw per triangle, so that the fragments come
+// out as a list in draw order / triangle order / row / column.
+// out file: u32 n, then n records of 10 words: u32 triangle sequence, u32 x, u32 y, f32 voxel[3], f32 colour[4]
+static int voxelize_pass(const struct Job* J, char** argv, const float* lights, const unsigned char* draws, const GLuint* mat_ubo, GLuint cam_ubo) {
+  GLuint prog = glCreateProgram();
+  glAttachShader(prog, compile(0x8B31, slurp(argv[1], "voxelize.vert"), "voxelize.vert"));
+  glAttachShader(prog, compile(0x8DD9, slurp(argv[1], "voxelize.geom"), "voxelize.geom"));
+  glAttachShader(prog, compile(0x8B30, slurp(argv[1], "voxelize.frag"), "voxelize.frag (image store replaced by colour outputs)"));
+  glLinkProgram(prog);
+  GLint ok = 0;
+  glGetProgramiv(prog, 0x8B82, &ok);
+  if (!ok) { char log[8192] = ""; glGetProgramInfoLog(prog, sizeof log, 0, log); fprintf(stderr, "%s\n", log); die("link failed (voxelize)"); }
+  const GLuint material_location = glGetUniformBlockIndex(prog, "material"), camera_location = glGetUniformBlockIndex(prog, "camera");
+  fprintf(stderr, "voxelize program: uniform block indices camera %u, material %u\n", camera_location, material_location);
+  const GLsizei V = (GLsizei)(2 * J->R);   // viewport_res = m_resolution * 2
+  GLuint fbo, rb[2];
+  glGenFramebuffers(1, &fbo); glBindFramebuffer(0x8D40, fbo);
+  glGenRenderbuffers(2, rb);
+  for (int i = 0; i < 2; i++) {
+    glBindRenderbuffer(0x8D41, rb[i]); glRenderbufferStorage(0x8D41, 0x8814 /*RGBA32F*/, V, V);
+    glFramebufferRenderbuffer(0x8D40, 0x8CE0 + i, 0x8D41, rb[i]);
+  }
+  const GLenum bufs[2] = {0x8CE0, 0x8CE1};
+  glDrawBuffers(2, bufs);
+  if (glCheckFramebufferStatus(0x8D40) != 0x8CD5) die("framebuffer incomplete (voxelize)");
+  glClampColor(0x891B, 0); glClampColor(0x891C, 0);
+  glUseProgram(prog);
+  glUniform1f(glGetUniformLocation(prog, "cube_size"), J->cube_size);
+  glUniform1i(glGetUniformLocation(prog, "vct_grid_res"), (GLint)J->R);
+  glBindBufferBase(0x8A11, camera_location, cam_ubo);
+  glUniform3fv(glGetUniformLocation(prog, "camera_position"), 1, J->view + 12);
+  for (uint32_t i = 0; i < J->n_lights; i++) {
+    char name[64];
+    snprintf(name, sizeof name, "point_lights[%u].position", i); glUniform3fv(glGetUniformLocation(prog, name), 1, lights + 7 * i);
+    snprintf(name, sizeof name, "point_lights[%u].color", i); glUniform3fv(glGetUniformLocation(prog, name), 1, lights + 7 * i + 3);
+    snprintf(name, sizeof name, "point_lights[%u].intensity", i); glUniform1f(glGetUniformLocation(prog, name), lights[7 * i + 6]);
+  }
+  glUniform1i(glGetUniformLocation(prog, "point_light_count"), (GLint)J->n_lights);
+  glViewport(0, 0, V, V);
+  glDisable(0x0B44 /*CULL_FACE*/);
+  glDisable(0x0B71 /*DEPTH_TEST*/);
+  glDisable(0x0BE2 /*BLEND*/);
+  glClearColor(0, 0, 0, 0);
+  glPixelStorei(0x0D05, 1);
+  FILE* out = fopen(argv[3], "wb");
+  if (!out) die("cannot open the output file");
+  uint32_t n_frag = 0, seq = 0;
+  fwrite(&n_frag, 4, 1, out);
+  float* vox = malloc((size_t)V * V * 16);
+  float* col = malloc((size_t)V * V * 16);
+  const GLint model_location = glGetUniformLocation(prog, "model");
+  for (uint32_t i = 0; i < J->n_draws; i++) {
+    uint32_t d[4];
+    memcpy(d, draws + 80 * (size_t)i, 16);
+    glUniformMatrix4fv(model_location, 1, 0, (const float*)(draws + 80 * (size_t)i + 16));
+    glBindBufferBase(0x8A11, material_location, mat_ubo[d[3]]);
+    for (uint32_t t = 0; t + 3 <= d[1]; t += 3, seq++) {
+      glClear(0x4000);
+      glDrawElementsBaseVertex(0x0004, 3, 0x1405, (const void*)(sizeof(unsigned) * ((size_t)d[0] + t)), (GLint)d[2]);
+      glReadBuffer(0x8CE0); glReadPixels(0, 0, V, V, 0x1908, 0x1406, vox);
+      glReadBuffer(0x8CE1); glReadPixels(0, 0, V, V, 0x1908, 0x1406, col);
+      for (GLsizei y = 0; y < V; y++)
+        for (GLsizei x = 0; x < V; x++) {
+          const float* v = vox + 4 * ((size_t)y * V + x);
+          if (v[3] != 1.0f) continue;
+          const uint32_t head[3] = {seq, (uint32_t)x, (uint32_t)y};
+          fwrite(head, 4, 3, out);
+          fwrite(v, 4, 3, out);
+          fwrite(col + 4 * ((size_t)y * V + x), 4, 4, out);
+          n_frag++;
+        }
+    }
+  }
+  if (glGetError()) die("GL error in the voxelization pass");
+  fseek(out, 0, SEEK_SET);
+  fwrite(&n_frag, 4, 1, out);
+  fclose(out);
+  fprintf(stderr, "voxelize: %u triangles, %u fragments\n", seq, n_frag);
+  return 0;
+}
 
 int main(int argc, char** argv) {
   if (argc != 4) die("usage: vct_gl_ref <shader dir> <job file> <out file>");
@@ -157,6 +242,27 @@ int main(int argc, char** argv) {
   unsigned char* verts; READ(verts, (size_t)J.n_verts * 32);
   unsigned char* indices; READ(indices, (size_t)J.n_indices * 4);
 
+  // ---- buffers: one VAO over all vertices / indices (load_model, renderer.cpp:559-600), one UBO per material, the camera UBO
+  GLuint vao, vbo, ebo, cam_ubo;
+  glGenVertexArrays(1, &vao);
+  glBindVertexArray(vao);
+  glGenBuffers(1, &vbo); glBindBuffer(0x8892 /*ARRAY_BUFFER*/, vbo); glBufferData(0x8892, (GLsizeiptr)J.n_verts * 32, verts, 0x88E4);
+  glGenBuffers(1, &ebo); glBindBuffer(0x8893 /*ELEMENT_ARRAY_BUFFER*/, ebo); glBufferData(0x8893, (GLsizeiptr)J.n_indices * 4, indices, 0x88E4);
+  glEnableVertexAttribArray(0); glVertexAttribPointer(0, 3, 0x1406, 0, 32, (const void*)0);
+  glEnableVertexAttribArray(1); glVertexAttribPointer(1, 3, 0x1406, 0, 32, (const void*)12);
+  glEnableVertexAttribArray(2); glVertexAttribPointer(2, 2, 0x1406, 0, 32, (const void*)24);
+  GLuint* mat_ubo = malloc(sizeof(GLuint) * (J.n_mats ? J.n_mats : 1));
+  glGenBuffers((GLsizei)J.n_mats, mat_ubo);
+  for (uint32_t i = 0; i < J.n_mats; i++) { glBindBuffer(0x8A11 /*UNIFORM_BUFFER*/, mat_ubo[i]); glBufferData(0x8A11, 128, mats + 128 * (size_t)i, 0x88E4); }
+  float cam[32];
+  memcpy(cam, J.proj, 64); memcpy(cam + 16, J.view, 64);   // camera_data_t: projection, view (renderer.h:81-85)
+  glGenBuffers(1, &cam_ubo); glBindBuffer(0x8A11, cam_ubo); glBufferData(0x8A11, 128, cam, 0x88E8);
+
+  if (J.levels == 0) {   // voxelization pass (see the header): fragments of every triangle, no textures in the job
+    fclose(f);
+    return voxelize_pass(&J, argv, lights, draws, mat_ubo, cam_ubo);
+  }
+
   // ---- create_tex_3d (texture_3d.cpp:3-25): RGBA8, `levels` levels, CLAMP_TO_BORDER, LINEAR_MIPMAP_LINEAR (the MAG_FILTER call with
   // that enum is an error in GL and leaves GL_LINEAR, as in the reference); texels from the job file
   GLuint tex[6];
@@ -195,22 +301,6 @@ int main(int argc, char** argv) {
   const GLuint material_location = glGetUniformBlockIndex(prog, "material"), camera_location = glGetUniformBlockIndex(prog, "camera");
   fprintf(stderr, "uniform block indices: camera %u, material %u (the reference binds its UBOs at these numbers; the shaders say binding 0 / 1)\n",
           camera_location, material_location);
-
-  // ---- buffers: one VAO over all vertices / indices (load_model, renderer.cpp:559-600), one UBO per material, the camera UBO
-  GLuint vao, vbo, ebo, cam_ubo;
-  glGenVertexArrays(1, &vao);
-  glBindVertexArray(vao);
-  glGenBuffers(1, &vbo); glBindBuffer(0x8892 /*ARRAY_BUFFER*/, vbo); glBufferData(0x8892, (GLsizeiptr)J.n_verts * 32, verts, 0x88E4);
-  glGenBuffers(1, &ebo); glBindBuffer(0x8893 /*ELEMENT_ARRAY_BUFFER*/, ebo); glBufferData(0x8893, (GLsizeiptr)J.n_indices * 4, indices, 0x88E4);
-  glEnableVertexAttribArray(0); glVertexAttribPointer(0, 3, 0x1406, 0, 32, (const void*)0);
-  glEnableVertexAttribArray(1); glVertexAttribPointer(1, 3, 0x1406, 0, 32, (const void*)12);
-  glEnableVertexAttribArray(2); glVertexAttribPointer(2, 2, 0x1406, 0, 32, (const void*)24);
-  GLuint* mat_ubo = malloc(sizeof(GLuint) * (J.n_mats ? J.n_mats : 1));
-  glGenBuffers((GLsizei)J.n_mats, mat_ubo);
-  for (uint32_t i = 0; i < J.n_mats; i++) { glBindBuffer(0x8A11 /*UNIFORM_BUFFER*/, mat_ubo[i]); glBufferData(0x8A11, 128, mats + 128 * (size_t)i, 0x88E4); }
-  float cam[32];
-  memcpy(cam, J.proj, 64); memcpy(cam + 16, J.view, 64);   // camera_data_t: projection, view (renderer.h:81-85)
-  glGenBuffers(1, &cam_ubo); glBindBuffer(0x8A11, cam_ubo); glBufferData(0x8A11, 128, cam, 0x88E8);
 
   FILE* out = fopen(argv[3], "wb");
   if (!out) die("cannot open the output file");

@@ -52,6 +52,9 @@ CASES = {
     "view_d4_lod2.9":     (False, {}, dict(view_voxel_dir=4, view_voxel_lod=2.9)),
 }
 FLOAT_CASES = [n for n in CASES if n.startswith("view_")]
+# the voxelization pass: name -> (suzanne, theta, grid resolution)
+VOXEL_CASES = {"vox_cornell_32": (False, 0.0, 32), "vox_suzanne_64": (True, 1.234, 64)}
+VOXEL_GOLDEN = os.path.join(ROOT, "tests", "golden", "gl_llvmpipe_voxel_fragments.npz")
 _PYR = {}
 
 
@@ -149,6 +152,45 @@ def test_whole_frames_match_gl(golden, brilinear, name, max_abs, frac_over_1):
     assert np.array_equal(g.tri_id == 0xFFFFFFFF, gl == BACKGROUND)
     d = channel_diff(frame, gl)
     assert d.max() <= max_abs and (d > 1).mean() <= frac_over_1 and (d > 0).mean() < 0.03, (d.max(), (d > 1).mean(), (d > 0).mean())
+
+
+def voxel_scene(name):
+    suzanne, theta, res = VOXEL_CASES[name]
+    return S.cornell_scene(with_suzanne=suzanne, theta=theta), res
+
+
+@pytest.mark.parametrize("name", sorted(VOXEL_CASES))
+def test_voxelization_fragments_match_gl(name):
+    """Renderer::voxelize on llvmpipe: the reference's voxelize.vert and voxelize.geom unmodified and its voxelize.frag up to the image store
+    (oracle/gl_ref.py: the store becomes two colour outputs, the driver has no image load/store) -- one fragment list in draw / triangle /
+    row / column order.  Pins V1-V4 against a real GL: the axis selection of the geometry shader, WHERE the fragments of the 2R x 2R
+    rasterisation fall (their number equals the oracle's, the occupied voxels and the 4-bit sample counts are identical) and the voxel
+    colour (one step of the 7-bit average on < 1 % of the voxels: llvmpipe's normalize / division differ in the last bits, and the shader
+    truncates).  The order in which fragments reach the running average stays a written rule (R4): GL itself does not define one."""
+    g = np.load(VOXEL_GOLDEN)
+    tri, vox, col = g[name + ":tri"], g[name + ":voxel"].astype(np.int64), g[name + ":colour"]
+    sc, res = voxel_scene(name)
+    base, st = orc.voxelize(sc, res)
+    assert len(tri) == st.fragments and st.fragments_oob == 0
+    assert np.all(np.diff(tri.astype(np.int64)) >= 0)
+    grid = np.zeros((res, res, res), np.uint32)
+    for i in range(len(tri)):                                   # imageAtomicRGBA8Avg in list order (orc.fold: pinned by tests/test_glsl_ref.py)
+        x, y, z = vox[i]
+        grid[z, y, x] = orc.fold(int(grid[z, y, x]), col[i])
+    assert np.array_equal(grid != 0, base != 0), "occupancy differs"
+    assert not ((grid ^ base) & 0x01010101).any(), "a voxel received a different number of fragments"
+    d = np.abs(grid.view(np.uint8).astype(int) - base.view(np.uint8).astype(int)).reshape(-1, 4).max(axis=1)
+    assert d.max() <= 2 and (d > 0).sum() <= 0.01 * st.occupied, (d.max(), (d > 0).sum(), st.occupied)
+
+
+def test_llvmpipe_rasterises_the_committed_fragments():
+    if not gl_ref.available():
+        pytest.skip("needs oracle/_ref/gl/vct_gl_ref, Nsight Compute's Mesa libGL and /root/reference/shader")
+    g = np.load(VOXEL_GOLDEN)
+    sc, res = voxel_scene("vox_cornell_32")
+    tri, xy, vox, col = gl_ref.voxelize_fragments(sc, res)
+    assert np.array_equal(tri, g["vox_cornell_32:tri"]) and np.array_equal(vox.astype(np.int16), g["vox_cornell_32:voxel"])
+    assert np.array_equal(col, g["vox_cornell_32:colour"])
 
 
 def test_brilinear_switch_is_off_by_default():

@@ -33,6 +33,15 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "gl_llvmpipe_frames.npz")
     np.savez_compressed(path, **out)
     print("->", path, os.path.getsize(path), "bytes")
+    vox = {}
+    for name in T.VOXEL_CASES:
+        sc, res = T.voxel_scene(name)
+        tri, xy, voxel, col = gl_ref.voxelize_fragments(sc, res)
+        assert np.array_equal(voxel, np.floor(voxel)) and voxel.min() >= 0 and voxel.max() < res
+        vox[name + ":tri"], vox[name + ":xy"], vox[name + ":voxel"], vox[name + ":colour"] = tri, xy.astype(np.uint16), voxel.astype(np.int16), col
+        print(name, len(tri), "fragments")
+    np.savez_compressed(T.VOXEL_GOLDEN, **vox)
+    print("->", T.VOXEL_GOLDEN, os.path.getsize(T.VOXEL_GOLDEN), "bytes")
 
 
 if __name__ == "__main__":
