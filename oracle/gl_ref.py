@@ -116,6 +116,54 @@ def voxelize_fragments(scene, R: int):
     return rec[:, 0].copy(), rec[:, 1:3].copy(), rec[:, 3:6].copy().view("<f4"), rec[:, 6:10].copy().view("<f4")
 
 
+def mip_shader_dir_for_driver(tmp: str) -> str:
+    """mipmap.comp as a fragment shader (llvmpipe 18.1 has no compute shaders): the work-group layout line goes, the image declaration
+    becomes six colour outputs + a layer uniform, `gl_GlobalInvocationID` becomes (gl_FragCoord.xy, layer), and each
+    `imageStore(dest_tex3D[k], write_pos, value)` becomes `vct_out[k] = (value)`.  fetch_texels, alpha_blend, the offset table and the
+    six filter expressions (mipmap.comp:10-100) stay character for character."""
+    import re
+    text = open(os.path.join(SHADER_DIR, "mipmap.comp")).read()
+
+    def once(old, new):
+        nonlocal text
+        assert text.count(old) == 1, old
+        text = text.replace(old, new)
+
+    once("layout (local_size_x = 8, local_size_y = 8, local_size_z = 8) in;", "")
+    once("uniform layout (binding = 0, RGBA8) image3D dest_tex3D[6];", "uniform int vct_layer;\nlayout (location = 0) out vec4 vct_out[6];")
+    assert text.count("gl_GlobalInvocationID") == 4
+    text = text.replace("gl_GlobalInvocationID", "uvec3(uvec2(gl_FragCoord.xy), uint(vct_layer))")
+    text, n = re.subn(r"imageStore\(dest_tex3D\[(\d)\], write_pos, ", r"vct_out[\1] = (", text)
+    assert n == 6
+    with open(os.path.join(tmp, "mipmap.comp"), "w") as f:
+        f.write(text)
+    return tmp
+
+
+def mip_chain(base: np.ndarray, levels: int = 7):
+    """Renderer::filter on llvmpipe: [dir][level] -> uint32[N, N, N] for levels 1..levels-1 (index 0 = `base`)."""
+    R = base.shape[0]
+    with tempfile.TemporaryDirectory() as d:
+        job, out = os.path.join(d, "job.bin"), os.path.join(d, "out.bin")
+        with open(job, "wb") as f:
+            f.write(b"VCTGLMIP")
+            f.write(struct.pack("<2I", R, levels))
+            f.write(np.ascontiguousarray(base, "<u4").tobytes())
+        r = subprocess.run([BINARY, mip_shader_dir_for_driver(d), job, out], capture_output=True, text=True, env=dict(os.environ, VCT_MESA_LIBGL=MESA_LIBGL))
+        if r.returncode:
+            raise RuntimeError(f"vct_gl_ref failed ({r.returncode}): {r.stderr[-2000:]}")
+        blob = open(out, "rb").read()
+    res, off = [], 0
+    for _dir in range(6):
+        chain = [base]
+        for l in range(1, levels):
+            N = R >> l
+            chain.append(np.frombuffer(blob, "<u4", N ** 3, off).reshape(N, N, N).copy())
+            off += 4 * N ** 3
+        res.append(chain)
+    return res
+
+
 def available() -> bool:
     return os.path.exists(BINARY) and os.path.exists(MESA_LIBGL) and os.path.exists(os.path.join(SHADER_DIR, "voxel_cone_tracing.frag"))
 

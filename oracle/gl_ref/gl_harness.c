@@ -53,7 +53,8 @@ typedef ptrdiff_t GLsizeiptr, GLintptr;
   X(void, BlendFunc, (GLenum, GLenum)) X(void, DrawElementsBaseVertex, (GLenum, GLsizei, GLenum, const void*, GLint))                           \
   X(void, ReadPixels, (GLint, GLint, GLsizei, GLsizei, GLenum, GLenum, void*)) X(void, PixelStorei, (GLenum, GLint)) X(GLenum, GetError, (void)) \
   X(void, DrawBuffers, (GLsizei, const GLenum*)) X(void, ReadBuffer, (GLenum)) X(void, ColorMask, (unsigned char, unsigned char, unsigned char, unsigned char)) \
-  X(void, Finish, (void)) X(const unsigned char*, GetString, (GLenum)) X(void, ClampColor, (GLenum, GLenum))
+  X(void, FramebufferTextureLayer, (GLenum, GLenum, GLuint, GLint, GLint)) X(void, GetTexImage, (GLenum, GLint, GLenum, GLenum, void*)) \
+  X(void, DrawArrays, (GLenum, GLint, GLsizei)) X(void, Finish, (void)) X(const unsigned char*, GetString, (GLenum)) X(void, ClampColor, (GLenum, GLenum))
 
 #define X(ret, name, args) static ret(*gl##name) args;
 GL_FUNCS(X)
@@ -181,6 +182,85 @@ static int voxelize_pass(const struct Job* J, char** argv, const float* lights, 
   return 0;
 }
 
+// ---- Renderer::filter (renderer.cpp:283-314) as far as this driver can run it: llvmpipe 18.1 has no compute shaders, so the reference's
+// mipmap.comp runs as a FRAGMENT shader (oracle/gl_ref.py rewrites three lines of its text: the invocation id comes from gl_FragCoord and a
+// layer uniform, the six imageStores become six colour outputs); its arithmetic, its texelFetches and its constant tables are untouched.
+// One draw per z layer of the destination level into six RGBA8 attachments (layer z of level mip + 1 of the six textures), so the
+// float -> unorm8 conversion is GL's own, like the image store's.
+// mip job: "VCTGLMIP" u32 R levels, R^3 u32 (level 0).  out file: for dir 0..5, level 1..levels-1: (R >> l)^3 u32
+static int mip_pass(char** argv) {
+  FILE* f = fopen(argv[2], "rb");
+  if (!f) die("cannot open the job file");
+  char magic[8];
+  uint32_t hdr[2];
+  if (fread(magic, 1, 8, f) != 8 || fread(hdr, 4, 2, f) != 2) die("bad mip job");
+  const uint32_t R = hdr[0], levels = hdr[1];
+  const size_t n0 = (size_t)R * R * R;
+  unsigned char* level0 = malloc(n0 * 4);
+  if (fread(level0, 4, n0, f) != n0) die("short mip job");
+  fclose(f);
+  GLuint tex[6];
+  glGenTextures(6, tex);
+  glPixelStorei(0x0CF5, 1); glPixelStorei(0x0D05, 1);
+  for (int d = 0; d < 6; d++) {   // create_tex_3d
+    glActiveTexture(0x84C0 + d);   // activate_tex_3d(m_mipmap_shader, m_voxel_maps[i], i)
+    glBindTexture(0x806F, tex[d]);
+    glTexParameteri(0x806F, 0x2802, 0x812D); glTexParameteri(0x806F, 0x2803, 0x812D); glTexParameteri(0x806F, 0x8072, 0x812D);
+    glTexParameteri(0x806F, 0x2801, 0x2703);
+    glTexStorage3D(0x806F, (GLsizei)levels, 0x8058, R, R, R);
+    glTexSubImage3D(0x806F, 0, 0, 0, 0, R, R, R, 0x1908, 0x1401, level0);
+  }
+  if (glGetError()) die("GL error while creating the textures (mip)");
+  static const char* vs =
+      "#version 450 core\nvoid main() { vec2 p = vec2((gl_VertexID << 1) & 2, gl_VertexID & 2); gl_Position = vec4(p * 2.0 - 1.0, 0.0, 1.0); }\n";
+  GLuint prog = glCreateProgram();
+  glAttachShader(prog, compile(0x8B31, vs, "full-screen triangle"));
+  glAttachShader(prog, compile(0x8B30, slurp(argv[1], "mipmap.comp"), "mipmap.comp (as a fragment shader)"));
+  glLinkProgram(prog);
+  GLint ok = 0;
+  glGetProgramiv(prog, 0x8B82, &ok);
+  if (!ok) { char log[8192] = ""; glGetProgramInfoLog(prog, sizeof log, 0, log); fprintf(stderr, "%s\n", log); die("link failed (mip)"); }
+  glUseProgram(prog);
+  GLuint vao, fbo;
+  glGenVertexArrays(1, &vao); glBindVertexArray(vao);
+  glGenFramebuffers(1, &fbo); glBindFramebuffer(0x8D40, fbo);
+  const GLenum bufs[6] = {0x8CE0, 0x8CE1, 0x8CE2, 0x8CE3, 0x8CE4, 0x8CE5};
+  glDisable(0x0B71); glDisable(0x0BE2); glDisable(0x0B44);
+  const GLint resolution_location = glGetUniformLocation(prog, "resolution"), mip_location = glGetUniformLocation(prog, "mip"),
+              layer_location = glGetUniformLocation(prog, "vct_layer");
+  uint32_t current_dim = R;
+  for (uint32_t mip = 0; mip + 1 < levels; mip++, current_dim /= 2) {   // filter(): while (current_dim >= 1), levels the texture has
+    const GLsizei N = (GLsizei)(current_dim / 2);
+    glUniform1i(resolution_location, (GLint)current_dim);
+    glUniform1i(mip_location, (GLint)mip);
+    glViewport(0, 0, N, N);
+    for (GLsizei z = 0; z < N; z++) {
+      for (int d = 0; d < 6; d++) glFramebufferTextureLayer(0x8D40, 0x8CE0 + d, tex[d], (GLint)mip + 1, z);
+      glDrawBuffers(6, bufs);
+      if (glCheckFramebufferStatus(0x8D40) != 0x8CD5) die("framebuffer incomplete (mip)");
+      glUniform1i(layer_location, z);
+      glDrawArrays(0x0004, 0, 3);
+    }
+    glFinish();
+  }
+  if (glGetError()) die("GL error in the mip pass");
+  FILE* out = fopen(argv[3], "wb");
+  if (!out) die("cannot open the output file");
+  for (int d = 0; d < 6; d++) {
+    glActiveTexture(0x84C0 + d);
+    for (uint32_t l = 1; l < levels; l++) {
+      const size_t N = R >> l;
+      void* buf = malloc(N * N * N * 4 + 16);
+      glGetTexImage(0x806F, (GLint)l, 0x1908, 0x1401, buf);
+      fwrite(buf, 4, N * N * N, out);
+      free(buf);
+    }
+  }
+  if (glGetError()) die("GL error while reading the levels back");
+  fclose(out);
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc != 4) die("usage: vct_gl_ref <shader dir> <job file> <out file>");
   const char* libgl = getenv("VCT_MESA_LIBGL");
@@ -233,6 +313,8 @@ int main(int argc, char** argv) {
   FILE* f = fopen(argv[2], "rb");
   if (!f) die("cannot open the job file");
   char magic[8];
+  if (fread(magic, 1, 8, f) == 8 && !memcmp(magic, "VCTGLMIP", 8)) { fclose(f); return mip_pass(argv); }
+  rewind(f);
   struct Job J;
   if (fread(magic, 1, 8, f) != 8 || memcmp(magic, "VCTGLJOB", 8) || fread(&J, sizeof J, 1, f) != 1) die("bad job file");
 #define READ(ptr, bytes) do { const size_t nb_ = (bytes); (ptr) = malloc(nb_ + 1); if (fread((ptr), 1, nb_, f) != nb_) die("short job file"); } while (0)

@@ -89,6 +89,8 @@ def lib():
                                 C.POINTER(TraceParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(TraceStats)]
         L.orc_set_num_threads.argtypes = [C.c_int]
         L.orc_debug_set_lod_filter.argtypes = [C.c_int]
+        L.orc_debug_set_unorm_unpack.argtypes = [C.c_int]
+        L.orc_debug_set_mip_balanced_sum.argtypes = [C.c_int]
         _LIB = L
     return _LIB
 
@@ -223,3 +225,14 @@ def set_num_threads(n: int) -> None:
 def debug_set_lod_filter(mode: int) -> None:
     """TEST SWITCH: 0 = rule R7, 1 = Mesa llvmpipe's brilinear mip filter (tests/test_gl_llvmpipe.py restores 0)."""
     lib().orc_debug_set_lod_filter(int(mode))
+
+
+def debug_set_unorm_unpack(mode: int) -> None:
+    """TEST SWITCH: 0 = rule R6 (unorm8 -> float = c / 255), 1 = c * (1.0f / 255.0f), as Mesa llvmpipe converts texels (tests/test_gl_llvmpipe.py)."""
+    lib().orc_debug_set_unorm_unpack(int(mode))
+
+
+
+def debug_set_mip_balanced_sum(on: int) -> None:
+    """TEST SWITCH: 1 = the mip filter's four terms added as a balanced tree, as Mesa's GLSL compiler arranges them (tests/test_gl_llvmpipe.py)."""
+    lib().orc_debug_set_mip_balanced_sum(int(on))

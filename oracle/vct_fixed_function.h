@@ -118,7 +118,16 @@ inline uint64_t pack_half4(const float v[4]) {
   return r;
 }
 
+/* TEST SWITCH (tests/test_gl_llvmpipe.py only; 0 everywhere else): 1 = unorm8 -> float as Mesa llvmpipe converts a texel, c * (1.0f / 255.0f)
+ * -- one rounding more than the specification's c / 255 (rule R6), up to one ulp off, which moves results of the mip filter that sit exactly
+ * on a rounding tie (a quarter of a sum of 8-bit values often does). */
+inline int& unorm_unpack_mode() { static int mode = 0; return mode; }
 inline void unpack_unorm(uint32_t c, float out[4]) {
+  if (unorm_unpack_mode() == 1) {
+    const float r = 1.0f / 255.0f;
+    for (int k = 0; k < 4; k++) out[k] = (float)((c >> (8 * k)) & 0xFFu) * r;
+    return;
+  }
   out[0] = (float)(c & 0xFFu) / 255.0f;
   out[1] = (float)((c >> 8) & 0xFFu) / 255.0f;
   out[2] = (float)((c >> 16) & 0xFFu) / 255.0f;

@@ -545,6 +545,7 @@ int orc_mipmap(const uint32_t* base, int R, int n_levels, uint32_t* const* out) 
 
 /* fmt 1: every array is uint64 per texel (RGBA16F); the blend runs in fp32 on the exactly converted halves, the result is clamped to
  * [0,1] like the unorm store of the reference and rounded to half (nearest even) */
+static int g_mip_balanced_sum = 0; /* TEST SWITCH, see orc_debug_set_mip_balanced_sum */
 int orc_mipmap_fmt(const uint32_t* base, int R, int n_levels, uint32_t* const* out, int fmt) {
   if (!base || !out || R <= 0 || n_levels < 1) return -1;
   size_t nvox = (size_t)R * R * R;
@@ -579,13 +580,15 @@ int orc_mipmap_fmt(const uint32_t* base, int R, int n_levels, uint32_t* const* o
             }
             float acc[4];
             for (int k = 0; k < 4; k++) {
-              float s = 0.0f;
+              float s = 0.0f, t[4];
               for (int pi = 0; pi < 4; pi++) {
                 const float* f = c[pairs[d][pi][0]];
                 const float* b = c[pairs[d][pi][1]];
                 float v = f[k] + ((1.0f - f[3]) * b[k]); /* alpha_blend :40-43 */
+                t[pi] = v;
                 s = pi == 0 ? v : s + v;
               }
+              if (g_mip_balanced_sum) s = (t[0] + t[1]) + (t[2] + t[3]); /* TEST SWITCH: Mesa's GLSL compiler rebalances the four-term sum */
               acc[k] = s / 4.0f;
             }
             if (fmt == 1) reinterpret_cast<uint64_t*>(dst)[((size_t)z * Nd + y) * Nd + x] = pack_half4(acc);
@@ -686,6 +689,8 @@ int orc_num_threads(void) {
 #endif
 }
 void orc_debug_set_lod_filter(int mode) { vct_ff::lod_filter_mode() = mode; }
+void orc_debug_set_mip_balanced_sum(int on) { g_mip_balanced_sum = on; }
+void orc_debug_set_unorm_unpack(int mode) { vct_ff::unorm_unpack_mode() = mode; }
 void orc_set_num_threads(int n) {
 #ifdef _OPENMP
   if (n > 0) omp_set_num_threads(n);

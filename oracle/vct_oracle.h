@@ -129,6 +129,11 @@ void orc_set_num_threads(int n);
 /* TEST SWITCH: 0 = rule R7 (default), 1 = Mesa llvmpipe's brilinear mip filter (vct_fixed_function.h lod_filter_mode); used only by
  * tests/test_gl_llvmpipe.py to compare the oracle with the reference's shaders running on that driver. */
 void orc_debug_set_lod_filter(int mode);
+/* TEST SWITCH: 0 = rule R6 (unorm8 -> float = c / 255), 1 = c * (1.0f / 255.0f) as Mesa llvmpipe converts texels; tests/test_gl_llvmpipe.py only. */
+void orc_debug_set_unorm_unpack(int mode);
+/* TEST SWITCH: 1 = the four alpha_blend terms of the mip filter added as (t0 + t1) + (t2 + t3) -- Mesa's GLSL compiler rebalances the sum
+ * mipmap.comp writes left to right (GLSL fixes no evaluation order without `precise`); tests/test_gl_llvmpipe.py only. */
+void orc_debug_set_mip_balanced_sum(int on);
 
 #ifdef __cplusplus
 }

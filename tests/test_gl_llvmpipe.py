@@ -193,6 +193,61 @@ def test_llvmpipe_rasterises_the_committed_fragments():
     assert np.array_equal(col, g["vox_cornell_32:colour"])
 
 
+MIP_GOLDEN = os.path.join(ROOT, "tests", "golden", "gl_llvmpipe_mip.npz")
+MIP_CASES = ["mip_scene_32", "mip_sparse_random_32", "mip_random_16"]
+
+
+def mip_base(name):
+    if name == "mip_scene_32":
+        return orc.voxelize(S.cornell_scene(with_suzanne=True), 32)[0]
+    rng = np.random.default_rng(5)
+    if name == "mip_random_16":
+        return rng.integers(0, 2 ** 32, (16, 16, 16), dtype=np.uint64).astype(np.uint32)
+    b = rng.integers(0, 2 ** 32, (32, 32, 32), dtype=np.uint64).astype(np.uint32)
+    b[rng.random((32, 32, 32)) < 0.7] = 0
+    return b
+
+
+@pytest.mark.parametrize("name", MIP_CASES)
+def test_mip_chain_matches_gl(name):
+    """Renderer::filter on llvmpipe: the reference's mipmap.comp executed as a fragment shader (no compute shaders in this driver; three lines
+    of its text rewritten, oracle/gl_ref.py), levels read with texelFetch and written through GL's own float -> unorm8 conversion.
+    Under rules R5 / R6 as written the oracle's chain is within ONE unit of the last place of llvmpipe's, on results that sit on a rounding
+    tie (a quarter of a sum of 8-bit values often does).  Two liberties of this driver account for every one of them -- texels converted as
+    c * (1 / 255) instead of c / 255, and the four-term sum evaluated as a balanced tree by Mesa's GLSL compiler: with both modelled (test
+    switches) all 36 volumes are equal BIT FOR BIT.  Ties of the float -> unorm8 conversion go to even on llvmpipe as in rule R6, and nothing
+    is fused into a multiply-add."""
+    g = np.load(MIP_GOLDEN)
+    base = mip_base(name)
+    levels = int(np.log2(base.shape[0])) + 1
+    plain = orc.mipmap(base, levels)
+    orc.debug_set_unorm_unpack(1); orc.debug_set_mip_balanced_sum(1)
+    try:
+        model = orc.mipmap(base, levels)
+    finally:
+        orc.debug_set_unorm_unpack(0); orc.debug_set_mip_balanced_sum(0)
+    n = n_off = 0
+    for d in range(6):
+        for l in range(1, levels):
+            gl = g[f"{name}:{d}:{l}"]
+            assert np.array_equal(model.levels[d][l], gl), (d, l)
+            diff = np.abs(plain.levels[d][l].view(np.uint8).astype(int) - gl.view(np.uint8).astype(int))
+            assert diff.max() <= 1
+            n += gl.size; n_off += int((plain.levels[d][l] != gl).sum())
+    assert n_off <= (0.01 if name == "mip_scene_32" else 0.15) * n, (n_off, n)
+    again = orc.mipmap(base, levels)
+    assert all(np.array_equal(again.levels[d][l], plain.levels[d][l]) for d in range(6) for l in range(levels))    # the switches are off again
+
+
+def test_llvmpipe_filters_the_committed_mip_chain():
+    if not gl_ref.available():
+        pytest.skip("needs oracle/_ref/gl/vct_gl_ref, Nsight Compute's Mesa libGL and /root/reference/shader")
+    g = np.load(MIP_GOLDEN)
+    base = mip_base("mip_random_16")
+    chain = gl_ref.mip_chain(base, 5)
+    assert all(np.array_equal(chain[d][l], g[f"mip_random_16:{d}:{l}"]) for d in range(6) for l in range(1, 5))
+
+
 def test_brilinear_switch_is_off_by_default():
     """Everything else in the suite (and the CUDA path) uses rule R7: the switch must not leak."""
     sc, view, proj, R_, W_, H_, prm = case_inputs("cornell")

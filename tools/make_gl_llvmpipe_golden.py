@@ -42,6 +42,17 @@ def main():
         print(name, len(tri), "fragments")
     np.savez_compressed(T.VOXEL_GOLDEN, **vox)
     print("->", T.VOXEL_GOLDEN, os.path.getsize(T.VOXEL_GOLDEN), "bytes")
+    mip = {}
+    for name in T.MIP_CASES:
+        base = T.mip_base(name)
+        levels = int(np.log2(base.shape[0])) + 1
+        chain = gl_ref.mip_chain(base, levels)
+        for d in range(6):
+            for l in range(1, levels):
+                mip[f"{name}:{d}:{l}"] = chain[d][l]
+        print(name, levels, "levels")
+    np.savez_compressed(T.MIP_GOLDEN, **mip)
+    print("->", T.MIP_GOLDEN, os.path.getsize(T.MIP_GOLDEN), "bytes")
 
 
 if __name__ == "__main__":
