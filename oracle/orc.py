@@ -1,8 +1,8 @@
 """ctypes binding of the CPU oracle (oracle/libvct_oracle.so).
 
 TEST INFRASTRUCTURE ONLY: the product (voxel_cone_tracing_b200) never imports this module.
-PARITY: shader arithmetic pinned to the reference's own GLSL run on the CPU (oracle/glsl_ref.py), fixed-function GL rules unpinned
--- see oracle/vct_oracle.h.
+PARITY: shader arithmetic pinned to the reference's own GLSL run on the CPU (oracle/glsl_ref.py); fixed-function GL rules held
+against Mesa llvmpipe running the reference's passes (oracle/gl_ref.py); fragment order (R4) a written rule -- see oracle/vct_oracle.h.
 """
 from __future__ import annotations
 

@@ -2,9 +2,9 @@
  * vct_oracle.cpp -- CPU ORACLE: a plain C++ restatement of the reference's GLSL hot path.
  *
  * TEST INFRASTRUCTURE ONLY (see vct_oracle.h).  PARITY: the shader arithmetic below is pinned, bit for bit, to the reference's
- * own GLSL text executed on the CPU (oracle/glsl_ref/, tests/test_glsl_ref.py); the fixed-function GL behaviour (rules R1-R4,
- * R6-R8, in vct_fixed_function.h) and the precision rules R5 / R9 are UNPINNED -- no OpenGL 4.5 implementation exists in this
- * image and the reference ships no tests / golden vectors.  Known-answer tests: tests/test_oracle_kat.py (derived by hand from
+ * own GLSL text executed on the CPU (oracle/glsl_ref/, tests/test_glsl_ref.py); the fixed-function GL behaviour (rules R1-R3,
+ * R6-R8, in vct_fixed_function.h) is held against Mesa llvmpipe running the reference's three passes (oracle/gl_ref/,
+ * tests/test_gl_llvmpipe.py); R4 (fragment order) is a written rule -- GL defines no order.  Known-answer tests: tests/test_oracle_kat.py (derived by hand from
  * the shader text).
  *
  * What is restated (paths relative to /root/reference):
@@ -14,7 +14,7 @@
  *   GL state of src/renderer.cpp:316-390, texture parameters of src/texture_3d.cpp:3-25
  *
  * Implementation-defined GL behaviour, FIXED HERE IN WRITING (the CUDA product follows the
- * same rules; none of this can be checked against a GL driver in this image):
+ * same rules; checked against Mesa llvmpipe where that driver can run the pass, see vct_oracle.h):
  *   R1 viewport: xw = (x_ndc + 1) * (W * 0.5), yw likewise, zw = (z_ndc + 1) * 0.5; y up,
  *      row 0 = bottom.
  *   R2 coverage: vertices snapped to 1/256 pixel (rintf, ties-to-even); 64-bit integer edge

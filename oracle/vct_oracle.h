@@ -8,12 +8,15 @@
  * they lie, are rewritten syntactically, compiled against the reference's vendored GLM and executed on the CPU
  * (oracle/glsl_ref/ -> oracle/_ref/libvct_glsl_ref.so); voxel grid, all mip volumes, G-buffer attributes and the frame of this
  * oracle equal that program's BIT FOR BIT (tests/test_glsl_ref.py; vectors it produced: tests/golden/glsl_ref_vectors.json,
- * tests/test_glsl_ref_golden.py).  The FIXED-FUNCTION stages stay UNPINNED: the reference (latencyhiding/voxel_cone_tracing) has
- * no tests, golden vectors or fixtures for this path and no OpenGL 4.5 driver exists in this image (no libGL/EGL/OSMesa, no
- * llvmpipe with compute/image-atomics), so rasterisation, fragment order, texture filtering and the precision of built-ins
- * follow written rules (R1-R9 in vct_oracle.cpp, shared with the GLSL harness through vct_fixed_function.h) that no GL
- * implementation has validated.  Beside that: known-answer tests derived by hand from the shader text
- * (tests/test_oracle_kat.py) and the tinyobjloader cross-check of the scene inputs.
+ * tests/test_glsl_ref_golden.py).  The FIXED-FUNCTION stages are held against a real OpenGL implementation, not the one BASELINE.json
+ * names (no OpenGL 4.5 driver exists in this image) but the Mesa 18.1 llvmpipe inside Nsight Compute, driven through all three passes of
+ * the reference with its own shader text (oracle/gl_ref/, tests/test_gl_llvmpipe.py): the fragments of the voxelization pass (count,
+ * occupancy and sample counts identical), the mip chain (bit for bit once two liberties of that driver are modelled, one LSB on rounding
+ * ties otherwise), raster coverage / clipping / interpolation / depth test / textureLod / blending / unorm conversion of the camera pass
+ * and whole frames (within 1/255).  What stays a WRITTEN RULE with no GL behind it: R4, the order in which fragments reach the running
+ * average (GL defines none; llvmpipe 18.1 has no image atomics to show one), and -- llvmpipe filtering mip levels "brilinearly" -- the
+ * linear LOD blend of R7 at fractions other than 0 and 0.5 (the specification's formula).  Beside that: known-answer tests derived by
+ * hand from the shader text (tests/test_oracle_kat.py) and the tinyobjloader cross-check of the scene inputs.
  */
 #ifndef VCT_ORACLE_H
 #define VCT_ORACLE_H
