@@ -1,8 +1,8 @@
 """GPU parity tests: every stage of the CUDA path (through the C ABI) against the CPU oracle on
 the same inputs.  Bars (BASELINE.json north_star): voxel occupancy bit-exact, voxel colour <= 1 LSB
 (we require bit-exact: the kernels share the oracle's arithmetic rules), frame max-abs <= 2/255 and
-PSNR >= 45 dB.  Oracle = CPU restatement, itself equal bit for bit to the reference's own GLSL run on the CPU (tests/test_glsl_ref.py); the
-fixed-function GL rules stay unpinned: llvmpipe is unavailable in this image."""
+PSNR >= 45 dB.  Oracle = CPU restatement, itself equal bit for bit to the reference's own GLSL run on the CPU (tests/test_glsl_ref.py) and held
+against the reference's shaders running on Mesa llvmpipe (tests/test_gl_llvmpipe.py, tests/test_gpu_vs_llvmpipe.py)."""
 import numpy as np
 import pytest
 
