@@ -164,6 +164,27 @@ def mip_chain(base: np.ndarray, levels: int = 7):
     return res
 
 
+def render_frame(scene, view, proj, R: int, W: int, H: int, params=None, levels: int = 7):
+    """Renderer::render on llvmpipe, all three passes chained: its fragments folded by the oracle's restatement of imageAtomicRGBA8Avg in list
+    order (rule R4: the one step with no GL behind it), its mip chain of that grid, its frame from those textures.
+    Returns dict(frame=uint32[H, W], base=uint32[R, R, R], pyramid=orc.Pyramid, fragments=n)."""
+    from . import orc
+    tri, xy, vox, col = voxelize_fragments(scene, R)
+    base = np.zeros((R, R, R), np.uint32)
+    v = vox.astype(np.int64)
+    for i in range(len(tri)):
+        x, y, z = v[i]
+        if 0 <= x < R and 0 <= y < R and 0 <= z < R:      # an image store outside the texture is dropped
+            base[z, y, x] = orc.fold(int(base[z, y, x]), col[i])
+    chain = mip_chain(base, levels)
+    pyr = orc.Pyramid(base, levels)
+    for d in range(6):
+        for l in range(1, levels):
+            pyr.levels[d][l][...] = chain[d][l]
+    frame, _ = visualize(scene, view, proj, pyr, W, H, params)
+    return dict(frame=frame, base=base, pyramid=pyr, fragments=len(tri))
+
+
 def available() -> bool:
     return os.path.exists(BINARY) and os.path.exists(MESA_LIBGL) and os.path.exists(os.path.join(SHADER_DIR, "voxel_cone_tracing.frag"))
 

@@ -248,6 +248,18 @@ def test_llvmpipe_filters_the_committed_mip_chain():
     assert all(np.array_equal(chain[d][l], g[f"mip_random_16:{d}:{l}"]) for d in range(6) for l in range(1, 5))
 
 
+def test_whole_pipeline_on_gl_matches_the_oracle(golden, brilinear):
+    """Renderer::render with EVERY pass executed by llvmpipe (oracle/gl_ref.render_frame: voxelization fragments folded in list order, the
+    driver's mip chain of that grid, the driver's frame from those textures) against the oracle end to end -- the nearest thing to the
+    "reference under Mesa llvmpipe" arm BASELINE.json names that this image can run.  Cornell box + Suzanne, 64^3, 160x120."""
+    gl = golden["pipeline_suzanne"]
+    sc, view, proj, R_, W_, H_, prm = case_inputs("suzanne")
+    ref = orc.render_frame(sc, view, proj, R_, W_, H_)
+    assert np.array_equal(ref["gbuffer"].tri_id == 0xFFFFFFFF, gl == BACKGROUND)
+    d = channel_diff(ref["frame"], gl)
+    assert d.max() <= 4 and (d > 1).mean() <= 0.001 and (d > 0).mean() < 0.08, (d.max(), (d > 1).mean(), (d > 0).mean())
+
+
 def test_brilinear_switch_is_off_by_default():
     """Everything else in the suite (and the CUDA path) uses rule R7: the switch must not leak."""
     sc, view, proj, R_, W_, H_, prm = case_inputs("cornell")

@@ -30,6 +30,8 @@ def main():
         out[name] = u8
         out[name + ":f32"] = f32[::2, ::2].astype(np.float32) if name in T.FLOAT_CASES else np.zeros(0, np.float32)   # every second pixel
         print(name, u8.shape)
+    sc, view, proj, R, W, H, prm = T.case_inputs("suzanne")
+    out["pipeline_suzanne"] = gl_ref.render_frame(sc, view, proj, R, W, H, prm)["frame"]     # all three passes on the driver
     path = os.path.join(ROOT, "tests", "golden", "gl_llvmpipe_frames.npz")
     np.savez_compressed(path, **out)
     print("->", path, os.path.getsize(path), "bytes")
