@@ -190,7 +190,7 @@ def test_llvmpipe_rasterises_the_committed_fragments():
     sc, res = voxel_scene("vox_cornell_32")
     tri, xy, vox, col = gl_ref.voxelize_fragments(sc, res)
     assert np.array_equal(tri, g["vox_cornell_32:tri"]) and np.array_equal(vox.astype(np.int16), g["vox_cornell_32:voxel"])
-    assert np.array_equal(col, g["vox_cornell_32:colour"])
+    assert np.allclose(col, g["vox_cornell_32:colour"], rtol=0, atol=1e-5)
 
 
 MIP_GOLDEN = os.path.join(ROOT, "tests", "golden", "gl_llvmpipe_mip.npz")
@@ -280,7 +280,8 @@ def test_llvmpipe_renders_the_committed_frames(golden):
     for name in ("cornell", "inside", "view_d3_lod2.75"):
         sc, view, proj, R_, W_, H_, prm = case_inputs(name)
         u8, f32 = gl_ref.visualize(sc, view, proj, pyramid(name), W_, H_, prm)
-        assert np.array_equal(u8, golden[name]), name
+        d = channel_diff(u8, golden[name])      # (identical on the machine that rendered them; another CPU's rsqrt / rcp approximations may move a last bit)
+        assert d.max() <= 1 and (d > 0).mean() < 0.01, (name, d.max(), (d > 0).mean())
     # the driver limitation the harness works around: without the six-way select every index samples tex3D[0]
     sc, view, proj, R_, W_, H_, prm = case_inputs("view_d3_lod1.5")
     raw, _ = gl_ref.visualize(sc, view, proj, pyramid("view_d3_lod1.5"), W_, H_, prm, expand_sampler_index=False)
