@@ -216,7 +216,7 @@ class CpuWorkload:
                f"each step cone-traces every {stride}th 32x32 tile; the frame time is EXTRAPOLATED: voxelize + mip + G-buffer + {stride} x the step's trace time")
         what = ("the reference's own GLSL (shader/*.vert|geom|frag|comp rewritten syntactically, compiled against its vendored GLM, oracle/_ref/libvct_glsl_ref.so) "
                 "executed on the CPU behind the oracle's fixed-function rules" if self.ref else "oracle = CPU restatement of the GLSL")
-        return (f"{what} (C++/OpenMP, {self.cores} threads; Mesa llvmpipe is unavailable in this image): "
+        return (f"{what} (C++/OpenMP, {self.cores} threads; no OpenGL 4.5 driver in this image: the reference executable cannot run): "
                 f"voxelize+mip+G-buffer of '{self.cfg['name']}' in full (timed once), {how}")
 
 
