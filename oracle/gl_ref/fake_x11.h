@@ -1,3 +1,6 @@
+// fake_x11.h -- TEST INFRASTRUCTURE.  The handful of Xlib types (public ABI layouts of <X11/Xlib.h> / Xlibint.h / XShm) that Mesa's xlib GLX
+// front end touches when it creates an off-screen context; used by fake_x11.c (the stand-in libX11.so.6) and gl_harness.c.  Nothing here talks to
+// an X server: there is none.
 #pragma once
 #include <stddef.h>
 typedef unsigned long XID, VisualID, Window, Drawable, Colormap, Pixmap, Font;
