@@ -260,6 +260,38 @@ def test_whole_pipeline_on_gl_matches_the_oracle(golden, brilinear):
     assert d.max() <= 4 and (d > 1).mean() <= 0.001 and (d > 0).mean() < 0.08, (d.max(), (d > 1).mean(), (d > 0).mean())
 
 
+EDGE_R, EDGE_W, EDGE_H = 32, 96, 64
+
+
+def edge_inputs(kind):
+    from edge_scenes import edge_scene
+    view, proj = S.reference_camera(EDGE_W / EDGE_H, eye=(0.1, 0.2, 1.6))
+    return edge_scene(kind), view, proj
+
+
+@pytest.mark.parametrize("kind", ["stack", "outside", "degenerate", "lights", "tir", "mirror", "nolight", "empty"])
+def test_corner_case_scenes_on_gl(golden, brilinear, kind):
+    """The corner-case scenes of tests/edge_scenes.py with every pass on llvmpipe (gl_ref.render_frame) against the oracle: the 4-bit count wrap
+    (80 fragments per voxel), degenerate triangles and zero-length normals, twelve lights (the shader clamps to ten), total reflection in
+    refract() -- the NaN cone and its black pixel are what llvmpipe renders too --, mirrored / sheared model matrices, no light, nothing at all:
+    within 1/255.
+    "outside" is the one place where the oracle (and the CUDA path) and this GL part: a fragment outside the cube leaves `final_color`
+    unwritten (voxel_cone_tracing.frag:251-252; undefined in GLSL).  llvmpipe blends a zero there -- the colour drawn EARLIER behind it stays
+    visible while the depth is taken -- whereas the written rule treats the pixel as background when its nearest fragment is such a one.
+    The difference is confined to exactly those pixels."""
+    gl = golden["edge:" + kind]
+    sc, view, proj = edge_inputs(kind)
+    ref = orc.render_frame(sc, view, proj, EDGE_R, EDGE_W, EDGE_H, n_levels=6)
+    d = np.abs(ref["frame"].view(np.uint8).reshape(EDGE_H, EDGE_W, 4).astype(int) - gl.view(np.uint8).reshape(EDGE_H, EDGE_W, 4).astype(int)).max(axis=2)
+    if kind != "outside":
+        assert d.max() <= 1, (kind, d.max())
+        return
+    g = ref["gbuffer"]
+    pos = np.float32(0.5) * (g.world_pos / np.float32(sc.cube_size)) + np.float32(0.5)
+    nearest_outside = (g.tri_id != 0xFFFFFFFF) & ~(np.abs(pos) < 1.0).all(axis=2)          # !within_cube(pos, 0) as the shader tests it: on the biased position (frag:249-250)
+    assert (d[~nearest_outside] <= 1).all() and (d[nearest_outside] > 1).any()
+
+
 def test_brilinear_switch_is_off_by_default():
     """Everything else in the suite (and the CUDA path) uses rule R7: the switch must not leak."""
     sc, view, proj, R_, W_, H_, prm = case_inputs("cornell")

@@ -32,6 +32,9 @@ def main():
         print(name, u8.shape)
     sc, view, proj, R, W, H, prm = T.case_inputs("suzanne")
     out["pipeline_suzanne"] = gl_ref.render_frame(sc, view, proj, R, W, H, prm)["frame"]     # all three passes on the driver
+    for kind in ("stack", "outside", "degenerate", "lights", "tir", "mirror", "nolight", "empty"):     # corner cases, all three passes on the driver
+        sc, view, proj = T.edge_inputs(kind)
+        out["edge:" + kind] = gl_ref.render_frame(sc, view, proj, T.EDGE_R, T.EDGE_W, T.EDGE_H, levels=6)["frame"]
     path = os.path.join(ROOT, "tests", "golden", "gl_llvmpipe_frames.npz")
     np.savez_compressed(path, **out)
     print("->", path, os.path.getsize(path), "bytes")
