@@ -87,6 +87,7 @@ def lib():
         L.orc_gbuffer.argtypes = [C.POINTER(SceneT), f32p, f32p, C.c_int, C.c_int] + [C.c_void_p] * 5
         L.orc_trace.argtypes = [C.POINTER(SceneT), f32p, C.c_int, C.c_int] + [C.c_void_p] * 4 + [C.c_void_p, C.c_int, C.c_int,
                                 C.POINTER(TraceParams), C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(TraceStats)]
+        L.orc_render_forward.argtypes = [C.POINTER(SceneT), f32p, f32p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.POINTER(TraceParams), C.c_void_p]
         L.orc_set_num_threads.argtypes = [C.c_int]
         L.orc_debug_set_lod_filter.argtypes = [C.c_int]
         L.orc_debug_set_unorm_unpack.argtypes = [C.c_int]
@@ -236,3 +237,14 @@ def debug_set_unorm_unpack(mode: int) -> None:
 def debug_set_mip_balanced_sum(on: int) -> None:
     """TEST SWITCH: 1 = the mip filter's four terms added as a balanced tree, as Mesa's GLSL compiler arranges them (tests/test_gl_llvmpipe.py)."""
     lib().orc_debug_set_mip_balanced_sum(int(on))
+
+
+def render_forward(scene, view, proj, p: Pyramid, W: int, H: int, params: TraceParams | None = None):
+    """TEST-ONLY: the visualisation pass as a forward renderer (every fragment that passes the depth test when it is drawn is shaded and
+    blended over what is there) -- what a GL pipeline does; gbuffer() + trace() keep the nearest fragment only."""
+    sr = SceneRef(scene)
+    params = params or default_params()
+    frame = np.zeros((H, W), np.uint32)
+    rc = lib().orc_render_forward(C.byref(sr.c), _fp(view), _fp(proj), W, H, p.ptrs, p.R, p.n_levels, C.byref(params), frame.ctypes.data)
+    assert rc == 0
+    return frame

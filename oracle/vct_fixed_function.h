@@ -312,6 +312,41 @@ class CameraPass {
     }
   }
 
+  /* TEST-ONLY companion of resolve() (tests/test_gl_llvmpipe.py): FORWARD rendering as a GL pipeline does it -- every fragment that passes
+   * the depth test at the moment it is drawn is handed to `on_fragment(px, world, normal, material)`, per pixel in draw order, so that the
+   * caller can shade it and blend it over what earlier fragments left (the voxel debug view's alpha blending, fragments whose shader
+   * writes nothing).  resolve() keeps only the nearest fragment; for frames of alpha 1 the two are the same picture. */
+  template <class F>
+  void forward(F&& on_fragment) const {
+    std::vector<float> depth((size_t)W * H, 1.0f);
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int j = 0; j < H; j++) {
+      for (size_t ti = 0; ti < tris.size(); ti++) {
+        const TriRec& r = tris[ti];
+        if (j < r.rt.jmin || j > r.rt.jmax) continue;
+        for (int i = r.rt.imin; i <= r.rt.imax; i++) {
+          float b[3];
+          if (!raster_sample(r.rt, i, j, b)) continue;
+          float zw = interp(b, r.zw[0], r.zw[1], r.zw[2]);
+          if (!(zw >= 0.0f && zw <= 1.0f)) continue;
+          size_t px = (size_t)j * W + i;
+          if (!(zw < depth[px])) continue;
+          depth[px] = zw;
+          float q[3] = {b[0] * r.iw[0], b[1] * r.iw[1], b[2] * r.iw[2]};
+          float qs = (q[0] + q[1]) + q[2];
+          V3 wp, nn;
+          wp.x = interp(q, r.world[0].x, r.world[1].x, r.world[2].x) / qs;
+          wp.y = interp(q, r.world[0].y, r.world[1].y, r.world[2].y) / qs;
+          wp.z = interp(q, r.world[0].z, r.world[1].z, r.world[2].z) / qs;
+          nn.x = interp(q, r.nrm[0].x, r.nrm[1].x, r.nrm[2].x) / qs;
+          nn.y = interp(q, r.nrm[0].y, r.nrm[1].y, r.nrm[2].y) / qs;
+          nn.z = interp(q, r.nrm[0].z, r.nrm[1].z, r.nrm[2].z) / qs;
+          on_fragment(px, wp, nn, r.material);
+        }
+      }
+    }
+  }
+
  private:
   struct TriRec { RasterTri rt; V3 world[3], nrm[3]; float iw[3], zw[3]; uint32_t material; uint32_t seq; };
   int W, H;

@@ -600,12 +600,9 @@ int orc_mipmap_fmt(const uint32_t* base, int R, int n_levels, uint32_t* const* o
 }
 
 /* ---------------- camera pass (C1) ---------------- */
-int orc_gbuffer(const orc_scene_t* sc, const float view[16], const float proj[16], int W, int H, uint32_t* tri_id,
-                float* depth, float* world_pos, float* normal, uint32_t* material) {
-  if (!sc || !tri_id || !depth) return -1;
+static void feed_camera_pass(CameraPass& pass, const orc_scene_t* sc, const float view[16], const float proj[16]) {
   float pv[16];
   mat4_mul(proj, view, pv); /* projection * view, voxel_cone_tracing.vert:25 */
-  CameraPass pass(W, H);   /* clipping, rasterisation, depth test, interpolation: vct_fixed_function.h */
   uint32_t seq = 0;
   for (uint32_t d = 0; d < sc->n_draws; d++) {
     const orc_draw_t& dr = sc->draws[d];
@@ -623,6 +620,13 @@ int orc_gbuffer(const orc_scene_t* sc, const float view[16], const float proj[16
       pass.add_triangle(in, dr.material, seq);
     }
   }
+}
+
+int orc_gbuffer(const orc_scene_t* sc, const float view[16], const float proj[16], int W, int H, uint32_t* tri_id,
+                float* depth, float* world_pos, float* normal, uint32_t* material) {
+  if (!sc || !tri_id || !depth) return -1;
+  CameraPass pass(W, H);   /* clipping, rasterisation, depth test, interpolation: vct_fixed_function.h */
+  feed_camera_pass(pass, sc, view, proj);
   pass.resolve(tri_id, depth, world_pos, normal, material);
   return 0;
 }
@@ -678,6 +682,34 @@ int orc_trace_fmt(const orc_scene_t* sc, const float view[16], int W, int H, con
     stats->shaded_pixels = n_shaded;
     stats->samples_diffuse = s_d; stats->samples_shadow = s_sh; stats->samples_specular = s_sp; stats->samples_refraction = s_rf;
   }
+  return 0;
+}
+
+/* TEST-ONLY (tests/test_gl_llvmpipe.py): Renderer::visualize as a forward renderer -- every fragment that passes the depth test when it is
+ * drawn is shaded and blended (SRC_ALPHA, ONE_MINUS_SRC_ALPHA, renderer.cpp:387-388) into an RGBA8 colour buffer over what is there; a
+ * fragment whose shader returns without writing (outside the cube) contributes what Mesa llvmpipe makes of the unwritten output, zero.
+ * orc_gbuffer + orc_trace keep one layer per pixel: the same picture whenever alpha is 1 and every nearest fragment writes. */
+int orc_render_forward(const orc_scene_t* sc, const float view[16], const float proj[16], int W, int H, const uint32_t* const* levels, int R,
+                       int n_levels, const orc_trace_params_t* prm, uint32_t* frame) {
+  if (!sc || !levels || !prm || !frame) return -1;
+  ShadeCtx c;
+  c.scene = sc;
+  c.pyr = Pyramid{levels, R, n_levels, 0};
+  c.prm = prm;
+  c.camera_position = v3(view[12], view[13], view[14]);
+  for (size_t i = 0; i < (size_t)W * H; i++) frame[i] = kClearColour;
+  CameraPass pass(W, H);
+  feed_camera_pass(pass, sc, view, proj);
+  pass.forward([&](size_t px, V3 world, V3 nrm, uint32_t material) {
+    SampleCount cnt;
+    float src[4], dst[4];
+    if (!shade(c, sc->mats[material], world, nrm, src, cnt)) src[0] = src[1] = src[2] = src[3] = 0.0f;
+    for (int k = 0; k < 4; k++) src[k] = clamp01(src[k]);   /* a fixed-point colour buffer clamps the fragment colour before blending */
+    unpack_unorm(frame[px], dst);
+    const float a = src[3];
+    for (int k = 0; k < 4; k++) dst[k] = src[k] * a + dst[k] * (1.0f - a);
+    frame[px] = pack_unorm(dst);
+  });
   return 0;
 }
 

@@ -128,6 +128,9 @@ int orc_trace(const orc_scene_t* scene, const float view[16], int W, int H,
               uint32_t* frame, orc_trace_stats_t* stats);
 
 int orc_num_threads(void);
+/* TEST-ONLY: Renderer::visualize as a forward renderer (every depth-passing fragment shaded and blended in draw order); see vct_oracle.cpp */
+int orc_render_forward(const orc_scene_t* scene, const float view[16], const float proj[16], int W, int H, const uint32_t* const* levels, int R,
+                       int n_levels, const orc_trace_params_t* params, uint32_t* frame);
 void orc_set_num_threads(int n);
 /* TEST SWITCH: 0 = rule R7 (default), 1 = Mesa llvmpipe's brilinear mip filter (vct_fixed_function.h lod_filter_mode); used only by
  * tests/test_gl_llvmpipe.py to compare the oracle with the reference's shaders running on that driver. */

@@ -292,6 +292,39 @@ def test_corner_case_scenes_on_gl(golden, brilinear, kind):
     assert (d[~nearest_outside] <= 1).all() and (d[nearest_outside] > 1).any()
 
 
+@pytest.mark.parametrize("name", ["cornell", "suzanne", "inside", "cornell_direct"])
+def test_one_layer_per_pixel_is_exact_for_shaded_frames(brilinear, name):
+    """The product (and orc.gbuffer + orc.trace) keeps the NEAREST fragment of a pixel and shades it once; GL shades every fragment that passes
+    the depth test when it is drawn and blends it over what is there.  With alpha = 1 (voxel_cone_tracing.frag:272-274) the last one wins:
+    the forward renderer (orc.render_forward, test-only) produces the same frame bit for bit."""
+    sc, view, proj, R_, W_, H_, prm = case_inputs(name)
+    one, _ = oracle_frame(name)
+    assert np.array_equal(orc.render_forward(sc, view, proj, pyramid(name), W_, H_, prm), one)
+
+
+@pytest.mark.parametrize("name", ["view_d0_lod0", "view_d3_lod1.5", "view_d5_lod4", "view_d0_lod0.25", "view_d3_lod2.75"])
+def test_debug_view_blends_over_the_layers_behind_like_gl(golden, brilinear, name):
+    """The voxel debug view has alpha < 1: GL blends the nearest surface over what was drawn behind it BEFORE it (2.7 % of the pixels here have
+    such a layer).  The forward renderer reproduces llvmpipe's frame on every pixel; the one-layer frame of the product differs there (the
+    reference's debug view is order dependent by construction)."""
+    sc, view, proj, R_, W_, H_, prm = case_inputs(name)
+    d = channel_diff(orc.render_forward(sc, view, proj, pyramid(name), W_, H_, prm), golden[name])
+    assert d.max() <= 2 and (d > 1).mean() < 0.001, (d.max(), (d > 1).mean())
+    one, _ = oracle_frame(name)
+    assert (channel_diff(one, golden[name]) > 2).mean() > 0.005
+
+
+def test_unwritten_fragments_outside_the_cube_like_gl(golden, brilinear):
+    """test_corner_case_scenes_on_gl[outside] continued: with every depth-passing fragment blended in draw order and an unwritten output taken
+    as zero (what llvmpipe makes of it), the oracle reproduces llvmpipe's frame of that scene on every pixel."""
+    sc, view, proj = edge_inputs("outside")
+    pyr = orc.render_frame(sc, view, proj, EDGE_R, EDGE_W, EDGE_H, n_levels=6)["pyramid"]
+    fwd = orc.render_forward(sc, view, proj, pyr, EDGE_W, EDGE_H)
+    gl = golden["edge:outside"]
+    d = np.abs(fwd.view(np.uint8).reshape(EDGE_H, EDGE_W, 4).astype(int) - gl.view(np.uint8).reshape(EDGE_H, EDGE_W, 4).astype(int)).max(axis=2)
+    assert d.max() <= 1
+
+
 def test_brilinear_switch_is_off_by_default():
     """Everything else in the suite (and the CUDA path) uses rule R7: the switch must not leak."""
     sc, view, proj, R_, W_, H_, prm = case_inputs("cornell")
