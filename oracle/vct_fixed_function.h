@@ -118,16 +118,16 @@ inline uint64_t pack_half4(const float v[4]) {
   return r;
 }
 
-/* TEST SWITCH (tests/test_gl_llvmpipe.py only; 0 everywhere else): 1 = unorm8 -> float as Mesa llvmpipe converts a texel, c * (1.0f / 255.0f)
- * -- one rounding more than the specification's c / 255 (rule R6), up to one ulp off, which moves results of the mip filter that sit exactly
- * on a rounding tie (a quarter of a sum of 8-bit values often does). */
-inline int& unorm_unpack_mode() { static int mode = 0; return mode; }
+/* TEST SWITCH (tests/test_gl_llvmpipe.py only; 0 everywhere else; read by the oracle's mip filter alone): 1 = unorm8 -> float as Mesa llvmpipe
+ * converts a texel, c * (1.0f / 255.0f) -- one rounding more than the specification's c / 255 (rule R6), up to one ulp off, which moves results
+ * of the mip filter that sit exactly on a rounding tie (a quarter of a sum of 8-bit values often does). */
+inline int g_unorm_unpack_mode = 0;   /* C++17 inline variable: one per shared library */
+inline int& unorm_unpack_mode() { return g_unorm_unpack_mode; }
+inline void unpack_unorm_reciprocal(uint32_t c, float out[4]) {
+  const float r = 1.0f / 255.0f;
+  for (int k = 0; k < 4; k++) out[k] = (float)((c >> (8 * k)) & 0xFFu) * r;
+}
 inline void unpack_unorm(uint32_t c, float out[4]) {
-  if (unorm_unpack_mode() == 1) {
-    const float r = 1.0f / 255.0f;
-    for (int k = 0; k < 4; k++) out[k] = (float)((c >> (8 * k)) & 0xFFu) * r;
-    return;
-  }
   out[0] = (float)(c & 0xFFu) / 255.0f;
   out[1] = (float)((c >> 8) & 0xFFu) / 255.0f;
   out[2] = (float)((c >> 16) & 0xFFu) / 255.0f;
@@ -179,7 +179,8 @@ inline void load_texel(const uint32_t* tex, size_t idx, int fmt, float c[4]) {
  * the coarser level is 2 phi - 1, and a weight <= 0 means the finer level alone -- i.e. one level for fractions below 0.25 and above 0.75, a
  * ramp of twice the slope between.  With the switch on, the oracle can be compared with the reference's shaders RUNNING on llvmpipe without
  * the driver's shortcut drowning everything else. */
-inline int& lod_filter_mode() { static int mode = 0; return mode; }
+inline int g_lod_filter_mode = 0;
+inline int& lod_filter_mode() { return g_lod_filter_mode; }
 
 inline void texture_lod(const Pyramid& p, int dir, V3 s, float lod, float out[4]) {
   float maxl = (float)(p.n_levels - 1);

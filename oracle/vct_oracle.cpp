@@ -576,7 +576,8 @@ int orc_mipmap_fmt(const uint32_t* base, int R, int n_levels, uint32_t* const* o
             float c[8][4];
             for (int i = 0; i < 8; i++) {
               int sx = 2 * x + off[i][0], sy = 2 * y + off[i][1], sz = 2 * z + off[i][2];
-              load_texel(src, ((size_t)sz * Ns + sy) * Ns + sx, fmt, c[i]);
+              if (fmt == 0 && unorm_unpack_mode() == 1) unpack_unorm_reciprocal(src[((size_t)sz * Ns + sy) * Ns + sx], c[i]); /* TEST SWITCH */
+              else load_texel(src, ((size_t)sz * Ns + sy) * Ns + sx, fmt, c[i]);
             }
             float acc[4];
             for (int k = 0; k < 4; k++) {
