@@ -1,14 +1,20 @@
 """The reference's visualisation pass on a real OpenGL implementation (TEST INFRASTRUCTURE ONLY).
 
-oracle/_ref/gl/vct_gl_ref (oracle/gl_ref/gl_harness.c) compiles the reference's UNMODIFIED shader/voxel_cone_tracing.vert|frag
-with Mesa 18.1 llvmpipe -- the software GL that ships inside Nsight Compute, loaded behind a stand-in libX11 -- and replays
-Renderer::visualize (src/renderer.cpp:355-390) with the GL state of the reference.  llvmpipe 18.1 cannot run the voxelization
-and mip passes (no image load/store, no compute), so the six voxel textures are filled with a given grid + mip chain.
+oracle/_ref/gl/vct_gl_ref (oracle/gl_ref/gl_harness.c) drives Mesa 18.1 llvmpipe -- the software GL that ships inside Nsight Compute,
+loaded behind a stand-in libX11 -- through the reference's three passes with the reference's shader text, read from the reference tree
+at run time and changed only where this GL 3.3 driver cannot run it (each change syntactic and asserted, see the three
+*_shader_dir_for_driver functions):
+  visualize()           Renderer::visualize (src/renderer.cpp:355-390): voxel_cone_tracing.vert unmodified, .frag with its dynamic
+                        sampler-array index expanded to a six-way select; voxel textures from a given grid + mip chain
+  voxelize_fragments()  Renderer::voxelize (:316-353): voxelize.vert / .geom unmodified, .frag up to the image store (no image
+                        load/store in the driver: voxel coordinate and colour of every fragment go to two render targets)
+  mip_chain()           Renderer::filter (:283-314): mipmap.comp as a fragment shader (no compute shaders in the driver)
+  render_frame()        the three chained
 
-What this pins: the fixed-function half the CPU restatements only write down as rules -- where a triangle's fragments fall,
-clipping, perspective-correct interpolation, the depth test, textureLod's filtering, blending and the unorm conversion -- plus
-the fragment shader as a GL compiler executes it, for the visualisation pass.  PARITY of the voxelization pass's raster /
-fragment order stays unpinned.
+What this pins: the fixed-function half the CPU restatements only write down as rules -- where a triangle's fragments fall in both
+rasterising passes, clipping, perspective-correct interpolation, the depth test, textureLod's filtering, blending, the unorm
+conversions -- plus the shaders as a GLSL compiler executes them.  What it cannot show: the ORDER in which fragments reach the
+running average (no image atomics in this driver; GL defines none): that stays a written rule (R4).
 
     frame_u8, frame_f32 = gl_ref.visualize(scene, view, proj, pyramid, W, H, params)
 """

@@ -5,7 +5,7 @@ rasterisers, and the grouped-diffuse cone path at 8K.
 
 Bars as in test_gpu_parity.py: voxels, all 36 mip volumes, visibility and G-buffer attributes BIT-EXACT against the oracle; the
 frame within 2/255 and 45 dB, compared on the 32x32 screen tiles the oracle traces (`orc.trace(stride, phase)`; tracing an 8K
-frame in full on the host would take minutes).  Oracle = CPU restatement (shader arithmetic pinned to the reference's GLSL, fixed-function GL rules unpinned: DESIGN.md section 0)."""
+frame in full on the host would take minutes).  Oracle = CPU restatement (shader arithmetic pinned to the reference's GLSL, fixed-function rules held against Mesa llvmpipe: DESIGN.md section 0)."""
 import numpy as np
 import pytest
 
