@@ -183,6 +183,45 @@ def test_voxelization_fragments_match_gl(name):
     assert d.max() <= 2 and (d > 0).sum() <= 0.01 * st.occupied, (d.max(), (d > 0).sum(), st.occupied)
 
 
+def raster_soup(n_tri=600, seed=7):
+    """Random triangles of all sizes (a hundredth of the cube to the whole cube), all inside the cube (nothing for a clipper to do), every
+    orientation: the geometry shader picks each of the three projection axes."""
+    rng = np.random.default_rng(seed)
+    b = S.SceneBuilder(1.0)
+    centre = (rng.random((n_tri, 1, 3)) - 0.5) * 1.6
+    size = rng.choice([0.02, 0.1, 0.4, 1.1], (n_tri, 1, 1))
+    pos = np.clip(centre + (rng.random((n_tri, 3, 3)) - 0.5) * size, -0.97, 0.97).reshape(-1, 3)
+    v = np.zeros(3 * n_tri, S.VERTEX)
+    v["pos"] = pos.astype(np.float32); v["norm"] = (0.0, 0.0, 1.0)
+    b.add_mesh(S.Mesh(v, np.arange(3 * n_tri, dtype="<u4"), [(0, 3 * n_tri, -1)], np.zeros(0, S.MATERIAL)), material_override=0)
+    b.add_light((0.0, 0.0, 0.5))
+    return b.build()
+
+
+def test_rasteriser_per_triangle_vs_gl():
+    """Rule R2 triangle by triangle: 600 random triangles at 2R x 2R (R = 32), each drawn on its own on llvmpipe; the oracle voxelizes each one
+    as a scene of its own -- the number of fragments is the same for EVERY triangle (not only in total), and so are the voxels they land in (but for a fragment within an
+    ulp of a voxel face in 3 of the 600)."""
+    g = np.load(VOXEL_GOLDEN)
+    tri, vox = g["raster_soup:tri"], g["raster_soup:voxel"].astype(np.int64)
+    sc = raster_soup()
+    per_tri = np.bincount(tri, minlength=sc.n_triangles)
+    assert per_tri.sum() > 20000 and (per_tri == 0).sum() > 20 and per_tri.max() > 300      # sub-pixel triangles that emit nothing .. a tenth of the viewport
+    bad = []
+    d = sc.draws[0]
+    for t in range(sc.n_triangles):
+        dd = sc.draws[0:1].copy()
+        dd["first_index"] = d["first_index"] + 3 * t; dd["index_count"] = 3
+        base, st = orc.voxelize(S.Scene(sc.verts, sc.indices, dd, sc.materials, sc.lights, sc.cube_size), 32)
+        mine = np.zeros((32, 32, 32), bool)
+        for x, y, z in vox[tri == t]:
+            mine[z, y, x] = True
+        assert st.fragments + st.fragments_oob == per_tri[t], (t, int(per_tri[t]), int(st.fragments))      # coverage: exact, every triangle
+        if not np.array_equal(mine, base != 0):
+            bad.append(t)
+    assert len(bad) <= 6, bad      # 1 %: a fragment whose interpolated position is within an ulp of a voxel face may land next door
+
+
 def test_llvmpipe_rasterises_the_committed_fragments():
     if not gl_ref.available():
         pytest.skip("needs oracle/_ref/gl/vct_gl_ref, Nsight Compute's Mesa libGL and /root/reference/shader")

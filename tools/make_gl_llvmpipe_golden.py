@@ -45,6 +45,9 @@ def main():
         assert np.array_equal(voxel, np.floor(voxel)) and voxel.min() >= 0 and voxel.max() < res
         vox[name + ":tri"], vox[name + ":xy"], vox[name + ":voxel"], vox[name + ":colour"] = tri, xy.astype(np.uint16), voxel.astype(np.int16), col
         print(name, len(tri), "fragments")
+    tri, xy, voxel, col = gl_ref.voxelize_fragments(T.raster_soup(), 32)      # per-triangle raster check
+    vox["raster_soup:tri"], vox["raster_soup:voxel"] = tri, voxel.astype(np.int16)
+    print("raster_soup", len(tri), "fragments")
     np.savez_compressed(T.VOXEL_GOLDEN, **vox)
     print("->", T.VOXEL_GOLDEN, os.path.getsize(T.VOXEL_GOLDEN), "bytes")
     mip = {}
